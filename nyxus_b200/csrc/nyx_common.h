@@ -1,0 +1,398 @@
+// nyxus_b200 -- shared scalar numerics and the per-CTA execution context used by every per-ROI feature body.
+//
+// The feature bodies (glcm_body.h, glrlm_body.h, ...) are written against the small `Cta` interface below:
+// strided loops over work items (`for (i = c.tid; i < n; i += c.nthr)`), `c.sync()`, block reductions and
+// integer shared-memory atomics.  On the device a CTA of 128-256 threads runs them; tests/emu compiles the very
+// same bodies for the host with nthr == 1 so their indexing/arithmetic can be checked against the oracle on a
+// machine without a GPU (test harness only; the product library contains only the CUDA instantiation).
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(__CUDACC__) && !defined(NYX_HOST_EMU)
+#define NYX_DEVICE_BUILD 1
+#define NYX_HD __host__ __device__ __forceinline__
+#define NYX_D __device__ __forceinline__
+#else
+#define NYX_DEVICE_BUILD 0
+#define NYX_HD inline
+#define NYX_D inline
+#endif
+
+namespace nyx
+{
+
+// ------------------------------------------------------------------------------------------------
+// Exactly-rounded, never-contracted FP ops.  The reference is built for generic x86-64 at -O2 (no FMA),
+// so every bit-exact path (binning, fast_log10, histogram bin indices) must avoid FMA contraction.
+// ------------------------------------------------------------------------------------------------
+NYX_HD double dmul (double a, double b)
+{
+#ifdef __CUDA_ARCH__
+	return __dmul_rn (a, b);
+#else
+	return a * b;
+#endif
+}
+NYX_HD double dadd (double a, double b)
+{
+#ifdef __CUDA_ARCH__
+	return __dadd_rn (a, b);
+#else
+	return a + b;
+#endif
+}
+NYX_HD double ddiv (double a, double b)
+{
+#ifdef __CUDA_ARCH__
+	return __ddiv_rn (a, b);
+#else
+	return a / b;
+#endif
+}
+NYX_HD float fmul (float a, float b)
+{
+#ifdef __CUDA_ARCH__
+	return __fmul_rn (a, b);
+#else
+	return a * b;
+#endif
+}
+NYX_HD float fadd (float a, float b)
+{
+#ifdef __CUDA_ARCH__
+	return __fadd_rn (a, b);
+#else
+	return a + b;
+#endif
+}
+NYX_HD uint32_t f2u (float f)
+{
+#ifdef __CUDA_ARCH__
+	return __float_as_uint (f);
+#else
+	uint32_t u;
+	memcpy (&u, &f, 4);
+	return u;
+#endif
+}
+NYX_HD float u2f (uint32_t u)
+{
+#ifdef __CUDA_ARCH__
+	return __uint_as_float (u);
+#else
+	float f;
+	memcpy (&f, &u, 4);
+	return f;
+#endif
+}
+
+constexpr double LOG10_2 = 0.30102999566;	// reference glcm.h:241, glrlm.h:171, glszm.h:140, gldm.h:106
+constexpr double GLCM_EPSILON = 0.000000001;	// reference glcm.h:249
+constexpr double EPS_ZONES = 2.2e-16;		// reference glrlm.h:169, glszm.h:138, gldm.h:105, gldzm.h:68
+
+// The reference's fast_log10() (helpers/helpers.h:283-330): a float32 quadratic approximation of log2(x)
+// scaled by log10(2).  Restated: split exponent / mantissa, reduce the significand to [0.75,1.5),
+// evaluate  fexp + a*s*s + b*s  left to right in float32, widen, scale.  Must be bit-identical.
+NYX_HD double fast_log10 (double xd)
+{
+	const float a = -.6296735f, b = 1.466967f;
+	float x = (float)xd;
+	uint32_t bits = f2u (x);
+	int e = (int)((bits & 0x7F800000u) >> 23);
+	bool upper = (bits & 0x00400000u) != 0;		// significand >= 1.5 -> halve it
+	float s = u2f ((bits & 0x007FFFFFu) | (upper ? 0x3f000000u : 0x3f800000u));
+	float fexp = (float)(upper ? e - 126 : e - 127);
+	s = fadd (s, -1.0f);
+	float lg2 = fadd (fadd (fexp, fmul (fmul (a, s), s)), fmul (b, s));
+	return dmul ((double)lg2, 0.30102999566);
+}
+
+// x * fast_log10(x + eps) / LOG10_2  -- the entropy term every family uses
+NYX_HD double plogp (double p, double eps)
+{
+	return ddiv (dmul (p, fast_log10 (dadd (p, eps))), LOG10_2);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Grey-level binning (reference features/texture_feature.h:23-50,138-167; helpers/helpers.h:337-345)
+// ------------------------------------------------------------------------------------------------
+struct Binner
+{
+	int greyinfo;		// >0 MATLAB levels, 0 IBSI identity (negative = PyRadiomics, not reachable from the Python API)
+	double slope;		// MATLAB: g / max
+	uint32_t n;
+
+	NYX_HD void init (int greyinfo_, uint32_t /*imin*/, uint32_t imax)
+	{
+		greyinfo = greyinfo_;
+		n = (uint32_t)(greyinfo_ > 0 ? greyinfo_ : 0);
+		slope = greyinfo_ > 0 ? ddiv ((double)greyinfo_, (double)imax) : 0.0;
+	}
+	NYX_HD uint32_t bin (uint32_t i) const
+	{
+		if (greyinfo == 0)
+			return i;
+		if (i == 0)
+			return 1;
+		double r = floor (dadd (dmul (slope, (double)i), 1.0));
+		uint32_t s = (uint32_t)r;
+		if (s > n) s = n;
+		if (s < 1) s = 1;
+		return s;
+	}
+};
+
+// Nyxus::to_grayscale (helpers.h:337-345): (uint)(double(i-min)/double(range)*double(n)); NaN (range==0) -> 0 like x86-64 gcc
+NYX_HD uint32_t to_grayscale (uint32_t i, uint32_t mn, uint32_t range, uint32_t n, bool disable)
+{
+	if (disable)
+		return i;
+	double pi = dmul (ddiv ((double)(uint32_t)(i - mn), (double)range), (double)n);
+	if (!(pi == pi))
+		return 0;
+	if (pi >= 4294967296.0)
+		return 0;
+	return (uint32_t)pi;
+}
+
+NYX_HD double finite_or (double v, double sub)
+{
+	return (isnan (v) || isinf (v)) ? sub : v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Device-side records
+// ------------------------------------------------------------------------------------------------
+struct RoiRec
+{
+	uint32_t label;
+	uint32_t area;
+	uint32_t imin, imax;
+	int32_t x0, y0, w, h;	// AABB origin and extent (w = xmax-xmin+1)
+	uint64_t cloud_off;	// offset of this ROI's pixels in the CSR cloud
+	int32_t z0, d;		// 3D only
+};
+
+struct ImageView
+{
+	const void* inten;	// uint32 or uint16 pixels, row-major
+	const uint32_t* label;
+	int32_t H, W;
+	int32_t inten_u16;
+};
+
+struct Params
+{
+	int32_t greydepth;	// coarse_gray_depth (>0)
+	int32_t ibsi;
+	int32_t glcm_offset;
+	int32_t glcm_symmetric;
+	double softnan;
+};
+
+NYX_HD uint32_t load_inten (const ImageView& im, size_t idx)
+{
+	return im.inten_u16 ? (uint32_t)((const uint16_t*)im.inten)[idx] : ((const uint32_t*)im.inten)[idx];
+}
+
+// tile cell code: level in the low 24 bits + flags
+constexpr uint32_t CELL_NZ = 0x80000000u;	// original intensity != 0 (and pixel belongs to the ROI)
+constexpr uint32_t CELL_IN = 0x40000000u;	// pixel belongs to the ROI (may have intensity 0)
+constexpr uint32_t CELL_LEVEL = 0x00FFFFFFu;
+
+// ------------------------------------------------------------------------------------------------
+// CTA context
+// ------------------------------------------------------------------------------------------------
+struct Cta
+{
+	int tid, nthr;
+	double* red;	// reduction scratch: RED_MAX * NW_MAX doubles
+
+#if NYX_DEVICE_BUILD
+	NYX_D void sync() const { __syncthreads(); }
+#else
+	inline void sync() const {}
+#endif
+};
+
+constexpr int RED_MAX = 48;
+constexpr int NW_MAX = 8;	// CTAs have at most 256 threads
+constexpr int RED_WORDS = RED_MAX * NW_MAX * 2;	// 32-bit words of reduction scratch
+
+NYX_D void atom_add (const Cta&, uint32_t* p, uint32_t v)
+{
+#if NYX_DEVICE_BUILD
+	atomicAdd (p, v);
+#else
+	*p += v;
+#endif
+}
+NYX_D void atom_max (const Cta&, uint32_t* p, uint32_t v)
+{
+#if NYX_DEVICE_BUILD
+	atomicMax (p, v);
+#else
+	if (v > *p) *p = v;
+#endif
+}
+NYX_D void atom_min (const Cta&, uint32_t* p, uint32_t v)
+{
+#if NYX_DEVICE_BUILD
+	atomicMin (p, v);
+#else
+	if (v < *p) *p = v;
+#endif
+}
+NYX_D void atom_add64 (const Cta&, unsigned long long* p, unsigned long long v)
+{
+#if NYX_DEVICE_BUILD
+	atomicAdd (p, v);
+#else
+	*p += v;
+#endif
+}
+
+// Block-wide sum of N doubles; the result is broadcast into v[] of every thread.  Fixed tree => deterministic.
+template <int N> NYX_D void cta_sum (const Cta& c, double (&v)[N])
+{
+#if NYX_DEVICE_BUILD
+	static_assert (N <= RED_MAX, "too many values");
+	const int lane = c.tid & 31, warp = c.tid >> 5, nw = (c.nthr + 31) >> 5;
+#pragma unroll
+	for (int k = 0; k < N; k++)
+	{
+		double x = v[k];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+			x += __shfl_xor_sync (0xffffffffu, x, o);
+		if (lane == 0)
+			c.red[k * NW_MAX + warp] = x;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < N; k++)
+	{
+		double x = 0;
+		for (int w = 0; w < nw; w++)
+			x += c.red[k * NW_MAX + w];
+		v[k] = x;
+	}
+	__syncthreads();
+#else
+	(void)c; (void)v;
+#endif
+}
+
+template <int N> NYX_D void cta_sum_u64 (const Cta& c, unsigned long long (&v)[N])
+{
+#if NYX_DEVICE_BUILD
+	static_assert (N <= RED_MAX, "too many values");
+	const int lane = c.tid & 31, warp = c.tid >> 5, nw = (c.nthr + 31) >> 5;
+	unsigned long long* red = (unsigned long long*)c.red;
+#pragma unroll
+	for (int k = 0; k < N; k++)
+	{
+		unsigned long long x = v[k];
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1)
+			x += __shfl_xor_sync (0xffffffffu, x, o);
+		if (lane == 0)
+			red[k * NW_MAX + warp] = x;
+	}
+	__syncthreads();
+#pragma unroll
+	for (int k = 0; k < N; k++)
+	{
+		unsigned long long x = 0;
+		for (int w = 0; w < nw; w++)
+			x += red[k * NW_MAX + w];
+		v[k] = x;
+	}
+	__syncthreads();
+#else
+	(void)c; (void)v;
+#endif
+}
+
+NYX_D unsigned long long cta_max_u64 (const Cta& c, unsigned long long x)
+{
+#if NYX_DEVICE_BUILD
+	const int lane = c.tid & 31, warp = c.tid >> 5, nw = (c.nthr + 31) >> 5;
+	unsigned long long* red = (unsigned long long*)c.red;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		unsigned long long y = __shfl_xor_sync (0xffffffffu, x, o);
+		x = y > x ? y : x;
+	}
+	if (lane == 0)
+		red[warp] = x;
+	__syncthreads();
+	x = 0;
+	for (int w = 0; w < nw; w++)
+		x = red[w] > x ? red[w] : x;
+	__syncthreads();
+	return x;
+#else
+	(void)c;
+	return x;
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------
+// In-shared-memory bitonic sort of npad (power of two) keys, ascending
+// ------------------------------------------------------------------------------------------------
+NYX_HD uint32_t next_pow2 (uint32_t n)
+{
+	uint32_t p = 1;
+	while (p < n) p <<= 1;
+	return p;
+}
+
+NYX_D void bitonic_sort (const Cta& c, uint32_t* a, uint32_t npad)
+{
+	for (uint32_t k = 2; k <= npad; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1)
+		{
+			for (uint32_t i = c.tid; i < npad; i += c.nthr)
+			{
+				uint32_t ixj = i ^ j;
+				if (ixj > i)
+				{
+					uint32_t x = a[i], y = a[ixj];
+					bool up = (i & k) == 0;
+					if ((x > y) == up)
+					{
+						a[i] = y;
+						a[ixj] = x;
+					}
+				}
+			}
+			c.sync();
+		}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Tile materialisation: the ROI's AABB read straight from the resident slide (reference:
+// ImageMatrix::calculate_from_pixelcloud, image_matrix.h:284-304 -- 0 outside the ROI).
+// cell[i] = binned level | CELL_NZ (orig != 0) | CELL_IN (label match)
+// ------------------------------------------------------------------------------------------------
+NYX_D void load_tile (const Cta& c, const ImageView& im, const RoiRec& r, const Binner& B, uint32_t* cell)
+{
+	const int n = r.w * r.h;
+	for (int i = c.tid; i < n; i += c.nthr)
+	{
+		int y = i / r.w, x = i - y * r.w;
+		size_t g = (size_t)(r.y0 + y) * im.W + (size_t)(r.x0 + x);
+		bool in = im.label[g] == r.label;
+		uint32_t v = in ? load_inten (im, g) : 0u;
+		uint32_t code = B.bin (v) & CELL_LEVEL;
+		if (v) code |= CELL_NZ;
+		if (in) code |= CELL_IN;
+		cell[i] = code;
+	}
+}
+
+} // namespace nyx

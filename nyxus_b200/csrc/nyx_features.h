@@ -1,0 +1,99 @@
+// nyxus_b200 -- canonical column layout of the texture + intensity path.
+//
+// The order is the reference's output contract: feature codes ascending in the Feature2D enum
+// (reference featureset.h:10-350), GLCM / GLRLM non-_AVE codes expanded into 4 angle columns
+// (reference output_2_buffer.cpp:331-358, 470-520).  337 columns in total.
+#pragma once
+
+namespace nyx
+{
+
+enum Family : int
+{
+	FAM_INT = 0, FAM_GLCM, FAM_GLRLM, FAM_GLDZM, FAM_GLSZM, FAM_GLDM, FAM_NGLDM, FAM_NGTDM, FAM_COUNT
+};
+
+// number of canonical columns per family and their base offsets
+constexpr int NCOL_INT = 36;
+constexpr int NCOL_GLCM = 30 * 4 + 29;
+constexpr int NCOL_GLRLM = 16 * 4 + 16;
+constexpr int NCOL_GLDZM = 18;
+constexpr int NCOL_GLSZM = 16;
+constexpr int NCOL_GLDM = 14;
+constexpr int NCOL_NGLDM = 19;
+constexpr int NCOL_NGTDM = 5;
+
+constexpr int COL_INT = 0;
+constexpr int COL_GLCM = COL_INT + NCOL_INT;
+constexpr int COL_GLRLM = COL_GLCM + NCOL_GLCM;
+constexpr int COL_GLDZM = COL_GLRLM + NCOL_GLRLM;
+constexpr int COL_GLSZM = COL_GLDZM + NCOL_GLDZM;
+constexpr int COL_GLDM = COL_GLSZM + NCOL_GLSZM;
+constexpr int COL_NGLDM = COL_GLDM + NCOL_GLDM;
+constexpr int COL_NGTDM = COL_NGLDM + NCOL_NGLDM;
+constexpr int NCOL_ALL = COL_NGTDM + NCOL_NGTDM;	// 337
+
+// ---- first-order (Feature2D::COV .. UNIFORMITY_PIU, featureset.h:13-48)
+enum IntCol : int
+{
+	I_COV = 0, I_COVERED_IMAGE_INTENSITY_RANGE, I_ENERGY, I_ENTROPY, I_EXCESS_KURTOSIS, I_HYPERFLATNESS, I_HYPERSKEWNESS,
+	I_INTEGRATED_INTENSITY, I_INTERQUARTILE_RANGE, I_KURTOSIS, I_MAX, I_MEAN, I_MEAN_ABSOLUTE_DEVIATION, I_MEDIAN,
+	I_MEDIAN_ABSOLUTE_DEVIATION, I_MIN, I_MODE, I_P01, I_P10, I_P25, I_P75, I_P90, I_P99, I_QCOD, I_RANGE, I_ROBUST_MEAN,
+	I_ROBUST_MEAN_ABSOLUTE_DEVIATION, I_ROOT_MEAN_SQUARED, I_SKEWNESS, I_STANDARD_DEVIATION, I_STANDARD_DEVIATION_BIASED,
+	I_STANDARD_ERROR, I_VARIANCE, I_VARIANCE_BIASED, I_UNIFORMITY, I_UNIFORMITY_PIU
+};
+
+// ---- GLCM angled features in enum order (featureset.h:174-203); column = COL_GLCM + 4*f + angle
+enum GlcmF : int
+{
+	G_ASM = 0, G_ACOR, G_CLUPROM, G_CLUSHADE, G_CLUTEND, G_CONTRAST, G_CORRELATION, G_DIFAVE, G_DIFENTRO, G_DIFVAR, G_DIS,
+	G_ENERGY, G_ENTROPY, G_HOM1, G_HOM2, G_ID, G_IDN, G_IDM, G_IDMN, G_INFOMEAS1, G_INFOMEAS2, G_IV, G_JAVE, G_JE, G_JMAX,
+	G_JVAR, G_SUMAVERAGE, G_SUMENTROPY, G_SUMVARIANCE, G_VARIANCE, G_NANGLED
+};
+// the 29 _AVE columns follow in THEIR enum order (featureset.h:205-233); entry = the angled feature averaged
+#define NYX_GLCM_AVE_ORDER { G_ASM, G_ACOR, G_CLUPROM, G_CLUSHADE, G_CLUTEND, G_CONTRAST, G_CORRELATION, G_DIFAVE, G_DIFENTRO, \
+	G_DIFVAR, G_DIS, G_ENERGY, G_ENTROPY, G_HOM1, G_ID, G_IDN, G_IDM, G_IDMN, G_IV, G_JAVE, G_JE, G_INFOMEAS1, G_INFOMEAS2, \
+	G_VARIANCE, G_JMAX, G_JVAR, G_SUMAVERAGE, G_SUMENTROPY, G_SUMVARIANCE }
+constexpr int G_NAVE = 29;
+
+// ---- GLRLM (featureset.h:236-268): 16 angled (column = COL_GLRLM + 4*f + angle) then 16 _AVE in the same order
+enum GlrlmF : int
+{
+	R_SRE = 0, R_LRE, R_GLN, R_GLNN, R_RLN, R_RLNN, R_RP, R_GLV, R_RV, R_RE, R_LGLRE, R_HGLRE, R_SRLGLE, R_SRHGLE, R_LRLGLE,
+	R_LRHGLE, R_NANGLED
+};
+
+// ---- GLDZM (featureset.h:271-288)
+enum GldzmF : int
+{
+	Z_SDE = 0, Z_LDE, Z_LGLZE, Z_HGLZE, Z_SDLGLE, Z_SDHGLE, Z_LDLGLE, Z_LDHGLE, Z_GLNU, Z_GLNUN, Z_ZDNU, Z_ZDNUN, Z_ZP, Z_GLM,
+	Z_GLV, Z_ZDM, Z_ZDV, Z_ZDE
+};
+
+// ---- GLSZM (featureset.h:291-306)
+enum GlszmF : int
+{
+	S_SAE = 0, S_LAE, S_GLN, S_GLNN, S_SZN, S_SZNN, S_ZP, S_GLV, S_ZV, S_ZE, S_LGLZE, S_HGLZE, S_SALGLE, S_SAHGLE, S_LALGLE,
+	S_LAHGLE
+};
+
+// ---- GLDM (featureset.h:309-322)
+enum GldmF : int
+{
+	D_SDE = 0, D_LDE, D_GLN, D_DN, D_DNN, D_GLV, D_DV, D_DE, D_LGLE, D_HGLE, D_SDLGLE, D_SDHGLE, D_LDLGLE, D_LDHGLE
+};
+
+// ---- NGLDM (featureset.h:325-343)
+enum NgldmF : int
+{
+	N_LDE = 0, N_HDE, N_LGLCE, N_HGLCE, N_LDLGLE, N_LDHGLE, N_HDLGLE, N_HDHGLE, N_GLNU, N_GLNUN, N_DCNU, N_DCNUN, N_DCP,
+	N_GLM, N_GLV, N_DCM, N_DCV, N_DCENT, N_DCENE
+};
+
+// ---- NGTDM (featureset.h:346-350)
+enum NgtdmF : int
+{
+	T_COARSENESS = 0, T_CONTRAST, T_BUSYNESS, T_COMPLEXITY, T_STRENGTH
+};
+
+} // namespace nyx

@@ -1,0 +1,122 @@
+// TEST HARNESS ONLY (never part of the product library): compiles the per-ROI feature bodies of
+// nyxus_b200/csrc/*_body.h for the HOST with a single-thread CTA context (NYX_HOST_EMU), so their
+// indexing and arithmetic can be checked against the oracle on a machine without a GPU.
+// The CUDA library (libnyxus_b200.so) instantiates the very same bodies with a real CTA.
+#define NYX_HOST_EMU 1
+#include <vector>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include "../../nyxus_b200/csrc/nyx_common.h"
+#include "../../nyxus_b200/csrc/nyx_features.h"
+#include "../../nyxus_b200/csrc/glcm_body.h"
+#include "../../nyxus_b200/csrc/glrlm_body.h"
+#include "../../nyxus_b200/csrc/zones_body.h"
+#include "../../nyxus_b200/csrc/nbr_body.h"
+#include "../../nyxus_b200/csrc/intensity_body.h"
+
+using namespace nyx;
+
+extern "C" int nyxemu_ncols() { return NCOL_ALL; }
+
+// tile: h*w intensities, mask: h*w membership.  fam_mask bits: 1 INT, 2 GLCM, 4 GLRLM, 8 GLDZM, 16 GLSZM, 32 GLDM, 64 NGLDM, 128 NGTDM
+extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, int w, int h,
+	int greydepth, int ibsi, int glcm_offset, unsigned fam_mask, double* out, int p16)
+{
+	std::vector<uint32_t> lab ((size_t)w * h);
+	RoiRec r;
+	memset (&r, 0, sizeof (r));
+	r.label = 1;
+	r.imin = 0xFFFFFFFFu;
+	r.imax = 0;
+	int x0 = w, x1 = -1, y0 = h, y1 = -1;
+	std::vector<uint32_t> cloud;
+	for (int y = 0; y < h; y++)
+		for (int x = 0; x < w; x++)
+		{
+			lab[y * w + x] = mask[y * w + x] ? 1 : 0;
+			if (mask[y * w + x])
+			{
+				uint32_t v = tile[y * w + x];
+				r.area++;
+				r.imin = std::min (r.imin, v);
+				r.imax = std::max (r.imax, v);
+				x0 = std::min (x0, x); x1 = std::max (x1, x);
+				y0 = std::min (y0, y); y1 = std::max (y1, y);
+				cloud.push_back (v);
+			}
+		}
+	if (!r.area)
+		return -1;
+	r.x0 = x0; r.y0 = y0; r.w = x1 - x0 + 1; r.h = y1 - y0 + 1;
+	ImageView im { tile, lab.data(), h, w, 0 };
+	Params prm { greydepth, ibsi, glcm_offset, 0, 0.0 };
+	std::vector<double> red (RED_MAX * NW_MAX);
+	Cta c { 0, 1, red.data() };
+	const int ncell = r.w * r.h;
+	Binner B;
+	B.init (ibsi ? 0 : greydepth, r.imin, r.imax);
+	std::vector<uint32_t> cell (ncell);
+	load_tile (c, im, r, B, cell.data());
+	const int Lmax = ibsi ? (int)r.imax : greydepth;
+	for (int i = 0; i < NCOL_ALL; i++)
+		out[i] = 0;
+	if (fam_mask & 1)
+	{
+		uint32_t npad = next_pow2 (r.area);
+		std::vector<uint32_t> mem (intensity_smem_words (npad, greydepth));
+		intensity_body (c, r, prm, cloud.data(), r.area, npad, mem.data(), out + COL_INT);
+	}
+	if (fam_mask & 2)
+	{
+		int Ng = Lmax;
+		if (p16)
+		{
+			std::vector<uint32_t> mem (glcm_smem_words<true> (Ng, 4));
+			glcm_body<true> (c, r, prm, cell.data(), mem.data(), Ng, out + COL_GLCM, nullptr);
+		}
+		else
+		{
+			std::vector<uint32_t> mem (glcm_smem_words<false> (Ng, 4));
+			glcm_body<false> (c, r, prm, cell.data(), mem.data(), Ng, out + COL_GLCM, nullptr);
+		}
+	}
+	if (fam_mask & 4)
+	{
+		int Nr = std::max (r.w, r.h);
+		std::vector<uint32_t> mem (glrlm_smem_words (Lmax, Nr));
+		glrlm_body (c, r, prm, cell.data(), mem.data(), Lmax, Nr, out + COL_GLRLM, nullptr);
+	}
+	if (fam_mask & 8)
+	{
+		std::vector<uint32_t> mem (gldzm_smem_words (ncell, std::max (r.w, r.h)));
+		gldzm_body (c, r, prm, cell.data(), mem.data(), out + COL_GLDZM, nullptr);
+	}
+	if (fam_mask & 16)
+	{
+		std::vector<uint32_t> mem (glszm_smem_words (ncell));
+		glszm_body (c, r, prm, cell.data(), mem.data(), out + COL_GLSZM, nullptr);
+	}
+	if (fam_mask & 32)
+	{
+		std::vector<uint32_t> mem (gldm_smem_words (Lmax));
+		gldm_body (c, r, prm, cell.data(), mem.data(), Lmax, out + COL_GLDM, nullptr);
+	}
+	if (fam_mask & 64)
+	{
+		std::vector<uint32_t> cell2 (ncell);
+		load_tile_ngldm (c, im, r, prm, cell2.data());
+		std::vector<uint32_t> mem (ngldm_smem_words (Lmax));
+		ngldm_body (c, r, prm, cell2.data(), mem.data(), Lmax, out + COL_NGLDM, nullptr);
+	}
+	if (fam_mask & 128)
+	{
+		std::vector<uint32_t> mem (ngtdm_smem_words (Lmax));
+		ngtdm_body (c, r, prm, cell.data(), mem.data(), Lmax, out + COL_NGTDM, nullptr);
+	}
+	return 0;
+}
+
+extern "C" double nyxemu_fast_log10 (double x) { return fast_log10 (x); }
+extern "C" unsigned nyxemu_bin (unsigned x, unsigned mn, unsigned mx, int g) { Binner B; B.init (g, mn, mx); return B.bin (x); }
+extern "C" unsigned nyxemu_to_grayscale (unsigned i, unsigned mn, unsigned range, unsigned n) { return to_grayscale (i, mn, range, n, false); }
