@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native texture + intensity feature path.
+
+A "step" = one pass of the hot path (phase-1 scan -> CSR pack -> 7 texture families + first-order -> table) over one
+synthetic whole-slide tile: BASELINE.json configs[1], 10k x 10k uint16 intensity + uint32 label mask with 103,684
+nucleus-sized ROIs, features *ALL_TEXTURE* + *ALL_INTENSITY* (337 columns), default settings (64 grey levels, MATLAB
+binning, GLCM offset 1).  One process per GPU; at N > 1 every rank processes its OWN slide (ROIs/slides are independent:
+weak scaling, no data-path collective) and the time is the max over ranks.
+
+  value : ROIs/s with the slide already resident in HBM (C ABI nyxb200_featurize_2d_device), device time from CUDA events
+          recorded on the library's launching stream, cross-checked against the host clock around the K steps.
+  e2e   : same metric through the host-buffer C ABI call (nyxb200_featurize_2d_u16) with PINNED host inputs; the H2D copy
+          of the slide and the D2H copy of the table are inside the timed region.
+  --impl reference : the reference's own CPU implementation (oracle/_ref = the unmodified reference sources compiled at
+          -O2 + our replay driver) on a bounded crop of the same slide with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FEATURES = ["*ALL_TEXTURE*", "*ALL_INTENSITY*"]
+METRIC = "ROIs/sec for *ALL_TEXTURE*+*ALL_INTENSITY* (Mpix/sec in config)"
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+            "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import ref
+    from nyxus_b200 import synth
+    if not ref.available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnyxus_ref.so not built (run oracle/Makefile.ref where /root/reference exists)"}))
+        return
+    cores = os.cpu_count() or 1
+    crop = args.ref_crop
+    inten, label = synth.config2(seed=2, size=crop)
+    inten32 = inten.astype(np.uint32)
+    times = []
+    nroi = 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        labels, tab, tph = ref.featurize_2d(inten32, label, greydepth=64, ibsi=False, nthreads=cores)
+        dt = time.perf_counter() - t0
+        nroi = len(labels)
+        if it >= args.warmup:
+            times.append(dt)
+    T = float(np.mean(times))
+    val = nroi / T
+    sample = "%dx%d crop of the configs[1] slide generator (%d ROIs), all families, one pass per step" % (crop, crop, nroi)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "ROIs/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": T * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1] bounded sample: " + sample, "features": FEATURES, "coarse_gray_depth": 64,
+                       "mpix_per_s": crop * crop / T / 1e6},
+            "cpu_baseline": {"value": val, "unit": "ROIs/s", "cores": cores, "kind": "reference", "sample": sample},
+            "e2e": {"value": val, "unit": "ROIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--size", type=int, default=10000, help="slide side (configs[1] = 10000)")
+    ap.add_argument("--ref-crop", type=int, default=3000, help="side of the crop the CPU reference is timed on")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from nyxus_b200 import Engine, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- synthetic slide of this rank (weak scaling: one configs[1] slide per GPU)
+    inten, label = synth.config2(seed=2 + rank, size=args.size)
+    H, W = inten.shape
+    npix = H * W
+    h_int = torch.from_numpy(inten).pin_memory()
+    h_lab = torch.from_numpy(label.view(np.int32)).pin_memory()
+    d_int = h_int.cuda()
+    d_lab = h_lab.cuda()
+    torch.cuda.synchronize()
+
+    eng = Engine(FEATURES, device=local_rank, coarse_gray_depth=64)
+    ncols = len(eng.columns)
+
+    def step_resident():
+        tab, _ = eng.featurize_ptr(d_int.data_ptr(), True, d_lab.data_ptr(), 1, H, W, on_device=True)
+        return tab
+
+    def step_e2e():
+        tab, _ = eng.featurize_ptr(h_int.data_ptr(), True, h_lab.data_ptr(), 1, H, W, on_device=False)
+        return tab
+
+    # ---- resident (value)
+    for _ in range(args.warmup):
+        tab = step_resident()
+    nroi = tab.shape[0]
+    counts = eng.counts()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stage_sum = {}
+    ev_ms = 0.0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_resident()
+        tm = eng.timings()
+        ev_ms += tm["total"]
+        for k, v in tm.items():
+            stage_sum[k] = stage_sum.get(k, 0.0) + v
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = eng.counts()["launches"] * args.steps
+
+    # ---- e2e (host pinned buffers through the C ABI)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    wall_e2e = time.perf_counter() - t1
+
+    # ---- max over ranks
+    ev_s = ev_ms / 1e3
+    tt = torch.tensor([ev_s, wall, wall_e2e], dtype=torch.float64, device="cuda")
+    nn = torch.tensor([float(nroi)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+    ev_s, wall, wall_e2e = [float(x) for x in tt.tolist()]
+    total_rois = float(nn.item())
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        per = {k: v / args.steps for k, v in stage_sum.items()}
+        fam_stages = ["intensity", "glcm", "glrlm", "gldzm", "glszm", "gldm", "ngldm", "ngtdm", "scan", "pack", "compact", "select"]
+        dom = max(fam_stages, key=lambda k: per.get(k, 0.0))
+        nfg = counts["fg_pixels"]
+        # algorithmic bytes per launch (DESIGN.md "Algorithmic bytes"): each element once at the width that crosses the API
+        ncol_fam = {"intensity": 36, "glcm": 149, "glrlm": 80, "gldzm": 18, "glszm": 16, "gldm": 14, "ngldm": 19, "ngtdm": 5}
+        alg = {"scan": npix * (2 + 4) + nroi * 32,
+               "pack": nfg * (2 + 4) + nfg * 4,
+               "intensity": nfg * 4 + nroi * 36 * 8}
+        for f, nc in ncol_fam.items():
+            if f != "intensity":
+                alg[f] = nfg * 2 + nroi * nc * 8
+        def roof(stage):
+            ms = per.get(stage, 0.0)
+            a = alg.get(stage, 0) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+            return {"kernel": stage, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                    "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg.get(stage, 0), "peak_source": peak_src}
+        line = {
+            "metric": METRIC, "value": total_rois * args.steps / ev_s, "unit": "ROIs/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "configs[1]: %dx%d uint16 slide + uint32 mask, %d ROIs per GPU, *ALL_TEXTURE*+*ALL_INTENSITY* (%d columns)" % (H, W, nroi, ncols),
+                       "features": FEATURES, "coarse_gray_depth": 64, "rois_per_gpu": nroi, "fg_pixels_per_gpu": nfg,
+                       "mpix_per_s": npix * world * args.steps / ev_s / 1e6,
+                       "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" % (npix * 6 / 1e6),
+                       "timing": "CUDA events on the library's launching stream, summed over the K steps, max over ranks",
+                       "wall_ms_per_step": wall / args.steps * 1e3},
+            "e2e": {"value": total_rois * args.steps / wall_e2e, "unit": "ROIs/s", "h2d_bytes_per_step": npix * 6,
+                    "d2h_bytes_per_step": nroi * (ncols + 2) * 8, "ms_per_step": wall_e2e / args.steps * 1e3,
+                    "mpix_per_s": npix * world * args.steps / wall_e2e / 1e6},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "stage_ms": {k: round(v, 4) for k, v in per.items()},
+            "roofline": roof(dom),
+            "roofline_passes": [roof(s) for s in ("scan", "pack", "intensity")],
+        }
+        if not args.no_cpu_baseline:
+            from oracle import ref
+            if ref.available():
+                cores = os.cpu_count() or 1
+                crop = args.ref_crop
+                ci, cl = synth.config2(seed=2, size=crop)
+                t2 = time.perf_counter()
+                rl, _, tph = ref.featurize_2d(ci.astype(np.uint32), cl, greydepth=64, nthreads=cores)
+                dt = time.perf_counter() - t2
+                line["cpu_baseline"] = {"value": len(rl) / dt, "unit": "ROIs/s", "cores": cores, "kind": "reference",
+                                        "sample": "%dx%d crop of the same slide generator (%d ROIs), one pass, %.1f s" % (crop, crop, len(rl), dt),
+                                        "phase_s": [round(float(x), 4) for x in tph[:11]]}
+            else:
+                line["cpu_baseline"] = {"value": None, "unit": "ROIs/s", "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

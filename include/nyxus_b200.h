@@ -1,0 +1,117 @@
+/*
+ * nyxus_b200 -- C ABI of the B200-native texture + intensity feature path.
+ *
+ * This is the drop-in boundary for ONE hot path of PolusAI/nyxus: everything that happens between
+ * `featurize_montage_imp()` receiving two uint32 arrays (reference src/nyx/python/new_bindings_py.cpp:562-645)
+ * and the numeric feature table it returns, i.e.
+ *     phase 1  gatherRoisMetricsInMemory      src/nyx/phase1.cpp:373-407
+ *     phase 2  processTrivialRoisInMemory     src/nyx/phase2_2d.cpp:637-770
+ *     reduce   reduce_trivial_2d              src/nyx/reduce_trivial_rois.cpp:62-253   (PixelIntensity, GLCM, GLRLM,
+ *                                                                                       GLDZM, GLSZM, GLDM, NGLDM, NGTDM)
+ *     output   save_features_2_buffer         src/nyx/output_2_buffer.cpp:303-582
+ * Plain pointers and sizes only; no C++/torch types.  Every function returns 0 on success or a negative
+ * NYXB200_E* code; nyxb200_last_error() gives the message (reference convention: C++ exceptions turned into
+ * Python exceptions by pybind11 -- the binding layer raises on a non-zero status).
+ * There is NO CPU fallback: without a CUDA device of compute capability 10.x nyxb200_create() fails.
+ */
+#ifndef NYXUS_B200_H
+#define NYXUS_B200_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NYXB200_OK 0
+#define NYXB200_EINVAL -1      /* bad argument / unknown feature name (reference: std::invalid_argument, env_features.cpp:496,507) */
+#define NYXB200_ECUDA -2       /* CUDA runtime failure or no usable device */
+#define NYXB200_EUNSUPPORTED -3 /* input outside what this build handles (message says which limit) */
+#define NYXB200_ENOMEM -4
+
+typedef struct nyxb200_ctx nyxb200_ctx;
+
+/* Mirrors the subset of Environment / Fsettings the path reads (reference env_features.cpp:712-736,
+ * feature_settings.h:19-53, nyxus.py:157-261 defaults). */
+typedef struct nyxb200_settings
+{
+	int32_t device;             /* CUDA device ordinal (>= 0) */
+	int32_t coarse_gray_depth;  /* NyxSetting::GREYDEPTH and GLCM_GREYDEPTH, default 64, must be > 0 */
+	int32_t ibsi;               /* NyxSetting::IBSI */
+	int32_t glcm_offset;        /* NyxSetting::GLCM_OFFSET, default 1 */
+	int32_t glcm_symmetric;     /* GLCMFeature::symmetric_glcm, default 0 */
+	int32_t verbose;
+	double soft_nan;            /* NyxSetting::SOFTNAN (resultOptions.noval), default 0.0 */
+} nyxb200_settings;
+
+/* Numeric result table, row-major, `ncols` doubles per row: ROI_label, t_index, then the enabled feature columns
+ * (reference output_2_buffer.cpp:441-578: rows by ascending label, every value through force_finite_number(v, noval)).
+ * `data` is owned by the library (pinned host memory) until nyxb200_table_free(). */
+typedef struct nyxb200_table
+{
+	double* data;
+	int64_t nrows;
+	int32_t ncols;
+	int32_t reserved;
+} nyxb200_table;
+
+void nyxb200_default_settings (nyxb200_settings* s);
+
+/* replaces backend.initialize_environment (new_bindings_py.cpp:75-154) for this path */
+int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out);
+/* replaces backend.release_environment_imp (new_bindings_py.cpp:42-46) */
+void nyxb200_destroy (nyxb200_ctx* ctx);
+const char* nyxb200_last_error (const nyxb200_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
+
+/* Feature selection: group names ("*ALL_INTENSITY*", "*ALL_GLCM*", ... plus "*ALL_TEXTURE*") and individual
+ * feature names, exactly as Environment::expand_featuregroups does (env_features.cpp:456-528).  Unknown name -> EINVAL. */
+int nyxb200_select_features (nyxb200_ctx* ctx, const char* const* names, int n);
+int nyxb200_num_columns (const nyxb200_ctx* ctx);               /* feature columns (without ROI_label, t_index) */
+const char* nyxb200_column_name (const nyxb200_ctx* ctx, int i); /* e.g. "GLCM_ASM_45" */
+int nyxb200_column_code (const nyxb200_ctx* ctx, int i);         /* Feature2D code of column i */
+/* replaces set_metaparam_imp("glcm/offset=..") etc. for the keys this path reads (env_metaparams.cpp:63-247) */
+int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value);
+
+/* THE hot path.  Host buffers (pageable or pinned), `n_img` images of H x W, row-major, C-contiguous:
+ * replaces featurize_montage_imp -> processMontage (workflow_pythonapi.cpp:88-192).  Rows of all images are
+ * concatenated; `row_image` (optional, may be NULL) receives a library-owned int32 array giving the image index
+ * of every row (valid until the table is freed). */
+int nyxb200_featurize_2d_u32 (nyxb200_ctx* ctx, const uint32_t* inten, const uint32_t* label,
+	int n_img, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+/* same, 16-bit intensities (avoids the uint32 widening copy of nyxus.py:485-486) */
+int nyxb200_featurize_2d_u16 (nyxb200_ctx* ctx, const uint16_t* inten, const uint32_t* label,
+	int n_img, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+/* same, but `inten` / `label` are DEVICE pointers on the context's device (inputs already resident in HBM);
+ * inten_is_u16 selects the pixel type.  The table still comes back to (pinned) host memory. */
+int nyxb200_featurize_2d_device (nyxb200_ctx* ctx, const void* inten, int inten_is_u16, const uint32_t* label,
+	int n_img, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t);
+
+/* ---- measurement hooks ---- */
+#define NYXB200_NSTAGES 16
+/* per-stage device time (ms, CUDA events on the launching stream) of the last featurize call:
+ * 0 h2d, 1 init, 2 scan, 3 compact, 4 pack, 5 intensity, 6 glcm, 7 glrlm, 8 gldzm, 9 glszm, 10 gldm, 11 ngldm,
+ * 12 ngtdm, 13 select, 14 d2h, 15 total */
+int nyxb200_last_timings (const nyxb200_ctx* ctx, float* ms, int n);
+/* counts of the last featurize call: 0 kernel launches, 1 ROIs, 2 foreground pixels, 3 all pixels */
+int nyxb200_last_counts (const nyxb200_ctx* ctx, int64_t* v, int n);
+const char* nyxb200_stage_name (int i);
+
+/* ---- test hooks (matrix-exact parity) ---- */
+/* ROI records of the last featurize call, 8 int64 per ROI: label, area, min, max, xmin, ymin, width, height */
+int nyxb200_debug_rois (nyxb200_ctx* ctx, int64_t* out, int64_t cap, int64_t* n);
+/* the CSR pixel cloud of one ROI (intensities in raster order) */
+int nyxb200_debug_cloud (nyxb200_ctx* ctx, uint32_t label, uint32_t* out, int64_t cap, int64_t* n);
+/* Sparse dump of one family's matrix for the ROI with `label` (image of the last call must be a 1-image call):
+ * rows of 4 int64 {angle, a, b, count}; family ids as in nyxb200_family_id().  For NGTDM `svals` receives S per row. */
+int nyxb200_debug_matrix (nyxb200_ctx* ctx, uint32_t label, int family, int64_t* trip, int64_t cap, int64_t* n,
+	double* svals);
+int nyxb200_family_id (const char* name); /* "INT" 0, "GLCM" 1, "GLRLM" 2, "GLDZM" 3, "GLSZM" 4, "GLDM" 5, "NGLDM" 6, "NGTDM" 7 */
+
+const char* nyxb200_version (void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -234,7 +234,9 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 		const double mr = (double)im[a * 5 + 0] / N;		// f_corr mr (:598-603), f_var mean (:657-665), JAVE (:1140-1146)
 		const double mc = (double)im[a * 5 + 1] / N;		// f_corr mc (:605-610), by_row_mean (:531-536)
 		const double diffavg = (double)im[a * 5 + 2] / N;	// f_difference_avg (:786-795), DIS (:1050-1052)
-		const double NgD = (double)Ng;
+		// Ng of THIS ROI: MATLAB = grey depth; IBSI = max level of the tile = aux_max (glcm.cpp:412-419).
+		// (the `Ng` argument may be a class-wide storage bound in IBSI mode)
+		const double NgD = prm.ibsi ? (double)r.imax : (double)Ng;
 		enum { M_S2R, M_S2C, M_JVAR, M_HX, M_IDM, M_ID, M_IDN, M_IDMN, M_IV, M_DENT, M_DVAR, M_SENT, M_CP, M_CS, M_CT, M_N };
 		double m[M_N];
 		for (int k = 0; k < M_N; k++)

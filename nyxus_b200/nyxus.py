@@ -1,0 +1,151 @@
+"""Host-side mirror of the reference's Python entry points for the texture + intensity path.
+
+`Nyxus(features, **kwargs).featurize(intensity_images, label_images, ...)` keeps the reference's signature, argument
+checks, error messages, DataFrame layout and column names (reference src/nyx/python/nyxus/nyxus.py:157-261, 385-518),
+but the work is done by the B200 library through the C ABI (include/nyxus_b200.h).  Feature names outside the
+texture/intensity path raise ValueError exactly like an unknown feature name does in the reference
+(env_features.cpp:496)."""
+from typing import List, Optional
+
+import numpy as np
+import pandas as pd
+
+from .engine import Engine
+
+_VALID_KEYS = {
+    'neighbor_distance', 'pixels_per_micron', 'coarse_gray_depth',
+    'n_feature_calc_threads', 'use_gpu_device', 'ibsi',
+    'gabor_kersize', 'gabor_gamma', 'gabor_sig2lam', 'gabor_f0',
+    'gabor_thold', 'gabor_thetas', 'gabor_freqs', 'channel_signature',
+    'parent_channel', 'child_channel', 'aggregate', 'dynamic_range', 'min_intensity',
+    'max_intensity', 'ram_limit', 'verbose',
+    'anisotropy_x', 'anisotropy_y', 'mergerois', 'preserve_hu'
+}
+
+
+class Nyxus:
+    """2D feature extraction (reference nyxus.py:23-518), texture + intensity path on a B200.
+
+    Differences from the reference, all deliberate:
+      * `use_gpu_device` selects the B200 the path runs on (default -1 means device 0): there is no CPU path here.
+      * `*ALL_TEXTURE*` is accepted and means the union of the seven 2D texture groups.
+      * `n_feature_calc_threads` is accepted and ignored (ROI parallelism is the GPU grid).
+    """
+
+    def __init__(self, features: List[str], **kwargs):
+        invalid_keys = set(kwargs.keys()) - _VALID_KEYS
+        if invalid_keys:
+            print(f"Warning: unexpected keyword argument(s): {', '.join(invalid_keys)}")
+        neighbor_distance = kwargs.get('neighbor_distance', 5)
+        pixels_per_micron = kwargs.get('pixels_per_micron', 1.0)
+        coarse_gray_depth = kwargs.get('coarse_gray_depth', 64)
+        n_feature_calc_threads = kwargs.get('n_feature_calc_threads', 4)
+        use_gpu_device = kwargs.get('use_gpu_device', -1)
+        ibsi = kwargs.get('ibsi', False)
+        verb_lvl = kwargs.get('verbose', 0)
+        aniso_x = kwargs.get('anisotropy_x', 1.0)
+        aniso_y = kwargs.get('anisotropy_y', 1.0)
+        mergerois = kwargs.get('mergerois', False)
+
+        if neighbor_distance <= 0:
+            raise ValueError("Neighbor distance must be greater than zero.")
+        if pixels_per_micron <= 0:
+            raise ValueError("Pixels per micron must be greater than zero.")
+        if coarse_gray_depth <= 0:
+            raise ValueError("Custom number of grayscale levels (parameter coarse_gray_depth, default=64) must be non-negative.")
+        if n_feature_calc_threads < 1:
+            raise ValueError("There must be at least one feature calculation thread.")
+        if verb_lvl < 0:
+            raise ValueError("verbosity must be non-negative")
+        if aniso_x <= 0:
+            raise ValueError("anisotropy_x must be positive")
+        if aniso_y <= 0:
+            raise ValueError("anisotropy_y must be positive")
+        if aniso_x != 1.0 or aniso_y != 1.0:
+            raise ValueError("anisotropy is outside the texture/intensity path implemented by nyxus_b200")
+
+        self._mergerois = bool(mergerois)
+        self._engine = Engine(list(features), device=max(int(use_gpu_device), 0), coarse_gray_depth=coarse_gray_depth,
+                              ibsi=ibsi, verbose=verb_lvl)
+        self._valid_output_types = ['pandas', 'arrowipc', 'parquet']
+        self.error_message = ''
+
+    # reference nyxus.py:1067-1086 set_metaparam_imp / get_metaparam_imp for the keys this path reads
+    def set_metaparam(self, expr: str):
+        key, _, val = expr.partition('=')
+        self._engine.set_param(key.strip(), float(val))
+
+    def set_params(self, **params):
+        for k, v in params.items():
+            if k == 'coarse_gray_depth':
+                self._engine.set_param('coarse_gray_depth', v)
+            elif k == 'ibsi':
+                self._engine.set_param('ibsi', 1.0 if v else 0.0)
+            elif k == 'features':
+                self._engine.select(list(v))
+            else:
+                raise ValueError(f"parameter {k} is outside the texture/intensity path implemented by nyxus_b200")
+
+    @property
+    def feature_columns(self):
+        return self._engine.columns
+
+    def featurize(self, intensity_images: np.ndarray, label_images: np.ndarray, intensity_names: list = [],
+                  label_names: list = [], output_type: Optional[str] = "pandas", output_path: Optional[str] = ""):
+        if (output_type != "" and output_type not in self._valid_output_types):
+            raise ValueError(f'Invalid output type: {output_type}. Valid options are: {self._valid_output_types}')
+        if not isinstance(intensity_images, np.ndarray):
+            raise ValueError("intensity_images parameter must be numpy.ndarray")
+        if not isinstance(label_images, np.ndarray):
+            raise ValueError("label_images parameter must be numpy.ndarray")
+        if (output_type not in self._valid_output_types):
+            raise ValueError(f'Invalid output type {output_type}. Valid output types are {self._valid_output_types}.')
+        if output_type != 'pandas':
+            raise ValueError("arrowipc / parquet writers are outside the texture/intensity path implemented by nyxus_b200")
+
+        if intensity_images.ndim == 2:
+            if label_images.ndim != 2:
+                raise ValueError("Both intensity and label arrays must be the same dimension")
+            intensity_images = np.array([intensity_images])
+            label_images = np.array([label_images])
+        elif intensity_images.ndim == 3:
+            if label_images.ndim != 3:
+                raise ValueError("Both intensity and label arrays must be the same dimension")
+        else:
+            raise ValueError("Intensity and label arrays must be 2D or 3D")
+        if intensity_images.shape != label_images.shape:
+            raise ValueError("Intensity and label image arrays must have the same number of images with matching dimensions")
+        if intensity_names == []:
+            intensity_names = ["Intensity" + str(i) for i in range(intensity_images.shape[0])]
+        if label_names == []:
+            label_names = ["Segmentation" + str(i) for i in range(label_images.shape[0])]
+        if intensity_images.shape[0] != len(intensity_names):
+            raise ValueError("Number of _intensity image names_ (" + str(len(intensity_names)) + ") must be the same as the number of intensity images (" + str(intensity_images.shape[0]) + ")")
+        if label_images.shape[0] != len(label_names):
+            raise ValueError("Number of segmentation names must be the same as the number of images.")
+
+        # Hounsfield-type scale: shift into the unsigned range IN PLACE like the reference (nyxus.py:481-484)
+        I = intensity_images
+        min_raw_I = np.min(intensity_images)
+        if min_raw_I < 0:
+            I -= min_raw_I
+        if I.dtype != np.uint16 and I.dtype != np.uint32:     # uint16 goes to the device as is (no widening copy)
+            I = I.astype(np.uint32)
+        M = label_images.astype(np.uint32)
+        if self._mergerois:                                   # phase1.cpp:392-393, phase2_2d.cpp:665-666
+            M = (M != 0).astype(np.uint32)
+
+        numeric, row_img = self._engine.featurize(I, M)
+        self.error_message = ''
+        header = ["intensity_image", "mask_image", "ROI_label", "t_index"] + self._engine.columns
+        string_data = np.array([[intensity_names[k], label_names[k]] for k in row_img], dtype=object).reshape(-1, 2)
+        df = pd.concat(
+            [
+                pd.DataFrame(string_data, columns=header[:2]),
+                pd.DataFrame(numeric, columns=header[2:]),
+            ],
+            axis=1,
+        )
+        if "ROI_label" in df.columns:
+            df.ROI_label = df.ROI_label.astype(np.uint32)
+        return df

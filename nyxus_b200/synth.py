@@ -1,0 +1,80 @@
+"""Synthetic inputs of the shapes BASELINE.json names, numpy PCG64 with fixed seeds."""
+import numpy as np
+
+
+def _smooth_noise(rng, H, W, sigma):
+    """cheap separable box-blur approximation of Gaussian-blurred white noise (no scipy dependency)"""
+    a = rng.standard_normal((H, W)).astype(np.float32)
+    k = max(1, int(sigma))
+    for _ in range(3):
+        c = np.cumsum(np.pad(a, ((k, k), (0, 0)), mode="wrap"), axis=0)
+        a = (c[2 * k:] - c[:-2 * k]) / (2 * k)
+        c = np.cumsum(np.pad(a, ((0, 0), (k, k)), mode="wrap"), axis=1)
+        a = (c[:, 2 * k:] - c[:, :-2 * k]) / (2 * k)
+    a /= (a.std() + 1e-12)
+    return a
+
+
+def blob_slide(H, W, pitch, rmin, rmax, seed, jitter=None, lobes=True, zero_frac=0.01, dtype=np.uint16, sigma=6):
+    """Grid of blob ROIs (disks with a 5-lobe sinusoidal boundary, amplitude 3 px), label id = 1 + row-major grid index.
+    intensity = clip(2000 + 1500*smooth + 800*N(0,1), 1, 65535), a fraction of in-ROI pixels forced to 0.
+    Vectorised per band of grid rows so a 10k x 10k slide takes seconds."""
+    rng = np.random.default_rng(seed)
+    ny, nx = H // pitch, W // pitch
+    if jitter is None:
+        jitter = max(0, pitch // 2 - rmax - (3 if lobes else 0) - 1)
+    r = rng.integers(rmin, rmax + 1, (ny, nx)).astype(np.float32)
+    dx = rng.integers(-jitter, jitter + 1, (ny, nx)).astype(np.float32)
+    dy = rng.integers(-jitter, jitter + 1, (ny, nx)).astype(np.float32)
+    ph = rng.uniform(0, 2 * np.pi, (ny, nx)).astype(np.float32)
+    label = np.zeros((H, W), np.uint32)
+    xs = np.arange(nx * pitch)
+    ci = xs // pitch
+    lx = (xs % pitch - pitch // 2).astype(np.float32)
+    for j in range(ny):
+        ly = (np.arange(pitch) - pitch // 2).astype(np.float32)[:, None]
+        X = lx[None, :] - dx[j, ci][None, :]
+        Y = ly - dy[j, ci][None, :]
+        rad = np.hypot(X, Y)
+        rr = r[j, ci][None, :]
+        if lobes:
+            rr = rr + 3.0 * np.sin(5.0 * np.arctan2(Y, X) + ph[j, ci][None, :])
+        ids = (1 + j * nx + ci).astype(np.uint32)[None, :]
+        label[j * pitch:(j + 1) * pitch, :nx * pitch] = np.where(rad <= rr, ids, 0)
+    smooth = _smooth_noise(rng, H, W, sigma)
+    inten = 2000.0 + 1500.0 * smooth + 800.0 * rng.standard_normal((H, W)).astype(np.float32)
+    inten = np.clip(inten, 1, 65535).astype(dtype)
+    if zero_frac > 0:
+        z = (rng.random((H, W), dtype=np.float32) < zero_frac) & (label != 0)
+        inten[z] = 0
+    return inten, label
+
+
+def config1(seed=1):
+    """C1: 1024x1024 uint16, 16x16 grid of 256 blob ROIs"""
+    return blob_slide(1024, 1024, 64, 12, 22, seed)
+
+
+def config2(seed=2, size=10000):
+    """C2: 10k x 10k, pitch 31 -> 322x322 = 103684 nucleus-sized ROIs"""
+    return blob_slide(size, size, 31, 7, 12, seed, jitter=0, lobes=True)
+
+
+def random_rois(H, W, nroi, seed, maxval=5000, levels=None):
+    """random rectangles / noisy masks with assorted intensity statistics, for parity tests"""
+    rng = np.random.default_rng(seed)
+    label = np.zeros((H, W), np.uint32)
+    inten = rng.integers(1, maxval, (H, W)).astype(np.uint32)
+    if levels:
+        inten = rng.integers(0, levels, (H, W)).astype(np.uint32)
+    lab = 1
+    for _ in range(nroi):
+        h, w = int(rng.integers(1, 40)), int(rng.integers(1, 40))
+        y, x = int(rng.integers(0, H - h)), int(rng.integers(0, W - w))
+        m = rng.random((h, w)) < rng.choice([0.4, 0.8, 1.0])
+        sub = label[y:y + h, x:x + w]
+        sub[m & (sub == 0)] = lab * 3 + 1      # sparse label values
+        lab += 1
+    z = rng.random((H, W)) < 0.02
+    inten[z] = 0
+    return inten, label
