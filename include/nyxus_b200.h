@@ -47,7 +47,8 @@ typedef struct nyxb200_settings
 
 /* Numeric result table, row-major, `ncols` doubles per row: ROI_label, t_index, then the enabled feature columns
  * (reference output_2_buffer.cpp:441-578: rows by ascending label, every value through force_finite_number(v, noval)).
- * `data` is owned by the library (pinned host memory) until nyxb200_table_free(). */
+ * `data` is owned by the library (the context's pinned host buffer): valid until the next featurize call on the
+ * same context, nyxb200_table_free() or nyxb200_destroy(). */
 typedef struct nyxb200_table
 {
 	double* data;

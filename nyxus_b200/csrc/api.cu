@@ -118,6 +118,9 @@ struct nyxb200_ctx
 	std::vector<RoiRec> h_rois;
 	bool h_rois_valid = false;
 
+	double* h_out = nullptr;		// pinned result buffer (grow-only)
+	size_t h_out_cap = 0, h_out_used = 0;
+
 	float stage_ms[NYXB200_NSTAGES] {};
 	int64_t counts[4] {};
 	std::vector<int32_t> row_image;
@@ -257,6 +260,8 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	ctx->d_blkcnt.release(); ctx->d_blkarea.release(); ctx->d_rois.release(); ctx->d_classslot.release(); ctx->d_tlist.release();
 	ctx->d_alist.release(); ctx->d_bases.release(); ctx->d_cloud.release(); ctx->d_full.release(); ctx->d_sel_out.release();
 	ctx->d_scratch.release(); ctx->d_rowoff.release(); ctx->d_dbg.release(); ctx->d_dbgf.release();
+	if (ctx->h_out)
+		cudaFreeHost (ctx->h_out);
 	for (auto& ev : ctx->ev)
 		cudaEventDestroy (ev);
 	cudaStreamDestroy (ctx->stream);
@@ -460,9 +465,26 @@ void stage_begin (nyxb200_ctx* ctx, int st)
 	ctx->ev_used[st] = true;
 }
 
-// One slide already resident on the device.  Appends its rows to `rows` (host) -- returns the row count through nrows.
-int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, std::vector<double>* host_rows, double* pinned_dst,
-	int64_t* nrows_out, bool want_rows_in_pinned)
+// grow-only pinned host buffer for the result table (keeps its content when it grows)
+int reserve_pinned_out (nyxb200_ctx* ctx, size_t n)
+{
+	if (n <= ctx->h_out_cap)
+		return 0;
+	size_t want = n + n / 2 + 1024;
+	double* p = nullptr;
+	CU (cudaMallocHost ((void**)&p, want * sizeof (double)));
+	if (ctx->h_out)
+	{
+		memcpy (p, ctx->h_out, ctx->h_out_used * sizeof (double));
+		cudaFreeHost (ctx->h_out);
+	}
+	ctx->h_out = p;
+	ctx->h_out_cap = want;
+	return 0;
+}
+
+// One slide already resident on the device.  Appends its rows to the context's pinned table buffer.
+int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t* nrows_out)
 {
 	const unsigned long long npix = (unsigned long long)im.H * (unsigned long long)im.W;
 	const Params prm = make_params (ctx);
@@ -642,14 +664,10 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, std::ve
 		ctx->counts[0]++;
 	}
 	stage_begin (ctx, ST_D2H);
-	if (want_rows_in_pinned)
-		CU (cudaMemcpyAsync (pinned_dst, ctx->d_sel_out.p, outn * sizeof (double), cudaMemcpyDeviceToHost, s));
-	else
-	{
-		size_t off = host_rows->size();
-		host_rows->resize (off + outn);
-		CU (cudaMemcpyAsync (host_rows->data() + off, ctx->d_sel_out.p, outn * sizeof (double), cudaMemcpyDeviceToHost, s));
-	}
+	if (int rc = reserve_pinned_out (ctx, ctx->h_out_used + outn))
+		return rc;
+	CU (cudaMemcpyAsync (ctx->h_out + ctx->h_out_used, ctx->d_sel_out.p, outn * sizeof (double), cudaMemcpyDeviceToHost, s));
+	ctx->h_out_used += outn;
 	stage_begin (ctx, ST_TOTAL);
 	CU (cudaStreamSynchronize (s));
 	(void)img_index;
@@ -691,7 +709,7 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 	ctx->row_image.clear();
 	const size_t npix = (size_t)H * (size_t)W;
 	const size_t ibytes = npix * (inten_u16 ? 2 : 4), lbytes = npix * 4;
-	std::vector<double> rows;
+	ctx->h_out_used = 0;
 	for (int k = 0; k < n_img; k++)
 	{
 		for (auto& u : ctx->ev_used) u = false;
@@ -717,7 +735,7 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 			im.label = ctx->d_label.p;
 		}
 		int64_t nr = 0;
-		int rc = process_slide (ctx, im, k, &rows, nullptr, &nr, false);
+		int rc = process_slide (ctx, im, k, &nr);
 		if (rc)
 			return rc;
 		collect_timings (ctx);
@@ -726,12 +744,7 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 	}
 	out->nrows = (int64_t)ctx->row_image.size();
 	if (out->nrows)
-	{
-		double* p = nullptr;
-		CU (cudaMallocHost ((void**)&p, rows.size() * sizeof (double)));
-		memcpy (p, rows.data(), rows.size() * sizeof (double));
-		out->data = p;
-	}
+		out->data = ctx->h_out;
 	if (row_image)
 		*row_image = ctx->row_image.data();
 	float tot = 0;
@@ -766,10 +779,9 @@ int nyxb200_featurize_2d_device (nyxb200_ctx* ctx, const void* inten, int inten_
 
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t)
 {
-	(void)ctx;
-	if (t && t->data)
+	(void)ctx;	// the rows live in the context's grow-only pinned buffer, reused by the next featurize call
+	if (t)
 	{
-		cudaFreeHost (t->data);
 		t->data = nullptr;
 		t->nrows = 0;
 	}

@@ -1,0 +1,225 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI, against
+  (1) golden vectors produced by the compiled reference (tests/golden/*.npz),
+  (2) the compiled reference itself (oracle/_ref, when the prebuilt .so travelled) on fresh seeded inputs,
+  (3) the numpy oracle,
+with every matrix entry exact and every derived feature within 1e-9 relative (north_star), plus size-independent
+properties at the full configs[1] size."""
+import numpy as np
+import pytest
+
+import nyx_testutil as tu
+from oracle import nyx_oracle as no
+from oracle import ref
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["*ALL_INTENSITY*", "*ALL_TEXTURE*"]
+COLS, CASES = tu.load_golden_rois()
+
+
+def _engine(features=ALL, **kw):
+    from nyxus_b200 import Engine
+    return Engine(features, **kw)
+
+
+@pytest.fixture(scope="module")
+def eng64():
+    e = _engine()
+    yield e
+    e.close()
+
+
+# ------------------------------------------------------------------------------------------------ golden, per ROI
+@pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
+def test_golden_roi_features_and_matrices(case):
+    e = _engine(coarse_gray_depth=case["g"], ibsi=case["ibsi"])
+    try:
+        I, L = tu.place_roi(case["tile"], case["mask"], label=5)
+        tab, img = e.featurize(I, L)
+        assert e.columns == COLS
+        assert tab.shape == (1, 339) and tab[0, 0] == 5 and tab[0, 1] == 0
+        bad = tu.mismatches(case["features"], tab[0, 2:], COLS)
+        assert not bad, bad[:8]
+        for fam in tu.FAMILIES:
+            got, svals = e.debug_matrix(5, fam)
+            assert sorted(got) == sorted(case["mats"][fam]), (fam, case["name"])
+            if fam == "NGTDM" and len(case["ngtdm_s"]):
+                assert np.allclose(svals, case["ngtdm_s"], rtol=1e-12, atol=1e-12)
+    finally:
+        e.close()
+
+
+def test_golden_slide_table(eng64):
+    s = tu.load_golden_slide()
+    tab, img = eng64.featurize(s["inten"], s["label"])
+    assert np.array_equal(tab[:, 0].astype(np.int64), s["labels"].astype(np.int64))       # rows by ascending label
+    assert not tu.mismatches(s["table"], tab[:, 2:], COLS)
+    # uint16 entry point gives the identical table
+    tab16, _ = eng64.featurize(s["inten"].astype(np.uint16), s["label"])
+    assert np.array_equal(tab, tab16)
+
+
+def test_golden_slide_table_ibsi():
+    s = tu.load_golden_slide()
+    e = _engine(ibsi=True)
+    try:
+        tab, _ = e.featurize(np.minimum(s["inten"], 255), s["label"])
+        assert np.array_equal(tab[:, 0].astype(np.int64), s["labels_ibsi"].astype(np.int64))
+        assert not tu.mismatches(s["table_ibsi"], tab[:, 2:], COLS)
+    finally:
+        e.close()
+
+
+# ------------------------------------------------------------------------------------------------ phase 1 / CSR pack: exact
+def test_phase1_records_and_cloud_exact(eng64):
+    from nyxus_b200 import synth
+    I, L = synth.random_rois(300, 257, 60, seed=21)       # odd width: scalar-load path of the scan
+    tab, _ = eng64.featurize(I, L)
+    recs = eng64.debug_rois()
+    labels = np.unique(L[L > 0])
+    assert np.array_equal(recs[:, 0], labels)
+    for r in recs:
+        m = L == r[0]
+        ys, xs = np.nonzero(m)
+        assert list(r[1:]) == [m.sum(), I[m].min(), I[m].max(), xs.min(), ys.min(), xs.max() - xs.min() + 1, ys.max() - ys.min() + 1]
+        assert np.array_equal(eng64.debug_cloud(int(r[0])), I[m])      # raster order
+    assert eng64.counts()["fg_pixels"] == int((L > 0).sum())
+
+
+# ------------------------------------------------------------------------------------------------ vs the compiled reference
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so did not travel")
+@pytest.mark.parametrize("seed,g,ibsi,levels", [(1, 64, False, None), (2, 16, False, None), (3, 256, False, None), (4, 64, True, 120),
+                                                (5, 64, False, 5), (6, 64, True, 9)])
+def test_random_slide_against_compiled_reference(seed, g, ibsi, levels):
+    from nyxus_b200 import synth
+    I, L = synth.random_rois(240, 260, 45, seed=100 + seed, levels=levels)
+    e = _engine(coarse_gray_depth=g, ibsi=ibsi)
+    try:
+        tab, _ = e.featurize(I, L)
+        rl, rt, _ = ref.featurize_2d(I, L, greydepth=g, ibsi=ibsi, nthreads=4)
+        assert np.array_equal(tab[:, 0].astype(np.int64), rl.astype(np.int64))
+        bad = tu.mismatches(rt, tab[:, 2:], COLS)
+        assert not bad, bad[:8]
+        recs = e.debug_rois()
+        for r in recs[::9]:
+            x0, y0, w, h = int(r[4]), int(r[5]), int(r[6]), int(r[7])
+            mask = L[y0:y0 + h, x0:x0 + w] == r[0]
+            rm = ref.roi_matrices(I[y0:y0 + h, x0:x0 + w] * mask, mask, g, ibsi)
+            for fam in tu.FAMILIES:
+                got, _ = e.debug_matrix(int(r[0]), fam)
+                assert sorted(got) == sorted(rm[fam]), (fam, int(r[0]))
+    finally:
+        e.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so did not travel")
+def test_config1_against_compiled_reference(eng64):
+    """BASELINE.json configs[0]: 1024x1024 uint16, 256 blob ROIs"""
+    from nyxus_b200 import synth
+    I, L = synth.config1()
+    tab, _ = eng64.featurize(I, L)
+    rl, rt, _ = ref.featurize_2d(I.astype(np.uint32), L, nthreads=8)
+    assert tab.shape[0] == 256 and np.array_equal(tab[:, 0].astype(np.int64), rl.astype(np.int64))
+    assert not tu.mismatches(rt, tab[:, 2:], COLS)
+
+
+# ------------------------------------------------------------------------------------------------ vs the numpy oracle
+def test_small_rois_against_numpy_oracle(eng64):
+    rng = np.random.default_rng(8)
+    I = rng.integers(1, 3000, (40, 48)).astype(np.uint32)
+    L = np.zeros((40, 48), np.uint32)
+    L[2:12, 3:14] = 4
+    L[15:22, 20:33] = 9
+    L[30:39, 1:9] = 2
+    L[25:27, 40:47] = 11
+    tab, _ = eng64.featurize(I, L)
+    for i, lab in enumerate(tab[:, 0].astype(int)):
+        m = L == lab
+        oc, om = no.roi_features(np.where(m, I, 0), m, 64, False)
+        assert not tu.mismatches(np.array([oc[c] for c in COLS]), tab[i, 2:], COLS)
+        for fam in tu.FAMILIES:
+            got, _ = eng64.debug_matrix(lab, fam)
+            assert sorted(got) == sorted(om[fam])
+
+
+# ------------------------------------------------------------------------------------------------ API behaviour / edge cases
+def test_empty_mask_and_montage_and_selection():
+    from nyxus_b200 import Nyxus
+    nyx = Nyxus(["GLCM_ASM", "MEAN", "*ALL_NGTDM*"])
+    assert nyx.feature_columns == ["MEAN", "GLCM_ASM_0", "GLCM_ASM_45", "GLCM_ASM_90", "GLCM_ASM_135", "NGTDM_COARSENESS",
+                                   "NGTDM_CONTRAST", "NGTDM_BUSYNESS", "NGTDM_COMPLEXITY", "NGTDM_STRENGTH"]
+    I = np.random.default_rng(1).integers(1, 500, (2, 32, 32)).astype(np.uint16)
+    L = np.zeros((2, 32, 32), np.int64)
+    df = nyx.featurize(I, L)                       # no ROI at all
+    assert df.shape == (0, 4 + 10)
+    L[0, 4:20, 4:20] = 2
+    L[1, 1:9, 1:9] = 7
+    L[1, 12:30, 10:28] = 3
+    df = nyx.featurize(I, L, intensity_names=["a", "b"], label_names=["ma", "mb"])
+    assert list(df.columns[:4]) == ["intensity_image", "mask_image", "ROI_label", "t_index"]
+    assert list(df.intensity_image) == ["a", "b", "b"] and list(df.ROI_label) == [2, 3, 7]
+    assert abs(df.MEAN[0] - I[0, 4:20, 4:20].mean()) < 1e-9
+    with pytest.raises(ValueError, match="not a valid 2D feature name"):
+        Nyxus(["NOT_A_FEATURE"])
+    with pytest.raises(ValueError):
+        nyx.featurize(I, L[:, :16])
+
+
+def test_negative_intensities_are_shifted_in_place_like_the_reference():
+    from nyxus_b200 import Nyxus
+    nyx = Nyxus(["MIN", "MAX"])
+    I = np.array([[-5, 1, 2], [3, 4, 5], [6, 7, 8]], np.int32)
+    L = np.ones((3, 3), np.uint32)
+    df = nyx.featurize(I, L)
+    assert df.MIN[0] == 0 and df.MAX[0] == 13 and I.min() == 0          # nyxus.py:481-484 mutates the caller's array
+
+
+def test_label_table_growth_and_limit(eng64):
+    I = np.full((16, 16), 10, np.uint32)
+    L = np.zeros((16, 16), np.uint32)
+    L[2:6, 2:6] = 3_000_000           # beyond the initial 2^20 table -> one retry
+    L[8:12, 8:12] = 17
+    tab, _ = eng64.featurize(I, L)
+    assert list(tab[:, 0]) == [17, 3_000_000]
+    from nyxus_b200 import NyxusB200Error
+    L[2:6, 2:6] = (1 << 27) + 5
+    with pytest.raises(NyxusB200Error, match="label"):
+        eng64.featurize(I, L)
+
+
+def test_runs_are_bitwise_deterministic(eng64):
+    from nyxus_b200 import synth
+    I, L = synth.blob_slide(512, 512, 31, 7, 12, seed=5, jitter=0)
+    a, _ = eng64.featurize(I, L)
+    b, _ = eng64.featurize(I, L)
+    assert np.array_equal(a, b)
+
+
+# ------------------------------------------------------------------------------------------------ full-size properties (configs[1])
+def test_config2_full_size_properties(eng64):
+    """10k x 10k, 103,684 ROIs.  Size-independent checks: (a) sum of areas == foreground pixels, (b) rows sorted by label,
+    (c) translation invariance: a ROI's features do not depend on where the ROI sits, (d) a crop processed on its own gives
+    bit-identical rows, (e) every value finite."""
+    from nyxus_b200 import synth
+    I, L = synth.config2(seed=2, size=10000)
+    tab, _ = eng64.featurize(I, L)
+    assert tab.shape == (103684, 339)
+    assert eng64.counts()["fg_pixels"] == int(np.count_nonzero(L))
+    assert np.all(np.diff(tab[:, 0]) > 0)
+    assert np.isfinite(tab).all()
+    # integrated intensity column sums to the sum over all foreground pixels (exact in FP64 at this size)
+    j = 2 + COLS.index("INTEGRATED_INTENSITY")
+    assert tab[:, j].sum() == float(I[L > 0].astype(np.int64).sum())
+    # crop: the first 5 grid rows/cols (pitch 31) re-labelled identically
+    c = 31 * 5
+    Ic, Lc = np.ascontiguousarray(I[:c, :c]), np.ascontiguousarray(L[:c, :c])
+    sub, _ = eng64.featurize(Ic, Lc)
+    keep = np.isin(tab[:, 0], sub[:, 0])
+    assert np.array_equal(tab[keep], sub)
+    # translation: shift the crop by (7, 13) inside a larger blank slide
+    I2 = np.zeros((c + 20, c + 30), I.dtype)
+    L2 = np.zeros((c + 20, c + 30), L.dtype)
+    I2[7:7 + c, 13:13 + c] = Ic
+    L2[7:7 + c, 13:13 + c] = Lc
+    sh, _ = eng64.featurize(I2, L2)
+    assert np.array_equal(sh, sub)

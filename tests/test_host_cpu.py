@@ -1,0 +1,133 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, the host-side mirror validates its
+arguments like the reference, the product refuses to run without a device, and the multi-rank sharding works (gloo)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import nyx_testutil as tu
+
+ROOT = tu.ROOT
+
+
+def _lib():
+    from nyxus_b200 import build
+    build.build()
+    from nyxus_b200 import _lib
+    return _lib.lib(), _lib
+
+
+def test_cabi_exports_every_declared_symbol():
+    L, mod = _lib()
+    hdr = open(os.path.join(ROOT, "include", "nyxus_b200.h")).read()
+    declared = set(re.findall(r"\b(nyxb200_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    for name in sorted(declared):
+        assert hasattr(L, name), "libnyxus_b200.so does not export " + name
+    assert declared == set(mod.EXPORTS)
+
+
+def test_library_contains_sm100a_code_only():
+    _lib()
+    out = subprocess.run(["cuobjdump", "-lelf", os.path.join(ROOT, "nyxus_b200", "libnyxus_b200.so")], capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out, out
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from nyxus_b200 import Engine, NyxusB200Error
+    with pytest.raises(NyxusB200Error) as e:
+        Engine(["*ALL_GLCM*"])
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "nyxus_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/", "").replace("the oracle", "") or f in ("nyx_common.h",), f
+
+
+def test_nyxus_argument_validation_matches_reference():
+    """reference nyxus.py:200-224 -- these raise before the backend is touched"""
+    from nyxus_b200 import Nyxus
+    with pytest.raises(ValueError, match="Neighbor distance"):
+        Nyxus(["*ALL_GLCM*"], neighbor_distance=0)
+    with pytest.raises(ValueError, match="Pixels per micron"):
+        Nyxus(["*ALL_GLCM*"], pixels_per_micron=0)
+    with pytest.raises(ValueError, match="grayscale levels"):
+        Nyxus(["*ALL_GLCM*"], coarse_gray_depth=0)
+    with pytest.raises(ValueError, match="at least one feature calculation thread"):
+        Nyxus(["*ALL_GLCM*"], n_feature_calc_threads=0)
+    with pytest.raises(ValueError, match="verbosity"):
+        Nyxus(["*ALL_GLCM*"], verbose=-1)
+
+
+def test_feature_table_layout():
+    from nyxus_b200 import feature_table as ft
+    assert len(ft.CANONICAL_COLUMNS) == 337 and len(ft.FEATURES) == 199
+    assert ft.CANONICAL_COLUMNS[0] == "COV" and ft.CANONICAL_COLUMNS[35] == "UNIFORMITY_PIU"
+    assert ft.CANONICAL_COLUMNS[36:40] == ["GLCM_ASM_0", "GLCM_ASM_45", "GLCM_ASM_90", "GLCM_ASM_135"]
+    assert ft.CANONICAL_COLUMNS[-5:] == ["NGTDM_COARSENESS", "NGTDM_CONTRAST", "NGTDM_BUSYNESS", "NGTDM_COMPLEXITY", "NGTDM_STRENGTH"]
+    codes = [f[1] for f in ft.FEATURES]
+    assert codes == sorted(codes) and codes[0] == 0 and codes[36] == 144   # Feature2D::COV, GLCM_ASM
+
+
+def test_lpt_partition_balances_and_is_deterministic():
+    from nyxus_b200.shard import lpt_partition
+    w = [100, 90, 80, 10, 10, 10, 5, 5]
+    parts = lpt_partition(w, 2)
+    assert sorted(i for p in parts for i in p) == list(range(len(w)))
+    loads = [sum(w[i] for i in p) for p in parts]
+    assert max(loads) <= (4.0 / 3.0) * (sum(w) / 2.0)      # Graham's LPT bound
+    assert parts == lpt_partition(w, 2)
+    assert lpt_partition([], 3) == [[], [], []]
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np
+import torch.distributed as dist
+from nyxus_b200.shard import featurize_sharded
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+rng = np.random.default_rng(3)
+slides = []
+for k in range(5):
+    h = 8 + 4 * k
+    lab = np.zeros((h, 16), np.uint32); lab[1:h-1, 2:9] = 3; lab[2:5, 10:15] = 7 + k
+    slides.append((rng.integers(1, 100, (h, 16)).astype(np.uint32), lab))
+def fake_featurize(inten, label):       # stands in for Engine.featurize: [label, t_index, area, sum]
+    rows = []
+    for l in np.unique(label[label > 0]):
+        m = label == l
+        rows.append([float(l), 0.0, float(m.sum()), float(inten[m].sum())])
+    return np.array(rows)
+res = featurize_sharded(slides, fake_featurize, rank, world)
+if rank == 0:
+    tab, idx = res
+    exp = np.concatenate([fake_featurize(*s) for s in slides])
+    exp_idx = np.concatenate([np.full(2, i) for i in range(5)])
+    assert np.array_equal(tab, exp) and np.array_equal(idx, exp_idx), (tab, exp)
+    print("SHARD_OK")
+else:
+    assert res is None
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_featurize_world_size_2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % {"root": ROOT})
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29517", str(script)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "SHARD_OK" in r.stdout, r.stdout + r.stderr

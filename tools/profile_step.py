@@ -1,0 +1,18 @@
+"""One resident pass of the hot path over a configs[1]-style slide -- the command wrapped by ncu (see profiles/README.md)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+from nyxus_b200 import Engine, synth
+
+size = int(sys.argv[1]) if len(sys.argv) > 1 else 10000
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+feats = sys.argv[3].split(",") if len(sys.argv) > 3 else ["*ALL_TEXTURE*", "*ALL_INTENSITY*"]
+inten, label = synth.config2(seed=2, size=size)
+d_int = torch.from_numpy(inten).cuda()
+d_lab = torch.from_numpy(label.view(np.int32)).cuda()
+eng = Engine(feats)
+H, W = inten.shape
+for _ in range(steps):
+    tab, _ = eng.featurize_ptr(d_int.data_ptr(), True, d_lab.data_ptr(), 1, H, W, on_device=True)
+print(tab.shape, {k: round(v, 3) for k, v in eng.timings().items()})
