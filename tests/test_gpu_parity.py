@@ -165,13 +165,18 @@ def test_empty_mask_and_montage_and_selection():
         nyx.featurize(I, L[:, :16])
 
 
-def test_negative_intensities_are_shifted_in_place_like_the_reference():
+def test_negative_intensities_are_shifted_like_the_reference():
     from nyxus_b200 import Nyxus
     nyx = Nyxus(["MIN", "MAX"])
     I = np.array([[-5, 1, 2], [3, 4, 5], [6, 7, 8]], np.int32)
     L = np.ones((3, 3), np.uint32)
     df = nyx.featurize(I, L)
-    assert df.MIN[0] == 0 and df.MAX[0] == 13 and I.min() == 0          # nyxus.py:481-484 mutates the caller's array
+    # 2D input is wrapped by np.array([..]) (a copy, nyxus.py:447) so the caller's array keeps its values ...
+    assert df.MIN[0] == 0 and df.MAX[0] == 13 and I.min() == -5
+    # ... while a 3D stack is shifted IN PLACE (nyxus.py:481-484)
+    I3 = I[None].copy()
+    df = nyx.featurize(I3, L[None])
+    assert df.MIN[0] == 0 and df.MAX[0] == 13 and I3.min() == 0
 
 
 def test_label_table_growth_and_limit(eng64):
