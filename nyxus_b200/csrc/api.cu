@@ -364,7 +364,7 @@ size_t family_words (int fam, bool p16, int Lmax, uint32_t maxcells, int maxwh)
 	switch (fam)
 	{
 	case FAM_GLCM: return p16 ? glcm_smem_words<true> (Lmax, 4) : glcm_smem_words<false> (Lmax, 4);
-	case FAM_GLRLM: return glrlm_smem_words (Lmax, maxwh);
+	case FAM_GLRLM: return glrlm_smem_words (Lmax, maxwh, (int)maxcells);
 	case FAM_GLDZM: return gldzm_smem_words ((int)maxcells, maxwh);
 	case FAM_GLSZM: return glszm_smem_words ((int)maxcells);
 	case FAM_GLDM: return gldm_smem_words (Lmax);
@@ -392,6 +392,7 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 		grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 2);
 		CU (ctx->d_scratch.reserve ((size_t)grid * famw));
 		gs = ctx->d_scratch.p;
+		CU (cudaMemsetAsync (gs, 0, (size_t)grid * famw * 4, ctx->stream));	// bodies expect (and leave) an all-zero region
 	}
 	auto kern = k_roi_family<FAM, P16>;
 	if (set_smem (ctx, kern, smem_words * 4))

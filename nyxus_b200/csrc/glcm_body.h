@@ -9,11 +9,20 @@
 //   features             :546-1202   (each formula is annotated below)
 //   _AVE                 :1205-1214
 //
-// B200 design: one CTA per ROI.  The joint counts and the four integer marginals (row, column, sum, difference) are
-// built by shared-memory integer atomics in ONE pass over the tile -- integers make the result order-independent and
-// therefore run-to-run deterministic.  Every feature that only needs a marginal is evaluated over <= 2*Ng entries;
-// only ASM / entropy / HXY1 / correlation's cross term / autocorrelation / max need the joint cells, and HXY2 needs
-// the outer product of the non-empty marginals (reference :905-911).  All sums are FP64 with a fixed reduction tree.
+// B200 design: one CTA per ROI, ONE WARP PER ANGLE (the four directions are independent after the tile load, so the
+// only block-wide barriers are the ones around the tile).  Per angle:
+//   pass 1  every (cell, neighbour) pair bumps the joint counter and the four integer marginals (row, column, sum,
+//           difference) with shared-memory integer atomics -- integers make the matrix order-independent, hence
+//           run-to-run deterministic; the integer first/second moments are accumulated per pair in registers.
+//   margin  one sweep over <= 2*Ng marginal entries gives px/py, every marginal-only feature, and (by ballot
+//           compaction) the lists of non-empty marginal levels.
+//   pass 2  "owner computes": every pair re-reads the count of ITS joint cell and adds that cell's term divided by
+//           the count, so  sum_cells f(cnt) == sum_pairs f(cnt)/cnt  needs no sweep over the Ng x Ng matrix
+//           (ASM and autocorrelation stay exact integers; the entropies become (1/N) sum_pairs log(p_cell)).
+//   pass 3  every pair zeroes its cell again: the matrix region is zero on entry AND on exit, so nothing of size
+//           Ng^2 is ever cleared or scanned per ROI (the reference's cost is ~35 dense Ng^2 loops per angle).
+//   HXY2    the outer product of the NON-EMPTY marginals only (reference :905-911).
+// All FP64 sums use fixed lane assignments and shuffle trees => deterministic.
 #pragma once
 #include "nyx_common.h"
 #include "nyx_features.h"
@@ -35,19 +44,31 @@ template <bool P16> struct Counters
 	NYX_D uint32_t get (int idx) const
 	{
 		if (P16)
-			return (w[idx >> 1] >> ((idx & 1) * 16)) & 0xFFFFu;
+			return ((const uint16_t*)w)[idx];
 		return w[idx];
+	}
+	NYX_D void clear (int idx) const
+	{
+		if (P16)
+			((uint16_t*)w)[idx] = 0;
+		else
+			w[idx] = 0;
 	}
 	static NYX_HD size_t words (size_t ncells) { return P16 ? (ncells + 1) / 2 : ncells; }
 };
 
+// 32-bit words of one angle's region: joint + R,C,SPM (Ng each) + SPP (2Ng) [+pad] + px,py (doubles) + 2 level lists (u16)
+template <bool P16> NYX_HD size_t glcm_angle_words (int Ng)
+{
+	size_t ints = Counters<P16>::words ((size_t)Ng * Ng) + (size_t)Ng * 5;
+	ints += ints & 1;
+	return ints + (size_t)Ng * 4 + (size_t)Ng + (Ng & 1);
+}
+
 // shared-memory words needed by glcm_body for `na` angles held at once
 template <bool P16> NYX_HD size_t glcm_smem_words (int Ng, int na)
 {
-	size_t joint = Counters<P16>::words ((size_t)Ng * Ng);
-	size_t marg = (size_t)Ng * 5;			// R, C, SPM (Ng each) + SPP (2Ng)
-	size_t pxy = (size_t)Ng * 2 * 2;		// px, py as doubles
-	return (size_t)na * (joint + marg + pxy);
+	return (size_t)na * glcm_angle_words<P16> (Ng);
 }
 
 struct GlcmDebug
@@ -55,13 +76,304 @@ struct GlcmDebug
 	uint32_t* joint;	// [4][Ng*Ng] dense dump (row = centre level-1, col = neighbour level-1), may be null
 };
 
-// out: NCOL_GLCM doubles of this ROI (angled block then _AVE block)
+constexpr double INV_LOG10_2 = 1.0 / LOG10_2;
+
+// One angle, one warp-wide context g.  reg: this angle's region (all integer words zero on entry and on exit).
 template <bool P16>
-NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Ng,
+NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* reg, int Ng,
 	double* out, const GlcmDebug* dbg)
 {
 	const int w = r.w, h = r.h, ncell = w * h;
 	const double softnan = prm.softnan;
+	const size_t jw = Counters<P16>::words ((size_t)Ng * Ng);
+	Counters<P16> J { reg };
+	uint32_t* Rm = reg + jw;		// [Ng]   row marginal (centre level)
+	uint32_t* Cm = Rm + Ng;			// [Ng]   column marginal (neighbour level)
+	uint32_t* SPM = Cm + Ng;		// [Ng]   |r-c| marginal
+	uint32_t* SPP = SPM + Ng;		// [2Ng]  r+c marginal
+	size_t ints = jw + (size_t)Ng * 5;
+	ints += ints & 1;
+	double* px = (double*)(reg + ints);	// [Ng] = C/N	(glcm.cpp:859-864: px[i] += P.xy(i,j) -> column marginal)
+	double* py = px + Ng;			// [Ng] = R/N
+	uint16_t* lx = (uint16_t*)(py + Ng);	// [Ng] non-empty columns
+	uint16_t* ly = lx + Ng;			// [Ng] non-empty rows
+
+	const int o = prm.glcm_offset;
+	const int dx = a == 2 ? 0 : (a == 3 ? -o : o), dy = a == 0 ? 0 : o;	// glcm.cpp:234-251
+	const bool sym = prm.glcm_symmetric || prm.ibsi;
+	FastDiv fw;
+	fw.init ((uint32_t)w);
+
+	// ---- pass 1: build (glcm.cpp:431-478) + integer moments per pair
+	enum { Q_N, Q_R, Q_C, Q_D, Q_D2, Q_S, Q_RC, Q_CNT };
+	unsigned long long q[Q_CNT];
+	for (int k = 0; k < Q_CNT; k++)
+		q[k] = 0;
+	for (int i = g.tid; i < ncell; i += g.nthr)
+	{
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_NZ))
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), col = i - row * w;
+		const int r2 = row + dy, c2 = col + dx;
+		if (r2 >= h || c2 < 0 || c2 >= w)
+			continue;
+		const uint32_t nc = cell[r2 * w + c2];
+		if (!(nc & CELL_NZ))
+			continue;
+		const int b = (int)(cc & CELL_LEVEL) - 1, av = (int)(nc & CELL_LEVEL) - 1;
+		const int d = av > b ? av - b : b - av;
+		const unsigned long long lb = (unsigned long long)(b + 1), la = (unsigned long long)(av + 1), ld = (unsigned long long)d;
+		J.inc (g, b * Ng + av);
+		atom_add (g, Rm + b, 1u);
+		atom_add (g, Cm + av, 1u);
+		if (sym)
+		{
+			J.inc (g, av * Ng + b);
+			atom_add (g, Rm + av, 1u);
+			atom_add (g, Cm + b, 1u);
+			atom_add (g, SPM + d, 2u);
+			atom_add (g, SPP + av + b, 2u);
+			q[Q_N] += 2;
+			q[Q_R] += lb + la;
+			q[Q_C] += lb + la;
+			q[Q_D] += 2 * ld;
+			q[Q_D2] += 2 * ld * ld;
+			q[Q_S] += 2 * (lb + la);
+			q[Q_RC] += 2 * lb * la;
+		}
+		else
+		{
+			atom_add (g, SPM + d, 1u);
+			atom_add (g, SPP + av + b, 1u);
+			q[Q_N] += 1;
+			q[Q_R] += lb;		// sum_r R[r] * I[r]
+			q[Q_C] += la;		// sum_c C[c] * I[c]
+			q[Q_D] += ld;		// sum_k k * Pxmy[k]
+			q[Q_D2] += ld * ld;	// sum_k k^2 * Pxmy[k]
+			q[Q_S] += lb + la;	// sum_k (I_x + I_y) * Pxpy[k]
+			q[Q_RC] += lb * la;	// sum cnt * I_r * I_c
+		}
+	}
+	g.sync();
+	cta_sum_u64<Q_CNT> (g, q);	// q[Q_N] = sum_p of this angle (glcm.cpp:480-484)
+
+	if (dbg && dbg->joint)
+		for (int i = g.tid; i < Ng * Ng; i += g.nthr)
+			dbg->joint[(size_t)a * Ng * Ng + i] = J.get (i);
+
+	if (!q[Q_N])	// glcm.cpp:260-295 (nothing was counted: the region is still all zero)
+	{
+		for (int f = g.tid; f < G_NANGLED; f += g.nthr)
+			out[f * 4 + a] = softnan;
+		return;
+	}
+	const double N = (double)q[Q_N];
+	const double mr = (double)q[Q_R] / N;		// f_corr mr (:598-603), f_var mean (:657-665), JAVE (:1140-1146)
+	const double mc = (double)q[Q_C] / N;		// f_corr mc (:605-610), by_row_mean (:531-536)
+	const double diffavg = (double)q[Q_D] / N;	// f_difference_avg (:786-795), DIS (:1050-1052)
+	// Ng of THIS ROI: MATLAB = grey depth; IBSI = max level of the tile = aux_max (glcm.cpp:412-419).
+	// (the `Ng` argument may be a class-wide storage bound in IBSI mode)
+	const double NgD = prm.ibsi ? (double)r.imax : (double)Ng;
+
+	// ---- marginal sweep: px/py, marginal-only features, lists of the non-empty levels
+	enum { M_S2R, M_S2C, M_JVAR, M_HX, M_IDM, M_ID, M_IDN, M_IDMN, M_IV, M_DENT, M_DVAR, M_SENT, M_CP, M_CS, M_CT, M_N };
+	double m[M_N];
+	for (int k = 0; k < M_N; k++)
+		m[k] = 0;
+	int nx = 0, ny = 0;
+	for (int base = 0; base < 2 * Ng; base += g.nthr)
+	{
+		const int k = base + g.tid;
+		uint32_t cv = 0, rv = 0;
+		if (k < Ng)
+		{
+			cv = Cm[k];
+			rv = Rm[k];
+			const double lv = (double)(k + 1);
+			const double pc = (double)cv / N, pr = (double)rv / N;
+			px[k] = pc;
+			py[k] = pr;
+			const double dr = lv - mr, dc = lv - mc;
+			m[M_S2R] += pr * dr * dr;			// :612-618, f_var :667-675
+			m[M_S2C] += pc * dc * dc;			// :621-627
+			m[M_JVAR] += dr * dr * pc;			// :1194-1200 (column marginal, row-marginal mean)
+			if (cv)
+				m[M_HX] += dmul (pc, fast_log10 (dadd (pc, GLCM_EPSILON)));	// :873-876
+			const uint32_t dv = SPM[k];
+			if (dv)
+			{
+				const double pm = (double)dv / N, kd = (double)k;
+				m[M_IDM] += pm / (1.0 + kd * kd);		// :685-687, HOM2 :1069
+				m[M_ID] += pm / (1.0 + kd);			// :1096-1097, HOM1 :942
+				m[M_IDN] += pm / (1.0 + kd / NgD);		// :1110-1111
+				m[M_IDMN] += pm / (1.0 + (kd * kd) / (NgD * NgD));	// :1082-1084
+				if (k >= 1)
+					m[M_IV] += pm / (kd * kd);		// :1123-1128
+				m[M_DENT] += dmul (pm, fast_log10 (dadd (pm, GLCM_EPSILON)));	// :778-781
+				const double dd = kd - diffavg;
+				m[M_DVAR] += dd * dd * pm;			// :753-765
+			}
+		}
+		if (k < 2 * Ng)
+		{
+			const uint32_t sv = SPP[k];
+			if (sv)
+			{
+				const double pp = (double)sv / N;
+				m[M_SENT] += dmul (pp, fast_log10 (dadd (pp, GLCM_EPSILON)));	// :712-716
+				const double mm = (double)(k + 2) - mc - mc;
+				m[M_CT] += mm * mm * pp;				// :1028-1036
+				m[M_CS] += mm * mm * mm * pp;				// :1001-1009
+				m[M_CP] += mm * mm * mm * mm * pp;			// :979-987
+			}
+		}
+		const unsigned bx = g.ballot (cv != 0), by = g.ballot (rv != 0);
+		if (cv)
+			lx[nx + popc32 (bx & g.lanemask_lt())] = (uint16_t)k;
+		if (rv)
+			ly[ny + popc32 (by & g.lanemask_lt())] = (uint16_t)k;
+		nx += popc32 (bx);
+		ny += popc32 (by);
+	}
+	g.sync();	// px/py/lx/ly visible
+	cta_sum<M_N> (g, m);
+
+	// ---- pass 2: owner-computes terms of the joint cells
+	unsigned long long s_asm = 0, jmax = 0;
+	double jd[3] = { 0, 0, 0 };	// sum log(p_cell), sum log(px*py), sum (r-mr)(c-mc)
+	for (int i = g.tid; i < ncell; i += g.nthr)
+	{
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_NZ))
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), col = i - row * w;
+		const int r2 = row + dy, c2 = col + dx;
+		if (r2 >= h || c2 < 0 || c2 >= w)
+			continue;
+		const uint32_t nc = cell[r2 * w + c2];
+		if (!(nc & CELL_NZ))
+			continue;
+		const int b = (int)(cc & CELL_LEVEL) - 1, av = (int)(nc & CELL_LEVEL) - 1;
+		const unsigned long long cnt = J.get (b * Ng + av);
+		const double p = (double)cnt / N;
+		const double l1 = fast_log10 (dadd (p, GLCM_EPSILON));					// HXY (glcm.cpp:868, 734-735, 1160-1161)
+		const double l2 = fast_log10 (dadd (dmul (px[av], py[b]), GLCM_EPSILON));		// HXY1 (:869)
+		double cr = ((double)(b + 1) - mr) * ((double)(av + 1) - mc);				// (:633)
+		if (sym)
+		{
+			// the mirrored cell (av,b) holds the same count; px == py
+			s_asm += 2 * cnt;
+			jd[0] += l1 + l1;
+			jd[1] += l2 + fast_log10 (dadd (dmul (px[b], py[av]), GLCM_EPSILON));
+			cr += ((double)(av + 1) - mr) * ((double)(b + 1) - mc);
+		}
+		else
+		{
+			s_asm += cnt;
+			jd[0] += l1;
+			jd[1] += l2;
+		}
+		jd[2] += cr;
+		jmax = cnt > jmax ? cnt : jmax;
+	}
+	{
+		unsigned long long t[1] = { s_asm };
+		cta_sum_u64<1> (g, t);	// (its shuffles/barrier also order pass 2's reads before pass 3's stores)
+		s_asm = t[0];
+	}
+	cta_sum<3> (g, jd);
+	jmax = cta_max_u64 (g, jmax);
+	g.sync();
+
+	// ---- pass 3: restore the all-zero region
+	for (int i = g.tid; i < ncell; i += g.nthr)
+	{
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_NZ))
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), col = i - row * w;
+		const int r2 = row + dy, c2 = col + dx;
+		if (r2 >= h || c2 < 0 || c2 >= w)
+			continue;
+		const uint32_t nc = cell[r2 * w + c2];
+		if (!(nc & CELL_NZ))
+			continue;
+		const int b = (int)(cc & CELL_LEVEL) - 1, av = (int)(nc & CELL_LEVEL) - 1;
+		J.clear (b * Ng + av);
+		if (sym)
+			J.clear (av * Ng + b);
+	}
+	for (int k = g.tid; k < 5 * Ng; k += g.nthr)
+		Rm[k] = 0;
+
+	// ---- HXY2 over the outer product of the non-empty marginals (glcm.cpp:905-911)
+	double hxy2[1] = { 0 };
+	{
+		const int tot = nx * ny;
+		FastDiv fy;
+		fy.init ((uint32_t)(ny > 0 ? ny : 1));
+		for (int k = g.tid; k < tot; k += g.nthr)
+		{
+			const int ii = (int)fy.div ((uint32_t)k), jj = k - ii * ny;
+			const double qv = dmul (px[lx[ii]], py[ly[jj]]);
+			hxy2[0] += dmul (qv, fast_log10 (dadd (qv, GLCM_EPSILON)));
+		}
+	}
+	cta_sum<1> (g, hxy2);
+	g.sync();	// the region (incl. px/py/lists) may be reused by the next ROI
+
+	// ---- features of this angle
+	const double sc_log = INV_LOG10_2;		// x / LOG10_2 (glcm.h:241) applied once per sum
+	const double HXY = jd[0] / N * sc_log, HX = m[M_HX] * sc_log;
+	double HXY1 = jd[1] / N * sc_log, HXY2 = hxy2[0] * sc_log;
+	// A single non-empty row or column makes every p(i,j) EXACTLY px(i)*py(j): the reference then sums identical terms
+	// for HXY, HXY1 and HXY2 and gets HXY - HXY2 == 0 exactly (INFOMEAS2 = 0, not sqrt(1e-16)); keep that identity.
+	if (nx == 1 || ny == 1)
+		HXY1 = HXY2 = HXY;
+	double f[G_NANGLED];
+	f[G_ASM] = (double)s_asm / (N * N);				// :546-558  (sum cnt^2 == sum over pairs of cnt)
+	f[G_ENERGY] = f[G_ASM];						// :916-932
+	f[G_ACOR] = (double)q[Q_RC] / N;				// :947-966
+	f[G_CLUPROM] = m[M_CP];
+	f[G_CLUSHADE] = m[M_CS];
+	f[G_CLUTEND] = m[M_CT];
+	f[G_SUMVARIANCE] = m[M_CT];					// :324-326
+	f[G_CONTRAST] = (double)q[Q_D2] / N;				// :566-584
+	const double sr = sqrt (m[M_S2R]), sc = sqrt (m[M_S2C]), den = sr * sc;
+	f[G_CORRELATION] = (den > 0.0) ? (jd[2] / N) / den : softnan;	// :637-643
+	f[G_DIFAVE] = diffavg;
+	f[G_DIFENTRO] = -m[M_DENT] * sc_log;
+	f[G_DIFVAR] = m[M_DVAR];
+	f[G_DIS] = diffavg;
+	f[G_ENTROPY] = -HXY;						// :722-739
+	f[G_JE] = -HXY;							// :1149-1165
+	f[G_HOM1] = m[M_ID];
+	f[G_HOM2] = m[M_IDM];
+	f[G_ID] = m[M_ID];
+	f[G_IDN] = m[M_IDN];
+	f[G_IDM] = m[M_IDM];
+	f[G_IDMN] = m[M_IDMN];
+	const double im1 = (HXY - HXY1) / HX;				// :880-883
+	f[G_INFOMEAS1] = (isnan (im1) || isinf (im1)) ? softnan : im1;
+	f[G_INFOMEAS2] = sqrt (fabs (1.0 - exp (-2.0 * (-HXY2 + HXY))));	// :913
+	f[G_IV] = m[M_IV];
+	f[G_JAVE] = mr;
+	f[G_JMAX] = (double)jmax / N;					// :1167-1183
+	f[G_JVAR] = m[M_JVAR];
+	f[G_SUMAVERAGE] = (double)q[Q_S] / N;				// :693-704
+	f[G_SUMENTROPY] = -m[M_SENT] * sc_log;
+	f[G_VARIANCE] = m[M_S2R];					// :647-676
+	if (g.tid == 0)
+		for (int k = 0; k < G_NANGLED; k++)
+			out[k * 4 + a] = f[k];
+}
+
+// out: NCOL_GLCM doubles of this ROI (angled block then _AVE block).  mem: 4 angle regions, zero on entry and exit.
+template <bool P16>
+NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Ng,
+	double* out, const GlcmDebug* dbg)
+{
 	constexpr int NA = 4;
 	const int ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
 
@@ -72,252 +384,14 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 		if (Bm.bin (r.imin) == Bm.bin (r.imax))
 		{
 			for (int i = c.tid; i < NCOL_GLCM; i += c.nthr)
-				out[i] = softnan;
+				out[i] = prm.softnan;
 			return;
 		}
 	}
-
-	// ---- carve shared memory
-	const size_t jw = Counters<P16>::words ((size_t)Ng * Ng);
-	uint32_t* jointw = mem;				// [NA][jw]
-	uint32_t* Rm = jointw + NA * jw;		// [NA][Ng]   row marginal (centre level)
-	uint32_t* Cm = Rm + NA * Ng;			// [NA][Ng]   column marginal (neighbour level)
-	uint32_t* SPM = Cm + NA * Ng;			// [NA][Ng]   |r-c| marginal
-	uint32_t* SPP = SPM + NA * Ng;			// [NA][2Ng]  r+c marginal
-	double* px = (double*)(SPP + NA * 2 * Ng);	// [NA][Ng] = C/N	(glcm.cpp:859-864: px[i] += P.xy(i,j) -> column marginal)
-	double* py = px + NA * Ng;			// [NA][Ng] = R/N
-	const size_t nwords = NA * (jw + 5 * (size_t)Ng);
-	for (size_t i = c.tid; i < nwords; i += c.nthr)
-		mem[i] = 0;
-	c.sync();
-
-	// ---- build (glcm.cpp:431-478)
-	const int o = prm.glcm_offset;
-	const int dxs[NA] = { o, o, 0, -o }, dys[NA] = { 0, o, o, o };
-	const bool sym = prm.glcm_symmetric || prm.ibsi;
-	unsigned long long npair[NA] = { 0, 0, 0, 0 };
-	for (int i = c.tid; i < ncell; i += c.nthr)
-	{
-		uint32_t cc = cell[i];
-		if (!(cc & CELL_NZ))
-			continue;
-		int row = i / w, col = i - row * w;
-		int b = (int)(cc & CELL_LEVEL) - 1;
-#pragma unroll
-		for (int a = 0; a < NA; a++)
-		{
-			int r2 = row + dys[a], c2 = col + dxs[a];
-			if (r2 < 0 || r2 >= h || c2 < 0 || c2 >= w)
-				continue;
-			uint32_t nc = cell[r2 * w + c2];
-			if (!(nc & CELL_NZ))
-				continue;
-			int av = (int)(nc & CELL_LEVEL) - 1;
-			Counters<P16> J { jointw + a * jw };
-			int d = av > b ? av - b : b - av;
-			J.inc (c, b * Ng + av);
-			atom_add (c, Rm + a * Ng + b, 1u);
-			atom_add (c, Cm + a * Ng + av, 1u);
-			if (sym)
-			{
-				J.inc (c, av * Ng + b);
-				atom_add (c, Rm + a * Ng + av, 1u);
-				atom_add (c, Cm + a * Ng + b, 1u);
-				atom_add (c, SPM + a * Ng + d, 2u);
-				atom_add (c, SPP + a * 2 * Ng + av + b, 2u);
-				npair[a] += 2;
-			}
-			else
-			{
-				atom_add (c, SPM + a * Ng + d, 1u);
-				atom_add (c, SPP + a * 2 * Ng + av + b, 1u);
-				npair[a] += 1;
-			}
-		}
-	}
-	c.sync();
-	cta_sum_u64<NA> (c, npair);	// sum_p per angle (glcm.cpp:480-484)
-
-	if (dbg && dbg->joint)
-		for (int a = 0; a < NA; a++)
-		{
-			Counters<P16> J { jointw + a * jw };
-			for (int i = c.tid; i < Ng * Ng; i += c.nthr)
-				dbg->joint[(size_t)a * Ng * Ng + i] = J.get (i);
-		}
-
-	// ---- integer first moments of the marginals + px/py
-	unsigned long long im[NA * 5];
-	for (int k = 0; k < NA * 5; k++)
-		im[k] = 0;
-	for (int a = 0; a < NA; a++)
-	{
-		const double N = (double)npair[a];
-		for (int k = c.tid; k < 2 * Ng; k += c.nthr)
-		{
-			if (k < Ng)
-			{
-				unsigned long long rv = Rm[a * Ng + k], cv = Cm[a * Ng + k], dv = SPM[a * Ng + k];
-				im[a * 5 + 0] += rv * (unsigned long long)(k + 1);		// sum R[r]*I[r]
-				im[a * 5 + 1] += cv * (unsigned long long)(k + 1);		// sum C[c]*I[c]
-				im[a * 5 + 2] += dv * (unsigned long long)k;			// sum k*Pxmy
-				im[a * 5 + 3] += dv * (unsigned long long)k * (unsigned long long)k;	// sum k^2*Pxmy
-				px[a * Ng + k] = npair[a] ? (double)cv / N : 0.0;
-				py[a * Ng + k] = npair[a] ? (double)rv / N : 0.0;
-			}
-			im[a * 5 + 4] += (unsigned long long)SPP[a * 2 * Ng + k] * (unsigned long long)(k + 2);	// sum (I_x+I_y)*Pxpy
-		}
-	}
-	cta_sum_u64<NA * 5> (c, im);	// (also orders the px/py writes before the reads below)
-
-	// ---- joint-cell pass: ASM, ACOR, JMAX (exact integers), HXY, HXY1, correlation cross term (FP64)
-	unsigned long long ji[NA * 2];
-	double jd[NA * 3];
-	unsigned long long jmax[NA];
-	for (int a = 0; a < NA; a++)
-	{
-		ji[a * 2] = ji[a * 2 + 1] = 0;
-		jd[a * 3] = jd[a * 3 + 1] = jd[a * 3 + 2] = 0;
-		jmax[a] = 0;
-		if (!npair[a])
-			continue;
-		const double N = (double)npair[a];
-		const double mr = (double)im[a * 5 + 0] / N, mc = (double)im[a * 5 + 1] / N;
-		Counters<P16> J { jointw + a * jw };
-		for (int i = c.tid; i < Ng * Ng; i += c.nthr)
-		{
-			unsigned long long cnt = J.get (i);
-			if (!cnt)
-				continue;
-			int rr = i / Ng, cl = i - rr * Ng;
-			ji[a * 2] += cnt * cnt;
-			ji[a * 2 + 1] += cnt * (unsigned long long)(rr + 1) * (unsigned long long)(cl + 1);
-			jmax[a] = cnt > jmax[a] ? cnt : jmax[a];
-			double p = (double)cnt / N;
-			jd[a * 3] += plogp (p, GLCM_EPSILON);									// HXY (glcm.cpp:868, 734-735, 1160-1161)
-			jd[a * 3 + 1] += ddiv (dmul (p, fast_log10 (dadd (dmul (px[a * Ng + cl], py[a * Ng + rr]), GLCM_EPSILON))), LOG10_2);	// HXY1 (:869)
-			jd[a * 3 + 2] += ((double)(rr + 1) - mr) * ((double)(cl + 1) - mc) * p;				// (:633)
-		}
-	}
-	cta_sum_u64<NA * 2> (c, ji);
-	cta_sum<NA * 3> (c, jd);
-	for (int a = 0; a < NA; a++)
-		jmax[a] = cta_max_u64 (c, jmax[a]);
-
-	// ---- HXY2 over the outer product of the marginals (glcm.cpp:905-911)
-	double hxy2[NA] = { 0, 0, 0, 0 };
-	for (int a = 0; a < NA; a++)
-	{
-		if (!npair[a])
-			continue;
-		for (int i = c.tid; i < Ng * Ng; i += c.nthr)
-		{
-			int ii = i / Ng, jj = i - ii * Ng;
-			double pxi = px[a * Ng + ii], pyj = py[a * Ng + jj];
-			if (pxi == 0 || pyj == 0)
-				continue;
-			hxy2[a] += plogp (dmul (pxi, pyj), GLCM_EPSILON);
-		}
-	}
-	cta_sum<NA> (c, hxy2);
-
-	// ---- marginal pass, one angle at a time
-	for (int a = 0; a < NA; a++)
-	{
-		if (!npair[a])
-		{
-			for (int f = c.tid; f < G_NANGLED; f += c.nthr)	// glcm.cpp:260-295
-				out[f * 4 + a] = softnan;
-			continue;
-		}
-		const double N = (double)npair[a];
-		const double mr = (double)im[a * 5 + 0] / N;		// f_corr mr (:598-603), f_var mean (:657-665), JAVE (:1140-1146)
-		const double mc = (double)im[a * 5 + 1] / N;		// f_corr mc (:605-610), by_row_mean (:531-536)
-		const double diffavg = (double)im[a * 5 + 2] / N;	// f_difference_avg (:786-795), DIS (:1050-1052)
-		// Ng of THIS ROI: MATLAB = grey depth; IBSI = max level of the tile = aux_max (glcm.cpp:412-419).
-		// (the `Ng` argument may be a class-wide storage bound in IBSI mode)
-		const double NgD = prm.ibsi ? (double)r.imax : (double)Ng;
-		enum { M_S2R, M_S2C, M_JVAR, M_HX, M_IDM, M_ID, M_IDN, M_IDMN, M_IV, M_DENT, M_DVAR, M_SENT, M_CP, M_CS, M_CT, M_N };
-		double m[M_N];
-		for (int k = 0; k < M_N; k++)
-			m[k] = 0;
-		for (int k = c.tid; k < 2 * Ng; k += c.nthr)
-		{
-			if (k < Ng)
-			{
-				double lv = (double)(k + 1);
-				double pr = py[a * Ng + k], pc = px[a * Ng + k];
-				double dr = lv - mr, dc = lv - mc, dj = lv - mr;
-				m[M_S2R] += pr * dr * dr;			// :612-618, f_var :667-675
-				m[M_S2C] += pc * dc * dc;			// :621-627
-				m[M_JVAR] += dj * dj * pc;			// :1194-1200 (column marginal, row-marginal mean)
-				if (pc > 0)
-					m[M_HX] += plogp (pc, GLCM_EPSILON);	// :873-876
-				uint32_t dv = SPM[a * Ng + k];
-				if (dv)
-				{
-					double pm = (double)dv / N, kd = (double)k;
-					m[M_IDM] += pm / (1.0 + kd * kd);		// :685-687, HOM2 :1069
-					m[M_ID] += pm / (1.0 + kd);			// :1096-1097, HOM1 :942
-					m[M_IDN] += pm / (1.0 + kd / NgD);		// :1110-1111
-					m[M_IDMN] += pm / (1.0 + (kd * kd) / (NgD * NgD));	// :1082-1084
-					if (k >= 1)
-						m[M_IV] += pm / (kd * kd);		// :1123-1128
-					m[M_DENT] += plogp (pm, GLCM_EPSILON);		// :778-781
-					double dd = kd - diffavg;
-					m[M_DVAR] += dd * dd * pm;			// :753-765
-				}
-			}
-			uint32_t sv = SPP[a * 2 * Ng + k];
-			if (sv)
-			{
-				double pp = (double)sv / N;
-				m[M_SENT] += plogp (pp, GLCM_EPSILON);			// :712-716
-				double mm = (double)(k + 2) - mc - mc;
-				m[M_CT] += mm * mm * pp;				// :1028-1036
-				m[M_CS] += mm * mm * mm * pp;				// :1001-1009
-				m[M_CP] += mm * mm * mm * mm * pp;			// :979-987
-			}
-		}
-		cta_sum<M_N> (c, m);
-
-		double f[G_NANGLED];
-		f[G_ASM] = (double)ji[a * 2] / (N * N);				// :546-558
-		f[G_ENERGY] = f[G_ASM];						// :916-932
-		f[G_ACOR] = (double)ji[a * 2 + 1] / N;				// :947-966
-		f[G_CLUPROM] = m[M_CP];
-		f[G_CLUSHADE] = m[M_CS];
-		f[G_CLUTEND] = m[M_CT];
-		f[G_SUMVARIANCE] = m[M_CT];					// :324-326
-		f[G_CONTRAST] = (double)im[a * 5 + 3] / N;			// :566-584
-		double sr = sqrt (m[M_S2R]), sc = sqrt (m[M_S2C]), den = sr * sc;
-		f[G_CORRELATION] = (den > 0.0) ? jd[a * 3 + 2] / den : softnan;	// :637-643
-		f[G_DIFAVE] = diffavg;
-		f[G_DIFENTRO] = -m[M_DENT];
-		f[G_DIFVAR] = m[M_DVAR];
-		f[G_DIS] = diffavg;
-		f[G_ENTROPY] = -jd[a * 3];					// :722-739
-		f[G_JE] = -jd[a * 3];						// :1149-1165
-		f[G_HOM1] = m[M_ID];
-		f[G_HOM2] = m[M_IDM];
-		f[G_ID] = m[M_ID];
-		f[G_IDN] = m[M_IDN];
-		f[G_IDM] = m[M_IDM];
-		f[G_IDMN] = m[M_IDMN];
-		double im1 = (jd[a * 3] - jd[a * 3 + 1]) / m[M_HX];		// :880-883
-		f[G_INFOMEAS1] = (isnan (im1) || isinf (im1)) ? softnan : im1;
-		f[G_INFOMEAS2] = sqrt (fabs (1.0 - exp (-2.0 * (-hxy2[a] + jd[a * 3]))));	// :913
-		f[G_IV] = m[M_IV];
-		f[G_JAVE] = mr;
-		f[G_JMAX] = (double)jmax[a] / N;				// :1167-1183
-		f[G_JVAR] = m[M_JVAR];
-		f[G_SUMAVERAGE] = (double)im[a * 5 + 4] / N;			// :693-704
-		f[G_SUMENTROPY] = -m[M_SENT];
-		f[G_VARIANCE] = m[M_S2R];					// :647-676
-		if (c.tid == 0)
-			for (int k = 0; k < G_NANGLED; k++)
-				out[k * 4 + a] = f[k];
-	}
+	const size_t aw = glcm_angle_words<P16> (Ng);
+	const Cta g = c.sub();
+	for (int a = c.sub_id(); a < NA; a += c.sub_count())
+		glcm_angle<P16> (g, a, r, prm, cell, mem + (size_t)a * aw, Ng, out, dbg);
 	c.sync();
 
 	// ---- _AVE = ((v0+v1)+v2)+v3)/4 (glcm.cpp:1205-1214)

@@ -10,8 +10,11 @@
 //   features     :357-882   sum_p == 0 -> 0.0 (not softNaN); SRLGLE/LRHGLE/... evaluate inten*inten*j*j in 32-bit
 //                           unsigned arithmetic before widening (:717,749,781,813,844,876)
 //
-// B200 design: one CTA per ROI; every cell tests "am I a run start" for the 4 directions and walks its run; the
-// run-length matrix and both marginals are integer shared-memory histograms (order independent, deterministic).
+// B200 design: one CTA per ROI, ONE WARP PER ANGLE.  Every cell tests "am I a run start" for the warp's direction and
+// walks its run; the run-length matrix and both marginals are integer shared-memory histograms (order independent,
+// deterministic).  The reducers never sweep the Ng x Nr matrix: every feature is a sum over RUNS ("owner computes":
+// sum_cells f(P) == sum_runs f(P_run)/P_run), and each run zeroes its own matrix cell afterwards, so the matrix region
+// is all zero on entry and on exit.
 #pragma once
 #include "nyx_common.h"
 #include "nyx_features.h"
@@ -19,9 +22,14 @@
 namespace nyx
 {
 
-NYX_HD size_t glrlm_smem_words (int Lmax, int Nr)
+// words of ONE angle's region: P[Lmax][Nr] + Ri[Lmax] + Cj[Nr] (zero on entry/exit) + run length per cell (u16)
+NYX_HD size_t glrlm_angle_words (int Lmax, int Nr, int maxcells)
 {
-	return 4 * ((size_t)Lmax * Nr + Lmax + Nr);
+	return (size_t)Lmax * Nr + Lmax + Nr + ((size_t)maxcells + 1) / 2;
+}
+NYX_HD size_t glrlm_smem_words (int Lmax, int Nr, int maxcells)
+{
+	return 4 * glrlm_angle_words (Lmax, Nr, maxcells);
 }
 
 struct GlrlmDebug
@@ -29,161 +37,157 @@ struct GlrlmDebug
 	uint32_t* P;	// [4][Lmax*Nr] dense dump, may be null
 };
 
-// cell: binned tile (level | flags).  Lmax = largest possible level, Nr = max(w,h).  out: NCOL_GLRLM doubles.
+NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* reg, int Lmax,
+	int Nr, double* out, const GlrlmDebug* dbg)
+{
+	const int w = r.w, h = r.h, ncell = w * h;
+	const size_t pw = (size_t)Lmax * Nr;
+	uint32_t* P = reg;			// [Lmax][Nr]
+	uint32_t* Ri = P + pw;			// [Lmax]  runs per level
+	uint32_t* Cj = Ri + Lmax;		// [Nr]    runs per length
+	uint16_t* rl = (uint16_t*)(Cj + Nr);	// [ncell] length of the run starting at the cell (0: not a start)
+	const int dx = a == 2 ? 0 : (a == 3 ? -1 : 1), dy = a == 0 ? 0 : 1;	// E, SE, S, SW (glrlm.cpp:129-175)
+	FastDiv fw;
+	fw.init ((uint32_t)w);
+
+	// ---- pass 1: runs -> matrix + marginals + per-run integer / FP sums
+	enum { Q_SUM, Q_LRE, Q_MUI, Q_MUJ, Q_HGL, Q_NP, Q_N };
+	unsigned long long q[Q_N];
+	for (int k = 0; k < Q_N; k++)
+		q[k] = 0;
+	enum { A_SRE, A_LGL, A_SRL, A_SRH, A_LRL, A_LRH, A_N };
+	double s[A_N];
+	for (int k = 0; k < A_N; k++)
+		s[k] = 0;
+	for (int i = g.tid; i < ncell; i += g.nthr)
+	{
+		const uint32_t cc = cell[i];
+		if (cc & CELL_NZ)
+			q[Q_NP]++;
+		const uint32_t lv = cc & CELL_LEVEL;
+		int len = 0;
+		if (lv)
+		{
+			const int row = (int)fw.div ((uint32_t)i), col = i - row * w;
+			const int pr = row - dy, pc = col - dx;
+			if (!(pr >= 0 && pc >= 0 && pc < w && (cell[pr * w + pc] & CELL_LEVEL) == lv))
+			{
+				len = 1;
+				int y = row + dy, x = col + dx;
+				while (y < h && x >= 0 && x < w && (cell[y * w + x] & CELL_LEVEL) == lv)
+				{
+					len++;
+					y += dy;
+					x += dx;
+				}
+				atom_add (g, P + (size_t)(lv - 1) * Nr + (len - 1), 1u);
+				atom_add (g, Ri + (lv - 1), 1u);
+				atom_add (g, Cj + (len - 1), 1u);
+				const uint32_t i2 = lv * lv, j2 = (uint32_t)(len * len), i2j2 = lv * lv * (uint32_t)len * (uint32_t)len;	// 32-bit wrap
+				q[Q_SUM] += 1;
+				q[Q_LRE] += (unsigned long long)len * (unsigned long long)len;	// :409-415
+				q[Q_MUI] += lv;							// :598-605
+				q[Q_MUJ] += (unsigned long long)len;				// :640-646
+				q[Q_HGL] += (unsigned long long)i2;				// :744-751
+				s[A_SRE] += 1.0 / (double)(len * len);				// :381-383
+				s[A_LGL] += 1.0 / (double)i2;					// :712-719
+				s[A_SRL] += 1.0 / (double)i2j2;					// :781
+				s[A_SRH] += (double)i2 / (double)(int)j2;			// :813
+				s[A_LRL] += (double)(int)j2 / (double)i2;			// :844
+				s[A_LRH] += (double)i2j2;					// :876
+			}
+		}
+		rl[i] = (uint16_t)len;
+	}
+	g.sync();
+	cta_sum_u64<Q_N> (g, q);
+	cta_sum<A_N> (g, s);
+
+	if (dbg && dbg->P)
+		for (size_t i = g.tid; i < pw; i += g.nthr)
+			dbg->P[(size_t)a * pw + i] = P[i];
+
+	if (q[Q_SUM] == 0)	// :363-366 etc. (no run: the region is still all zero)
+	{
+		for (int f = g.tid; f < R_NANGLED; f += g.nthr)
+			out[f * 4 + a] = 0.0;
+		return;
+	}
+	const double sum = (double)q[Q_SUM], Np = (double)q[Q_NP];
+	const double mui = (double)q[Q_MUI] / sum, muj = (double)q[Q_MUJ] / sum;
+
+	// ---- pass 2: terms that need the counts (owner computes)
+	unsigned long long q2[2] = { 0, 0 };	// sum Ri^2 (:441-448), sum Cj^2 (:509-517)
+	double t[3] = { 0, 0, 0 };		// GLV, RV, RE
+	for (int i = g.tid; i < ncell; i += g.nthr)
+	{
+		const int len = rl[i];
+		if (!len)
+			continue;
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		q2[0] += Ri[lv - 1];
+		q2[1] += Cj[len - 1];
+		const double di = (double)lv - mui, dj = (double)len - muj;
+		t[0] += di * di;								// :608-616
+		t[1] += dj * dj;								// :649-656
+		const double p = (double)P[(size_t)(lv - 1) * Nr + (len - 1)] / sum;
+		t[2] += fast_log10 (dadd (p, EPS_ZONES));					// :684-685
+	}
+	cta_sum_u64<2> (g, q2);
+	cta_sum<3> (g, t);
+	g.sync();
+
+	// ---- pass 3: restore the all-zero region
+	for (int i = g.tid; i < ncell; i += g.nthr)
+	{
+		const int len = rl[i];
+		if (len)
+			P[(size_t)((cell[i] & CELL_LEVEL) - 1) * Nr + (len - 1)] = 0;
+	}
+	for (int k = g.tid; k < Lmax + Nr; k += g.nthr)
+		Ri[k] = 0;
+	g.sync();
+
+	if (g.tid == 0)
+	{
+		double f[R_NANGLED];
+		f[R_SRE] = s[A_SRE] / sum;
+		f[R_LRE] = (double)q[Q_LRE] / sum;
+		f[R_GLN] = (double)q2[0] / sum;
+		f[R_GLNN] = (double)q2[0] / (sum * sum);
+		f[R_RLN] = (double)q2[1] / sum;
+		f[R_RLNN] = (double)q2[1] / (sum * sum);
+		f[R_RP] = sum / Np;					// :573
+		f[R_GLV] = t[0] / sum;
+		f[R_RV] = t[1] / sum;
+		f[R_RE] = -(t[2] / sum) * (1.0 / LOG10_2);
+		f[R_LGLRE] = s[A_LGL] / sum;
+		f[R_HGLRE] = (double)q[Q_HGL] / sum;
+		f[R_SRLGLE] = s[A_SRL] / sum;
+		f[R_SRHGLE] = s[A_SRH] / sum;
+		f[R_LRLGLE] = s[A_LRL] / sum;
+		f[R_LRHGLE] = s[A_LRH] / sum;
+		for (int k = 0; k < R_NANGLED; k++)
+			out[k * 4 + a] = f[k];
+	}
+}
+
+// cell: binned tile (level | flags).  Lmax = largest possible level, Nr = max(w,h) bound of the launch, maxcells = cell
+// bound of the launch.  mem: 4 angle regions (zero on entry and exit).  out: NCOL_GLRLM doubles.
 NYX_D void glrlm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax, int Nr,
-	double* out, const GlrlmDebug* dbg)
+	int maxcells, double* out, const GlrlmDebug* dbg)
 {
 	constexpr int NA = 4;
-	const int w = r.w, h = r.h, ncell = w * h;
 	if (r.imin == r.imax)
 	{
 		for (int i = c.tid; i < NCOL_GLRLM; i += c.nthr)
 			out[i] = prm.softnan;
 		return;
 	}
-	const size_t pw = (size_t)Lmax * Nr;
-	uint32_t* P = mem;			// [NA][Lmax][Nr]
-	uint32_t* Ri = P + NA * pw;		// [NA][Lmax]  runs per level
-	uint32_t* Cj = Ri + NA * Lmax;		// [NA][Nr]    runs per length
-	const size_t nwords = glrlm_smem_words (Lmax, Nr);
-	for (size_t i = c.tid; i < nwords; i += c.nthr)
-		mem[i] = 0;
-	c.sync();
-
-	const int dxs[NA] = { 1, 1, 0, -1 }, dys[NA] = { 0, 1, 1, 1 };
-	unsigned long long cnt[1] = { 0 };
-	for (int i = c.tid; i < ncell; i += c.nthr)
-	{
-		uint32_t cc = cell[i];
-		if (cc & CELL_NZ)
-			cnt[0]++;
-		uint32_t lv = cc & CELL_LEVEL;
-		if (!lv)
-			continue;
-		int row = i / w, col = i - row * w;
-#pragma unroll
-		for (int a = 0; a < NA; a++)
-		{
-			int pr = row - dys[a], pc = col - dxs[a];
-			if (pr >= 0 && pc >= 0 && pc < w && (cell[pr * w + pc] & CELL_LEVEL) == lv)
-				continue;	// not a run start
-			int len = 1, y = row + dys[a], x = col + dxs[a];
-			while (y < h && x >= 0 && x < w && (cell[y * w + x] & CELL_LEVEL) == lv)
-			{
-				len++;
-				y += dys[a];
-				x += dxs[a];
-			}
-			atom_add (c, P + a * pw + (size_t)(lv - 1) * Nr + (len - 1), 1u);
-			atom_add (c, Ri + a * Lmax + (lv - 1), 1u);
-			atom_add (c, Cj + a * Nr + (len - 1), 1u);
-		}
-	}
-	c.sync();
-	cta_sum_u64<1> (c, cnt);
-	const double Np = (double)cnt[0];
-
-	if (dbg && dbg->P)
-		for (size_t i = c.tid; i < NA * pw; i += c.nthr)
-			dbg->P[i] = P[i];
-
-	for (int a = 0; a < NA; a++)
-	{
-		// ---- integer marginal sums
-		enum { Q_SUM, Q_LRE, Q_GLN, Q_RLN, Q_MUI, Q_MUJ, Q_HGL, Q_N };
-		unsigned long long q[Q_N];
-		for (int k = 0; k < Q_N; k++)
-			q[k] = 0;
-		for (int k = c.tid; k < Lmax; k += c.nthr)
-		{
-			unsigned long long v = Ri[a * Lmax + k];
-			uint32_t lv = (uint32_t)(k + 1);
-			q[Q_SUM] += v;
-			q[Q_GLN] += v * v;				// :441-448
-			q[Q_MUI] += v * lv;				// :598-605
-			q[Q_HGL] += v * (unsigned long long)(uint32_t)(lv * lv);	// :744-751
-		}
-		for (int k = c.tid; k < Nr; k += c.nthr)
-		{
-			unsigned long long v = Cj[a * Nr + k], j = (unsigned long long)(k + 1);
-			q[Q_LRE] += v * j * j;				// :409-415
-			q[Q_RLN] += v * v;				// :509-517
-			q[Q_MUJ] += v * j;				// :640-646
-		}
-		cta_sum_u64<Q_N> (c, q);
-		if (q[Q_SUM] == 0)
-		{
-			for (int f = c.tid; f < R_NANGLED; f += c.nthr)	// :363-366 etc.
-				out[f * 4 + a] = 0.0;
-			continue;
-		}
-		const double sum = (double)q[Q_SUM];
-		const double mui = (double)q[Q_MUI] / sum, muj = (double)q[Q_MUJ] / sum;
-
-		// ---- FP marginal + cell sums
-		enum { A_SRE, A_GLV, A_RV, A_RE, A_LGL, A_SRL, A_SRH, A_LRL, A_LRH, A_N };
-		double s[A_N];
-		for (int k = 0; k < A_N; k++)
-			s[k] = 0;
-		for (int k = c.tid; k < Nr; k += c.nthr)
-		{
-			uint32_t v = Cj[a * Nr + k];
-			if (!v)
-				continue;
-			int j = k + 1;
-			s[A_SRE] += (double)v / (double)(j * j);		// :381-383
-			double dj = (double)j - muj;
-			s[A_RV] += (double)v / sum * (dj * dj);			// :649-656
-		}
-		for (int k = c.tid; k < Lmax; k += c.nthr)
-		{
-			uint32_t v = Ri[a * Lmax + k];
-			if (!v)
-				continue;
-			uint32_t lv = (uint32_t)(k + 1);
-			double di = (double)lv - mui;
-			s[A_GLV] += (double)v / sum * (di * di);		// :608-616
-			s[A_LGL] += (double)v / (double)(uint32_t)(lv * lv);	// :712-719
-		}
-		for (size_t i = c.tid; i < pw; i += c.nthr)
-		{
-			uint32_t v = P[a * pw + i];
-			if (!v)
-				continue;
-			uint32_t lv = (uint32_t)(i / Nr) + 1;
-			int j = (int)(i % Nr) + 1;
-			double p = (double)v / sum;
-			s[A_RE] += dmul (p, ddiv (fast_log10 (dadd (p, EPS_ZONES)), LOG10_2));	// :684-685
-			uint32_t i2 = lv * lv, j2 = (uint32_t)(j * j), i2j2 = lv * lv * (uint32_t)j * (uint32_t)j;
-			s[A_SRL] += (double)v / (double)i2j2;					// :781
-			s[A_SRH] += (double)v * (double)i2 / (double)(int)j2;			// :813
-			s[A_LRL] += (double)v * (double)(int)j2 / (double)i2;			// :844
-			s[A_LRH] += (double)v * (double)i2j2;					// :876
-		}
-		cta_sum<A_N> (c, s);
-		if (c.tid == 0)
-		{
-			double f[R_NANGLED];
-			f[R_SRE] = s[A_SRE] / sum;
-			f[R_LRE] = (double)q[Q_LRE] / sum;
-			f[R_GLN] = (double)q[Q_GLN] / sum;
-			f[R_GLNN] = (double)q[Q_GLN] / (sum * sum);
-			f[R_RLN] = (double)q[Q_RLN] / sum;
-			f[R_RLNN] = (double)q[Q_RLN] / (sum * sum);
-			f[R_RP] = sum / Np;					// :573
-			f[R_GLV] = s[A_GLV];
-			f[R_RV] = s[A_RV];
-			f[R_RE] = -s[A_RE];
-			f[R_LGLRE] = s[A_LGL] / sum;
-			f[R_HGLRE] = (double)q[Q_HGL] / sum;
-			f[R_SRLGLE] = s[A_SRL] / sum;
-			f[R_SRHGLE] = s[A_SRH] / sum;
-			f[R_LRLGLE] = s[A_LRL] / sum;
-			f[R_LRHGLE] = s[A_LRH] / sum;
-			for (int k = 0; k < R_NANGLED; k++)
-				out[k * 4 + a] = f[k];
-		}
-	}
+	const size_t aw = glrlm_angle_words (Lmax, Nr, maxcells);
+	const Cta g = c.sub();
+	for (int a = c.sub_id(); a < NA; a += c.sub_count())
+		glrlm_angle (g, a, r, prm, cell, mem + (size_t)a * aw, Lmax, Nr, out, dbg);
 	c.sync();
 	for (int k = c.tid; k < R_NANGLED; k += c.nthr)		// glrlm.cpp:336-351, 902-909
 	{

@@ -459,6 +459,11 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family (ImageView im, const
 	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
 	uint32_t* cell = smem + RED_WORDS;
 	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : cell + ((maxcells + 1) & ~1u);
+	// the family region is all zero on entry of every body and every body leaves it all zero again (owner-zeroing):
+	// cleared here once per CTA (the global scratch slots are cleared by the host before the launch)
+	if (!gscratch)
+		for (size_t i = threadIdx.x; i < gwords; i += blockDim.x)
+			mem[i] = 0;
 	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
 	{
 		const uint32_t ri = list ? list[k] : k;
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family (ImageView im, const
 		else if (FAM == FAM_GLRLM)
 		{
 			GlrlmDebug d { dbg.u32 };
-			glrlm_body (c, r, prm, cell, mem, Lmax, maxwh, o + COL_GLRLM, dbg.u32 ? &d : nullptr);
+			glrlm_body (c, r, prm, cell, mem, Lmax, maxwh, (int)maxcells, o + COL_GLRLM, dbg.u32 ? &d : nullptr);
 		}
 		else if (FAM == FAM_GLDZM)
 		{

@@ -208,13 +208,59 @@ constexpr uint32_t CELL_LEVEL = 0x00FFFFFFu;
 struct Cta
 {
 	int tid, nthr;
-	double* red;	// reduction scratch: RED_MAX * NW_MAX doubles
+	double* red;	// reduction scratch: RED_MAX * NW_MAX doubles (unused by a warp-wide context)
+	int wmode = 0;	// 1: this context is ONE full warp (nthr == 32): sync = __syncwarp, reductions by shuffles only
 
 #if NYX_DEVICE_BUILD
-	NYX_D void sync() const { __syncthreads(); }
+	NYX_D void sync() const
+	{
+		if (wmode)
+			__syncwarp();
+		else
+			__syncthreads();
+	}
+	// sub-groups: the warps of this context (a warp-wide context is its own single sub-group)
+	NYX_D int sub_id() const { return wmode ? 0 : (tid >> 5); }
+	NYX_D int sub_count() const { return wmode ? 1 : ((nthr + 31) >> 5); }
+	NYX_D Cta sub() const { return Cta { tid & 31, 32, red, 1 }; }
+	NYX_D unsigned ballot (bool p) const { return __ballot_sync (0xffffffffu, p); }	// sub-group (warp) contexts only
+	NYX_D unsigned lanemask_lt() const { return (1u << (tid & 31)) - 1u; }
 #else
 	inline void sync() const {}
+	inline int sub_id() const { return 0; }
+	inline int sub_count() const { return 1; }
+	inline Cta sub() const { return *this; }
+	inline unsigned ballot (bool p) const { return p ? 1u : 0u; }
+	inline unsigned lanemask_lt() const { return 0u; }
 #endif
+};
+
+NYX_HD int popc32 (unsigned v)
+{
+#ifdef __CUDA_ARCH__
+	return __popc (v);
+#else
+	return __builtin_popcount (v);
+#endif
+}
+
+// exact n / d for n * d < 2^32 by one multiply-high (tile indices: n < cells of a tile, d = tile width)
+struct FastDiv
+{
+	uint32_t d, m;
+	NYX_HD void init (uint32_t d_)
+	{
+		d = d_;
+		m = d_ > 1 ? (uint32_t)((0x100000000ull + d_ - 1) / d_) : 0;
+	}
+	NYX_HD uint32_t div (uint32_t n) const
+	{
+#ifdef __CUDA_ARCH__
+		return d > 1 ? __umulhi (n, m) : n;
+#else
+		return n / d;
+#endif
+	}
 };
 
 constexpr int RED_MAX = 48;
@@ -259,6 +305,19 @@ template <int N> NYX_D void cta_sum (const Cta& c, double (&v)[N])
 {
 #if NYX_DEVICE_BUILD
 	static_assert (N <= RED_MAX, "too many values");
+	if (c.wmode)
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++)
+		{
+			double x = v[k];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				x += __shfl_xor_sync (0xffffffffu, x, o);
+			v[k] = x;
+		}
+		return;
+	}
 	const int lane = c.tid & 31, warp = c.tid >> 5, nw = (c.nthr + 31) >> 5;
 #pragma unroll
 	for (int k = 0; k < N; k++)
@@ -289,6 +348,19 @@ template <int N> NYX_D void cta_sum_u64 (const Cta& c, unsigned long long (&v)[N
 {
 #if NYX_DEVICE_BUILD
 	static_assert (N <= RED_MAX, "too many values");
+	if (c.wmode)
+	{
+#pragma unroll
+		for (int k = 0; k < N; k++)
+		{
+			unsigned long long x = v[k];
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1)
+				x += __shfl_xor_sync (0xffffffffu, x, o);
+			v[k] = x;
+		}
+		return;
+	}
 	const int lane = c.tid & 31, warp = c.tid >> 5, nw = (c.nthr + 31) >> 5;
 	unsigned long long* red = (unsigned long long*)c.red;
 #pragma unroll
@@ -327,6 +399,8 @@ NYX_D unsigned long long cta_max_u64 (const Cta& c, unsigned long long x)
 		unsigned long long y = __shfl_xor_sync (0xffffffffu, x, o);
 		x = y > x ? y : x;
 	}
+	if (c.wmode)
+		return x;
 	if (lane == 0)
 		red[warp] = x;
 	__syncthreads();

@@ -84,8 +84,8 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 	if (fam_mask & 4)
 	{
 		int Nr = std::max (r.w, r.h);
-		std::vector<uint32_t> mem (glrlm_smem_words (Lmax, Nr));
-		glrlm_body (c, r, prm, cell.data(), mem.data(), Lmax, Nr, out + COL_GLRLM, nullptr);
+		std::vector<uint32_t> mem (glrlm_smem_words (Lmax, Nr, ncell));
+		glrlm_body (c, r, prm, cell.data(), mem.data(), Lmax, Nr, ncell, out + COL_GLRLM, nullptr);
 	}
 	if (fam_mask & 8)
 	{
