@@ -365,14 +365,16 @@ size_t family_words (int fam, bool p16, int Lmax, uint32_t maxcells, int maxwh)
 	{
 	case FAM_GLCM: return p16 ? glcm_smem_words<true> (Lmax, 4) : glcm_smem_words<false> (Lmax, 4);
 	case FAM_GLRLM: return glrlm_smem_words (Lmax, maxwh, (int)maxcells);
-	case FAM_GLDZM: return gldzm_smem_words ((int)maxcells, maxwh);
-	case FAM_GLSZM: return glszm_smem_words ((int)maxcells);
+	case FAM_GLDZM: return gldzm_smem_words (Lmax, gldzm_nd_bound (maxcells, maxwh), maxcells);
+	case FAM_GLSZM: return glszm_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));
 	case FAM_GLDM: return gldm_smem_words (Lmax);
 	case FAM_NGLDM: return ngldm_smem_words (Lmax);
 	case FAM_NGTDM: return ngtdm_smem_words (Lmax);
 	}
 	return 0;
 }
+
+constexpr size_t WARP_SLICE_LIMIT_WORDS = (28 * 1024) / 4;	// per-warp shared memory above which the CTA-per-ROI form is used
 
 template <int FAM, bool P16>
 int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list, uint32_t n, const Params& prm, int Lmax,
@@ -382,6 +384,20 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 		return 0;
 	const size_t tilew = (maxcells + 1) & ~(size_t)1;
 	const size_t famw = (family_words (FAM, P16, Lmax, maxcells, maxwh) + 1) & ~(size_t)1;
+	// small tiles of the single-matrix families: one warp per ROI
+	if (FAM != FAM_GLCM && FAM != FAM_GLRLM && !dbg.u32 && maxcells <= 1024 && tilew + famw <= WARP_SLICE_LIMIT_WORDS)
+	{
+		const size_t bytes = (tilew + famw) * 4 * ROI_WARPS;
+		auto kw = k_roi_family_w<FAM>;
+		if (set_smem (ctx, kw, bytes))
+			return NYXB200_ECUDA;
+		const int per_sm = (int)std::max<size_t> (1, std::min<size_t> (16, (size_t)(227 * 1024) / (bytes + 1024)));
+		const int grid = (int)std::min<uint32_t> ((n + ROI_WARPS - 1) / ROI_WARPS, (uint32_t)(ctx->sm_count * per_sm));
+		kw<<<grid, ROI_THREADS, bytes, ctx->stream>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out, NCOL_ALL, famw);
+		CU (cudaGetLastError());
+		ctx->counts[0]++;
+		return 0;
+	}
 	size_t smem_words = RED_WORDS + tilew + famw;
 	uint32_t* gs = nullptr;
 	int grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 16);
@@ -430,6 +446,18 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 		return 0;
 	const uint32_t npad = next_pow2 (maxarea);
 	const size_t memw = (intensity_smem_words (npad, prm.greydepth) + 1) & ~(size_t)1;
+	if (npad <= 1024 && memw <= WARP_SLICE_LIMIT_WORDS)	// small clouds: one warp per ROI
+	{
+		const size_t bytes = memw * 4 * ROI_WARPS;
+		if (set_smem (ctx, k_roi_intensity_w, bytes))
+			return NYXB200_ECUDA;
+		const int per_sm = (int)std::max<size_t> (1, std::min<size_t> (16, (size_t)(227 * 1024) / (bytes + 1024)));
+		const int grid = (int)std::min<uint32_t> ((n + ROI_WARPS - 1) / ROI_WARPS, (uint32_t)(ctx->sm_count * per_sm));
+		k_roi_intensity_w<<<grid, ROI_THREADS, bytes, ctx->stream>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, out, NCOL_ALL, memw);
+		CU (cudaGetLastError());
+		ctx->counts[0]++;
+		return 0;
+	}
 	size_t smem_words = RED_WORDS + memw;
 	uint32_t* gs = nullptr;
 	int grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 16);
@@ -942,6 +970,7 @@ int nyxb200_debug_matrix (nyxb200_ctx* ctx, uint32_t label, int family, int64_t*
 	case FAM_GLSZM:
 	{
 		uint32_t nk = h[words];
+		std::sort (h.begin(), h.begin() + nk);	// one key per zone, unsorted on the device
 		for (uint32_t i = 0; i < nk; )
 		{
 			uint32_t j = i;

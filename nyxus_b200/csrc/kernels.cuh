@@ -449,7 +449,61 @@ struct DebugOut
 };
 
 constexpr int ROI_THREADS = 128;
+constexpr int ROI_WARPS = ROI_THREADS / 32;
 
+// tile load + one family body for one ROI, run by the context c (a CTA or a single warp)
+template <int FAM, bool P16>
+__device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, const RoiRec& r, const Params& prm, uint32_t* cell,
+	uint32_t* mem, int Lmax, uint32_t maxcells, int maxwh, double* o, const DebugOut& dbg)
+{
+	if (FAM == FAM_NGLDM)
+		load_tile_ngldm (c, im, r, prm, cell);
+	else
+	{
+		Binner B;
+		B.init (prm.ibsi ? 0 : prm.greydepth, r.imin, r.imax);
+		load_tile (c, im, r, B, cell);
+	}
+	c.sync();
+	if (FAM == FAM_GLCM)
+	{
+		GlcmDebug d { dbg.u32 };
+		glcm_body<P16> (c, r, prm, cell, mem, Lmax, o + COL_GLCM, dbg.u32 ? &d : nullptr);
+	}
+	else if (FAM == FAM_GLRLM)
+	{
+		GlrlmDebug d { dbg.u32 };
+		glrlm_body (c, r, prm, cell, mem, Lmax, maxwh, (int)maxcells, o + COL_GLRLM, dbg.u32 ? &d : nullptr);
+	}
+	else if (FAM == FAM_GLDZM)
+	{
+		ZoneDebug d { dbg.u32, dbg.nkeys };
+		gldzm_body (c, r, prm, cell, mem, Lmax, gldzm_nd_bound (maxcells, maxwh), maxcells, o + COL_GLDZM, dbg.u32 ? &d : nullptr);
+	}
+	else if (FAM == FAM_GLSZM)
+	{
+		ZoneDebug d { dbg.u32, dbg.nkeys };
+		glszm_body (c, r, prm, cell, mem, maxcells, glszm_hash_slots (Lmax, maxcells), o + COL_GLSZM, dbg.u32 ? &d : nullptr);
+	}
+	else if (FAM == FAM_GLDM)
+	{
+		DenseDebug d { dbg.u32 };
+		gldm_body (c, r, prm, cell, mem, Lmax, o + COL_GLDM, dbg.u32 ? &d : nullptr);
+	}
+	else if (FAM == FAM_NGLDM)
+	{
+		DenseDebug d { dbg.u32 };
+		ngldm_body (c, r, prm, cell, mem, Lmax, o + COL_NGLDM, dbg.u32 ? &d : nullptr);
+	}
+	else if (FAM == FAM_NGTDM)
+	{
+		NgtdmDebug d { dbg.u32, dbg.f64 };
+		ngtdm_body (c, r, prm, cell, mem, Lmax, o + COL_NGTDM, dbg.u32 ? &d : nullptr);
+	}
+	c.sync();
+}
+
+// CTA per ROI (GLCM / GLRLM: one warp per angle; every family for the larger tile classes)
 template <int FAM, bool P16>
 __global__ void __launch_bounds__(ROI_THREADS) k_roi_family (ImageView im, const RoiRec* __restrict__ rois,
 	const uint32_t* __restrict__ list, uint32_t n, Params prm, int Lmax, uint32_t maxcells, int maxwh,
@@ -468,52 +522,32 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family (ImageView im, const
 	{
 		const uint32_t ri = list ? list[k] : k;
 		const RoiRec r = rois[ri];
-		double* o = out + (size_t)ri * out_stride;
-		if (FAM == FAM_NGLDM)
-			load_tile_ngldm (c, im, r, prm, cell);
-		else
-		{
-			Binner B;
-			B.init (prm.ibsi ? 0 : prm.greydepth, r.imin, r.imax);
-			load_tile (c, im, r, B, cell);
-		}
-		c.sync();
-		if (FAM == FAM_GLCM)
-		{
-			GlcmDebug d { dbg.u32 };
-			glcm_body<P16> (c, r, prm, cell, mem, Lmax, o + COL_GLCM, dbg.u32 ? &d : nullptr);
-		}
-		else if (FAM == FAM_GLRLM)
-		{
-			GlrlmDebug d { dbg.u32 };
-			glrlm_body (c, r, prm, cell, mem, Lmax, maxwh, (int)maxcells, o + COL_GLRLM, dbg.u32 ? &d : nullptr);
-		}
-		else if (FAM == FAM_GLDZM)
-		{
-			ZoneDebug d { dbg.u32, dbg.nkeys };
-			gldzm_body (c, r, prm, cell, mem, o + COL_GLDZM, dbg.u32 ? &d : nullptr);
-		}
-		else if (FAM == FAM_GLSZM)
-		{
-			ZoneDebug d { dbg.u32, dbg.nkeys };
-			glszm_body (c, r, prm, cell, mem, o + COL_GLSZM, dbg.u32 ? &d : nullptr);
-		}
-		else if (FAM == FAM_GLDM)
-		{
-			DenseDebug d { dbg.u32 };
-			gldm_body (c, r, prm, cell, mem, Lmax, o + COL_GLDM, dbg.u32 ? &d : nullptr);
-		}
-		else if (FAM == FAM_NGLDM)
-		{
-			DenseDebug d { dbg.u32 };
-			ngldm_body (c, r, prm, cell, mem, Lmax, o + COL_NGLDM, dbg.u32 ? &d : nullptr);
-		}
-		else if (FAM == FAM_NGTDM)
-		{
-			NgtdmDebug d { dbg.u32, dbg.f64 };
-			ngtdm_body (c, r, prm, cell, mem, Lmax, o + COL_NGTDM, dbg.u32 ? &d : nullptr);
-		}
-		c.sync();
+		run_family<FAM, P16> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, dbg);
+	}
+}
+
+// WARP per ROI (single-matrix families on small tiles): every warp of the CTA owns a private shared-memory slice
+// (tile + family region) and walks its own ROIs -- no block-wide barrier anywhere, reductions are shuffle trees.
+template <int FAM>
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_family_w (ImageView im, const RoiRec* __restrict__ rois,
+	const uint32_t* __restrict__ list, uint32_t n, Params prm, int Lmax, uint32_t maxcells, int maxwh,
+	double* out, int out_stride, size_t famw)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const size_t tilew = (maxcells + 1) & ~1u;
+	uint32_t* cell = smem + (size_t)warp * (tilew + famw);
+	uint32_t* mem = cell + tilew;
+	Cta c { lane, 32, nullptr, 1 };
+	for (size_t i = lane; i < famw; i += 32)
+		mem[i] = 0;
+	__syncwarp();
+	const DebugOut nodbg { nullptr, nullptr, nullptr };
+	for (uint32_t k = blockIdx.x * ROI_WARPS + warp; k < n; k += gridDim.x * ROI_WARPS)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		const RoiRec r = rois[ri];
+		run_family<FAM, false> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, nodbg);
 	}
 }
 
@@ -526,6 +560,23 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_intensity (const RoiRec* __
 	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
 	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : smem + RED_WORDS;
 	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		const RoiRec r = rois[ri];
+		intensity_body (c, r, prm, cloud + r.cloud_off, r.area, next_pow2 (r.area), mem, out + (size_t)ri * out_stride + COL_INT);
+		c.sync();
+	}
+}
+
+// first-order, warp per ROI (small clouds)
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_intensity_w (const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+	uint32_t n, Params prm, const uint32_t* __restrict__ cloud, double* out, int out_stride, size_t memw)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t* mem = smem + (size_t)warp * memw;
+	Cta c { lane, 32, nullptr, 1 };
+	for (uint32_t k = blockIdx.x * ROI_WARPS + warp; k < n; k += gridDim.x * ROI_WARPS)
 	{
 		const uint32_t ri = list ? list[k] : k;
 		const RoiRec r = rois[ri];

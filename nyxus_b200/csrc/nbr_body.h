@@ -8,9 +8,12 @@
 // NGTDM (reference features/ngtdm.cpp): no blank test, |I| < 2 -> softNaN (:70-78); centres/neighbours by BINNED level != 0
 //        (:88-146); N[level]++, S[level] += |level - mean of neighbours| (:159-183); features :228-347.
 //
-// B200 design: one CTA per ROI, one 3x3 stencil pass over the shared-memory tile, integer shared-memory histograms.
-// NGTDM's S is accumulated as exact integers |level*nd - sum| per neighbour count nd and divided once per (level, nd),
-// which makes it independent of the accumulation order (deterministic) and within a few ulp of the reference.
+// B200 design: one WARP (small tiles) or one CTA per ROI, one 3x3 stencil pass over the shared-memory tile, integer
+// shared-memory histograms.  GLDM / NGLDM reducers are "owner computes": every pixel re-reads the count of its own
+// matrix cell (its dependence is stashed in spare bits of the tile word), so no [level][dependence] sweep per ROI and the
+// matrix region is all zero on entry and exit.  NGTDM's S is accumulated as exact integers |level*nd - sum| per
+// neighbour count nd and divided once per (level, nd) -- independent of the accumulation order (deterministic) and
+// within a few ulp of the reference; its O(Ng^2) pair features run over the compacted list of present levels only.
 #pragma once
 #include "nyx_common.h"
 #include "nyx_features.h"
@@ -23,15 +26,40 @@ struct DenseDebug
 	uint32_t* P;	// dense dump of the family's matrix, may be null
 };
 
+constexpr int CELL_AUX_SHIFT = 24;		// 4 spare bits of the tile word: the pixel's dependence count (stash between passes)
+constexpr uint32_t CELL_AUX = 0x0F000000u;
+
+// number of 8-neighbours q of cell (x,y) with (cell[q] & flag) and the same level
+NYX_D int nbr_same_level (const uint32_t* cell, int w, int h, int x, int y, uint32_t lv, uint32_t flag)
+{
+	int n = 0;
+	for (int dy = -1; dy <= 1; dy++)
+	{
+		const int yy = y + dy;
+		if (yy < 0 || yy >= h)
+			continue;
+		for (int dx = -1; dx <= 1; dx++)
+		{
+			const int xx = x + dx;
+			if ((!dx && !dy) || xx < 0 || xx >= w)
+				continue;
+			const uint32_t q = cell[yy * w + xx];
+			if ((q & flag) && (q & CELL_LEVEL) == lv)
+				n++;
+		}
+	}
+	return n;
+}
+
 // ------------------------------------------------------------------------------------------------
-// GLDM: hist[(Lmax+1)][10]
+// GLDM: P[(Lmax+1)][10] + Si[Lmax+1] + Sj[10], all zero on entry and exit
 // ------------------------------------------------------------------------------------------------
 NYX_HD size_t gldm_smem_words (int Lmax)
 {
-	return (size_t)(Lmax + 1) * 10;
+	return (size_t)(Lmax + 1) * 11 + 10;
 }
 
-NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax,
+NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t* cell, uint32_t* mem, int Lmax,
 	double* out, const DenseDebug* dbg)
 {
 	const int w = r.w, h = r.h, ncell = w * h;
@@ -41,79 +69,52 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 			out[i] = prm.softnan;
 		return;
 	}
-	uint32_t* P = mem;	// [level][nd], nd in 1..9
-	const size_t nw = gldm_smem_words (Lmax);
-	for (size_t i = c.tid; i < nw; i += c.nthr)
-		P[i] = 0;
-	c.sync();
-	for (int i = c.tid; i < ncell; i += c.nthr)
-	{
-		uint32_t cc = cell[i];
-		if (!(cc & CELL_NZ))
-			continue;
-		uint32_t lv = cc & CELL_LEVEL;
-		int y = i / w, x = i - y * w, nd = 1;
-		for (int dy = -1; dy <= 1; dy++)
-			for (int dx = -1; dx <= 1; dx++)
-			{
-				if (!dx && !dy)
-					continue;
-				int yy = y + dy, xx = x + dx;
-				if (yy < 0 || yy >= h || xx < 0 || xx >= w)
-					continue;
-				uint32_t q = cell[yy * w + xx];
-				if ((q & CELL_NZ) && (q & CELL_LEVEL) == lv)
-					nd++;
-			}
-		atom_add (c, P + (size_t)lv * 10 + nd, 1u);
-	}
-	c.sync();
-	if (dbg && dbg->P)
-		for (size_t i = c.tid; i < nw; i += c.nthr)
-			dbg->P[i] = P[i];
+	uint32_t* P = mem;				// [level][nd], nd in 1..9
+	uint32_t* Si = P + (size_t)(Lmax + 1) * 10;	// [level]
+	uint32_t* Sj = Si + (Lmax + 1);			// [nd]
+	FastDiv fw;
+	fw.init ((uint32_t)w);
 
-	// per-level and per-dependence marginals are recomputed on the fly (10 columns)
-	enum { Q_NZ, Q_LDE, Q_GLN, Q_MUI, Q_MUJ, Q_HGL, Q_N };
+	enum { Q_NZ, Q_LDE, Q_MUI, Q_MUJ, Q_HGL, Q_N };
 	unsigned long long q[Q_N];
 	for (int k = 0; k < Q_N; k++)
 		q[k] = 0;
-	unsigned long long sj[10];
-	for (int k = 0; k < 10; k++)
-		sj[k] = 0;
-	enum { A_SDE, A_LGL, A_DE0, A_SDL, A_SDH, A_LDL, A_LDH, A_N };
+	enum { A_SDE, A_LGL, A_SDL, A_SDH, A_LDL, A_LDH, A_N };
 	double s[A_N];
 	for (int k = 0; k < A_N; k++)
 		s[k] = 0;
-	for (int lv = c.tid + 1; lv <= Lmax; lv += c.nthr)
+	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		unsigned long long si = 0;
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_NZ))
+			continue;
+		const uint32_t lv = cc & CELL_LEVEL;
+		const int y = (int)fw.div ((uint32_t)i), x = i - y * w;
+		const int j = 1 + nbr_same_level (cell, w, h, x, y, lv, CELL_NZ);	// gldm.cpp:74-166
+		cell[i] = cc | ((uint32_t)j << CELL_AUX_SHIFT);
+		atom_add (c, P + (size_t)lv * 10 + j, 1u);
+		atom_add (c, Si + lv, 1u);
+		atom_add (c, Sj + j, 1u);
 		const double in = (double)lv;
-		for (int j = 1; j <= 9; j++)
-		{
-			unsigned long long v = P[(size_t)lv * 10 + j];
-			if (!v)
-				continue;
-			si += v;
-			sj[j] += v;
-			q[Q_LDE] += v * (unsigned long long)(j * j);			// gldm.cpp:314-316
-			q[Q_MUJ] += v * (unsigned long long)j;				// :410
-			s[A_SDE] += (double)v / ((double)j * (double)j);		// :301-302
-			s[A_SDL] += (double)v / (double)(in * in * j * j);		// :498-505
-			s[A_SDH] += (double)v * (in * in) / (double)(j * j);		// :513-520
-			s[A_LDL] += (double)v * (double)(j * j) / (in * in);		// :528-535
-			s[A_LDH] += (double)v * (double)(in * in * j * j);		// :543-550
-		}
-		q[Q_NZ] += si;
-		q[Q_GLN] += si * si;							// :325-338
-		q[Q_MUI] += si * (unsigned long long)lv;				// :388-395
-		q[Q_HGL] += si * (unsigned long long)lv * (unsigned long long)lv;	// :470-484
-		if (si)
-			s[A_LGL] += (double)si / (in * in);				// :452-464
+		q[Q_NZ] += 1;
+		q[Q_LDE] += (unsigned long long)(j * j);			// gldm.cpp:314-316
+		q[Q_MUJ] += (unsigned long long)j;				// :410
+		q[Q_MUI] += lv;							// :388-395
+		q[Q_HGL] += (unsigned long long)lv * (unsigned long long)lv;	// :470-484
+		s[A_SDE] += 1.0 / ((double)j * (double)j);			// :301-302
+		s[A_LGL] += 1.0 / (in * in);					// :452-464
+		s[A_SDL] += 1.0 / (double)(in * in * j * j);			// :498-505
+		s[A_SDH] += (in * in) / (double)(j * j);			// :513-520
+		s[A_LDL] += (double)(j * j) / (in * in);			// :528-535
+		s[A_LDH] += (double)(in * in * j * j);				// :543-550
 	}
+	c.sync();
+	if (dbg && dbg->P)
+		for (size_t i = c.tid; i < (size_t)(Lmax + 1) * 10; i += c.nthr)
+			dbg->P[i] = P[i];
 	cta_sum_u64<Q_N> (c, q);
-	cta_sum_u64<10> (c, sj);
 	cta_sum<A_N> (c, s);
-	if (q[Q_NZ] == 0)	// gldm.cpp:213-231
+	if (q[Q_NZ] == 0)	// gldm.cpp:213-231 (nothing was counted: the region is still all zero)
 	{
 		for (int i = c.tid; i < NCOL_GLDM; i += c.nthr)
 			out[i] = prm.softnan;
@@ -121,44 +122,50 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 	}
 	const double Nz = (double)q[Q_NZ];
 	const double mui = (double)q[Q_MUI] / Nz, muj = (double)q[Q_MUJ] / Nz;
-	double t[2] = { 0, 0 };	// GLV, DE
-	for (int lv = c.tid + 1; lv <= Lmax; lv += c.nthr)
+
+	// ---- pass 2: terms that need the counts (owner computes)
+	unsigned long long q2[2] = { 0, 0 };	// sum Si^2 (:325-338), sum Sj^2 (:343-357)
+	double t[3] = { 0, 0, 0 };		// GLV, DV, DE
+	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		unsigned long long si = 0;
-		for (int j = 1; j <= 9; j++)
-		{
-			uint32_t v = P[(size_t)lv * 10 + j];
-			if (!v)
-				continue;
-			si += v;
-			double p = (double)v / Nz;
-			t[1] += dmul (p, ddiv (fast_log10 (dadd (p, EPS_ZONES)), LOG10_2));	// :437-446
-		}
-		if (si)
-		{
-			double di = (double)lv - mui;
-			t[0] += (double)si / Nz * (di * di);				// :398-406
-		}
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_NZ))
+			continue;
+		const uint32_t lv = cc & CELL_LEVEL, j = (cc & CELL_AUX) >> CELL_AUX_SHIFT;
+		q2[0] += Si[lv];
+		q2[1] += Sj[j];
+		const double di = (double)lv - mui, dj = (double)j - muj;
+		t[0] += di * di;							// :398-406
+		t[1] += dj * dj;							// :418-429
+		const double p = (double)P[(size_t)lv * 10 + j] / Nz;
+		t[2] += fast_log10 (dadd (p, EPS_ZONES));				// :437-446
 	}
-	cta_sum<2> (c, t);
+	cta_sum_u64<2> (c, q2);
+	cta_sum<3> (c, t);
+	c.sync();
+	// ---- pass 3: restore the all-zero region
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_NZ))
+			continue;
+		const uint32_t lv = cc & CELL_LEVEL, j = (cc & CELL_AUX) >> CELL_AUX_SHIFT;
+		P[(size_t)lv * 10 + j] = 0;
+		Si[lv] = 0;
+	}
+	for (int k = c.tid; k < 10; k += c.nthr)
+		Sj[k] = 0;
+	c.sync();
 	if (c.tid == 0)
 	{
-		unsigned long long dn = 0;
-		double dv = 0;
-		for (int j = 1; j <= 9; j++)
-		{
-			dn += sj[j] * sj[j];						// :343-357
-			double d = (double)j - muj;
-			dv += (double)sj[j] / Nz * (d * d);				// :418-429
-		}
 		out[D_SDE] = s[A_SDE] / Nz;
 		out[D_LDE] = (double)q[Q_LDE] / Nz;
-		out[D_GLN] = (double)q[Q_GLN] / Nz;
-		out[D_DN] = (double)dn / Nz;
-		out[D_DNN] = (double)dn / (Nz * Nz);
-		out[D_GLV] = t[0];
-		out[D_DV] = dv;
-		out[D_DE] = -t[1];
+		out[D_GLN] = (double)q2[0] / Nz;
+		out[D_DN] = (double)q2[1] / Nz;
+		out[D_DNN] = (double)q2[1] / (Nz * Nz);
+		out[D_GLV] = t[0] / Nz;
+		out[D_DV] = t[1] / Nz;
+		out[D_DE] = -(t[2] / Nz) * (1.0 / LOG10_2);
 		out[D_LGLE] = s[A_LGL] / Nz;
 		out[D_HGLE] = (double)q[Q_HGL] / Nz;
 		out[D_SDLGLE] = s[A_SDL] / Nz;
@@ -169,20 +176,23 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 }
 
 // ------------------------------------------------------------------------------------------------
-// NGLDM: the tile passed here carries to_grayscale() levels (see load_tile_ngldm); hist[(Lmax+1)][9]
+// NGLDM: the tile passed here carries to_grayscale() levels (see load_tile_ngldm);
+// P[(Lmax+1)][9] + Sg[Lmax+1] + Sr[9], all zero on entry and exit
 // ------------------------------------------------------------------------------------------------
 NYX_HD size_t ngldm_smem_words (int Lmax)
 {
-	return (size_t)(Lmax + 1) * 9;
+	return (size_t)(Lmax + 1) * 10 + 9;
 }
 
 // tile for NGLDM: level = to_grayscale(i, 0, aux_max, greydepth, ibsi) (ngldm.cpp:42,126), CELL_IN = cloud mask
 NYX_D void load_tile_ngldm (const Cta& c, const ImageView& im, const RoiRec& r, const Params& prm, uint32_t* cell)
 {
 	const int n = r.w * r.h;
+	FastDiv fw;
+	fw.init ((uint32_t)r.w);
 	for (int i = c.tid; i < n; i += c.nthr)
 	{
-		int y = i / r.w, x = i - y * r.w;
+		int y = (int)fw.div ((uint32_t)i), x = i - y * r.w;
 		size_t g = (size_t)(r.y0 + y) * im.W + (size_t)(r.x0 + x);
 		bool in = im.label[g] == r.label;
 		uint32_t code = 0;
@@ -192,7 +202,7 @@ NYX_D void load_tile_ngldm (const Cta& c, const ImageView& im, const RoiRec& r, 
 	}
 }
 
-NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax,
+NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t* cell, uint32_t* mem, int Lmax,
 	double* out, const DenseDebug* dbg)
 {
 	const int w = r.w, h = r.h, ncell = w * h;
@@ -202,108 +212,93 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 			out[i] = prm.softnan;
 		return;
 	}
-	uint32_t* P = mem;	// [level 0..Lmax][matches 0..8]
-	const size_t nw = ngldm_smem_words (Lmax);
-	for (size_t i = c.tid; i < nw; i += c.nthr)
-		P[i] = 0;
-	c.sync();
-	for (int i = c.tid; i < ncell; i += c.nthr)
-	{
-		uint32_t cc = cell[i];
-		if (!(cc & CELL_IN))
-			continue;
-		uint32_t lv = cc & CELL_LEVEL;
-		int y = i / w, x = i - y * w, nm = 0;
-		for (int dy = -1; dy <= 1; dy++)
-			for (int dx = -1; dx <= 1; dx++)
-			{
-				if (!dx && !dy)
-					continue;
-				int yy = y + dy, xx = x + dx;
-				if (yy < 0 || yy >= h || xx < 0 || xx >= w)
-					continue;
-				uint32_t q = cell[yy * w + xx];
-				if ((q & CELL_IN) && (q & CELL_LEVEL) == lv)
-					nm++;
-			}
-		atom_add (c, P + (size_t)lv * 9 + nm, 1u);
-	}
-	c.sync();
-	if (dbg && dbg->P)
-		for (size_t i = c.tid; i < nw; i += c.nthr)
-			dbg->P[i] = P[i];
+	uint32_t* P = mem;				// [level 0..Lmax][matches 0..8]
+	uint32_t* Sg = P + (size_t)(Lmax + 1) * 9;	// [level]
+	uint32_t* Sr = Sg + (Lmax + 1);			// [matches]
+	FastDiv fw;
+	fw.init ((uint32_t)w);
 
-	unsigned long long q[2] = { 0, 0 };	// Ns, sum Sg^2
-	unsigned long long sr[9];
-	for (int k = 0; k < 9; k++)
-		sr[k] = 0;
-	for (int lv = c.tid; lv <= Lmax; lv += c.nthr)
-	{
-		unsigned long long sg = 0;
-		for (int j = 0; j < 9; j++)
-		{
-			unsigned long long v = P[(size_t)lv * 9 + j];
-			sg += v;
-			sr[j] += v;
-		}
-		q[0] += sg;
-		q[1] += sg * sg;
-	}
-	cta_sum_u64<2> (c, q);
-	cta_sum_u64<9> (c, sr);
-	const double Ns = (double)q[0];
-	enum { A_LDE, A_HDE, A_LGLCE, A_HGLCE, A_LDLGLE, A_LDHGLE, A_HDLGLE, A_HDHGLE, A_GLM, A_DCM, A_DCENT, A_DCENE, A_N };
+	enum { Q_NS, Q_G, Q_DC, Q_N };
+	unsigned long long q[Q_N];
+	for (int k = 0; k < Q_N; k++)
+		q[k] = 0;
+	enum { A_LDE, A_HDE, A_LGLCE, A_HGLCE, A_LDLGLE, A_LDHGLE, A_HDLGLE, A_HDHGLE, A_N };
 	double s[A_N];
 	for (int k = 0; k < A_N; k++)
 		s[k] = 0;
-	for (int lv = c.tid; lv <= Lmax; lv += c.nthr)
+	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		const double g = (double)lv;
-		for (int j = 0; j < 9; j++)
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_IN))
+			continue;
+		const uint32_t lv = cc & CELL_LEVEL;
+		const int y = (int)fw.div ((uint32_t)i), x = i - y * w;
+		const int nm = nbr_same_level (cell, w, h, x, y, lv, CELL_IN);	// ngldm.cpp:116-154
+		cell[i] = cc | ((uint32_t)nm << CELL_AUX_SHIFT);
+		atom_add (c, P + (size_t)lv * 9 + nm, 1u);
+		atom_add (c, Sg + lv, 1u);
+		atom_add (c, Sr + nm, 1u);
+		const double g = (double)lv, dc = (double)(nm + 1);		// ngldm.cpp:283-305
+		q[Q_NS] += 1;
+		q[Q_G] += lv;
+		q[Q_DC] += (unsigned long long)(nm + 1);
+		s[A_LDE] += 1.0 / dc / dc;
+		s[A_HDE] += dc * dc;
+		if (g != 0.0)
 		{
-			uint32_t v = P[(size_t)lv * 9 + j];
-			if (!v)
-				continue;
-			double dc = (double)(j + 1), sij = (double)v, pij = sij / Ns;	// ngldm.cpp:283-305
-			s[A_LDE] += sij / dc / dc;
-			s[A_HDE] += sij * dc * dc;
-			if (g != 0.0)
-			{
-				s[A_LGLCE] += sij / g / g;
-				s[A_LDLGLE] += sij / dc / dc / g / g;
-				s[A_HDLGLE] += sij * dc * dc / g / g;
-			}
-			s[A_HGLCE] += sij * g * g;
-			s[A_LDHGLE] += sij * g * g / dc / dc;
-			s[A_HDHGLE] += sij * dc * dc * g * g;
-			s[A_GLM] += g * pij;
-			s[A_DCM] += dc * pij;
-			if (pij > 0.0)
-				s[A_DCENT] -= pij * log (pij) / log (2.0);
-			s[A_DCENE] += pij * pij;
+			s[A_LGLCE] += 1.0 / g / g;
+			s[A_LDLGLE] += 1.0 / dc / dc / g / g;
+			s[A_HDLGLE] += dc * dc / g / g;
 		}
+		s[A_HGLCE] += g * g;
+		s[A_LDHGLE] += g * g / dc / dc;
+		s[A_HDHGLE] += dc * dc * g * g;
 	}
+	c.sync();
+	if (dbg && dbg->P)
+		for (size_t i = c.tid; i < (size_t)(Lmax + 1) * 9; i += c.nthr)
+			dbg->P[i] = P[i];
+	cta_sum_u64<Q_N> (c, q);
 	cta_sum<A_N> (c, s);
-	double t[2] = { 0, 0 };
-	for (int lv = c.tid; lv <= Lmax; lv += c.nthr)
+	const double Ns = (double)q[Q_NS];
+	const double glm = (double)q[Q_G] / Ns, dcm = (double)q[Q_DC] / Ns;	// sum g*p, sum dc*p
+
+	// ---- pass 2 (owner computes)
+	unsigned long long q2[3] = { 0, 0, 0 };	// sum Sg^2, sum Sr^2, sum P^2
+	double t[3] = { 0, 0, 0 };		// GLV (:330), DCV (:337), sum log(p) (:302-303)
+	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		const double g = (double)lv;
-		for (int j = 0; j < 9; j++)
-		{
-			uint32_t v = P[(size_t)lv * 9 + j];
-			if (!v)
-				continue;
-			double dc = (double)(j + 1), pij = (double)v / Ns;
-			t[0] += (g - s[A_GLM]) * (g - s[A_GLM]) * pij;			// :330
-			t[1] += (dc - s[A_DCM]) * (dc - s[A_DCM]) * pij;		// :337
-		}
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_IN))
+			continue;
+		const uint32_t lv = cc & CELL_LEVEL, nm = (cc & CELL_AUX) >> CELL_AUX_SHIFT;
+		const uint32_t v = P[(size_t)lv * 9 + nm];
+		q2[0] += Sg[lv];
+		q2[1] += Sr[nm];
+		q2[2] += v;
+		const double dg = (double)lv - glm, dd = (double)(nm + 1) - dcm;
+		t[0] += dg * dg;
+		t[1] += dd * dd;
+		t[2] += log ((double)v / Ns);
 	}
-	cta_sum<2> (c, t);
+	cta_sum_u64<3> (c, q2);
+	cta_sum<3> (c, t);
+	c.sync();
+	// ---- pass 3: restore the all-zero region
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t cc = cell[i];
+		if (!(cc & CELL_IN))
+			continue;
+		const uint32_t lv = cc & CELL_LEVEL, nm = (cc & CELL_AUX) >> CELL_AUX_SHIFT;
+		P[(size_t)lv * 9 + nm] = 0;
+		Sg[lv] = 0;
+	}
+	for (int k = c.tid; k < 9; k += c.nthr)
+		Sr[k] = 0;
+	c.sync();
 	if (c.tid == 0)
 	{
-		unsigned long long dcn = 0;
-		for (int j = 0; j < 9; j++)
-			dcn += sr[j] * sr[j];
 		out[N_LDE] = s[A_LDE] / Ns;
 		out[N_HDE] = s[A_HDE] / Ns;
 		out[N_LGLCE] = s[A_LGLCE] / Ns;
@@ -312,26 +307,30 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		out[N_LDHGLE] = s[A_LDHGLE] / Ns;
 		out[N_HDLGLE] = s[A_HDLGLE] / Ns;
 		out[N_HDHGLE] = s[A_HDHGLE] / Ns;
-		out[N_GLNU] = (double)q[1] / Ns;
-		out[N_GLNUN] = (double)q[1] / (Ns * Ns);
-		out[N_DCNU] = (double)dcn / Ns;
-		out[N_DCNUN] = (double)dcn / (Ns * Ns);
+		out[N_GLNU] = (double)q2[0] / Ns;
+		out[N_GLNUN] = (double)q2[0] / (Ns * Ns);
+		out[N_DCNU] = (double)q2[1] / Ns;
+		out[N_DCNUN] = (double)q2[1] / (Ns * Ns);
 		out[N_DCP] = 1.0;						// :354
-		out[N_GLM] = s[A_GLM];
-		out[N_GLV] = t[0];
-		out[N_DCM] = s[A_DCM];
-		out[N_DCV] = t[1];
-		out[N_DCENT] = s[A_DCENT];
-		out[N_DCENE] = s[A_DCENE];
+		out[N_GLM] = glm;
+		out[N_GLV] = t[0] / Ns;
+		out[N_DCM] = dcm;
+		out[N_DCV] = t[1] / Ns;
+		out[N_DCENT] = -(t[2] / Ns) / log (2.0);
+		out[N_DCENE] = (double)q2[2] / (Ns * Ns);
 	}
 }
 
 // ------------------------------------------------------------------------------------------------
-// NGTDM: N[(Lmax+1)], SI[(Lmax+1)][8] exact integer |level*nd - sum|, PR[(Lmax+1)] presence, then P,S doubles
+// NGTDM: N[L1], SI[L1][8] exact integer |level*nd - sum|, PR[L1] presence (zero on entry/exit), then the compacted
+// list of present levels with their P and S
 // ------------------------------------------------------------------------------------------------
 NYX_HD size_t ngtdm_smem_words (int Lmax)
 {
-	return (size_t)(Lmax + 1) * (1 + 8 + 1) + 2 + (size_t)(Lmax + 1) * 4;
+	size_t L1 = (size_t)Lmax + 1;
+	size_t ints = L1 * 10 + (L1 + 1) / 2;	// + level list (u16)
+	ints += ints & 1;
+	return ints + L1 * 4;			// + Pl, Sl doubles
 }
 
 struct NgtdmDebug
@@ -345,103 +344,153 @@ NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 {
 	const int w = r.w, h = r.h, ncell = w * h;
 	const int L1 = Lmax + 1;
-	uint32_t* Nn = mem;			// [L1]
-	uint32_t* SI = Nn + L1;			// [L1][8]
-	uint32_t* PR = SI + (size_t)L1 * 8;	// [L1] level present anywhere in the binned tile
-	size_t off = (size_t)L1 * 10;
+	uint32_t* Nn = mem;				// [L1]
+	uint32_t* SI = Nn + L1;				// [L1][8]
+	uint32_t* PR = SI + (size_t)L1 * 8;		// [L1] level present anywhere in the binned tile
+	uint16_t* lst = (uint16_t*)(PR + L1);		// [L1] levels with N > 0, ascending
+	size_t off = (size_t)L1 * 10 + ((size_t)L1 + 1) / 2;
 	off += off & 1;
-	double* Pd = (double*)(mem + off);	// [L1]
-	double* Sd = Pd + L1;			// [L1]
-	for (size_t i = c.tid; i < (size_t)L1 * 10; i += c.nthr)
-		mem[i] = 0;
-	c.sync();
+	double* Pl = (double*)(mem + off);		// [L1] P of the listed levels (:191-192)
+	double* Sl = Pl + L1;				// [L1] S of the listed levels
+	FastDiv fw;
+	fw.init ((uint32_t)w);
+
+	unsigned long long q[1] = { 0 };		// Nvc
 	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		uint32_t lv = cell[i] & CELL_LEVEL;
+		const uint32_t lv = cell[i] & CELL_LEVEL;
 		if (!lv)
 			continue;
 		PR[lv] = 1;
-		int y = i / w, x = i - y * w, nd = 0;
+		const int y = (int)fw.div ((uint32_t)i), x = i - y * w;
+		int nd = 0;
 		uint32_t sum = 0;
 		for (int dy = -1; dy <= 1; dy++)
+		{
+			const int yy = y + dy;
+			if (yy < 0 || yy >= h)
+				continue;
 			for (int dx = -1; dx <= 1; dx++)
 			{
-				if (!dx && !dy)
+				const int xx = x + dx;
+				if ((!dx && !dy) || xx < 0 || xx >= w)
 					continue;
-				int yy = y + dy, xx = x + dx;
-				if (yy < 0 || yy >= h || xx < 0 || xx >= w)
-					continue;
-				uint32_t q = cell[yy * w + xx] & CELL_LEVEL;
-				if (q)
+				const uint32_t qv = cell[yy * w + xx] & CELL_LEVEL;
+				if (qv)
 				{
-					sum += q;
+					sum += qv;
 					nd++;
 				}
 			}
-		if (nd > 0)
+		}
+		if (nd > 0)	// ngtdm.cpp:83-146
 		{
 			long long df = (long long)lv * nd - (long long)sum;
 			atom_add (c, Nn + lv, 1u);
 			atom_add (c, SI + (size_t)lv * 8 + (nd - 1), (uint32_t)(df < 0 ? -df : df));
+			q[0]++;
 		}
 	}
 	c.sync();
-	// ---- counts: Ngp = unique non-zero levels in the tile (ngtdm.cpp:53-55,152), Nvc = sum N
-	unsigned long long q[2] = { 0, 0 };
-	for (int lv = c.tid + 1; lv <= Lmax; lv += c.nthr)
+	cta_sum_u64<1> (c, q);
+	const double Nvc = (double)q[0], Nvp = (double)q[0];	// every kept pixel has a positive neighbourhood mean (:181-182)
+
+	// ---- one sub-group sweeps the levels: Ngp, compaction of the present levels, S and P, and restores the zero region
+	int* shared_cnt = (int*)c.red;	// [0] Ngp, [1] list length (block mode); a warp-wide context keeps them in registers
+	int Ngp = 0, nl = 0;
+	if (c.sub_id() == 0)
 	{
-		q[0] += PR[lv] ? 1 : 0;
-		q[1] += Nn[lv];
+		const Cta g = c.sub();
+		for (int base = 0; base <= Lmax; base += g.nthr)
+		{
+			const int lv = base + g.tid;
+			uint32_t n = 0, pr = 0;
+			double sv = 0;
+			if (lv <= Lmax)
+			{
+				n = Nn[lv];
+				pr = lv >= 1 ? PR[lv] : 0;
+				for (int k = 0; k < 8; k++)
+				{
+					const uint32_t si = SI[(size_t)lv * 8 + k];
+					if (si)
+						sv += (double)si / (double)(k + 1);
+					SI[(size_t)lv * 8 + k] = 0;
+				}
+				Nn[lv] = 0;
+				PR[lv] = 0;
+				if (dbg && dbg->N)
+				{
+					dbg->N[lv] = n;
+					dbg->S[lv] = sv;
+				}
+			}
+			const bool keep = n != 0 && lv >= 1;
+			const unsigned bk = g.ballot (keep), bp = g.ballot (pr != 0);
+			if (keep)
+			{
+				const int pos = nl + popc32 (bk & g.lanemask_lt());
+				lst[pos] = (uint16_t)lv;
+				Pl[pos] = (double)n / Nvc;
+				Sl[pos] = sv;
+			}
+			nl += popc32 (bk);
+			Ngp += popc32 (bp);	// unique non-zero levels in the tile (ngtdm.cpp:53-55,152)
+		}
+		if (!c.wmode && g.tid == 0)
+		{
+			shared_cnt[0] = Ngp;
+			shared_cnt[1] = nl;
+		}
 	}
-	cta_sum_u64<2> (c, q);
-	const int Ngp = (int)q[0];
+	c.sync();
+#if NYX_DEVICE_BUILD
+	if (!c.wmode)
+	{
+		Ngp = shared_cnt[0];
+		nl = shared_cnt[1];
+		__syncthreads();
+	}
+#endif
 	const int Isize = prm.ibsi ? (Ngp ? Lmax + 1 : 0) : Ngp;	// |I| (:57-67); IBSI: 0..max(D)
 	if (Isize < 2)
 	{
 		for (int i = c.tid; i < NCOL_NGTDM; i += c.nthr)
 			out[i] = prm.softnan;
+		if (dbg && dbg->N)	// the reference returns before building the matrix (ngtdm.cpp:70-78)
+			for (int lv = c.tid; lv <= Lmax; lv += c.nthr)
+			{
+				dbg->N[lv] = 0;
+				dbg->S[lv] = 0;
+			}
 		return;
 	}
-	const double Nvc = (double)q[1], Nvp = (double)q[1];	// every kept pixel has a positive neighbourhood mean (:181-182)
-	for (int lv = c.tid; lv <= Lmax; lv += c.nthr)
-	{
-		double sv = 0;
-		for (int k = 0; k < 8; k++)
-			if (SI[(size_t)lv * 8 + k])
-				sv += (double)SI[(size_t)lv * 8 + k] / (double)(k + 1);
-		Sd[lv] = sv;
-		Pd[lv] = (double)Nn[lv] / Nvc;		// :191-192
-	}
-	c.sync();
-	if (dbg && dbg->N)
-		for (int lv = c.tid; lv <= Lmax; lv += c.nthr)
-		{
-			dbg->N[lv] = Nn[lv];
-			dbg->S[lv] = Sd[lv];
-		}
 	enum { A_PS, A_S, A_CON, A_BUSY, A_CPLX, A_STR, A_N };
 	double s[A_N];
 	for (int k = 0; k < A_N; k++)
 		s[k] = 0;
-	for (int lv = c.tid + 1; lv <= Lmax; lv += c.nthr)
+	for (int k = c.tid; k < nl; k += c.nthr)
 	{
-		s[A_PS] += Pd[lv] * Sd[lv];		// :231-233
-		s[A_S] += Sd[lv];			// :256-258
+		s[A_PS] += Pl[k] * Sl[k];		// :231-233
+		s[A_S] += Sl[k];			// :256-258
 	}
-	const long long npair = (long long)Lmax * Lmax;
-	for (long long k = c.tid; k < npair; k += c.nthr)
 	{
-		int i = (int)(k / Lmax) + 1, j = (int)(k % Lmax) + 1;
-		double pi = Pd[i], pj = Pd[j];
-		if (pi == 0 || pj == 0)
-			continue;
-		double iv = (double)i, jv = (double)j;
-		s[A_CON] += pi * pj * (iv - jv) * (iv - jv);						// :245-251
-		s[A_BUSY] += fabs (pi * iv - pj * jv);							// :283-287
-		s[A_CPLX] += fabs (iv - jv) * (pi * Sd[i] + pj * Sd[j]) / (pi + pj);			// :311-314
-		s[A_STR] += (pi + pj) * (iv - jv) * (iv - jv);						// :333-336
+		const int npair = nl * nl;
+		FastDiv fl;
+		fl.init ((uint32_t)(nl > 0 ? nl : 1));
+		for (int k = c.tid; k < npair; k += c.nthr)
+		{
+			const int a = (int)fl.div ((uint32_t)k), b = k - a * nl;
+			const double pi = Pl[a], pj = Pl[b];
+			const double iv = (double)lst[a], jv = (double)lst[b];
+			s[A_CON] += pi * pj * (iv - jv) * (iv - jv);						// :245-251
+			s[A_BUSY] += fabs (pi * iv - pj * jv);							// :283-287
+			s[A_CPLX] += fabs (iv - jv) * (pi * Sl[a] + pj * Sl[b]) / (pi + pj);			// :311-314
+			s[A_STR] += (pi + pj) * (iv - jv) * (iv - jv);						// :333-336
+		}
 	}
 	cta_sum<A_N> (c, s);
+	c.sync();	// the lists may be rewritten by the next ROI
 	if (c.tid == 0)
 	{
 		out[T_COARSENESS] = 1.0 / s[A_PS];

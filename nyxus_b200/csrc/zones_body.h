@@ -20,45 +20,19 @@
 //   zone metric  = minimum over member pixels; matrix[level][metric] :239-258, :38-50
 //   features     :353-478   Nv = aux_area; entropy with real log2
 //
-// B200 design: one CTA per ROI, labels in shared memory; GLDZM components by lock-free union-find (atomicMin
-// hooking); sparse (level,minor) histograms by an in-smem bitonic sort of 32-bit keys -- independent of the number
-// of grey levels, deterministic.
+// B200 design: one WARP (small tiles) or one CTA per ROI, labels in shared memory.  GLSZM labels: per row a
+// {NW,N,NE} minimum and a segmented min-scan along the same-level runs (warp shuffles in the warp-per-ROI form).
+// GLDZM components by lock-free union-find (atomicMin hooking).  The sparse (level,size) matrix of GLSZM and its two
+// marginals live in ONE open-addressing hash table of integer counters (three key kinds); GLDZM's small
+// [level][distance] matrix is dense.  Reducers are "owner computes": every zone re-reads the count of its own matrix
+// cell, so sum_cells f(P) == sum_zones f(P_zone)/P_zone and nothing is sorted or swept.  Integer counters make every
+// matrix order-independent; FP sums use fixed lane assignments => deterministic.
 #pragma once
 #include "nyx_common.h"
 #include "nyx_features.h"
 
 namespace nyx
 {
-
-constexpr uint32_t KEY_PAD = 0xFFFFFFFFu;
-
-// visit every distinct key of a sorted list: f(major = key>>16, minor = key&0xFFFF, count)
-template <class F> NYX_D void for_each_unique_key (const Cta& c, const uint32_t* keys, uint32_t n, F f)
-{
-	for (uint32_t i = c.tid; i < n; i += c.nthr)
-	{
-		uint32_t k = keys[i];
-		if (i && keys[i - 1] == k)
-			continue;
-		uint32_t j = i + 1;
-		while (j < n && keys[j] == k) j++;
-		f (k >> 16, k & 0xFFFFu, j - i);
-	}
-}
-
-// visit every distinct major (level) of a sorted list: f(level, number of list entries with that level)
-template <class F> NYX_D void for_each_major (const Cta& c, const uint32_t* keys, uint32_t n, F f)
-{
-	for (uint32_t i = c.tid; i < n; i += c.nthr)
-	{
-		uint32_t m = keys[i] >> 16;
-		if (i && (keys[i - 1] >> 16) == m)
-			continue;
-		uint32_t j = i + 1;
-		while (j < n && (keys[j] >> 16) == m) j++;
-		f (m, j - i);
-	}
-}
 
 NYX_D uint32_t atom_min_ret (const Cta&, uint32_t* p, uint32_t v)
 {
@@ -77,6 +51,63 @@ NYX_D uint32_t atom_inc_ret (const Cta&, uint32_t* p)
 #else
 	return (*p)++;
 #endif
+}
+NYX_D uint32_t atom_cas (const Cta&, uint32_t* p, uint32_t cmp, uint32_t val)
+{
+#if NYX_DEVICE_BUILD
+	return atomicCAS (p, cmp, val);
+#else
+	uint32_t o = *p;
+	if (o == cmp) *p = val;
+	return o;
+#endif
+}
+
+// ---- open-addressing table of integer counters: keys[slots] (0 = empty) + cnts[slots], slots = power of two
+NYX_HD uint32_t htab_mix (uint32_t k)
+{
+	k *= 0x9E3779B1u;
+	return k ^ (k >> 15);
+}
+NYX_D void htab_add (const Cta& c, uint32_t* keys, uint32_t* cnts, uint32_t mask, uint32_t key)
+{
+	uint32_t slot = htab_mix (key) & mask;
+	for (;;)
+	{
+		uint32_t k = ((volatile uint32_t*)keys)[slot];
+		if (k == 0)
+			k = atom_cas (c, keys + slot, 0u, key);
+		if (k == 0 || k == key)
+			break;
+		slot = (slot + 1) & mask;
+	}
+	atom_add (c, cnts + slot, 1u);
+}
+NYX_D uint32_t htab_get (const uint32_t* keys, const uint32_t* cnts, uint32_t mask, uint32_t key)
+{
+	uint32_t slot = htab_mix (key) & mask;
+	while (keys[slot] != key)
+		slot = (slot + 1) & mask;
+	return cnts[slot];
+}
+
+// upper bound of the distinct keys one GLSZM tile can produce: (level,size) keys -- sizes 1,2,3.. each usable by at
+// most Lmax levels with sum of sizes <= cells -- plus one key per distinct level and per distinct size
+NYX_HD uint32_t glszm_hash_slots (int Lmax, uint32_t maxcells)
+{
+	unsigned long long K = 0, cost = 0;
+	for (unsigned long long m = 1; cost < maxcells; m++)
+	{
+		unsigned long long can = (maxcells - cost) / m;
+		if (can > (unsigned long long)Lmax) can = (unsigned long long)Lmax;
+		if (!can) break;
+		K += can;
+		cost += can * m;
+	}
+	unsigned long long nl = (unsigned long long)Lmax < maxcells ? (unsigned long long)Lmax : maxcells, ns = 2;
+	while (ns * (ns + 1) / 2 <= maxcells) ns++;
+	K += nl + ns;
+	return next_pow2 ((uint32_t)(K + K / 8 + 2));
 }
 
 NYX_D uint32_t uf_find (const volatile uint32_t* parent, uint32_t x)
@@ -111,22 +142,23 @@ NYX_D void uf_unite (const Cta& c, uint32_t* parent, uint32_t a, uint32_t b)
 	}
 }
 
+struct ZoneDebug
+{
+	uint32_t* keys;		// one (level<<16 | minor) key per zone of this ROI (unsorted), capacity = ncell
+	uint32_t* nkeys;	// number of keys (zero-initialised by the host)
+};
+
 // ------------------------------------------------------------------------------------------------
 // GLSZM
 // ------------------------------------------------------------------------------------------------
-NYX_HD size_t glszm_smem_words (int ncell)
+// region: hash keys[slots] + cnts[slots] (zero on entry/exit) + lab (u16 per cell) + zone sizes (u16 per cell)
+NYX_HD size_t glszm_smem_words (uint32_t maxcells, uint32_t slots)
 {
-	return (size_t)ncell * 2 + next_pow2 ((uint32_t)ncell) + (size_t)ncell + 1 + 4;
+	return (size_t)slots * 2 + 2 * (((size_t)maxcells + 1) / 2);
 }
 
-struct ZoneDebug
-{
-	uint32_t* keys;		// sorted (level<<16 | minor) keys of this ROI's zones, capacity = ncell
-	uint32_t* nkeys;	// number of keys
-};
-
-NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem,
-	double* out, const ZoneDebug* dbg)
+NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, uint32_t maxcells,
+	uint32_t slots, double* out, const ZoneDebug* dbg)
 {
 	const int w = r.w, h = r.h, ncell = w * h;
 	if (r.imin == r.imax)
@@ -135,161 +167,198 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 			out[i] = prm.softnan;
 		return;
 	}
-	const uint32_t npad = next_pow2 ((uint32_t)ncell);
-	uint32_t* lab = mem;				// [ncell] zone label = raster index of the seed
-	uint32_t* zs = lab + ncell;			// [ncell] zone size at the seed index
-	uint32_t* keys = zs + ncell;			// [npad]
-	uint32_t* sjh = keys + npad;			// [ncell+1] zones per size
-	uint32_t* cnt = sjh + ncell + 1;		// [0] number of zones
+	uint32_t* keys = mem;						// [slots]
+	uint32_t* cnts = keys + slots;					// [slots]
+	uint16_t* lab = (uint16_t*)(cnts + slots);			// [ncell] zone label = raster index of the seed
+	uint32_t* zsw = cnts + slots + ((size_t)maxcells + 1) / 2;	// [ncell] zone size at the seed index, packed u16 pairs
+	const uint16_t* zs = (const uint16_t*)zsw;
+	const uint32_t mask = slots - 1;
 
-	for (uint32_t i = c.tid; i < npad; i += c.nthr)
-		keys[i] = KEY_PAD;
-	for (int i = c.tid; i < ncell; i += c.nthr)
+	for (int i = c.tid; i < (ncell + 1) / 2; i += c.nthr)
+		zsw[i] = 0;
+
+	// ---- forward-reachability labels, row by row
+#if NYX_DEVICE_BUILD
+	if (c.wmode)
 	{
-		zs[i] = 0;
-		sjh[i] = 0;
+		const int lane = c.tid;
+		for (int y = 0; y < h; y++)
+		{
+			uint32_t carry_lv = 0, carry_lab = 0;	// last cell of the previous 32-cell chunk of this row
+			for (int x0 = 0; x0 < w; x0 += 32)
+			{
+				const int x = x0 + lane, i = y * w + x;
+				uint32_t lv = 0, m = 0xFFFFu;
+				if (x < w)
+				{
+					lv = cell[i] & CELL_LEVEL;
+					m = (uint32_t)i;
+					if (lv && y > 0)
+					{
+						const int up = i - w;
+						if (x > 0 && (cell[up - 1] & CELL_LEVEL) == lv) m = min (m, (uint32_t)lab[up - 1]);
+						if ((cell[up] & CELL_LEVEL) == lv) m = min (m, (uint32_t)lab[up]);
+						if (x + 1 < w && (cell[up + 1] & CELL_LEVEL) == lv) m = min (m, (uint32_t)lab[up + 1]);
+					}
+				}
+				// run heads: level differs from the left neighbour (the carry for lane 0)
+				uint32_t left_lv = __shfl_up_sync (0xffffffffu, lv, 1);
+				if (lane == 0)
+					left_lv = carry_lv;
+				const bool head = !lv || left_lv != lv;
+				if (lane == 0 && !head)
+					m = min (m, carry_lab);
+				const unsigned heads = __ballot_sync (0xffffffffu, head);
+				// lane of the head of my run (bit 0 is forced: a run continuing from the carry starts at lane 0)
+				const int start = 31 - __clz ((heads | 1u) & (0xFFFFFFFFu >> (31 - lane)));
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1)
+				{
+					const uint32_t t = __shfl_up_sync (0xffffffffu, m, o);
+					if (lane - o >= start)
+						m = min (m, t);
+				}
+				if (x < w)
+					lab[i] = (uint16_t)m;
+				carry_lv = __shfl_sync (0xffffffffu, lv, 31);
+				carry_lab = __shfl_sync (0xffffffffu, m, 31);
+			}
+			__syncwarp();
+		}
 	}
-	if (c.tid == 0)
+	else
+#endif
 	{
-		sjh[ncell] = 0;
-		cnt[0] = 0;
+		c.sync();
+		for (int y = 0; y < h; y++)
+		{
+			for (int x = c.tid; x < w; x += c.nthr)
+			{
+				int i = y * w + x;
+				uint32_t lv = cell[i] & CELL_LEVEL;
+				uint32_t m = (uint32_t)i;
+				if (lv && y > 0)
+				{
+					const int up = i - w;
+					if (x > 0 && (cell[up - 1] & CELL_LEVEL) == lv) m = lab[up - 1] < m ? lab[up - 1] : m;
+					if ((cell[up] & CELL_LEVEL) == lv) m = lab[up] < m ? lab[up] : m;
+					if (x + 1 < w && (cell[up + 1] & CELL_LEVEL) == lv) m = lab[up + 1] < m ? lab[up + 1] : m;
+				}
+				lab[i] = (uint16_t)m;
+			}
+			c.sync();
+			for (int x = c.tid; x < w; x += c.nthr)
+			{
+				int i = y * w + x;
+				uint32_t lv = cell[i] & CELL_LEVEL;
+				if (!lv || (x > 0 && (cell[i - 1] & CELL_LEVEL) == lv))
+					continue;	// not the start of a horizontal run
+				uint32_t cur = lab[i];
+				for (int x2 = x + 1; x2 < w && (cell[i + (x2 - x)] & CELL_LEVEL) == lv; x2++)
+				{
+					uint32_t v = lab[i + (x2 - x)];
+					cur = v < cur ? v : cur;
+					lab[i + (x2 - x)] = (uint16_t)cur;
+				}
+			}
+			c.sync();
+		}
 	}
 	c.sync();
 
-	// ---- forward-reachability labels, row by row
-	for (int y = 0; y < h; y++)
-	{
-		for (int x = c.tid; x < w; x += c.nthr)
-		{
-			int i = y * w + x;
-			uint32_t lv = cell[i] & CELL_LEVEL;
-			uint32_t m = (uint32_t)i;
-			if (lv && y > 0)
-			{
-				const int up = i - w;
-				if (x > 0 && (cell[up - 1] & CELL_LEVEL) == lv) m = lab[up - 1] < m ? lab[up - 1] : m;
-				if ((cell[up] & CELL_LEVEL) == lv) m = lab[up] < m ? lab[up] : m;
-				if (x + 1 < w && (cell[up + 1] & CELL_LEVEL) == lv) m = lab[up + 1] < m ? lab[up + 1] : m;
-			}
-			lab[i] = m;
-		}
-		c.sync();
-		for (int x = c.tid; x < w; x += c.nthr)
-		{
-			int i = y * w + x;
-			uint32_t lv = cell[i] & CELL_LEVEL;
-			if (!lv || (x > 0 && (cell[i - 1] & CELL_LEVEL) == lv))
-				continue;	// not the start of a horizontal run
-			uint32_t cur = lab[i];
-			for (int x2 = x + 1; x2 < w && (cell[i + (x2 - x)] & CELL_LEVEL) == lv; x2++)
-			{
-				uint32_t v = lab[i + (x2 - x)];
-				cur = v < cur ? v : cur;
-				lab[i + (x2 - x)] = cur;
-			}
-		}
-		c.sync();
-	}
-
-	// ---- zone sizes, Np
+	// ---- zone sizes (packed 16-bit counters: a size is at most the cell count < 65536), Np
 	unsigned long long np[1] = { 0 };
 	for (int i = c.tid; i < ncell; i += c.nthr)
 		if (cell[i] & CELL_LEVEL)
 		{
 			np[0]++;
-			atom_add (c, zs + lab[i], 1u);
+			const uint32_t l = lab[i];
+			atom_add (c, zsw + (l >> 1), 1u << ((l & 1) * 16));
 		}
 	c.sync();
-	cta_sum_u64<1> (c, np);
 
-	// ---- zone list -> keys (level<<16 | size), size histogram
+	// ---- pass 1 over the zones (= seed cells): matrix cell (level,size) and both marginals into the hash; direct sums
+	enum { Q_NZ, Q_LAE, Q_MUJ, Q_MUI, Q_HGL, Q_NP, Q_N };
+	unsigned long long q[Q_N];
+	for (int k = 0; k < Q_N; k++)
+		q[k] = 0;
+	q[Q_NP] = np[0];
+	enum { A_SAE, A_LGL, A_SAL, A_SAH, A_LAL, A_LAH, A_N };
+	double s[A_N];
+	for (int k = 0; k < A_N; k++)
+		s[k] = 0;
 	for (int i = c.tid; i < ncell; i += c.nthr)
-		if ((cell[i] & CELL_LEVEL) && lab[i] == (uint32_t)i)
-		{
-			uint32_t sz = zs[i];
-			uint32_t slot = atom_inc_ret (c, cnt);
-			keys[slot] = ((cell[i] & CELL_LEVEL) << 16) | sz;
-			atom_add (c, sjh + sz, 1u);
-		}
-	c.sync();
-	const uint32_t nz = cnt[0];
-	bitonic_sort (c, keys, npad);
-	if (dbg && dbg->keys)
 	{
-		for (uint32_t i = c.tid; i < nz; i += c.nthr)
-			dbg->keys[i] = keys[i];
-		if (c.tid == 0)
-			*dbg->nkeys = nz;
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (!lv || lab[i] != (uint32_t)i)
+			continue;
+		const uint32_t sz = zs[i];
+		htab_add (c, keys, cnts, mask, (lv << 16) | sz);
+		htab_add (c, keys, cnts, mask, lv << 16);
+		htab_add (c, keys, cnts, mask, sz);
+		if (dbg && dbg->keys)
+			dbg->keys[atom_inc_ret (c, dbg->nkeys)] = (lv << 16) | sz;
+		q[Q_NZ] += 1;
+		q[Q_LAE] += (unsigned long long)sz * sz;			// :437-440
+		q[Q_MUJ] += sz;							// :380
+		q[Q_MUI] += lv;							// :381
+		q[Q_HGL] += (unsigned long long)lv * lv;			// :574-578
+		const double i2 = (double)lv * (double)lv, j2 = (double)sz * (double)sz;
+		s[A_SAE] += 1.0 / (double)(int)(sz * sz);			// :424-427 (int j*j)
+		s[A_LGL] += 1.0 / i2;						// :559-563
+		s[A_LAH] += i2 * j2;						// :372-375
+		s[A_LAL] += j2 / i2;
+		s[A_SAH] += i2 / j2;
+		s[A_SAL] += 1.0 / (i2 * j2);
 	}
-	if (nz == 0)	// glszm.cpp:244-248
+	c.sync();
+	cta_sum_u64<Q_N> (c, q);
+	cta_sum<A_N> (c, s);
+	const uint32_t nz = (uint32_t)q[Q_NZ];
+	if (nz == 0)	// glszm.cpp:244-248 (nothing was inserted: the table is still all zero)
 	{
 		for (int i = c.tid; i < NCOL_GLSZM; i += c.nthr)
 			out[i] = prm.softnan;
 		return;
 	}
 	const double sum = (double)nz;
-
-	// ---- integer sums
-	enum { Q_GLN, Q_SZN, Q_LAE, Q_MUJ, Q_MUI, Q_HGL, Q_N };
-	unsigned long long q[Q_N];
-	for (int k = 0; k < Q_N; k++)
-		q[k] = 0;
-	for (int j = c.tid + 1; j <= ncell; j += c.nthr)
-	{
-		unsigned long long v = sjh[j];
-		q[Q_SZN] += v * v;						// :481-485
-		q[Q_LAE] += v * (unsigned long long)j * (unsigned long long)j;	// :437-440
-		q[Q_MUJ] += v * (unsigned long long)j;				// :380
-	}
-	for_each_major (c, keys, nz, [&](uint32_t lv, uint32_t n) {
-		q[Q_GLN] += (unsigned long long)n * n;				// :450-454
-		q[Q_MUI] += (unsigned long long)n * lv;				// :381
-		q[Q_HGL] += (unsigned long long)n * lv * lv;			// :574-578
-	});
-	cta_sum_u64<Q_N> (c, q);
 	const double mui = (double)q[Q_MUI] / sum, muj = (double)q[Q_MUJ] / sum;
 
-	// ---- FP sums
-	enum { A_SAE, A_GLV, A_ZV, A_ZE, A_LGL, A_SAL, A_SAH, A_LAL, A_LAH, A_N };
-	double s[A_N];
-	for (int k = 0; k < A_N; k++)
-		s[k] = 0;
-	for (int j = c.tid + 1; j <= ncell; j += c.nthr)
+	// ---- pass 2: terms that need the counts (owner computes)
+	unsigned long long q2[2] = { 0, 0 };	// sum n_level^2 (:450-454), sum n_size^2 (:481-485)
+	double t[3] = { 0, 0, 0 };		// GLV, ZV, ZE
+	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		uint32_t v = sjh[j];
-		if (!v)
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (!lv || lab[i] != (uint32_t)i)
 			continue;
-		s[A_SAE] += (double)v / (double)(j * j);			// :424-427 (int j*j)
-		double dj = (double)j - muj;
-		s[A_ZV] += (double)v / sum * (dj * dj);				// :535-542
+		const uint32_t sz = zs[i];
+		q2[0] += htab_get (keys, cnts, mask, lv << 16);
+		q2[1] += htab_get (keys, cnts, mask, sz);
+		const double di = (double)lv - mui, dj = (double)sz - muj;
+		t[0] += di * di;									// :518-526
+		t[1] += dj * dj;									// :535-542
+		const double pn = (double)htab_get (keys, cnts, mask, (lv << 16) | sz) / sum;
+		t[2] += fast_log10 (dadd (pn, EPS_ZONES));						// :377-378
 	}
-	for_each_major (c, keys, nz, [&](uint32_t lv, uint32_t n) {
-		double in = (double)lv, di = in - mui;
-		s[A_GLV] += (double)n / sum * (di * di);			// :518-526
-		s[A_LGL] += (double)n / (in * in);				// :559-563
-	});
-	for_each_unique_key (c, keys, nz, [&](uint32_t lv, uint32_t sz, uint32_t n) {
-		double p = (double)n, i2 = (double)lv * (double)lv, j2 = (double)sz * (double)sz;
-		s[A_LAH] += p * i2 * j2;					// :372-375
-		s[A_LAL] += p * j2 / i2;
-		s[A_SAH] += p * i2 / j2;
-		s[A_SAL] += p / (i2 * j2);
-		double pn = p / sum;
-		s[A_ZE] += dmul (pn, ddiv (fast_log10 (dadd (pn, EPS_ZONES)), LOG10_2));	// :377-378
-	});
-	cta_sum<A_N> (c, s);
+	cta_sum_u64<2> (c, q2);
+	cta_sum<3> (c, t);
+	c.sync();
+	for (uint32_t i = c.tid; i < 2 * slots; i += c.nthr)	// restore the all-zero table
+		keys[i] = 0;
+	c.sync();
 	if (c.tid == 0)
 	{
 		out[S_SAE] = s[A_SAE] / sum;
 		out[S_LAE] = (double)q[Q_LAE] / sum;
-		out[S_GLN] = (double)q[Q_GLN] / sum;
-		out[S_GLNN] = (double)q[Q_GLN] / (sum * sum);
-		out[S_SZN] = (double)q[Q_SZN] / sum;
-		out[S_SZNN] = (double)q[Q_SZN] / (sum * sum);
-		out[S_ZP] = sum / (double)np[0];				// :507-511
-		out[S_GLV] = s[A_GLV];
-		out[S_ZV] = s[A_ZV];
-		out[S_ZE] = -s[A_ZE];
+		out[S_GLN] = (double)q2[0] / sum;
+		out[S_GLNN] = (double)q2[0] / (sum * sum);
+		out[S_SZN] = (double)q2[1] / sum;
+		out[S_SZNN] = (double)q2[1] / (sum * sum);
+		out[S_ZP] = sum / (double)q[Q_NP];				// :507-511
+		out[S_GLV] = t[0] / sum;
+		out[S_ZV] = t[1] / sum;
+		out[S_ZE] = -(t[2] / sum) * (1.0 / LOG10_2);
 		out[S_LGLZE] = s[A_LGL] / sum;
 		out[S_HGLZE] = (double)q[Q_HGL] / sum;
 		out[S_SALGLE] = s[A_SAL] / sum;
@@ -302,9 +371,18 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 // ------------------------------------------------------------------------------------------------
 // GLDZM
 // ------------------------------------------------------------------------------------------------
-NYX_HD size_t gldzm_smem_words (int ncell, int maxwh)
+// largest zone metric of a tile: min over the 4 directions of (steps + 1) <= (min(w,h) + 1) / 2 + 1
+NYX_HD int gldzm_nd_bound (uint32_t maxcells, int maxwh)
 {
-	return (size_t)ncell * 2 + next_pow2 ((uint32_t)ncell) + (size_t)maxwh + 2 + 4;
+	int s = 1;
+	while ((unsigned long long)s * s < maxcells) s++;	// min(w,h) <= sqrt(cells)
+	if (s > maxwh) s = maxwh;
+	return (s + 1) / 2 + 2;
+}
+// region: P[Lmax+1][Nd] + Ri[Lmax+1] + Cd[Nd] (zero on entry/exit) + parent[ncell] + zmin[ncell]
+NYX_HD size_t gldzm_smem_words (int Lmax, int Nd, uint32_t maxcells)
+{
+	return (size_t)(Lmax + 1) * Nd + (Lmax + 1) + Nd + 2 * (size_t)maxcells;
 }
 
 // distance of cell (x,y) to the ROI/tile border exactly as gldzm.cpp:306-351 (zeros = level-0 cells of the binned tile)
@@ -340,11 +418,10 @@ NYX_D int gldzm_dist2border (const uint32_t* cell, int w, int h, int x, int y, b
 	return m == 0 ? 1 : m;
 }
 
-NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem,
-	double* out, const ZoneDebug* dbg)
+NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax, int Nd,
+	uint32_t maxcells, double* out, const ZoneDebug* dbg)
 {
 	const int w = r.w, h = r.h, ncell = w * h;
-	const int maxwh = w > h ? w : h;
 	if (r.imin == r.imax)	// gldzm.cpp:266-289
 	{
 		for (int i = c.tid; i < NCOL_GLDZM; i += c.nthr)
@@ -352,37 +429,43 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		return;
 	}
 	const bool ibsi = prm.ibsi != 0;
-	const uint32_t npad = next_pow2 ((uint32_t)ncell);
-	uint32_t* parent = mem;				// [ncell]
-	uint32_t* zmin = parent + ncell;		// [ncell] zone metric at the root
-	uint32_t* keys = zmin + ncell;			// [npad]
-	uint32_t* sdh = keys + npad;			// [maxwh+2] zones per distance
-	uint32_t* cnt = sdh + maxwh + 2;
+	uint32_t* P = mem;					// [Lmax+1][Nd]  zones per (level, metric)
+	uint32_t* Ri = P + (size_t)(Lmax + 1) * Nd;		// [Lmax+1]      zones per level
+	uint32_t* Cd = Ri + (Lmax + 1);				// [Nd]          zones per metric
+	uint32_t* parent = Cd + Nd;				// [ncell]
+	uint32_t* zmin = parent + maxcells;			// [ncell] zone metric at the root
+	FastDiv fw;
+	fw.init ((uint32_t)w);
 
-	for (uint32_t i = c.tid; i < npad; i += c.nthr)
-		keys[i] = KEY_PAD;
+	// ---- 4-connected components of equal level: every cell starts hooked to the head of its horizontal same-level run,
+	// then one union per vertically adjacent pair of RUNS (a pair whose left neighbours already joined the same two
+	// runs is skipped), so the union-find only ever sees run heads
 	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		parent[i] = (uint32_t)i;
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		int hd = i;
+		if (!(ibsi && !lv))
+		{
+			int x = i - (int)fw.div ((uint32_t)i) * w;
+			while (x > 0 && (cell[hd - 1] & CELL_LEVEL) == lv)
+			{
+				hd--;
+				x--;
+			}
+		}
+		parent[i] = (uint32_t)hd;
 		zmin[i] = 0x7FFFFFFFu;
 	}
-	for (int i = c.tid; i < maxwh + 2; i += c.nthr)
-		sdh[i] = 0;
-	if (c.tid == 0)
-		cnt[0] = 0;
 	c.sync();
-
-	// ---- 4-connected components of equal level
-	for (int i = c.tid; i < ncell; i += c.nthr)
+	for (int i = c.tid + w; i < ncell; i += c.nthr)
 	{
-		uint32_t lv = cell[i] & CELL_LEVEL;
-		if (ibsi && !lv)
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if ((ibsi && !lv) || (cell[i - w] & CELL_LEVEL) != lv)
 			continue;
-		int y = i / w, x = i - y * w;
-		if (x > 0 && (cell[i - 1] & CELL_LEVEL) == lv)
-			uf_unite (c, parent, (uint32_t)i, (uint32_t)(i - 1));
-		if (y > 0 && (cell[i - w] & CELL_LEVEL) == lv)
-			uf_unite (c, parent, (uint32_t)i, (uint32_t)(i - w));
+		const int x = i - (int)fw.div ((uint32_t)i) * w;
+		if (x > 0 && (cell[i - 1] & CELL_LEVEL) == lv && (cell[i - w - 1] & CELL_LEVEL) == lv)
+			continue;
+		uf_unite (c, parent, (uint32_t)i, (uint32_t)(i - w));
 	}
 	c.sync();
 	// ---- zone metric = min member distance
@@ -391,86 +474,85 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		uint32_t lv = cell[i] & CELL_LEVEL;
 		if (ibsi && !lv)
 			continue;
-		int y = i / w, x = i - y * w;
+		int y = (int)fw.div ((uint32_t)i), x = i - y * w;
 		uint32_t root = uf_find (parent, (uint32_t)i);
 		atom_min (c, zmin + root, (uint32_t)gldzm_dist2border (cell, w, h, x, y, !ibsi));
 	}
 	c.sync();
-	for (int i = c.tid; i < ncell; i += c.nthr)
-	{
-		uint32_t lv = cell[i] & CELL_LEVEL;
-		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
-			continue;
-		uint32_t d = zmin[i];
-		uint32_t slot = atom_inc_ret (c, cnt);
-		keys[slot] = (lv << 16) | d;
-		atom_add (c, sdh + d, 1u);
-	}
-	c.sync();
-	const uint32_t nz = cnt[0];
-	bitonic_sort (c, keys, npad);
-	if (dbg && dbg->keys)
-	{
-		for (uint32_t i = c.tid; i < nz; i += c.nthr)
-			dbg->keys[i] = keys[i];
-		if (c.tid == 0)
-			*dbg->nkeys = nz;
-	}
-	const double Ns = (double)nz, Nv = (double)r.area;
 
-	enum { Q_ZDNU, Q_LDE, Q_ZDM, Q_GLNU, Q_GLM, Q_HGL, Q_N };
+	// ---- pass 1 over the zones (= roots)
+	enum { Q_NS, Q_LDE, Q_ZDM, Q_GLM, Q_HGL, Q_N };
 	unsigned long long q[Q_N];
 	for (int k = 0; k < Q_N; k++)
 		q[k] = 0;
-	enum { A_SDE, A_LGL, A_SDL, A_SDH, A_LDL, A_LDH, A_ZDE, A_N };
+	enum { A_SDE, A_LGL, A_SDL, A_SDH, A_LDL, A_LDH, A_N };
 	double s[A_N];
 	for (int k = 0; k < A_N; k++)
 		s[k] = 0;
-	for (int d = c.tid + 1; d <= maxwh + 1; d += c.nthr)
+	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		unsigned long long v = sdh[d];
-		if (!v)
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
 			continue;
-		q[Q_ZDNU] += v * v;						// gldzm.cpp:404
-		q[Q_LDE] += v * (unsigned long long)d * (unsigned long long)d;	// :403
-		q[Q_ZDM] += v * (unsigned long long)d;				// :445
-		s[A_SDE] += (double)v / (double)d / (double)d;			// :402
+		const uint32_t dd = zmin[i];
+		atom_add (c, P + (size_t)lv * Nd + dd, 1u);
+		atom_add (c, Ri + lv, 1u);
+		atom_add (c, Cd + dd, 1u);
+		if (dbg && dbg->keys)
+			dbg->keys[atom_inc_ret (c, dbg->nkeys)] = (lv << 16) | dd;
+		q[Q_NS] += 1;
+		q[Q_LDE] += (unsigned long long)dd * dd;			// gldzm.cpp:403
+		q[Q_ZDM] += dd;							// :445
+		q[Q_GLM] += lv;							// :444
+		q[Q_HGL] += (unsigned long long)lv * lv;			// :422
+		const double g = (double)lv, d = (double)dd;
+		s[A_SDE] += 1.0 / d / d;					// :402
+		s[A_LGL] += 1.0 / (g * g);					// :421
+		s[A_SDL] += 1.0 / g / g / d / d;				// :440
+		s[A_SDH] += g * g / d / d;					// :441
+		s[A_LDL] += d * d / g / g;					// :442
+		s[A_LDH] += g * g * d * d;					// :443
 	}
-	for_each_major (c, keys, nz, [&](uint32_t lv, uint32_t n) {
-		q[Q_GLNU] += (unsigned long long)n * n;				// :423
-		q[Q_GLM] += (unsigned long long)n * lv;				// :444
-		q[Q_HGL] += (unsigned long long)n * lv * lv;			// :422
-		double g = (double)lv;
-		s[A_LGL] += (double)n / (g * g);				// :421
-	});
-	for_each_unique_key (c, keys, nz, [&](uint32_t lv, uint32_t dd, uint32_t n) {
-		double p = (double)n, g = (double)lv, d = (double)dd;
-		s[A_SDL] += p / g / g / d / d;					// :440
-		s[A_SDH] += g * g * p / d / d;					// :441
-		s[A_LDL] += d * d * p / g / g;					// :442
-		s[A_LDH] += g * g * d * d * p;					// :443
-		s[A_ZDE] += p / Ns * log2 (p / Ns + EPS_ZONES);			// :446
-	});
+	c.sync();
 	cta_sum_u64<Q_N> (c, q);
 	cta_sum<A_N> (c, s);
+	const double Ns = (double)q[Q_NS], Nv = (double)r.area;
 	const double glm = (double)q[Q_GLM] / Ns, zdm = (double)q[Q_ZDM] / Ns;
-	double v2[2] = { 0, 0 };
-	for_each_major (c, keys, nz, [&](uint32_t lv, uint32_t n) {
-		double dif = (double)lv - glm;
-		v2[0] += dif * dif * ((double)n / Ns);				// :468-471
-	});
-	for (int d = c.tid + 1; d <= maxwh + 1; d += c.nthr)
+
+	// ---- pass 2: terms that need the counts (owner computes)
+	unsigned long long q2[2] = { 0, 0 };	// sum n_level^2 (:423), sum n_metric^2 (:404)
+	double t[3] = { 0, 0, 0 };		// GLV, ZDV, ZDE
+	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
-		uint32_t v = sdh[d];
-		if (!v)
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
 			continue;
-		double dif = (double)d - zdm;
-		v2[1] += dif * dif * ((double)v / Ns);				// :474-476
+		const uint32_t dd = zmin[i];
+		q2[0] += Ri[lv];
+		q2[1] += Cd[dd];
+		const double di = (double)lv - glm, dj = (double)dd - zdm;
+		t[0] += di * di;						// :468-471
+		t[1] += dj * dj;						// :474-476
+		const double p = (double)P[(size_t)lv * Nd + dd] / Ns;
+		t[2] += log2 (p + EPS_ZONES);					// :446
 	}
-	cta_sum<2> (c, v2);
+	cta_sum_u64<2> (c, q2);
+	cta_sum<3> (c, t);
+	c.sync();
+	// ---- pass 3: restore the all-zero region
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
+			continue;
+		P[(size_t)lv * Nd + zmin[i]] = 0;
+	}
+	for (int k = c.tid; k < Lmax + 1 + Nd; k += c.nthr)
+		Ri[k] = 0;
+	c.sync();
 	if (c.tid == 0)
 	{
-		double zdnu = (double)q[Q_ZDNU] / Ns, glnu = (double)q[Q_GLNU] / Ns;
+		const double zdnu = (double)q2[1] / Ns, glnu = (double)q2[0] / Ns;
 		out[Z_SDE] = s[A_SDE] / Ns;
 		out[Z_LDE] = (double)q[Q_LDE] / Ns;
 		out[Z_LGLZE] = s[A_LGL] / Ns;
@@ -485,10 +567,10 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		out[Z_ZDNUN] = zdnu / Ns;					// :411
 		out[Z_ZP] = Ns / Nv;						// :455
 		out[Z_GLM] = glm;
-		out[Z_GLV] = v2[0];
+		out[Z_GLV] = t[0] / Ns;
 		out[Z_ZDM] = zdm;
-		out[Z_ZDV] = v2[1];
-		out[Z_ZDE] = -s[A_ZDE];
+		out[Z_ZDV] = t[1] / Ns;
+		out[Z_ZDE] = -(t[2] / Ns);
 	}
 }
 

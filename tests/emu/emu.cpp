@@ -89,13 +89,15 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 	}
 	if (fam_mask & 8)
 	{
-		std::vector<uint32_t> mem (gldzm_smem_words (ncell, std::max (r.w, r.h)));
-		gldzm_body (c, r, prm, cell.data(), mem.data(), out + COL_GLDZM, nullptr);
+		const int Nd = gldzm_nd_bound ((uint32_t)ncell, std::max (r.w, r.h));
+		std::vector<uint32_t> mem (gldzm_smem_words (Lmax, Nd, (uint32_t)ncell));
+		gldzm_body (c, r, prm, cell.data(), mem.data(), Lmax, Nd, (uint32_t)ncell, out + COL_GLDZM, nullptr);
 	}
 	if (fam_mask & 16)
 	{
-		std::vector<uint32_t> mem (glszm_smem_words (ncell));
-		glszm_body (c, r, prm, cell.data(), mem.data(), out + COL_GLSZM, nullptr);
+		const uint32_t slots = glszm_hash_slots (Lmax, (uint32_t)ncell);
+		std::vector<uint32_t> mem (glszm_smem_words ((uint32_t)ncell, slots));
+		glszm_body (c, r, prm, cell.data(), mem.data(), (uint32_t)ncell, slots, out + COL_GLSZM, nullptr);
 	}
 	if (fam_mask & 32)
 	{
