@@ -173,11 +173,11 @@ def main():
     ncols = len(eng.columns)
 
     def step_resident():
-        tab, _ = eng.featurize_ptr(d_int.data_ptr(), True, d_lab.data_ptr(), 1, H, W, on_device=True)
+        tab, _ = eng.featurize_ptr(d_int.data_ptr(), True, d_lab.data_ptr(), 1, H, W, on_device=True, copy=False)
         return tab
 
     def step_e2e():
-        tab, _ = eng.featurize_ptr(h_int.data_ptr(), True, h_lab.data_ptr(), 1, H, W, on_device=False)
+        tab, _ = eng.featurize_ptr(h_int.data_ptr(), True, h_lab.data_ptr(), 1, H, W, on_device=False, copy=False)
         return tab
 
     # ---- resident (value)

@@ -43,6 +43,8 @@ typedef struct nyxb200_settings
 	int32_t glcm_symmetric;     /* GLCMFeature::symmetric_glcm, default 0 */
 	int32_t verbose;
 	double soft_nan;            /* NyxSetting::SOFTNAN (resultOptions.noval), default 0.0 */
+	int32_t dim;                /* 2: Nyxus (2D feature codes, nyxb200_featurize_2d_*); 3: Nyxus3D (Feature3D codes, nyxb200_featurize_3d_*) */
+	int32_t reserved;
 } nyxb200_settings;
 
 /* Numeric result table, row-major, `ncols` doubles per row: ROI_label, t_index, then the enabled feature columns
@@ -71,7 +73,9 @@ int nyxb200_select_features (nyxb200_ctx* ctx, const char* const* names, int n);
 int nyxb200_num_columns (const nyxb200_ctx* ctx);               /* feature columns (without ROI_label, t_index) */
 const char* nyxb200_column_name (const nyxb200_ctx* ctx, int i); /* e.g. "GLCM_ASM_45" */
 int nyxb200_column_code (const nyxb200_ctx* ctx, int i);         /* Feature2D code of column i */
-/* replaces set_metaparam_imp("glcm/offset=..") etc. for the keys this path reads (env_metaparams.cpp:63-247) */
+/* replaces set_metaparam_imp("glcm/offset=..") etc. for the keys this path reads (env_metaparams.cpp:63-247):
+ * "glcm/offset", "glcm/greydepth", "coarse_gray_depth", "ibsi", "glcm/symmetric", "soft_nan", and for dim == 3
+ * "3glcm/greydepth", "3glszm/greydepth", "3ngtdm/greydepth", "3ngtdm/radius" */
 int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value);
 
 /* THE hot path.  Host buffers (pageable or pinned), `n_img` images of H x W, row-major, C-contiguous:
@@ -87,6 +91,19 @@ int nyxb200_featurize_2d_u16 (nyxb200_ctx* ctx, const uint16_t* inten, const uin
  * inten_is_u16 selects the pixel type.  The table still comes back to (pinned) host memory. */
 int nyxb200_featurize_2d_device (nyxb200_ctx* ctx, const void* inten, int inten_is_u16, const uint32_t* label,
 	int n_img, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+/* 3D (dim == 3 contexts): `n_vol` volumes of D x H x W voxels, voxel (z,y,x) at (z*H + y)*W + x.  Replaces the compute
+ * part of featurize_fname_lists_3D_imp -> processDataset_3D_segmented (new_bindings_py.cpp:753-856,
+ * workflow_3d_segmented.cpp:35-260): gatherRoisMetrics_3D (phase1.cpp:248-366), scanTrivialRois_3D +
+ * allocateTrivialRoisBuffers_3D (phase2_3d.cpp:24-158,816-840) and the D3_VoxelIntensityFeatures / D3_GLCM_feature /
+ * D3_GLSZM_feature / D3_NGTDM_feature reducers (reduce_trivial_rois.cpp:342-413).  File decoding (NIfTI) stays with the
+ * caller.  Feature names are the reference's "3COV", "3GLCM_ASM", ... and the groups *3D_ALL_INTENSITY*, *3D_GLCM*,
+ * *3D_GLSZM*, *3D_NGTDM*. */
+int nyxb200_featurize_3d_u32 (nyxb200_ctx* ctx, const uint32_t* inten, const uint32_t* label,
+	int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+int nyxb200_featurize_3d_u16 (nyxb200_ctx* ctx, const uint16_t* inten, const uint32_t* label,
+	int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+int nyxb200_featurize_3d_device (nyxb200_ctx* ctx, const void* inten, int inten_is_u16, const uint32_t* label,
+	int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t);
 
 /* ---- measurement hooks ---- */

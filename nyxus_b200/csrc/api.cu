@@ -18,15 +18,19 @@ namespace
 {
 
 struct FeatureDef { const char* name; int code; int family; int col0; int ncols; };
-const FeatureDef g_features[] = {
+const FeatureDef g_features2d[] = {
 #include "nyx_feature_table.inc"
 };
-constexpr int NFEATURES = (int)(sizeof (g_features) / sizeof (g_features[0]));
+struct FeatureDef3 { const char* name; int code; int family; int col0; };
+const FeatureDef3 g_features3d_src[] = {
+#include "nyx_feature_table3d.inc"
+};
+constexpr int NFEATURES_MAX = 256;
 
 struct GroupDef { const char* name; int fam_mask; };
 // reference featureset.cpp:650-668 (2D group names); *ALL_TEXTURE* is defined HERE as the union of the seven 2D
 // texture groups (the reference has no 2D *ALL_TEXTURE*, only *3D_ALL_TEXTURE*: env_features.cpp:199-337,383-393)
-const GroupDef g_groups[] = {
+const GroupDef g_groups2d[] = {
 	{ "*ALL_INTENSITY*", 1 << FAM_INT },
 	{ "*ALL_GLCM*", 1 << FAM_GLCM },
 	{ "*ALL_GLRLM*", 1 << FAM_GLRLM },
@@ -37,6 +41,16 @@ const GroupDef g_groups[] = {
 	{ "*ALL_NGTDM*", 1 << FAM_NGTDM },
 	{ "*ALL_TEXTURE*", (1 << FAM_GLCM) | (1 << FAM_GLRLM) | (1 << FAM_GLDZM) | (1 << FAM_GLSZM) | (1 << FAM_GLDM) | (1 << FAM_NGLDM) | (1 << FAM_NGTDM) },
 };
+// reference featureset.cpp:940-953 (3D group names) for the 3D families on this path
+const GroupDef g_groups3d[] = {
+	{ "*3D_ALL_INTENSITY*", 1 << FAM3_INT },
+	{ "*3D_GLCM*", 1 << FAM3_GLCM },
+	{ "*3D_GLSZM*", 1 << FAM3_GLSZM },
+	{ "*3D_NGTDM*", 1 << FAM3_NGTDM },
+};
+// 3D groups of the reference that contain families outside this path (3D GLRLM / GLDM / GLDZM / NGLDM, morphology, moments)
+const char* g_groups3d_unbuilt[] = { "*3D_ALL*", "*3D_ALL_TEXTURE*", "*3D_ALL_MORPHOLOGY*", "*3D_GLDM*", "*3D_GLDZM*", "*3D_GLRLM*",
+	"*3D_NGLDM*", "*3D_ALL_NEIGHBOR*", "*3D_MOMENTS*" };
 
 const char* g_stage_names[NYXB200_NSTAGES] = { "h2d", "init", "scan", "compact", "pack", "intensity", "glcm", "glrlm", "gldzm",
 	"glszm", "gldm", "ngldm", "ngtdm", "select", "d2h", "total" };
@@ -86,7 +100,8 @@ struct nyxb200_ctx
 	bool ev_used[NYXB200_NSTAGES + 2];
 
 	// selection
-	bool feat_on[NFEATURES];
+	std::vector<FeatureDef> feats;	// the context's feature table (2D or 3D codes)
+	bool feat_on[NFEATURES_MAX];
 	int fam_mask = 0;
 	std::vector<int> sel_cols;		// canonical column of every output column
 	std::vector<std::string> sel_names;
@@ -98,6 +113,7 @@ struct nyxb200_ctx
 	DevBuf<uint8_t> d_inten;
 	DevBuf<uint32_t> d_label;
 	DevBuf<LabelStat> d_stats;
+	DevBuf<uint2> d_ztab;
 	uint32_t stats_cap = 1u << 20;
 	DevBuf<SlideInfo> d_info;
 	DevBuf<uint32_t> d_blkcnt;
@@ -120,6 +136,8 @@ struct nyxb200_ctx
 
 	double* h_out = nullptr;		// pinned result buffer (grow-only)
 	size_t h_out_cap = 0, h_out_used = 0;
+
+	int glszm3_greydepth = 0, ngtdm3_greydepth = 0, ngtdm3_radius = 0;	// env_features.cpp:712-736: zero unless set
 
 	float stage_ms[NYXB200_NSTAGES] {};
 	int64_t counts[4] {};
@@ -153,11 +171,11 @@ void rebuild_selection (nyxb200_ctx* ctx)
 	ctx->fam_mask = 0;
 	static const int angles[4] = { 0, 45, 90, 135 };
 	// enabled features in ascending code order (reference featureset.cpp getEnabledFeatures; the table is already sorted)
-	for (int i = 0; i < NFEATURES; i++)
+	for (int i = 0; i < (int)ctx->feats.size(); i++)
 	{
 		if (!ctx->feat_on[i])
 			continue;
-		const FeatureDef& f = g_features[i];
+		const FeatureDef& f = ctx->feats[i];
 		ctx->fam_mask |= 1 << f.family;
 		for (int k = 0; k < f.ncols; k++)
 		{
@@ -204,6 +222,8 @@ void nyxb200_default_settings (nyxb200_settings* s)
 	s->glcm_symmetric = 0;		// glcm.cpp:8
 	s->verbose = 0;
 	s->soft_nan = 0.0;		// cli_result_options.h:75
+	s->dim = 2;
+	s->reserved = 0;
 }
 
 const char* nyxb200_last_error (const nyxb200_ctx* ctx)
@@ -220,6 +240,8 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out)
 		return fail (nullptr, NYXB200_EINVAL, "Custom number of grayscale levels (parameter coarse_gray_depth, default=64) must be non-negative.");
 	if (s->coarse_gray_depth > 65535)
 		return fail (nullptr, NYXB200_EUNSUPPORTED, "coarse_gray_depth > 65535 is not supported");
+	if (s->dim != 2 && s->dim != 3)
+		return fail (nullptr, NYXB200_EINVAL, "dim must be 2 or 3");
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount (&ndev);
 	if (e != cudaSuccess || ndev == 0)
@@ -236,7 +258,13 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out)
 	nyxb200_ctx* ctx = new nyxb200_ctx();
 	ctx->st = *s;
 	ctx->sm_count = prop.multiProcessorCount;
-	for (int i = 0; i < NFEATURES; i++)
+	if (s->dim == 3)
+		for (const auto& f : g_features3d_src)
+			ctx->feats.push_back ({ f.name, f.code, f.family, f.col0, 1 });
+	else
+		for (const auto& f : g_features2d)
+			ctx->feats.push_back (f);
+	for (int i = 0; i < NFEATURES_MAX; i++)
 		ctx->feat_on[i] = false;
 	if (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
 	{
@@ -256,7 +284,7 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 		return;
 	cudaSetDevice (ctx->st.device);
 	cudaStreamSynchronize (ctx->stream);
-	ctx->d_sel.release(); ctx->d_inten.release(); ctx->d_label.release(); ctx->d_stats.release(); ctx->d_info.release();
+	ctx->d_ztab.release(); ctx->d_sel.release(); ctx->d_inten.release(); ctx->d_label.release(); ctx->d_stats.release(); ctx->d_info.release();
 	ctx->d_blkcnt.release(); ctx->d_blkarea.release(); ctx->d_rois.release(); ctx->d_classslot.release(); ctx->d_tlist.release();
 	ctx->d_alist.release(); ctx->d_bases.release(); ctx->d_cloud.release(); ctx->d_full.release(); ctx->d_sel_out.release();
 	ctx->d_scratch.release(); ctx->d_rowoff.release(); ctx->d_dbg.release(); ctx->d_dbgf.release();
@@ -272,33 +300,41 @@ int nyxb200_select_features (nyxb200_ctx* ctx, const char* const* names, int n)
 {
 	if (!ctx || (!names && n))
 		return fail (ctx, NYXB200_EINVAL, "null argument");
-	bool on[NFEATURES];
-	for (int i = 0; i < NFEATURES; i++)
+	bool on[NFEATURES_MAX];
+	const int nf = (int)ctx->feats.size();
+	const bool d3 = ctx->st.dim == 3;
+	for (int i = 0; i < NFEATURES_MAX; i++)
 		on[i] = false;	// env_features.cpp:459 "initially, no features are enabled"
 	for (int k = 0; k < n; k++)
 	{
 		const char* s = names[k];
 		bool found = false;
-		for (const auto& g : g_groups)
-			if (!strcmp (g.name, s))
+		const GroupDef* groups = d3 ? g_groups3d : g_groups2d;
+		const int ngroups = d3 ? (int)(sizeof (g_groups3d) / sizeof (g_groups3d[0])) : (int)(sizeof (g_groups2d) / sizeof (g_groups2d[0]));
+		for (int gi = 0; gi < ngroups && !found; gi++)
+			if (!strcmp (groups[gi].name, s))
 			{
-				for (int i = 0; i < NFEATURES; i++)
-					if (g.fam_mask & (1 << g_features[i].family))
+				for (int i = 0; i < nf; i++)
+					if (groups[gi].fam_mask & (1 << ctx->feats[i].family))
 						on[i] = true;
 				found = true;
-				break;
 			}
 		if (found)
 			continue;
-		for (int i = 0; i < NFEATURES; i++)
-			if (!strcmp (g_features[i].name, s))
+		if (d3)
+			for (const char* g : g_groups3d_unbuilt)
+				if (!strcmp (g, s))
+					return fail (ctx, NYXB200_EUNSUPPORTED, "feature group '%s' contains 3D families outside this path "
+						"(built: *3D_ALL_INTENSITY*, *3D_GLCM*, *3D_GLSZM*, *3D_NGTDM*)", s);
+		for (int i = 0; i < nf; i++)
+			if (!strcmp (ctx->feats[i].name, s))
 			{
 				on[i] = true;
 				found = true;
 				break;
 			}
-		if (!found)	// env_features.cpp:496
-			return fail (ctx, NYXB200_EINVAL, "Error: '%s' is not a valid 2D feature name ", s);
+		if (!found)	// env_features.cpp:496,507
+			return fail (ctx, NYXB200_EINVAL, "Error: '%s' is not a valid %s feature name ", s, d3 ? "3D" : "2D");
 	}
 	memcpy (ctx->feat_on, on, sizeof (on));
 	rebuild_selection (ctx);
@@ -338,6 +374,32 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 		ctx->st.glcm_symmetric = iv != 0;
 	else if (!strcmp (key, "soft_nan"))
 		ctx->st.soft_nan = value;
+	else if (!strcmp (key, "3glcm/greydepth"))		// env_metaparams.cpp:109-120
+	{
+		if (iv <= 0 || iv > 65535)
+			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 1..65535");
+		ctx->st.coarse_gray_depth = iv;
+	}
+	else if (!strcmp (key, "3glszm/greydepth"))		// env_metaparams.cpp:222-233
+	{
+		if (iv < 0 || iv > 65535)
+			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 0..65535");
+		ctx->glszm3_greydepth = iv;
+	}
+	else if (!strcmp (key, "3ngtdm/greydepth"))		// env_metaparams.cpp:175-186
+	{
+		if (iv < 0 || iv > 65535)
+			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 0..65535");
+		ctx->ngtdm3_greydepth = iv;
+	}
+	else if (!strcmp (key, "3ngtdm/radius"))		// env_metaparams.cpp:187-197
+	{
+		if (iv < 0)
+			return fail (ctx, NYXB200_EINVAL, "3ngtdm/radius: expecting a positive integer");
+		if (iv > 1)
+			return fail (ctx, NYXB200_EUNSUPPORTED, "3ngtdm/radius > 1 is not built (26-neighbourhood only)");
+		ctx->ngtdm3_radius = iv;
+	}
 	else
 		return fail (ctx, NYXB200_EINVAL, "unknown parameter '%s'", key);
 	return NYXB200_OK;
@@ -440,7 +502,7 @@ int launch_family (nyxb200_ctx* ctx, int fam, const ImageView& im, const uint32_
 	return 0;
 }
 
-int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const Params& prm, uint32_t maxarea, double* out)
+int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const Params& prm, uint32_t maxarea, double* out, int ostride)
 {
 	if (!n)
 		return 0;
@@ -453,7 +515,7 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 			return NYXB200_ECUDA;
 		const int per_sm = (int)std::max<size_t> (1, std::min<size_t> (16, (size_t)(227 * 1024) / (bytes + 1024)));
 		const int grid = (int)std::min<uint32_t> ((n + ROI_WARPS - 1) / ROI_WARPS, (uint32_t)(ctx->sm_count * per_sm));
-		k_roi_intensity_w<<<grid, ROI_THREADS, bytes, ctx->stream>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, out, NCOL_ALL, memw);
+		k_roi_intensity_w<<<grid, ROI_THREADS, bytes, ctx->stream>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, out, ostride, memw);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		return 0;
@@ -471,7 +533,41 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 	if (set_smem (ctx, k_roi_intensity, smem_words * 4))
 		return NYXB200_ECUDA;
 	k_roi_intensity<<<grid, ROI_THREADS, smem_words * 4, ctx->stream>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
-		NCOL_ALL, gs, memw);
+		ostride, gs, memw);
+	CU (cudaGetLastError());
+	ctx->counts[0]++;
+	return 0;
+}
+
+// ---- 3D families: CTA per ROI on the AABB cube
+template <int FAM3, bool P16>
+int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list, uint32_t n, const Params& prm, int greyinfo,
+	int Lmax, uint32_t maxcells, double* out)
+{
+	if (!n)
+		return 0;
+	const size_t tilew = (maxcells + 1) & ~(size_t)1;
+	size_t famw = 0;
+	if (FAM3 == FAM3_GLCM) famw = P16 ? glcm_smem_words<true> (Lmax, 4) : glcm_smem_words<false> (Lmax, 4);
+	if (FAM3 == FAM3_GLSZM) famw = glszm3d_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));
+	if (FAM3 == FAM3_NGTDM) famw = ngtdm3d_smem_words (Lmax);
+	famw = (famw + 1) & ~(size_t)1;
+	size_t smem_words = RED_WORDS + tilew + famw;
+	uint32_t* gs = nullptr;
+	int grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 8);
+	if (smem_words > SMEM_LIMIT_WORDS)
+	{
+		smem_words = RED_WORDS + tilew;
+		grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 2);
+		CU (ctx->d_scratch.reserve ((size_t)grid * famw));
+		gs = ctx->d_scratch.p;
+		CU (cudaMemsetAsync (gs, 0, (size_t)grid * famw * 4, ctx->stream));
+	}
+	auto kern = k_roi_family3<FAM3, P16>;
+	if (set_smem (ctx, kern, smem_words * 4))
+		return NYXB200_ECUDA;
+	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->stream>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,
+		NCOL3_ALL, gs, famw);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
 	return 0;
@@ -485,6 +581,9 @@ Params make_params (const nyxb200_ctx* ctx)
 	p.glcm_offset = ctx->st.glcm_offset;
 	p.glcm_symmetric = ctx->st.glcm_symmetric;
 	p.softnan = ctx->st.soft_nan;
+	p.glszm3_greydepth = ctx->glszm3_greydepth;
+	p.ngtdm3_greydepth = ctx->ngtdm3_greydepth;
+	p.ngtdm3_radius = ctx->ngtdm3_radius;
 	return p;
 }
 
@@ -515,8 +614,10 @@ int reserve_pinned_out (nyxb200_ctx* ctx, size_t n)
 // One slide already resident on the device.  Appends its rows to the context's pinned table buffer.
 int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t* nrows_out)
 {
-	const unsigned long long npix = (unsigned long long)im.H * (unsigned long long)im.W;
-	const Params prm = make_params (ctx);
+	const unsigned long long npix = (unsigned long long)im.D * (unsigned long long)im.H * (unsigned long long)im.W;
+	const bool d3 = ctx->st.dim == 3;
+	const int ncol_all = d3 ? NCOL3_ALL : NCOL_ALL;
+	Params prm = make_params (ctx);
 	cudaStream_t s = ctx->stream;
 	CU (ctx->d_info.reserve (1));
 	SlideInfo info;
@@ -525,8 +626,14 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	for (int attempt = 0; ; attempt++)
 	{
 		CU (ctx->d_stats.reserve (ctx->stats_cap));
+		uint2* ztab = nullptr;
+		if (d3)
+		{
+			CU (ctx->d_ztab.reserve (ctx->stats_cap));
+			ztab = ctx->d_ztab.p;
+		}
 		stage_begin (ctx, ST_INIT);
-		k_init_stats<<<(ctx->stats_cap + 255) / 256, 256, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p);
+		k_init_stats<<<(ctx->stats_cap + 255) / 256, 256, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab);
 		CU (cudaGetLastError());
 		stage_begin (ctx, ST_SCAN);
 		const bool vec = ((uintptr_t)im.label % 16 == 0) && ((uintptr_t)im.inten % (im.inten_u16 ? 8 : 16) == 0);
@@ -535,13 +642,13 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		grid = std::max (grid, 1);
 		if (im.inten_u16)
 		{
-			if (vec) k_scan_stats<true, true><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p);
-			else k_scan_stats<true, false><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p);
+			if (vec) k_scan_stats<true, true><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab, (uint32_t)im.H);
+			else k_scan_stats<true, false><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab, (uint32_t)im.H);
 		}
 		else
 		{
-			if (vec) k_scan_stats<false, true><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p);
-			else k_scan_stats<false, false><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p);
+			if (vec) k_scan_stats<false, true><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab, (uint32_t)im.H);
+			else k_scan_stats<false, false><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab, (uint32_t)im.H);
 		}
 		CU (cudaGetLastError());
 		ctx->counts[0] += 2;
@@ -590,7 +697,7 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	{
 		const uint32_t nblk = (ctx->stats_cap + CB - 1) / CB;
 		k_compact_write<<<nblk, CB, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ctx->d_blkcnt.p, ctx->d_blkarea.p,
-			ctx->d_rois.p, ctx->d_classslot.p);
+			ctx->d_rois.p, ctx->d_classslot.p, d3 ? ctx->d_ztab.p : nullptr);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		CU (cudaMemcpyAsync (&info, ctx->d_info.p, sizeof (info), cudaMemcpyDeviceToHost, s));
@@ -619,8 +726,10 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	ctx->last_info = info;
 
 	// ---- canonical table
-	CU (ctx->d_full.reserve ((size_t)nroi * NCOL_ALL));
-	CU (cudaMemsetAsync (ctx->d_full.p, 0, (size_t)nroi * NCOL_ALL * sizeof (double), s));
+	CU (ctx->d_full.reserve ((size_t)nroi * ncol_all));
+	CU (cudaMemsetAsync (ctx->d_full.p, 0, (size_t)nroi * ncol_all * sizeof (double), s));
+	if (d3)	// 3d_intensity.cpp:56-61: ROI range over the scanned range of the labelled voxels (slideprops.cpp:305-327)
+		prm.covered_den = (double)info.max_inten - (double)(~info.inv_min_inten);
 
 	// ---- CSR cloud (first-order only)
 	stage_begin (ctx, ST_PACK);
@@ -638,7 +747,7 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		if (nlarge)
 		{
 			const int grid = (int)std::min<uint32_t> (nlarge, (uint32_t)ctx->sm_count * 4);
-			const size_t stride = (size_t)im.H + 2;
+			const size_t stride = (size_t)im.H * (size_t)im.D + 2;
 			CU (ctx->d_rowoff.reserve ((size_t)grid * stride));
 			k_pack_cloud_large<<<grid, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->tbase[NCLASS], nlarge, ctx->d_cloud.p,
 				ctx->d_rowoff.p, stride);
@@ -654,13 +763,61 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	if (ctx->fam_mask & (1 << FAM_INT))
 	{
 		for (int c = 0; c < NACLASS; c++)
-			if (int rc = launch_intensity (ctx, ctx->d_alist.p + ctx->abase[c], info.aclass_count[c], prm, info.aclass_maxarea[c], ctx->d_full.p))
+			if (int rc = launch_intensity (ctx, ctx->d_alist.p + ctx->abase[c], info.aclass_count[c], prm, info.aclass_maxarea[c], ctx->d_full.p, ncol_all))
 				return rc;
 		if (info.aclass_count[NACLASS])
-			if (int rc = launch_intensity (ctx, ctx->d_alist.p + ctx->abase[NACLASS], info.aclass_count[NACLASS], prm, info.aclass_maxarea[NACLASS], ctx->d_full.p))
+			if (int rc = launch_intensity (ctx, ctx->d_alist.p + ctx->abase[NACLASS], info.aclass_count[NACLASS], prm, info.aclass_maxarea[NACLASS], ctx->d_full.p, ncol_all))
 				return rc;
 	}
 	static const int fam_stage[FAM_COUNT] = { ST_INT, ST_GLCM, ST_GLRLM, ST_GLDZM, ST_GLSZM, ST_GLDM, ST_NGLDM, ST_NGTDM };
+	if (d3)
+	{
+		if ((ctx->fam_mask & ~(1 << FAM3_INT)) && info.class_count[NCLASS])
+			return fail (ctx, NYXB200_EUNSUPPORTED, "a 3D ROI whose bounding cube exceeds 40000 voxels needs the large-ROI texture path (not in this build)");
+		const int maxI = (int)std::max<uint32_t> (info.max_inten, 1u);
+		for (int fam = FAM3_GLCM; fam < FAM3_COUNT; fam++)
+		{
+			static const int st3[FAM3_COUNT] = { ST_INT, ST_GLCM, ST_GLSZM, ST_NGTDM };
+			stage_begin (ctx, st3[fam]);
+			if (!(ctx->fam_mask & (1 << fam)))
+				continue;
+			// grey-binning info per family (3d_glcm.cpp:53-55, 3d_glszm.cpp:490-492, 3d_ngtdm.cpp:195-197); 0 = no binning
+			int g = fam == FAM3_GLCM ? ctx->st.coarse_gray_depth : fam == FAM3_GLSZM ? ctx->glszm3_greydepth : ctx->ngtdm3_greydepth;
+			if (ctx->st.ibsi)
+				g = 0;
+			int Lm = g > 0 ? g : maxI;
+			if (fam == FAM3_NGTDM && ctx->ngtdm3_radius == 0)
+				Lm = 1;		// nothing is accumulated (see ngtdm3d_body)
+			for (int c = 0; c < NCLASS; c++)
+			{
+				const uint32_t n = info.class_count[c], mc = info.class_maxcells[c];
+				const uint32_t* lst = ctx->d_tlist.p + ctx->tbase[c];
+				int rc = 0;
+				if (fam == FAM3_GLCM)
+				{
+					if (g == 0 && Lm > 4096)
+						return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLCM without grey binning needs intensities <= 4096 (max %d)", Lm);
+					rc = mc < 32768 ? launch_family3_t<FAM3_GLCM, true> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
+						: launch_family3_t<FAM3_GLCM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+				}
+				else if (fam == FAM3_GLSZM)
+				{
+					if (Lm > 65535)
+						return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLSZM needs grey levels < 65536 (max %d)", Lm);
+					rc = launch_family3_t<FAM3_GLSZM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+				}
+				else
+				{
+					if ((unsigned long long)(Lm + 2) * NGTDM3_NDMAX * (unsigned long long)mc >= 0xFFFFFFFFull || Lm + 2 > 65535)
+						return fail (ctx, NYXB200_EUNSUPPORTED, "3D NGTDM: level range %d too large for the exact integer accumulators; set 3ngtdm/greydepth", Lm);
+					rc = launch_family3_t<FAM3_NGTDM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+				}
+				if (rc)
+					return rc;
+			}
+		}
+	}
+	else
 	for (int fam = FAM_GLCM; fam < FAM_COUNT; fam++)
 	{
 		stage_begin (ctx, fam_stage[fam]);
@@ -688,7 +845,7 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	CU (ctx->d_sel_out.reserve (outn));
 	{
 		int grid = (int)std::min<size_t> ((outn + 255) / 256, (size_t)ctx->sm_count * 16);
-		k_select_columns<<<grid, 256, 0, s>>> (ctx->d_full.p, ctx->d_rois.p, nroi, ctx->d_sel.p, nsel, ctx->st.soft_nan, 0.0, ctx->d_sel_out.p);
+		k_select_columns<<<grid, 256, 0, s>>> (ctx->d_full.p, ncol_all, ctx->d_rois.p, nroi, ctx->d_sel.p, nsel, ctx->st.soft_nan, 0.0, ctx->d_sel_out.p);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 	}
@@ -720,12 +877,14 @@ void collect_timings (nyxb200_ctx* ctx)
 }
 
 int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const uint32_t* label, bool on_device,
-	int n_img, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
+	int n_img, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
 {
 	if (!ctx || !inten || !label || !out)
 		return fail (ctx, NYXB200_EINVAL, "null argument");
-	if (n_img <= 0 || H <= 0 || W <= 0)
+	if (n_img <= 0 || H <= 0 || W <= 0 || D <= 0)
 		return fail (ctx, NYXB200_EINVAL, "bad image dimensions");
+	if (D * H > 0x7FFFFFFF)
+		return fail (ctx, NYXB200_EUNSUPPORTED, "volume has more than 2^31-1 rows");
 	if (H > 0x7FFFFFFF || W > 0x7FFFFFFF)
 		return fail (ctx, NYXB200_EUNSUPPORTED, "image side exceeds 2^31-1");
 	out->data = nullptr;
@@ -736,7 +895,7 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 	for (auto& m : ctx->stage_ms) m = 0;
 	for (auto& v : ctx->counts) v = 0;
 	ctx->row_image.clear();
-	const size_t npix = (size_t)H * (size_t)W;
+	const size_t npix = (size_t)D * (size_t)H * (size_t)W;
 	const size_t ibytes = npix * (inten_u16 ? 2 : 4), lbytes = npix * 4;
 	ctx->h_out_used = 0;
 	for (int k = 0; k < n_img; k++)
@@ -745,6 +904,7 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 		ImageView im;
 		im.H = (int32_t)H;
 		im.W = (int32_t)W;
+		im.D = (int32_t)D;
 		im.inten_u16 = inten_u16;
 		const uint8_t* ip = (const uint8_t*)inten + (size_t)k * ibytes;
 		const uint32_t* lp = label + (size_t)k * npix;
@@ -791,19 +951,49 @@ extern "C"
 int nyxb200_featurize_2d_u32 (nyxb200_ctx* ctx, const uint32_t* inten, const uint32_t* label, int n_img, int64_t H, int64_t W,
 	nyxb200_table* out, const int32_t** row_image)
 {
-	return featurize_common (ctx, inten, 0, label, false, n_img, H, W, out, row_image);
+	if (ctx && ctx->st.dim != 2)
+		return fail (ctx, NYXB200_EINVAL, "this context was created for 3D features (dim = 3)");
+	return featurize_common (ctx, inten, 0, label, false, n_img, 1, H, W, out, row_image);
 }
 
 int nyxb200_featurize_2d_u16 (nyxb200_ctx* ctx, const uint16_t* inten, const uint32_t* label, int n_img, int64_t H, int64_t W,
 	nyxb200_table* out, const int32_t** row_image)
 {
-	return featurize_common (ctx, inten, 1, label, false, n_img, H, W, out, row_image);
+	if (ctx && ctx->st.dim != 2)
+		return fail (ctx, NYXB200_EINVAL, "this context was created for 3D features (dim = 3)");
+	return featurize_common (ctx, inten, 1, label, false, n_img, 1, H, W, out, row_image);
 }
 
 int nyxb200_featurize_2d_device (nyxb200_ctx* ctx, const void* inten, int inten_is_u16, const uint32_t* label, int n_img,
 	int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
 {
-	return featurize_common (ctx, inten, inten_is_u16 ? 1 : 0, label, true, n_img, H, W, out, row_image);
+	if (ctx && ctx->st.dim != 2)
+		return fail (ctx, NYXB200_EINVAL, "this context was created for 3D features (dim = 3)");
+	return featurize_common (ctx, inten, inten_is_u16 ? 1 : 0, label, true, n_img, 1, H, W, out, row_image);
+}
+
+int nyxb200_featurize_3d_u32 (nyxb200_ctx* ctx, const uint32_t* inten, const uint32_t* label, int n_vol, int64_t D, int64_t H, int64_t W,
+	nyxb200_table* out, const int32_t** row_image)
+{
+	if (ctx && ctx->st.dim != 3)
+		return fail (ctx, NYXB200_EINVAL, "this context was created for 2D features (dim = 2)");
+	return featurize_common (ctx, inten, 0, label, false, n_vol, D, H, W, out, row_image);
+}
+
+int nyxb200_featurize_3d_u16 (nyxb200_ctx* ctx, const uint16_t* inten, const uint32_t* label, int n_vol, int64_t D, int64_t H, int64_t W,
+	nyxb200_table* out, const int32_t** row_image)
+{
+	if (ctx && ctx->st.dim != 3)
+		return fail (ctx, NYXB200_EINVAL, "this context was created for 2D features (dim = 2)");
+	return featurize_common (ctx, inten, 1, label, false, n_vol, D, H, W, out, row_image);
+}
+
+int nyxb200_featurize_3d_device (nyxb200_ctx* ctx, const void* inten, int inten_is_u16, const uint32_t* label, int n_vol,
+	int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
+{
+	if (ctx && ctx->st.dim != 3)
+		return fail (ctx, NYXB200_EINVAL, "this context was created for 2D features (dim = 2)");
+	return featurize_common (ctx, inten, inten_is_u16 ? 1 : 0, label, true, n_vol, D, H, W, out, row_image);
 }
 
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t)

@@ -78,12 +78,66 @@ struct GlcmDebug
 
 constexpr double INV_LOG10_2 = 1.0 / LOG10_2;
 
-// One angle, one warp-wide context g.  reg: this angle's region (all integer words zero on entry and on exit).
-template <bool P16>
-NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* reg, int Ng,
-	double* out, const GlcmDebug* dbg)
+// Pair enumeration.  2D (glcm.cpp:431-478): centre and neighbour must both have a non-zero ORIGINAL intensity.
+// 3D (3d_glcm.cpp:333-372): every in-cube pair counts (MATLAB binning turns background into level 1) unless the
+// binning keeps zeros (IBSI), where zero levels are skipped.
+template <bool D3> struct GlcmGeom
 {
-	const int w = r.w, h = r.h, ncell = w * h;
+	int w, h, d, dx, dy, dz;
+	bool skipzero;
+	FastDiv fw, fh;
+	NYX_D void init (const RoiRec& r, int dx_, int dy_, int dz_, bool skipzero_)
+	{
+		w = r.w; h = r.h; d = D3 ? r.d : 1;
+		dx = dx_; dy = dy_; dz = dz_;
+		skipzero = skipzero_;
+		fw.init ((uint32_t)w);
+		fh.init ((uint32_t)h);
+	}
+	NYX_D int ncell() const { return w * h * d; }
+	NYX_D bool pair (const uint32_t* cell, int i, int& b, int& av) const
+	{
+		const uint32_t cc = cell[i];
+		uint32_t nc;
+		if (!D3)
+		{
+			if (!(cc & CELL_NZ))
+				return false;
+			const int row = (int)fw.div ((uint32_t)i), col = i - row * w;
+			const int r2 = row + dy, c2 = col + dx;
+			if (r2 < 0 || r2 >= h || c2 < 0 || c2 >= w)
+				return false;
+			nc = cell[r2 * w + c2];
+			if (!(nc & CELL_NZ))
+				return false;
+		}
+		else
+		{
+			if (skipzero && !(cc & CELL_LEVEL))
+				return false;
+			const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+			const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+			const int x2 = x + dx, y2 = y + dy, z2 = z + dz;
+			if (x2 < 0 || x2 >= w || y2 < 0 || y2 >= h || z2 < 0 || z2 >= d)
+				return false;
+			nc = cell[(z2 * h + y2) * w + x2];
+			if (skipzero && !(nc & CELL_LEVEL))
+				return false;
+		}
+		b = (int)(cc & CELL_LEVEL) - 1;
+		av = (int)(nc & CELL_LEVEL) - 1;
+		return true;
+	}
+};
+
+// One angle, one warp-wide context g.  reg: this angle's region (all integer words zero on entry and on exit).
+// The angle's 30 values go to out[f * ostride + a].  guard: 2D softNaN guards of CORRELATION / INFOMEAS1
+// (glcm.cpp:637-639,880-883), absent from 3d_glcm.cpp.
+template <bool P16, bool D3>
+NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec& r, const Params& prm, const uint32_t* cell,
+	uint32_t* reg, int Ng, double* out, int ostride, const GlcmDebug* dbg)
+{
+	const int ncell = G.ncell();
 	const double softnan = prm.softnan;
 	const size_t jw = Counters<P16>::words ((size_t)Ng * Ng);
 	Counters<P16> J { reg };
@@ -98,11 +152,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, 
 	uint16_t* lx = (uint16_t*)(py + Ng);	// [Ng] non-empty columns
 	uint16_t* ly = lx + Ng;			// [Ng] non-empty rows
 
-	const int o = prm.glcm_offset;
-	const int dx = a == 2 ? 0 : (a == 3 ? -o : o), dy = a == 0 ? 0 : o;	// glcm.cpp:234-251
 	const bool sym = prm.glcm_symmetric || prm.ibsi;
-	FastDiv fw;
-	fw.init ((uint32_t)w);
 
 	// ---- pass 1: build (glcm.cpp:431-478) + integer moments per pair
 	enum { Q_N, Q_R, Q_C, Q_D, Q_D2, Q_S, Q_RC, Q_CNT };
@@ -111,17 +161,9 @@ NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, 
 		q[k] = 0;
 	for (int i = g.tid; i < ncell; i += g.nthr)
 	{
-		const uint32_t cc = cell[i];
-		if (!(cc & CELL_NZ))
+		int b, av;
+		if (!G.pair (cell, i, b, av))
 			continue;
-		const int row = (int)fw.div ((uint32_t)i), col = i - row * w;
-		const int r2 = row + dy, c2 = col + dx;
-		if (r2 >= h || c2 < 0 || c2 >= w)
-			continue;
-		const uint32_t nc = cell[r2 * w + c2];
-		if (!(nc & CELL_NZ))
-			continue;
-		const int b = (int)(cc & CELL_LEVEL) - 1, av = (int)(nc & CELL_LEVEL) - 1;
 		const int d = av > b ? av - b : b - av;
 		const unsigned long long lb = (unsigned long long)(b + 1), la = (unsigned long long)(av + 1), ld = (unsigned long long)d;
 		J.inc (g, b * Ng + av);
@@ -165,7 +207,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, 
 	if (!q[Q_N])	// glcm.cpp:260-295 (nothing was counted: the region is still all zero)
 	{
 		for (int f = g.tid; f < G_NANGLED; f += g.nthr)
-			out[f * 4 + a] = softnan;
+			out[f * ostride + a] = softnan;
 		return;
 	}
 	const double N = (double)q[Q_N];
@@ -244,17 +286,9 @@ NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, 
 	double jd[3] = { 0, 0, 0 };	// sum log(p_cell), sum log(px*py), sum (r-mr)(c-mc)
 	for (int i = g.tid; i < ncell; i += g.nthr)
 	{
-		const uint32_t cc = cell[i];
-		if (!(cc & CELL_NZ))
+		int b, av;
+		if (!G.pair (cell, i, b, av))
 			continue;
-		const int row = (int)fw.div ((uint32_t)i), col = i - row * w;
-		const int r2 = row + dy, c2 = col + dx;
-		if (r2 >= h || c2 < 0 || c2 >= w)
-			continue;
-		const uint32_t nc = cell[r2 * w + c2];
-		if (!(nc & CELL_NZ))
-			continue;
-		const int b = (int)(cc & CELL_LEVEL) - 1, av = (int)(nc & CELL_LEVEL) - 1;
 		const unsigned long long cnt = J.get (b * Ng + av);
 		const double p = (double)cnt / N;
 		const double l1 = fast_log10 (dadd (p, GLCM_EPSILON));					// HXY (glcm.cpp:868, 734-735, 1160-1161)
@@ -289,17 +323,9 @@ NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, 
 	// ---- pass 3: restore the all-zero region
 	for (int i = g.tid; i < ncell; i += g.nthr)
 	{
-		const uint32_t cc = cell[i];
-		if (!(cc & CELL_NZ))
+		int b, av;
+		if (!G.pair (cell, i, b, av))
 			continue;
-		const int row = (int)fw.div ((uint32_t)i), col = i - row * w;
-		const int r2 = row + dy, c2 = col + dx;
-		if (r2 >= h || c2 < 0 || c2 >= w)
-			continue;
-		const uint32_t nc = cell[r2 * w + c2];
-		if (!(nc & CELL_NZ))
-			continue;
-		const int b = (int)(cc & CELL_LEVEL) - 1, av = (int)(nc & CELL_LEVEL) - 1;
 		J.clear (b * Ng + av);
 		if (sym)
 			J.clear (av * Ng + b);
@@ -341,7 +367,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, 
 	f[G_SUMVARIANCE] = m[M_CT];					// :324-326
 	f[G_CONTRAST] = (double)q[Q_D2] / N;				// :566-584
 	const double sr = sqrt (m[M_S2R]), sc = sqrt (m[M_S2C]), den = sr * sc;
-	f[G_CORRELATION] = (den > 0.0) ? (jd[2] / N) / den : softnan;	// :637-643
+	f[G_CORRELATION] = (D3 || den > 0.0) ? (jd[2] / N) / den : softnan;	// :637-643 (3d_glcm.cpp: unguarded)
 	f[G_DIFAVE] = diffavg;
 	f[G_DIFENTRO] = -m[M_DENT] * sc_log;
 	f[G_DIFVAR] = m[M_DVAR];
@@ -355,7 +381,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, 
 	f[G_IDM] = m[M_IDM];
 	f[G_IDMN] = m[M_IDMN];
 	const double im1 = (HXY - HXY1) / HX;				// :880-883
-	f[G_INFOMEAS1] = (isnan (im1) || isinf (im1)) ? softnan : im1;
+	f[G_INFOMEAS1] = (!D3 && (isnan (im1) || isinf (im1))) ? softnan : im1;
 	f[G_INFOMEAS2] = sqrt (fabs (1.0 - exp (-2.0 * (-HXY2 + HXY))));	// :913
 	f[G_IV] = m[M_IV];
 	f[G_JAVE] = mr;
@@ -366,7 +392,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm, 
 	f[G_VARIANCE] = m[M_S2R];					// :647-676
 	if (g.tid == 0)
 		for (int k = 0; k < G_NANGLED; k++)
-			out[k * 4 + a] = f[k];
+			out[k * ostride + a] = f[k];
 }
 
 // out: NCOL_GLCM doubles of this ROI (angled block then _AVE block).  mem: 4 angle regions, zero on entry and exit.
@@ -390,8 +416,13 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 	}
 	const size_t aw = glcm_angle_words<P16> (Ng);
 	const Cta g = c.sub();
+	const int o = prm.glcm_offset;
 	for (int a = c.sub_id(); a < NA; a += c.sub_count())
-		glcm_angle<P16> (g, a, r, prm, cell, mem + (size_t)a * aw, Ng, out, dbg);
+	{
+		GlcmGeom<false> G;
+		G.init (r, a == 2 ? 0 : (a == 3 ? -o : o), a == 0 ? 0 : o, 0, false);	// glcm.cpp:234-251
+		glcm_angle<P16, false> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg);
+	}
 	c.sync();
 
 	// ---- _AVE = ((v0+v1)+v2)+v3)/4 (glcm.cpp:1205-1214)
@@ -399,6 +430,43 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 	{
 		const double* v = out + ave_order[k] * 4;
 		out[G_NANGLED * 4 + k] = (((v[0] + v[1]) + v[2]) + v[3]) / 4.0;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3D GLCM (reference features/3d_glcm.cpp): 13 directions (:16-31) x static offset 1, all formulas as in 2D but without
+// the CORRELATION / INFOMEAS1 guards; the table exports direction 0 of every angled code plus the 13-direction _AVE.
+// out: the ROI's 3D GLCM block: [30][13] per-direction values, then 29 _AVE.
+// ------------------------------------------------------------------------------------------------
+constexpr int G3_NDIR = 13;
+constexpr int NCOL_GLCM3 = G_NANGLED * G3_NDIR + G_NAVE;
+
+template <bool P16>
+NYX_D void glcm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Ng,
+	double* out)
+{
+	const int ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
+	const int sx[G3_NDIR] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0 };
+	const int sy[G3_NDIR] = { 1, 1, 1, 0, 0, 0, -1, -1, -1, 1, 1, 1, 0 };
+	const int sz[G3_NDIR] = { 1, 0, -1, 1, 0, -1, 1, 0, -1, 1, 0, -1, 1 };
+	const size_t aw = glcm_angle_words<P16> (Ng);
+	const Cta g = c.sub();
+	const int nsub = c.sub_count() < 4 ? c.sub_count() : 4;	// at most 4 regions
+	if (c.sub_id() < nsub)
+		for (int a = c.sub_id(); a < G3_NDIR; a += nsub)
+		{
+			GlcmGeom<true> G;
+			G.init (r, sx[a], sy[a], sz[a], prm.ibsi != 0);
+			glcm_angle<P16, true> (g, a, G, r, prm, cell, mem + (size_t)c.sub_id() * aw, Ng, out, G3_NDIR, nullptr);
+		}
+	c.sync();
+	for (int k = c.tid; k < G_NAVE; k += c.nthr)	// calc_ave (texture_feature.h:121-130)
+	{
+		const double* v = out + ave_order[k] * G3_NDIR;
+		double sum = 0;
+		for (int a = 0; a < G3_NDIR; a++)
+			sum += v[a];
+		out[G_NANGLED * G3_NDIR + k] = sum / (double)G3_NDIR;
 	}
 }
 

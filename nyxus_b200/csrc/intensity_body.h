@@ -114,7 +114,8 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 		out[I_RANGE] = (double)mx - (double)mn;
 		// in-memory featurize(): slide extrema are the sentinels lowest()/max() (slideprops.cpp:29-30,74-75)
 		// -> range / (lowest - max) = range / -inf = -0.0
-		out[I_COVERED_IMAGE_INTENSITY_RANGE] = -0.0;
+		// file-based volumes: the scanned slide range over the labelled voxels (slideprops.cpp:305-327, 3d_intensity.cpp:56-61)
+		out[I_COVERED_IMAGE_INTENSITY_RANGE] = prm.covered_den != 0.0 ? (double)(uint32_t)(mx - mn) / prm.covered_den : -0.0;
 		out[I_MEAN] = mean;
 		out[I_ENERGY] = energy;
 		out[I_ROOT_MEAN_SQUARED] = sqrt (energy / nd);

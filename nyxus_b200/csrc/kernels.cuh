@@ -8,6 +8,7 @@
 #include "zones_body.h"
 #include "nbr_body.h"
 #include "intensity_body.h"
+#include "vol_body.h"
 
 namespace nyx
 {
@@ -39,7 +40,7 @@ struct SlideInfo
 	uint32_t class_maxwh[NCLASS + 1];
 	uint32_t aclass_count[NACLASS + 1];
 	uint32_t aclass_maxarea[NACLASS + 1];
-	uint32_t pad;
+	uint32_t inv_min_inten;		// ~(smallest aux_min over ROIs): the slide's foreground minimum (3D COVERED_IMAGE_INTENSITY_RANGE)
 };
 
 __host__ __device__ inline int tile_class (uint32_t ncell)
@@ -51,7 +52,7 @@ __host__ __device__ inline int area_class (uint32_t area)
 	return area <= 256 ? 0 : area <= 1024 ? 1 : area <= 4096 ? 2 : area <= 16384 ? 3 : area <= 32768 ? 4 : NACLASS;
 }
 
-__global__ void k_init_stats (LabelStat* tab, uint32_t cap, SlideInfo* info)
+__global__ void k_init_stats (LabelStat* tab, uint32_t cap, SlideInfo* info, uint2* ztab = nullptr)
 {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < cap)
@@ -59,14 +60,23 @@ __global__ void k_init_stats (LabelStat* tab, uint32_t cap, SlideInfo* info)
 		LabelStat s;
 		s.area = 0; s.imin = 0xFFFFFFFFu; s.imax = 0; s.xmin = 0xFFFFFFFFu; s.xmax = 0; s.ymin = 0xFFFFFFFFu; s.ymax = 0; s.pad = 0;
 		tab[i] = s;
+		if (ztab)
+			ztab[i] = make_uint2 (0xFFFFFFFFu, 0u);
 	}
 	if (i == 0)
 		memset (info, 0, sizeof (SlideInfo));
 }
 
 __device__ __forceinline__ void stat_group_update (unsigned part, LabelStat* tab, uint32_t cap, uint32_t lbl, uint32_t cnt,
-	uint32_t vmin, uint32_t vmax, uint32_t xmin, uint32_t xmax, uint32_t y)
+	uint32_t vmin, uint32_t vmax, uint32_t xmin, uint32_t xmax, uint32_t y, uint2* ztab = nullptr, uint32_t H = 0)
 {
+	// volumes: `y` arrives as the row index over all slices (z*H + y); lanes of one group may sit in different slices
+	uint32_t z = 0;
+	if (ztab)
+	{
+		z = y / H;
+		y -= z * H;
+	}
 	// `part` = lanes taking part (same value in all of them); lanes with the same label reduce together, the lowest commits
 	const unsigned mask = __match_any_sync (part, lbl);
 	const int lane = threadIdx.x & 31;
@@ -88,11 +98,20 @@ __device__ __forceinline__ void stat_group_update (unsigned part, LabelStat* tab
 		atomicMin (&s->ymin, ymin);
 		atomicMax (&s->ymax, ymax);
 	}
+	if (ztab)
+	{
+		const uint32_t zmin = __reduce_min_sync (mask, z), zmax = __reduce_max_sync (mask, z);
+		if (lane == __ffs (mask) - 1 && lbl < cap)
+		{
+			atomicMin (&ztab[lbl].x, zmin);
+			atomicMax (&ztab[lbl].y, zmax);
+		}
+	}
 }
 
 template <bool U16, bool VEC>
 __global__ void __launch_bounds__(256) k_scan_stats (const void* __restrict__ inten_, const uint32_t* __restrict__ label,
-	unsigned long long npix, uint32_t W, LabelStat* tab, uint32_t cap, SlideInfo* info)
+	unsigned long long npix, uint32_t W, LabelStat* tab, uint32_t cap, SlideInfo* info, uint2* ztab = nullptr, uint32_t H = 0)
 {
 	const unsigned long long ngroups = (npix + 3) / 4;
 	uint32_t warp_maxlbl = 0;
@@ -142,7 +161,7 @@ __global__ void __launch_bounds__(256) k_scan_stats (const void* __restrict__ in
 			if (l[0] != 0)
 			{
 				uint32_t vmin = min (min (v[0], v[1]), min (v[2], v[3])), vmax = max (max (v[0], v[1]), max (v[2], v[3]));
-				stat_group_update (part, tab, cap, l[0], 4, vmin, vmax, x0, x0 + 3, y0);
+				stat_group_update (part, tab, cap, l[0], 4, vmin, vmax, x0, x0 + 3, y0, ztab, H);
 			}
 		}
 		else
@@ -163,7 +182,7 @@ __global__ void __launch_bounds__(256) k_scan_stats (const void* __restrict__ in
 				}
 				const unsigned part = __ballot_sync (0xffffffffu, l[k] != 0);
 				if (l[k] != 0)
-					stat_group_update (part, tab, cap, l[k], 1, v[k], v[k], x, x, y);
+					stat_group_update (part, tab, cap, l[k], 1, v[k], v[k], x, x, y, ztab, H);
 			}
 		}
 	}
@@ -290,7 +309,7 @@ __global__ void __launch_bounds__(CB) k_compact_scan (uint32_t* blk_cnt, unsigne
 }
 
 __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uint32_t cap, SlideInfo* info,
-	const uint32_t* blk_cnt, const unsigned long long* blk_area, RoiRec* rois, uint32_t* class_slot)
+	const uint32_t* blk_cnt, const unsigned long long* blk_area, RoiRec* rois, uint32_t* class_slot, const uint2* ztab = nullptr)
 {
 	__shared__ uint32_t sa[33];
 	__shared__ unsigned long long sb[33];
@@ -324,16 +343,23 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 		r.cloud_off = blk_area[blockIdx.x] + b;
 		r.z0 = 0;
 		r.d = 1;
+		if (ztab)
+		{
+			const uint2 zz = ztab[i];
+			r.z0 = (int32_t)zz.x;
+			r.d = (int32_t)(zz.y - zz.x + 1);
+		}
 		rois[idx] = r;
-		const unsigned long long ncell64 = (unsigned long long)r.w * (unsigned long long)r.h;
+		const unsigned long long ncell64 = (unsigned long long)r.w * (unsigned long long)r.h * (unsigned long long)r.d;
 		const uint32_t ncell = ncell64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ncell64;
 		const int tc = tile_class (ncell), ac = area_class (r.area);
 		class_slot[idx * 2] = ((uint32_t)tc << 28) | atomicAdd (&info->class_count[tc], 1u);
 		class_slot[idx * 2 + 1] = ((uint32_t)ac << 28) | atomicAdd (&info->aclass_count[ac], 1u);
 		atomicMax (&info->class_maxcells[tc], ncell);
-		atomicMax (&info->class_maxwh[tc], (uint32_t)max (r.w, r.h));
+		atomicMax (&info->class_maxwh[tc], (uint32_t)max (max (r.w, r.h), r.d));
 		atomicMax (&info->aclass_maxarea[ac], r.area);
 		atomicMax (&info->max_inten, r.imax);
+		atomicMax (&info->inv_min_inten, ~r.imin);
 	}
 }
 
@@ -363,9 +389,10 @@ __global__ void __launch_bounds__(256) k_pack_cloud (ImageView im, const RoiRec*
 	const RoiRec r = rois[list ? list[warp] : warp];
 	uint32_t* dst = cloud + r.cloud_off;
 	uint32_t run = 0;
-	for (int y = 0; y < r.h; y++)
+	for (int yz = 0; yz < r.h * r.d; yz++)	// rows of the AABB, slice by slice (2D: d == 1)
 	{
-		const size_t rowbase = (size_t)(r.y0 + y) * im.W + r.x0;
+		const int z = yz / r.h, y = yz - z * r.h;
+		const size_t rowbase = ((size_t)(r.z0 + z) * im.H + (size_t)(r.y0 + y)) * im.W + r.x0;
 		for (int xb = 0; xb < r.w; xb += 32)
 		{
 			const int x = xb + lane;
@@ -394,9 +421,11 @@ __global__ void __launch_bounds__(256) k_pack_cloud_large (ImageView im, const R
 		const RoiRec r = rois[list[k]];
 		unsigned long long* rowoff = rowoff_scratch + (size_t)blockIdx.x * rowoff_stride;
 		const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-		for (int y = warp; y < r.h; y += nw)
+		const int nrows = r.h * r.d;	// rows of the AABB, slice by slice (2D: d == 1)
+		for (int y = warp; y < nrows; y += nw)
 		{
-			const size_t rowbase = (size_t)(r.y0 + y) * im.W + r.x0;
+			const int zz = y / r.h, yy = y - zz * r.h;
+			const size_t rowbase = ((size_t)(r.z0 + zz) * im.H + (size_t)(r.y0 + yy)) * im.W + r.x0;
 			uint32_t cnt = 0;
 			for (int x = lane; x < r.w; x += 32)
 				cnt += im.label[rowbase + x] == r.label ? 1 : 0;
@@ -408,14 +437,15 @@ __global__ void __launch_bounds__(256) k_pack_cloud_large (ImageView im, const R
 		if (threadIdx.x == 0)
 		{
 			rowoff[0] = 0;
-			for (int y = 0; y < r.h; y++)
+			for (int y = 0; y < nrows; y++)
 				rowoff[y + 1] += rowoff[y];
 		}
 		__syncthreads();
 		uint32_t* dst = cloud + r.cloud_off;
-		for (int y = warp; y < r.h; y += nw)
+		for (int y = warp; y < nrows; y += nw)
 		{
-			const size_t rowbase = (size_t)(r.y0 + y) * im.W + r.x0;
+			const int zz = y / r.h, yy = y - zz * r.h;
+			const size_t rowbase = ((size_t)(r.z0 + zz) * im.H + (size_t)(r.y0 + yy)) * im.W + r.x0;
 			unsigned long long run = rowoff[y];
 			for (int xb = 0; xb < r.w; xb += 32)
 			{
@@ -551,6 +581,46 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family_w (ImageView im, con
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3D (Nyxus3D) families: CTA per ROI, the ROI's AABB cube in shared memory, family region in shared memory or in a
+// per-CTA global slot.  FAM3: 1 GLCM, 2 GLSZM, 3 NGTDM.
+// ------------------------------------------------------------------------------------------------
+enum Family3 : int { FAM3_INT = 0, FAM3_GLCM, FAM3_GLSZM, FAM3_NGTDM, FAM3_COUNT };
+constexpr int NCOL3_INT = NCOL_INT, NCOL3_GLCM = NCOL_GLCM3, NCOL3_NGTDM = NCOL_NGTDM, NCOL3_GLSZM = NCOL_GLSZM;
+constexpr int COL3_INT = 0, COL3_GLCM = COL3_INT + NCOL3_INT, COL3_NGTDM = COL3_GLCM + NCOL3_GLCM, COL3_GLSZM = COL3_NGTDM + NCOL3_NGTDM;
+constexpr int NCOL3_ALL = COL3_GLSZM + NCOL3_GLSZM;
+
+template <int FAM3, bool P16>
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, const RoiRec* __restrict__ rois,
+	const uint32_t* __restrict__ list, uint32_t n, Params prm, int greyinfo, int Lmax, uint32_t maxcells,
+	double* out, int out_stride, uint32_t* gscratch, size_t gwords)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
+	uint32_t* cell = smem + RED_WORDS;
+	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : cell + ((maxcells + 1) & ~1u);
+	if (!gscratch)
+		for (size_t i = threadIdx.x; i < gwords; i += blockDim.x)
+			mem[i] = 0;
+	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		const RoiRec r = rois[ri];
+		double* o = out + (size_t)ri * out_stride;
+		Binner B;
+		B.init (greyinfo, r.imin, r.imax);
+		load_cube (c, im, r, B, cell);
+		c.sync();
+		if (FAM3 == FAM3_GLCM)
+			glcm3d_body<P16> (c, r, prm, cell, mem, Lmax, o + COL3_GLCM);
+		else if (FAM3 == FAM3_GLSZM)
+			glszm3d_body (c, r, prm, cell, mem, maxcells, glszm_hash_slots (Lmax, maxcells), greyinfo > 0, o + COL3_GLSZM);
+		else if (FAM3 == FAM3_NGTDM)
+			ngtdm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_NGTDM);
+		c.sync();
+	}
+}
+
 // first-order: reads the ROI's CSR slice
 __global__ void __launch_bounds__(ROI_THREADS) k_roi_intensity (const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
 	uint32_t n, Params prm, const uint32_t* __restrict__ cloud, uint32_t npad_max, double* out, int out_stride,
@@ -587,7 +657,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_intensity_w (const RoiRec* 
 
 // final gather: canonical table -> [label, t_index, selected columns], values through force_finite_number(v, noval)
 // (reference output_2_buffer.cpp:490,577)
-__global__ void k_select_columns (const double* __restrict__ full, const RoiRec* __restrict__ rois, uint32_t n,
+__global__ void k_select_columns (const double* __restrict__ full, int full_stride, const RoiRec* __restrict__ rois, uint32_t n,
 	const int* __restrict__ sel, int nsel, double noval, double t_index, double* __restrict__ dst)
 {
 	const size_t total = (size_t)n * (nsel + 2);
@@ -601,7 +671,7 @@ __global__ void k_select_columns (const double* __restrict__ full, const RoiRec*
 		else if (cidx == 1)
 			v = t_index;
 		else
-			v = finite_or (full[(size_t)r * NCOL_ALL + sel[cidx - 2]], noval);
+			v = finite_or (full[(size_t)r * full_stride + sel[cidx - 2]], noval);
 		dst[i] = v;
 	}
 }

@@ -325,12 +325,16 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 // NGTDM: N[L1], SI[L1][8] exact integer |level*nd - sum|, PR[L1] presence (zero on entry/exit), then the compacted
 // list of present levels with their P and S
 // ------------------------------------------------------------------------------------------------
+// NDMAX = largest neighbour count (2D: 8; 3D radius 1: 26).  L1 = number of level slots.
+NYX_HD size_t ngtdm_words (int L1, int ndmax)
+{
+	size_t ints = (size_t)L1 * (ndmax + 2) + ((size_t)L1 + 1) / 2;	// N, SI[ndmax], PR + level list (u16)
+	ints += ints & 1;
+	return ints + (size_t)L1 * 4;					// + Pl, Sl doubles
+}
 NYX_HD size_t ngtdm_smem_words (int Lmax)
 {
-	size_t L1 = (size_t)Lmax + 1;
-	size_t ints = L1 * 10 + (L1 + 1) / 2;	// + level list (u16)
-	ints += ints & 1;
-	return ints + L1 * 4;			// + Pl, Sl doubles
+	return ngtdm_words (Lmax + 1, 8);
 }
 
 struct NgtdmDebug
@@ -339,61 +343,21 @@ struct NgtdmDebug
 	double* S;	// [Lmax+1]
 };
 
-NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax,
-	double* out, const NgtdmDebug* dbg)
+// Common tail of 2D and 3D NGTDM.  mem = N[L1] | SI[L1][ndmax] | PR[L1] (zero on exit) | list | Pl | Sl.
+// lv0: first level that may be a centre level (levels below only count for presence).  nvc: number of kept centres.
+// isize_fixed >= 0: |I| given by the caller (3D); else derived like ngtdm.cpp:57-67.
+NYX_D void ngtdm_reduce (const Cta& c, const Params& prm, uint32_t* mem, int L1, int ndmax, int lv0, double nvc, int isize_fixed,
+	bool ibsi_list, double* out, const NgtdmDebug* dbg)
 {
-	const int w = r.w, h = r.h, ncell = w * h;
-	const int L1 = Lmax + 1;
 	uint32_t* Nn = mem;				// [L1]
-	uint32_t* SI = Nn + L1;				// [L1][8]
-	uint32_t* PR = SI + (size_t)L1 * 8;		// [L1] level present anywhere in the binned tile
+	uint32_t* SI = Nn + L1;				// [L1][ndmax]
+	uint32_t* PR = SI + (size_t)L1 * ndmax;		// [L1] level present anywhere in the binned tile
 	uint16_t* lst = (uint16_t*)(PR + L1);		// [L1] levels with N > 0, ascending
-	size_t off = (size_t)L1 * 10 + ((size_t)L1 + 1) / 2;
+	size_t off = (size_t)L1 * (ndmax + 2) + ((size_t)L1 + 1) / 2;
 	off += off & 1;
 	double* Pl = (double*)(mem + off);		// [L1] P of the listed levels (:191-192)
 	double* Sl = Pl + L1;				// [L1] S of the listed levels
-	FastDiv fw;
-	fw.init ((uint32_t)w);
-
-	unsigned long long q[1] = { 0 };		// Nvc
-	for (int i = c.tid; i < ncell; i += c.nthr)
-	{
-		const uint32_t lv = cell[i] & CELL_LEVEL;
-		if (!lv)
-			continue;
-		PR[lv] = 1;
-		const int y = (int)fw.div ((uint32_t)i), x = i - y * w;
-		int nd = 0;
-		uint32_t sum = 0;
-		for (int dy = -1; dy <= 1; dy++)
-		{
-			const int yy = y + dy;
-			if (yy < 0 || yy >= h)
-				continue;
-			for (int dx = -1; dx <= 1; dx++)
-			{
-				const int xx = x + dx;
-				if ((!dx && !dy) || xx < 0 || xx >= w)
-					continue;
-				const uint32_t qv = cell[yy * w + xx] & CELL_LEVEL;
-				if (qv)
-				{
-					sum += qv;
-					nd++;
-				}
-			}
-		}
-		if (nd > 0)	// ngtdm.cpp:83-146
-		{
-			long long df = (long long)lv * nd - (long long)sum;
-			atom_add (c, Nn + lv, 1u);
-			atom_add (c, SI + (size_t)lv * 8 + (nd - 1), (uint32_t)(df < 0 ? -df : df));
-			q[0]++;
-		}
-	}
-	c.sync();
-	cta_sum_u64<1> (c, q);
-	const double Nvc = (double)q[0], Nvp = (double)q[0];	// every kept pixel has a positive neighbourhood mean (:181-182)
+	const double Nvc = nvc, Nvp = nvc;		// every kept pixel has a positive neighbourhood mean (:181-182)
 
 	// ---- one sub-group sweeps the levels: Ngp, compaction of the present levels, S and P, and restores the zero region
 	int* shared_cnt = (int*)c.red;	// [0] Ngp, [1] list length (block mode); a warp-wide context keeps them in registers
@@ -401,21 +365,21 @@ NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	if (c.sub_id() == 0)
 	{
 		const Cta g = c.sub();
-		for (int base = 0; base <= Lmax; base += g.nthr)
+		for (int base = 0; base < L1; base += g.nthr)
 		{
 			const int lv = base + g.tid;
 			uint32_t n = 0, pr = 0;
 			double sv = 0;
-			if (lv <= Lmax)
+			if (lv < L1)
 			{
 				n = Nn[lv];
-				pr = lv >= 1 ? PR[lv] : 0;
-				for (int k = 0; k < 8; k++)
+				pr = PR[lv];
+				for (int k = 0; k < ndmax; k++)
 				{
-					const uint32_t si = SI[(size_t)lv * 8 + k];
+					const uint32_t si = SI[(size_t)lv * ndmax + k];
 					if (si)
 						sv += (double)si / (double)(k + 1);
-					SI[(size_t)lv * 8 + k] = 0;
+					SI[(size_t)lv * ndmax + k] = 0;
 				}
 				Nn[lv] = 0;
 				PR[lv] = 0;
@@ -425,7 +389,7 @@ NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 					dbg->S[lv] = sv;
 				}
 			}
-			const bool keep = n != 0 && lv >= 1;
+			const bool keep = n != 0 && lv >= lv0;
 			const unsigned bk = g.ballot (keep), bp = g.ballot (pr != 0);
 			if (keep)
 			{
@@ -435,7 +399,7 @@ NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 				Sl[pos] = sv;
 			}
 			nl += popc32 (bk);
-			Ngp += popc32 (bp);	// unique non-zero levels in the tile (ngtdm.cpp:53-55,152)
+			Ngp += popc32 (bp);	// unique levels in the tile (ngtdm.cpp:53-55,152)
 		}
 		if (!c.wmode && g.tid == 0)
 		{
@@ -452,13 +416,13 @@ NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		__syncthreads();
 	}
 #endif
-	const int Isize = prm.ibsi ? (Ngp ? Lmax + 1 : 0) : Ngp;	// |I| (:57-67); IBSI: 0..max(D)
+	const int Isize = isize_fixed >= 0 ? isize_fixed : (ibsi_list ? (Ngp ? L1 : 0) : Ngp);	// |I| (:57-67); IBSI: 0..max(D)
 	if (Isize < 2)
 	{
 		for (int i = c.tid; i < NCOL_NGTDM; i += c.nthr)
 			out[i] = prm.softnan;
 		if (dbg && dbg->N)	// the reference returns before building the matrix (ngtdm.cpp:70-78)
-			for (int lv = c.tid; lv <= Lmax; lv += c.nthr)
+			for (int lv = c.tid; lv < L1; lv += c.nthr)
 			{
 				dbg->N[lv] = 0;
 				dbg->S[lv] = 0;
@@ -500,6 +464,58 @@ NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		out[T_COMPLEXITY] = s[A_CPLX] / Nvp;
 		out[T_STRENGTH] = s[A_STR] / s[A_S];
 	}
+}
+
+NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax,
+	double* out, const NgtdmDebug* dbg)
+{
+	const int w = r.w, h = r.h, ncell = w * h;
+	const int L1 = Lmax + 1;
+	uint32_t* Nn = mem;				// [L1]
+	uint32_t* SI = Nn + L1;				// [L1][8]
+	uint32_t* PR = SI + (size_t)L1 * 8;		// [L1] level present anywhere in the binned tile
+	FastDiv fw;
+	fw.init ((uint32_t)w);
+
+	unsigned long long q[1] = { 0 };		// Nvc
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (!lv)
+			continue;
+		PR[lv] = 1;
+		const int y = (int)fw.div ((uint32_t)i), x = i - y * w;
+		int nd = 0;
+		uint32_t sum = 0;
+		for (int dy = -1; dy <= 1; dy++)
+		{
+			const int yy = y + dy;
+			if (yy < 0 || yy >= h)
+				continue;
+			for (int dx = -1; dx <= 1; dx++)
+			{
+				const int xx = x + dx;
+				if ((!dx && !dy) || xx < 0 || xx >= w)
+					continue;
+				const uint32_t qv = cell[yy * w + xx] & CELL_LEVEL;
+				if (qv)
+				{
+					sum += qv;
+					nd++;
+				}
+			}
+		}
+		if (nd > 0)	// ngtdm.cpp:83-146
+		{
+			long long df = (long long)lv * nd - (long long)sum;
+			atom_add (c, Nn + lv, 1u);
+			atom_add (c, SI + (size_t)lv * 8 + (nd - 1), (uint32_t)(df < 0 ? -df : df));
+			q[0]++;
+		}
+	}
+	c.sync();
+	cta_sum_u64<1> (c, q);
+	ngtdm_reduce (c, prm, mem, L1, 8, 1, (double)q[0], -1, prm.ibsi != 0, out, dbg);
 }
 
 } // namespace nyx

@@ -181,6 +181,7 @@ struct ImageView
 	const uint32_t* label;
 	int32_t H, W;
 	int32_t inten_u16;
+	int32_t D = 1;		// slices (1: 2D image); voxel (z,y,x) lives at (z*H + y)*W + x
 };
 
 struct Params
@@ -190,6 +191,10 @@ struct Params
 	int32_t glcm_offset;
 	int32_t glcm_symmetric;
 	double softnan;
+	// 3D (Nyxus3D) settings: per-family grey depths (env_features.cpp:712-736: only GLCM gets a default, the rest are 0
+	// = no binning unless set through set_metaparam) and the NGTDM neighbourhood radius
+	int32_t glszm3_greydepth = 0, ngtdm3_greydepth = 0, ngtdm3_radius = 0, pad3 = 0;
+	double covered_den = 0;	// first-order COVERED_IMAGE_INTENSITY_RANGE denominator (slide max - min); 0 = in-memory sentinel
 };
 
 NYX_HD uint32_t load_inten (const ImageView& im, size_t idx)
@@ -456,10 +461,33 @@ NYX_D void bitonic_sort (const Cta& c, uint32_t* a, uint32_t npad)
 NYX_D void load_tile (const Cta& c, const ImageView& im, const RoiRec& r, const Binner& B, uint32_t* cell)
 {
 	const int n = r.w * r.h;
+	FastDiv fw;
+	fw.init ((uint32_t)r.w);
 	for (int i = c.tid; i < n; i += c.nthr)
 	{
-		int y = i / r.w, x = i - y * r.w;
+		int y = (int)fw.div ((uint32_t)i), x = i - y * r.w;
 		size_t g = (size_t)(r.y0 + y) * im.W + (size_t)(r.x0 + x);
+		bool in = im.label[g] == r.label;
+		uint32_t v = in ? load_inten (im, g) : 0u;
+		uint32_t code = B.bin (v) & CELL_LEVEL;
+		if (v) code |= CELL_NZ;
+		if (in) code |= CELL_IN;
+		cell[i] = code;
+	}
+}
+
+// 3D: the ROI's AABB cube, cell index (z*h + y)*w + x (reference: SimpleCube::calculate_from_pixelcloud, image_cube.h:43-66)
+NYX_D void load_cube (const Cta& c, const ImageView& im, const RoiRec& r, const Binner& B, uint32_t* cell)
+{
+	const int n = r.w * r.h * r.d;
+	FastDiv fw, fh;
+	fw.init ((uint32_t)r.w);
+	fh.init ((uint32_t)r.h);
+	for (int i = c.tid; i < n; i += c.nthr)
+	{
+		const int row = (int)fw.div ((uint32_t)i), x = i - row * r.w;
+		const int z = (int)fh.div ((uint32_t)row), y = row - z * r.h;
+		size_t g = ((size_t)(r.z0 + z) * im.H + (size_t)(r.y0 + y)) * im.W + (size_t)(r.x0 + x);
 		bool in = im.label[g] == r.label;
 		uint32_t v = in ? load_inten (im, g) : 0u;
 		uint32_t code = B.bin (v) & CELL_LEVEL;

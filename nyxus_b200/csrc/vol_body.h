@@ -1,0 +1,274 @@
+// nyxus_b200 -- per-ROI 3D (Nyxus3D) families on the ROI's AABB cube: GLSZM and NGTDM.  (3D GLCM lives in glcm_body.h,
+// 3D first-order re-uses intensity_body.h on the voxel cloud.)
+//
+// 3D GLSZM (reference features/3d_glszm.cpp):
+//   blank test     :476-480   aux_min == aux_max -> 16 x softNaN
+//   binning        :490-494   GLSZM_GREYDEPTH (0 unless set through "3glszm/greydepth": no binning), IBSI forces 0
+//   background     :515       zeroI = 1 under MATLAB binning (background 0 is binned to level 1, so GENUINE level-1 voxels are
+//                             dropped as well), else 0
+//   zones          :44-469    flood over all 26 neighbours with back-tracking = 26-connected components of equal level
+//   Ns = max zone size, Nz = #zones, Np = voxel-cloud size :527-534;  features :583-860 (SAE / LAE as direct double loops)
+// 3D NGTDM (reference features/3d_ngtdm.cpp):
+//   binning        :195-198   NGTDM_GREYDEPTH (0 unless set), IBSI forces 0
+//   levels         :200-225   U = unique binned values of the WHOLE cube (background included); I = 0..max (IBSI flag) or
+//                             sorted U; if I[0] == 0 every level and every voxel is shifted by +1
+//   centres        :68-121    voxels whose (shifted) level != zeroI; neighbourhood = Chebyshev cube of NGTDM_RADIUS over all
+//                             in-cube voxels INCLUDING background; nd == 0 -> dropped
+//   |I| < 2 -> 5 x softNaN :229-237;  features :395-534
+//
+// B200 design: one CTA per ROI, cube in shared memory.  Components by lock-free union-find on 16-bit parents (a cube of
+// the supported size class has < 65536 cells), every cell first hooked to the head of its x-run; reducers shared with 2D.
+#pragma once
+#include "nyx_common.h"
+#include "nyx_features.h"
+#include "zones_body.h"
+#include "nbr_body.h"
+
+namespace nyx
+{
+
+// ---- union-find on 16-bit parents (atomic min through a 16-bit compare-and-swap)
+NYX_D uint32_t uf16_find (const volatile uint16_t* parent, uint32_t x)
+{
+	uint32_t p = parent[x];
+	while (p != x)
+	{
+		x = p;
+		p = parent[x];
+	}
+	return x;
+}
+NYX_D uint32_t atom_min16_ret (const Cta&, uint16_t* p, uint32_t v)
+{
+#if NYX_DEVICE_BUILD
+	unsigned short old = *(volatile unsigned short*)p;
+	while (v < old)
+	{
+		const unsigned short seen = atomicCAS ((unsigned short*)p, old, (unsigned short)v);
+		if (seen == old)
+			break;
+		old = seen;
+	}
+	return old;
+#else
+	uint32_t o = *p;
+	if (v < o) *p = (uint16_t)v;
+	return o;
+#endif
+}
+NYX_D void uf16_unite (const Cta& c, uint16_t* parent, uint32_t a, uint32_t b)
+{
+	for (;;)
+	{
+		a = uf16_find (parent, a);
+		b = uf16_find (parent, b);
+		if (a == b)
+			return;
+		if (a < b)
+		{
+			uint32_t t = a;
+			a = b;
+			b = t;
+		}
+		uint32_t old = atom_min16_ret (c, parent + a, b);	// hook the larger root under the smaller
+		if (old == a)
+			return;
+		a = old;
+	}
+}
+
+// region: hash keys[slots] + cnts[slots] (zero on entry/exit) + parent/label (u16 per cell) + zone sizes (u16 per cell)
+NYX_HD size_t glszm3d_smem_words (uint32_t maxcells, uint32_t slots)
+{
+	return glszm_smem_words (maxcells, slots);
+}
+
+// cell: cube binned with the GLSZM grey depth.  matlab: the binning was MATLAB (zeroI = 1).
+NYX_D void glszm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, uint32_t maxcells,
+	uint32_t slots, bool matlab, double* out)
+{
+	const int w = r.w, h = r.h, d = r.d, ncell = w * h * d;
+	if (r.imin == r.imax)
+	{
+		for (int i = c.tid; i < NCOL_GLSZM; i += c.nthr)
+			out[i] = prm.softnan;
+		return;
+	}
+	uint32_t* keys = mem;
+	uint32_t* cnts = keys + slots;
+	uint16_t* lab = (uint16_t*)(cnts + slots);
+	uint32_t* zsw = cnts + slots + ((size_t)maxcells + 1) / 2;
+	const uint32_t mask = slots - 1;
+	const uint32_t skip = matlab ? 1u : 0u;
+	FastDiv fw, fh;
+	fw.init ((uint32_t)w);
+	fh.init ((uint32_t)h);
+
+	for (int i = c.tid; i < (ncell + 1) / 2; i += c.nthr)
+		zsw[i] = 0;
+	// every cell hooked to the head of its same-level run along x
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		int hd = i;
+		if (lv != skip)
+		{
+			int x = i - (int)fw.div ((uint32_t)i) * w;
+			while (x > 0 && (cell[hd - 1] & CELL_LEVEL) == lv)
+			{
+				hd--;
+				x--;
+			}
+		}
+		lab[i] = (uint16_t)hd;
+	}
+	c.sync();
+	// unions with the 12 remaining "backward" neighbours (previous rows of this slice, all of the previous slice)
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (lv == skip)
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+		const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+		for (int dz = -1; dz <= 0; dz++)
+		{
+			const int zz = z + dz;
+			if (zz < 0)
+				continue;
+			for (int dy = -1; dy <= (dz < 0 ? 1 : -1); dy++)
+			{
+				const int yy = y + dy;
+				if (yy < 0 || yy >= h)
+					continue;
+				for (int dx = -1; dx <= 1; dx++)
+				{
+					const int xx = x + dx;
+					if (xx < 0 || xx >= w)
+						continue;
+					const int j = (zz * h + yy) * w + xx;
+					if ((cell[j] & CELL_LEVEL) == lv)
+						uf16_unite (c, lab, (uint32_t)i, (uint32_t)j);
+				}
+			}
+		}
+	}
+	c.sync();
+	// flatten: lab[i] = root.  A root keeps pointing to itself, and a non-root is only ever read through find(), so the
+	// in-place rewrite is safe without a second buffer.
+	for (int i = c.tid; i < ncell; i += c.nthr)
+		if ((cell[i] & CELL_LEVEL) != skip)
+		{
+			const uint32_t root = uf16_find (lab, (uint32_t)i);
+			if (root != (uint32_t)i)
+				lab[i] = (uint16_t)root;
+		}
+	c.sync();
+	glszm_reduce (c, prm, cell, keys, cnts, mask, lab, zsw, ncell, skip, (double)r.area, out, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3D NGTDM, Chebyshev radius <= 1 (26 neighbours).  L1 = level slots = (largest binned level) + 2 (room for the +1 shift)
+// ------------------------------------------------------------------------------------------------
+constexpr int NGTDM3_NDMAX = 26;
+NYX_HD size_t ngtdm3d_smem_words (int Lmax)
+{
+	return ngtdm_words (Lmax + 2, NGTDM3_NDMAX) + 2;
+}
+
+// cell: cube binned with the NGTDM grey depth; matlab: the binning was MATLAB (zeroI = 1); maxlevel: largest level in the cube
+NYX_D void ngtdm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax,
+	bool matlab, double* out)
+{
+	const int w = r.w, h = r.h, d = r.d, ncell = w * h * d;
+	const int L1 = Lmax + 2;
+	const int R = prm.ngtdm3_radius;
+	if (R == 0)
+	{
+		// the default radius (env_features.cpp leaves NGTDM_RADIUS at 0): no voxel has a neighbour, the matrix is empty and
+		// every feature is NaN (or softNaN when |I| < 2) -> `noval` at output either way (output_2_buffer.cpp:577)
+		for (int i = c.tid; i < NCOL_NGTDM; i += c.nthr)
+			out[i] = nan ("");
+		return;
+	}
+	uint32_t* Nn = mem;
+	uint32_t* SI = Nn + L1;
+	uint32_t* PR = SI + (size_t)L1 * NGTDM3_NDMAX;
+	uint32_t* flags = mem + ngtdm_words (L1, NGTDM3_NDMAX);	// [0] some cell has level 0, [1] largest level
+	FastDiv fw, fh;
+	fw.init ((uint32_t)w);
+	fh.init ((uint32_t)h);
+
+	// ---- pass 0: does the cube hold a zero level; largest level (3d_ngtdm.cpp:200-225)
+	if (c.tid == 0)
+	{
+		flags[0] = 0;
+		flags[1] = 0;
+	}
+	c.sync();
+	{
+		uint32_t z0 = 0, mx = 0;
+		for (int i = c.tid; i < ncell; i += c.nthr)
+		{
+			const uint32_t lv = cell[i] & CELL_LEVEL;
+			z0 |= lv == 0 ? 1u : 0u;
+			mx = lv > mx ? lv : mx;
+		}
+		if (z0)
+			flags[0] = 1;
+		atom_max (c, flags + 1, mx);
+	}
+	c.sync();
+	const bool ibsi = prm.ibsi != 0;
+	const uint32_t shift = (ibsi || flags[0]) ? 1u : 0u;	// IBSI: I = 0..max so I[0] == 0 always
+	const uint32_t maxlv = flags[1];
+	const uint32_t zeroI = matlab ? 1u : 0u;
+	c.sync();
+
+	unsigned long long q[1] = { 0 };
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = (cell[i] & CELL_LEVEL) + shift;
+		PR[lv] = 1;	// U holds every value of the cube
+		if (lv == zeroI)
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+		const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+		int nd = 0;
+		uint32_t sum = 0;
+		for (int dz = -R; dz <= R; dz++)
+		{
+			const int zz = z + dz;
+			if (zz < 0 || zz >= d)
+				continue;
+			for (int dy = -R; dy <= R; dy++)
+			{
+				const int yy = y + dy;
+				if (yy < 0 || yy >= h)
+					continue;
+				for (int dx = -R; dx <= R; dx++)
+				{
+					const int xx = x + dx;
+					if ((!dx && !dy && !dz) || xx < 0 || xx >= w)
+						continue;
+					sum += (cell[(zz * h + yy) * w + xx] & CELL_LEVEL) + shift;
+					nd++;
+				}
+			}
+		}
+		if (nd > 0)
+		{
+			long long df = (long long)lv * nd - (long long)sum;
+			atom_add (c, Nn + lv, 1u);
+			atom_add (c, SI + (size_t)lv * NGTDM3_NDMAX + (nd - 1), (uint32_t)(df < 0 ? -df : df));
+			q[0]++;
+		}
+	}
+	c.sync();
+	cta_sum_u64<1> (c, q);
+	// |I|: IBSI flag -> 0..max (max + 1 levels); else the number of distinct values = Ngp, found by the sweep (-1)
+	const int isize = ibsi ? (int)maxlv + 1 : -1;
+	ngtdm_reduce (c, prm, mem, L1, NGTDM3_NDMAX, 0, (double)q[0], isize, false, out, nullptr);
+}
+
+} // namespace nyx

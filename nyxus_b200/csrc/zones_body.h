@@ -157,6 +157,9 @@ NYX_HD size_t glszm_smem_words (uint32_t maxcells, uint32_t slots)
 	return (size_t)slots * 2 + 2 * (((size_t)maxcells + 1) / 2);
 }
 
+NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, uint32_t* keys, uint32_t* cnts, uint32_t mask,
+	const uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg);
+
 NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, uint32_t maxcells,
 	uint32_t slots, double* out, const ZoneDebug* dbg)
 {
@@ -265,11 +268,20 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		}
 	}
 	c.sync();
+	glszm_reduce (c, prm, cell, keys, cnts, mask, lab, zsw, ncell, 0u, -1.0, out, dbg);
+}
 
+// Common tail of 2D and 3D GLSZM.  lab[i] = zone id (cell index of the zone's representative) of every cell whose level is
+// not `skip`; zsw: zeroed packed u16 size counters.  np_fixed >= 0 overrides Np (3D: the voxel-cloud size, 3d_glszm.cpp:534).
+NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, uint32_t* keys, uint32_t* cnts, uint32_t mask,
+	const uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg)
+{
+	const uint16_t* zs = (const uint16_t*)zsw;
+	const uint32_t slots = mask + 1;
 	// ---- zone sizes (packed 16-bit counters: a size is at most the cell count < 65536), Np
 	unsigned long long np[1] = { 0 };
 	for (int i = c.tid; i < ncell; i += c.nthr)
-		if (cell[i] & CELL_LEVEL)
+		if ((cell[i] & CELL_LEVEL) != skip)
 		{
 			np[0]++;
 			const uint32_t l = lab[i];
@@ -290,7 +302,7 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
 		const uint32_t lv = cell[i] & CELL_LEVEL;
-		if (!lv || lab[i] != (uint32_t)i)
+		if (lv == skip || lab[i] != (uint32_t)i)
 			continue;
 		const uint32_t sz = zs[i];
 		htab_add (c, keys, cnts, mask, (lv << 16) | sz);
@@ -330,7 +342,7 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
 		const uint32_t lv = cell[i] & CELL_LEVEL;
-		if (!lv || lab[i] != (uint32_t)i)
+		if (lv == skip || lab[i] != (uint32_t)i)
 			continue;
 		const uint32_t sz = zs[i];
 		q2[0] += htab_get (keys, cnts, mask, lv << 16);
@@ -355,7 +367,7 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		out[S_GLNN] = (double)q2[0] / (sum * sum);
 		out[S_SZN] = (double)q2[1] / sum;
 		out[S_SZNN] = (double)q2[1] / (sum * sum);
-		out[S_ZP] = sum / (double)q[Q_NP];				// :507-511
+		out[S_ZP] = sum / (np_fixed >= 0 ? np_fixed : (double)q[Q_NP]);	// :507-511
 		out[S_GLV] = t[0] / sum;
 		out[S_ZV] = t[1] / sum;
 		out[S_ZE] = -(t[2] / sum) * (1.0 / LOG10_2);

@@ -12,7 +12,7 @@ class NyxusB200Error(RuntimeError):
 
 class Engine:
     def __init__(self, features, device=0, coarse_gray_depth=64, ibsi=False, glcm_offset=1, glcm_symmetric=False,
-                 soft_nan=0.0, verbose=0):
+                 soft_nan=0.0, verbose=0, dim=2):
         self._L = _lib.lib()
         self._ctx = C.c_void_p()
         st = _lib.Settings()
@@ -24,6 +24,8 @@ class Engine:
         st.glcm_symmetric = int(bool(glcm_symmetric))
         st.soft_nan = float(soft_nan)
         st.verbose = int(verbose)
+        st.dim = int(dim)
+        self.dim = int(dim)
         rc = self._L.nyxb200_create(C.byref(st), C.byref(self._ctx))
         if rc != 0:
             msg = self._L.nyxb200_last_error(None).decode()
@@ -68,11 +70,16 @@ class Engine:
         n = self._L.nyxb200_num_columns(self._ctx)
         return [self._L.nyxb200_column_code(self._ctx, i) for i in range(n)]
 
-    def _collect(self, tab, rimg):
+    def _collect(self, tab, rimg, copy=True):
         n, nc = tab.nrows, tab.ncols
         if n:
-            data = np.ctypeslib.as_array(tab.data, shape=(n, nc)).copy()
-            img = np.ctypeslib.as_array(rimg, shape=(n,)).copy()
+            # the table lives in the context's pinned host buffer (include/nyxus_b200.h: valid until the next featurize
+            # call on this context); copy=False hands out a view of it, like the reference's zero-copy capsule
+            # (new_bindings_py.cpp:63-73)
+            data = np.ctypeslib.as_array(tab.data, shape=(n, nc))
+            img = np.ctypeslib.as_array(rimg, shape=(n,))
+            if copy:
+                data, img = data.copy(), img.copy()
         else:
             data = np.zeros((0, nc))
             img = np.zeros((0,), np.int32)
@@ -98,8 +105,29 @@ class Engine:
         self._check(fn(self._ctx, inten.ctypes.data, label.ctypes.data, N, H, W, C.byref(tab), C.byref(rimg)))
         return self._collect(tab, rimg)
 
-    def featurize_ptr(self, inten_ptr, inten_is_u16, label_ptr, n_img, H, W, on_device):
-        """Raw-pointer entry (bench / torch interop).  on_device: pointers are device memory of this engine's GPU."""
+    def featurize_volume(self, inten, label):
+        """3D (dim=3 engines).  inten: uint16 or uint32 [D,H,W] or [N,D,H,W]; label: uint32 same shape.
+        Returns (table[nrows, 2+F], volume index per row)."""
+        inten = np.asarray(inten)
+        label = np.asarray(label)
+        if inten.ndim == 3:
+            inten, label = inten[None], label[None]
+        if inten.shape != label.shape or inten.ndim != 4:
+            raise ValueError("Intensity and label volumes must have matching dimensions")
+        if inten.dtype not in (np.uint16, np.uint32):
+            inten = inten.astype(np.uint32)
+        inten = np.ascontiguousarray(inten)
+        label = np.ascontiguousarray(label, dtype=np.uint32)
+        N, D, H, W = inten.shape
+        tab = _lib.Table()
+        rimg = C.POINTER(C.c_int32)()
+        fn = self._L.nyxb200_featurize_3d_u16 if inten.dtype == np.uint16 else self._L.nyxb200_featurize_3d_u32
+        self._check(fn(self._ctx, inten.ctypes.data, label.ctypes.data, N, D, H, W, C.byref(tab), C.byref(rimg)))
+        return self._collect(tab, rimg)
+
+    def featurize_ptr(self, inten_ptr, inten_is_u16, label_ptr, n_img, H, W, on_device, copy=True):
+        """Raw-pointer entry (bench / torch interop).  on_device: pointers are device memory of this engine's GPU.
+        copy=False returns views of the library-owned pinned result buffer (valid until the next call)."""
         tab = _lib.Table()
         rimg = C.POINTER(C.c_int32)()
         if on_device:
@@ -110,7 +138,7 @@ class Engine:
         else:
             rc = self._L.nyxb200_featurize_2d_u32(self._ctx, inten_ptr, label_ptr, n_img, H, W, C.byref(tab), C.byref(rimg))
         self._check(rc)
-        return self._collect(tab, rimg)
+        return self._collect(tab, rimg, copy)
 
     def timings(self):
         ms = (C.c_float * _lib.NSTAGES)()

@@ -149,3 +149,139 @@ class Nyxus:
         if "ROI_label" in df.columns:
             df.ROI_label = df.ROI_label.astype(np.uint32)
         return df
+
+
+_VALID_KEYS_3D = {
+    'neighbor_distance', 'pixels_per_micron', 'coarse_gray_depth',
+    'n_feature_calc_threads', 'use_gpu_device', 'ibsi', 'channel_signature',
+    'parent_channel', 'child_channel', 'aggregate',
+    'dynamic_range', 'min_intensity', 'max_intensity', 'ram_limit',
+    'verbose', 'anisotropy_x', 'anisotropy_y', 'anisotropy_z', 'preserve_hu'
+}
+
+
+class Nyxus3D:
+    """3D feature extraction (reference nyxus.py:923-1489) for the 3D families on this path: first-order
+    (*3D_ALL_INTENSITY*), *3D_GLCM*, *3D_GLSZM*, *3D_NGTDM* on a B200.
+
+    Like the reference, the class has no in-memory entry point of its own: `featurize_files` /
+    `featurize_directory` read NIfTI volumes.  `featurize(volume, labels)` is an addition for callers that already hold
+    the voxels.  Metaparameters follow the reference: only 3glcm/greydepth has a default (coarse_gray_depth);
+    3glszm/greydepth, 3ngtdm/greydepth and 3ngtdm/radius are 0 until set with `set_metaparam` (env_features.cpp:712-736)."""
+
+    def __init__(self, features: List[str], **kwargs):
+        invalid_keys = set(kwargs.keys()) - _VALID_KEYS_3D
+        if invalid_keys:
+            print(f"Warning: unexpected keyword argument(s): {', '.join(invalid_keys)}")
+        neighbor_distance = kwargs.get('neighbor_distance', 5)
+        pixels_per_micron = kwargs.get('pixels_per_micron', 1.0)
+        coarse_gray_depth = kwargs.get('coarse_gray_depth', 64)
+        n_feature_calc_threads = kwargs.get('n_feature_calc_threads', 4)
+        use_gpu_device = kwargs.get('use_gpu_device', -1)
+        ibsi = kwargs.get('ibsi', False)
+        verb_lvl = kwargs.get('verbose', 0)
+        aniso = [kwargs.get('anisotropy_x', 1.0), kwargs.get('anisotropy_y', 1.0), kwargs.get('anisotropy_z', 1.0)]
+        if neighbor_distance <= 0:
+            raise ValueError("Neighbor distance must be greater than zero.")
+        if pixels_per_micron <= 0:
+            raise ValueError("Pixels per micron must be greater than zero.")
+        if coarse_gray_depth <= 0:
+            raise ValueError("Custom number of grayscale levels (parameter coarse_gray_depth, default=64) must be non-negative.")
+        if n_feature_calc_threads < 1:
+            raise ValueError("There must be at least one feature calculation thread.")
+        if verb_lvl < 0:
+            raise ValueError("verbosity must be non-negative")
+        for name, a in zip("xyz", aniso):
+            if a <= 0:
+                raise ValueError(f"anisotropy_{name} must be positive")
+        if any(a != 1.0 for a in aniso):
+            raise ValueError("anisotropy is outside the texture/intensity path implemented by nyxus_b200")
+        if kwargs.get('preserve_hu', False):
+            raise ValueError("preserve_hu is outside the texture/intensity path implemented by nyxus_b200")
+        self._engine = Engine(list(features), device=max(int(use_gpu_device), 0), coarse_gray_depth=coarse_gray_depth,
+                              ibsi=ibsi, verbose=verb_lvl, dim=3)
+        self._valid_output_types = ['pandas', 'arrowipc', 'parquet']
+
+    def set_metaparam(self, paramval: str):
+        key, _, val = paramval.partition('=')
+        try:
+            self._engine.set_param(key.strip(), float(val))
+        except Exception as e:
+            raise ValueError(f'Invalid metaparameter value {paramval}: {e}')
+
+    @property
+    def feature_columns(self):
+        return self._engine.columns
+
+    def _frame(self, numeric, row_vol, int_names, seg_names):
+        header = ["intensity_image", "mask_image", "ROI_label", "t_index"] + self._engine.columns
+        string_data = np.array([[int_names[k], seg_names[k]] for k in row_vol], dtype=object).reshape(-1, 2)
+        df = pd.concat([pd.DataFrame(string_data, columns=header[:2]), pd.DataFrame(numeric, columns=header[2:])], axis=1)
+        if "ROI_label" in df.columns:
+            df.ROI_label = df.ROI_label.astype(np.uint32)
+        return df
+
+    def featurize(self, intensity_volume: np.ndarray, label_volume: np.ndarray, intensity_name: str = "Intensity0",
+                  label_name: str = "Segmentation0"):
+        """In-memory volume pair [D,H,W] (extension; the reference only reads files)."""
+        if not isinstance(intensity_volume, np.ndarray) or not isinstance(label_volume, np.ndarray):
+            raise ValueError("intensity_volume and label_volume must be numpy.ndarray")
+        if intensity_volume.ndim != 3 or intensity_volume.shape != label_volume.shape:
+            raise ValueError("Intensity and label volumes must be 3D arrays of the same shape")
+        I = intensity_volume
+        if I.dtype not in (np.uint16, np.uint32):
+            if np.min(I) < 0:
+                raise ValueError("negative voxels (Hounsfield-type scale) are outside the path implemented by nyxus_b200")
+            I = I.astype(np.uint32)
+        numeric, row_vol = self._engine.featurize_volume(I, label_volume.astype(np.uint32))
+        return self._frame(numeric, row_vol, [intensity_name], [label_name])
+
+    def featurize_files(self, intensity_files: list, mask_files: list, single_roi: bool, output_type: Optional[str] = "pandas",
+                        output_path: Optional[str] = ""):
+        import os
+        from . import nifti
+        if intensity_files is None:
+            raise IOError("The list of intensity file paths is empty")
+        if mask_files is None:
+            raise IOError("The list of segment file paths is empty")
+        if output_type not in self._valid_output_types:
+            raise ValueError(f'Invalid output type {output_type}. Valid output types are {self._valid_output_types}')
+        if output_type != 'pandas':
+            raise ValueError("arrowipc / parquet writers are outside the texture/intensity path implemented by nyxus_b200")
+        if not single_roi and len(intensity_files) != len(mask_files):
+            raise ValueError("Number of intensity files must match the number of mask files")
+        frames = []
+        for k, ifile in enumerate(intensity_files):
+            if not os.path.exists(ifile):
+                raise IOError(f"Error: file {ifile} does not exist")
+            I = nifti.to_grey(nifti.read(ifile), "intensity")
+            if single_roi:
+                M = np.ones(I.shape, np.uint32)       # whole volume = ROI 1 (new_bindings_py.cpp:788-795)
+                mname = ""
+            else:
+                if not os.path.exists(mask_files[k]):
+                    raise IOError(f"Error: file {mask_files[k]} does not exist")
+                M = nifti.to_grey(nifti.read(mask_files[k]), "mask").astype(np.uint32)
+                mname = os.path.basename(mask_files[k])
+                if M.shape != I.shape:
+                    raise ValueError(f"intensity / mask volume size mismatch: {I.shape} vs {M.shape}")
+            numeric, row_vol = self._engine.featurize_volume(I, M)
+            frames.append(self._frame(numeric, row_vol, [os.path.basename(ifile)], [mname]))
+        if not frames:
+            return self._frame(np.zeros((0, 2 + len(self._engine.columns))), [], [], [])
+        return pd.concat(frames, axis=0, ignore_index=True)
+
+    def featurize_directory(self, intensity_dir: str, label_dir: str, file_pattern: str, output_type: Optional[str] = "pandas",
+                            output_path: Optional[str] = ""):
+        import os
+        import re
+        if not os.path.exists(intensity_dir):
+            raise IOError(f"Provided intensity image directory '{intensity_dir}' does not exist.")
+        if label_dir is not None and not os.path.exists(label_dir):
+            raise IOError(f"Provided label image directory '{label_dir}' does not exist.")
+        single = label_dir is None or label_dir == intensity_dir
+        rx = re.compile(file_pattern)
+        names = sorted(f for f in os.listdir(intensity_dir) if rx.fullmatch(f) or rx.match(f))
+        ifiles = [os.path.join(intensity_dir, f) for f in names]
+        mfiles = [] if single else [os.path.join(label_dir, f) for f in names]
+        return self.featurize_files(ifiles, mfiles, single, output_type, output_path)

@@ -78,3 +78,43 @@ def random_rois(H, W, nroi, seed, maxval=5000, levels=None):
     z = rng.random((H, W)) < 0.02
     inten[z] = 0
     return inten, label
+
+
+def ellipsoid_volume(D, H, W, pitch, amin, amax, seed, dtype=np.uint16, zero_frac=0.01, sigma=4):
+    """Jittered lattice of ellipsoid ROIs (semi-axes U{amin..amax}); label id = 1 + lattice index.  Intensity model as in
+    blob_slide.  Returns (inten[D,H,W], label[D,H,W] uint32)."""
+    rng = np.random.default_rng(seed)
+    nz, ny, nx = D // pitch, H // pitch, W // pitch
+    label = np.zeros((D, H, W), np.uint32)
+    g = np.arange(pitch) - pitch // 2
+    Z, Y, X = np.meshgrid(g, g, g, indexing="ij")
+    lab = 1
+    jit = max(0, pitch // 2 - amax - 1)
+    for k in range(nz):
+        for j in range(ny):
+            for i in range(nx):
+                a = rng.integers(amin, amax + 1, 3).astype(np.float32)
+                dz, dy, dx = rng.integers(-jit, jit + 1, 3) if jit else (0, 0, 0)
+                m = ((Z - dz) / a[0]) ** 2 + ((Y - dy) / a[1]) ** 2 + ((X - dx) / a[2]) ** 2 <= 1.0
+                sub = label[k * pitch:(k + 1) * pitch, j * pitch:(j + 1) * pitch, i * pitch:(i + 1) * pitch]
+                sub[m] = lab
+                lab += 1
+    smooth = rng.standard_normal((D, H, W)).astype(np.float32)
+    kk = max(1, int(sigma))
+    for ax in range(3):
+        for _ in range(2):
+            c = np.cumsum(np.concatenate([smooth.take(range(-kk, 0), axis=ax), smooth, smooth.take(range(0, kk), axis=ax)], axis=ax), axis=ax)
+            n = smooth.shape[ax]
+            smooth = (c.take(range(2 * kk, 2 * kk + n), axis=ax) - c.take(range(0, n), axis=ax)) / (2 * kk)
+    smooth /= (smooth.std() + 1e-12)
+    inten = 2000.0 + 1500.0 * smooth + 800.0 * rng.standard_normal((D, H, W)).astype(np.float32)
+    inten = np.clip(inten, 1, 65535).astype(dtype)
+    if zero_frac > 0:
+        z = (rng.random((D, H, W), dtype=np.float32) < zero_frac) & (label != 0)
+        inten[z] = 0
+    return inten, label
+
+
+def config4(seed=4, size=512):
+    """C4: size^3 uint16 volume, ellipsoid ROIs (semi-axes 6..14) on a pitch-39 lattice: 13^3 = 2197 ROIs at 512^3"""
+    return ellipsoid_volume(size, size, size, 39, 6, 14, seed)

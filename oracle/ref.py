@@ -123,3 +123,37 @@ def roi_matrices(tile, mask, greydepth=64, ibsi=False, glcm_offset=1, fam_mask=F
             ks += 1
     res["NGTDM_S"] = S
     return res
+
+
+# ---------------------------------------------------------------------------------------------- 3D (Nyxus3D path)
+FAM3 = {"INT": 1, "GLCM": 2, "NGTDM": 4, "GLSZM": 8}
+
+
+def columns_3d():
+    L = lib()
+    L.nyxref3d_colname.restype = C.c_char_p
+    return [L.nyxref3d_colname(i).decode() for i in range(L.nyxref3d_ncols())]
+
+
+def featurize_3d(inten, label, greydepth=64, glcm_greydepth=None, glszm_greydepth=0, ngtdm_greydepth=0, ngtdm_radius=0,
+                 ibsi=False, fam_mask=15, nthreads=1, force_finite=True):
+    """inten, label: [D,H,W].  Returns (labels, table[n, 116], phase seconds).  Defaults follow env_features.cpp:712-736
+    (only GLCM gets a grey depth; 3D GLSZM / NGTDM depths and the NGTDM radius are 0 unless set)."""
+    L = lib()
+    I = np.ascontiguousarray(inten, dtype=np.uint32)
+    M = np.ascontiguousarray(label, dtype=np.uint32)
+    D, H, W = I.shape
+    nc = L.nyxref3d_ncols()
+    cap = int(len(np.unique(M))) + 1
+    labels = np.zeros(cap, np.int32)
+    out = np.zeros((cap, nc), np.float64)
+    tph = np.zeros(8, np.float64)
+    L.nyxref_featurize_3d.restype = C.c_int
+    L.nyxref_featurize_3d.argtypes = [C.c_void_p, C.c_void_p] + [C.c_int] * 9 + [C.c_uint, C.c_int, C.c_int, C.c_int,
+                                                                                  C.c_void_p, C.c_void_p, C.c_void_p]
+    n = L.nyxref_featurize_3d(I.ctypes.data, M.ctypes.data, D, H, W, int(greydepth),
+                              int(greydepth if glcm_greydepth is None else glcm_greydepth), int(glszm_greydepth),
+                              int(ngtdm_greydepth), int(ngtdm_radius), int(bool(ibsi)), int(fam_mask), int(nthreads),
+                              int(bool(force_finite)), cap, labels.ctypes.data, out.ctypes.data, tph.ctypes.data)
+    assert n >= 0, n
+    return labels[:n].copy(), out[:n].copy(), tph

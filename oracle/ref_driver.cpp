@@ -92,6 +92,10 @@
 #include "features/gldm.h"
 #include "features/ngldm.h"
 #include "features/ngtdm.h"
+#include "features/3d_intensity.h"
+#include "features/3d_glcm.h"
+#include "features/3d_glszm.h"
+#include "features/3d_ngtdm.h"
 #undef private
 #undef protected
 
@@ -102,6 +106,8 @@ namespace Nyxus
 	// defined in features_calc_workflow.cpp
 	void init_label_record_3 (LR& lr, int x, int y, PixIntens intensity);
 	void update_label_record_3 (LR& lr, int x, int y, PixIntens intensity);
+	void init_label_record_3D (LR& lr, int x, int y, int z, int label, PixIntens intensity);
+	void update_label_record_3D (LR& lr, int x, int y, int z, int label, PixIntens intensity);
 }
 
 namespace
@@ -505,5 +511,163 @@ int64_t nyxref_roi_matrices (const uint32_t* tile, const uint8_t* mask, int w, i
 double nyxref_fast_log10 (double x) { return Nyxus::fast_log10 (x); }
 unsigned nyxref_bin_pixel (unsigned x, unsigned mn, unsigned mx, int greyinfo) { return TextureFeature::bin_pixel (x, mn, mx, greyinfo); }
 unsigned nyxref_to_grayscale (unsigned i, unsigned mn, unsigned range, unsigned n) { return Nyxus::to_grayscale (i, mn, range, n, false); }
+
+} // extern "C"
+
+// ====================================================================================================
+// 3D (Nyxus3D path): D3_VoxelIntensityFeatures, D3_GLCM_feature, D3_GLSZM_feature, D3_NGTDM_feature
+// ====================================================================================================
+namespace
+{
+	enum Fam3 { F3_INT = 1, F3_GLCM = 2, F3_NGTDM = 4, F3_GLSZM = 8 };
+	struct Col3 { int code; std::string name; int fam; };
+	std::vector<Col3> g_cols3;
+
+	void build_cols3()
+	{
+		if (!g_cols3.empty())
+			return;
+		FeatureSet fs;
+		std::vector<std::pair<int, int>> codes;
+		for (auto c : D3_VoxelIntensityFeatures::featureset) codes.push_back ({ (int)c, F3_INT });
+		for (auto c : D3_GLCM_feature::featureset) codes.push_back ({ (int)c, F3_GLCM });
+		for (auto c : D3_NGTDM_feature::featureset) codes.push_back ({ (int)c, F3_NGTDM });
+		for (auto c : D3_GLSZM_feature::featureset) codes.push_back ({ (int)c, F3_GLSZM });
+		std::sort (codes.begin(), codes.end());
+		// one column per code: save_features_2_buffer treats every 3D code as a regular feature and exports fvals[code][0]
+		// (output_2_buffer.cpp:331-358 only expands Feature2D GLCM / GLRLM codes)
+		for (auto [c, fam] : codes)
+			g_cols3.push_back ({ c, fs.findFeatureNameByCode ((Feature3D)c), fam });
+	}
+}
+
+extern "C"
+{
+
+int nyxref3d_ncols() { build_cols3(); return (int)g_cols3.size(); }
+const char* nyxref3d_colname (int i) { build_cols3(); return g_cols3[i].name.c_str(); }
+int nyxref3d_colcode (int i) { build_cols3(); return g_cols3[i].code; }
+int nyxref3d_colfamily (int i) { build_cols3(); return g_cols3[i].fam; }
+
+// Whole volume: replays gatherRoisMetrics_3D (phase1.cpp:248-366: voxel loop z,y,x + feed_pixel_2_metrics_3D),
+// scanTrivialRois_3D (feed_pixel_2_cache_3D_LR, pixel_feed.cpp:76-95), allocateTrivialRoisBuffers_3D
+// (phase2_3d.cpp:816-840) and the four reducers.  Slide extrema = min/max over the labelled voxels
+// (slideprops.cpp:305-327).  I, L: [D][H][W].  out: n x nyxref3d_ncols().
+int nyxref_featurize_3d (const uint32_t* I, const uint32_t* L, int D, int H, int W,
+	int greydepth, int glcm_greydepth, int glszm_greydepth, int ngtdm_greydepth, int ngtdm_radius, int ibsi,
+	unsigned fam_mask, int nthreads, int force_finite, int cap, int32_t* out_labels, double* out, double* t_phase)
+{
+	build_cols3();
+	Fsettings s = make_settings (greydepth, ibsi != 0, 1);
+	s[(int)NyxSetting::GLCM_GREYDEPTH].ival = glcm_greydepth;
+	s[(int)NyxSetting::GLSZM_GREYDEPTH].ival = glszm_greydepth;
+	s[(int)NyxSetting::NGTDM_GREYDEPTH].ival = ngtdm_greydepth;
+	s[(int)NyxSetting::NGTDM_RADIUS].ival = ngtdm_radius;
+	std::unordered_set<int> uniqueLabels;
+	std::unordered_map<int, LR> roiData;
+	double t0 = now_s();
+	double smin = (std::numeric_limits<double>::max)(), smax = (std::numeric_limits<double>::lowest)();
+	const size_t slice = (size_t)H * W;
+	for (int z = 0; z < D; z++)
+		for (int y = 0; y < H; y++)
+			for (int x = 0; x < W; x++)
+			{
+				const size_t i = z * slice + (size_t)y * W + x;
+				int label = (int)L[i];
+				if (!label)
+					continue;
+				PixIntens inten = I[i];
+				smin = std::min (smin, (double)inten);
+				smax = std::max (smax, (double)inten);
+				if (uniqueLabels.find (label) == uniqueLabels.end())
+				{
+					uniqueLabels.insert (label);
+					LR newRoi (label);
+					newRoi.slide_idx = 0;
+					init_label_record_3D (newRoi, x, y, z, label, inten);
+					roiData[label] = newRoi;
+				}
+				else
+					update_label_record_3D (roiData[label], x, y, z, label, inten);
+			}
+	Dataset ds;
+	{
+		SlideProps p;
+		p.max_preroi_inten = smax;
+		p.min_preroi_inten = smin;
+		ds.dataset_props.push_back (p);
+	}
+	for (auto& kv : roiData)
+	{
+		kv.second.make_nonanisotropic_aabb();
+		kv.second.initialize_fvals();
+	}
+	std::vector<int> labels (uniqueLabels.begin(), uniqueLabels.end());
+	std::sort (labels.begin(), labels.end());
+	int n = (int)labels.size();
+	if (n > cap)
+		return -n;
+	double t1 = now_s();
+	for (int z = 0; z < D; z++)
+		for (int y = 0; y < H; y++)
+			for (int x = 0; x < W; x++)
+			{
+				const size_t i = z * slice + (size_t)y * W + x;
+				int label = (int)L[i];
+				if (!label)
+					continue;
+				LR& r = roiData[label];
+				r.raw_pixels_3D.push_back (Pixel3 (x, y, z, I[i]));
+			}
+	for (auto lab : labels)
+	{
+		LR& r = roiData[lab];
+		r.aux_image_cube.calculate_from_pixelcloud (r.raw_pixels_3D, r.aabb);
+	}
+	double t2 = now_s();
+	if (t_phase)
+	{
+		t_phase[0] = t1 - t0;
+		t_phase[1] = t2 - t1;
+	}
+	int nThr = std::max (1, nthreads);
+	size_t job = labels.size(), wpt = job / nThr;
+	struct Step { unsigned fam; functype f; };
+	const Step steps[] = {
+		{ F3_INT, D3_VoxelIntensityFeatures::reduce },
+		{ F3_GLCM, D3_GLCM_feature::reduce },
+		{ F3_NGTDM, D3_NGTDM_feature::reduce },
+		{ F3_GLSZM, D3_GLSZM_feature::reduce } };
+	int si = 2;
+	for (const auto& st : steps)
+	{
+		double ta = now_s();
+		if (fam_mask & st.fam)
+			runParallel (st.f, nThr, wpt, job, &labels, &roiData, s, ds);
+		if (t_phase)
+			t_phase[si] = now_s() - ta;
+		si++;
+	}
+	size_t nc = g_cols3.size();
+	for (int i = 0; i < n; i++)
+	{
+		const LR& r = roiData[labels[i]];
+		out_labels[i] = labels[i];
+		for (size_t c = 0; c < nc; c++)
+		{
+			const Col3& col = g_cols3[c];
+			double v = 0.0;
+			if (fam_mask & col.fam)
+			{
+				const auto& vv = r.fvals[col.code];
+				v = vv.empty() ? 0.0 : vv[0];
+			}
+			if (force_finite)
+				v = force_finite_number (v, 0.0);
+			out[(size_t)i * nc + c] = v;
+		}
+	}
+	return n;
+}
 
 } // extern "C"

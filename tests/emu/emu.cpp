@@ -14,6 +14,7 @@
 #include "../../nyxus_b200/csrc/zones_body.h"
 #include "../../nyxus_b200/csrc/nbr_body.h"
 #include "../../nyxus_b200/csrc/intensity_body.h"
+#include "../../nyxus_b200/csrc/vol_body.h"
 
 using namespace nyx;
 
@@ -115,6 +116,92 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 	{
 		std::vector<uint32_t> mem (ngtdm_smem_words (Lmax));
 		ngtdm_body (c, r, prm, cell.data(), mem.data(), Lmax, out + COL_NGTDM, nullptr);
+	}
+	return 0;
+}
+
+
+// ---- 3D: one labelled volume [D][H][W], label value `lab`; fam_mask bits: 1 INT, 2 GLCM, 4 NGTDM, 8 GLSZM.
+// out layout: 36 first-order | 30x13 + 29 GLCM | 5 NGTDM | 16 GLSZM   (the canonical 3D table of the library)
+extern "C" int nyxemu_ncols3d() { return NCOL_INT + NCOL_GLCM3 + NCOL_NGTDM + NCOL_GLSZM; }
+extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl, int D, int H, int W, uint32_t lab,
+	int greydepth, int glszm_g, int ngtdm_g, int ngtdm_radius, int ibsi, double covered_den, unsigned fam_mask, double* out)
+{
+	RoiRec r;
+	memset (&r, 0, sizeof (r));
+	r.label = lab;
+	r.imin = 0xFFFFFFFFu;
+	int x0 = W, x1 = -1, y0 = H, y1 = -1, z0 = D, z1 = -1;
+	std::vector<uint32_t> cloud;
+	for (int z = 0; z < D; z++)
+		for (int y = 0; y < H; y++)
+			for (int x = 0; x < W; x++)
+			{
+				size_t i = ((size_t)z * H + y) * W + x;
+				if (lbl[i] != lab)
+					continue;
+				uint32_t v = vol[i];
+				r.area++;
+				r.imin = std::min (r.imin, v);
+				r.imax = std::max (r.imax, v);
+				x0 = std::min (x0, x); x1 = std::max (x1, x);
+				y0 = std::min (y0, y); y1 = std::max (y1, y);
+				z0 = std::min (z0, z); z1 = std::max (z1, z);
+				cloud.push_back (v);
+			}
+	if (!r.area)
+		return -1;
+	r.x0 = x0; r.y0 = y0; r.z0 = z0; r.w = x1 - x0 + 1; r.h = y1 - y0 + 1; r.d = z1 - z0 + 1;
+	ImageView im { vol, lbl, H, W, 0, D };
+	Params prm { greydepth, ibsi, 1, 0, 0.0 };
+	prm.glszm3_greydepth = glszm_g;
+	prm.ngtdm3_greydepth = ngtdm_g;
+	prm.ngtdm3_radius = ngtdm_radius;
+	prm.covered_den = covered_den;
+	std::vector<double> red (RED_MAX * NW_MAX);
+	Cta c { 0, 1, red.data() };
+	const int ncell = r.w * r.h * r.d;
+	const int n3 = nyxemu_ncols3d();
+	for (int i = 0; i < n3; i++)
+		out[i] = 0;
+	const int O_GLCM = NCOL_INT, O_NGTDM = O_GLCM + NCOL_GLCM3, O_GLSZM = O_NGTDM + NCOL_NGTDM;
+	std::vector<uint32_t> cell (ncell);
+	if (fam_mask & 1)
+	{
+		uint32_t npad = next_pow2 (r.area);
+		std::vector<uint32_t> mem (intensity_smem_words (npad, greydepth));
+		intensity_body (c, r, prm, cloud.data(), r.area, npad, mem.data(), out);
+	}
+	for (int fam = 1; fam <= 3; fam++)
+	{
+		const unsigned bit = fam == 1 ? 2u : fam == 2 ? 8u : 4u;	// GLCM, GLSZM, NGTDM
+		if (!(fam_mask & bit))
+			continue;
+		int g = fam == 1 ? greydepth : fam == 2 ? glszm_g : ngtdm_g;
+		if (ibsi)
+			g = 0;
+		Binner B;
+		B.init (g, r.imin, r.imax);
+		load_cube (c, im, r, B, cell.data());
+		int Lm = g > 0 ? g : (int)std::max (r.imax, 1u);
+		if (fam == 1)
+		{
+			std::vector<uint32_t> mem (glcm_smem_words<false> (Lm, 4));
+			glcm3d_body<false> (c, r, prm, cell.data(), mem.data(), Lm, out + O_GLCM);
+		}
+		else if (fam == 2)
+		{
+			const uint32_t slots = glszm_hash_slots (Lm, (uint32_t)ncell);
+			std::vector<uint32_t> mem (glszm3d_smem_words ((uint32_t)ncell, slots));
+			glszm3d_body (c, r, prm, cell.data(), mem.data(), (uint32_t)ncell, slots, g > 0, out + O_GLSZM);
+		}
+		else
+		{
+			if (ngtdm_radius == 0)
+				Lm = 1;
+			std::vector<uint32_t> mem (ngtdm3d_smem_words (Lm));
+			ngtdm3d_body (c, r, prm, cell.data(), mem.data(), Lm, g > 0, out + O_NGTDM);
+		}
 	}
 	return 0;
 }

@@ -65,6 +65,8 @@ def build_emu():
     L.nyxemu_bin.argtypes = [C.c_uint, C.c_uint, C.c_uint, C.c_int]
     L.nyxemu_to_grayscale.restype = C.c_uint
     L.nyxemu_to_grayscale.argtypes = [C.c_uint] * 4
+    L.nyxemu_roi_features_3d.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_int,
+                                         C.c_int, C.c_int, C.c_double, C.c_uint, C.c_void_p]
     return L
 
 
@@ -87,3 +89,53 @@ def place_roi(tile, mask, H=None, W=None, y=3, x=5, label=1):
     I[y:y + h, x:x + w] = tile
     L[y:y + h, x:x + w] = np.where(mask != 0, label, 0)
     return I, L
+
+
+# ---------------------------------------------------------------------------------------------- 3D helpers
+G3 = ["ASM", "ACOR", "CLUPROM", "CLUSHADE", "CLUTEND", "CONTRAST", "CORRELATION", "DIFAVE", "DIFENTRO", "DIFVAR", "DIS", "ENERGY",
+      "ENTROPY", "HOM1", "HOM2", "ID", "IDN", "IDM", "IDMN", "INFOMEAS1", "INFOMEAS2", "IV", "JAVE", "JE", "JMAX", "JVAR",
+      "SUMAVERAGE", "SUMENTROPY", "SUMVARIANCE", "VARIANCE"]
+
+
+def load_golden_vol():
+    z = np.load(os.path.join(GOLDEN, "golden_vol.npz"))
+    d = {k: z[k] for k in z.files}
+    d["columns"] = [str(c) for c in d["columns"]]
+    return d
+
+
+def canonical3d_index(cols):
+    """position of every reference 3D column in the library's canonical 3D table (36 | 30x13+29 | 5 | 16)"""
+    idx, nave, pi, pn, pz = [], 0, 0, 0, 0
+    for c in cols:
+        if c.startswith("3GLCM_"):
+            s = c[6:]
+            if s.endswith("_AVE"):
+                idx.append(36 + 390 + nave)
+                nave += 1
+            else:
+                idx.append(36 + G3.index(s) * 13)
+        elif c.startswith("3NGTDM_"):
+            idx.append(36 + 419 + pn)
+            pn += 1
+        elif c.startswith("3GLSZM_"):
+            idx.append(36 + 419 + 5 + pz)
+            pz += 1
+        else:
+            idx.append(pi)
+            pi += 1
+    return np.array(idx)
+
+
+def emu_roi_features_3d(L, vol, lbl, lab, g, gz, gn, rad, ibsi, cols):
+    """host-emulated 3D bodies for the ROI `lab` of a labelled volume, in the reference's column order"""
+    V = np.ascontiguousarray(vol, np.uint32)
+    M = np.ascontiguousarray(lbl, np.uint32)
+    fg = V[M > 0]
+    den = float(fg.max()) - float(fg.min())
+    out = np.zeros(36 + 419 + 5 + 16)
+    D, H, W = V.shape
+    rc = L.nyxemu_roi_features_3d(V.ctypes.data, M.ctypes.data, D, H, W, int(lab), int(g), int(gz), int(gn), int(rad), int(bool(ibsi)),
+                                  den, 15, out.ctypes.data)
+    assert rc == 0
+    return finite0(out[canonical3d_index(cols)])

@@ -228,3 +228,83 @@ def test_config2_full_size_properties(eng64):
     L2[7:7 + c, 13:13 + c] = Lc
     sh, _ = eng64.featurize(I2, L2)
     assert np.array_equal(sh, sub)
+
+
+# ------------------------------------------------------------------------------------------------ 3D (Nyxus3D path)
+GV = tu.load_golden_vol()
+
+
+def _engine3(case_params, features=("*3D_ALL_INTENSITY*", "*3D_GLCM*", "*3D_NGTDM*", "*3D_GLSZM*")):
+    from nyxus_b200 import Engine
+    g, gz, gn, rad, ibsi = [int(v) for v in case_params]
+    e = Engine(list(features), coarse_gray_depth=g, ibsi=bool(ibsi), dim=3)
+    e.set_param("3glszm/greydepth", gz)
+    e.set_param("3ngtdm/greydepth", gn)
+    e.set_param("3ngtdm/radius", rad)
+    return e
+
+
+@pytest.mark.parametrize("case", ["matlab64_r1", "defaults", "g16_r1", "ibsi_r1"])
+def test_golden_volume_table(case):
+    e = _engine3(GV["params_" + case])
+    try:
+        assert e.columns == GV["columns"]
+        vol = GV["inten_ibsi"] if case.startswith("ibsi") else GV["inten"]
+        tab, _ = e.featurize_volume(vol, GV["label"])
+        assert np.array_equal(tab[:, 0].astype(np.int64), GV["labels_" + case].astype(np.int64))
+        bad = tu.mismatches(GV["table_" + case], tab[:, 2:], GV["columns"])
+        assert not bad, bad[:8]
+        tab32, _ = e.featurize_volume(vol.astype(np.uint32), GV["label"])       # uint32 entry point: identical table
+        assert np.array_equal(tab, tab32)
+        recs = e.debug_rois()
+        L = GV["label"]
+        for r in recs:
+            zs, ys, xs = np.nonzero(L == r[0])
+            assert r[1] == len(zs) and (r[4], r[5], r[6], r[7]) == (xs.min(), ys.min(), xs.max() - xs.min() + 1, ys.max() - ys.min() + 1)
+    finally:
+        e.close()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so did not travel")
+def test_config4_style_volume_against_compiled_reference():
+    """BASELINE.json configs[3] at reduced size: 78^3 uint16, 8 ellipsoid ROIs (semi-axes 6..14), metaparams of SURVEY section 8d"""
+    from nyxus_b200 import synth
+    I, L = synth.config4(seed=4, size=78)
+    e = _engine3([64, 64, 64, 1, 0])
+    try:
+        tab, _ = e.featurize_volume(I, L)
+        rl, rt, _ = ref.featurize_3d(I.astype(np.uint32), L, greydepth=64, glszm_greydepth=64, ngtdm_greydepth=64, ngtdm_radius=1, nthreads=8)
+        assert tab.shape[0] == 8 and np.array_equal(tab[:, 0].astype(np.int64), rl.astype(np.int64))
+        bad = tu.mismatches(rt, tab[:, 2:], GV["columns"])
+        assert not bad, bad[:8]
+    finally:
+        e.close()
+
+
+def test_nyxus3d_featurize_files_nifti(tmp_path):
+    import os
+    from nyxus_b200 import Nyxus3D, nifti
+    ip, mp = os.path.join(tmp_path, "vol_int.nii.gz"), os.path.join(tmp_path, "vol_seg.nii")
+    nifti.write(ip, GV["inten"])
+    nifti.write(mp, GV["label"])
+    nyx = Nyxus3D(["*3D_ALL_INTENSITY*", "3GLCM_ASM", "3GLCM_CONTRAST_AVE", "*3D_GLSZM*", "*3D_NGTDM*"])
+    nyx.set_metaparam("3glszm/greydepth=64")
+    nyx.set_metaparam("3ngtdm/greydepth=64")
+    nyx.set_metaparam("3ngtdm/radius=1")
+    df = nyx.featurize_files([ip], [mp], False)
+    assert list(df.columns[:4]) == ["intensity_image", "mask_image", "ROI_label", "t_index"]
+    assert list(df.intensity_image.unique()) == ["vol_int.nii.gz"] and list(df.mask_image.unique()) == ["vol_seg.nii"]
+    assert list(df.ROI_label) == [int(v) for v in GV["labels_matlab64_r1"]]
+    cols = GV["columns"]
+    ref_tab = GV["table_matlab64_r1"]
+    for c in df.columns[4:]:
+        assert not tu.mismatches(ref_tab[:, cols.index(c)], df[c].to_numpy()), c
+    with pytest.raises(NyxusError_or_ValueError()):
+        Nyxus3D(["*3D_ALL_TEXTURE*"])                    # holds 3D families outside this path
+    with pytest.raises(ValueError, match="not a valid 3D feature name"):
+        Nyxus3D(["GLCM_ASM"])
+
+
+def NyxusError_or_ValueError():
+    from nyxus_b200 import NyxusB200Error
+    return (NyxusB200Error, ValueError)

@@ -1,0 +1,80 @@
+"""CPU tests of the 3D (Nyxus3D) path: the product's 3D feature bodies (host-emulated, test harness only) against golden
+vectors produced by the compiled reference, the NIfTI reader/writer, and the library's 3D column contract."""
+import os
+
+import numpy as np
+import pytest
+
+import nyx_testutil as tu
+from oracle import ref
+
+GV = tu.load_golden_vol()
+CASES = ["matlab64_r1", "defaults", "g16_r1", "ibsi_r1"]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_3d_feature_bodies_match_reference_golden(case):
+    L = tu.build_emu()
+    g, gz, gn, rad, ibsi = [int(v) for v in GV["params_" + case]]
+    vol = GV["inten_ibsi"] if ibsi else GV["inten"]
+    labels = GV["labels_" + case]
+    table = GV["table_" + case]
+    assert list(labels) == sorted(int(v) for v in np.unique(GV["label"]) if v)
+    for k, lab in enumerate(labels):
+        got = tu.emu_roi_features_3d(L, vol, GV["label"], lab, g, gz, gn, rad, ibsi, GV["columns"])
+        bad = tu.mismatches(table[k], got, GV["columns"])
+        assert not bad, (case, int(lab), bad[:6])
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so not built")
+def test_compiled_reference_reproduces_3d_golden():
+    for case in CASES:
+        g, gz, gn, rad, ibsi = [int(v) for v in GV["params_" + case]]
+        vol = GV["inten_ibsi"] if ibsi else GV["inten"]
+        labs, tab, _ = ref.featurize_3d(vol.astype(np.uint32), GV["label"], greydepth=g, glszm_greydepth=gz, ngtdm_greydepth=gn,
+                                        ngtdm_radius=rad, ibsi=bool(ibsi))
+        assert np.array_equal(labs, GV["labels_" + case])
+        assert np.array_equal(tab, GV["table_" + case])
+    assert ref.columns_3d() == GV["columns"]
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so not built")
+def test_3d_feature_bodies_randomised_against_compiled_reference():
+    L = tu.build_emu()
+    rng = np.random.default_rng(77)
+    cols = GV["columns"]
+    for it in range(24):
+        D, H, W = [int(rng.integers(2, 8)) for _ in range(3)]
+        kind = it % 3
+        V = rng.integers(1, 5000, (D, H, W)) if kind == 0 else rng.integers(1, 6, (D, H, W)) if kind == 1 else rng.integers(0, 200, (D, H, W))
+        M = (rng.random((D, H, W)) < rng.choice([0.6, 0.9, 1.0])).astype(np.uint32) * 7
+        if not M.any():
+            M[0, 0, 0] = 7
+        ibsi = bool(it % 4 == 0 and kind > 0)
+        g, gz, gn, rad = int(rng.choice([8, 64])), int(rng.choice([16, 64])), int(rng.choice([16, 64])), int(rng.choice([0, 1, 1]))
+        labs, tab, _ = ref.featurize_3d(V.astype(np.uint32), M, greydepth=g, glszm_greydepth=gz, ngtdm_greydepth=gn, ngtdm_radius=rad, ibsi=ibsi)
+        got = tu.emu_roi_features_3d(L, V, M, 7, g, gz, gn, rad, ibsi, cols)
+        assert not tu.mismatches(tab[0], got, cols), (it, kind, ibsi)
+
+
+def test_nifti_round_trip(tmp_path):
+    from nyxus_b200 import nifti
+    rng = np.random.default_rng(3)
+    for dt, name in [(np.uint8, "a.nii"), (np.uint16, "b.nii.gz"), (np.int16, "c.nii"), (np.uint32, "d.nii.gz"), (np.float32, "e.nii")]:
+        v = rng.integers(0, 200, (5, 6, 7)).astype(dt)
+        p = os.path.join(tmp_path, name)
+        nifti.write(p, v)
+        r = nifti.read(p)
+        assert r.shape == (5, 6, 7) and np.array_equal(r, v)
+        assert np.array_equal(nifti.to_grey(r), v.astype(np.uint32))
+    with pytest.raises(ValueError):
+        nifti.to_grey(np.array([[[0.5]]], np.float32))
+    with pytest.raises(ValueError):
+        nifti.to_grey(np.array([[[-3]]], np.int16))
+
+
+def test_3d_column_contract_of_the_library():
+    """the generated 3D table (nyx_feature_table3d.inc) lists the reference's 116 columns in Feature3D code order"""
+    inc = os.path.join(tu.ROOT, "nyxus_b200", "csrc", "nyx_feature_table3d.inc")
+    names = [ln.split('"')[1] for ln in open(inc) if ln.startswith("{")]
+    assert names == GV["columns"] and len(names) == 116
