@@ -78,6 +78,95 @@ struct GlcmDebug
 
 constexpr double INV_LOG10_2 = 1.0 / LOG10_2;
 
+// sums over the marginals of one angle (shared by the per-pair ROI kernels and the dense large-ROI reducer)
+enum GlcmM { M_S2R, M_S2C, M_JVAR, M_HX, M_IDM, M_ID, M_IDN, M_IDMN, M_IV, M_DENT, M_DVAR, M_SENT, M_CP, M_CS, M_CT, M_N };
+
+// contribution of marginal index k (k < 2Ng): cv = C[k], rv = R[k], dv = SPM[k] (k < Ng), sv = SPP[k]
+NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned long long rv, unsigned long long dv, unsigned long long sv,
+	double N, double mr, double mc, double diffavg, double NgD, double* m, double* px, double* py)
+{
+	if (k < Ng)
+	{
+		const double lv = (double)(k + 1);
+		const double pc = (double)cv / N, pr = (double)rv / N;
+		px[k] = pc;
+		py[k] = pr;
+		const double dr = lv - mr, dc = lv - mc;
+		m[M_S2R] += pr * dr * dr;			// :612-618, f_var :667-675
+		m[M_S2C] += pc * dc * dc;			// :621-627
+		m[M_JVAR] += dr * dr * pc;			// :1194-1200 (column marginal, row-marginal mean)
+		if (cv)
+			m[M_HX] += dmul (pc, fast_log10 (dadd (pc, GLCM_EPSILON)));	// :873-876
+		if (dv)
+		{
+			const double pm = (double)dv / N, kd = (double)k;
+			m[M_IDM] += pm / (1.0 + kd * kd);		// :685-687, HOM2 :1069
+			m[M_ID] += pm / (1.0 + kd);			// :1096-1097, HOM1 :942
+			m[M_IDN] += pm / (1.0 + kd / NgD);		// :1110-1111
+			m[M_IDMN] += pm / (1.0 + (kd * kd) / (NgD * NgD));	// :1082-1084
+			if (k >= 1)
+				m[M_IV] += pm / (kd * kd);		// :1123-1128
+			m[M_DENT] += dmul (pm, fast_log10 (dadd (pm, GLCM_EPSILON)));	// :778-781
+			const double dd = kd - diffavg;
+			m[M_DVAR] += dd * dd * pm;			// :753-765
+		}
+	}
+	if (k < 2 * Ng && sv)
+	{
+		const double pp = (double)sv / N;
+		m[M_SENT] += dmul (pp, fast_log10 (dadd (pp, GLCM_EPSILON)));	// :712-716
+		const double mm = (double)(k + 2) - mc - mc;
+		m[M_CT] += mm * mm * pp;				// :1028-1036
+		m[M_CS] += mm * mm * mm * pp;				// :1001-1009
+		m[M_CP] += mm * mm * mm * mm * pp;			// :979-987
+	}
+}
+
+// the 30 values of one angle from its sums.  sum_cnt2 = sum cnt^2, sum_rc = sum cnt*I_r*I_c, sum_d2 = sum k^2 Pxmy*N,
+// sum_s = sum (I_x+I_y) Pxpy*N (integers held in doubles are exact below 2^53);  HXY.. already scaled by 1/LOG10_2;
+// corr = sum (r-mr)(c-mc) p.  guard: the 2D softNaN guards (glcm.cpp:637-639,880-883; absent from 3d_glcm.cpp).
+NYX_D void glcm_finish (double* f, const double* m, double N, double mr, double diffavg, double sum_cnt2, double sum_rc, double sum_d2,
+	double sum_s, double jmax, double HXY, double HXY1, double HXY2, double HX, double corr, bool degenerate, bool guard, double softnan)
+{
+	// A single non-empty row or column makes every p(i,j) EXACTLY px(i)*py(j): the reference then sums identical terms
+	// for HXY, HXY1 and HXY2 and gets HXY - HXY2 == 0 exactly (INFOMEAS2 = 0, not sqrt(1e-16)); keep that identity.
+	if (degenerate)
+		HXY1 = HXY2 = HXY;
+	f[G_ASM] = sum_cnt2 / (N * N);					// :546-558
+	f[G_ENERGY] = f[G_ASM];						// :916-932
+	f[G_ACOR] = sum_rc / N;						// :947-966
+	f[G_CLUPROM] = m[M_CP];
+	f[G_CLUSHADE] = m[M_CS];
+	f[G_CLUTEND] = m[M_CT];
+	f[G_SUMVARIANCE] = m[M_CT];					// :324-326
+	f[G_CONTRAST] = sum_d2 / N;					// :566-584
+	const double sr = sqrt (m[M_S2R]), sc = sqrt (m[M_S2C]), den = sr * sc;
+	f[G_CORRELATION] = (!guard || den > 0.0) ? corr / den : softnan;	// :637-643 (3d_glcm.cpp: unguarded)
+	f[G_DIFAVE] = diffavg;
+	f[G_DIFENTRO] = -m[M_DENT] * INV_LOG10_2;
+	f[G_DIFVAR] = m[M_DVAR];
+	f[G_DIS] = diffavg;
+	f[G_ENTROPY] = -HXY;						// :722-739
+	f[G_JE] = -HXY;							// :1149-1165
+	f[G_HOM1] = m[M_ID];
+	f[G_HOM2] = m[M_IDM];
+	f[G_ID] = m[M_ID];
+	f[G_IDN] = m[M_IDN];
+	f[G_IDM] = m[M_IDM];
+	f[G_IDMN] = m[M_IDMN];
+	const double im1 = (HXY - HXY1) / HX;				// :880-883
+	f[G_INFOMEAS1] = (guard && (isnan (im1) || isinf (im1))) ? softnan : im1;
+	f[G_INFOMEAS2] = sqrt (fabs (1.0 - exp (-2.0 * (-HXY2 + HXY))));	// :913
+	f[G_IV] = m[M_IV];
+	f[G_JAVE] = mr;
+	f[G_JMAX] = jmax / N;						// :1167-1183
+	f[G_JVAR] = m[M_JVAR];
+	f[G_SUMAVERAGE] = sum_s / N;					// :693-704
+	f[G_SUMENTROPY] = -m[M_SENT] * INV_LOG10_2;
+	f[G_VARIANCE] = m[M_S2R];					// :647-676
+}
+
+
 // Pair enumeration.  2D (glcm.cpp:431-478): centre and neighbour must both have a non-zero ORIGINAL intensity.
 // 3D (3d_glcm.cpp:333-372): every in-cube pair counts (MATLAB binning turns background into level 1) unless the
 // binning keeps zeros (IBSI), where zero levels are skipped.
@@ -219,7 +308,6 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	const double NgD = prm.ibsi ? (double)r.imax : (double)Ng;
 
 	// ---- marginal sweep: px/py, marginal-only features, lists of the non-empty levels
-	enum { M_S2R, M_S2C, M_JVAR, M_HX, M_IDM, M_ID, M_IDN, M_IDMN, M_IV, M_DENT, M_DVAR, M_SENT, M_CP, M_CS, M_CT, M_N };
 	double m[M_N];
 	for (int k = 0; k < M_N; k++)
 		m[k] = 0;
@@ -227,49 +315,16 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	for (int base = 0; base < 2 * Ng; base += g.nthr)
 	{
 		const int k = base + g.tid;
-		uint32_t cv = 0, rv = 0;
+		uint32_t cv = 0, rv = 0, dv = 0, sv = 0;
 		if (k < Ng)
 		{
 			cv = Cm[k];
 			rv = Rm[k];
-			const double lv = (double)(k + 1);
-			const double pc = (double)cv / N, pr = (double)rv / N;
-			px[k] = pc;
-			py[k] = pr;
-			const double dr = lv - mr, dc = lv - mc;
-			m[M_S2R] += pr * dr * dr;			// :612-618, f_var :667-675
-			m[M_S2C] += pc * dc * dc;			// :621-627
-			m[M_JVAR] += dr * dr * pc;			// :1194-1200 (column marginal, row-marginal mean)
-			if (cv)
-				m[M_HX] += dmul (pc, fast_log10 (dadd (pc, GLCM_EPSILON)));	// :873-876
-			const uint32_t dv = SPM[k];
-			if (dv)
-			{
-				const double pm = (double)dv / N, kd = (double)k;
-				m[M_IDM] += pm / (1.0 + kd * kd);		// :685-687, HOM2 :1069
-				m[M_ID] += pm / (1.0 + kd);			// :1096-1097, HOM1 :942
-				m[M_IDN] += pm / (1.0 + kd / NgD);		// :1110-1111
-				m[M_IDMN] += pm / (1.0 + (kd * kd) / (NgD * NgD));	// :1082-1084
-				if (k >= 1)
-					m[M_IV] += pm / (kd * kd);		// :1123-1128
-				m[M_DENT] += dmul (pm, fast_log10 (dadd (pm, GLCM_EPSILON)));	// :778-781
-				const double dd = kd - diffavg;
-				m[M_DVAR] += dd * dd * pm;			// :753-765
-			}
+			dv = SPM[k];
 		}
 		if (k < 2 * Ng)
-		{
-			const uint32_t sv = SPP[k];
-			if (sv)
-			{
-				const double pp = (double)sv / N;
-				m[M_SENT] += dmul (pp, fast_log10 (dadd (pp, GLCM_EPSILON)));	// :712-716
-				const double mm = (double)(k + 2) - mc - mc;
-				m[M_CT] += mm * mm * pp;				// :1028-1036
-				m[M_CS] += mm * mm * mm * pp;				// :1001-1009
-				m[M_CP] += mm * mm * mm * mm * pp;			// :979-987
-			}
-		}
+			sv = SPP[k];
+		glcm_marginal_terms (k, Ng, cv, rv, dv, sv, N, mr, mc, diffavg, NgD, m, px, py);
 		const unsigned bx = g.ballot (cv != 0), by = g.ballot (rv != 0);
 		if (cv)
 			lx[nx + popc32 (bx & g.lanemask_lt())] = (uint16_t)k;
@@ -350,46 +405,10 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	g.sync();	// the region (incl. px/py/lists) may be reused by the next ROI
 
 	// ---- features of this angle
-	const double sc_log = INV_LOG10_2;		// x / LOG10_2 (glcm.h:241) applied once per sum
-	const double HXY = jd[0] / N * sc_log, HX = m[M_HX] * sc_log;
-	double HXY1 = jd[1] / N * sc_log, HXY2 = hxy2[0] * sc_log;
-	// A single non-empty row or column makes every p(i,j) EXACTLY px(i)*py(j): the reference then sums identical terms
-	// for HXY, HXY1 and HXY2 and gets HXY - HXY2 == 0 exactly (INFOMEAS2 = 0, not sqrt(1e-16)); keep that identity.
-	if (nx == 1 || ny == 1)
-		HXY1 = HXY2 = HXY;
 	double f[G_NANGLED];
-	f[G_ASM] = (double)s_asm / (N * N);				// :546-558  (sum cnt^2 == sum over pairs of cnt)
-	f[G_ENERGY] = f[G_ASM];						// :916-932
-	f[G_ACOR] = (double)q[Q_RC] / N;				// :947-966
-	f[G_CLUPROM] = m[M_CP];
-	f[G_CLUSHADE] = m[M_CS];
-	f[G_CLUTEND] = m[M_CT];
-	f[G_SUMVARIANCE] = m[M_CT];					// :324-326
-	f[G_CONTRAST] = (double)q[Q_D2] / N;				// :566-584
-	const double sr = sqrt (m[M_S2R]), sc = sqrt (m[M_S2C]), den = sr * sc;
-	f[G_CORRELATION] = (D3 || den > 0.0) ? (jd[2] / N) / den : softnan;	// :637-643 (3d_glcm.cpp: unguarded)
-	f[G_DIFAVE] = diffavg;
-	f[G_DIFENTRO] = -m[M_DENT] * sc_log;
-	f[G_DIFVAR] = m[M_DVAR];
-	f[G_DIS] = diffavg;
-	f[G_ENTROPY] = -HXY;						// :722-739
-	f[G_JE] = -HXY;							// :1149-1165
-	f[G_HOM1] = m[M_ID];
-	f[G_HOM2] = m[M_IDM];
-	f[G_ID] = m[M_ID];
-	f[G_IDN] = m[M_IDN];
-	f[G_IDM] = m[M_IDM];
-	f[G_IDMN] = m[M_IDMN];
-	const double im1 = (HXY - HXY1) / HX;				// :880-883
-	f[G_INFOMEAS1] = (!D3 && (isnan (im1) || isinf (im1))) ? softnan : im1;
-	f[G_INFOMEAS2] = sqrt (fabs (1.0 - exp (-2.0 * (-HXY2 + HXY))));	// :913
-	f[G_IV] = m[M_IV];
-	f[G_JAVE] = mr;
-	f[G_JMAX] = (double)jmax / N;					// :1167-1183
-	f[G_JVAR] = m[M_JVAR];
-	f[G_SUMAVERAGE] = (double)q[Q_S] / N;				// :693-704
-	f[G_SUMENTROPY] = -m[M_SENT] * sc_log;
-	f[G_VARIANCE] = m[M_S2R];					// :647-676
+	glcm_finish (f, m, N, mr, diffavg, (double)s_asm, (double)q[Q_RC], (double)q[Q_D2], (double)q[Q_S], (double)jmax,
+		jd[0] / N * INV_LOG10_2, jd[1] / N * INV_LOG10_2, hxy2[0] * INV_LOG10_2, m[M_HX] * INV_LOG10_2, jd[2] / N,
+		nx == 1 || ny == 1, !D3, softnan);
 	if (g.tid == 0)
 		for (int k = 0; k < G_NANGLED; k++)
 			out[k * ostride + a] = f[k];
