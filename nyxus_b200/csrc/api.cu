@@ -636,20 +636,23 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		k_init_stats<<<(ctx->stats_cap + 255) / 256, 256, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab);
 		CU (cudaGetLastError());
 		stage_begin (ctx, ST_SCAN);
-		const bool vec = ((uintptr_t)im.label % 16 == 0) && ((uintptr_t)im.inten % (im.inten_u16 ? 8 : 16) == 0);
-		const unsigned long long ngroups = (npix + 3) / 4;
-		int grid = (int)std::min<unsigned long long> ((ngroups + 255) / 256, (unsigned long long)ctx->sm_count * 32);
-		grid = std::max (grid, 1);
-		if (im.inten_u16)
+		const bool vec = (im.W % 4 == 0) && ((uintptr_t)im.label % 16 == 0) && ((uintptr_t)im.inten % (im.inten_u16 ? 8 : 16) == 0);
+		const uint32_t nrows = (uint32_t)im.D * (uint32_t)im.H, nchunk = ((uint32_t)im.W + 127) / 128;
+		const unsigned long long nitems = (unsigned long long)nrows * nchunk;
+		const int grid = (int)std::max<unsigned long long> (1, std::min<unsigned long long> ((nitems + 7) / 8, (unsigned long long)ctx->sm_count * 8));
+#define NYX_SCAN(U16, VEC, D3) k_scan_stats<U16, VEC, D3><<<grid, 256, 0, s>>> (im.inten, im.label, (uint32_t)im.W, nrows, (uint32_t)im.H, nchunk, \
+			ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab)
+		if (d3)
 		{
-			if (vec) k_scan_stats<true, true><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab, (uint32_t)im.H);
-			else k_scan_stats<true, false><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab, (uint32_t)im.H);
+			if (im.inten_u16) { if (vec) NYX_SCAN (true, true, true); else NYX_SCAN (true, false, true); }
+			else { if (vec) NYX_SCAN (false, true, true); else NYX_SCAN (false, false, true); }
 		}
 		else
 		{
-			if (vec) k_scan_stats<false, true><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab, (uint32_t)im.H);
-			else k_scan_stats<false, false><<<grid, 256, 0, s>>> (im.inten, im.label, npix, (uint32_t)im.W, ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab, (uint32_t)im.H);
+			if (im.inten_u16) { if (vec) NYX_SCAN (true, true, false); else NYX_SCAN (true, false, false); }
+			else { if (vec) NYX_SCAN (false, true, false); else NYX_SCAN (false, false, false); }
 		}
+#undef NYX_SCAN
 		CU (cudaGetLastError());
 		ctx->counts[0] += 2;
 		stage_begin (ctx, ST_COMPACT);

@@ -67,128 +67,195 @@ __global__ void k_init_stats (LabelStat* tab, uint32_t cap, SlideInfo* info, uin
 		memset (info, 0, sizeof (SlideInfo));
 }
 
-__device__ __forceinline__ void stat_group_update (unsigned part, LabelStat* tab, uint32_t cap, uint32_t lbl, uint32_t cnt,
-	uint32_t vmin, uint32_t vmax, uint32_t xmin, uint32_t xmax, uint32_t y, uint2* ztab = nullptr, uint32_t H = 0)
+// One finished run of equal labels inside a row: the 7 (2D) or 9 (3D) commutative updates of its label record.
+__device__ __forceinline__ void stat_commit (LabelStat* tab, uint32_t cap, uint32_t lbl, uint32_t cnt, uint32_t vmin, uint32_t vmax,
+	uint32_t xmin, uint32_t xmax, uint32_t ymin, uint32_t ymax, uint2* ztab, uint32_t zmin, uint32_t zmax)
 {
-	// volumes: `y` arrives as the row index over all slices (z*H + y); lanes of one group may sit in different slices
-	uint32_t z = 0;
+	if (lbl >= cap)		// table too small: the host sees info->max_label and retries with a larger one
+		return;
+	LabelStat* s = tab + lbl;
+	atomicAdd (&s->area, cnt);
+	atomicMin (&s->imin, vmin);
+	atomicMax (&s->imax, vmax);
+	atomicMin (&s->xmin, xmin);
+	atomicMax (&s->xmax, xmax);
+	atomicMin (&s->ymin, ymin);
+	atomicMax (&s->ymax, ymax);
 	if (ztab)
 	{
-		z = y / H;
-		y -= z * H;
-	}
-	// `part` = lanes taking part (same value in all of them); lanes with the same label reduce together, the lowest commits
-	const unsigned mask = __match_any_sync (part, lbl);
-	const int lane = threadIdx.x & 31;
-	uint32_t area = __reduce_add_sync (mask, cnt);
-	vmin = __reduce_min_sync (mask, vmin);
-	vmax = __reduce_max_sync (mask, vmax);
-	xmin = __reduce_min_sync (mask, xmin);
-	xmax = __reduce_max_sync (mask, xmax);
-	uint32_t ymin = __reduce_min_sync (mask, y);
-	uint32_t ymax = __reduce_max_sync (mask, y);
-	if (lane == __ffs (mask) - 1 && lbl < cap)
-	{
-		LabelStat* s = tab + lbl;
-		atomicAdd (&s->area, area);
-		atomicMin (&s->imin, vmin);
-		atomicMax (&s->imax, vmax);
-		atomicMin (&s->xmin, xmin);
-		atomicMax (&s->xmax, xmax);
-		atomicMin (&s->ymin, ymin);
-		atomicMax (&s->ymax, ymax);
-	}
-	if (ztab)
-	{
-		const uint32_t zmin = __reduce_min_sync (mask, z), zmax = __reduce_max_sync (mask, z);
-		if (lane == __ffs (mask) - 1 && lbl < cap)
-		{
-			atomicMin (&ztab[lbl].x, zmin);
-			atomicMax (&ztab[lbl].y, zmax);
-		}
+		atomicMin (&ztab[lbl].x, zmin);
+		atomicMax (&ztab[lbl].y, zmax);
 	}
 }
 
-template <bool U16, bool VEC>
+// Work item = (row, 128-pixel chunk): one warp, 4 consecutive pixels per lane (128-bit label load, 64/128-bit intensity
+// load).  Equal labels are contiguous along a row, so the warp does a SEGMENTED scan over lanes (shuffles, no
+// match.any) and exactly one lane per run -- the one holding the run's last pixel -- commits it: x-extent follows from
+// the run length (xmin = xmax - cnt + 1), y/z are warp-uniform.  The run that reaches a lane's last pixel is first merged
+// into a one-entry per-lane register cache, so a label that keeps ending on the same lane in successive items (a whole-
+// slide ROI: always lane 31) costs one commit per warp instead of one per row chunk.
+template <bool U16, bool VEC, bool D3>
 __global__ void __launch_bounds__(256) k_scan_stats (const void* __restrict__ inten_, const uint32_t* __restrict__ label,
-	unsigned long long npix, uint32_t W, LabelStat* tab, uint32_t cap, SlideInfo* info, uint2* ztab = nullptr, uint32_t H = 0)
+	uint32_t W, uint32_t nrows, uint32_t H, uint32_t nchunk, LabelStat* tab, uint32_t cap, SlideInfo* info, uint2* ztab)
 {
-	const unsigned long long ngroups = (npix + 3) / 4;
-	uint32_t warp_maxlbl = 0;
-	for (unsigned long long g = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; ; g += (unsigned long long)gridDim.x * blockDim.x)
+	const uint32_t lane = threadIdx.x & 31;
+	const unsigned long long nitems = (unsigned long long)nrows * nchunk;
+	const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+	uint32_t maxlbl = 0;
+	// per-lane run cache (c_lbl == 0: empty)
+	uint32_t c_lbl = 0, c_cnt = 0, c_vmin = 0, c_vmax = 0, c_xmin = 0, c_xmax = 0, c_ymin = 0, c_ymax = 0, c_zmin = 0, c_zmax = 0;
+	FastDiv fc, fh;
+	fc.init (nchunk);
+	fh.init (H);
+	const bool small = nitems < 0x100000000ull / (nchunk > H ? nchunk : H);	// FastDiv is exact for n * d < 2^32
+	for (unsigned long long item = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += nwarps)
 	{
-		// keep whole warps together: the loop bound is evaluated on the warp's first group
-		const unsigned long long gw = g - (threadIdx.x & 31);
-		if (gw >= ngroups)
-			break;
+		const uint32_t row = small ? fc.div ((uint32_t)item) : (uint32_t)(item / nchunk);
+		const uint32_t x0 = ((uint32_t)(item - (unsigned long long)row * nchunk) << 7) + lane * 4;
+		const size_t base = (size_t)row * W + x0;
 		uint32_t l[4] = { 0, 0, 0, 0 }, v[4] = { 0, 0, 0, 0 };
-		const unsigned long long p0 = g * 4;
-		if (g < ngroups)
+		if (VEC && x0 + 3 < W)
 		{
-			if (VEC && p0 + 3 < npix)
-			{
-				uint4 lv = *reinterpret_cast<const uint4*> (label + p0);
-				l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
-				if (l[0] | l[1] | l[2] | l[3])
-				{
-					if (U16)
-					{
-						ushort4 iv = *reinterpret_cast<const ushort4*> ((const uint16_t*)inten_ + p0);
-						v[0] = iv.x; v[1] = iv.y; v[2] = iv.z; v[3] = iv.w;
-					}
-					else
-					{
-						uint4 iv = *reinterpret_cast<const uint4*> ((const uint32_t*)inten_ + p0);
-						v[0] = iv.x; v[1] = iv.y; v[2] = iv.z; v[3] = iv.w;
-					}
-				}
-			}
-			else
-				for (int k = 0; k < 4; k++)
-					if (p0 + k < npix)
-					{
-						l[k] = label[p0 + k];
-						v[k] = U16 ? (uint32_t)((const uint16_t*)inten_)[p0 + k] : ((const uint32_t*)inten_)[p0 + k];
-					}
-		}
-		const uint32_t y0 = (uint32_t)(p0 / W), x0 = (uint32_t)(p0 - (unsigned long long)y0 * W);
-		const bool uni = (l[0] == l[1]) && (l[1] == l[2]) && (l[2] == l[3]) && (x0 + 3 < W);
-		uint32_t m = max (max (l[0], l[1]), max (l[2], l[3]));
-		warp_maxlbl = max (warp_maxlbl, m);
-		if (__all_sync (0xffffffffu, uni))
-		{
-			const unsigned part = __ballot_sync (0xffffffffu, l[0] != 0);
-			if (l[0] != 0)
-			{
-				uint32_t vmin = min (min (v[0], v[1]), min (v[2], v[3])), vmax = max (max (v[0], v[1]), max (v[2], v[3]));
-				stat_group_update (part, tab, cap, l[0], 4, vmin, vmax, x0, x0 + 3, y0, ztab, H);
-			}
+			const uint4 lv = __ldg (reinterpret_cast<const uint4*> (label + base));
+			l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
 		}
 		else
 		{
 #pragma unroll
 			for (int k = 0; k < 4; k++)
+				if (x0 + k < W)
+					l[k] = __ldg (label + base + k);
+		}
+		const uint32_t any = l[0] | l[1] | l[2] | l[3];
+		if (__ballot_sync (0xffffffffu, any != 0) == 0)
+			continue;		// background chunk
+		if (any)
+		{
+			if (VEC && x0 + 3 < W)
 			{
-				uint32_t x = x0 + k, y = y0;
-				if (x >= W)
+				if (U16)
 				{
-					x -= W;
-					y += 1;
-					if (x >= W)	// W < 4: fall back to exact division
-					{
-						y = (uint32_t)((p0 + k) / W);
-						x = (uint32_t)((p0 + k) - (unsigned long long)y * W);
-					}
+					const ushort4 iv = __ldg (reinterpret_cast<const ushort4*> ((const uint16_t*)inten_ + base));
+					v[0] = iv.x; v[1] = iv.y; v[2] = iv.z; v[3] = iv.w;
 				}
-				const unsigned part = __ballot_sync (0xffffffffu, l[k] != 0);
-				if (l[k] != 0)
-					stat_group_update (part, tab, cap, l[k], 1, v[k], v[k], x, x, y, ztab, H);
+				else
+				{
+					const uint4 iv = __ldg (reinterpret_cast<const uint4*> ((const uint32_t*)inten_ + base));
+					v[0] = iv.x; v[1] = iv.y; v[2] = iv.z; v[3] = iv.w;
+				}
+			}
+			else
+			{
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+					if (x0 + k < W)
+						v[k] = U16 ? (uint32_t)__ldg ((const uint16_t*)inten_ + base + k) : __ldg ((const uint32_t*)inten_ + base + k);
+			}
+		}
+		maxlbl = max (maxlbl, max (max (l[0], l[1]), max (l[2], l[3])));
+		uint32_t y = row, z = 0;
+		if (D3)
+		{
+			z = small ? fh.div (row) : row / H;
+			y = row - z * H;
+		}
+
+		// ---- run structure of this lane's 4 pixels
+		const uint32_t prev = __shfl_up_sync (0xffffffffu, l[3], 1);
+		const bool s0 = lane == 0 || l[0] != prev;			// pixel 0 starts a run
+		const bool s1 = l[1] != l[0], s2 = l[2] != l[1], s3 = l[3] != l[2];
+		const int a = s1 ? 1 : s2 ? 2 : s3 ? 3 : 4;			// left part L = pixels [0, a)
+		const int b = s3 ? 3 : s2 ? 2 : s1 ? 1 : 0;			// right-open part R = pixels [b, 4); b == 0: R == L == whole lane
+		uint32_t r_cnt = 4 - b, r_min = v[3], r_max = v[3];
+		if (b < 3) { r_min = min (r_min, v[2]); r_max = max (r_max, v[2]); }
+		if (b < 2) { r_min = min (r_min, v[1]); r_max = max (r_max, v[1]); }
+		if (b < 1) { r_min = min (r_min, v[0]); r_max = max (r_max, v[0]); }
+		// ---- inclusive segmented scan of R over the lanes; a segment starts where R starts inside the lane
+		const bool head = b > 0 || s0;
+		const unsigned heads = __ballot_sync (0xffffffffu, head);
+		const int headlane = 31 - __clz (heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1)
+		{
+			const uint32_t tc = __shfl_up_sync (0xffffffffu, r_cnt, o);
+			const uint32_t tn = __shfl_up_sync (0xffffffffu, r_min, o);
+			const uint32_t tx = __shfl_up_sync (0xffffffffu, r_max, o);
+			if ((int)lane - o >= headlane)
+			{
+				r_cnt += tc;
+				r_min = min (r_min, tn);
+				r_max = max (r_max, tx);
+			}
+		}
+		// what flows in from the lanes to the left (meaningful when !s0)
+		const uint32_t k_cnt = __shfl_up_sync (0xffffffffu, r_cnt, 1);
+		const uint32_t k_min = __shfl_up_sync (0xffffffffu, r_min, 1);
+		const uint32_t k_max = __shfl_up_sync (0xffffffffu, r_max, 1);
+		const bool next_s0 = __shfl_down_sync (0xffffffffu, s0 ? 1 : 0, 1) != 0 || lane == 31;
+
+		// ---- L closes inside this lane (b > 0): commit it, joined with the inflow
+		if (b > 0 && l[0] != 0)
+		{
+			uint32_t cnt = a, mn = v[0], mx = v[0];
+			if (a > 1) { mn = min (mn, v[1]); mx = max (mx, v[1]); }
+			if (a > 2) { mn = min (mn, v[2]); mx = max (mx, v[2]); }
+			if (!s0)
+			{
+				cnt += k_cnt;
+				mn = min (mn, k_min);
+				mx = max (mx, k_max);
+			}
+			const uint32_t xe = x0 + a - 1;
+			stat_commit (tab, cap, l[0], cnt, mn, mx, xe - cnt + 1, xe, y, y, D3 ? ztab : nullptr, z, z);
+		}
+		// ---- runs strictly inside the lane (3 or 4 different runs in 4 pixels)
+		if (a < b)
+		{
+			const bool p1 = a == 1, p2 = b == 3;		// pixel 1 / pixel 2 belongs to neither L nor R
+			if (p1 && p2 && !s2)
+			{
+				if (l[1] != 0)
+					stat_commit (tab, cap, l[1], 2, min (v[1], v[2]), max (v[1], v[2]), x0 + 1, x0 + 2, y, y, D3 ? ztab : nullptr, z, z);
+			}
+			else
+			{
+				if (p1 && l[1] != 0)
+					stat_commit (tab, cap, l[1], 1, v[1], v[1], x0 + 1, x0 + 1, y, y, D3 ? ztab : nullptr, z, z);
+				if (p2 && l[2] != 0)
+					stat_commit (tab, cap, l[2], 1, v[2], v[2], x0 + 2, x0 + 2, y, y, D3 ? ztab : nullptr, z, z);
+			}
+		}
+		// ---- R ends with this lane: into the lane's cache
+		if (next_s0 && l[3] != 0)
+		{
+			const uint32_t xe = x0 + 3, xs = xe - r_cnt + 1;
+			if (c_lbl == l[3])
+			{
+				c_cnt += r_cnt;
+				c_vmin = min (c_vmin, r_min);
+				c_vmax = max (c_vmax, r_max);
+				c_xmin = min (c_xmin, xs);
+				c_xmax = max (c_xmax, xe);
+				c_ymin = min (c_ymin, y);
+				c_ymax = max (c_ymax, y);
+				c_zmin = min (c_zmin, z);
+				c_zmax = max (c_zmax, z);
+			}
+			else
+			{
+				if (c_lbl)
+					stat_commit (tab, cap, c_lbl, c_cnt, c_vmin, c_vmax, c_xmin, c_xmax, c_ymin, c_ymax, D3 ? ztab : nullptr, c_zmin, c_zmax);
+				c_lbl = l[3]; c_cnt = r_cnt; c_vmin = r_min; c_vmax = r_max; c_xmin = xs; c_xmax = xe;
+				c_ymin = c_ymax = y;
+				c_zmin = c_zmax = z;
 			}
 		}
 	}
-	warp_maxlbl = __reduce_max_sync (0xffffffffu, warp_maxlbl);
-	if ((threadIdx.x & 31) == 0 && warp_maxlbl)
-		atomicMax (&info->max_label, warp_maxlbl);
+	if (c_lbl)
+		stat_commit (tab, cap, c_lbl, c_cnt, c_vmin, c_vmax, c_xmin, c_xmax, c_ymin, c_ymax, D3 ? ztab : nullptr, c_zmin, c_zmax);
+	maxlbl = __reduce_max_sync (0xffffffffu, maxlbl);
+	if (lane == 0 && maxlbl)
+		atomicMax (&info->max_label, maxlbl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -313,6 +380,25 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 {
 	__shared__ uint32_t sa[33];
 	__shared__ unsigned long long sb[33];
+	// per-block class tallies: slots are handed out inside the block first, ONE global atomic per (block, class) after
+	__shared__ uint32_t s_cnt[NCLASS + 1], s_acnt[NACLASS + 1], s_base[NCLASS + 1], s_abase[NACLASS + 1];
+	__shared__ uint32_t s_maxcells[NCLASS + 1], s_maxwh[NCLASS + 1], s_maxarea[NACLASS + 1], s_maxinten, s_invmin;
+	if (threadIdx.x <= NCLASS)
+	{
+		s_cnt[threadIdx.x] = 0;
+		s_maxcells[threadIdx.x] = 0;
+		s_maxwh[threadIdx.x] = 0;
+	}
+	if (threadIdx.x <= NACLASS)
+	{
+		s_acnt[threadIdx.x] = 0;
+		s_maxarea[threadIdx.x] = 0;
+	}
+	if (threadIdx.x == 0)
+	{
+		s_maxinten = 0;
+		s_invmin = 0;
+	}
 	const uint32_t i = blockIdx.x * CB + threadIdx.x;
 	uint32_t a = 0;
 	unsigned long long b = 0;
@@ -327,11 +413,15 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 	uint32_t ta;
 	unsigned long long tb;
 	const uint32_t present = a;
-	block_exscan_2 (a, b, sa, sb, ta, tb);
+	block_exscan_2 (a, b, sa, sb, ta, tb);		// (contains the barriers that publish the zeroed tallies)
+	if (ta == 0)
+		return;
+	RoiRec r;
+	uint32_t idx = 0, tslot = 0, aslot = 0;
+	int tc = 0, ac = 0;
 	if (present)
 	{
-		const uint32_t idx = blk_cnt[blockIdx.x] + a;
-		RoiRec r;
+		idx = blk_cnt[blockIdx.x] + a;
 		r.label = i;
 		r.area = s.area;
 		r.imin = s.imin;
@@ -352,14 +442,38 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 		rois[idx] = r;
 		const unsigned long long ncell64 = (unsigned long long)r.w * (unsigned long long)r.h * (unsigned long long)r.d;
 		const uint32_t ncell = ncell64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ncell64;
-		const int tc = tile_class (ncell), ac = area_class (r.area);
-		class_slot[idx * 2] = ((uint32_t)tc << 28) | atomicAdd (&info->class_count[tc], 1u);
-		class_slot[idx * 2 + 1] = ((uint32_t)ac << 28) | atomicAdd (&info->aclass_count[ac], 1u);
-		atomicMax (&info->class_maxcells[tc], ncell);
-		atomicMax (&info->class_maxwh[tc], (uint32_t)max (max (r.w, r.h), r.d));
-		atomicMax (&info->aclass_maxarea[ac], r.area);
-		atomicMax (&info->max_inten, r.imax);
-		atomicMax (&info->inv_min_inten, ~r.imin);
+		tc = tile_class (ncell);
+		ac = area_class (r.area);
+		tslot = atomicAdd (&s_cnt[tc], 1u);
+		aslot = atomicAdd (&s_acnt[ac], 1u);
+		atomicMax (&s_maxcells[tc], ncell);
+		atomicMax (&s_maxwh[tc], (uint32_t)max (max (r.w, r.h), r.d));
+		atomicMax (&s_maxarea[ac], r.area);
+		atomicMax (&s_maxinten, r.imax);
+		atomicMax (&s_invmin, ~r.imin);
+	}
+	__syncthreads();
+	if (threadIdx.x <= NCLASS && s_cnt[threadIdx.x])
+	{
+		s_base[threadIdx.x] = atomicAdd (&info->class_count[threadIdx.x], s_cnt[threadIdx.x]);
+		atomicMax (&info->class_maxcells[threadIdx.x], s_maxcells[threadIdx.x]);
+		atomicMax (&info->class_maxwh[threadIdx.x], s_maxwh[threadIdx.x]);
+	}
+	if (threadIdx.x >= 32 && threadIdx.x - 32 <= NACLASS && s_acnt[threadIdx.x - 32])
+	{
+		s_abase[threadIdx.x - 32] = atomicAdd (&info->aclass_count[threadIdx.x - 32], s_acnt[threadIdx.x - 32]);
+		atomicMax (&info->aclass_maxarea[threadIdx.x - 32], s_maxarea[threadIdx.x - 32]);
+	}
+	if (threadIdx.x == 64)
+	{
+		atomicMax (&info->max_inten, s_maxinten);
+		atomicMax (&info->inv_min_inten, s_invmin);
+	}
+	__syncthreads();
+	if (present)
+	{
+		class_slot[idx * 2] = ((uint32_t)tc << 28) | (s_base[tc] + tslot);
+		class_slot[idx * 2 + 1] = ((uint32_t)ac << 28) | (s_abase[ac] + aslot);
 	}
 }
 

@@ -86,6 +86,53 @@ def test_phase1_records_and_cloud_exact(eng64):
     assert eng64.counts()["fg_pixels"] == int((L > 0).sum())
 
 
+def _phase1_expected(I, L):
+    """per-label (label, area, min, max, xmin, ymin, w, h) by numpy (reference: init/update_label_record_3)"""
+    lab = L.ravel().astype(np.int64)
+    fg = lab > 0
+    ys, xs = np.divmod(np.nonzero(fg)[0], L.shape[1])
+    lab = lab[fg]
+    val = I.ravel()[fg].astype(np.int64)
+    order = np.argsort(lab, kind="stable")
+    lab, ys, xs, val = lab[order], ys[order], xs[order], val[order]
+    u, first = np.unique(lab, return_index=True)
+    red = lambda f, a: f.reduceat(a, first)
+    area = np.diff(np.append(first, len(lab)))
+    x0, x1, y0, y1 = red(np.minimum, xs), red(np.maximum, xs), red(np.minimum, ys), red(np.maximum, ys)
+    return np.stack([u, area, red(np.minimum, val), red(np.maximum, val), x0, y0, x1 - x0 + 1, y1 - y0 + 1], 1)
+
+
+@pytest.mark.parametrize("H,W,kind", [(37, 256, "noise"), (64, 131, "noise"), (50, 1000, "runs"), (33, 515, "runs"), (200, 384, "one"),
+                                      (5, 3, "noise"), (300, 1028, "blocks")])
+def test_scan_run_segmentation_stress(H, W, kind):
+    """label layouts that exercise every branch of the row-run scan: 1-pixel runs (3-4 runs inside one lane), runs crossing
+    lanes and 128-pixel chunks, a whole-image label (per-lane cache), widths with and without the 128-bit load path"""
+    rng = np.random.default_rng(H * 1000 + W)
+    if kind == "noise":
+        L = rng.integers(0, 6, (H, W)).astype(np.uint32)
+    elif kind == "runs":
+        L = np.zeros((H, W), np.uint32)
+        for y in range(H):
+            x = 0
+            while x < W:
+                n = int(rng.integers(1, 200))
+                L[y, x:x + n] = rng.integers(0, 40)
+                x += n
+    elif kind == "one":
+        L = np.full((H, W), 7, np.uint32)
+    else:
+        L = (1 + (np.arange(H)[:, None] // 50) * 40 + np.arange(W)[None, :] // 30).astype(np.uint32)
+        L[rng.random((H, W)) < 0.05] = 0
+    I = rng.integers(0, 60000, (H, W)).astype(np.uint16)
+    e = _engine(features=["MEAN"])
+    try:
+        for inten in (I, I.astype(np.uint32)):
+            e.featurize(inten, L)
+            assert np.array_equal(e.debug_rois(), _phase1_expected(inten, L))
+    finally:
+        e.close()
+
+
 # ------------------------------------------------------------------------------------------------ vs the compiled reference
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so did not travel")
 @pytest.mark.parametrize("seed,g,ibsi,levels", [(1, 64, False, None), (2, 16, False, None), (3, 256, False, None), (4, 64, True, 120),

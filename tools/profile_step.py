@@ -1,5 +1,5 @@
 """One resident pass of the hot path over a configs[1]-style slide -- the command wrapped by ncu (see profiles/README.md)."""
-import os, sys
+import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
@@ -14,5 +14,8 @@ d_lab = torch.from_numpy(label.view(np.int32)).cuda()
 eng = Engine(feats)
 H, W = inten.shape
 for _ in range(steps):
-    tab, _ = eng.featurize_ptr(d_int.data_ptr(), True, d_lab.data_ptr(), 1, H, W, on_device=True)
-print(tab.shape, {k: round(v, 3) for k, v in eng.timings().items()})
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tab, _ = eng.featurize_ptr(d_int.data_ptr(), True, d_lab.data_ptr(), 1, H, W, on_device=True, copy=False)
+    wall = (time.perf_counter() - t0) * 1e3
+    print(tab.shape, "wall_ms %.2f" % wall, {k: round(v, 3) for k, v in eng.timings().items()})
