@@ -107,10 +107,12 @@ int nyxb200_featurize_3d_device (nyxb200_ctx* ctx, const void* inten, int inten_
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t);
 
 /* ---- measurement hooks ---- */
-#define NYXB200_NSTAGES 16
+#define NYXB200_NSTAGES 18
 /* per-stage device time (ms, CUDA events on the launching stream) of the last featurize call:
  * 0 h2d, 1 init, 2 scan, 3 compact, 4 pack, 5 intensity, 6 glcm, 7 glrlm, 8 gldzm, 9 glszm, 10 gldm, 11 ngldm,
- * 12 ngtdm, 13 select, 14 d2h, 15 total */
+ * 12 ngtdm, 13 select, 14 d2h, 15 total (first to last event of the call), 16 families (the fork/join window: the
+ * family stages 4..12 run on their own streams and overlap unless nyxb200_set_param("concurrent_families", 0)),
+ * 17 giant (ROIs larger than the shared-memory size classes, processed one at a time by whole-GPU kernels) */
 int nyxb200_last_timings (const nyxb200_ctx* ctx, float* ms, int n);
 /* counts of the last featurize call: 0 kernel launches, 1 ROIs, 2 foreground pixels, 3 all pixels */
 int nyxb200_last_counts (const nyxb200_ctx* ctx, int64_t* v, int n);

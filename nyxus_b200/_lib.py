@@ -8,7 +8,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libnyxus_b200.so")
 
-NSTAGES = 16
+NSTAGES = 18
 
 
 class Settings(C.Structure):

@@ -11,6 +11,7 @@
 #include <vector>
 #include "../../include/nyxus_b200.h"
 #include "kernels.cuh"
+#include "giant.cuh"
 
 using namespace nyx;
 
@@ -53,9 +54,9 @@ const char* g_groups3d_unbuilt[] = { "*3D_ALL*", "*3D_ALL_TEXTURE*", "*3D_ALL_MO
 	"*3D_NGLDM*", "*3D_ALL_NEIGHBOR*", "*3D_MOMENTS*" };
 
 const char* g_stage_names[NYXB200_NSTAGES] = { "h2d", "init", "scan", "compact", "pack", "intensity", "glcm", "glrlm", "gldzm",
-	"glszm", "gldm", "ngldm", "ngtdm", "select", "d2h", "total" };
+	"glszm", "gldm", "ngldm", "ngtdm", "select", "d2h", "total", "families", "giant" };
 enum Stage { ST_H2D = 0, ST_INIT, ST_SCAN, ST_COMPACT, ST_PACK, ST_INT, ST_GLCM, ST_GLRLM, ST_GLDZM, ST_GLSZM, ST_GLDM, ST_NGLDM,
-	ST_NGTDM, ST_SELECT, ST_D2H, ST_TOTAL };
+	ST_NGTDM, ST_SELECT, ST_D2H, ST_TOTAL, ST_FAMILIES, ST_GIANT };
 
 std::string g_create_error;
 
@@ -96,8 +97,19 @@ struct nyxb200_ctx
 	std::string err;
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[NYXB200_NSTAGES + 2];
+	cudaEvent_t ev[NYXB200_NSTAGES + 2];		// stage begin
+	cudaEvent_t ev_end[NYXB200_NSTAGES + 2];	// stage end
 	bool ev_used[NYXB200_NSTAGES + 2];
+	bool ev_end_used[NYXB200_NSTAGES + 2];
+	// the eight families are independent once the ROI records exist: each runs on its own stream (fork/join by events)
+	// so their low-occupancy, issue-bound kernels share the SMs; `concurrent = 0` serialises them (per-stage timing)
+	static constexpr int NFSTREAM = 8;
+	cudaStream_t fstream[NFSTREAM];
+	cudaEvent_t ev_fork, ev_join[NFSTREAM];
+	int concurrent = 1;
+	cudaStream_t ls = nullptr;	// stream the family launchers submit to (the main stream or a family stream)
+	int lsi = 0;			// scratch slot that goes with it
+	int open_stage = -1;		// main-stream stage whose end event is still to be recorded
 
 	// selection
 	std::vector<FeatureDef> feats;	// the context's feature table (2D or 3D codes)
@@ -122,10 +134,16 @@ struct nyxb200_ctx
 	DevBuf<uint32_t> d_classslot, d_tlist, d_alist, d_bases;
 	DevBuf<uint32_t> d_cloud;
 	DevBuf<double> d_full, d_sel_out;
-	DevBuf<uint32_t> d_scratch;
+	DevBuf<uint32_t> d_scratch[NFSTREAM];	// per-family global matrix slots (families run concurrently)
 	DevBuf<unsigned long long> d_rowoff;
 	DevBuf<uint32_t> d_dbg;
 	DevBuf<double> d_dbgf;
+	// large-ROI (giant) path: global-memory tile + work arrays of ONE ROI at a time (giant.cuh)
+	DevBuf<uint32_t> g_cell, g_cell2, g_auxA, g_auxB, g_auxC, g_mat, g_hcnts, g_flags, g_idx;
+	DevBuf<unsigned long long> g_acc, g_hkeys;
+	DevBuf<double> g_part;
+	DevBuf<RoiRec> g_recs;
+	int64_t giant_rois = 0;		// ROIs of the last call that went through the giant path
 
 	// state of the last processed image (for the debug hooks)
 	ImageView last_im {};
@@ -273,6 +291,14 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out)
 	}
 	for (auto& ev : ctx->ev)
 		cudaEventCreate (&ev);
+	for (auto& ev : ctx->ev_end)
+		cudaEventCreate (&ev);
+	for (auto& fs : ctx->fstream)
+		cudaStreamCreateWithFlags (&fs, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags (&ctx->ev_fork, cudaEventDisableTiming);
+	for (auto& ev : ctx->ev_join)
+		cudaEventCreateWithFlags (&ev, cudaEventDisableTiming);
+	ctx->ls = ctx->stream;
 	rebuild_selection (ctx);
 	*out = ctx;
 	return NYXB200_OK;
@@ -283,15 +309,26 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	if (!ctx)
 		return;
 	cudaSetDevice (ctx->st.device);
-	cudaStreamSynchronize (ctx->stream);
+	cudaDeviceSynchronize();
 	ctx->d_ztab.release(); ctx->d_sel.release(); ctx->d_inten.release(); ctx->d_label.release(); ctx->d_stats.release(); ctx->d_info.release();
 	ctx->d_blkcnt.release(); ctx->d_blkarea.release(); ctx->d_rois.release(); ctx->d_classslot.release(); ctx->d_tlist.release();
 	ctx->d_alist.release(); ctx->d_bases.release(); ctx->d_cloud.release(); ctx->d_full.release(); ctx->d_sel_out.release();
-	ctx->d_scratch.release(); ctx->d_rowoff.release(); ctx->d_dbg.release(); ctx->d_dbgf.release();
+	for (auto& b : ctx->d_scratch) b.release();
+	ctx->g_cell.release(); ctx->g_cell2.release(); ctx->g_auxA.release(); ctx->g_auxB.release(); ctx->g_auxC.release(); ctx->g_mat.release();
+	ctx->g_hcnts.release(); ctx->g_flags.release(); ctx->g_idx.release(); ctx->g_acc.release(); ctx->g_hkeys.release(); ctx->g_part.release();
+	ctx->g_recs.release();
+	ctx->d_rowoff.release(); ctx->d_dbg.release(); ctx->d_dbgf.release();
 	if (ctx->h_out)
 		cudaFreeHost (ctx->h_out);
 	for (auto& ev : ctx->ev)
 		cudaEventDestroy (ev);
+	for (auto& ev : ctx->ev_end)
+		cudaEventDestroy (ev);
+	for (auto& ev : ctx->ev_join)
+		cudaEventDestroy (ev);
+	cudaEventDestroy (ctx->ev_fork);
+	for (auto& fs : ctx->fstream)
+		cudaStreamDestroy (fs);
 	cudaStreamDestroy (ctx->stream);
 	delete ctx;
 }
@@ -374,6 +411,8 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 		ctx->st.glcm_symmetric = iv != 0;
 	else if (!strcmp (key, "soft_nan"))
 		ctx->st.soft_nan = value;
+	else if (!strcmp (key, "concurrent_families"))	// measurement knob: 0 = one family after the other (clean per-stage times)
+		ctx->concurrent = iv != 0;
 	else if (!strcmp (key, "3glcm/greydepth"))		// env_metaparams.cpp:109-120
 	{
 		if (iv <= 0 || iv > 65535)
@@ -455,7 +494,7 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 			return NYXB200_ECUDA;
 		const int per_sm = (int)std::max<size_t> (1, std::min<size_t> (16, (size_t)(227 * 1024) / (bytes + 1024)));
 		const int grid = (int)std::min<uint32_t> ((n + ROI_WARPS - 1) / ROI_WARPS, (uint32_t)(ctx->sm_count * per_sm));
-		kw<<<grid, ROI_THREADS, bytes, ctx->stream>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out, NCOL_ALL, famw);
+		kw<<<grid, ROI_THREADS, bytes, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out, NCOL_ALL, famw);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		return 0;
@@ -468,14 +507,14 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 		// matrices go to a per-CTA slot in global memory (L2 resident), the tile stays in shared memory
 		smem_words = RED_WORDS + tilew;
 		grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 2);
-		CU (ctx->d_scratch.reserve ((size_t)grid * famw));
-		gs = ctx->d_scratch.p;
-		CU (cudaMemsetAsync (gs, 0, (size_t)grid * famw * 4, ctx->stream));	// bodies expect (and leave) an all-zero region
+		CU (ctx->d_scratch[ctx->lsi].reserve ((size_t)grid * famw));
+		gs = ctx->d_scratch[ctx->lsi].p;
+		CU (cudaMemsetAsync (gs, 0, (size_t)grid * famw * 4, ctx->ls));	// bodies expect (and leave) an all-zero region
 	}
 	auto kern = k_roi_family<FAM, P16>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
-	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->stream>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out,
+	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out,
 		NCOL_ALL, gs, famw, dbg);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
@@ -515,7 +554,7 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 			return NYXB200_ECUDA;
 		const int per_sm = (int)std::max<size_t> (1, std::min<size_t> (16, (size_t)(227 * 1024) / (bytes + 1024)));
 		const int grid = (int)std::min<uint32_t> ((n + ROI_WARPS - 1) / ROI_WARPS, (uint32_t)(ctx->sm_count * per_sm));
-		k_roi_intensity_w<<<grid, ROI_THREADS, bytes, ctx->stream>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, out, ostride, memw);
+		k_roi_intensity_w<<<grid, ROI_THREADS, bytes, ctx->ls>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, out, ostride, memw);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		return 0;
@@ -527,12 +566,12 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 	{
 		smem_words = RED_WORDS;
 		grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 2);
-		CU (ctx->d_scratch.reserve ((size_t)grid * memw));
-		gs = ctx->d_scratch.p;
+		CU (ctx->d_scratch[ctx->lsi].reserve ((size_t)grid * memw));
+		gs = ctx->d_scratch[ctx->lsi].p;
 	}
 	if (set_smem (ctx, k_roi_intensity, smem_words * 4))
 		return NYXB200_ECUDA;
-	k_roi_intensity<<<grid, ROI_THREADS, smem_words * 4, ctx->stream>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
+	k_roi_intensity<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
 		ostride, gs, memw);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
@@ -559,14 +598,14 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 	{
 		smem_words = RED_WORDS + tilew;
 		grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 2);
-		CU (ctx->d_scratch.reserve ((size_t)grid * famw));
-		gs = ctx->d_scratch.p;
-		CU (cudaMemsetAsync (gs, 0, (size_t)grid * famw * 4, ctx->stream));
+		CU (ctx->d_scratch[ctx->lsi].reserve ((size_t)grid * famw));
+		gs = ctx->d_scratch[ctx->lsi].p;
+		CU (cudaMemsetAsync (gs, 0, (size_t)grid * famw * 4, ctx->ls));
 	}
 	auto kern = k_roi_family3<FAM3, P16>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
-	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->stream>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,
+	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,
 		NCOL3_ALL, gs, famw);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
@@ -587,10 +626,448 @@ Params make_params (const nyxb200_ctx* ctx)
 	return p;
 }
 
-void stage_begin (nyxb200_ctx* ctx, int st)
+
+// ====================================================================================================
+// large-ROI (giant) path: host loop over the oversize ROIs of the slide, whole-GPU kernels per ROI (giant.cuh)
+// ====================================================================================================
+constexpr unsigned long long GIANT_MAX_CELLS = 0xFFFFFFF0ull;	// 32-bit cell indices
+constexpr size_t GIANT_MAX_MATRIX_WORDS = (size_t)1 << 28;	// 1 GiB per dense family matrix
+
+int fetch_class_rois (nyxb200_ctx* ctx, const uint32_t* dlist, uint32_t n, std::vector<RoiRec>& recs, std::vector<uint32_t>& idx)
 {
-	cudaEventRecord (ctx->ev[st], ctx->stream);
+	recs.resize (n);
+	idx.resize (n);
+	if (!n)
+		return 0;
+	CU (ctx->g_recs.reserve (n));
+	CU (ctx->g_idx.reserve (n));
+	k_gather_rois<<<(n + 255) / 256, 256, 0, ctx->stream>>> (ctx->d_rois.p, dlist, n, ctx->g_recs.p, ctx->g_idx.p);
+	CU (cudaGetLastError());
+	ctx->counts[0]++;
+	CU (cudaMemcpyAsync (recs.data(), ctx->g_recs.p, sizeof (RoiRec) * n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU (cudaMemcpyAsync (idx.data(), ctx->g_idx.p, sizeof (uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream));
+	CU (cudaStreamSynchronize (ctx->stream));
+	return 0;
+}
+
+// optional dumps for the matrix-exact tests (nyxb200_debug_matrix on a giant ROI)
+struct GiantDebug
+{
+	int family = -1;
+	std::vector<uint32_t>* dense = nullptr;		// GLCM joint [4][Ng][Ng], GLRLM P [4][Lm][Nr], GLDM/NGLDM P [L1][10], NGTDM N [L1]
+	std::vector<uint32_t>* zone_keys = nullptr;	// GLSZM / GLDZM: (level, minor) per zone
+	std::vector<double>* ngtdm_s = nullptr;
+	int dim0 = 0, dim1 = 0;
+};
+
+int giant_texture_roi (nyxb200_ctx* ctx, const ImageView& im, const RoiRec& r, const Params& prm, int fam_mask, double* orow, GiantDebug* dbg)
+{
+	cudaStream_t s = ctx->stream;
+	const unsigned long long ncell = (unsigned long long)r.w * (unsigned long long)r.h;
+	if (ncell > GIANT_MAX_CELLS)
+		return fail (ctx, NYXB200_EUNSUPPORTED, "ROI %u: bounding box of %llu pixels exceeds the 2^32 cell limit of the large-ROI path", r.label, ncell);
+	const int GB = ctx->sm_count * 4;
+	const bool ibsi = prm.ibsi != 0;
+	const int Lm = ibsi ? (int)std::max<uint32_t> (r.imax, 1u) : prm.greydepth;	// largest level of this ROI's binned tile
+	const int L1 = Lm + 1;
+	const bool blank = r.imin == r.imax;
+	auto fill = [&](int col, int n, double v) { k_big_fill<<<1, 128, 0, s>>> (orow + col, n, v); ctx->counts[0]++; };
+	auto need_smem = [&](auto kern, size_t bytes) -> int { return set_smem (ctx, kern, bytes); };
+
+	// ---- tile(s)
+	const bool want_ngldm = (fam_mask & (1 << FAM_NGLDM)) && !blank;
+	const bool want_tile = (fam_mask & ~((1 << FAM_NGLDM) | (1 << FAM_INT))) != 0;
+	if (want_tile)
+		CU (ctx->g_cell.reserve (ncell));
+	if (want_ngldm)
+		CU (ctx->g_cell2.reserve (ncell));
+	k_big_tile<<<GB, BG_T, 0, s>>> (im, r, prm, want_tile ? ctx->g_cell.p : nullptr, want_ngldm ? ctx->g_cell2.p : nullptr);
+	CU (cudaGetLastError());
+	ctx->counts[0]++;
+	const uint32_t* cell = ctx->g_cell.p;
+	CU (ctx->g_acc.reserve (BG_NACC * 2));
+	CU (ctx->g_part.reserve ((size_t)GB * BG_NPART));
+
+	// ---- GLCM
+	if (fam_mask & (1 << FAM_GLCM))
+	{
+		Binner Bm;
+		Bm.init (prm.greydepth, r.imin, r.imax);
+		if (Bm.bin (r.imin) == Bm.bin (r.imax))		// glcm.cpp:27-95
+			fill (COL_GLCM, NCOL_GLCM, prm.softnan);
+		else
+		{
+			const int Ng = Lm;
+			if (Ng > 4096)
+				return fail (ctx, NYXB200_EUNSUPPORTED, "ROI %u: the large-ROI GLCM path handles at most 4096 grey levels (have %d); use coarse_gray_depth binning", r.label, Ng);
+			const size_t nn = (size_t)Ng * Ng;
+			CU (ctx->g_mat.reserve (4 * nn));
+			CU (cudaMemsetAsync (ctx->g_mat.p, 0, 4 * nn * 4, s));
+			int bw = (int)std::min<size_t> ((size_t)2 * Ng - 1, BG_SMEM_WORDS / (size_t)Ng);
+			if (!(bw & 1))
+				bw--;
+			if (bw < 1)
+				bw = 1;
+			if (need_smem (k_big_glcm_build, (size_t)Ng * bw * 4))
+				return NYXB200_ECUDA;
+			k_big_glcm_build<<<GB, BG_T, (size_t)Ng * bw * 4, s>>> (cell, r.w, r.h, Ng, prm.glcm_offset, (prm.glcm_symmetric || ibsi) ? 1 : 0, bw, ctx->g_mat.p);
+			CU (cudaGetLastError());
+			const size_t rw = big_glcm_reduce_words (Ng) * 4;
+			if (need_smem (k_big_glcm_reduce, rw))
+				return NYXB200_ECUDA;
+			k_big_glcm_reduce<<<4, BG_T, rw, s>>> (ctx->g_mat.p, Ng, r, prm, orow + COL_GLCM);
+			k_big_ave<<<1, 32, 0, s>>> (orow + COL_GLCM, 1);
+			CU (cudaGetLastError());
+			ctx->counts[0] += 3;
+			if (dbg && dbg->family == FAM_GLCM)
+			{
+				dbg->dense->resize (4 * nn);
+				dbg->dim0 = Ng;
+				CU (cudaMemcpyAsync (dbg->dense->data(), ctx->g_mat.p, 4 * nn * 4, cudaMemcpyDeviceToHost, s));
+				CU (cudaStreamSynchronize (s));
+			}
+		}
+	}
+
+	// ---- GLRLM
+	if (fam_mask & (1 << FAM_GLRLM))
+	{
+		if (blank)	// glrlm.cpp:29-52
+			fill (COL_GLRLM, NCOL_GLRLM, prm.softnan);
+		else
+		{
+			const int Nr = std::max (r.w, r.h);
+			const size_t pw = (size_t)4 * Lm * Nr;
+			if (pw > GIANT_MAX_MATRIX_WORDS || (size_t)Lm + Nr > 56000)
+				return fail (ctx, NYXB200_EUNSUPPORTED, "ROI %u: run-length matrix of %d levels x %d run lengths exceeds the large-ROI GLRLM limits", r.label, Lm, Nr);
+			CU (ctx->g_mat.reserve (pw));
+			CU (cudaMemsetAsync (ctx->g_mat.p, 0, pw * 4, s));
+			CU (cudaMemsetAsync (ctx->g_acc.p, 0, BG_NACC * 2 * 8, s));
+			const int SL = (size_t)4 * Lm * 8 <= BG_SMEM_WORDS ? 8 : 0;
+			if (need_smem (k_big_glrlm_build, (size_t)4 * Lm * SL * 4))
+				return NYXB200_ECUDA;
+			k_big_glrlm_build<<<GB, BG_T, (size_t)4 * Lm * SL * 4, s>>> (cell, r.w, r.h, Lm, Nr, SL, ctx->g_mat.p, ctx->g_acc.p);
+			CU (cudaGetLastError());
+			if (need_smem (k_big_glrlm_reduce, ((size_t)Lm + Nr) * 4))
+				return NYXB200_ECUDA;
+			k_big_glrlm_reduce<<<4, BG_T, ((size_t)Lm + Nr) * 4, s>>> (ctx->g_mat.p, Lm, Nr, ctx->g_acc.p, orow + COL_GLRLM);
+			k_big_ave<<<1, 32, 0, s>>> (orow + COL_GLRLM, 0);
+			CU (cudaGetLastError());
+			ctx->counts[0] += 3;
+			if (dbg && dbg->family == FAM_GLRLM)
+			{
+				dbg->dense->resize (pw);
+				dbg->dim0 = Lm;
+				dbg->dim1 = Nr;
+				CU (cudaMemcpyAsync (dbg->dense->data(), ctx->g_mat.p, pw * 4, cudaMemcpyDeviceToHost, s));
+				CU (cudaStreamSynchronize (s));
+			}
+		}
+	}
+
+	// ---- GLSZM
+	if (fam_mask & (1 << FAM_GLSZM))
+	{
+		if (blank)	// glszm.cpp:61-65
+			fill (COL_GLSZM, NCOL_GLSZM, prm.softnan);
+		else
+		{
+			CU (ctx->g_auxA.reserve (ncell));
+			CU (ctx->g_auxB.reserve (ncell));
+			uint32_t* lab = ctx->g_auxA.p;
+			uint32_t* zs = ctx->g_auxB.p;
+			k_big_iota<<<GB, BG_T, 0, s>>> (lab, ncell);
+			CU (cudaMemsetAsync (zs, 0, ncell * 4, s));
+			const int R = std::max (4, (r.h + GB - 1) / GB);
+			const int nbands = (r.h + R - 1) / R;
+			CU (ctx->g_flags.reserve ((size_t)2 * (nbands + 1) + 1));
+			uint32_t* dirty[2] = { ctx->g_flags.p, ctx->g_flags.p + nbands + 1 };
+			uint32_t* anyf = ctx->g_flags.p + 2 * (nbands + 1);
+			CU (cudaMemsetAsync (dirty[0], 0xFF, (size_t)(nbands + 1) * 4, s));
+			ctx->counts[0]++;
+			for (int sweep = 0; ; sweep++)
+			{
+				uint32_t* din = dirty[sweep & 1];
+				uint32_t* dout = dirty[(sweep + 1) & 1];
+				CU (cudaMemsetAsync (dout, 0, (size_t)(nbands + 1) * 4, s));
+				CU (cudaMemsetAsync (anyf, 0, 4, s));
+				k_big_glszm_pass<<<nbands, BG_T, 0, s>>> (cell, r.w, r.h, R, lab, din, dout, anyf);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+				uint32_t any = 0;
+				CU (cudaMemcpyAsync (&any, anyf, 4, cudaMemcpyDeviceToHost, s));
+				CU (cudaStreamSynchronize (s));
+				if (!any)
+					break;
+				if (sweep > r.h + 4)
+					return fail (ctx, NYXB200_ECUDA, "GLSZM zone labelling did not converge");
+			}
+			CU (cudaMemsetAsync (ctx->g_acc.p, 0, BG_NACC * 2 * 8, s));
+			k_big_zone_sizes<<<GB, BG_T, 0, s>>> (cell, lab, zs, ncell, 0, 0, ctx->g_acc.p + BG_NACC);
+			const uint32_t slots = glszm_hash_slots (Lm, (uint32_t)std::min<unsigned long long> (ncell, 0xFFFFFFFFull));
+			CU (ctx->g_hkeys.reserve (slots));
+			CU (ctx->g_hcnts.reserve (slots));
+			CU (cudaMemsetAsync (ctx->g_hkeys.p, 0, (size_t)slots * 8, s));
+			CU (cudaMemsetAsync (ctx->g_hcnts.p, 0, (size_t)slots * 4, s));
+			const size_t dw = big_glszm_dense_words (L1);
+			CU (ctx->g_mat.reserve (dw));
+			CU (cudaMemsetAsync (ctx->g_mat.p, 0, dw * 4, s));
+			const int use_sm = dw <= BG_SMEM_WORDS;
+			if (need_smem (k_big_glszm_zones, use_sm ? dw * 4 : 0))
+				return NYXB200_ECUDA;
+			uint32_t* dk = nullptr;
+			if (dbg && dbg->family == FAM_GLSZM)
+			{
+				CU (ctx->g_auxC.reserve (2 * ncell + 4));
+				dk = ctx->g_auxC.p;
+				CU (cudaMemsetAsync (dk + 2 * ncell, 0, 4, s));
+			}
+			k_big_glszm_zones<<<GB, BG_T, use_sm ? dw * 4 : 0, s>>> (cell, lab, zs, ncell, L1, use_sm, ctx->g_mat.p, ctx->g_hkeys.p,
+				ctx->g_hcnts.p, slots - 1, ctx->g_acc.p, ctx->g_part.p, dk, dk ? dk + 2 * ncell : nullptr);
+			k_big_glszm_reduce<<<1, BG_T, 0, s>>> (ctx->g_mat.p, L1, ctx->g_hkeys.p, ctx->g_hcnts.p, slots, ctx->g_acc.p,
+				ctx->g_acc.p + BG_NACC, ctx->g_part.p, GB, ncell, prm, orow + COL_GLSZM);
+			CU (cudaGetLastError());
+			ctx->counts[0] += 3;
+			if (dk)
+			{
+				uint32_t nk = 0;
+				CU (cudaMemcpyAsync (&nk, dk + 2 * ncell, 4, cudaMemcpyDeviceToHost, s));
+				CU (cudaStreamSynchronize (s));
+				dbg->zone_keys->resize ((size_t)2 * nk);
+				CU (cudaMemcpy (dbg->zone_keys->data(), dk, (size_t)2 * nk * 4, cudaMemcpyDeviceToHost));
+			}
+		}
+	}
+
+	// ---- GLDZM
+	if (fam_mask & (1 << FAM_GLDZM))
+	{
+		if (blank)	// gldzm.cpp:266-289
+			fill (COL_GLDZM, NCOL_GLDZM, prm.softnan);
+		else
+		{
+			const int Nd = gldzm_nd_bound ((uint32_t)std::min<unsigned long long> (ncell, 0xFFFFFFFFull), std::max (r.w, r.h));
+			const size_t pw = (size_t)L1 * Nd;
+			if (pw > GIANT_MAX_MATRIX_WORDS || Nd > 56000)
+				return fail (ctx, NYXB200_EUNSUPPORTED, "ROI %u: distance-zone matrix of %d levels x %d distances exceeds the large-ROI GLDZM limits", r.label, L1, Nd);
+			CU (ctx->g_auxA.reserve (ncell));
+			CU (ctx->g_auxB.reserve (ncell));
+			uint32_t* parent = ctx->g_auxA.p;
+			uint32_t* zmin = ctx->g_auxB.p;
+			uint32_t* dmap = nullptr;
+			k_big_runheads<<<GB, BG_T, 0, s>>> (cell, r.w, r.h, ibsi, parent, zmin);
+			k_big_unite_rows<<<GB, BG_T, 0, s>>> (cell, r.w, r.h, ibsi, parent);
+			k_big_flatten<<<GB, BG_T, 0, s>>> (parent, ncell);
+			ctx->counts[0] += 3;
+			if (ibsi)
+			{
+				CU (ctx->g_auxC.reserve (2 * ncell + 4));
+				dmap = ctx->g_auxC.p;
+				k_big_dist_rows<<<GB, BG_T, 0, s>>> (cell, r.w, r.h, dmap);
+				k_big_dist_cols<<<std::max (1, std::min (GB, (r.w + BG_T - 1) / BG_T)), BG_T, 0, s>>> (cell, r.w, r.h, dmap);
+				ctx->counts[0] += 2;
+			}
+			k_big_zone_metric<<<GB, BG_T, 0, s>>> (cell, parent, dmap, r.w, r.h, ibsi, zmin);
+			CU (cudaGetLastError());
+			CU (ctx->g_mat.reserve (pw));
+			CU (cudaMemsetAsync (ctx->g_mat.p, 0, pw * 4, s));
+			CU (cudaMemsetAsync (ctx->g_acc.p, 0, BG_NACC * 2 * 8, s));
+			const int use_sm = (size_t)L1 * GD_SD <= BG_SMEM_WORDS;
+			if (need_smem (k_big_gldzm_zones, use_sm ? (size_t)L1 * GD_SD * 4 : 0))
+				return NYXB200_ECUDA;
+			uint32_t* dk = nullptr;
+			if (dbg && dbg->family == FAM_GLDZM)
+			{
+				CU (ctx->g_cell2.reserve (2 * ncell + 4));	// (free in a debug call: NGLDM is not selected there)
+				dk = ctx->g_cell2.p;
+				CU (cudaMemsetAsync (dk + 2 * ncell, 0, 4, s));
+			}
+			k_big_gldzm_zones<<<GB, BG_T, use_sm ? (size_t)L1 * GD_SD * 4 : 0, s>>> (cell, parent, zmin, ncell, ibsi, L1, Nd, use_sm,
+				ctx->g_mat.p, ctx->g_acc.p, ctx->g_part.p, dk, dk ? dk + 2 * ncell : nullptr);
+			if (need_smem (k_big_gldzm_reduce, (size_t)Nd * 4))
+				return NYXB200_ECUDA;
+			k_big_gldzm_reduce<<<1, BG_T, (size_t)Nd * 4, s>>> (ctx->g_mat.p, L1, Nd, ctx->g_acc.p, ctx->g_part.p, GB, r, prm, orow + COL_GLDZM);
+			CU (cudaGetLastError());
+			ctx->counts[0] += 3;
+			if (dk)
+			{
+				uint32_t nk = 0;
+				CU (cudaMemcpyAsync (&nk, dk + 2 * ncell, 4, cudaMemcpyDeviceToHost, s));
+				CU (cudaStreamSynchronize (s));
+				dbg->zone_keys->resize ((size_t)2 * nk);
+				CU (cudaMemcpy (dbg->zone_keys->data(), dk, (size_t)2 * nk * 4, cudaMemcpyDeviceToHost));
+			}
+		}
+	}
+
+	// ---- GLDM / NGLDM
+	for (int fam : { (int)FAM_GLDM, (int)FAM_NGLDM })
+	{
+		if (!(fam_mask & (1 << fam)))
+			continue;
+		const int col = fam == FAM_GLDM ? COL_GLDM : COL_NGLDM, ncol = fam == FAM_GLDM ? NCOL_GLDM : NCOL_NGLDM;
+		if (blank)	// gldm.cpp:22-40, ngldm.cpp:163-185
+		{
+			fill (col, ncol, prm.softnan);
+			continue;
+		}
+		const int L1f = fam == FAM_NGLDM ? (ibsi ? (int)r.imax : prm.greydepth) + 1 : L1;
+		const size_t pw = (size_t)L1f * 10;
+		CU (ctx->g_mat.reserve (pw));
+		CU (cudaMemsetAsync (ctx->g_mat.p, 0, pw * 4, s));
+		const int use_sm = pw <= BG_SMEM_WORDS;
+		if (need_smem (k_big_dep_build, use_sm ? pw * 4 : 0))
+			return NYXB200_ECUDA;
+		k_big_dep_build<<<GB, BG_T, use_sm ? pw * 4 : 0, s>>> (fam == FAM_NGLDM ? ctx->g_cell2.p : cell, r.w, r.h, L1f, fam == FAM_NGLDM, use_sm, ctx->g_mat.p);
+		if (fam == FAM_GLDM)
+			k_big_gldm_reduce<<<1, BG_T, 0, s>>> (ctx->g_mat.p, L1f, prm, orow + col);
+		else
+			k_big_ngldm_reduce<<<1, BG_T, 0, s>>> (ctx->g_mat.p, L1f, prm, orow + col);
+		CU (cudaGetLastError());
+		ctx->counts[0] += 2;
+		if (dbg && dbg->family == fam)
+		{
+			dbg->dense->resize (pw);
+			dbg->dim0 = L1f;
+			CU (cudaMemcpyAsync (dbg->dense->data(), ctx->g_mat.p, pw * 4, cudaMemcpyDeviceToHost, s));
+			CU (cudaStreamSynchronize (s));
+		}
+	}
+
+	// ---- NGTDM
+	if (fam_mask & (1 << FAM_NGTDM))
+	{
+		// g_mat: N[L1] | PR[L1] | lst[L1] | pad | SI[L1][8] (u64) | Pl[L1] | Sl[L1] (f64)
+		size_t w32 = (size_t)3 * L1;
+		w32 += w32 & 1;
+		const size_t total = w32 + (size_t)L1 * 16 + (size_t)L1 * 4;
+		CU (ctx->g_mat.reserve (total));
+		CU (cudaMemsetAsync (ctx->g_mat.p, 0, total * 4, s));
+		CU (cudaMemsetAsync (ctx->g_acc.p, 0, BG_NACC * 2 * 8, s));
+		uint32_t* Nn = ctx->g_mat.p;
+		uint32_t* PR = Nn + L1;
+		uint32_t* lst = PR + L1;
+		unsigned long long* SI = (unsigned long long*)(ctx->g_mat.p + w32);
+		double* Pl = (double*)(SI + (size_t)L1 * 8);
+		double* Sl = Pl + L1;
+		const size_t smw = (size_t)L1 * 16 + (size_t)2 * L1;
+		const int use_sm = smw <= BG_SMEM_WORDS;
+		if (need_smem (k_big_ngtdm_build, use_sm ? smw * 4 : 0))
+			return NYXB200_ECUDA;
+		k_big_ngtdm_build<<<GB, BG_T, use_sm ? smw * 4 : 0, s>>> (cell, r.w, r.h, L1, use_sm, Nn, SI, PR, ctx->g_acc.p);
+		k_big_ngtdm_reduce<<<1, BG_T, 0, s>>> (Nn, SI, PR, L1, ctx->g_acc.p, ibsi, prm, lst, Pl, Sl, orow + COL_NGTDM);
+		CU (cudaGetLastError());
+		ctx->counts[0] += 2;
+		if (dbg && dbg->family == FAM_NGTDM)
+		{
+			dbg->dense->resize ((size_t)2 * L1);	// N[L1] then PR[L1]
+			dbg->dim0 = L1;
+			std::vector<unsigned long long> si ((size_t)L1 * 8);
+			CU (cudaMemcpyAsync (dbg->dense->data(), Nn, (size_t)2 * L1 * 4, cudaMemcpyDeviceToHost, s));
+			CU (cudaMemcpyAsync (si.data(), SI, (size_t)L1 * 64, cudaMemcpyDeviceToHost, s));
+			CU (cudaStreamSynchronize (s));
+			dbg->ngtdm_s->assign (L1, 0.0);
+			for (int lv = 0; lv < L1; lv++)
+				for (int k = 0; k < 8; k++)
+					if (si[(size_t)lv * 8 + k])
+						(*dbg->ngtdm_s)[lv] += (double)si[(size_t)lv * 8 + k] / (double)(k + 1);
+		}
+	}
+	return 0;
+}
+
+int giant_intensity_roi (nyxb200_ctx* ctx, const ImageView& im, const RoiRec& r, const Params& prm, double* orow)
+{
+	cudaStream_t s = ctx->stream;
+	const unsigned long long nbins = (unsigned long long)(r.imax - r.imin) + 1ull;
+	if (nbins > ((unsigned long long)1 << 26))
+		return fail (ctx, NYXB200_EUNSUPPORTED, "ROI %u: intensity range %llu exceeds the 2^26 values the large-ROI first-order path histograms exactly", r.label, nbins);
+	const int GB = ctx->sm_count * 4;
+	CU (ctx->g_mat.reserve (nbins + 4));
+	CU (cudaMemsetAsync (ctx->g_mat.p, 0, nbins * 4, s));
+	k_big_int_hist<<<GB, BG_T, 0, s>>> (im, r, ctx->g_mat.p);
+	const int nb = prm.greydepth > 0 ? prm.greydepth : -prm.greydepth;
+	const size_t smb = (size_t)(101 + nb + 2) * 4;
+	if (set_smem (ctx, k_big_int_reduce, smb))
+		return NYXB200_ECUDA;
+	k_big_int_reduce<<<1, BG_T, smb, s>>> (ctx->g_mat.p, r, prm, orow + COL_INT);
+	CU (cudaGetLastError());
+	ctx->counts[0] += 2;
+	return 0;
+}
+
+// all oversize ROIs of the slide (main stream, after the small classes were joined)
+int process_giant_rois (nyxb200_ctx* ctx, const ImageView& im, const SlideInfo& info, const Params& prm, int ncol_all)
+{
+	std::vector<RoiRec> recs;
+	std::vector<uint32_t> idx;
+	const int tex_mask = ctx->fam_mask & ~(1 << FAM_INT);
+	if (tex_mask && info.class_count[NCLASS])
+	{
+		if (int rc = fetch_class_rois (ctx, ctx->d_tlist.p + ctx->tbase[NCLASS], info.class_count[NCLASS], recs, idx))
+			return rc;
+		for (size_t k = 0; k < recs.size(); k++)
+			if (int rc = giant_texture_roi (ctx, im, recs[k], prm, tex_mask, ctx->d_full.p + (size_t)idx[k] * ncol_all, nullptr))
+				return rc;
+		ctx->giant_rois += (int64_t)recs.size();
+	}
+	if ((ctx->fam_mask & (1 << FAM_INT)) && info.aclass_count[NACLASS])
+	{
+		if (int rc = fetch_class_rois (ctx, ctx->d_alist.p + ctx->abase[NACLASS], info.aclass_count[NACLASS], recs, idx))
+			return rc;
+		for (size_t k = 0; k < recs.size(); k++)
+			if (int rc = giant_intensity_roi (ctx, im, recs[k], prm, ctx->d_full.p + (size_t)idx[k] * ncol_all))
+				return rc;
+	}
+	return 0;
+}
+
+// stage st runs from this event to its stage_end (or, on the main stream, to the next stage's begin)
+void stage_end (nyxb200_ctx* ctx, int st, cudaStream_t s = nullptr)
+{
+	cudaEventRecord (ctx->ev_end[st], s ? s : ctx->stream);
+	ctx->ev_end_used[st] = true;
+	if (!s)
+		ctx->open_stage = -1;
+}
+void stage_begin (nyxb200_ctx* ctx, int st, cudaStream_t s = nullptr)
+{
+	if (!s && ctx->open_stage >= 0)		// main-stream stages are back to back
+		stage_end (ctx, ctx->open_stage);
+	cudaEventRecord (ctx->ev[st], s ? s : ctx->stream);
 	ctx->ev_used[st] = true;
+	if (!s)
+		ctx->open_stage = st;
+}
+
+// fork: family streams wait for everything submitted to the main stream so far
+int fork_families (nyxb200_ctx* ctx)
+{
+	if (!ctx->concurrent)
+		return 0;
+	CU (cudaEventRecord (ctx->ev_fork, ctx->stream));
+	for (auto& fs : ctx->fstream)
+		CU (cudaStreamWaitEvent (fs, ctx->ev_fork, 0));
+	return 0;
+}
+// family `slot` submits to its own stream (or to the main stream when serialised)
+void use_family_stream (nyxb200_ctx* ctx, int slot)
+{
+	ctx->lsi = slot;
+	ctx->ls = ctx->concurrent ? ctx->fstream[slot] : ctx->stream;
+}
+int join_families (nyxb200_ctx* ctx)
+{
+	ctx->ls = ctx->stream;
+	ctx->lsi = 0;
+	if (!ctx->concurrent)
+		return 0;
+	for (int i = 0; i < nyxb200_ctx::NFSTREAM; i++)
+	{
+		CU (cudaEventRecord (ctx->ev_join[i], ctx->fstream[i]));
+		CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_join[i], 0));
+	}
+	return 0;
 }
 
 // grow-only pinned host buffer for the result table (keeps its content when it grows)
@@ -686,6 +1163,8 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	if (nroi == 0)
 	{
 		ctx->last_info = info;
+		stage_begin (ctx, ST_TOTAL);
+		ctx->open_stage = -1;
 		return 0;
 	}
 	if (ctx->st.ibsi && info.max_inten > CELL_LEVEL)
@@ -734,15 +1213,21 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	if (d3)	// 3d_intensity.cpp:56-61: ROI range over the scanned range of the labelled voxels (slideprops.cpp:305-327)
 		prm.covered_den = (double)info.max_inten - (double)(~info.inv_min_inten);
 
-	// ---- CSR cloud (first-order only)
-	stage_begin (ctx, ST_PACK);
+	// ---- families: fork onto the family streams (slot 0 = CSR cloud + first-order, then one slot per texture family)
+	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : ctx->st.coarse_gray_depth;
+	DebugOut nodbg { nullptr, nullptr, nullptr };
+	stage_begin (ctx, ST_FAMILIES);
+	if (int rc = fork_families (ctx))
+		return rc;
+	use_family_stream (ctx, 0);
+	stage_begin (ctx, ST_PACK, ctx->ls);
 	if (ctx->fam_mask & (1 << FAM_INT))
 	{
 		CU (ctx->d_cloud.reserve ((size_t)info.n_fg + 4));
 		const uint32_t nsmall = ctx->tbase[NCLASS];
 		if (nsmall)
 		{
-			k_pack_cloud<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p, nsmall, ctx->d_cloud.p);
+			k_pack_cloud<<<(nsmall * 32 + 255) / 256, 256, 0, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p, nsmall, ctx->d_cloud.p);
 			CU (cudaGetLastError());
 			ctx->counts[0]++;
 		}
@@ -752,26 +1237,25 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 			const int grid = (int)std::min<uint32_t> (nlarge, (uint32_t)ctx->sm_count * 4);
 			const size_t stride = (size_t)im.H * (size_t)im.D + 2;
 			CU (ctx->d_rowoff.reserve ((size_t)grid * stride));
-			k_pack_cloud_large<<<grid, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->tbase[NCLASS], nlarge, ctx->d_cloud.p,
+			k_pack_cloud_large<<<grid, 256, 0, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->tbase[NCLASS], nlarge, ctx->d_cloud.p,
 				ctx->d_rowoff.p, stride);
 			CU (cudaGetLastError());
 			ctx->counts[0]++;
 		}
 	}
-
-	// ---- families
-	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : ctx->st.coarse_gray_depth;
-	DebugOut nodbg { nullptr, nullptr, nullptr };
-	stage_begin (ctx, ST_INT);
+	stage_end (ctx, ST_PACK, ctx->ls);
+	stage_begin (ctx, ST_INT, ctx->ls);
 	if (ctx->fam_mask & (1 << FAM_INT))
 	{
 		for (int c = 0; c < NACLASS; c++)
 			if (int rc = launch_intensity (ctx, ctx->d_alist.p + ctx->abase[c], info.aclass_count[c], prm, info.aclass_maxarea[c], ctx->d_full.p, ncol_all))
 				return rc;
-		if (info.aclass_count[NACLASS])
+		// clouds above 32768 pixels: 3D keeps the CTA-per-ROI kernel (global scratch); 2D goes through the giant path below
+		if (d3 && info.aclass_count[NACLASS])
 			if (int rc = launch_intensity (ctx, ctx->d_alist.p + ctx->abase[NACLASS], info.aclass_count[NACLASS], prm, info.aclass_maxarea[NACLASS], ctx->d_full.p, ncol_all))
 				return rc;
 	}
+	stage_end (ctx, ST_INT, ctx->ls);
 	static const int fam_stage[FAM_COUNT] = { ST_INT, ST_GLCM, ST_GLRLM, ST_GLDZM, ST_GLSZM, ST_GLDM, ST_NGLDM, ST_NGTDM };
 	if (d3)
 	{
@@ -781,9 +1265,10 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		for (int fam = FAM3_GLCM; fam < FAM3_COUNT; fam++)
 		{
 			static const int st3[FAM3_COUNT] = { ST_INT, ST_GLCM, ST_GLSZM, ST_NGTDM };
-			stage_begin (ctx, st3[fam]);
 			if (!(ctx->fam_mask & (1 << fam)))
 				continue;
+			use_family_stream (ctx, fam);
+			stage_begin (ctx, st3[fam], ctx->ls);
 			// grey-binning info per family (3d_glcm.cpp:53-55, 3d_glszm.cpp:490-492, 3d_ngtdm.cpp:195-197); 0 = no binning
 			int g = fam == FAM3_GLCM ? ctx->st.coarse_gray_depth : fam == FAM3_GLSZM ? ctx->glszm3_greydepth : ctx->ngtdm3_greydepth;
 			if (ctx->st.ibsi)
@@ -818,20 +1303,30 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 				if (rc)
 					return rc;
 			}
+			stage_end (ctx, st3[fam], ctx->ls);
 		}
 	}
 	else
 	for (int fam = FAM_GLCM; fam < FAM_COUNT; fam++)
 	{
-		stage_begin (ctx, fam_stage[fam]);
 		if (!(ctx->fam_mask & (1 << fam)))
 			continue;
-		if (info.class_count[NCLASS])
-			return fail (ctx, NYXB200_EUNSUPPORTED, "a ROI with an AABB larger than 40000 pixels needs the large-ROI texture path (not in this build)");
+		use_family_stream (ctx, fam);
+		stage_begin (ctx, fam_stage[fam], ctx->ls);
 		for (int c = 0; c < NCLASS; c++)
 			if (int rc = launch_family (ctx, fam, im, ctx->d_tlist.p + ctx->tbase[c], info.class_count[c], prm, Lmax,
 				info.class_maxcells[c], (int)info.class_maxwh[c], ctx->d_full.p, nodbg))
 				return rc;
+		stage_end (ctx, fam_stage[fam], ctx->ls);
+	}
+	if (int rc = join_families (ctx))
+		return rc;
+	// ---- ROIs too large for the shared-memory classes: one at a time, whole-GPU kernels (giant.cuh)
+	if (!d3 && (info.class_count[NCLASS] || info.aclass_count[NACLASS]))
+	{
+		stage_begin (ctx, ST_GIANT);
+		if (int rc = process_giant_rois (ctx, im, info, prm, ncol_all))
+			return rc;
 	}
 
 	// ---- select + D2H
@@ -857,7 +1352,8 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		return rc;
 	CU (cudaMemcpyAsync (ctx->h_out + ctx->h_out_used, ctx->d_sel_out.p, outn * sizeof (double), cudaMemcpyDeviceToHost, s));
 	ctx->h_out_used += outn;
-	stage_begin (ctx, ST_TOTAL);
+	stage_begin (ctx, ST_TOTAL);	// closes ST_D2H; ev[ST_TOTAL] marks the end of the slide
+	ctx->open_stage = -1;
 	CU (cudaStreamSynchronize (s));
 	(void)img_index;
 	return 0;
@@ -865,18 +1361,17 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 
 void collect_timings (nyxb200_ctx* ctx)
 {
-	// stage i lasts from its own event to the next recorded event
-	int order[NYXB200_NSTAGES + 1];
-	int n = 0;
-	for (int i = 0; i <= ST_TOTAL; i++)
-		if (ctx->ev_used[i])
-			order[n++] = i;
-	for (int k = 0; k + 1 < n; k++)
+	// every stage has its own begin / end event pair (family stages overlap when they run concurrently);
+	// total = first event of the slide to the end-of-slide event on the main stream
+	for (int i = 0; i < NYXB200_NSTAGES; i++)
 	{
 		float ms = 0;
-		if (cudaEventElapsedTime (&ms, ctx->ev[order[k]], ctx->ev[order[k + 1]]) == cudaSuccess)
-			ctx->stage_ms[order[k]] += ms;
+		if (i != ST_TOTAL && ctx->ev_used[i] && ctx->ev_end_used[i] && cudaEventElapsedTime (&ms, ctx->ev[i], ctx->ev_end[i]) == cudaSuccess)
+			ctx->stage_ms[i] += ms;
 	}
+	float ms = 0;
+	if (ctx->ev_used[ST_H2D] && ctx->ev_used[ST_TOTAL] && cudaEventElapsedTime (&ms, ctx->ev[ST_H2D], ctx->ev[ST_TOTAL]) == cudaSuccess)
+		ctx->stage_ms[ST_TOTAL] += ms;
 }
 
 int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const uint32_t* label, bool on_device,
@@ -897,6 +1392,7 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 	CU (cudaSetDevice (ctx->st.device));
 	for (auto& m : ctx->stage_ms) m = 0;
 	for (auto& v : ctx->counts) v = 0;
+	ctx->giant_rois = 0;
 	ctx->row_image.clear();
 	const size_t npix = (size_t)D * (size_t)H * (size_t)W;
 	const size_t ibytes = npix * (inten_u16 ? 2 : 4), lbytes = npix * 4;
@@ -904,6 +1400,8 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 	for (int k = 0; k < n_img; k++)
 	{
 		for (auto& u : ctx->ev_used) u = false;
+		for (auto& u : ctx->ev_end_used) u = false;
+		ctx->open_stage = -1;
 		ImageView im;
 		im.H = (int32_t)H;
 		im.W = (int32_t)W;
@@ -939,10 +1437,6 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 		out->data = ctx->h_out;
 	if (row_image)
 		*row_image = ctx->row_image.data();
-	float tot = 0;
-	for (int i = 0; i < ST_TOTAL; i++)
-		tot += ctx->stage_ms[i];
-	ctx->stage_ms[ST_TOTAL] = tot;
 	return NYXB200_OK;
 }
 
@@ -1095,9 +1589,87 @@ int nyxb200_debug_matrix (nyxb200_ctx* ctx, uint32_t label, int family, int64_t*
 		return fail (ctx, NYXB200_EINVAL, "label %u not found in the last slide", label);
 	const RoiRec r = ctx->h_rois[ri];
 	const uint32_t ncell = (uint32_t)r.w * (uint32_t)r.h;
-	if (tile_class (ncell) >= NCLASS)
-		return fail (ctx, NYXB200_EUNSUPPORTED, "ROI too large for the debug dump");
 	const Params prm = make_params (ctx);
+	if ((unsigned long long)r.w * (unsigned long long)r.h > 40000ull)
+	{
+		// giant path: run this one family on the ROI and read its finished matrix back
+		GiantDebug gd;
+		std::vector<uint32_t> dense, zk;
+		std::vector<double> sv;
+		gd.family = family;
+		gd.dense = &dense;
+		gd.zone_keys = &zk;
+		gd.ngtdm_s = &sv;
+		DevBuf<double> row;
+		CU (row.reserve (NCOL_ALL));
+		int rc = giant_texture_roi (ctx, ctx->last_im, r, prm, 1 << family, row.p, &gd);
+		cudaStreamSynchronize (ctx->stream);
+		row.release();
+		if (rc)
+			return rc;
+		int64_t cnt = 0;
+		auto emit = [&](int64_t ang, int64_t a, int64_t b, int64_t c, double s) {
+			if (trip && cnt < cap)
+			{
+				trip[cnt * 4] = ang; trip[cnt * 4 + 1] = a; trip[cnt * 4 + 2] = b; trip[cnt * 4 + 3] = c;
+				if (svals)
+					svals[cnt] = s;
+			}
+			cnt++;
+		};
+		if (family == FAM_GLCM && !dense.empty())
+		{
+			const size_t Ng = gd.dim0;
+			for (size_t a = 0; a < 4; a++)
+				for (size_t row_ = 0; row_ < Ng; row_++)
+					for (size_t col = 0; col < Ng; col++)
+						if (uint32_t v = dense[(a * Ng + row_) * Ng + col])
+							emit ((int64_t)a, (int64_t)row_ + 1, (int64_t)col + 1, v, 0);
+		}
+		else if (family == FAM_GLRLM && !dense.empty())
+		{
+			const size_t Lm = gd.dim0, Nr = gd.dim1;
+			for (size_t a = 0; a < 4; a++)
+				for (size_t lv = 0; lv < Lm; lv++)
+					for (size_t j = 0; j < Nr; j++)
+						if (uint32_t v = dense[(a * Lm + lv) * Nr + j])
+							emit ((int64_t)a, (int64_t)lv + 1, (int64_t)j + 1, v, 0);
+		}
+		else if (family == FAM_GLSZM || family == FAM_GLDZM)
+		{
+			std::vector<unsigned long long> keys (zk.size() / 2);
+			for (size_t i = 0; i < keys.size(); i++)
+				keys[i] = ((unsigned long long)zk[2 * i] << 32) | zk[2 * i + 1];
+			std::sort (keys.begin(), keys.end());
+			for (size_t i = 0; i < keys.size(); )
+			{
+				size_t j = i;
+				while (j < keys.size() && keys[j] == keys[i]) j++;
+				emit (0, (int64_t)(keys[i] >> 32), (int64_t)(keys[i] & 0xFFFFFFFFull), (int64_t)(j - i), 0);
+				i = j;
+			}
+		}
+		else if ((family == FAM_GLDM || family == FAM_NGLDM) && !dense.empty())
+		{
+			const int j0 = family == FAM_GLDM ? 1 : 0, j1 = family == FAM_GLDM ? 9 : 8;
+			for (int lv = family == FAM_GLDM ? 1 : 0; lv < gd.dim0; lv++)
+				for (int j = j0; j <= j1; j++)
+					if (uint32_t v = dense[(size_t)lv * 10 + j])
+						emit (0, lv, j, v, 0);
+		}
+		else if (family == FAM_NGTDM && !dense.empty())
+		{
+			int present = 0;	// the reference returns before building the matrix when |I| < 2 (ngtdm.cpp:70-78)
+			for (int lv = 0; lv < gd.dim0; lv++)
+				present += dense[(size_t)gd.dim0 + lv] != 0;
+			const int isize = ctx->st.ibsi ? (present ? gd.dim0 : 0) : present;
+			for (int lv = 0; lv < gd.dim0 && isize >= 2; lv++)
+				if (dense[lv])
+					emit (0, lv, 0, dense[lv], sv[lv]);
+		}
+		*n = cnt;
+		return NYXB200_OK;
+	}
 	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (r.imax, 1u) : ctx->st.coarse_gray_depth;
 	const int maxwh = std::max (r.w, r.h);
 	size_t words = 0;

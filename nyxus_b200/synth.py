@@ -60,6 +60,18 @@ def config2(seed=2, size=10000):
     return blob_slide(size, size, 31, 7, 12, seed, jitter=0, lobes=True)
 
 
+def config3(seed=3, size=16384):
+    """C3: size x size uint16 slide, label == 1 everywhere (whole-image single ROI), intensity model of blob_slide with
+    sigma = 12; run with coarse_gray_depth = 256, GLCM + GLRLM + GLSZM"""
+    rng = np.random.default_rng(seed)
+    smooth = _smooth_noise(rng, size, size, 12)
+    inten = 2000.0 + 1500.0 * smooth
+    del smooth
+    inten += 800.0 * rng.standard_normal((size, size), dtype=np.float32)
+    inten = np.clip(inten, 1, 65535).astype(np.uint16)
+    return inten, np.ones((size, size), np.uint32)
+
+
 def random_rois(H, W, nroi, seed, maxval=5000, levels=None):
     """random rectangles / noisy masks with assorted intensity statistics, for parity tests"""
     rng = np.random.default_rng(seed)

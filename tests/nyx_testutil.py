@@ -139,3 +139,60 @@ def emu_roi_features_3d(L, vol, lbl, lab, g, gz, gn, rad, ibsi, cols):
                                   den, 15, out.ctypes.data)
     assert rc == 0
     return finite0(out[canonical3d_index(cols)])
+
+
+# ---------------------------------------------------------------------------------------------- large-ROI (giant path) cases
+def _smooth_field(rng, H, W, lo, hi, passes=3):
+    f = rng.random((H, W))
+    for _ in range(passes):
+        f = (f + np.roll(f, 1, 0) + np.roll(f, 1, 1) + np.roll(f, -1, 0) + np.roll(f, -1, 1)) / 5.0
+    f = (f - f.min()) / (f.max() - f.min())
+    return (lo + f * (hi - lo)).astype(np.uint32)
+
+
+def giant_cases():
+    """(name, intensity, label, settings) -- every case holds at least one ROI whose AABB exceeds the 40000-cell shared-memory
+    classes, so it runs through giant.cuh.  Sizes stay small enough for the compiled reference to finish in seconds."""
+    rng = np.random.default_rng(77)
+    out = []
+    # 1. whole-image single ROI (label == 1 everywhere), MATLAB binning, >= 65536 cells (GLSZM_SAE int-wrap NaN case)
+    I = _smooth_field(rng, 260, 270, 500, 9000, 2) + rng.integers(0, 300, (260, 270)).astype(np.uint32)
+    out.append(("whole_260x270", I.astype(np.uint16), np.ones((260, 270), np.uint32), dict(g=64)))
+    # 2. concave blob with a hole + small ROIs around it; background inside the AABB becomes level-1 zones/runs
+    H, W = 330, 380
+    yy, xx = np.mgrid[0:H, 0:W]
+    big = (((yy - 160) / 130.0) ** 2 + ((xx - 180) / 150.0) ** 2 < 1) & ~((((yy - 150) / 40.0) ** 2 + ((xx - 200) / 60.0) ** 2) < 1)
+    big &= ~((yy > 200) & (xx > 250) & (yy - 200 > (xx - 250) * 0.3))
+    L = np.where(big, 7, 0).astype(np.uint32)
+    for k in range(12):
+        cy, cx = 12 + 25 * k, 360
+        m = ((yy - cy) ** 2 + (xx - cx) ** 2 < 81) & (L == 0)
+        L[m] = 20 + k
+    I = _smooth_field(rng, H, W, 100, 4000, 3) + rng.integers(0, 200, (H, W)).astype(np.uint32)
+    I[rng.random((H, W)) < 0.01] = 0            # intensity-0 pixels inside ROIs
+    out.append(("blob_hole_mixed", I.astype(np.uint16), L, dict(g=64)))
+    # 3. IBSI mode, <= 180 levels, zeros inside the ROI (GLDZM distance maps, zero-level exclusion)
+    I = _smooth_field(rng, 230, 240, 1, 180, 2)
+    I[rng.random((230, 240)) < 0.02] = 0
+    L = np.ones((230, 240), np.uint32)
+    L[:3, :5] = 0
+    out.append(("ibsi_230x240", I, L, dict(ibsi=True)))
+    # 4. 256 grey levels (BASELINE configs[2] settings) on a noisy 300x300 single ROI
+    I = _smooth_field(rng, 300, 300, 2000, 5000, 4) + rng.normal(0, 400, (300, 300)).clip(-1500, 1500).astype(np.int64).astype(np.uint32)
+    out.append(("g256_300x300", I.astype(np.uint16), np.ones((300, 300), np.uint32), dict(g=256)))
+    # 5. sparse ROI: huge AABB, tiny area (giant texture path, small-cloud first-order path) + a long thin ROI
+    I = _smooth_field(rng, 300, 420, 10, 3000, 1)
+    L = np.zeros((300, 420), np.uint32)
+    L[5:9, 4:9] = 3
+    L[280:286, 400:410] = 3
+    L[150, 10:400] = 5
+    L[151, 10:400:2] = 5
+    out.append(("sparse_and_thin", I, L, dict(g=64)))
+    # 6. constant-intensity giant ROI (blank: every texture family softNaN) next to a low-contrast one
+    I = np.full((250, 420), 777, np.uint32)
+    L = np.zeros((250, 420), np.uint32)
+    L[:, :205] = 1
+    L[:, 210:] = 2
+    I[:, 210:] = 40000 + rng.integers(0, 40, (250, 210)) ** 2 // 40   # skewed, narrow range on a high mean
+    out.append(("blank_and_lowcontrast", I, L, dict(g=64)))
+    return out

@@ -355,3 +355,65 @@ def test_nyxus3d_featurize_files_nifti(tmp_path):
 def NyxusError_or_ValueError():
     from nyxus_b200 import NyxusB200Error
     return (NyxusB200Error, ValueError)
+
+
+# ------------------------------------------------------------------------------------------------ large ROIs (giant.cuh)
+_GIANT = tu.giant_cases()
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("case", _GIANT, ids=[c[0] for c in _GIANT])
+def test_giant_roi_table_and_matrices_match_reference(case):
+    """ROIs whose AABB exceeds the shared-memory size classes (> 40000 cells) run through the whole-GPU kernels of
+    giant.cuh: the full 337-column table within 1e-9 of the compiled reference and every matrix entry exact."""
+    name, I, L, kw = case
+    g, ibsi = kw.get("g", 64), kw.get("ibsi", False)
+    e = _engine(coarse_gray_depth=g, ibsi=ibsi)
+    try:
+        tab, _ = e.featurize(I, L)
+        rl, rt, _ = ref.featurize_2d(I, L, greydepth=g, ibsi=ibsi, nthreads=8)
+        assert e.columns == ref.columns()
+        assert np.array_equal(tab[:, 0].astype(np.int64), rl.astype(np.int64))
+        bad = tu.mismatches(rt, tab[:, 2:], e.columns)
+        assert not bad, (name, bad[:8])
+        recs = e.debug_rois()
+        big = [r for r in recs if r[6] * r[7] > 40000]
+        assert big, "case holds no giant ROI"
+        for r in big[:2]:
+            lab, x0, y0, w, h = int(r[0]), int(r[4]), int(r[5]), int(r[6]), int(r[7])
+            mask = L[y0:y0 + h, x0:x0 + w] == lab
+            tile = I[y0:y0 + h, x0:x0 + w].astype(np.uint32) * mask
+            rm = ref.roi_matrices(tile, mask, g, ibsi)
+            for fam in tu.FAMILIES:
+                got, svals = e.debug_matrix(lab, fam)
+                assert sorted(got) == sorted(rm[fam]), (name, fam, lab)
+                if fam == "NGTDM" and len(rm["NGTDM_S"]):
+                    order = np.argsort([t[1] for t in got])
+                    assert np.allclose(np.array(svals)[order], rm["NGTDM_S"], rtol=1e-12, atol=1e-9)
+    finally:
+        e.close()
+
+
+def test_giant_whole_slide_properties():
+    """BASELINE configs[2] shape at 4096^2 (256 grey levels, GLCM + GLRLM + GLSZM, label == 1 everywhere): size-independent
+    properties -- a transposed slide swaps the 0 and 90 degree GLCM / GLRLM columns and leaves 45 degrees alone; run
+    percentage and zone percentage lie in (0, 1]; repeated calls are bit-identical (integer matrices, fixed-order FP64)."""
+    from nyxus_b200 import synth
+    I, L = synth.config3(size=2048)
+    e = _engine(["*ALL_GLCM*", "*ALL_GLRLM*", "*ALL_GLSZM*"], coarse_gray_depth=256)
+    try:
+        t1, _ = e.featurize(I, L)
+        t2, _ = e.featurize(I, L)
+        assert np.array_equal(t1, t2)
+        tt, _ = e.featurize(np.ascontiguousarray(I.T), L)
+        cols = e.columns
+        c = {n: i + 2 for i, n in enumerate(cols)}
+        for f in ("GLCM_ASM", "GLCM_CONTRAST", "GLCM_JE", "GLRLM_SRE", "GLRLM_RP", "GLRLM_RE"):
+            assert np.isclose(t1[0, c[f + "_0"]], tt[0, c[f + "_90"]], rtol=1e-12), f
+            assert np.isclose(t1[0, c[f + "_90"]], tt[0, c[f + "_0"]], rtol=1e-12), f
+        for f in ("GLCM_ASM", "GLCM_CONTRAST", "GLCM_JE"):   # MATLAB mode: asymmetric matrix, transposition flips (dx,dy)=(1,1) onto itself
+            assert np.isclose(t1[0, c[f + "_45"]], tt[0, c[f + "_45"]], rtol=1e-12), f
+        assert 0 < t1[0, c["GLRLM_RP_0"]] <= 1 and 0 < t1[0, c["GLSZM_ZP"]] <= 1
+        assert t1[0, c["GLSZM_SAE"]] == 0.0     # >= 65536 cells: the reference's int j*j wrap turns SAE into NaN -> noval
+    finally:
+        e.close()
