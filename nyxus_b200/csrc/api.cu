@@ -129,7 +129,9 @@ struct nyxb200_ctx
 	uint32_t stats_cap = 1u << 20;
 	DevBuf<SlideInfo> d_info;
 	DevBuf<uint32_t> d_blkcnt;
-	DevBuf<unsigned long long> d_blkarea;
+	DevBuf<unsigned long long> d_blkarea, d_blkcells;
+	DevBuf<uint16_t> d_tiles;	// binned-tile store (k_pack_tiles)
+	int use_tile_store = 1;
 	DevBuf<RoiRec> d_rois;
 	DevBuf<uint32_t> d_classslot, d_tlist, d_alist, d_bases;
 	DevBuf<uint32_t> d_cloud;
@@ -413,6 +415,8 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 		ctx->st.soft_nan = value;
 	else if (!strcmp (key, "concurrent_families"))	// measurement knob: 0 = one family after the other (clean per-stage times)
 		ctx->concurrent = iv != 0;
+	else if (!strcmp (key, "tile_store"))			// test knob: 0 = family kernels bin straight from the slide
+		ctx->use_tile_store = iv != 0;
 	else if (!strcmp (key, "3glcm/greydepth"))		// env_metaparams.cpp:109-120
 	{
 		if (iv <= 0 || iv > 65535)
@@ -483,7 +487,7 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 {
 	if (!n)
 		return 0;
-	const size_t tilew = (maxcells + 1) & ~(size_t)1;
+	const size_t tilew = tile_words (maxcells);
 	const size_t famw = (family_words (FAM, P16, Lmax, maxcells, maxwh) + 1) & ~(size_t)1;
 	// small tiles of the single-matrix families: one warp per ROI
 	if (FAM != FAM_GLCM && FAM != FAM_GLRLM && !dbg.u32 && maxcells <= 1024 && tilew + famw <= WARP_SLICE_LIMIT_WORDS)
@@ -545,8 +549,8 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 {
 	if (!n)
 		return 0;
-	const uint32_t npad = next_pow2 (maxarea);
-	const size_t memw = (intensity_smem_words (npad, prm.greydepth) + 1) & ~(size_t)1;
+	const uint32_t npad = std::max (next_pow2 (maxarea), 64u);	// the warp-per-ROI register sort works on >= 64 keys
+	const size_t memw = (intensity_smem_words (npad, prm.greydepth) + 3) & ~(size_t)3;	// 16-byte aligned warp slices
 	if (npad <= 1024 && memw <= WARP_SLICE_LIMIT_WORDS)	// small clouds: one warp per ROI
 	{
 		const size_t bytes = memw * 4 * ROI_WARPS;
@@ -585,7 +589,7 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 {
 	if (!n)
 		return 0;
-	const size_t tilew = (maxcells + 1) & ~(size_t)1;
+	const size_t tilew = tile_words (maxcells);
 	size_t famw = 0;
 	if (FAM3 == FAM3_GLCM) famw = P16 ? glcm_smem_words<true> (Lmax, 4) : glcm_smem_words<false> (Lmax, 4);
 	if (FAM3 == FAM3_GLSZM) famw = glszm3d_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));
@@ -1136,8 +1140,10 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		const uint32_t nblk = (ctx->stats_cap + CB - 1) / CB;
 		CU (ctx->d_blkcnt.reserve (nblk));
 		CU (ctx->d_blkarea.reserve (nblk));
-		k_compact_count<<<nblk, CB, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ctx->d_blkcnt.p, ctx->d_blkarea.p);
-		k_compact_scan<<<1, CB, 0, s>>> (ctx->d_blkcnt.p, ctx->d_blkarea.p, nblk, ctx->d_info.p);
+		CU (ctx->d_blkcells.reserve (nblk));
+		k_compact_count<<<nblk, CB, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ctx->d_blkcnt.p, ctx->d_blkarea.p,
+			ctx->d_blkcells.p, d3 ? 1 : 0);
+		k_compact_scan<<<1, CB, 0, s>>> (ctx->d_blkcnt.p, ctx->d_blkarea.p, ctx->d_blkcells.p, nblk, ctx->d_info.p);
 		CU (cudaGetLastError());
 		ctx->counts[0] += 2;
 		CU (cudaMemcpyAsync (&info, ctx->d_info.p, sizeof (info), cudaMemcpyDeviceToHost, s));
@@ -1179,7 +1185,7 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	{
 		const uint32_t nblk = (ctx->stats_cap + CB - 1) / CB;
 		k_compact_write<<<nblk, CB, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ctx->d_blkcnt.p, ctx->d_blkarea.p,
-			ctx->d_rois.p, ctx->d_classslot.p, d3 ? ctx->d_ztab.p : nullptr);
+			ctx->d_blkcells.p, ctx->d_rois.p, ctx->d_classslot.p, d3 ? ctx->d_ztab.p : nullptr);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		CU (cudaMemcpyAsync (&info, ctx->d_info.p, sizeof (info), cudaMemcpyDeviceToHost, s));
@@ -1213,37 +1219,56 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	if (d3)	// 3d_intensity.cpp:56-61: ROI range over the scanned range of the labelled voxels (slideprops.cpp:305-327)
 		prm.covered_den = (double)info.max_inten - (double)(~info.inv_min_inten);
 
-	// ---- families: fork onto the family streams (slot 0 = CSR cloud + first-order, then one slot per texture family)
+	// ---- K2: CSR cloud + binned-tile store in one pass over the ROIs' AABBs (main stream: every family depends on it)
 	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : ctx->st.coarse_gray_depth;
 	DebugOut nodbg { nullptr, nullptr, nullptr };
-	stage_begin (ctx, ST_FAMILIES);
-	if (int rc = fork_families (ctx))
-		return rc;
-	use_family_stream (ctx, 0);
-	stage_begin (ctx, ST_PACK, ctx->ls);
-	if (ctx->fam_mask & (1 << FAM_INT))
+	ImageView imf = im;		// the view the family kernels get (with the tile store when it is used)
+	stage_begin (ctx, ST_PACK);
 	{
-		CU (ctx->d_cloud.reserve ((size_t)info.n_fg + 4));
-		const uint32_t nsmall = ctx->tbase[NCLASS];
-		if (nsmall)
+		const bool want_cloud = (ctx->fam_mask & (1 << FAM_INT)) != 0;
+		const bool want_tex = !d3 && (ctx->fam_mask & ~(1 << FAM_INT)) != 0;
+		// 16-bit codes hold 14-bit levels: MATLAB binning up to 16383 levels, IBSI (identity) up to that intensity
+		const bool tiles = want_tex && ctx->use_tile_store && info.n_tile_cells > 0 && (uint32_t)Lmax <= TILE16_LEVEL
+			&& (uint32_t)ctx->st.coarse_gray_depth <= TILE16_LEVEL;
+		const bool tiles_b = tiles && (ctx->fam_mask & (1 << FAM_NGLDM));
+		if (want_cloud)
+			CU (ctx->d_cloud.reserve ((size_t)info.n_fg + 4));
+		if (tiles)
 		{
-			k_pack_cloud<<<(nsmall * 32 + 255) / 256, 256, 0, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p, nsmall, ctx->d_cloud.p);
+			CU (ctx->d_tiles.reserve ((size_t)info.n_tile_cells * (tiles_b ? 2 : 1)));
+			imf.tileA = ctx->d_tiles.p;
+			imf.tileB = tiles_b ? ctx->d_tiles.p + info.n_tile_cells : nullptr;
+		}
+		const uint32_t nsmall = ctx->tbase[NCLASS];
+		if (nsmall && (want_cloud || tiles))
+		{
+			if (d3)
+				k_pack_cloud<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p, nsmall, ctx->d_cloud.p);
+			else
+				k_pack_tiles<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p, nsmall, prm,
+					want_cloud ? ctx->d_cloud.p : nullptr, (uint16_t*)imf.tileA, (uint16_t*)imf.tileB);
 			CU (cudaGetLastError());
 			ctx->counts[0]++;
 		}
 		const uint32_t nlarge = info.class_count[NCLASS];
-		if (nlarge)
+		if (nlarge && want_cloud)
 		{
 			const int grid = (int)std::min<uint32_t> (nlarge, (uint32_t)ctx->sm_count * 4);
 			const size_t stride = (size_t)im.H * (size_t)im.D + 2;
 			CU (ctx->d_rowoff.reserve ((size_t)grid * stride));
-			k_pack_cloud_large<<<grid, 256, 0, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->tbase[NCLASS], nlarge, ctx->d_cloud.p,
+			k_pack_cloud_large<<<grid, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->tbase[NCLASS], nlarge, ctx->d_cloud.p,
 				ctx->d_rowoff.p, stride);
 			CU (cudaGetLastError());
 			ctx->counts[0]++;
 		}
 	}
-	stage_end (ctx, ST_PACK, ctx->ls);
+	ctx->last_im = imf;
+
+	// ---- families: fork onto the family streams (slot 0 = first-order, then one slot per texture family)
+	stage_begin (ctx, ST_FAMILIES);
+	if (int rc = fork_families (ctx))
+		return rc;
+	use_family_stream (ctx, 0);
 	stage_begin (ctx, ST_INT, ctx->ls);
 	if (ctx->fam_mask & (1 << FAM_INT))
 	{
@@ -1314,7 +1339,7 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		use_family_stream (ctx, fam);
 		stage_begin (ctx, fam_stage[fam], ctx->ls);
 		for (int c = 0; c < NCLASS; c++)
-			if (int rc = launch_family (ctx, fam, im, ctx->d_tlist.p + ctx->tbase[c], info.class_count[c], prm, Lmax,
+			if (int rc = launch_family (ctx, fam, imf, ctx->d_tlist.p + ctx->tbase[c], info.class_count[c], prm, Lmax,
 				info.class_maxcells[c], (int)info.class_maxwh[c], ctx->d_full.p, nodbg))
 				return rc;
 		stage_end (ctx, fam_stage[fam], ctx->ls);

@@ -159,7 +159,7 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 	const double p01 = sh[0], p10 = sh[1], p25 = sh[2], p75 = sh[3], p90 = sh[4], p99 = sh[5];
 
 	// ---- sort -> median (histogram.h:268-287), mode (:289-309)
-	bitonic_sort (c, srt, npad);
+	sort_keys (c, srt, npad);
 	double median;
 	if (n & 1)
 		median = (double)srt[n / 2];

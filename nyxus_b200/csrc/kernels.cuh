@@ -41,6 +41,7 @@ struct SlideInfo
 	uint32_t aclass_count[NACLASS + 1];
 	uint32_t aclass_maxarea[NACLASS + 1];
 	uint32_t inv_min_inten;		// ~(smallest aux_min over ROIs): the slide's foreground minimum (3D COVERED_IMAGE_INTENSITY_RANGE)
+	unsigned long long n_tile_cells;	// cells of the binned-tile store (sum of the padded AABBs of the small-class ROIs)
 };
 
 __host__ __device__ inline int tile_class (uint32_t ncell)
@@ -265,121 +266,152 @@ __global__ void __launch_bounds__(256) k_scan_stats (const void* __restrict__ in
 // ------------------------------------------------------------------------------------------------
 constexpr int CB = 1024;
 
-__device__ __forceinline__ void block_exscan_2 (uint32_t& a, unsigned long long& b, uint32_t* sa, unsigned long long* sb,
-	uint32_t& tot_a, unsigned long long& tot_b)
+// cells of the ROI's slot in the binned-tile store: the AABB padded to 8 cells (one 128-bit load of 16-bit codes);
+// ROIs beyond the shared-memory classes (giant path) and 3D ROIs keep no stored tile
+__host__ __device__ inline uint32_t tile_store_cells (uint32_t w, uint32_t h, bool d3)
 {
-	// exclusive scan over the block of (a, b); sa/sb: 32-entry shared scratch each
+	if (d3)
+		return 0;
+	const unsigned long long nc = (unsigned long long)w * h;
+	if (nc > 40000ull)
+		return 0;
+	return ((uint32_t)nc + 7u) & ~7u;
+}
+
+__device__ __forceinline__ void block_exscan_3 (uint32_t& a, unsigned long long& b, unsigned long long& cc, uint32_t* sa,
+	unsigned long long* sb, unsigned long long* sc, uint32_t& tot_a, unsigned long long& tot_b, unsigned long long& tot_c)
+{
+	// exclusive scan over the block of (a, b, cc); sa/sb/sc: 33-entry shared scratch each
 	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	uint32_t ia = a;
-	unsigned long long ib = b;
+	unsigned long long ib = b, ic = cc;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1)
 	{
 		uint32_t ta = __shfl_up_sync (0xffffffffu, ia, o);
 		unsigned long long tb = __shfl_up_sync (0xffffffffu, ib, o);
+		unsigned long long tc = __shfl_up_sync (0xffffffffu, ic, o);
 		if (lane >= o)
 		{
 			ia += ta;
 			ib += tb;
+			ic += tc;
 		}
 	}
 	if (lane == 31)
 	{
 		sa[warp] = ia;
 		sb[warp] = ib;
+		sc[warp] = ic;
 	}
 	__syncthreads();
 	if (warp == 0)
 	{
 		uint32_t wa = lane < (blockDim.x >> 5) ? sa[lane] : 0;
 		unsigned long long wb = lane < (blockDim.x >> 5) ? sb[lane] : 0;
+		unsigned long long wc = lane < (blockDim.x >> 5) ? sc[lane] : 0;
 		uint32_t xa = wa;
-		unsigned long long xb = wb;
+		unsigned long long xb = wb, xc = wc;
 #pragma unroll
 		for (int o = 1; o < 32; o <<= 1)
 		{
 			uint32_t ta = __shfl_up_sync (0xffffffffu, xa, o);
 			unsigned long long tb = __shfl_up_sync (0xffffffffu, xb, o);
+			unsigned long long tc = __shfl_up_sync (0xffffffffu, xc, o);
 			if (lane >= o)
 			{
 				xa += ta;
 				xb += tb;
+				xc += tc;
 			}
 		}
 		sa[lane] = xa - wa;	// exclusive warp offsets
 		sb[lane] = xb - wb;
+		sc[lane] = xc - wc;
 		if (lane == 31)
 		{
 			sa[32] = xa;
 			sb[32] = xb;
+			sc[32] = xc;
 		}
 	}
 	__syncthreads();
 	a = sa[warp] + ia - a;
 	b = sb[warp] + ib - b;
+	cc = sc[warp] + ic - cc;
 	tot_a = sa[32];
 	tot_b = sb[32];
+	tot_c = sc[32];
 	__syncthreads();
 }
 
 __global__ void __launch_bounds__(CB) k_compact_count (const LabelStat* tab, uint32_t cap, const SlideInfo* info,
-	uint32_t* blk_cnt, unsigned long long* blk_area)
+	uint32_t* blk_cnt, unsigned long long* blk_area, unsigned long long* blk_cells, int d3)
 {
 	__shared__ uint32_t sa[33];
-	__shared__ unsigned long long sb[33];
+	__shared__ unsigned long long sb[33], sc[33];
 	const uint32_t i = blockIdx.x * CB + threadIdx.x;
 	uint32_t a = 0;
-	unsigned long long b = 0;
+	unsigned long long b = 0, cc = 0;
 	if (i < cap && i <= info->max_label && i > 0)
 	{
-		uint32_t ar = tab[i].area;
-		a = ar ? 1 : 0;
-		b = ar;
+		const LabelStat s = tab[i];
+		a = s.area ? 1 : 0;
+		b = s.area;
+		if (s.area)
+			cc = tile_store_cells (s.xmax - s.xmin + 1, s.ymax - s.ymin + 1, d3 != 0);
 	}
 	uint32_t ta;
-	unsigned long long tb;
-	block_exscan_2 (a, b, sa, sb, ta, tb);
+	unsigned long long tb, tc;
+	block_exscan_3 (a, b, cc, sa, sb, sc, ta, tb, tc);
 	if (threadIdx.x == 0)
 	{
 		blk_cnt[blockIdx.x] = ta;
 		blk_area[blockIdx.x] = tb;
+		blk_cells[blockIdx.x] = tc;
 	}
 }
 
-__global__ void __launch_bounds__(CB) k_compact_scan (uint32_t* blk_cnt, unsigned long long* blk_area, uint32_t nblk, SlideInfo* info)
+__global__ void __launch_bounds__(CB) k_compact_scan (uint32_t* blk_cnt, unsigned long long* blk_area, unsigned long long* blk_cells,
+	uint32_t nblk, SlideInfo* info)
 {
 	__shared__ uint32_t sa[33];
-	__shared__ unsigned long long sb[33];
+	__shared__ unsigned long long sb[33], sc[33];
 	uint32_t run_a = 0;
-	unsigned long long run_b = 0;
+	unsigned long long run_b = 0, run_c = 0;
 	for (uint32_t base = 0; base < nblk; base += CB)
 	{
 		uint32_t i = base + threadIdx.x;
 		uint32_t a = i < nblk ? blk_cnt[i] : 0;
 		unsigned long long b = i < nblk ? blk_area[i] : 0;
+		unsigned long long cc = i < nblk ? blk_cells[i] : 0;
 		uint32_t ta;
-		unsigned long long tb;
-		block_exscan_2 (a, b, sa, sb, ta, tb);
+		unsigned long long tb, tc;
+		block_exscan_3 (a, b, cc, sa, sb, sc, ta, tb, tc);
 		if (i < nblk)
 		{
 			blk_cnt[i] = a + run_a;
 			blk_area[i] = b + run_b;
+			blk_cells[i] = cc + run_c;
 		}
 		run_a += ta;
 		run_b += tb;
+		run_c += tc;
 	}
 	if (threadIdx.x == 0)
 	{
 		info->n_roi = run_a;
 		info->n_fg = run_b;
+		info->n_tile_cells = run_c;
 	}
 }
 
 __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uint32_t cap, SlideInfo* info,
-	const uint32_t* blk_cnt, const unsigned long long* blk_area, RoiRec* rois, uint32_t* class_slot, const uint2* ztab = nullptr)
+	const uint32_t* blk_cnt, const unsigned long long* blk_area, const unsigned long long* blk_cells, RoiRec* rois,
+	uint32_t* class_slot, const uint2* ztab = nullptr)
 {
 	__shared__ uint32_t sa[33];
-	__shared__ unsigned long long sb[33];
+	__shared__ unsigned long long sb[33], sc[33];
 	// per-block class tallies: slots are handed out inside the block first, ONE global atomic per (block, class) after
 	__shared__ uint32_t s_cnt[NCLASS + 1], s_acnt[NACLASS + 1], s_base[NCLASS + 1], s_abase[NACLASS + 1];
 	__shared__ uint32_t s_maxcells[NCLASS + 1], s_maxwh[NCLASS + 1], s_maxarea[NACLASS + 1], s_maxinten, s_invmin;
@@ -401,7 +433,7 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 	}
 	const uint32_t i = blockIdx.x * CB + threadIdx.x;
 	uint32_t a = 0;
-	unsigned long long b = 0;
+	unsigned long long b = 0, cc = 0;
 	LabelStat s;
 	s.area = 0;
 	if (i < cap && i <= info->max_label && i > 0)
@@ -409,16 +441,18 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 		s = tab[i];
 		a = s.area ? 1 : 0;
 		b = s.area;
+		if (s.area)
+			cc = tile_store_cells (s.xmax - s.xmin + 1, s.ymax - s.ymin + 1, ztab != nullptr);
 	}
 	uint32_t ta;
-	unsigned long long tb;
+	unsigned long long tb, tc;
 	const uint32_t present = a;
-	block_exscan_2 (a, b, sa, sb, ta, tb);		// (contains the barriers that publish the zeroed tallies)
+	block_exscan_3 (a, b, cc, sa, sb, sc, ta, tb, tc);		// (contains the barriers that publish the zeroed tallies)
 	if (ta == 0)
 		return;
 	RoiRec r;
 	uint32_t idx = 0, tslot = 0, aslot = 0;
-	int tc = 0, ac = 0;
+	int tc_ = 0, ac = 0;
 	if (present)
 	{
 		idx = blk_cnt[blockIdx.x] + a;
@@ -431,6 +465,7 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 		r.w = (int32_t)(s.xmax - s.xmin + 1);
 		r.h = (int32_t)(s.ymax - s.ymin + 1);
 		r.cloud_off = blk_area[blockIdx.x] + b;
+		r.tile_off = blk_cells[blockIdx.x] + cc;
 		r.z0 = 0;
 		r.d = 1;
 		if (ztab)
@@ -442,12 +477,12 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 		rois[idx] = r;
 		const unsigned long long ncell64 = (unsigned long long)r.w * (unsigned long long)r.h * (unsigned long long)r.d;
 		const uint32_t ncell = ncell64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ncell64;
-		tc = tile_class (ncell);
+		tc_ = tile_class (ncell);
 		ac = area_class (r.area);
-		tslot = atomicAdd (&s_cnt[tc], 1u);
+		tslot = atomicAdd (&s_cnt[tc_], 1u);
 		aslot = atomicAdd (&s_acnt[ac], 1u);
-		atomicMax (&s_maxcells[tc], ncell);
-		atomicMax (&s_maxwh[tc], (uint32_t)max (max (r.w, r.h), r.d));
+		atomicMax (&s_maxcells[tc_], ncell);
+		atomicMax (&s_maxwh[tc_], (uint32_t)max (max (r.w, r.h), r.d));
 		atomicMax (&s_maxarea[ac], r.area);
 		atomicMax (&s_maxinten, r.imax);
 		atomicMax (&s_invmin, ~r.imin);
@@ -472,7 +507,7 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 	__syncthreads();
 	if (present)
 	{
-		class_slot[idx * 2] = ((uint32_t)tc << 28) | (s_base[tc] + tslot);
+		class_slot[idx * 2] = ((uint32_t)tc_ << 28) | (s_base[tc_] + tslot);
 		class_slot[idx * 2 + 1] = ((uint32_t)ac << 28) | (s_abase[ac] + aslot);
 	}
 }
@@ -517,6 +552,66 @@ __global__ void __launch_bounds__(256) k_pack_cloud (ImageView im, const RoiRec*
 				in = true;
 				v = load_inten (im, rowbase + x);
 			}
+			const unsigned b = __ballot_sync (0xffffffffu, in);
+			if (in)
+				dst[run + __popc (b & ((1u << lane) - 1))] = v;
+			run += __popc (b);
+		}
+	}
+}
+
+// Binning + packing in one pass (K2): one warp per ROI walks the ROI's AABB once in raster order and writes
+//   * the CSR cloud slice (ballot/popc compaction, as k_pack_cloud),
+//   * the ROI's slot of the binned-tile store: 16-bit codes (level + NZ/IN flags) of EVERY AABB cell, contiguous,
+//     so the seven texture kernels load a coalesced pre-binned tile instead of re-gathering label + intensity rows and
+//     re-binning them (reference: bin_intensities is redone per family and per angle, texture_feature.h:23-167).
+// tileB: NGLDM's own grey scale (to_grayscale over [0, aux_max], ngldm.cpp:42,126).
+__global__ void __launch_bounds__(256) k_pack_tiles (ImageView im, const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+	uint32_t n, Params prm, uint32_t* __restrict__ cloud, uint16_t* __restrict__ tileA, uint16_t* __restrict__ tileB)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	if (warp >= n)
+		return;
+	const RoiRec r = rois[list ? list[warp] : warp];
+	const uint32_t ncell = (uint32_t)r.w * (uint32_t)r.h, npad = (ncell + 7u) & ~7u;
+	Binner B;
+	B.init (prm.ibsi ? 0 : prm.greydepth, r.imin, r.imax);
+	FastDiv fw;
+	fw.init ((uint32_t)r.w);
+	uint32_t* dst = cloud ? cloud + r.cloud_off : nullptr;
+	uint16_t* ta = tileA ? tileA + r.tile_off : nullptr;
+	uint16_t* tb = tileB ? tileB + r.tile_off : nullptr;
+	const size_t origin = (size_t)r.y0 * im.W + (size_t)r.x0;
+	uint32_t run = 0;
+	for (uint32_t base = 0; base < npad; base += 32)
+	{
+		const uint32_t i = base + lane;
+		bool in = false;
+		uint32_t v = 0;
+		if (i < ncell)
+		{
+			const uint32_t y = fw.div (i), x = i - y * (uint32_t)r.w;
+			const size_t g = origin + (size_t)y * im.W + x;
+			if (im.label[g] == r.label)
+			{
+				in = true;
+				v = load_inten (im, g);
+			}
+		}
+		if (i < npad)
+		{
+			if (ta)
+			{
+				uint32_t code = 0;
+				if (i < ncell)
+					code = (B.bin (v) & TILE16_LEVEL) | (v ? 0x8000u : 0u) | (in ? 0x4000u : 0u);
+				ta[i] = (uint16_t)code;
+			}
+			if (tb)
+				tb[i] = in ? (uint16_t)((to_grayscale (v, 0, r.imax, (uint32_t)prm.greydepth, prm.ibsi != 0) & TILE16_LEVEL) | 0x4000u) : (uint16_t)0;
+		}
+		if (dst)
+		{
 			const unsigned b = __ballot_sync (0xffffffffu, in);
 			if (in)
 				dst[run + __popc (b & ((1u << lane) - 1))] = v;
@@ -600,7 +695,9 @@ template <int FAM, bool P16>
 __device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, const RoiRec& r, const Params& prm, uint32_t* cell,
 	uint32_t* mem, int Lmax, uint32_t maxcells, int maxwh, double* o, const DebugOut& dbg)
 {
-	if (FAM == FAM_NGLDM)
+	if (FAM == FAM_NGLDM ? im.tileB != nullptr : im.tileA != nullptr)
+		load_tile_store (c, (FAM == FAM_NGLDM ? im.tileB : im.tileA) + r.tile_off, r.w * r.h, cell);
+	else if (FAM == FAM_NGLDM)
 		load_tile_ngldm (c, im, r, prm, cell);
 	else
 	{
@@ -656,7 +753,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family (ImageView im, const
 	extern __shared__ __align__(16) uint32_t smem[];
 	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
 	uint32_t* cell = smem + RED_WORDS;
-	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : cell + ((maxcells + 1) & ~1u);
+	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : cell + tile_words (maxcells);
 	// the family region is all zero on entry of every body and every body leaves it all zero again (owner-zeroing):
 	// cleared here once per CTA (the global scratch slots are cleared by the host before the launch)
 	if (!gscratch)
@@ -679,7 +776,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family_w (ImageView im, con
 {
 	extern __shared__ __align__(16) uint32_t smem[];
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const size_t tilew = (maxcells + 1) & ~1u;
+	const size_t tilew = tile_words (maxcells);
 	uint32_t* cell = smem + (size_t)warp * (tilew + famw);
 	uint32_t* mem = cell + tilew;
 	Cta c { lane, 32, nullptr, 1 };
@@ -712,7 +809,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 	extern __shared__ __align__(16) uint32_t smem[];
 	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
 	uint32_t* cell = smem + RED_WORDS;
-	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : cell + ((maxcells + 1) & ~1u);
+	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : cell + tile_words (maxcells);
 	if (!gscratch)
 		for (size_t i = threadIdx.x; i < gwords; i += blockDim.x)
 			mem[i] = 0;
@@ -764,7 +861,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_intensity_w (const RoiRec* 
 	{
 		const uint32_t ri = list ? list[k] : k;
 		const RoiRec r = rois[ri];
-		intensity_body (c, r, prm, cloud + r.cloud_off, r.area, next_pow2 (r.area), mem, out + (size_t)ri * out_stride + COL_INT);
+		intensity_body (c, r, prm, cloud + r.cloud_off, r.area, max (next_pow2 (r.area), 64u), mem, out + (size_t)ri * out_stride + COL_INT);
 		c.sync();
 	}
 }

@@ -173,6 +173,7 @@ struct RoiRec
 	int32_t x0, y0, w, h;	// AABB origin and extent (w = xmax-xmin+1)
 	uint64_t cloud_off;	// offset of this ROI's pixels in the CSR cloud
 	int32_t z0, d;		// 3D only
+	uint64_t tile_off;	// first cell of this ROI's slot in the binned-tile store (multiple of 8)
 };
 
 struct ImageView
@@ -182,6 +183,10 @@ struct ImageView
 	int32_t H, W;
 	int32_t inten_u16;
 	int32_t D = 1;		// slices (1: 2D image); voxel (z,y,x) lives at (z*H + y)*W + x
+	// binned-tile store written by k_pack_tiles (null: the family kernels bin straight from the slide):
+	// tileA = Binner levels + NZ/IN flags, tileB = NGLDM's to_grayscale levels + IN flag; 16-bit codes, ROI slot at RoiRec::tile_off
+	const uint16_t* tileA = nullptr;
+	const uint16_t* tileB = nullptr;
 };
 
 struct Params
@@ -453,6 +458,89 @@ NYX_D void bitonic_sort (const Cta& c, uint32_t* a, uint32_t npad)
 		}
 }
 
+#if NYX_DEVICE_BUILD
+// One warp sorts 32*R keys held in REGISTERS (R per lane): a bitonic network over the element index e = lane*R + r.
+// Exchanges at distance j < R stay inside a lane (a min/max pair), j >= R are one shuffle per register; nothing goes
+// through shared memory until the sorted keys are stored.  In: a[] filled from srt[r*32 + lane] (any order is a valid
+// input).  Out: srt[0 .. 32R) ascending.
+template <int R> NYX_D void warp_sort_regs (uint32_t* srt, int lane)
+{
+	uint32_t a[R];
+#pragma unroll
+	for (int r = 0; r < R; r++)
+		a[r] = srt[r * 32 + lane];
+	__syncwarp();
+#pragma unroll
+	for (int k = 2; k <= 32 * R; k <<= 1)
+	{
+		// direction of the k-block this element is in: ascending when (e & k) == 0
+		const bool lane_up = k >= R ? (lane & (k / R)) == 0 : true;	// k >= R: the bit lives in the lane part of e
+#pragma unroll
+		for (int j = k >> 1; j > 0; j >>= 1)
+		{
+			if (j >= R)
+			{
+				const bool lower = (lane & (j / R)) == 0;
+				const bool keep_min = lower == lane_up;
+#pragma unroll
+				for (int r = 0; r < R; r++)
+				{
+					const uint32_t t = __shfl_xor_sync (0xffffffffu, a[r], j / R);
+					a[r] = keep_min ? min (a[r], t) : max (a[r], t);
+				}
+			}
+			else
+			{
+#pragma unroll
+				for (int r = 0; r < R; r++)
+					if ((r & j) == 0)
+					{
+						const bool up = k >= R ? lane_up : (r & k) == 0;
+						const uint32_t x = a[r], y = a[r | j];
+						const uint32_t mn = min (x, y), mx = max (x, y);
+						a[r] = up ? mn : mx;
+						a[r | j] = up ? mx : mn;
+					}
+			}
+		}
+	}
+	if (R >= 4)
+	{
+		uint4* d4 = reinterpret_cast<uint4*> (srt + lane * R);	// 16-byte aligned: srt is, and R is a multiple of 4
+#pragma unroll
+		for (int r = 0; r + 3 < R; r += 4)
+			d4[r >> 2] = make_uint4 (a[r], a[r + 1], a[r + 2], a[r + 3]);
+	}
+	else
+	{
+#pragma unroll
+		for (int r = 0; r < R; r++)
+			srt[lane * R + r] = a[r];
+	}
+	__syncwarp();
+}
+#endif
+
+// ascending sort of npad keys (power of two, >= 64 for a warp-wide context) in shared memory
+NYX_D void sort_keys (const Cta& c, uint32_t* a, uint32_t npad)
+{
+#if NYX_DEVICE_BUILD
+	if (c.wmode && npad >= 64 && npad <= 1024)
+	{
+		switch (npad)
+		{
+		case 64: warp_sort_regs<2> (a, c.tid); break;
+		case 128: warp_sort_regs<4> (a, c.tid); break;
+		case 256: warp_sort_regs<8> (a, c.tid); break;
+		case 512: warp_sort_regs<16> (a, c.tid); break;
+		default: warp_sort_regs<32> (a, c.tid); break;
+		}
+		return;
+	}
+#endif
+	bitonic_sort (c, a, npad);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Tile materialisation: the ROI's AABB read straight from the resident slide (reference:
 // ImageMatrix::calculate_from_pixelcloud, image_matrix.h:284-304 -- 0 outside the ROI).
@@ -473,6 +561,36 @@ NYX_D void load_tile (const Cta& c, const ImageView& im, const RoiRec& r, const 
 		if (v) code |= CELL_NZ;
 		if (in) code |= CELL_IN;
 		cell[i] = code;
+	}
+}
+
+// 16-bit code of the binned-tile store: level in the low 14 bits, CELL_IN -> bit 14, CELL_NZ -> bit 15
+constexpr uint32_t TILE16_LEVEL = 0x3FFFu;
+NYX_HD uint32_t tile16_encode (uint32_t cellcode)
+{
+	return (cellcode & TILE16_LEVEL) | ((cellcode >> 16) & 0xC000u);
+}
+NYX_HD uint32_t tile16_decode (uint32_t code16)
+{
+	return (code16 & TILE16_LEVEL) | ((code16 & 0xC000u) << 16);
+}
+// words of the shared-memory tile of a class (room for the 8-cell padding of a stored tile)
+NYX_HD size_t tile_words (uint32_t maxcells)
+{
+	return ((size_t)maxcells + 7) & ~(size_t)7;
+}
+
+// tile from the binned-tile store: coalesced 32-bit loads of two codes each (the slot is padded to 8 cells and 16-byte
+// aligned; cell[] has tile_words() room)
+NYX_D void load_tile_store (const Cta& c, const uint16_t* slot, int ncell, uint32_t* cell)
+{
+	const uint32_t* s2 = (const uint32_t*)slot;
+	const int n2 = (ncell + 1) >> 1;
+	for (int k = c.tid; k < n2; k += c.nthr)
+	{
+		const uint32_t u = s2[k];
+		cell[2 * k] = tile16_decode (u & 0xFFFFu);
+		cell[2 * k + 1] = tile16_decode (u >> 16);
 	}
 }
 

@@ -239,6 +239,26 @@ def test_label_table_growth_and_limit(eng64):
         eng64.featurize(I, L)
 
 
+@pytest.mark.parametrize("ibsi", [False, True])
+def test_tile_store_and_direct_binning_give_identical_tables(ibsi):
+    """K2's binned-tile store (16-bit codes read back by the family kernels) vs binning straight from the slide."""
+    from nyxus_b200 import synth
+    I, L = synth.random_rois(300, 257, 60, seed=33)
+    if ibsi:
+        I = np.minimum(I, 200)
+    e = _engine(ibsi=ibsi)
+    try:
+        a, _ = e.featurize(I, L)
+        mats = {f: e.debug_matrix(int(a[3, 0]), f)[0] for f in tu.FAMILIES}
+        e.set_param("tile_store", 0)
+        b, _ = e.featurize(I, L)
+        assert np.array_equal(a, b)
+        for f in tu.FAMILIES:
+            assert e.debug_matrix(int(a[3, 0]), f)[0] == mats[f], f
+    finally:
+        e.close()
+
+
 def test_runs_are_bitwise_deterministic(eng64):
     from nyxus_b200 import synth
     I, L = synth.blob_slide(512, 512, 31, 7, 12, seed=5, jitter=0)
