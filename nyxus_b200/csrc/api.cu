@@ -97,10 +97,16 @@ struct nyxb200_ctx
 	std::string err;
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t ev[NYXB200_NSTAGES + 2];		// stage begin
-	cudaEvent_t ev_end[NYXB200_NSTAGES + 2];	// stage end
-	bool ev_used[NYXB200_NSTAGES + 2];
-	bool ev_end_used[NYXB200_NSTAGES + 2];
+	// stage begin / end events, one set per ROI batch (stage times are summed over the batches)
+	static constexpr int NEV = NYXB200_NSTAGES + 2;
+	cudaEvent_t ev[NB_MAX * NEV];
+	cudaEvent_t ev_end[NB_MAX * NEV];
+	bool ev_used[NB_MAX * NEV];
+	bool ev_end_used[NB_MAX * NEV];
+	int cur_b = 0;			// batch whose event set stage_begin / stage_end record into
+	int roi_batches = 0;		// 0 = automatic
+	cudaStream_t copy_stream = nullptr;	// D2H of a finished batch's rows
+	cudaEvent_t ev_sel;
 	// the eight families are independent once the ROI records exist: each runs on its own stream (fork/join by events)
 	// so their low-occupancy, issue-bound kernels share the SMs; `concurrent = 0` serialises them (per-stage timing)
 	static constexpr int NFSTREAM = 8;
@@ -150,7 +156,8 @@ struct nyxb200_ctx
 	// state of the last processed image (for the debug hooks)
 	ImageView last_im {};
 	SlideInfo last_info {};
-	uint32_t tbase[NCLASS + 2] {}, abase[NACLASS + 2] {};
+	uint32_t tbase[NTK] {}, abase[NAK] {};	// list offsets per (batch, class) key
+	uint32_t giant_tbase = 0, giant_tcount = 0, giant_abase = 0, giant_acount = 0;	// oversize ROIs of all batches (contiguous)
 	std::vector<RoiRec> h_rois;
 	bool h_rois_valid = false;
 
@@ -206,15 +213,6 @@ void rebuild_selection (nyxb200_ctx* ctx)
 	}
 	ctx->sel_dirty = true;
 }
-
-struct Timer
-{
-	nyxb200_ctx* ctx;
-	void begin (int st)
-	{
-		cudaEventRecord (ctx->ev[st], ctx->stream);
-	}
-};
 
 } // namespace
 
@@ -297,6 +295,8 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out)
 		cudaEventCreate (&ev);
 	for (auto& fs : ctx->fstream)
 		cudaStreamCreateWithFlags (&fs, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags (&ctx->copy_stream, cudaStreamNonBlocking);
+	cudaEventCreateWithFlags (&ctx->ev_sel, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&ctx->ev_fork, cudaEventDisableTiming);
 	for (auto& ev : ctx->ev_join)
 		cudaEventCreateWithFlags (&ev, cudaEventDisableTiming);
@@ -319,7 +319,7 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	ctx->g_cell.release(); ctx->g_cell2.release(); ctx->g_auxA.release(); ctx->g_auxB.release(); ctx->g_auxC.release(); ctx->g_mat.release();
 	ctx->g_hcnts.release(); ctx->g_flags.release(); ctx->g_idx.release(); ctx->g_acc.release(); ctx->g_hkeys.release(); ctx->g_part.release();
 	ctx->g_recs.release();
-	ctx->d_rowoff.release(); ctx->d_dbg.release(); ctx->d_dbgf.release();
+	ctx->d_rowoff.release(); ctx->d_dbg.release(); ctx->d_dbgf.release(); ctx->d_blkcells.release(); ctx->d_tiles.release();
 	if (ctx->h_out)
 		cudaFreeHost (ctx->h_out);
 	for (auto& ev : ctx->ev)
@@ -329,8 +329,10 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	for (auto& ev : ctx->ev_join)
 		cudaEventDestroy (ev);
 	cudaEventDestroy (ctx->ev_fork);
+	cudaEventDestroy (ctx->ev_sel);
 	for (auto& fs : ctx->fstream)
 		cudaStreamDestroy (fs);
+	cudaStreamDestroy (ctx->copy_stream);
 	cudaStreamDestroy (ctx->stream);
 	delete ctx;
 }
@@ -415,6 +417,12 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 		ctx->st.soft_nan = value;
 	else if (!strcmp (key, "concurrent_families"))	// measurement knob: 0 = one family after the other (clean per-stage times)
 		ctx->concurrent = iv != 0;
+	else if (!strcmp (key, "roi_batches"))			// 0 = automatic, else 1..NB_MAX
+	{
+		if (iv < 0 || iv > NB_MAX)
+			return fail (ctx, NYXB200_EINVAL, "roi_batches must be in 0..%d", NB_MAX);
+		ctx->roi_batches = iv;
+	}
 	else if (!strcmp (key, "tile_store"))			// test knob: 0 = family kernels bin straight from the slide
 		ctx->use_tile_store = iv != 0;
 	else if (!strcmp (key, "3glcm/greydepth"))		// env_metaparams.cpp:109-120
@@ -1006,18 +1014,18 @@ int process_giant_rois (nyxb200_ctx* ctx, const ImageView& im, const SlideInfo& 
 	std::vector<RoiRec> recs;
 	std::vector<uint32_t> idx;
 	const int tex_mask = ctx->fam_mask & ~(1 << FAM_INT);
-	if (tex_mask && info.class_count[NCLASS])
+	if (tex_mask && ctx->giant_tcount)
 	{
-		if (int rc = fetch_class_rois (ctx, ctx->d_tlist.p + ctx->tbase[NCLASS], info.class_count[NCLASS], recs, idx))
+		if (int rc = fetch_class_rois (ctx, ctx->d_tlist.p + ctx->giant_tbase, ctx->giant_tcount, recs, idx))
 			return rc;
 		for (size_t k = 0; k < recs.size(); k++)
 			if (int rc = giant_texture_roi (ctx, im, recs[k], prm, tex_mask, ctx->d_full.p + (size_t)idx[k] * ncol_all, nullptr))
 				return rc;
 		ctx->giant_rois += (int64_t)recs.size();
 	}
-	if ((ctx->fam_mask & (1 << FAM_INT)) && info.aclass_count[NACLASS])
+	if ((ctx->fam_mask & (1 << FAM_INT)) && ctx->giant_acount)
 	{
-		if (int rc = fetch_class_rois (ctx, ctx->d_alist.p + ctx->abase[NACLASS], info.aclass_count[NACLASS], recs, idx))
+		if (int rc = fetch_class_rois (ctx, ctx->d_alist.p + ctx->giant_abase, ctx->giant_acount, recs, idx))
 			return rc;
 		for (size_t k = 0; k < recs.size(); k++)
 			if (int rc = giant_intensity_roi (ctx, im, recs[k], prm, ctx->d_full.p + (size_t)idx[k] * ncol_all))
@@ -1029,8 +1037,9 @@ int process_giant_rois (nyxb200_ctx* ctx, const ImageView& im, const SlideInfo& 
 // stage st runs from this event to its stage_end (or, on the main stream, to the next stage's begin)
 void stage_end (nyxb200_ctx* ctx, int st, cudaStream_t s = nullptr)
 {
-	cudaEventRecord (ctx->ev_end[st], s ? s : ctx->stream);
-	ctx->ev_end_used[st] = true;
+	const int e = ctx->cur_b * nyxb200_ctx::NEV + st;
+	cudaEventRecord (ctx->ev_end[e], s ? s : ctx->stream);
+	ctx->ev_end_used[e] = true;
 	if (!s)
 		ctx->open_stage = -1;
 }
@@ -1038,8 +1047,9 @@ void stage_begin (nyxb200_ctx* ctx, int st, cudaStream_t s = nullptr)
 {
 	if (!s && ctx->open_stage >= 0)		// main-stream stages are back to back
 		stage_end (ctx, ctx->open_stage);
-	cudaEventRecord (ctx->ev[st], s ? s : ctx->stream);
-	ctx->ev_used[st] = true;
+	const int e = ctx->cur_b * nyxb200_ctx::NEV + st;
+	cudaEventRecord (ctx->ev[e], s ? s : ctx->stream);
+	ctx->ev_used[e] = true;
 	if (!s)
 		ctx->open_stage = st;
 }
@@ -1100,6 +1110,7 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	const int ncol_all = d3 ? NCOL3_ALL : NCOL_ALL;
 	Params prm = make_params (ctx);
 	cudaStream_t s = ctx->stream;
+	ctx->cur_b = 0;
 	CU (ctx->d_info.reserve (1));
 	SlideInfo info;
 
@@ -1176,42 +1187,68 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	if (ctx->st.ibsi && info.max_inten > CELL_LEVEL)
 		return fail (ctx, NYXB200_EUNSUPPORTED, "IBSI mode needs intensities < 2^24 (max %u)", info.max_inten);
 
-	// ---- ROI records + class lists
+	// ---- ROI batches: rows of batch b travel to the host while batch b+1 computes (the reference also walks the ROIs in
+	// batches, phase2_2d.cpp:427-465 -- there to bound RAM, here to hide the table's D2H copy)
+	int nb = ctx->roi_batches > 0 ? ctx->roi_batches : (int)(nroi / 16384);
+	nb = std::max (1, std::min (nb, NB_MAX));
+	const uint32_t bs = (nroi + nb - 1) / nb;		// ROIs per batch (index ranges of the label-ordered ROI array)
+	nb = (int)((nroi + bs - 1) / bs);
+
+	// ---- ROI records + class lists per (batch, class)
 	CU (ctx->d_rois.reserve (nroi));
-	CU (ctx->d_classslot.reserve ((size_t)nroi * 2));
+	CU (ctx->d_classslot.reserve ((size_t)nroi * 4));
 	CU (ctx->d_tlist.reserve (nroi));
 	CU (ctx->d_alist.reserve (nroi));
-	CU (ctx->d_bases.reserve (NCLASS + NACLASS + 4));
+	CU (ctx->d_bases.reserve (NTK + NAK));
 	{
 		const uint32_t nblk = (ctx->stats_cap + CB - 1) / CB;
 		k_compact_write<<<nblk, CB, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ctx->d_blkcnt.p, ctx->d_blkarea.p,
-			ctx->d_blkcells.p, ctx->d_rois.p, ctx->d_classslot.p, d3 ? ctx->d_ztab.p : nullptr);
+			ctx->d_blkcells.p, ctx->d_rois.p, ctx->d_classslot.p, bs, d3 ? ctx->d_ztab.p : nullptr);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		CU (cudaMemcpyAsync (&info, ctx->d_info.p, sizeof (info), cudaMemcpyDeviceToHost, s));
 		CU (cudaStreamSynchronize (s));
-		uint32_t bases[NCLASS + NACLASS + 4];
+		// list layout: the shared-memory classes batch-major, then the oversize class of every batch at the end (one
+		// contiguous list for the giant path)
+		uint32_t bases[NTK + NAK];
 		uint32_t acc = 0;
-		for (int c = 0; c <= NCLASS; c++)
+		for (int bb = 0; bb < NB_MAX; bb++)
+			for (int c = 0; c < NCLASS; c++)
+			{
+				ctx->tbase[bb * (NCLASS + 1) + c] = acc;
+				acc += info.class_count[bb * (NCLASS + 1) + c];
+			}
+		ctx->giant_tbase = acc;
+		for (int bb = 0; bb < NB_MAX; bb++)
 		{
-			ctx->tbase[c] = bases[c] = acc;
-			acc += info.class_count[c];
+			ctx->tbase[bb * (NCLASS + 1) + NCLASS] = acc;
+			acc += info.class_count[bb * (NCLASS + 1) + NCLASS];
 		}
-		ctx->tbase[NCLASS + 1] = acc;
+		ctx->giant_tcount = acc - ctx->giant_tbase;
 		acc = 0;
-		for (int c = 0; c <= NACLASS; c++)
+		for (int bb = 0; bb < NB_MAX; bb++)
+			for (int c = 0; c < NACLASS; c++)
+			{
+				ctx->abase[bb * (NACLASS + 1) + c] = acc;
+				acc += info.aclass_count[bb * (NACLASS + 1) + c];
+			}
+		ctx->giant_abase = acc;
+		for (int bb = 0; bb < NB_MAX; bb++)
 		{
-			ctx->abase[c] = bases[NCLASS + 1 + c] = acc;
-			acc += info.aclass_count[c];
+			ctx->abase[bb * (NACLASS + 1) + NACLASS] = acc;
+			acc += info.aclass_count[bb * (NACLASS + 1) + NACLASS];
 		}
-		ctx->abase[NACLASS + 1] = acc;
-		CU (cudaMemcpyAsync (ctx->d_bases.p, bases, sizeof (uint32_t) * (NCLASS + NACLASS + 2), cudaMemcpyHostToDevice, s));
-		k_fill_class_lists<<<(nroi + 255) / 256, 256, 0, s>>> (ctx->d_classslot.p, nroi, ctx->d_bases.p, ctx->d_bases.p + NCLASS + 1,
+		ctx->giant_acount = acc - ctx->giant_abase;
+		memcpy (bases, ctx->tbase, sizeof (uint32_t) * NTK);
+		memcpy (bases + NTK, ctx->abase, sizeof (uint32_t) * NAK);
+		CU (cudaMemcpyAsync (ctx->d_bases.p, bases, sizeof (bases), cudaMemcpyHostToDevice, s));
+		k_fill_class_lists<<<(nroi + 255) / 256, 256, 0, s>>> (ctx->d_classslot.p, nroi, ctx->d_bases.p, ctx->d_bases.p + NTK,
 			ctx->d_tlist.p, ctx->d_alist.p);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 	}
 	ctx->last_info = info;
+	const bool any_giant = !d3 && (ctx->giant_tcount || ctx->giant_acount);
 
 	// ---- canonical table
 	CU (ctx->d_full.reserve ((size_t)nroi * ncol_all));
@@ -1219,143 +1256,30 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	if (d3)	// 3d_intensity.cpp:56-61: ROI range over the scanned range of the labelled voxels (slideprops.cpp:305-327)
 		prm.covered_den = (double)info.max_inten - (double)(~info.inv_min_inten);
 
-	// ---- K2: CSR cloud + binned-tile store in one pass over the ROIs' AABBs (main stream: every family depends on it)
 	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : ctx->st.coarse_gray_depth;
 	DebugOut nodbg { nullptr, nullptr, nullptr };
 	ImageView imf = im;		// the view the family kernels get (with the tile store when it is used)
-	stage_begin (ctx, ST_PACK);
+	const bool want_cloud = (ctx->fam_mask & (1 << FAM_INT)) != 0;
+	const bool want_tex = !d3 && (ctx->fam_mask & ~(1 << FAM_INT)) != 0;
+	// 16-bit tile codes hold 14-bit levels: MATLAB binning up to 16383 levels, IBSI (identity) up to that intensity
+	const bool tiles = want_tex && ctx->use_tile_store && info.n_tile_cells > 0 && (uint32_t)Lmax <= TILE16_LEVEL
+		&& (uint32_t)ctx->st.coarse_gray_depth <= TILE16_LEVEL;
+	const bool tiles_b = tiles && (ctx->fam_mask & (1 << FAM_NGLDM));
+	if (want_cloud)
+		CU (ctx->d_cloud.reserve ((size_t)info.n_fg + 4));
+	if (tiles)
 	{
-		const bool want_cloud = (ctx->fam_mask & (1 << FAM_INT)) != 0;
-		const bool want_tex = !d3 && (ctx->fam_mask & ~(1 << FAM_INT)) != 0;
-		// 16-bit codes hold 14-bit levels: MATLAB binning up to 16383 levels, IBSI (identity) up to that intensity
-		const bool tiles = want_tex && ctx->use_tile_store && info.n_tile_cells > 0 && (uint32_t)Lmax <= TILE16_LEVEL
-			&& (uint32_t)ctx->st.coarse_gray_depth <= TILE16_LEVEL;
-		const bool tiles_b = tiles && (ctx->fam_mask & (1 << FAM_NGLDM));
-		if (want_cloud)
-			CU (ctx->d_cloud.reserve ((size_t)info.n_fg + 4));
-		if (tiles)
-		{
-			CU (ctx->d_tiles.reserve ((size_t)info.n_tile_cells * (tiles_b ? 2 : 1)));
-			imf.tileA = ctx->d_tiles.p;
-			imf.tileB = tiles_b ? ctx->d_tiles.p + info.n_tile_cells : nullptr;
-		}
-		const uint32_t nsmall = ctx->tbase[NCLASS];
-		if (nsmall && (want_cloud || tiles))
-		{
-			if (d3)
-				k_pack_cloud<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p, nsmall, ctx->d_cloud.p);
-			else
-				k_pack_tiles<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p, nsmall, prm,
-					want_cloud ? ctx->d_cloud.p : nullptr, (uint16_t*)imf.tileA, (uint16_t*)imf.tileB);
-			CU (cudaGetLastError());
-			ctx->counts[0]++;
-		}
-		const uint32_t nlarge = info.class_count[NCLASS];
-		if (nlarge && want_cloud)
-		{
-			const int grid = (int)std::min<uint32_t> (nlarge, (uint32_t)ctx->sm_count * 4);
-			const size_t stride = (size_t)im.H * (size_t)im.D + 2;
-			CU (ctx->d_rowoff.reserve ((size_t)grid * stride));
-			k_pack_cloud_large<<<grid, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->tbase[NCLASS], nlarge, ctx->d_cloud.p,
-				ctx->d_rowoff.p, stride);
-			CU (cudaGetLastError());
-			ctx->counts[0]++;
-		}
+		CU (ctx->d_tiles.reserve ((size_t)info.n_tile_cells * (tiles_b ? 2 : 1)));
+		imf.tileA = ctx->d_tiles.p;
+		imf.tileB = tiles_b ? ctx->d_tiles.p + info.n_tile_cells : nullptr;
 	}
 	ctx->last_im = imf;
+	if (d3 && (ctx->fam_mask & ~(1 << FAM3_INT)))
+		for (int bb = 0; bb < nb; bb++)
+			if (info.class_count[bb * (NCLASS + 1) + NCLASS])
+				return fail (ctx, NYXB200_EUNSUPPORTED, "a 3D ROI whose bounding cube exceeds 40000 voxels needs the large-ROI texture path (not in this build)");
 
-	// ---- families: fork onto the family streams (slot 0 = first-order, then one slot per texture family)
-	stage_begin (ctx, ST_FAMILIES);
-	if (int rc = fork_families (ctx))
-		return rc;
-	use_family_stream (ctx, 0);
-	stage_begin (ctx, ST_INT, ctx->ls);
-	if (ctx->fam_mask & (1 << FAM_INT))
-	{
-		for (int c = 0; c < NACLASS; c++)
-			if (int rc = launch_intensity (ctx, ctx->d_alist.p + ctx->abase[c], info.aclass_count[c], prm, info.aclass_maxarea[c], ctx->d_full.p, ncol_all))
-				return rc;
-		// clouds above 32768 pixels: 3D keeps the CTA-per-ROI kernel (global scratch); 2D goes through the giant path below
-		if (d3 && info.aclass_count[NACLASS])
-			if (int rc = launch_intensity (ctx, ctx->d_alist.p + ctx->abase[NACLASS], info.aclass_count[NACLASS], prm, info.aclass_maxarea[NACLASS], ctx->d_full.p, ncol_all))
-				return rc;
-	}
-	stage_end (ctx, ST_INT, ctx->ls);
-	static const int fam_stage[FAM_COUNT] = { ST_INT, ST_GLCM, ST_GLRLM, ST_GLDZM, ST_GLSZM, ST_GLDM, ST_NGLDM, ST_NGTDM };
-	if (d3)
-	{
-		if ((ctx->fam_mask & ~(1 << FAM3_INT)) && info.class_count[NCLASS])
-			return fail (ctx, NYXB200_EUNSUPPORTED, "a 3D ROI whose bounding cube exceeds 40000 voxels needs the large-ROI texture path (not in this build)");
-		const int maxI = (int)std::max<uint32_t> (info.max_inten, 1u);
-		for (int fam = FAM3_GLCM; fam < FAM3_COUNT; fam++)
-		{
-			static const int st3[FAM3_COUNT] = { ST_INT, ST_GLCM, ST_GLSZM, ST_NGTDM };
-			if (!(ctx->fam_mask & (1 << fam)))
-				continue;
-			use_family_stream (ctx, fam);
-			stage_begin (ctx, st3[fam], ctx->ls);
-			// grey-binning info per family (3d_glcm.cpp:53-55, 3d_glszm.cpp:490-492, 3d_ngtdm.cpp:195-197); 0 = no binning
-			int g = fam == FAM3_GLCM ? ctx->st.coarse_gray_depth : fam == FAM3_GLSZM ? ctx->glszm3_greydepth : ctx->ngtdm3_greydepth;
-			if (ctx->st.ibsi)
-				g = 0;
-			int Lm = g > 0 ? g : maxI;
-			if (fam == FAM3_NGTDM && ctx->ngtdm3_radius == 0)
-				Lm = 1;		// nothing is accumulated (see ngtdm3d_body)
-			for (int c = 0; c < NCLASS; c++)
-			{
-				const uint32_t n = info.class_count[c], mc = info.class_maxcells[c];
-				const uint32_t* lst = ctx->d_tlist.p + ctx->tbase[c];
-				int rc = 0;
-				if (fam == FAM3_GLCM)
-				{
-					if (g == 0 && Lm > 4096)
-						return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLCM without grey binning needs intensities <= 4096 (max %d)", Lm);
-					rc = mc < 32768 ? launch_family3_t<FAM3_GLCM, true> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
-						: launch_family3_t<FAM3_GLCM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
-				}
-				else if (fam == FAM3_GLSZM)
-				{
-					if (Lm > 65535)
-						return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLSZM needs grey levels < 65536 (max %d)", Lm);
-					rc = launch_family3_t<FAM3_GLSZM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
-				}
-				else
-				{
-					if ((unsigned long long)(Lm + 2) * NGTDM3_NDMAX * (unsigned long long)mc >= 0xFFFFFFFFull || Lm + 2 > 65535)
-						return fail (ctx, NYXB200_EUNSUPPORTED, "3D NGTDM: level range %d too large for the exact integer accumulators; set 3ngtdm/greydepth", Lm);
-					rc = launch_family3_t<FAM3_NGTDM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
-				}
-				if (rc)
-					return rc;
-			}
-			stage_end (ctx, st3[fam], ctx->ls);
-		}
-	}
-	else
-	for (int fam = FAM_GLCM; fam < FAM_COUNT; fam++)
-	{
-		if (!(ctx->fam_mask & (1 << fam)))
-			continue;
-		use_family_stream (ctx, fam);
-		stage_begin (ctx, fam_stage[fam], ctx->ls);
-		for (int c = 0; c < NCLASS; c++)
-			if (int rc = launch_family (ctx, fam, imf, ctx->d_tlist.p + ctx->tbase[c], info.class_count[c], prm, Lmax,
-				info.class_maxcells[c], (int)info.class_maxwh[c], ctx->d_full.p, nodbg))
-				return rc;
-		stage_end (ctx, fam_stage[fam], ctx->ls);
-	}
-	if (int rc = join_families (ctx))
-		return rc;
-	// ---- ROIs too large for the shared-memory classes: one at a time, whole-GPU kernels (giant.cuh)
-	if (!d3 && (info.class_count[NCLASS] || info.aclass_count[NACLASS]))
-	{
-		stage_begin (ctx, ST_GIANT);
-		if (int rc = process_giant_rois (ctx, im, info, prm, ncol_all))
-			return rc;
-	}
-
-	// ---- select + D2H
-	stage_begin (ctx, ST_SELECT);
+	// ---- output buffers
 	const int nsel = (int)ctx->sel_cols.size();
 	if (ctx->sel_dirty)
 	{
@@ -1364,20 +1288,178 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 			CU (cudaMemcpyAsync (ctx->d_sel.p, ctx->sel_cols.data(), sizeof (int) * nsel, cudaMemcpyHostToDevice, s));
 		ctx->sel_dirty = false;
 	}
-	const size_t outn = (size_t)nroi * (nsel + 2);
+	const size_t rowlen = (size_t)nsel + 2, outn = (size_t)nroi * rowlen;
 	CU (ctx->d_sel_out.reserve (outn));
-	{
-		int grid = (int)std::min<size_t> ((outn + 255) / 256, (size_t)ctx->sm_count * 16);
-		k_select_columns<<<grid, 256, 0, s>>> (ctx->d_full.p, ncol_all, ctx->d_rois.p, nroi, ctx->d_sel.p, nsel, ctx->st.soft_nan, 0.0, ctx->d_sel_out.p);
-		CU (cudaGetLastError());
-		ctx->counts[0]++;
-	}
-	stage_begin (ctx, ST_D2H);
 	if (int rc = reserve_pinned_out (ctx, ctx->h_out_used + outn))
 		return rc;
-	CU (cudaMemcpyAsync (ctx->h_out + ctx->h_out_used, ctx->d_sel_out.p, outn * sizeof (double), cudaMemcpyDeviceToHost, s));
+	double* const h_dst = ctx->h_out + ctx->h_out_used;
 	ctx->h_out_used += outn;
-	stage_begin (ctx, ST_TOTAL);	// closes ST_D2H; ev[ST_TOTAL] marks the end of the slide
+	auto select_and_copy = [&](uint32_t r0, uint32_t r1, bool overlap) -> int
+	{
+		// rows [r0, r1): gather the enabled columns on the main stream, copy them on the copy stream (overlap) or in line
+		const size_t n = (size_t)(r1 - r0) * rowlen;
+		stage_begin (ctx, ST_SELECT);
+		const int grid = (int)std::min<size_t> ((n + 255) / 256, (size_t)ctx->sm_count * 16);
+		k_select_columns<<<grid, 256, 0, s>>> (ctx->d_full.p + (size_t)r0 * ncol_all, ncol_all, ctx->d_rois.p + r0, r1 - r0, ctx->d_sel.p, nsel,
+			ctx->st.soft_nan, 0.0, ctx->d_sel_out.p + (size_t)r0 * rowlen);
+		CU (cudaGetLastError());
+		ctx->counts[0]++;
+		stage_end (ctx, ST_SELECT);
+		cudaStream_t cs = overlap ? ctx->copy_stream : s;
+		if (overlap)
+		{
+			CU (cudaEventRecord (ctx->ev_sel, s));
+			CU (cudaStreamWaitEvent (cs, ctx->ev_sel, 0));
+		}
+		stage_begin (ctx, ST_D2H, cs);
+		CU (cudaMemcpyAsync (h_dst + (size_t)r0 * rowlen, ctx->d_sel_out.p + (size_t)r0 * rowlen, n * sizeof (double), cudaMemcpyDeviceToHost, cs));
+		stage_end (ctx, ST_D2H, cs);
+		return 0;
+	};
+
+	static const int fam_stage[FAM_COUNT] = { ST_INT, ST_GLCM, ST_GLRLM, ST_GLDZM, ST_GLSZM, ST_GLDM, ST_NGLDM, ST_NGTDM };
+	for (int bb = 0; bb < nb; bb++)
+	{
+		ctx->cur_b = bb;
+		const uint32_t* ccount = info.class_count + bb * (NCLASS + 1);
+		const uint32_t* cmaxcells = info.class_maxcells + bb * (NCLASS + 1);
+		const uint32_t* cmaxwh = info.class_maxwh + bb * (NCLASS + 1);
+		const uint32_t* acount = info.aclass_count + bb * (NACLASS + 1);
+		const uint32_t* amaxarea = info.aclass_maxarea + bb * (NACLASS + 1);
+		const uint32_t* tb = ctx->tbase + bb * (NCLASS + 1);
+		const uint32_t* ab = ctx->abase + bb * (NACLASS + 1);
+
+		// ---- K2: CSR cloud + binned-tile store in one pass over the ROIs' AABBs (main stream: every family depends on it)
+		stage_begin (ctx, ST_PACK);
+		{
+			uint32_t nsmall = 0;
+			for (int c = 0; c < NCLASS; c++)
+				nsmall += ccount[c];
+			if (nsmall && (want_cloud || tiles))
+			{
+				if (d3)
+					k_pack_cloud<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[0], nsmall, ctx->d_cloud.p);
+				else
+					k_pack_tiles<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[0], nsmall, prm,
+						want_cloud ? ctx->d_cloud.p : nullptr, (uint16_t*)imf.tileA, (uint16_t*)imf.tileB);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+			const uint32_t nlarge = ccount[NCLASS];
+			if (nlarge && want_cloud)
+			{
+				const int grid = (int)std::min<uint32_t> (nlarge, (uint32_t)ctx->sm_count * 4);
+				const size_t stride = (size_t)im.H * (size_t)im.D + 2;
+				CU (ctx->d_rowoff.reserve ((size_t)grid * stride));
+				k_pack_cloud_large<<<grid, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[NCLASS], nlarge, ctx->d_cloud.p,
+					ctx->d_rowoff.p, stride);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+		}
+
+		// ---- families: fork onto the family streams (slot 0 = first-order, then one slot per texture family)
+		stage_begin (ctx, ST_FAMILIES);
+		if (int rc = fork_families (ctx))
+			return rc;
+		use_family_stream (ctx, 0);
+		stage_begin (ctx, ST_INT, ctx->ls);
+		if (want_cloud)
+		{
+			for (int c = 0; c < NACLASS; c++)
+				if (int rc = launch_intensity (ctx, ctx->d_alist.p + ab[c], acount[c], prm, amaxarea[c], ctx->d_full.p, ncol_all))
+					return rc;
+			// clouds above 32768 pixels: 3D keeps the CTA-per-ROI kernel (global scratch); 2D goes through the giant path below
+			if (d3 && acount[NACLASS])
+				if (int rc = launch_intensity (ctx, ctx->d_alist.p + ab[NACLASS], acount[NACLASS], prm, amaxarea[NACLASS], ctx->d_full.p, ncol_all))
+					return rc;
+		}
+		stage_end (ctx, ST_INT, ctx->ls);
+		if (d3)
+		{
+			const int maxI = (int)std::max<uint32_t> (info.max_inten, 1u);
+			for (int fam = FAM3_GLCM; fam < FAM3_COUNT; fam++)
+			{
+				static const int st3[FAM3_COUNT] = { ST_INT, ST_GLCM, ST_GLSZM, ST_NGTDM };
+				if (!(ctx->fam_mask & (1 << fam)))
+					continue;
+				use_family_stream (ctx, fam);
+				stage_begin (ctx, st3[fam], ctx->ls);
+				// grey-binning info per family (3d_glcm.cpp:53-55, 3d_glszm.cpp:490-492, 3d_ngtdm.cpp:195-197); 0 = no binning
+				int g = fam == FAM3_GLCM ? ctx->st.coarse_gray_depth : fam == FAM3_GLSZM ? ctx->glszm3_greydepth : ctx->ngtdm3_greydepth;
+				if (ctx->st.ibsi)
+					g = 0;
+				int Lm = g > 0 ? g : maxI;
+				if (fam == FAM3_NGTDM && ctx->ngtdm3_radius == 0)
+					Lm = 1;		// nothing is accumulated (see ngtdm3d_body)
+				for (int c = 0; c < NCLASS; c++)
+				{
+					const uint32_t n = ccount[c], mc = cmaxcells[c];
+					const uint32_t* lst = ctx->d_tlist.p + tb[c];
+					int rc = 0;
+					if (fam == FAM3_GLCM)
+					{
+						if (g == 0 && Lm > 4096)
+							return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLCM without grey binning needs intensities <= 4096 (max %d)", Lm);
+						rc = mc < 32768 ? launch_family3_t<FAM3_GLCM, true> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
+							: launch_family3_t<FAM3_GLCM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+					}
+					else if (fam == FAM3_GLSZM)
+					{
+						if (Lm > 65535)
+							return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLSZM needs grey levels < 65536 (max %d)", Lm);
+						rc = launch_family3_t<FAM3_GLSZM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+					}
+					else
+					{
+						if ((unsigned long long)(Lm + 2) * NGTDM3_NDMAX * (unsigned long long)mc >= 0xFFFFFFFFull || Lm + 2 > 65535)
+							return fail (ctx, NYXB200_EUNSUPPORTED, "3D NGTDM: level range %d too large for the exact integer accumulators; set 3ngtdm/greydepth", Lm);
+						rc = launch_family3_t<FAM3_NGTDM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+					}
+					if (rc)
+						return rc;
+				}
+				stage_end (ctx, st3[fam], ctx->ls);
+			}
+		}
+		else
+		for (int fam = FAM_GLCM; fam < FAM_COUNT; fam++)
+		{
+			if (!(ctx->fam_mask & (1 << fam)))
+				continue;
+			use_family_stream (ctx, fam);
+			stage_begin (ctx, fam_stage[fam], ctx->ls);
+			for (int c = 0; c < NCLASS; c++)
+				if (int rc = launch_family (ctx, fam, imf, ctx->d_tlist.p + tb[c], ccount[c], prm, Lmax,
+					cmaxcells[c], (int)cmaxwh[c], ctx->d_full.p, nodbg))
+					return rc;
+			stage_end (ctx, fam_stage[fam], ctx->ls);
+		}
+		if (int rc = join_families (ctx))
+			return rc;
+		stage_end (ctx, ST_FAMILIES);
+		// ---- rows of this batch: select + D2H, overlapped with the next batch (deferred when giant ROIs are pending)
+		if (!any_giant)
+			if (int rc = select_and_copy (bb * bs, std::min<uint32_t> (nroi, (bb + 1) * bs), nb > 1))
+				return rc;
+	}
+	// ---- ROIs too large for the shared-memory classes: one at a time, whole-GPU kernels (giant.cuh)
+	if (any_giant)
+	{
+		stage_begin (ctx, ST_GIANT);
+		if (int rc = process_giant_rois (ctx, im, info, prm, ncol_all))
+			return rc;
+		stage_end (ctx, ST_GIANT);
+		if (int rc = select_and_copy (0, nroi, false))
+			return rc;
+	}
+	else if (nb > 1)
+	{
+		CU (cudaEventRecord (ctx->ev_sel, ctx->copy_stream));
+		CU (cudaStreamWaitEvent (s, ctx->ev_sel, 0));
+	}
+	ctx->cur_b = 0;
+	stage_begin (ctx, ST_TOTAL);	// ev[ST_TOTAL] marks the end of the slide
 	ctx->open_stage = -1;
 	CU (cudaStreamSynchronize (s));
 	(void)img_index;
@@ -1386,14 +1468,16 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 
 void collect_timings (nyxb200_ctx* ctx)
 {
-	// every stage has its own begin / end event pair (family stages overlap when they run concurrently);
+	// every stage has its own begin / end event pair per ROI batch (family stages overlap when they run concurrently);
 	// total = first event of the slide to the end-of-slide event on the main stream
-	for (int i = 0; i < NYXB200_NSTAGES; i++)
-	{
-		float ms = 0;
-		if (i != ST_TOTAL && ctx->ev_used[i] && ctx->ev_end_used[i] && cudaEventElapsedTime (&ms, ctx->ev[i], ctx->ev_end[i]) == cudaSuccess)
-			ctx->stage_ms[i] += ms;
-	}
+	for (int b = 0; b < NB_MAX; b++)
+		for (int i = 0; i < NYXB200_NSTAGES; i++)
+		{
+			const int e = b * nyxb200_ctx::NEV + i;
+			float ms = 0;
+			if (i != ST_TOTAL && ctx->ev_used[e] && ctx->ev_end_used[e] && cudaEventElapsedTime (&ms, ctx->ev[e], ctx->ev_end[e]) == cudaSuccess)
+				ctx->stage_ms[i] += ms;
+		}
 	float ms = 0;
 	if (ctx->ev_used[ST_H2D] && ctx->ev_used[ST_TOTAL] && cudaEventElapsedTime (&ms, ctx->ev[ST_H2D], ctx->ev[ST_TOTAL]) == cudaSuccess)
 		ctx->stage_ms[ST_TOTAL] += ms;

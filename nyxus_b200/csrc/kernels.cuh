@@ -29,17 +29,20 @@ struct __align__(32) LabelStat
 // info block shared between device and host (one D2H copy per slide)
 constexpr int NCLASS = 5;		// tile classes by cell count
 constexpr int NACLASS = 5;		// cloud classes by area
+constexpr int NB_MAX = 8;		// ROI batches per slide (rows of batch b are copied to the host while batch b+1 computes)
+constexpr int NTK = NB_MAX * (NCLASS + 1), NAK = NB_MAX * (NACLASS + 1);	// (batch, class) keys
 struct SlideInfo
 {
 	uint32_t max_label;		// largest label value seen by the scan
 	uint32_t n_roi;
 	unsigned long long n_fg;	// foreground pixels = sum of areas
 	uint32_t max_inten;		// largest aux_max over ROIs (IBSI level bound)
-	uint32_t class_count[NCLASS + 1];	// last = oversize
-	uint32_t class_maxcells[NCLASS + 1];
-	uint32_t class_maxwh[NCLASS + 1];
-	uint32_t aclass_count[NACLASS + 1];
-	uint32_t aclass_maxarea[NACLASS + 1];
+	// per (batch, class) key = batch * (NCLASS + 1) + class; the last class of a batch = oversize (giant path)
+	uint32_t class_count[NTK];
+	uint32_t class_maxcells[NTK];
+	uint32_t class_maxwh[NTK];
+	uint32_t aclass_count[NAK];
+	uint32_t aclass_maxarea[NAK];
 	uint32_t inv_min_inten;		// ~(smallest aux_min over ROIs): the slide's foreground minimum (3D COVERED_IMAGE_INTENSITY_RANGE)
 	unsigned long long n_tile_cells;	// cells of the binned-tile store (sum of the padded AABBs of the small-class ROIs)
 };
@@ -408,20 +411,20 @@ __global__ void __launch_bounds__(CB) k_compact_scan (uint32_t* blk_cnt, unsigne
 
 __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uint32_t cap, SlideInfo* info,
 	const uint32_t* blk_cnt, const unsigned long long* blk_area, const unsigned long long* blk_cells, RoiRec* rois,
-	uint32_t* class_slot, const uint2* ztab = nullptr)
+	uint32_t* class_slot, uint32_t batch_rois, const uint2* ztab = nullptr)
 {
 	__shared__ uint32_t sa[33];
 	__shared__ unsigned long long sb[33], sc[33];
 	// per-block class tallies: slots are handed out inside the block first, ONE global atomic per (block, class) after
-	__shared__ uint32_t s_cnt[NCLASS + 1], s_acnt[NACLASS + 1], s_base[NCLASS + 1], s_abase[NACLASS + 1];
-	__shared__ uint32_t s_maxcells[NCLASS + 1], s_maxwh[NCLASS + 1], s_maxarea[NACLASS + 1], s_maxinten, s_invmin;
-	if (threadIdx.x <= NCLASS)
+	__shared__ uint32_t s_cnt[NTK], s_acnt[NAK], s_base[NTK], s_abase[NAK];
+	__shared__ uint32_t s_maxcells[NTK], s_maxwh[NTK], s_maxarea[NAK], s_maxinten, s_invmin;
+	if (threadIdx.x < NTK)
 	{
 		s_cnt[threadIdx.x] = 0;
 		s_maxcells[threadIdx.x] = 0;
 		s_maxwh[threadIdx.x] = 0;
 	}
-	if (threadIdx.x <= NACLASS)
+	if (threadIdx.x < NAK)
 	{
 		s_acnt[threadIdx.x] = 0;
 		s_maxarea[threadIdx.x] = 0;
@@ -477,8 +480,9 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 		rois[idx] = r;
 		const unsigned long long ncell64 = (unsigned long long)r.w * (unsigned long long)r.h * (unsigned long long)r.d;
 		const uint32_t ncell = ncell64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ncell64;
-		tc_ = tile_class (ncell);
-		ac = area_class (r.area);
+		const int batch = (int)(idx / batch_rois);
+		tc_ = batch * (NCLASS + 1) + tile_class (ncell);
+		ac = batch * (NACLASS + 1) + area_class (r.area);
 		tslot = atomicAdd (&s_cnt[tc_], 1u);
 		aslot = atomicAdd (&s_acnt[ac], 1u);
 		atomicMax (&s_maxcells[tc_], ncell);
@@ -488,18 +492,18 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 		atomicMax (&s_invmin, ~r.imin);
 	}
 	__syncthreads();
-	if (threadIdx.x <= NCLASS && s_cnt[threadIdx.x])
+	if (threadIdx.x < NTK && s_cnt[threadIdx.x])
 	{
 		s_base[threadIdx.x] = atomicAdd (&info->class_count[threadIdx.x], s_cnt[threadIdx.x]);
 		atomicMax (&info->class_maxcells[threadIdx.x], s_maxcells[threadIdx.x]);
 		atomicMax (&info->class_maxwh[threadIdx.x], s_maxwh[threadIdx.x]);
 	}
-	if (threadIdx.x >= 32 && threadIdx.x - 32 <= NACLASS && s_acnt[threadIdx.x - 32])
+	if (threadIdx.x >= 64 && threadIdx.x - 64 < NAK && s_acnt[threadIdx.x - 64])
 	{
-		s_abase[threadIdx.x - 32] = atomicAdd (&info->aclass_count[threadIdx.x - 32], s_acnt[threadIdx.x - 32]);
-		atomicMax (&info->aclass_maxarea[threadIdx.x - 32], s_maxarea[threadIdx.x - 32]);
+		s_abase[threadIdx.x - 64] = atomicAdd (&info->aclass_count[threadIdx.x - 64], s_acnt[threadIdx.x - 64]);
+		atomicMax (&info->aclass_maxarea[threadIdx.x - 64], s_maxarea[threadIdx.x - 64]);
 	}
-	if (threadIdx.x == 64)
+	if (threadIdx.x == 128)
 	{
 		atomicMax (&info->max_inten, s_maxinten);
 		atomicMax (&info->inv_min_inten, s_invmin);
@@ -507,8 +511,7 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 	__syncthreads();
 	if (present)
 	{
-		class_slot[idx * 2] = ((uint32_t)tc_ << 28) | (s_base[tc_] + tslot);
-		class_slot[idx * 2 + 1] = ((uint32_t)ac << 28) | (s_abase[ac] + aslot);
+		reinterpret_cast<uint4*> (class_slot)[idx] = make_uint4 ((uint32_t)tc_, s_base[tc_] + tslot, (uint32_t)ac, s_abase[ac] + aslot);
 	}
 }
 
@@ -519,9 +522,9 @@ __global__ void k_fill_class_lists (const uint32_t* class_slot, uint32_t n, cons
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n)
 		return;
-	uint32_t t = class_slot[i * 2], a = class_slot[i * 2 + 1];
-	tlist[tbase[t >> 28] + (t & 0x0FFFFFFFu)] = i;
-	alist[abase[a >> 28] + (a & 0x0FFFFFFFu)] = i;
+	const uint4 k = reinterpret_cast<const uint4*> (class_slot)[i];	// (tile key, slot, area key, slot)
+	tlist[tbase[k.x] + k.y] = i;
+	alist[abase[k.z] + k.w] = i;
 }
 
 // ------------------------------------------------------------------------------------------------

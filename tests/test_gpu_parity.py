@@ -259,6 +259,24 @@ def test_tile_store_and_direct_binning_give_identical_tables(ibsi):
         e.close()
 
 
+@pytest.mark.parametrize("nb", [2, 5, 8])
+def test_roi_batches_give_identical_tables(nb):
+    """Rows are produced batch by batch (D2H of batch b overlaps batch b+1); the table must not depend on the split."""
+    from nyxus_b200 import synth
+    I, L = synth.random_rois(300, 257, 60, seed=34)
+    I2, L2 = synth.random_rois(300, 257, 7, seed=35)
+    e = _engine()
+    try:
+        e.set_param("roi_batches", 1)
+        a, ia = e.featurize(np.stack([I, I2]), np.stack([L, L2]))
+        e.set_param("roi_batches", nb)
+        b, ib = e.featurize(np.stack([I, I2]), np.stack([L, L2]))
+        assert np.array_equal(a, b) and np.array_equal(ia, ib)
+        assert np.all(np.diff(a[ia == 0, 0]) > 0) and np.all(np.diff(a[ia == 1, 0]) > 0)
+    finally:
+        e.close()
+
+
 def test_runs_are_bitwise_deterministic(eng64):
     from nyxus_b200 import synth
     I, L = synth.blob_slide(512, 512, 31, 7, 12, seed=5, jitter=0)
