@@ -104,6 +104,16 @@ int nyxb200_featurize_3d_u16 (nyxb200_ctx* ctx, const uint16_t* inten, const uin
 	int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
 int nyxb200_featurize_3d_device (nyxb200_ctx* ctx, const void* inten, int inten_is_u16, const uint32_t* label,
 	int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+/* A LIST of slides / volumes of one shape, each with its own pointer (host when on_device == 0, else device): replaces
+ * the slide loop of processMontage (workflow_pythonapi.cpp:104-190) and of the file-list workflows
+ * (featurize_fname_lists_imp / featurize_fname_lists_3D_imp, new_bindings_py.cpp:647-856) after decoding.  Host slides are
+ * pipelined: slide k+1 is copied to the device (second buffer, own stream) while slide k computes and the rows of
+ * slide k-1 travel back, so a multi-slide job runs at max(upload, compute) per slide instead of their sum.  The
+ * contiguous-stack entry points above take the same pipeline when n_img > 1. */
+int nyxb200_featurize_2d_list (nyxb200_ctx* ctx, const void* const* inten, int inten_is_u16, const uint32_t* const* label,
+	int on_device, int n_img, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+int nyxb200_featurize_3d_list (nyxb200_ctx* ctx, const void* const* inten, int inten_is_u16, const uint32_t* const* label,
+	int on_device, int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t);
 
 /* ---- measurement hooks ---- */

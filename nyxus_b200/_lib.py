@@ -50,6 +50,8 @@ def lib():
     for f in (L.nyxb200_featurize_3d_u32, L.nyxb200_featurize_3d_u16):
         f.argtypes = [vp, vp, vp, i32, i64, i64, i64, C.POINTER(Table), C.POINTER(C.POINTER(C.c_int32))]
     L.nyxb200_featurize_3d_device.argtypes = [vp, vp, i32, vp, i32, i64, i64, i64, C.POINTER(Table), C.POINTER(C.POINTER(C.c_int32))]
+    L.nyxb200_featurize_2d_list.argtypes = [vp, C.POINTER(vp), i32, C.POINTER(vp), i32, i32, i64, i64, C.POINTER(Table), C.POINTER(C.POINTER(C.c_int32))]
+    L.nyxb200_featurize_3d_list.argtypes = [vp, C.POINTER(vp), i32, C.POINTER(vp), i32, i32, i64, i64, i64, C.POINTER(Table), C.POINTER(C.POINTER(C.c_int32))]
     L.nyxb200_table_free.argtypes = [vp, C.POINTER(Table)]
     L.nyxb200_last_timings.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.nyxb200_last_counts.argtypes = [vp, C.POINTER(C.c_int64), i32]
@@ -67,6 +69,6 @@ def lib():
 EXPORTS = ["nyxb200_default_settings", "nyxb200_create", "nyxb200_destroy", "nyxb200_last_error", "nyxb200_select_features",
            "nyxb200_num_columns", "nyxb200_column_name", "nyxb200_column_code", "nyxb200_set_param", "nyxb200_featurize_2d_u32",
            "nyxb200_featurize_2d_u16", "nyxb200_featurize_2d_device", "nyxb200_featurize_3d_u32", "nyxb200_featurize_3d_u16",
-           "nyxb200_featurize_3d_device", "nyxb200_table_free", "nyxb200_last_timings",
+           "nyxb200_featurize_3d_device", "nyxb200_featurize_2d_list", "nyxb200_featurize_3d_list", "nyxb200_table_free", "nyxb200_last_timings",
            "nyxb200_last_counts", "nyxb200_stage_name", "nyxb200_debug_rois", "nyxb200_debug_cloud", "nyxb200_debug_matrix",
            "nyxb200_family_id", "nyxb200_version"]

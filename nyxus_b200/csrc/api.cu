@@ -107,6 +107,9 @@ struct nyxb200_ctx
 	int roi_batches = 0;		// 0 = automatic
 	cudaStream_t copy_stream = nullptr;	// D2H of a finished batch's rows
 	cudaEvent_t ev_sel;
+	// host slides travel on their own stream into two alternating device buffers: slide k+1 is uploaded while slide k computes
+	cudaStream_t up_stream = nullptr;
+	cudaEvent_t ev_up[2];
 	// the eight families are independent once the ROI records exist: each runs on its own stream (fork/join by events)
 	// so their low-occupancy, issue-bound kernels share the SMs; `concurrent = 0` serialises them (per-stage timing)
 	static constexpr int NFSTREAM = 8;
@@ -128,8 +131,8 @@ struct nyxb200_ctx
 	bool sel_dirty = true;
 
 	// device buffers (grow-only)
-	DevBuf<uint8_t> d_inten;
-	DevBuf<uint32_t> d_label;
+	DevBuf<uint8_t> d_inten[2];
+	DevBuf<uint32_t> d_label[2];
 	DevBuf<LabelStat> d_stats;
 	DevBuf<uint2> d_ztab;
 	uint32_t stats_cap = 1u << 20;
@@ -296,6 +299,9 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out)
 	for (auto& fs : ctx->fstream)
 		cudaStreamCreateWithFlags (&fs, cudaStreamNonBlocking);
 	cudaStreamCreateWithFlags (&ctx->copy_stream, cudaStreamNonBlocking);
+	cudaStreamCreateWithFlags (&ctx->up_stream, cudaStreamNonBlocking);
+	for (auto& ev : ctx->ev_up)
+		cudaEventCreateWithFlags (&ev, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&ctx->ev_sel, cudaEventDisableTiming);
 	cudaEventCreateWithFlags (&ctx->ev_fork, cudaEventDisableTiming);
 	for (auto& ev : ctx->ev_join)
@@ -312,7 +318,7 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 		return;
 	cudaSetDevice (ctx->st.device);
 	cudaDeviceSynchronize();
-	ctx->d_ztab.release(); ctx->d_sel.release(); ctx->d_inten.release(); ctx->d_label.release(); ctx->d_stats.release(); ctx->d_info.release();
+	ctx->d_ztab.release(); ctx->d_sel.release(); for (int i = 0; i < 2; i++) { ctx->d_inten[i].release(); ctx->d_label[i].release(); } ctx->d_stats.release(); ctx->d_info.release();
 	ctx->d_blkcnt.release(); ctx->d_blkarea.release(); ctx->d_rois.release(); ctx->d_classslot.release(); ctx->d_tlist.release();
 	ctx->d_alist.release(); ctx->d_bases.release(); ctx->d_cloud.release(); ctx->d_full.release(); ctx->d_sel_out.release();
 	for (auto& b : ctx->d_scratch) b.release();
@@ -333,6 +339,9 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	for (auto& fs : ctx->fstream)
 		cudaStreamDestroy (fs);
 	cudaStreamDestroy (ctx->copy_stream);
+	cudaStreamDestroy (ctx->up_stream);
+	for (auto& ev : ctx->ev_up)
+		cudaEventDestroy (ev);
 	cudaStreamDestroy (ctx->stream);
 	delete ctx;
 }
@@ -1483,7 +1492,10 @@ void collect_timings (nyxb200_ctx* ctx)
 		ctx->stage_ms[ST_TOTAL] += ms;
 }
 
-int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const uint32_t* label, bool on_device,
+// `inten[k]` / `label[k]`: slide k (host or device memory).  Host slides are uploaded on the upload stream into two
+// alternating device buffers, slide k+1 while slide k computes; the main stream's "h2d" stage is the part of the
+// upload it had to wait for.
+int featurize_slides (nyxb200_ctx* ctx, const void* const* inten, int inten_u16, const uint32_t* const* label, bool on_device,
 	int n_img, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
 {
 	if (!ctx || !inten || !label || !out)
@@ -1494,6 +1506,9 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 		return fail (ctx, NYXB200_EUNSUPPORTED, "volume has more than 2^31-1 rows");
 	if (H > 0x7FFFFFFF || W > 0x7FFFFFFF)
 		return fail (ctx, NYXB200_EUNSUPPORTED, "image side exceeds 2^31-1");
+	for (int k = 0; k < n_img; k++)
+		if (!inten[k] || !label[k])
+			return fail (ctx, NYXB200_EINVAL, "null slide pointer (image %d)", k);
 	out->data = nullptr;
 	out->nrows = 0;
 	out->ncols = (int)ctx->sel_cols.size() + 2;
@@ -1506,6 +1521,23 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 	const size_t npix = (size_t)D * (size_t)H * (size_t)W;
 	const size_t ibytes = npix * (inten_u16 ? 2 : 4), lbytes = npix * 4;
 	ctx->h_out_used = 0;
+	const int nbuf = on_device ? 0 : (n_img > 1 ? 2 : 1);
+	for (int b = 0; b < nbuf; b++)
+	{
+		CU (ctx->d_inten[b].reserve (ibytes));
+		CU (ctx->d_label[b].reserve (npix));
+	}
+	auto upload = [&](int k) -> int
+	{
+		const int b = k & 1;
+		CU (cudaMemcpyAsync (ctx->d_inten[b].p, inten[k], ibytes, cudaMemcpyHostToDevice, ctx->up_stream));
+		CU (cudaMemcpyAsync (ctx->d_label[b].p, label[k], lbytes, cudaMemcpyHostToDevice, ctx->up_stream));
+		CU (cudaEventRecord (ctx->ev_up[b], ctx->up_stream));
+		return 0;
+	};
+	if (!on_device)
+		if (int rc = upload (0))
+			return rc;
 	for (int k = 0; k < n_img; k++)
 	{
 		for (auto& u : ctx->ev_used) u = false;
@@ -1516,27 +1548,29 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 		im.W = (int32_t)W;
 		im.D = (int32_t)D;
 		im.inten_u16 = inten_u16;
-		const uint8_t* ip = (const uint8_t*)inten + (size_t)k * ibytes;
-		const uint32_t* lp = label + (size_t)k * npix;
 		stage_begin (ctx, ST_H2D);
 		if (on_device)
 		{
-			im.inten = ip;
-			im.label = lp;
+			im.inten = inten[k];
+			im.label = label[k];
 		}
 		else
 		{
-			CU (ctx->d_inten.reserve (ibytes));
-			CU (ctx->d_label.reserve (npix));
-			CU (cudaMemcpyAsync (ctx->d_inten.p, ip, ibytes, cudaMemcpyHostToDevice, ctx->stream));
-			CU (cudaMemcpyAsync (ctx->d_label.p, lp, lbytes, cudaMemcpyHostToDevice, ctx->stream));
-			im.inten = ctx->d_inten.p;
-			im.label = ctx->d_label.p;
+			// buffer (k+1)&1 held slide k-1, which has been fully processed (process_slide ends synchronised)
+			if (k + 1 < n_img)
+				if (int rc = upload (k + 1))
+					return rc;
+			CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_up[k & 1], 0));
+			im.inten = ctx->d_inten[k & 1].p;
+			im.label = ctx->d_label[k & 1].p;
 		}
 		int64_t nr = 0;
 		int rc = process_slide (ctx, im, k, &nr);
 		if (rc)
+		{
+			cudaStreamSynchronize (ctx->up_stream);	// nothing may still be reading the caller's buffers
 			return rc;
+		}
 		collect_timings (ctx);
 		for (int64_t i = 0; i < nr; i++)
 			ctx->row_image.push_back (k);
@@ -1547,6 +1581,25 @@ int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const 
 	if (row_image)
 		*row_image = ctx->row_image.data();
 	return NYXB200_OK;
+}
+
+// contiguous stack of n_img slides
+int featurize_common (nyxb200_ctx* ctx, const void* inten, int inten_u16, const uint32_t* label, bool on_device,
+	int n_img, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
+{
+	if (!ctx || !inten || !label || !out)
+		return fail (ctx, NYXB200_EINVAL, "null argument");
+	if (n_img <= 0 || H <= 0 || W <= 0 || D <= 0)
+		return fail (ctx, NYXB200_EINVAL, "bad image dimensions");
+	const size_t npix = (size_t)D * (size_t)H * (size_t)W;
+	std::vector<const void*> ip (n_img);
+	std::vector<const uint32_t*> lp (n_img);
+	for (int k = 0; k < n_img; k++)
+	{
+		ip[k] = (const uint8_t*)inten + (size_t)k * npix * (inten_u16 ? 2 : 4);
+		lp[k] = label + (size_t)k * npix;
+	}
+	return featurize_slides (ctx, ip.data(), inten_u16, lp.data(), on_device, n_img, D, H, W, out, row_image);
 }
 
 } // namespace
@@ -1600,6 +1653,22 @@ int nyxb200_featurize_3d_device (nyxb200_ctx* ctx, const void* inten, int inten_
 	if (ctx && ctx->st.dim != 3)
 		return fail (ctx, NYXB200_EINVAL, "this context was created for 2D features (dim = 2)");
 	return featurize_common (ctx, inten, inten_is_u16 ? 1 : 0, label, true, n_vol, D, H, W, out, row_image);
+}
+
+int nyxb200_featurize_2d_list (nyxb200_ctx* ctx, const void* const* inten, int inten_is_u16, const uint32_t* const* label,
+	int on_device, int n_img, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
+{
+	if (ctx && ctx->st.dim != 2)
+		return fail (ctx, NYXB200_EINVAL, "this context was created for 3D features (dim = 3)");
+	return featurize_slides (ctx, inten, inten_is_u16 ? 1 : 0, label, on_device != 0, n_img, 1, H, W, out, row_image);
+}
+
+int nyxb200_featurize_3d_list (nyxb200_ctx* ctx, const void* const* inten, int inten_is_u16, const uint32_t* const* label,
+	int on_device, int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
+{
+	if (ctx && ctx->st.dim != 3)
+		return fail (ctx, NYXB200_EINVAL, "this context was created for 2D features (dim = 2)");
+	return featurize_slides (ctx, inten, inten_is_u16 ? 1 : 0, label, on_device != 0, n_vol, D, H, W, out, row_image);
 }
 
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t)

@@ -140,6 +140,25 @@ class Engine:
         self._check(rc)
         return self._collect(tab, rimg, copy)
 
+    def featurize_list(self, inten_ptrs, inten_is_u16, label_ptrs, H, W, on_device=False, copy=True, D=None):
+        """A list of same-shape slides (2D) or volumes (D given), one raw pointer each (host unless on_device).  Host
+        slides are pipelined: upload of slide k+1 overlaps the compute of slide k."""
+        n = len(inten_ptrs)
+        if n != len(label_ptrs) or n == 0:
+            raise ValueError("Intensity and label lists must have the same, non-zero length")
+        ip = (C.c_void_p * n)(*[int(p) for p in inten_ptrs])
+        lp = (C.c_void_p * n)(*[int(p) for p in label_ptrs])
+        tab = _lib.Table()
+        rimg = C.POINTER(C.c_int32)()
+        if D is None:
+            rc = self._L.nyxb200_featurize_2d_list(self._ctx, ip, int(inten_is_u16), lp, int(on_device), n, H, W,
+                                                   C.byref(tab), C.byref(rimg))
+        else:
+            rc = self._L.nyxb200_featurize_3d_list(self._ctx, ip, int(inten_is_u16), lp, int(on_device), n, D, H, W,
+                                                   C.byref(tab), C.byref(rimg))
+        self._check(rc)
+        return self._collect(tab, rimg, copy)
+
     def timings(self):
         ms = (C.c_float * _lib.NSTAGES)()
         self._L.nyxb200_last_timings(self._ctx, ms, _lib.NSTAGES)

@@ -212,6 +212,25 @@ def test_empty_mask_and_montage_and_selection():
         nyx.featurize(I, L[:, :16])
 
 
+def test_pipelined_slide_list_equals_single_slide_calls(eng64):
+    """nyxb200_featurize_2d_list / the contiguous stack with n_img > 1: slide k+1 is uploaded into the second device buffer
+    while slide k computes.  Rows must be bit-identical to one call per slide, in slide order."""
+    from nyxus_b200 import synth
+    slides = [synth.blob_slide(300, 420, 30, 7, 12, seed=40 + k) for k in range(5)]
+    singles = [eng64.featurize(I, L)[0] for I, L in slides]
+    I = np.ascontiguousarray(np.stack([s[0] for s in slides]))
+    L = np.ascontiguousarray(np.stack([s[1] for s in slides]).astype(np.uint32))
+    tab, img = eng64.featurize(I, L)
+    assert np.array_equal(tab, np.concatenate(singles))
+    assert np.array_equal(img, np.concatenate([np.full(len(t), k, np.int32) for k, t in enumerate(singles)]))
+    # separate host buffers, in reverse order
+    keep = [(np.ascontiguousarray(s[0]), np.ascontiguousarray(s[1].astype(np.uint32))) for s in slides[::-1]]
+    tab2, img2 = eng64.featurize_list([a.ctypes.data for a, _ in keep], keep[0][0].dtype == np.uint16,
+                                      [b.ctypes.data for _, b in keep], 300, 420)
+    assert np.array_equal(tab2, np.concatenate(singles[::-1]))
+    assert np.array_equal(img2, np.concatenate([np.full(len(t), k, np.int32) for k, t in enumerate(singles[::-1])]))
+
+
 def test_negative_intensities_are_shifted_like_the_reference():
     from nyxus_b200 import Nyxus
     nyx = Nyxus(["MIN", "MAX"])

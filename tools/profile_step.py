@@ -12,6 +12,9 @@ inten, label = synth.config2(seed=2, size=size)
 d_int = torch.from_numpy(inten).cuda()
 d_lab = torch.from_numpy(label.view(np.int32)).cuda()
 eng = Engine(feats)
+for kv in sys.argv[4:]:            # library knobs, e.g. roi_batches=1 concurrent_families=0
+    k, v = kv.split("=")
+    eng.set_param(k, float(v))
 H, W = inten.shape
 for _ in range(steps):
     torch.cuda.synchronize()
