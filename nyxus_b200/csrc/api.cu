@@ -4,6 +4,7 @@
 // processIntSegImagePairInMemory (new_bindings_py.cpp:562-645, workflow_pythonapi.cpp:39-192).
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -276,6 +277,14 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out)
 		return fail (nullptr, NYXB200_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", s->device, prop.major, prop.minor);
 	if ((e = cudaSetDevice (s->device)) != cudaSuccess)
 		return fail (nullptr, NYXB200_ECUDA, "cudaSetDevice: %s", cudaGetErrorString (e));
+	{
+		// ln(k) of small integer counts (nyx_common.h ln_count), per device
+		static double lnt[LN_TABLE_N];
+		for (uint32_t k = 0; k < LN_TABLE_N; k++)
+			lnt[k] = k ? std::log ((double)k) : -INFINITY;
+		if ((e = cudaMemcpyToSymbol (g_ln_table, lnt, sizeof (lnt))) != cudaSuccess)
+			return fail (nullptr, NYXB200_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString (e));
+	}
 	nyxb200_ctx* ctx = new nyxb200_ctx();
 	ctx->st = *s;
 	ctx->sm_count = prop.multiProcessorCount;

@@ -57,12 +57,13 @@ template <bool P16> struct Counters
 	static NYX_HD size_t words (size_t ncells) { return P16 ? (ncells + 1) / 2 : ncells; }
 };
 
-// 32-bit words of one angle's region: joint + R,C,SPM (Ng each) + SPP (2Ng) [+pad] + px,py (doubles) + 2 level lists (u16)
+// 32-bit words of one angle's region: joint + R,C,SPM (Ng each) + SPP (2Ng) [+pad] + px,py (doubles, by level) +
+// the compacted non-empty px / py values (doubles)
 template <bool P16> NYX_HD size_t glcm_angle_words (int Ng)
 {
 	size_t ints = Counters<P16>::words ((size_t)Ng * Ng) + (size_t)Ng * 5;
 	ints += ints & 1;
-	return ints + (size_t)Ng * 4 + (size_t)Ng + (Ng & 1);
+	return ints + (size_t)Ng * 8;
 }
 
 // shared-memory words needed by glcm_body for `na` angles held at once
@@ -238,8 +239,8 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	ints += ints & 1;
 	double* px = (double*)(reg + ints);	// [Ng] = C/N	(glcm.cpp:859-864: px[i] += P.xy(i,j) -> column marginal)
 	double* py = px + Ng;			// [Ng] = R/N
-	uint16_t* lx = (uint16_t*)(py + Ng);	// [Ng] non-empty columns
-	uint16_t* ly = lx + Ng;			// [Ng] non-empty rows
+	double* pxc = py + Ng;			// [nx] px of the non-empty columns, ascending level
+	double* pyc = pxc + Ng;			// [ny] py of the non-empty rows
 
 	const bool sym = prm.glcm_symmetric || prm.ibsi;
 
@@ -327,16 +328,17 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		glcm_marginal_terms (k, Ng, cv, rv, dv, sv, N, mr, mc, diffavg, NgD, m, px, py);
 		const unsigned bx = g.ballot (cv != 0), by = g.ballot (rv != 0);
 		if (cv)
-			lx[nx + popc32 (bx & g.lanemask_lt())] = (uint16_t)k;
+			pxc[nx + popc32 (bx & g.lanemask_lt())] = (double)cv / N;
 		if (rv)
-			ly[ny + popc32 (by & g.lanemask_lt())] = (uint16_t)k;
+			pyc[ny + popc32 (by & g.lanemask_lt())] = (double)rv / N;
 		nx += popc32 (bx);
 		ny += popc32 (by);
 	}
-	g.sync();	// px/py/lx/ly visible
+	g.sync();	// px/py and the compacted lists visible
 	cta_sum<M_N> (g, m);
 
 	// ---- pass 2: owner-computes terms of the joint cells
+	const double invN = 1.0 / N;
 	unsigned long long s_asm = 0, jmax = 0;
 	double jd[3] = { 0, 0, 0 };	// sum log(p_cell), sum log(px*py), sum (r-mr)(c-mc)
 	for (int i = g.tid; i < ncell; i += g.nthr)
@@ -345,7 +347,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		if (!G.pair (cell, i, b, av))
 			continue;
 		const unsigned long long cnt = J.get (b * Ng + av);
-		const double p = (double)cnt / N;
+		const double p = (double)cnt * invN;
 		const double l1 = fast_log10 (dadd (p, GLCM_EPSILON));					// HXY (glcm.cpp:868, 734-735, 1160-1161)
 		const double l2 = fast_log10 (dadd (dmul (px[av], py[b]), GLCM_EPSILON));		// HXY1 (:869)
 		double cr = ((double)(b + 1) - mr) * ((double)(av + 1) - mc);				// (:633)
@@ -391,14 +393,21 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	// ---- HXY2 over the outer product of the non-empty marginals (glcm.cpp:905-911)
 	double hxy2[1] = { 0 };
 	{
-		const int tot = nx * ny;
-		FastDiv fy;
-		fy.init ((uint32_t)(ny > 0 ? ny : 1));
+		// flat index k = ii * ny + jj, advanced by nthr per step without a division
+		const int tot = nx * ny, nyy = ny > 0 ? ny : 1;
+		int ii = g.tid / nyy, jj = g.tid - ii * nyy;
+		const int di = g.nthr / nyy, dj = g.nthr - di * nyy;
 		for (int k = g.tid; k < tot; k += g.nthr)
 		{
-			const int ii = (int)fy.div ((uint32_t)k), jj = k - ii * ny;
-			const double qv = dmul (px[lx[ii]], py[ly[jj]]);
+			const double qv = dmul (pxc[ii], pyc[jj]);
 			hxy2[0] += dmul (qv, fast_log10 (dadd (qv, GLCM_EPSILON)));
+			ii += di;
+			jj += dj;
+			if (jj >= nyy)
+			{
+				jj -= nyy;
+				ii++;
+			}
 		}
 	}
 	cta_sum<1> (g, hxy2);

@@ -89,12 +89,17 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 				q[Q_MUI] += lv;							// :598-605
 				q[Q_MUJ] += (unsigned long long)len;				// :640-646
 				q[Q_HGL] += (unsigned long long)i2;				// :744-751
-				s[A_SRE] += 1.0 / (double)(len * len);				// :381-383
-				s[A_LGL] += 1.0 / (double)i2;					// :712-719
-				s[A_SRL] += 1.0 / (double)i2j2;					// :781
-				s[A_SRH] += (double)i2 / (double)(int)j2;			// :813
-				s[A_LRL] += (double)(int)j2 / (double)i2;			// :844
-				s[A_LRH] += (double)i2j2;					// :876
+				if (lv < 65536u && (unsigned long long)i2 * (unsigned long long)j2 < 0x100000000ull)
+					emphasis6 (s, (double)i2, (double)(int)j2);			// :381-383,712-719,781,813,844,876 (no 32-bit wrap: i2j2 == i2 * j2)
+				else
+				{
+					s[A_SRE] += 1.0 / (double)(len * len);
+					s[A_LGL] += 1.0 / (double)i2;
+					s[A_SRL] += 1.0 / (double)i2j2;
+					s[A_SRH] += (double)i2 / (double)(int)j2;
+					s[A_LRL] += (double)(int)j2 / (double)i2;
+					s[A_LRH] += (double)i2j2;
+				}
 			}
 		}
 		rl[i] = (uint16_t)len;
@@ -115,6 +120,7 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 	}
 	const double sum = (double)q[Q_SUM], Np = (double)q[Q_NP];
 	const double mui = (double)q[Q_MUI] / sum, muj = (double)q[Q_MUJ] / sum;
+	const double inv_sum = 1.0 / sum;
 
 	// ---- pass 2: terms that need the counts (owner computes)
 	unsigned long long q2[2] = { 0, 0 };	// sum Ri^2 (:441-448), sum Cj^2 (:509-517)
@@ -130,7 +136,7 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 		const double di = (double)lv - mui, dj = (double)len - muj;
 		t[0] += di * di;								// :608-616
 		t[1] += dj * dj;								// :649-656
-		const double p = (double)P[(size_t)(lv - 1) * Nr + (len - 1)] / sum;
+		const double p = (double)P[(size_t)(lv - 1) * Nr + (len - 1)] * inv_sum;
 		t[2] += fast_log10 (dadd (p, EPS_ZONES));					// :684-685
 	}
 	cta_sum_u64<2> (g, q2);

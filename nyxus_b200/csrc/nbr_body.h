@@ -101,12 +101,7 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 		q[Q_MUJ] += (unsigned long long)j;				// :410
 		q[Q_MUI] += lv;							// :388-395
 		q[Q_HGL] += (unsigned long long)lv * (unsigned long long)lv;	// :470-484
-		s[A_SDE] += 1.0 / ((double)j * (double)j);			// :301-302
-		s[A_LGL] += 1.0 / (in * in);					// :452-464
-		s[A_SDL] += 1.0 / (double)(in * in * j * j);			// :498-505
-		s[A_SDH] += (in * in) / (double)(j * j);			// :513-520
-		s[A_LDL] += (double)(j * j) / (in * in);			// :528-535
-		s[A_LDH] += (double)(in * in * j * j);				// :543-550
+		emphasis6 (s, in * in, (double)(j * j));			// :301-302, 452-464, 498-550
 	}
 	c.sync();
 	if (dbg && dbg->P)
@@ -122,6 +117,7 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 	}
 	const double Nz = (double)q[Q_NZ];
 	const double mui = (double)q[Q_MUI] / Nz, muj = (double)q[Q_MUJ] / Nz;
+	const double inv_nz = 1.0 / Nz;
 
 	// ---- pass 2: terms that need the counts (owner computes)
 	unsigned long long q2[2] = { 0, 0 };	// sum Si^2 (:325-338), sum Sj^2 (:343-357)
@@ -137,7 +133,7 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 		const double di = (double)lv - mui, dj = (double)j - muj;
 		t[0] += di * di;							// :398-406
 		t[1] += dj * dj;							// :418-429
-		const double p = (double)P[(size_t)lv * 10 + j] / Nz;
+		const double p = (double)P[(size_t)lv * 10 + j] * inv_nz;
 		t[2] += fast_log10 (dadd (p, EPS_ZONES));				// :437-446
 	}
 	cta_sum_u64<2> (c, q2);
@@ -242,17 +238,19 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 		q[Q_NS] += 1;
 		q[Q_G] += lv;
 		q[Q_DC] += (unsigned long long)(nm + 1);
-		s[A_LDE] += 1.0 / dc / dc;
-		s[A_HDE] += dc * dc;
+		const double d2 = dc * dc, g2 = g * g, rd = 1.0 / d2;	// reciprocals instead of the reference's chained divisions (<= 2 ulp)
+		s[A_LDE] += rd;
+		s[A_HDE] += d2;
 		if (g != 0.0)
 		{
-			s[A_LGLCE] += 1.0 / g / g;
-			s[A_LDLGLE] += 1.0 / dc / dc / g / g;
-			s[A_HDLGLE] += dc * dc / g / g;
+			const double rg = 1.0 / g2;
+			s[A_LGLCE] += rg;
+			s[A_LDLGLE] += rd * rg;
+			s[A_HDLGLE] += d2 * rg;
 		}
-		s[A_HGLCE] += g * g;
-		s[A_LDHGLE] += g * g / dc / dc;
-		s[A_HDHGLE] += dc * dc * g * g;
+		s[A_HGLCE] += g2;
+		s[A_LDHGLE] += g2 * rd;
+		s[A_HDHGLE] += d2 * g2;
 	}
 	c.sync();
 	if (dbg && dbg->P)
@@ -279,7 +277,7 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 		const double dg = (double)lv - glm, dd = (double)(nm + 1) - dcm;
 		t[0] += dg * dg;
 		t[1] += dd * dd;
-		t[2] += log ((double)v / Ns);
+		t[2] += ln_count (v);		// log(v / Ns), summed as ln(v) and finished below
 	}
 	cta_sum_u64<3> (c, q2);
 	cta_sum<3> (c, t);
@@ -316,7 +314,7 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 		out[N_GLV] = t[0] / Ns;
 		out[N_DCM] = dcm;
 		out[N_DCV] = t[1] / Ns;
-		out[N_DCENT] = -(t[2] / Ns) / log (2.0);
+		out[N_DCENT] = -((t[2] - Ns * log (Ns)) / Ns) * INV_LN2;
 		out[N_DCENE] = (double)q2[2] / (Ns * Ns);
 	}
 }

@@ -115,6 +115,39 @@ NYX_HD double plogp (double p, double eps)
 	return ddiv (dmul (p, fast_log10 (dadd (p, eps))), LOG10_2);
 }
 
+// The six "emphasis" sums every run / zone / dependence family takes over its elements (level i, minor j):
+//   s[0] += 1/j^2   s[1] += 1/i^2   s[2] += 1/(i^2 j^2)   s[3] += i^2/j^2   s[4] += j^2/i^2   s[5] += i^2 j^2
+// (GLRLM glrlm.cpp:381-383,712-719,781,813,844,876; GLSZM glszm.cpp:372-375,424-427,559-563; GLDZM gldzm.cpp:402,421,
+// 440-443; GLDM gldm.cpp:301-302,452-550).  Two reciprocals instead of the reference's five-to-thirteen divisions per
+// element: each term differs from the reference's by at most 2 ulp (features are held to 1e-9, not bit-exact).
+NYX_HD void emphasis6 (double* s, double i2, double j2)
+{
+	const double ri = 1.0 / i2, rj = 1.0 / j2;
+	s[0] += rj;
+	s[1] += ri;
+	s[2] += ri * rj;
+	s[3] += i2 * rj;
+	s[4] += j2 * ri;
+	s[5] += i2 * j2;
+}
+
+// ln(k) of a small integer count.  Entropies over integer matrices, sum_cells P log(P/N), become
+// sum_elements ln(count) - n ln(N): the per-element log is a table load (the table is filled by the host when the
+// context is created).  |error| ~ 1e-16 relative to the reference's log(count/N + 2.2e-16).
+constexpr uint32_t LN_TABLE_N = 1024;
+#if NYX_DEVICE_BUILD
+__device__ double g_ln_table[LN_TABLE_N];
+#endif
+NYX_D double ln_count (uint32_t k)
+{
+#if NYX_DEVICE_BUILD
+	return k < LN_TABLE_N ? g_ln_table[k] : log ((double)k);
+#else
+	return log ((double)k);
+#endif
+}
+constexpr double INV_LN2 = 1.4426950408889634074;
+
 // ------------------------------------------------------------------------------------------------
 // Grey-level binning (reference features/texture_feature.h:23-50,138-167; helpers/helpers.h:337-345)
 // ------------------------------------------------------------------------------------------------

@@ -315,13 +315,7 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 		q[Q_MUJ] += sz;							// :380
 		q[Q_MUI] += lv;							// :381
 		q[Q_HGL] += (unsigned long long)lv * lv;			// :574-578
-		const double i2 = (double)lv * (double)lv, j2 = (double)sz * (double)sz;
-		s[A_SAE] += 1.0 / (double)(int)(sz * sz);			// :424-427 (int j*j)
-		s[A_LGL] += 1.0 / i2;						// :559-563
-		s[A_LAH] += i2 * j2;						// :372-375
-		s[A_LAL] += j2 / i2;
-		s[A_SAH] += i2 / j2;
-		s[A_SAL] += 1.0 / (i2 * j2);
+		emphasis6 (s, (double)lv * (double)lv, (double)sz * (double)sz);	// :372-375, 424-427 (sz < 65536: int j*j exact), 559-563
 	}
 	c.sync();
 	cta_sum_u64<Q_N> (c, q);
@@ -335,6 +329,7 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 	}
 	const double sum = (double)nz;
 	const double mui = (double)q[Q_MUI] / sum, muj = (double)q[Q_MUJ] / sum;
+	const double inv_sum = 1.0 / sum;
 
 	// ---- pass 2: terms that need the counts (owner computes)
 	unsigned long long q2[2] = { 0, 0 };	// sum n_level^2 (:450-454), sum n_size^2 (:481-485)
@@ -350,7 +345,7 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 		const double di = (double)lv - mui, dj = (double)sz - muj;
 		t[0] += di * di;									// :518-526
 		t[1] += dj * dj;									// :535-542
-		const double pn = (double)htab_get (keys, cnts, mask, (lv << 16) | sz) / sum;
+		const double pn = (double)htab_get (keys, cnts, mask, (lv << 16) | sz) * inv_sum;
 		t[2] += fast_log10 (dadd (pn, EPS_ZONES));						// :377-378
 	}
 	cta_sum_u64<2> (c, q2);
@@ -517,13 +512,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		q[Q_ZDM] += dd;							// :445
 		q[Q_GLM] += lv;							// :444
 		q[Q_HGL] += (unsigned long long)lv * lv;			// :422
-		const double g = (double)lv, d = (double)dd;
-		s[A_SDE] += 1.0 / d / d;					// :402
-		s[A_LGL] += 1.0 / (g * g);					// :421
-		s[A_SDL] += 1.0 / g / g / d / d;				// :440
-		s[A_SDH] += g * g / d / d;					// :441
-		s[A_LDL] += d * d / g / g;					// :442
-		s[A_LDH] += g * g * d * d;					// :443
+		emphasis6 (s, (double)lv * (double)lv, (double)dd * (double)dd);	// :402, 421, 440-443
 	}
 	c.sync();
 	cta_sum_u64<Q_N> (c, q);
@@ -545,8 +534,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		const double di = (double)lv - glm, dj = (double)dd - zdm;
 		t[0] += di * di;						// :468-471
 		t[1] += dj * dj;						// :474-476
-		const double p = (double)P[(size_t)lv * Nd + dd] / Ns;
-		t[2] += log2 (p + EPS_ZONES);					// :446
+		t[2] += ln_count (P[(size_t)lv * Nd + dd]);			// :446  log2(P/Ns + eps), summed as ln(P) and finished below
 	}
 	cta_sum_u64<2> (c, q2);
 	cta_sum<3> (c, t);
@@ -582,7 +570,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		out[Z_GLV] = t[0] / Ns;
 		out[Z_ZDM] = zdm;
 		out[Z_ZDV] = t[1] / Ns;
-		out[Z_ZDE] = -(t[2] / Ns);
+		out[Z_ZDE] = -((t[2] - Ns * log (Ns)) * INV_LN2 / Ns);
 	}
 }
 
