@@ -1120,6 +1120,27 @@ int reserve_pinned_out (nyxb200_ctx* ctx, size_t n)
 	return 0;
 }
 
+// phase-1 scan launch: a grid of exactly the resident CTAs; rows per unit as large as keeps >= 8 units per resident warp
+// (long units = more runs merged per commit by the per-lane cache)
+template <bool U16, bool VEC, bool D3>
+int launch_scan (nyxb200_ctx* ctx, const ImageView& im, uint32_t nrows, uint32_t nchunk, uint2* ztab)
+{
+	auto kern = k_scan_stats<U16, VEC, D3>;
+	int per_sm = 0;
+	CU (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kern, 256, 0));
+	per_sm = std::max (per_sm, 1);
+	const unsigned long long resident_warps = (unsigned long long)ctx->sm_count * per_sm * 8;
+	uint32_t rpu = 32;
+	while (rpu > 1 && (unsigned long long)((nrows + rpu - 1) / rpu) * nchunk < 8 * resident_warps)
+		rpu >>= 1;
+	const unsigned long long nunits = (unsigned long long)((nrows + rpu - 1) / rpu) * nchunk;
+	const int grid = (int)std::max<unsigned long long> (1, std::min<unsigned long long> ((nunits + 7) / 8, (unsigned long long)ctx->sm_count * per_sm));
+	kern<<<grid, 256, 0, ctx->stream>>> (im.inten, im.label, (uint32_t)im.W, nrows, (uint32_t)im.H, nchunk, rpu, ctx->d_stats.p,
+		ctx->stats_cap, ctx->d_info.p, ztab);
+	CU (cudaGetLastError());
+	return 0;
+}
+
 // One slide already resident on the device.  Appends its rows to the context's pinned table buffer.
 int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t* nrows_out)
 {
@@ -1146,12 +1167,10 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		k_init_stats<<<(ctx->stats_cap + 255) / 256, 256, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab);
 		CU (cudaGetLastError());
 		stage_begin (ctx, ST_SCAN);
-		const bool vec = (im.W % 4 == 0) && ((uintptr_t)im.label % 16 == 0) && ((uintptr_t)im.inten % (im.inten_u16 ? 8 : 16) == 0);
-		const uint32_t nrows = (uint32_t)im.D * (uint32_t)im.H, nchunk = ((uint32_t)im.W + 127) / 128;
-		const unsigned long long nitems = (unsigned long long)nrows * nchunk;
-		const int grid = (int)std::max<unsigned long long> (1, std::min<unsigned long long> ((nitems + 7) / 8, (unsigned long long)ctx->sm_count * 8));
-#define NYX_SCAN(U16, VEC, D3) k_scan_stats<U16, VEC, D3><<<grid, 256, 0, s>>> (im.inten, im.label, (uint32_t)im.W, nrows, (uint32_t)im.H, nchunk, \
-			ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ztab)
+		const bool vec = (im.W % SCAN_PX == 0) && ((uintptr_t)im.label % 16 == 0) && ((uintptr_t)im.inten % 16 == 0);
+		const uint32_t nrows = (uint32_t)im.D * (uint32_t)im.H, nchunk = ((uint32_t)im.W + SCAN_CHUNK - 1) / SCAN_CHUNK;
+#define NYX_SCAN(U16, VEC, D3) rc_scan = launch_scan<U16, VEC, D3> (ctx, im, nrows, nchunk, ztab)
+		int rc_scan = 0;
 		if (d3)
 		{
 			if (im.inten_u16) { if (vec) NYX_SCAN (true, true, true); else NYX_SCAN (true, false, true); }
@@ -1163,6 +1182,8 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 			else { if (vec) NYX_SCAN (false, true, false); else NYX_SCAN (false, false, false); }
 		}
 #undef NYX_SCAN
+		if (rc_scan)
+			return rc_scan;
 		CU (cudaGetLastError());
 		ctx->counts[0] += 2;
 		stage_begin (ctx, ST_COMPACT);

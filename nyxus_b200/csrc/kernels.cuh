@@ -17,9 +17,9 @@ namespace nyx
 // Phase 1: one streaming pass over the slide -> per-label {area, min, max, AABB}
 // (reference: gatherRoisMetricsInMemory phase1.cpp:373-407 + feed_pixel_2_metrics pixel_feed.cpp:19-43 +
 //  init/update_label_record_3 features_calc_workflow.cpp:65-105: two hash probes per foreground pixel.)
-// Here: a dense label-indexed table in HBM (32 B per label = one sector), 128-bit loads, and warp-aggregated
-// updates: lanes holding the same label are grouped with match.any, reduced with redux.sync, and ONE lane issues
-// the 7 atomics of the group.
+// Here: a dense label-indexed table in HBM (32 B per label = one sector), 128-bit loads, and run-aggregated
+// updates: the pixels of a row run (and, through a per-lane cache, of the runs of a few consecutive rows) are
+// reduced in registers / by warp shuffles and ONE lane issues the 7 atomics of the run.
 // ------------------------------------------------------------------------------------------------
 struct __align__(32) LabelStat
 {
@@ -92,171 +92,222 @@ __device__ __forceinline__ void stat_commit (LabelStat* tab, uint32_t cap, uint3
 	}
 }
 
-// Work item = (row, 128-pixel chunk): one warp, 4 consecutive pixels per lane (128-bit label load, 64/128-bit intensity
-// load).  Equal labels are contiguous along a row, so the warp does a SEGMENTED scan over lanes (shuffles, no
-// match.any) and exactly one lane per run -- the one holding the run's last pixel -- commits it: x-extent follows from
-// the run length (xmin = xmax - cnt + 1), y/z are warp-uniform.  The run that reaches a lane's last pixel is first merged
-// into a one-entry per-lane register cache, so a label that keeps ending on the same lane in successive items (a whole-
-// slide ROI: always lane 31) costs one commit per warp instead of one per row chunk.
-template <bool U16, bool VEC, bool D3>
-__global__ void __launch_bounds__(256) k_scan_stats (const void* __restrict__ inten_, const uint32_t* __restrict__ label,
-	uint32_t W, uint32_t nrows, uint32_t H, uint32_t nchunk, LabelStat* tab, uint32_t cap, SlideInfo* info, uint2* ztab)
+// (min, max) of a set of intensities.  16-bit intensities: ONE register, (65535 - min) in the high half and max in the
+// low half, joined by a single VIMNMX.U16x2; 32-bit intensities: two registers.
+template <bool U16> struct MinMax
 {
-	const uint32_t lane = threadIdx.x & 31;
-	const unsigned long long nitems = (unsigned long long)nrows * nchunk;
-	const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-	uint32_t maxlbl = 0;
-	// per-lane run cache (c_lbl == 0: empty)
-	uint32_t c_lbl = 0, c_cnt = 0, c_vmin = 0, c_vmax = 0, c_xmin = 0, c_xmax = 0, c_ymin = 0, c_ymax = 0, c_zmin = 0, c_zmax = 0;
-	FastDiv fc, fh;
-	fc.init (nchunk);
-	fh.init (H);
-	const bool small = nitems < 0x100000000ull / (nchunk > H ? nchunk : H);	// FastDiv is exact for n * d < 2^32
-	for (unsigned long long item = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; item < nitems; item += nwarps)
+	uint32_t a, b;
+	__device__ __forceinline__ static MinMax of (uint32_t v)
 	{
-		const uint32_t row = small ? fc.div ((uint32_t)item) : (uint32_t)(item / nchunk);
-		const uint32_t x0 = ((uint32_t)(item - (unsigned long long)row * nchunk) << 7) + lane * 4;
-		const size_t base = (size_t)row * W + x0;
-		uint32_t l[4] = { 0, 0, 0, 0 }, v[4] = { 0, 0, 0, 0 };
-		if (VEC && x0 + 3 < W)
+		MinMax m;
+		if (U16) { m.a = ((v ^ 0xFFFFu) << 16) | v; m.b = 0; }
+		else { m.a = v; m.b = v; }
+		return m;
+	}
+	__device__ __forceinline__ void join (const MinMax& o)
+	{
+		if (U16) a = __vmaxu2 (a, o.a);
+		else { a = min (a, o.a); b = max (b, o.b); }
+	}
+	__device__ __forceinline__ uint32_t vmin() const { return U16 ? (a >> 16) ^ 0xFFFFu : a; }
+	__device__ __forceinline__ uint32_t vmax() const { return U16 ? (a & 0xFFFFu) : b; }
+	__device__ __forceinline__ MinMax up (int o) const
+	{
+		MinMax m;
+		m.a = __shfl_up_sync (0xffffffffu, a, o);
+		m.b = U16 ? 0u : __shfl_up_sync (0xffffffffu, b, o);
+		return m;
+	}
+};
+
+constexpr int SCAN_PX = 8;			// pixels per lane
+constexpr int SCAN_CHUNK = 32 * SCAN_PX;	// pixels per warp and row
+
+// The 8 pixels of one lane: labels l[], intensities as MinMax singletons p[]
+template <bool U16, bool VEC>
+__device__ __forceinline__ void scan_load (const void* __restrict__ inten_, const uint32_t* __restrict__ label, size_t rowbase, uint32_t x0,
+	uint32_t W, uint32_t (&l)[SCAN_PX], MinMax<U16> (&p)[SCAN_PX])
+{
+#pragma unroll
+	for (int k = 0; k < SCAN_PX; k++)
+	{
+		l[k] = 0;
+		p[k] = MinMax<U16>::of (0);
+	}
+	if (x0 >= W)
+		return;
+	const size_t base = rowbase + x0;
+	if (VEC)	// W % 8 == 0 and 16-byte aligned images: the lane's pixels are all inside the row
+	{
+		const uint4 l0 = __ldg (reinterpret_cast<const uint4*> (label + base));
+		const uint4 l1 = __ldg (reinterpret_cast<const uint4*> (label + base) + 1);
+		l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
+		if (U16)
 		{
-			const uint4 lv = __ldg (reinterpret_cast<const uint4*> (label + base));
-			l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+			const uint4 iv = __ldg (reinterpret_cast<const uint4*> ((const uint16_t*)inten_ + base));
+			const uint32_t w4[4] = { iv.x, iv.y, iv.z, iv.w };
+#pragma unroll
+			for (int j = 0; j < 4; j++)
+			{
+				// two pixels per word -> ((65535 - v) << 16) | v of each half with two byte permutes
+				p[2 * j].a = __byte_perm (w4[j], ~w4[j], 0x5410);
+				p[2 * j + 1].a = __byte_perm (w4[j], ~w4[j], 0x7632);
+			}
 		}
 		else
 		{
+			const uint4 i0 = __ldg (reinterpret_cast<const uint4*> ((const uint32_t*)inten_ + base));
+			const uint4 i1 = __ldg (reinterpret_cast<const uint4*> ((const uint32_t*)inten_ + base) + 1);
+			p[0] = MinMax<U16>::of (i0.x); p[1] = MinMax<U16>::of (i0.y); p[2] = MinMax<U16>::of (i0.z); p[3] = MinMax<U16>::of (i0.w);
+			p[4] = MinMax<U16>::of (i1.x); p[5] = MinMax<U16>::of (i1.y); p[6] = MinMax<U16>::of (i1.z); p[7] = MinMax<U16>::of (i1.w);
+		}
+	}
+	else
+	{
 #pragma unroll
-			for (int k = 0; k < 4; k++)
-				if (x0 + k < W)
-					l[k] = __ldg (label + base + k);
-		}
-		const uint32_t any = l[0] | l[1] | l[2] | l[3];
-		if (__ballot_sync (0xffffffffu, any != 0) == 0)
-			continue;		// background chunk
-		if (any)
-		{
-			if (VEC && x0 + 3 < W)
+		for (int k = 0; k < SCAN_PX; k++)
+			if (x0 + k < W)
 			{
-				if (U16)
-				{
-					const ushort4 iv = __ldg (reinterpret_cast<const ushort4*> ((const uint16_t*)inten_ + base));
-					v[0] = iv.x; v[1] = iv.y; v[2] = iv.z; v[3] = iv.w;
-				}
-				else
-				{
-					const uint4 iv = __ldg (reinterpret_cast<const uint4*> ((const uint32_t*)inten_ + base));
-					v[0] = iv.x; v[1] = iv.y; v[2] = iv.z; v[3] = iv.w;
-				}
+				l[k] = __ldg (label + base + k);
+				p[k] = MinMax<U16>::of (U16 ? (uint32_t)__ldg ((const uint16_t*)inten_ + base + k) : __ldg ((const uint32_t*)inten_ + base + k));
 			}
-			else
-			{
-#pragma unroll
-				for (int k = 0; k < 4; k++)
-					if (x0 + k < W)
-						v[k] = U16 ? (uint32_t)__ldg ((const uint16_t*)inten_ + base + k) : __ldg ((const uint32_t*)inten_ + base + k);
-			}
-		}
-		maxlbl = max (maxlbl, max (max (l[0], l[1]), max (l[2], l[3])));
-		uint32_t y = row, z = 0;
-		if (D3)
-		{
-			z = small ? fh.div (row) : row / H;
-			y = row - z * H;
-		}
+	}
+}
 
-		// ---- run structure of this lane's 4 pixels
-		const uint32_t prev = __shfl_up_sync (0xffffffffu, l[3], 1);
-		const bool s0 = lane == 0 || l[0] != prev;			// pixel 0 starts a run
-		const bool s1 = l[1] != l[0], s2 = l[2] != l[1], s3 = l[3] != l[2];
-		const int a = s1 ? 1 : s2 ? 2 : s3 ? 3 : 4;			// left part L = pixels [0, a)
-		const int b = s3 ? 3 : s2 ? 2 : s1 ? 1 : 0;			// right-open part R = pixels [b, 4); b == 0: R == L == whole lane
-		uint32_t r_cnt = 4 - b, r_min = v[3], r_max = v[3];
-		if (b < 3) { r_min = min (r_min, v[2]); r_max = max (r_max, v[2]); }
-		if (b < 2) { r_min = min (r_min, v[1]); r_max = max (r_max, v[1]); }
-		if (b < 1) { r_min = min (r_min, v[0]); r_max = max (r_max, v[0]); }
-		// ---- inclusive segmented scan of R over the lanes; a segment starts where R starts inside the lane
-		const bool head = b > 0 || s0;
-		const unsigned heads = __ballot_sync (0xffffffffu, head);
-		const int headlane = 31 - __clz (heads & (0xffffffffu >> (31 - lane)));
+// Work unit = (block of `rpu` consecutive rows, 256-pixel chunk): one warp, 8 consecutive pixels per lane (two 128-bit
+// label loads, one or two 128-bit intensity loads; the next row's loads are issued before the current row is processed).
+// Equal labels are contiguous along a row, so per row the warp does a SEGMENTED max-scan over lanes (shuffles) of the
+// packed (min, max) and exactly one lane per run -- the one holding the run's last pixel -- commits it; the run length
+// needs no scan (end position minus the start position held by the segment's head lane), y/z are warp-uniform.
+// The run that reaches a lane's last pixel is first merged into a one-entry per-lane register cache: walking DOWN the
+// rows of the unit, the right edge of a ROI usually stays in the same lane for several rows, so a ROI costs one commit
+// per few rows instead of one per row (a whole-slide ROI: one per unit).
+template <bool U16, bool VEC, bool D3>
+__global__ void __launch_bounds__(256, U16 ? 3 : 2) k_scan_stats (const void* __restrict__ inten_, const uint32_t* __restrict__ label,
+	uint32_t W, uint32_t nrows, uint32_t H, uint32_t nchunk, uint32_t rpu, LabelStat* tab, uint32_t cap, SlideInfo* info, uint2* ztab)
+{
+	typedef MinMax<U16> MM;
+	const uint32_t lane = threadIdx.x & 31;
+	const unsigned long long nunits = (unsigned long long)((nrows + rpu - 1) / rpu) * nchunk;
+	const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+	uint32_t maxlbl = 0;
+	// per-lane run cache (c_lbl == 0: empty)
+	uint32_t c_lbl = 0, c_cnt = 0, c_xmin = 0, c_xmax = 0, c_ymin = 0, c_ymax = 0, c_zmin = 0, c_zmax = 0;
+	MM c_mm = MM::of (0);
+	for (unsigned long long unit = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; unit < nunits; unit += nwarps)
+	{
+		const uint32_t rb = (uint32_t)(unit / nchunk);
+		const uint32_t x0 = ((uint32_t)(unit - (unsigned long long)rb * nchunk) * SCAN_CHUNK) + lane * SCAN_PX;
+		const uint32_t row0 = rb * rpu, row1 = min (nrows, row0 + rpu);
+		uint32_t l[SCAN_PX], ln[SCAN_PX];
+		MM p[SCAN_PX], pn[SCAN_PX];
+		scan_load<U16, VEC> (inten_, label, (size_t)row0 * W, x0, W, l, p);
+		for (uint32_t row = row0; row < row1; row++)
+		{
+			if (row + 1 < row1)
+				scan_load<U16, VEC> (inten_, label, (size_t)(row + 1) * W, x0, W, ln, pn);
+			uint32_t any = l[0];
 #pragma unroll
-		for (int o = 1; o < 32; o <<= 1)
-		{
-			const uint32_t tc = __shfl_up_sync (0xffffffffu, r_cnt, o);
-			const uint32_t tn = __shfl_up_sync (0xffffffffu, r_min, o);
-			const uint32_t tx = __shfl_up_sync (0xffffffffu, r_max, o);
-			if ((int)lane - o >= headlane)
+			for (int k = 1; k < SCAN_PX; k++)
+				any |= l[k];
+			if (__ballot_sync (0xffffffffu, any != 0) != 0)		// else: background chunk
 			{
-				r_cnt += tc;
-				r_min = min (r_min, tn);
-				r_max = max (r_max, tx);
-			}
-		}
-		// what flows in from the lanes to the left (meaningful when !s0)
-		const uint32_t k_cnt = __shfl_up_sync (0xffffffffu, r_cnt, 1);
-		const uint32_t k_min = __shfl_up_sync (0xffffffffu, r_min, 1);
-		const uint32_t k_max = __shfl_up_sync (0xffffffffu, r_max, 1);
-		const bool next_s0 = __shfl_down_sync (0xffffffffu, s0 ? 1 : 0, 1) != 0 || lane == 31;
+				uint32_t y = row, z = 0;
+				if (D3)
+				{
+					z = row / H;
+					y = row - z * H;
+				}
+				// ---- runs inside the lane: L = pixels [0, a) (closes here when b > 0), R = pixels [b, 8) (open to the right),
+				// runs strictly between them are committed on the spot (they need nothing from other lanes)
+				const uint32_t prev = __shfl_up_sync (0xffffffffu, l[SCAN_PX - 1], 1);
+				const bool s0 = lane == 0 || l[0] != prev;	// pixel 0 starts a run
+				MM cur = p[0], Lmm = p[0];
+				int a = SCAN_PX, b = 0;
+				maxlbl = max (maxlbl, l[0]);
+#pragma unroll
+				for (int k = 1; k < SCAN_PX; k++)
+				{
+					if (l[k] != l[k - 1])
+					{
+						if (b == 0)
+						{
+							a = k;
+							Lmm = cur;
+						}
+						else if (l[k - 1] != 0)
+							stat_commit (tab, cap, l[k - 1], (uint32_t)(k - b), cur.vmin(), cur.vmax(), x0 + b, x0 + k - 1, y, y, D3 ? ztab : nullptr, z, z);
+						b = k;
+						cur = p[k];
+						maxlbl = max (maxlbl, l[k]);
+					}
+					else
+						cur.join (p[k]);
+				}
+				// ---- inclusive segmented scan of R over the lanes; a segment starts where R starts inside the lane
+				const bool head = b > 0 || s0;
+				const unsigned heads = __ballot_sync (0xffffffffu, head);
+				const int headlane = 31 - __clz (heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+				for (int o = 1; o < 32; o <<= 1)
+				{
+					const MM t = cur.up (o);
+					if ((int)lane - o >= headlane)
+						cur.join (t);
+				}
+				const uint32_t sx = __shfl_sync (0xffffffffu, x0 + (uint32_t)b, headlane);	// first pixel of my R segment
+				// what flows in from the lanes to the left (meaningful when !s0)
+				const MM kin = cur.up (1);
+				const uint32_t ksx = __shfl_up_sync (0xffffffffu, sx, 1);
+				const bool next_s0 = __shfl_down_sync (0xffffffffu, s0 ? 1 : 0, 1) != 0 || lane == 31;
 
-		// ---- L closes inside this lane (b > 0): commit it, joined with the inflow
-		if (b > 0 && l[0] != 0)
-		{
-			uint32_t cnt = a, mn = v[0], mx = v[0];
-			if (a > 1) { mn = min (mn, v[1]); mx = max (mx, v[1]); }
-			if (a > 2) { mn = min (mn, v[2]); mx = max (mx, v[2]); }
-			if (!s0)
-			{
-				cnt += k_cnt;
-				mn = min (mn, k_min);
-				mx = max (mx, k_max);
+				// ---- L closes inside this lane (b > 0): commit it, joined with the inflow
+				if (b > 0 && l[0] != 0)
+				{
+					uint32_t xs = x0;
+					if (!s0)
+					{
+						Lmm.join (kin);
+						xs = ksx;
+					}
+					const uint32_t xe = x0 + a - 1;
+					stat_commit (tab, cap, l[0], xe - xs + 1, Lmm.vmin(), Lmm.vmax(), xs, xe, y, y, D3 ? ztab : nullptr, z, z);
+				}
+				// ---- R ends with this lane: into the lane's cache
+				if (next_s0 && l[SCAN_PX - 1] != 0)
+				{
+					const uint32_t xe = x0 + SCAN_PX - 1, cnt = xe - sx + 1;
+					if (c_lbl == l[SCAN_PX - 1])
+					{
+						c_cnt += cnt;
+						c_mm.join (cur);
+						c_xmin = min (c_xmin, sx);
+						c_xmax = max (c_xmax, xe);
+						c_ymin = min (c_ymin, y);
+						c_ymax = max (c_ymax, y);
+						c_zmin = min (c_zmin, z);
+						c_zmax = max (c_zmax, z);
+					}
+					else
+					{
+						if (c_lbl)
+							stat_commit (tab, cap, c_lbl, c_cnt, c_mm.vmin(), c_mm.vmax(), c_xmin, c_xmax, c_ymin, c_ymax, D3 ? ztab : nullptr, c_zmin, c_zmax);
+						c_lbl = l[SCAN_PX - 1]; c_cnt = cnt; c_mm = cur; c_xmin = sx; c_xmax = xe;
+						c_ymin = c_ymax = y;
+						c_zmin = c_zmax = z;
+					}
+				}
 			}
-			const uint32_t xe = x0 + a - 1;
-			stat_commit (tab, cap, l[0], cnt, mn, mx, xe - cnt + 1, xe, y, y, D3 ? ztab : nullptr, z, z);
-		}
-		// ---- runs strictly inside the lane (3 or 4 different runs in 4 pixels)
-		if (a < b)
-		{
-			const bool p1 = a == 1, p2 = b == 3;		// pixel 1 / pixel 2 belongs to neither L nor R
-			if (p1 && p2 && !s2)
+#pragma unroll
+			for (int k = 0; k < SCAN_PX; k++)
 			{
-				if (l[1] != 0)
-					stat_commit (tab, cap, l[1], 2, min (v[1], v[2]), max (v[1], v[2]), x0 + 1, x0 + 2, y, y, D3 ? ztab : nullptr, z, z);
-			}
-			else
-			{
-				if (p1 && l[1] != 0)
-					stat_commit (tab, cap, l[1], 1, v[1], v[1], x0 + 1, x0 + 1, y, y, D3 ? ztab : nullptr, z, z);
-				if (p2 && l[2] != 0)
-					stat_commit (tab, cap, l[2], 1, v[2], v[2], x0 + 2, x0 + 2, y, y, D3 ? ztab : nullptr, z, z);
-			}
-		}
-		// ---- R ends with this lane: into the lane's cache
-		if (next_s0 && l[3] != 0)
-		{
-			const uint32_t xe = x0 + 3, xs = xe - r_cnt + 1;
-			if (c_lbl == l[3])
-			{
-				c_cnt += r_cnt;
-				c_vmin = min (c_vmin, r_min);
-				c_vmax = max (c_vmax, r_max);
-				c_xmin = min (c_xmin, xs);
-				c_xmax = max (c_xmax, xe);
-				c_ymin = min (c_ymin, y);
-				c_ymax = max (c_ymax, y);
-				c_zmin = min (c_zmin, z);
-				c_zmax = max (c_zmax, z);
-			}
-			else
-			{
-				if (c_lbl)
-					stat_commit (tab, cap, c_lbl, c_cnt, c_vmin, c_vmax, c_xmin, c_xmax, c_ymin, c_ymax, D3 ? ztab : nullptr, c_zmin, c_zmax);
-				c_lbl = l[3]; c_cnt = r_cnt; c_vmin = r_min; c_vmax = r_max; c_xmin = xs; c_xmax = xe;
-				c_ymin = c_ymax = y;
-				c_zmin = c_zmax = z;
+				l[k] = ln[k];
+				p[k] = pn[k];
 			}
 		}
 	}
 	if (c_lbl)
-		stat_commit (tab, cap, c_lbl, c_cnt, c_vmin, c_vmax, c_xmin, c_xmax, c_ymin, c_ymax, D3 ? ztab : nullptr, c_zmin, c_zmax);
+		stat_commit (tab, cap, c_lbl, c_cnt, c_mm.vmin(), c_mm.vmax(), c_xmin, c_xmax, c_ymin, c_ymax, D3 ? ztab : nullptr, c_zmin, c_zmax);
 	maxlbl = __reduce_max_sync (0xffffffffu, maxlbl);
 	if (lane == 0 && maxlbl)
 		atomicMax (&info->max_label, maxlbl);

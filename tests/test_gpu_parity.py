@@ -103,10 +103,10 @@ def _phase1_expected(I, L):
 
 
 @pytest.mark.parametrize("H,W,kind", [(37, 256, "noise"), (64, 131, "noise"), (50, 1000, "runs"), (33, 515, "runs"), (200, 384, "one"),
-                                      (5, 3, "noise"), (300, 1028, "blocks")])
+                                      (5, 3, "noise"), (300, 1028, "blocks"), (70, 2056, "runs"), (40, 520, "noise"), (9, 8, "one")])
 def test_scan_run_segmentation_stress(H, W, kind):
     """label layouts that exercise every branch of the row-run scan: 1-pixel runs (3-4 runs inside one lane), runs crossing
-    lanes and 128-pixel chunks, a whole-image label (per-lane cache), widths with and without the 128-bit load path"""
+    lanes and 256-pixel chunks, a whole-image label (per-lane cache), widths with and without the 128-bit load path"""
     rng = np.random.default_rng(H * 1000 + W)
     if kind == "noise":
         L = rng.integers(0, 6, (H, W)).astype(np.uint32)
