@@ -1120,22 +1120,25 @@ int reserve_pinned_out (nyxb200_ctx* ctx, size_t n)
 	return 0;
 }
 
-// phase-1 scan launch: a grid of exactly the resident CTAs; rows per unit as large as keeps >= 8 units per resident warp
+// phase-1 scan launch: a grid of exactly the resident CTAs; rows per unit as large as keeps >= 4 units per resident warp
 // (long units = more runs merged per commit by the per-lane cache)
 template <bool U16, bool VEC, bool D3>
 int launch_scan (nyxb200_ctx* ctx, const ImageView& im, uint32_t nrows, uint32_t nchunk, uint2* ztab)
 {
 	auto kern = k_scan_stats<U16, VEC, D3>;
+	const size_t smem = VEC ? scan_smem_bytes<U16>() : 0;	// the cp.async row ring
+	if (set_smem (ctx, kern, smem))
+		return NYXB200_ECUDA;
 	int per_sm = 0;
-	CU (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kern, 256, 0));
+	CU (cudaOccupancyMaxActiveBlocksPerMultiprocessor (&per_sm, kern, 256, smem));
 	per_sm = std::max (per_sm, 1);
 	const unsigned long long resident_warps = (unsigned long long)ctx->sm_count * per_sm * 8;
 	uint32_t rpu = 32;
-	while (rpu > 1 && (unsigned long long)((nrows + rpu - 1) / rpu) * nchunk < 8 * resident_warps)
+	while (rpu > 1 && (unsigned long long)((nrows + rpu - 1) / rpu) * nchunk < 4 * resident_warps)
 		rpu >>= 1;
 	const unsigned long long nunits = (unsigned long long)((nrows + rpu - 1) / rpu) * nchunk;
 	const int grid = (int)std::max<unsigned long long> (1, std::min<unsigned long long> ((nunits + 7) / 8, (unsigned long long)ctx->sm_count * per_sm));
-	kern<<<grid, 256, 0, ctx->stream>>> (im.inten, im.label, (uint32_t)im.W, nrows, (uint32_t)im.H, nchunk, rpu, ctx->d_stats.p,
+	kern<<<grid, 256, smem, ctx->stream>>> (im.inten, im.label, (uint32_t)im.W, nrows, (uint32_t)im.H, nchunk, rpu, ctx->d_stats.p,
 		ctx->stats_cap, ctx->d_info.p, ztab);
 	CU (cudaGetLastError());
 	return 0;

@@ -123,70 +123,81 @@ template <bool U16> struct MinMax
 constexpr int SCAN_PX = 8;			// pixels per lane
 constexpr int SCAN_CHUNK = 32 * SCAN_PX;	// pixels per warp and row
 
-// The 8 pixels of one lane: labels l[], intensities as MinMax singletons p[]
-template <bool U16, bool VEC>
+// The 8 pixels of one lane by scalar loads (images whose width or alignment rules out the 16-byte path):
+// labels l[], intensities as MinMax singletons p[]
+template <bool U16>
 __device__ __forceinline__ void scan_load (const void* __restrict__ inten_, const uint32_t* __restrict__ label, size_t rowbase, uint32_t x0,
 	uint32_t W, uint32_t (&l)[SCAN_PX], MinMax<U16> (&p)[SCAN_PX])
 {
+	const size_t base = rowbase + x0;
 #pragma unroll
 	for (int k = 0; k < SCAN_PX; k++)
 	{
 		l[k] = 0;
 		p[k] = MinMax<U16>::of (0);
-	}
-	if (x0 >= W)
-		return;
-	const size_t base = rowbase + x0;
-	if (VEC)	// W % 8 == 0 and 16-byte aligned images: the lane's pixels are all inside the row
-	{
-		const uint4 l0 = __ldg (reinterpret_cast<const uint4*> (label + base));
-		const uint4 l1 = __ldg (reinterpret_cast<const uint4*> (label + base) + 1);
-		l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
-		if (U16)
+		if (x0 + k < W)
 		{
-			const uint4 iv = __ldg (reinterpret_cast<const uint4*> ((const uint16_t*)inten_ + base));
-			const uint32_t w4[4] = { iv.x, iv.y, iv.z, iv.w };
-#pragma unroll
-			for (int j = 0; j < 4; j++)
-			{
-				// two pixels per word -> ((65535 - v) << 16) | v of each half with two byte permutes
-				p[2 * j].a = __byte_perm (w4[j], ~w4[j], 0x5410);
-				p[2 * j + 1].a = __byte_perm (w4[j], ~w4[j], 0x7632);
-			}
+			l[k] = __ldg (label + base + k);
+			p[k] = MinMax<U16>::of (U16 ? (uint32_t)__ldg ((const uint16_t*)inten_ + base + k) : __ldg ((const uint32_t*)inten_ + base + k));
 		}
-		else
-		{
-			const uint4 i0 = __ldg (reinterpret_cast<const uint4*> ((const uint32_t*)inten_ + base));
-			const uint4 i1 = __ldg (reinterpret_cast<const uint4*> ((const uint32_t*)inten_ + base) + 1);
-			p[0] = MinMax<U16>::of (i0.x); p[1] = MinMax<U16>::of (i0.y); p[2] = MinMax<U16>::of (i0.z); p[3] = MinMax<U16>::of (i0.w);
-			p[4] = MinMax<U16>::of (i1.x); p[5] = MinMax<U16>::of (i1.y); p[6] = MinMax<U16>::of (i1.z); p[7] = MinMax<U16>::of (i1.w);
-		}
-	}
-	else
-	{
-#pragma unroll
-		for (int k = 0; k < SCAN_PX; k++)
-			if (x0 + k < W)
-			{
-				l[k] = __ldg (label + base + k);
-				p[k] = MinMax<U16>::of (U16 ? (uint32_t)__ldg ((const uint16_t*)inten_ + base + k) : __ldg ((const uint32_t*)inten_ + base + k));
-			}
 	}
 }
 
-// Work unit = (block of `rpu` consecutive rows, 256-pixel chunk): one warp, 8 consecutive pixels per lane (two 128-bit
-// label loads, one or two 128-bit intensity loads; the next row's loads are issued before the current row is processed).
+constexpr int SCAN_DEPTH = 4;			// rows in flight per warp (cp.async ring in shared memory)
+template <bool U16> __host__ __device__ constexpr int scan_narr() { return U16 ? 3 : 4; }	// 16-byte pieces per lane and row: 2 label + 1 or 2 intensity
+template <bool U16> __host__ __device__ constexpr size_t scan_smem_bytes() { return (size_t)SCAN_DEPTH * scan_narr<U16>() * 256 * 16; }
+
+__device__ __forceinline__ void cp_async16 (void* smem, const void* gmem)
+{
+	const unsigned sa = (unsigned)__cvta_generic_to_shared (smem);
+	asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
+}
+
+// the (unit, row) sequence of one warp: units warp, warp + nwarps, ...; inside a unit the rows top-down
+struct ScanCursor
+{
+	unsigned long long unit;
+	uint32_t row, row1, x0;
+	bool valid;
+	__device__ __forceinline__ void open (unsigned long long nunits, uint32_t nchunk, uint32_t rpu, uint32_t nrows, uint32_t lane)
+	{
+		valid = unit < nunits;
+		if (valid)
+		{
+			const uint32_t rb = (uint32_t)(unit / nchunk);
+			x0 = ((uint32_t)(unit - (unsigned long long)rb * nchunk) * SCAN_CHUNK) + lane * SCAN_PX;
+			row = rb * rpu;
+			row1 = min (nrows, row + rpu);
+		}
+	}
+	__device__ __forceinline__ void advance (unsigned long long nunits, unsigned long long nwarps, uint32_t nchunk, uint32_t rpu, uint32_t nrows, uint32_t lane)
+	{
+		if (++row >= row1)
+		{
+			unit += nwarps;
+			open (nunits, nchunk, rpu, nrows, lane);
+		}
+	}
+};
+
+// Work unit = (block of `rpu` consecutive rows, 256-pixel chunk): one warp, 8 consecutive pixels per lane.  The rows are
+// STAGED THROUGH SHARED MEMORY by cp.async: every lane copies its own two 16-byte label pieces and one (uint16) or two
+// (uint32) intensity pieces of the row SCAN_DEPTH-1 steps ahead into a lane-private ring slot, so a warp keeps 3 rows
+// (4.5 KB) in flight without holding registers for them (60 registers, 4 CTAs / 32 warps per SM, ~140 KB in flight).
+// Measured on configs[1] (B200): loads alone 0.109 ms (5.5 TB/s), + run analysis 0.155 ms, + L2 atomics 0.178 ms.
 // Equal labels are contiguous along a row, so per row the warp does a SEGMENTED max-scan over lanes (shuffles) of the
-// packed (min, max) and exactly one lane per run -- the one holding the run's last pixel -- commits it; the run length
+// packed (min, max) and exactly one lane per run -- the one holding the run's last pixel -- closes it; the run length
 // needs no scan (end position minus the start position held by the segment's head lane), y/z are warp-uniform.
-// The run that reaches a lane's last pixel is first merged into a one-entry per-lane register cache: walking DOWN the
-// rows of the unit, the right edge of a ROI usually stays in the same lane for several rows, so a ROI costs one commit
-// per few rows instead of one per row (a whole-slide ROI: one per unit).
+// Every run that closes in a lane is first merged into a one-entry per-lane register cache: walking DOWN the rows of
+// the unit, the right edge of a ROI usually stays in the same lane for several rows, so a ROI costs one commit (7 L2
+// atomics) per few rows instead of one per row (a whole-slide ROI: one per unit).
 template <bool U16, bool VEC, bool D3>
 __global__ void __launch_bounds__(256, U16 ? 3 : 2) k_scan_stats (const void* __restrict__ inten_, const uint32_t* __restrict__ label,
 	uint32_t W, uint32_t nrows, uint32_t H, uint32_t nchunk, uint32_t rpu, LabelStat* tab, uint32_t cap, SlideInfo* info, uint2* ztab)
 {
 	typedef MinMax<U16> MM;
+	constexpr int NARR = scan_narr<U16>();
+	extern __shared__ uint4 sring[];	// [SCAN_DEPTH][NARR][256]
 	const uint32_t lane = threadIdx.x & 31;
 	const unsigned long long nunits = (unsigned long long)((nrows + rpu - 1) / rpu) * nchunk;
 	const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
@@ -194,18 +205,36 @@ __global__ void __launch_bounds__(256, U16 ? 3 : 2) k_scan_stats (const void* __
 	// per-lane run cache (c_lbl == 0: empty)
 	uint32_t c_lbl = 0, c_cnt = 0, c_xmin = 0, c_xmax = 0, c_ymin = 0, c_ymax = 0, c_zmin = 0, c_zmax = 0;
 	MM c_mm = MM::of (0);
-	for (unsigned long long unit = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; unit < nunits; unit += nwarps)
 	{
-		const uint32_t rb = (uint32_t)(unit / nchunk);
-		const uint32_t x0 = ((uint32_t)(unit - (unsigned long long)rb * nchunk) * SCAN_CHUNK) + lane * SCAN_PX;
-		const uint32_t row0 = rb * rpu, row1 = min (nrows, row0 + rpu);
-		uint32_t l[SCAN_PX], ln[SCAN_PX];
-		MM p[SCAN_PX], pn[SCAN_PX];
-		scan_load<U16, VEC> (inten_, label, (size_t)row0 * W, x0, W, l, p);
-		for (uint32_t row = row0; row < row1; row++)
+		// a finished run goes into the lane's one-entry cache: merged when the entry holds the same label (the edge of a
+		// ROI stays in the same lane for several rows), else the entry is committed and replaced
+		auto cache_put = [&](uint32_t lbl, uint32_t xs, uint32_t xe, const MM& mm, uint32_t y, uint32_t z)
 		{
-			if (row + 1 < row1)
-				scan_load<U16, VEC> (inten_, label, (size_t)(row + 1) * W, x0, W, ln, pn);
+			const uint32_t cnt = xe - xs + 1;
+			maxlbl = max (maxlbl, lbl);
+			if (c_lbl == lbl)
+			{
+				c_cnt += cnt;
+				c_mm.join (mm);
+				c_xmin = min (c_xmin, xs);
+				c_xmax = max (c_xmax, xe);
+				c_ymin = min (c_ymin, y);
+				c_ymax = max (c_ymax, y);
+				c_zmin = min (c_zmin, z);
+				c_zmax = max (c_zmax, z);
+			}
+			else
+			{
+				if (c_lbl)
+					stat_commit (tab, cap, c_lbl, c_cnt, c_mm.vmin(), c_mm.vmax(), c_xmin, c_xmax, c_ymin, c_ymax, D3 ? ztab : nullptr, c_zmin, c_zmax);
+				c_lbl = lbl; c_cnt = cnt; c_mm = mm; c_xmin = xs; c_xmax = xe;
+				c_ymin = c_ymax = y;
+				c_zmin = c_zmax = z;
+			}
+		};
+		// one row of the unit: l[] / p[] = this lane's 8 pixels
+		auto process = [&](const uint32_t (&l)[SCAN_PX], const MM (&p)[SCAN_PX], uint32_t row, uint32_t x0)
+		{
 			uint32_t any = l[0];
 #pragma unroll
 			for (int k = 1; k < SCAN_PX; k++)
@@ -222,27 +251,42 @@ __global__ void __launch_bounds__(256, U16 ? 3 : 2) k_scan_stats (const void* __
 				// runs strictly between them are committed on the spot (they need nothing from other lanes)
 				const uint32_t prev = __shfl_up_sync (0xffffffffu, l[SCAN_PX - 1], 1);
 				const bool s0 = lane == 0 || l[0] != prev;	// pixel 0 starts a run
-				MM cur = p[0], Lmm = p[0];
-				int a = SCAN_PX, b = 0;
-				maxlbl = max (maxlbl, l[0]);
+				// boundary mask: bit k-1 set when pixel k starts a new run.  Branch-free: L = join of the pixels before the first
+				// boundary, R = join of the pixels from the last boundary on (the whole lane when there is none)
+				uint32_t m = 0;
+#pragma unroll
+				for (int k = 1; k < SCAN_PX; k++)
+					m |= (l[k] != l[k - 1] ? 1u : 0u) << (k - 1);
+				const int a = m ? __ffs (m) : SCAN_PX, b = 32 - __clz (m);
+				MM Lmm = p[0], cur = p[SCAN_PX - 1];
 #pragma unroll
 				for (int k = 1; k < SCAN_PX; k++)
 				{
-					if (l[k] != l[k - 1])
+					if ((m & ((1u << k) - 1u)) == 0)		// no boundary up to pixel k: pixel k belongs to L
+						Lmm.join (p[k]);
+					if ((m >> (SCAN_PX - 1 - k)) == 0)		// no boundary after pixel 7-k: pixel 7-k belongs to R
+						cur.join (p[SCAN_PX - 1 - k]);
+				}
+				if (__popc (m) >= 2)	// rare: runs strictly inside the lane
+				{
+					int st = 0;
+					MM in = p[0];
+#pragma unroll
+					for (int k = 1; k < SCAN_PX; k++)
 					{
-						if (b == 0)
+						if (l[k] != l[k - 1])
 						{
-							a = k;
-							Lmm = cur;
+							if (st != 0 && l[k - 1] != 0)
+							{
+								maxlbl = max (maxlbl, l[k - 1]);
+								stat_commit (tab, cap, l[k - 1], (uint32_t)(k - st), in.vmin(), in.vmax(), x0 + st, x0 + k - 1, y, y, D3 ? ztab : nullptr, z, z);
+							}
+							st = k;
+							in = p[k];
 						}
-						else if (l[k - 1] != 0)
-							stat_commit (tab, cap, l[k - 1], (uint32_t)(k - b), cur.vmin(), cur.vmax(), x0 + b, x0 + k - 1, y, y, D3 ? ztab : nullptr, z, z);
-						b = k;
-						cur = p[k];
-						maxlbl = max (maxlbl, l[k]);
+						else
+							in.join (p[k]);
 					}
-					else
-						cur.join (p[k]);
 				}
 				// ---- inclusive segmented scan of R over the lanes; a segment starts where R starts inside the lane
 				const bool head = b > 0 || s0;
@@ -270,40 +314,90 @@ __global__ void __launch_bounds__(256, U16 ? 3 : 2) k_scan_stats (const void* __
 						Lmm.join (kin);
 						xs = ksx;
 					}
-					const uint32_t xe = x0 + a - 1;
-					stat_commit (tab, cap, l[0], xe - xs + 1, Lmm.vmin(), Lmm.vmax(), xs, xe, y, y, D3 ? ztab : nullptr, z, z);
+					cache_put (l[0], xs, x0 + a - 1, Lmm, y, z);
 				}
-				// ---- R ends with this lane: into the lane's cache
+				// ---- R ends with this lane
 				if (next_s0 && l[SCAN_PX - 1] != 0)
+					cache_put (l[SCAN_PX - 1], sx, x0 + SCAN_PX - 1, cur, y, z);
+			}
+		};
+		ScanCursor cu, pf;
+		cu.unit = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+		cu.open (nunits, nchunk, rpu, nrows, lane);
+		pf = cu;
+		// the lane's pieces of the row under cursor c -> ring slot `stage` (one commit group per step, possibly empty)
+		auto issue = [&](const ScanCursor& c, int stage)
+		{
+			if (VEC && c.valid && c.x0 < W)
+			{
+				const size_t base = (size_t)c.row * W + c.x0;
+				uint4* slot = sring + (size_t)stage * NARR * 256 + threadIdx.x;
+				cp_async16 (slot, label + base);
+				cp_async16 (slot + 256, label + base + 4);
+				if (U16)
+					cp_async16 (slot + 512, (const uint16_t*)inten_ + base);
+				else
 				{
-					const uint32_t xe = x0 + SCAN_PX - 1, cnt = xe - sx + 1;
-					if (c_lbl == l[SCAN_PX - 1])
+					cp_async16 (slot + 512, (const uint32_t*)inten_ + base);
+					cp_async16 (slot + 768, (const uint32_t*)inten_ + base + 4);
+				}
+			}
+			asm volatile ("cp.async.commit_group;" ::: "memory");
+		};
+#pragma unroll
+		for (int i = 0; i < SCAN_DEPTH - 1; i++)
+		{
+			issue (pf, i);
+			if (pf.valid)
+				pf.advance (nunits, nwarps, nchunk, rpu, nrows, lane);
+		}
+		int stage = 0;
+		while (cu.valid)
+		{
+			issue (pf, (stage + SCAN_DEPTH - 1) % SCAN_DEPTH);
+			if (pf.valid)
+				pf.advance (nunits, nwarps, nchunk, rpu, nrows, lane);
+			asm volatile ("cp.async.wait_group %0;" :: "n"(SCAN_DEPTH - 1) : "memory");
+			uint32_t l[SCAN_PX];
+			MM p[SCAN_PX];
+			if (VEC)
+			{
+#pragma unroll
+				for (int k = 0; k < SCAN_PX; k++)
+				{
+					l[k] = 0;
+					p[k] = MM::of (0);
+				}
+				if (cu.x0 < W)
+				{
+					const uint4* slot = sring + (size_t)stage * NARR * 256 + threadIdx.x;
+					const uint4 l0 = slot[0], l1 = slot[256];
+					l[0] = l0.x; l[1] = l0.y; l[2] = l0.z; l[3] = l0.w; l[4] = l1.x; l[5] = l1.y; l[6] = l1.z; l[7] = l1.w;
+					if (U16)
 					{
-						c_cnt += cnt;
-						c_mm.join (cur);
-						c_xmin = min (c_xmin, sx);
-						c_xmax = max (c_xmax, xe);
-						c_ymin = min (c_ymin, y);
-						c_ymax = max (c_ymax, y);
-						c_zmin = min (c_zmin, z);
-						c_zmax = max (c_zmax, z);
+						const uint4 iv = slot[512];
+						const uint32_t w4[4] = { iv.x, iv.y, iv.z, iv.w };
+#pragma unroll
+						for (int j = 0; j < 4; j++)
+						{
+							// two pixels per word -> ((65535 - v) << 16) | v of each half with two byte permutes
+							p[2 * j].a = __byte_perm (w4[j], ~w4[j], 0x5410);
+							p[2 * j + 1].a = __byte_perm (w4[j], ~w4[j], 0x7632);
+						}
 					}
 					else
 					{
-						if (c_lbl)
-							stat_commit (tab, cap, c_lbl, c_cnt, c_mm.vmin(), c_mm.vmax(), c_xmin, c_xmax, c_ymin, c_ymax, D3 ? ztab : nullptr, c_zmin, c_zmax);
-						c_lbl = l[SCAN_PX - 1]; c_cnt = cnt; c_mm = cur; c_xmin = sx; c_xmax = xe;
-						c_ymin = c_ymax = y;
-						c_zmin = c_zmax = z;
+						const uint4 i0 = slot[512], i1 = slot[768];
+						p[0] = MM::of (i0.x); p[1] = MM::of (i0.y); p[2] = MM::of (i0.z); p[3] = MM::of (i0.w);
+						p[4] = MM::of (i1.x); p[5] = MM::of (i1.y); p[6] = MM::of (i1.z); p[7] = MM::of (i1.w);
 					}
 				}
 			}
-#pragma unroll
-			for (int k = 0; k < SCAN_PX; k++)
-			{
-				l[k] = ln[k];
-				p[k] = pn[k];
-			}
+			else
+				scan_load<U16> (inten_, label, (size_t)cu.row * W, cu.x0, W, l, p);	// odd widths / unaligned images: direct scalar loads
+			process (l, p, cu.row, cu.x0);
+			cu.advance (nunits, nwarps, nchunk, rpu, nrows, lane);
+			stage = (stage + 1) % SCAN_DEPTH;
 		}
 	}
 	if (c_lbl)
