@@ -91,6 +91,17 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def cpu_sample_side(ref, synth, cores, target_s):
+    """side of the configs[1]-style crop the CPU reference needs about target_s seconds for (probe: a 1550^2 crop)"""
+    probe = 1550
+    pi, pl = synth.config2(seed=2, size=probe)
+    t0 = time.perf_counter()
+    ref.featurize_2d(pi.astype(np.uint32), pl, greydepth=64, ibsi=False, nthreads=cores)
+    dt = max(time.perf_counter() - t0, 1e-3)
+    side = int(probe * (target_s / dt) ** 0.5)
+    return max(31 * 20, min(10000, side // 31 * 31))
+
+
 def reference_arm(args, rank, world):
     """The reference's own CPU implementation on the host cores (rank 0 only)."""
     if rank != 0:
@@ -101,7 +112,7 @@ def reference_arm(args, rank, world):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libnyxus_ref.so not built (run oracle/Makefile.ref where /root/reference exists)"}))
         return
     cores = os.cpu_count() or 1
-    crop = args.ref_crop
+    crop = args.ref_crop if args.ref_crop > 0 else cpu_sample_side(ref, synth, cores, target_s=4.0)
     inten, label = synth.config2(seed=2, size=crop)
     inten32 = inten.astype(np.uint32)
     times = []
@@ -133,7 +144,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, default=10000, help="slide side (configs[1] = 10000)")
-    ap.add_argument("--ref-crop", type=int, default=3000, help="side of the crop the CPU reference is timed on")
+    ap.add_argument("--ref-crop", type=int, default=0, help="side of the crop the CPU reference is timed on (0 = sized from a probe: "
+                    "~4 s per step for --impl reference, ~15 s for the cpu_baseline of the default arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
@@ -268,11 +280,21 @@ def main():
         for f, nc in ncol_fam.items():
             if f != "intensity":
                 alg[f] = nfg * 2 + nroi * nc * 8
+        # DRAM bytes per step of every stage from the committed `ncu --set full` capture (dram__bytes_read.sum +
+        # dram__bytes_write.sum, summed over the stage's launches of one step; tools/ncu_traffic.py)
+        traffic = {}
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp) and args.size == 10000:
+            try:
+                traffic = json.load(open(tp))["bytes_per_step"]
+            except Exception:
+                traffic = {}
+
         def roof(stage):
             ms = per.get(stage, 0.0)
             a = alg.get(stage, 0) / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
             return {"kernel": stage, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
-                    "traffic": None, "ms_per_launch": ms, "algorithmic_bytes": alg.get(stage, 0), "peak_source": peak_src}
+                    "traffic": traffic.get(stage), "ms_per_launch": ms, "algorithmic_bytes": alg.get(stage, 0), "peak_source": peak_src}
         line = {
             "metric": METRIC, "value": total_rois * args.steps / ev_s, "unit": "ROIs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -301,7 +323,7 @@ def main():
             from oracle import ref
             if ref.available():
                 cores = os.cpu_count() or 1
-                crop = args.ref_crop
+                crop = args.ref_crop if args.ref_crop > 0 else cpu_sample_side(ref, synth, cores, target_s=15.0)
                 ci, cl = synth.config2(seed=2, size=crop)
                 t2 = time.perf_counter()
                 rl, _, tph = ref.featurize_2d(ci.astype(np.uint32), cl, greydepth=64, nthreads=cores)

@@ -541,7 +541,7 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 		gs = ctx->d_scratch[ctx->lsi].p;
 		CU (cudaMemsetAsync (gs, 0, (size_t)grid * famw * 4, ctx->ls));	// bodies expect (and leave) an all-zero region
 	}
-	auto kern = k_roi_family<FAM, P16>;
+	auto kern = gs ? k_roi_family<FAM, P16, true> : k_roi_family<FAM, P16, false>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
 	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out,
@@ -599,9 +599,10 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 		CU (ctx->d_scratch[ctx->lsi].reserve ((size_t)grid * memw));
 		gs = ctx->d_scratch[ctx->lsi].p;
 	}
-	if (set_smem (ctx, k_roi_intensity, smem_words * 4))
+	auto kern = gs ? k_roi_intensity<true> : k_roi_intensity<false>;
+	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
-	k_roi_intensity<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
+	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
 		ostride, gs, memw);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
@@ -632,7 +633,7 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 		gs = ctx->d_scratch[ctx->lsi].p;
 		CU (cudaMemsetAsync (gs, 0, (size_t)grid * famw * 4, ctx->ls));
 	}
-	auto kern = k_roi_family3<FAM3, P16>;
+	auto kern = gs ? k_roi_family3<FAM3, P16, true> : k_roi_family3<FAM3, P16, false>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
 	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,

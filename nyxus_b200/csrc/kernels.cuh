@@ -731,39 +731,51 @@ __global__ void __launch_bounds__(256) k_pack_tiles (ImageView im, const RoiRec*
 	uint16_t* tb = tileB ? tileB + r.tile_off : nullptr;
 	const size_t origin = (size_t)r.y0 * im.W + (size_t)r.x0;
 	uint32_t run = 0;
-	for (uint32_t base = 0; base < npad; base += 32)
+	constexpr int UN = 4;	// 32-cell chunks whose (independent) label and intensity loads are issued together
+	for (uint32_t base0 = 0; base0 < npad; base0 += 32 * UN)
 	{
-		const uint32_t i = base + lane;
-		bool in = false;
-		uint32_t v = 0;
-		if (i < ncell)
+		uint32_t lb[UN], vv[UN];
+#pragma unroll
+		for (int u = 0; u < UN; u++)
 		{
-			const uint32_t y = fw.div (i), x = i - y * (uint32_t)r.w;
-			const size_t g = origin + (size_t)y * im.W + x;
-			if (im.label[g] == r.label)
+			const uint32_t i = base0 + u * 32 + lane;
+			lb[u] = 0;
+			vv[u] = 0;
+			if (i < ncell)
 			{
-				in = true;
-				v = load_inten (im, g);
+				const uint32_t y = fw.div (i), x = i - y * (uint32_t)r.w;
+				const size_t g = origin + (size_t)y * im.W + x;
+				lb[u] = im.label[g];
+				vv[u] = load_inten (im, g);
 			}
 		}
-		if (i < npad)
+#pragma unroll
+		for (int u = 0; u < UN; u++)
 		{
-			if (ta)
+			const uint32_t i = base0 + u * 32 + lane;
+			if (base0 + u * 32 >= npad)
+				break;
+			const bool in = i < ncell && lb[u] == r.label;
+			const uint32_t v = in ? vv[u] : 0u;
+			if (i < npad)
 			{
-				uint32_t code = 0;
-				if (i < ncell)
-					code = (B.bin (v) & TILE16_LEVEL) | (v ? 0x8000u : 0u) | (in ? 0x4000u : 0u);
-				ta[i] = (uint16_t)code;
+				if (ta)
+				{
+					uint32_t code = 0;
+					if (i < ncell)
+						code = (B.bin (v) & TILE16_LEVEL) | (v ? 0x8000u : 0u) | (in ? 0x4000u : 0u);
+					ta[i] = (uint16_t)code;
+				}
+				if (tb)
+					tb[i] = in ? (uint16_t)((to_grayscale (v, 0, r.imax, (uint32_t)prm.greydepth, prm.ibsi != 0) & TILE16_LEVEL) | 0x4000u) : (uint16_t)0;
 			}
-			if (tb)
-				tb[i] = in ? (uint16_t)((to_grayscale (v, 0, r.imax, (uint32_t)prm.greydepth, prm.ibsi != 0) & TILE16_LEVEL) | 0x4000u) : (uint16_t)0;
-		}
-		if (dst)
-		{
-			const unsigned b = __ballot_sync (0xffffffffu, in);
-			if (in)
-				dst[run + __popc (b & ((1u << lane) - 1))] = v;
-			run += __popc (b);
+			if (dst)
+			{
+				const unsigned b = __ballot_sync (0xffffffffu, in);
+				if (in)
+					dst[run + __popc (b & ((1u << lane) - 1))] = v;
+				run += __popc (b);
+			}
 		}
 	}
 }
@@ -893,7 +905,10 @@ __device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, c
 }
 
 // CTA per ROI (GLCM / GLRLM: one warp per angle; every family for the larger tile classes)
-template <int FAM, bool P16>
+// GSCR: the family region lives in a per-CTA global-memory slot (classes whose matrices exceed shared memory).  A
+// template parameter, not a run-time select, so that in the common case the compiler sees a pure shared-memory pointer
+// and emits LDS / STS / ATOMS with 32-bit addressing instead of generic LD / ATOM with 64-bit address arithmetic.
+template <int FAM, bool P16, bool GSCR>
 __global__ void __launch_bounds__(ROI_THREADS) k_roi_family (ImageView im, const RoiRec* __restrict__ rois,
 	const uint32_t* __restrict__ list, uint32_t n, Params prm, int Lmax, uint32_t maxcells, int maxwh,
 	double* out, int out_stride, uint32_t* gscratch, size_t gwords, DebugOut dbg)
@@ -901,10 +916,10 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family (ImageView im, const
 	extern __shared__ __align__(16) uint32_t smem[];
 	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
 	uint32_t* cell = smem + RED_WORDS;
-	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : cell + tile_words (maxcells);
+	uint32_t* mem = GSCR ? gscratch + (size_t)blockIdx.x * gwords : cell + tile_words (maxcells);
 	// the family region is all zero on entry of every body and every body leaves it all zero again (owner-zeroing):
 	// cleared here once per CTA (the global scratch slots are cleared by the host before the launch)
-	if (!gscratch)
+	if (!GSCR)
 		for (size_t i = threadIdx.x; i < gwords; i += blockDim.x)
 			mem[i] = 0;
 	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
@@ -949,7 +964,7 @@ constexpr int NCOL3_INT = NCOL_INT, NCOL3_GLCM = NCOL_GLCM3, NCOL3_NGTDM = NCOL_
 constexpr int COL3_INT = 0, COL3_GLCM = COL3_INT + NCOL3_INT, COL3_NGTDM = COL3_GLCM + NCOL3_GLCM, COL3_GLSZM = COL3_NGTDM + NCOL3_NGTDM;
 constexpr int NCOL3_ALL = COL3_GLSZM + NCOL3_GLSZM;
 
-template <int FAM3, bool P16>
+template <int FAM3, bool P16, bool GSCR>
 __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, const RoiRec* __restrict__ rois,
 	const uint32_t* __restrict__ list, uint32_t n, Params prm, int greyinfo, int Lmax, uint32_t maxcells,
 	double* out, int out_stride, uint32_t* gscratch, size_t gwords)
@@ -957,8 +972,8 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 	extern __shared__ __align__(16) uint32_t smem[];
 	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
 	uint32_t* cell = smem + RED_WORDS;
-	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : cell + tile_words (maxcells);
-	if (!gscratch)
+	uint32_t* mem = GSCR ? gscratch + (size_t)blockIdx.x * gwords : cell + tile_words (maxcells);
+	if (!GSCR)
 		for (size_t i = threadIdx.x; i < gwords; i += blockDim.x)
 			mem[i] = 0;
 	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
@@ -981,13 +996,14 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 }
 
 // first-order: reads the ROI's CSR slice
+template <bool GSCR>
 __global__ void __launch_bounds__(ROI_THREADS) k_roi_intensity (const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
 	uint32_t n, Params prm, const uint32_t* __restrict__ cloud, uint32_t npad_max, double* out, int out_stride,
 	uint32_t* gscratch, size_t gwords)
 {
 	extern __shared__ __align__(16) uint32_t smem[];
 	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
-	uint32_t* mem = gscratch ? gscratch + (size_t)blockIdx.x * gwords : smem + RED_WORDS;
+	uint32_t* mem = GSCR ? gscratch + (size_t)blockIdx.x * gwords : smem + RED_WORDS;
 	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
 	{
 		const uint32_t ri = list ? list[k] : k;
