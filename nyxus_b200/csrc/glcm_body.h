@@ -377,7 +377,17 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	jmax = cta_max_u64 (g, jmax);
 	g.sync();
 
-	// ---- pass 3: restore the all-zero region
+	// ---- pass 3: restore the all-zero region: a small joint matrix is cheaper to wipe with 128-bit stores than to
+	// re-enumerate the pairs (Ng = 64, packed counters: 16 stores per lane), a large one is cleared cell by cell
+#if NYX_DEVICE_BUILD
+	if (jw * 4 <= (size_t)ncell * 24 && (jw & 3) == 0 && ((size_t)reg & 15) == 0)
+	{
+		uint4* j4 = reinterpret_cast<uint4*> (reg);
+		for (int i = g.tid; i < (int)(jw >> 2); i += g.nthr)
+			j4[i] = make_uint4 (0u, 0u, 0u, 0u);
+	}
+	else
+#endif
 	for (int i = g.tid; i < ncell; i += g.nthr)
 	{
 		int b, av;

@@ -26,8 +26,6 @@ struct DenseDebug
 	uint32_t* P;	// dense dump of the family's matrix, may be null
 };
 
-constexpr int CELL_AUX_SHIFT = 24;		// 4 spare bits of the tile word: the pixel's dependence count (stash between passes)
-constexpr uint32_t CELL_AUX = 0x0F000000u;
 
 // number of 8-neighbours q of cell (x,y) with (cell[q] & flag) and the same level
 NYX_D int nbr_same_level (const uint32_t* cell, int w, int h, int x, int y, uint32_t lv, uint32_t flag)
@@ -54,9 +52,10 @@ NYX_D int nbr_same_level (const uint32_t* cell, int w, int h, int x, int y, uint
 // ------------------------------------------------------------------------------------------------
 // GLDM: P[(Lmax+1)][10] + Si[Lmax+1] + Sj[10], all zero on entry and exit
 // ------------------------------------------------------------------------------------------------
-NYX_HD size_t gldm_smem_words (int Lmax)
+// (+ one byte per cell: the cell's dependence count, kept between the passes)
+NYX_HD size_t gldm_smem_words (int Lmax, uint32_t maxcells = 0)
 {
-	return (size_t)(Lmax + 1) * 11 + 10;
+	return (size_t)(Lmax + 1) * 11 + 10 + ((size_t)maxcells + 3) / 4;
 }
 
 NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t* cell, uint32_t* mem, int Lmax,
@@ -72,6 +71,7 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 	uint32_t* P = mem;				// [level][nd], nd in 1..9
 	uint32_t* Si = P + (size_t)(Lmax + 1) * 10;	// [level]
 	uint32_t* Sj = Si + (Lmax + 1);			// [nd]
+	uint8_t* aux = (uint8_t*)(Sj + 10);		// [ncell] dependence count of the cell (written in pass 1, read in passes 2-3)
 	FastDiv fw;
 	fw.init ((uint32_t)w);
 
@@ -91,7 +91,7 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 		const uint32_t lv = cc & CELL_LEVEL;
 		const int y = (int)fw.div ((uint32_t)i), x = i - y * w;
 		const int j = 1 + nbr_same_level (cell, w, h, x, y, lv, CELL_NZ);	// gldm.cpp:74-166
-		cell[i] = cc | ((uint32_t)j << CELL_AUX_SHIFT);
+		aux[i] = (uint8_t)j;
 		atom_add (c, P + (size_t)lv * 10 + j, 1u);
 		atom_add (c, Si + lv, 1u);
 		atom_add (c, Sj + j, 1u);
@@ -127,7 +127,7 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 		const uint32_t cc = cell[i];
 		if (!(cc & CELL_NZ))
 			continue;
-		const uint32_t lv = cc & CELL_LEVEL, j = (cc & CELL_AUX) >> CELL_AUX_SHIFT;
+		const uint32_t lv = cc & CELL_LEVEL, j = aux[i];
 		q2[0] += Si[lv];
 		q2[1] += Sj[j];
 		const double di = (double)lv - mui, dj = (double)j - muj;
@@ -145,7 +145,7 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 		const uint32_t cc = cell[i];
 		if (!(cc & CELL_NZ))
 			continue;
-		const uint32_t lv = cc & CELL_LEVEL, j = (cc & CELL_AUX) >> CELL_AUX_SHIFT;
+		const uint32_t lv = cc & CELL_LEVEL, j = aux[i];
 		P[(size_t)lv * 10 + j] = 0;
 		Si[lv] = 0;
 	}
@@ -175,9 +175,9 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 // NGLDM: the tile passed here carries to_grayscale() levels (see load_tile_ngldm);
 // P[(Lmax+1)][9] + Sg[Lmax+1] + Sr[9], all zero on entry and exit
 // ------------------------------------------------------------------------------------------------
-NYX_HD size_t ngldm_smem_words (int Lmax)
+NYX_HD size_t ngldm_smem_words (int Lmax, uint32_t maxcells = 0)
 {
-	return (size_t)(Lmax + 1) * 10 + 9;
+	return (size_t)(Lmax + 1) * 10 + 9 + ((size_t)maxcells + 3) / 4;
 }
 
 // tile for NGLDM: level = to_grayscale(i, 0, aux_max, greydepth, ibsi) (ngldm.cpp:42,126), CELL_IN = cloud mask
@@ -211,6 +211,7 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 	uint32_t* P = mem;				// [level 0..Lmax][matches 0..8]
 	uint32_t* Sg = P + (size_t)(Lmax + 1) * 9;	// [level]
 	uint32_t* Sr = Sg + (Lmax + 1);			// [matches]
+	uint8_t* aux = (uint8_t*)(Sr + 9);		// [ncell] match count of the cell (written in pass 1, read in passes 2-3)
 	FastDiv fw;
 	fw.init ((uint32_t)w);
 
@@ -230,7 +231,7 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 		const uint32_t lv = cc & CELL_LEVEL;
 		const int y = (int)fw.div ((uint32_t)i), x = i - y * w;
 		const int nm = nbr_same_level (cell, w, h, x, y, lv, CELL_IN);	// ngldm.cpp:116-154
-		cell[i] = cc | ((uint32_t)nm << CELL_AUX_SHIFT);
+		aux[i] = (uint8_t)nm;
 		atom_add (c, P + (size_t)lv * 9 + nm, 1u);
 		atom_add (c, Sg + lv, 1u);
 		atom_add (c, Sr + nm, 1u);
@@ -269,7 +270,7 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 		const uint32_t cc = cell[i];
 		if (!(cc & CELL_IN))
 			continue;
-		const uint32_t lv = cc & CELL_LEVEL, nm = (cc & CELL_AUX) >> CELL_AUX_SHIFT;
+		const uint32_t lv = cc & CELL_LEVEL, nm = aux[i];
 		const uint32_t v = P[(size_t)lv * 9 + nm];
 		q2[0] += Sg[lv];
 		q2[1] += Sr[nm];
@@ -288,7 +289,7 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 		const uint32_t cc = cell[i];
 		if (!(cc & CELL_IN))
 			continue;
-		const uint32_t lv = cc & CELL_LEVEL, nm = (cc & CELL_AUX) >> CELL_AUX_SHIFT;
+		const uint32_t lv = cc & CELL_LEVEL, nm = aux[i];
 		P[(size_t)lv * 9 + nm] = 0;
 		Sg[lv] = 0;
 	}

@@ -387,6 +387,23 @@ template <int N> NYX_D void cta_sum (const Cta& c, double (&v)[N])
 #endif
 }
 
+#if NYX_DEVICE_BUILD
+// exact warp-wide sum / max of 64-bit integers with redux.sync (one instruction per 32-bit piece instead of a
+// 5-step shuffle butterfly): 26 + 26 + 12 bit pieces cannot overflow a 32-bit lane sum
+NYX_D unsigned long long warp_sum_u64 (unsigned long long x)
+{
+	const uint32_t lo = (uint32_t)x & 0x3FFFFFFu, mid = (uint32_t)(x >> 26) & 0x3FFFFFFu, hi = (uint32_t)(x >> 52);
+	return (unsigned long long)__reduce_add_sync (0xffffffffu, lo) + ((unsigned long long)__reduce_add_sync (0xffffffffu, mid) << 26)
+		+ ((unsigned long long)__reduce_add_sync (0xffffffffu, hi) << 52);
+}
+NYX_D unsigned long long warp_max_u64 (unsigned long long x)
+{
+	const uint32_t hi = (uint32_t)(x >> 32), mh = __reduce_max_sync (0xffffffffu, hi);
+	const uint32_t ml = __reduce_max_sync (0xffffffffu, hi == mh ? (uint32_t)x : 0u);
+	return ((unsigned long long)mh << 32) | ml;
+}
+#endif
+
 template <int N> NYX_D void cta_sum_u64 (const Cta& c, unsigned long long (&v)[N])
 {
 #if NYX_DEVICE_BUILD
@@ -395,13 +412,7 @@ template <int N> NYX_D void cta_sum_u64 (const Cta& c, unsigned long long (&v)[N
 	{
 #pragma unroll
 		for (int k = 0; k < N; k++)
-		{
-			unsigned long long x = v[k];
-#pragma unroll
-			for (int o = 16; o > 0; o >>= 1)
-				x += __shfl_xor_sync (0xffffffffu, x, o);
-			v[k] = x;
-		}
+			v[k] = warp_sum_u64 (v[k]);
 		return;
 	}
 	const int lane = c.tid & 31, warp = c.tid >> 5, nw = (c.nthr + 31) >> 5;
@@ -409,10 +420,7 @@ template <int N> NYX_D void cta_sum_u64 (const Cta& c, unsigned long long (&v)[N
 #pragma unroll
 	for (int k = 0; k < N; k++)
 	{
-		unsigned long long x = v[k];
-#pragma unroll
-		for (int o = 16; o > 0; o >>= 1)
-			x += __shfl_xor_sync (0xffffffffu, x, o);
+		const unsigned long long x = warp_sum_u64 (v[k]);
 		if (lane == 0)
 			red[k * NW_MAX + warp] = x;
 	}
@@ -436,12 +444,7 @@ NYX_D unsigned long long cta_max_u64 (const Cta& c, unsigned long long x)
 #if NYX_DEVICE_BUILD
 	const int lane = c.tid & 31, warp = c.tid >> 5, nw = (c.nthr + 31) >> 5;
 	unsigned long long* red = (unsigned long long*)c.red;
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1)
-	{
-		unsigned long long y = __shfl_xor_sync (0xffffffffu, x, o);
-		x = y > x ? y : x;
-	}
+	x = warp_max_u64 (x);
 	if (c.wmode)
 		return x;
 	if (lane == 0)

@@ -102,14 +102,14 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 	}
 	if (fam_mask & 32)
 	{
-		std::vector<uint32_t> mem (gldm_smem_words (Lmax));
+		std::vector<uint32_t> mem (gldm_smem_words (Lmax, (uint32_t)ncell));
 		gldm_body (c, r, prm, cell.data(), mem.data(), Lmax, out + COL_GLDM, nullptr);
 	}
 	if (fam_mask & 64)
 	{
 		std::vector<uint32_t> cell2 (ncell);
 		load_tile_ngldm (c, im, r, prm, cell2.data());
-		std::vector<uint32_t> mem (ngldm_smem_words (Lmax));
+		std::vector<uint32_t> mem (ngldm_smem_words (Lmax, (uint32_t)ncell));
 		ngldm_body (c, r, prm, cell2.data(), mem.data(), Lmax, out + COL_NGLDM, nullptr);
 	}
 	if (fam_mask & 128)
