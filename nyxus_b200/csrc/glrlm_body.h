@@ -144,14 +144,19 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 	g.sync();
 
 	// ---- pass 3: restore the all-zero region
-	for (int i = g.tid; i < ncell; i += g.nthr)
+	if (pw + Lmax + Nr <= (size_t)ncell * 2)	// small matrix: wipe P, Ri, Cj (contiguous) with 128-bit stores
+		wipe_words (g, P, pw + Lmax + Nr);
+	else
 	{
-		const int len = rl[i];
-		if (len)
-			P[(size_t)((cell[i] & CELL_LEVEL) - 1) * Nr + (len - 1)] = 0;
+		for (int i = g.tid; i < ncell; i += g.nthr)
+		{
+			const int len = rl[i];
+			if (len)
+				P[(size_t)((cell[i] & CELL_LEVEL) - 1) * Nr + (len - 1)] = 0;
+		}
+		for (int k = g.tid; k < Lmax + Nr; k += g.nthr)
+			Ri[k] = 0;
 	}
-	for (int k = g.tid; k < Lmax + Nr; k += g.nthr)
-		Ri[k] = 0;
 	g.sync();
 
 	if (g.tid == 0)

@@ -343,6 +343,26 @@ NYX_D void atom_add64 (const Cta&, unsigned long long* p, unsigned long long v)
 #endif
 }
 
+// zero n 32-bit words (128-bit stores when the range is 16-byte aligned): small dense matrices are cheaper to wipe
+// than to clear cell by cell through a re-enumeration of their owners
+template <class C> NYX_D void wipe_words (const C& c, uint32_t* p, size_t n)
+{
+#if NYX_DEVICE_BUILD
+	if (((size_t)p & 15) == 0)
+	{
+		uint4* p4 = reinterpret_cast<uint4*> (p);
+		const int n4 = (int)(n >> 2);
+		for (int i = c.tid; i < n4; i += c.nthr)
+			p4[i] = make_uint4 (0u, 0u, 0u, 0u);
+		for (int i = (n4 << 2) + c.tid; i < (int)n; i += c.nthr)
+			p[i] = 0;
+		return;
+	}
+#endif
+	for (size_t i = c.tid; i < n; i += c.nthr)
+		p[i] = 0;
+}
+
 // Block-wide sum of N doubles; the result is broadcast into v[] of every thread.  Fixed tree => deterministic.
 template <int N> NYX_D void cta_sum (const Cta& c, double (&v)[N])
 {

@@ -540,15 +540,20 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	cta_sum<3> (c, t);
 	c.sync();
 	// ---- pass 3: restore the all-zero region
-	for (int i = c.tid; i < ncell; i += c.nthr)
+	if ((size_t)(Lmax + 1) * (Nd + 1) + Nd <= (size_t)ncell * 2)	// small matrix: wipe P, Ri, Cd (contiguous) with 128-bit stores
+		wipe_words (c, P, (size_t)(Lmax + 1) * (Nd + 1) + Nd);
+	else
 	{
-		const uint32_t lv = cell[i] & CELL_LEVEL;
-		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
-			continue;
-		P[(size_t)lv * Nd + zmin[i]] = 0;
+		for (int i = c.tid; i < ncell; i += c.nthr)
+		{
+			const uint32_t lv = cell[i] & CELL_LEVEL;
+			if ((ibsi && !lv) || parent[i] != (uint32_t)i)
+				continue;
+			P[(size_t)lv * Nd + zmin[i]] = 0;
+		}
+		for (int k = c.tid; k < Lmax + 1 + Nd; k += c.nthr)
+			Ri[k] = 0;
 	}
-	for (int k = c.tid; k < Lmax + 1 + Nd; k += c.nthr)
-		Ri[k] = 0;
 	c.sync();
 	if (c.tid == 0)
 	{
