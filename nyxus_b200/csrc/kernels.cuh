@@ -933,7 +933,7 @@ __global__ void __launch_bounds__(ROI_THREADS, FAM == FAM_GLCM ? 4 : FAM == FAM_
 // WARP per ROI (single-matrix families on small tiles): every warp of the CTA owns a private shared-memory slice
 // (tile + family region) and walks its own ROIs -- no block-wide barrier anywhere, reductions are shuffle trees.
 template <int FAM>
-__global__ void __launch_bounds__(ROI_THREADS, (FAM == FAM_GLDM || FAM == FAM_NGLDM) ? 8 : 1) k_roi_family_w (ImageView im, const RoiRec* __restrict__ rois,
+__global__ void __launch_bounds__(ROI_THREADS, (FAM == FAM_GLDM || FAM == FAM_NGLDM) ? 8 : FAM == FAM_NGTDM ? 7 : 1) k_roi_family_w (ImageView im, const RoiRec* __restrict__ rois,
 	const uint32_t* __restrict__ list, uint32_t n, Params prm, int Lmax, uint32_t maxcells, int maxwh,
 	double* out, int out_stride, size_t famw)
 {
