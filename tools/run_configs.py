@@ -4,14 +4,14 @@
   C4  512^3 volume, 2197 ROIs, 3D GLCM / GLSZM / NGTDM + first-order     (resident)
   C5  a job of N configs[1] slides from pinned host memory, *ALL_TEXTURE* + *ALL_INTENSITY* (pipelined list call) --
       what ONE GPU of the 64-slide job does
-usage: run_configs.py [c1,c3,c4,c5] [n_slides_c5]    -> prints one JSON line per config (profiles/r1_configs_*.json)"""
+usage: run_configs.py [c1,c2ibsi,c3,c4,c5] [n_slides_c5]    -> prints one JSON line per config (profiles/r1_configs_*.json)"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from nyxus_b200 import Engine, synth
 
-which = (sys.argv[1] if len(sys.argv) > 1 else "c1,c3,c4,c5").split(",")
+which = (sys.argv[1] if len(sys.argv) > 1 else "c1,c2ibsi,c3,c4,c5").split(",")
 n5 = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 
 
@@ -34,6 +34,21 @@ if "c1" in which:
                       "rois": int(tab.shape[0]), "rois_per_s": tab.shape[0] / dt, "mpix_per_s": I.size / dt / 1e6,
                       "stage_ms": {k: round(v, 3) for k, v in eng.timings().items() if v > 0.001}}), flush=True)
     eng.close()
+
+if "c2ibsi" in which:
+    # second sweep with ibsi=True on configs[1] after re-quantising the intensities to <= 256 levels
+    I, L = synth.config2(seed=2)
+    Iq = (I >> 8).astype(np.uint16)                       # 0..255 (zeros stay zeros)
+    d_i = torch.from_numpy(Iq).cuda()
+    d_l = torch.from_numpy(L.view(np.int32)).cuda()
+    eng = Engine(["*ALL_TEXTURE*", "*ALL_INTENSITY*"], ibsi=True)
+    H, W = I.shape
+    dt, (tab, _) = timed(lambda: eng.featurize_ptr(d_i.data_ptr(), True, d_l.data_ptr(), 1, H, W, on_device=True, copy=False))
+    print(json.dumps({"config": "C2 with ibsi=True, intensities re-quantised to 8 bits (>> 8), *ALL_TEXTURE*+*ALL_INTENSITY*, resident",
+                      "ms": dt * 1e3, "rois": int(tab.shape[0]), "rois_per_s": tab.shape[0] / dt, "mpix_per_s": I.size / dt / 1e6,
+                      "stage_ms": {k: round(v, 3) for k, v in eng.timings().items() if v > 0.001}}), flush=True)
+    eng.close()
+    del d_i, d_l
 
 if "c3" in which:
     I, L = synth.config3()
