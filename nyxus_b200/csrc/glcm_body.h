@@ -313,6 +313,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	for (int k = 0; k < M_N; k++)
 		m[k] = 0;
 	int nx = 0, ny = 0;
+	unsigned long long cmax = 0, rmax = 0;
 	for (int base = 0; base < 2 * Ng; base += g.nthr)
 	{
 		const int k = base + g.tid;
@@ -326,15 +327,99 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		if (k < 2 * Ng)
 			sv = SPP[k];
 		glcm_marginal_terms (k, Ng, cv, rv, dv, sv, N, mr, mc, diffavg, NgD, m, px, py);
-		const unsigned bx = g.ballot (cv != 0), by = g.ballot (rv != 0);
-		if (cv)
-			pxc[nx + popc32 (bx & g.lanemask_lt())] = (double)cv / N;
-		if (rv)
-			pyc[ny + popc32 (by & g.lanemask_lt())] = (double)rv / N;
-		nx += popc32 (bx);
-		ny += popc32 (by);
+		nx += popc32 (g.ballot (cv != 0));
+		ny += popc32 (g.ballot (rv != 0));
+		cmax = cv > cmax ? cv : cmax;
+		rmax = rv > rmax ? rv : rmax;
 	}
-	g.sync();	// px/py and the compacted lists visible
+	cmax = cta_max_u64 (g, cmax);
+	rmax = cta_max_u64 (g, rmax);
+	// ---- the marginals as lists of DISTINCT values with multiplicities (for HXY2): px[i] = C[i] / N takes few distinct
+	// values (a ROI of some hundred pixels over ~50 levels has column counts 1..~20), and the HXY2 term of a pair of levels
+	// depends on (C[i], R[j]) only.  Counts below 2 Ng are bucketed in two tables that live in the list region itself;
+	// lists: pxc[i] / pyc[j] = value, mxl[i] / myl[j] = number of levels that have it (in the marginal region, which is
+	// dead after this point and zeroed again after HXY2).
+	uint32_t* mxl = Rm;			// [<= Ng]
+	uint32_t* myl = Rm + Ng;		// [<= Ng]
+	uint32_t* cxl = Rm + 2 * Ng;		// [<= Ng] the distinct column counts
+	uint32_t* cyl = Rm + 3 * Ng;		// [<= Ng] the distinct row counts
+	int ndx = 0, ndy = 0;
+	const int T = 2 * Ng;
+	uint32_t* TX = (uint32_t*)pxc;		// [2 Ng] levels per column count
+	uint32_t* TY = (uint32_t*)pyc;		// [2 Ng] levels per row count
+	if (cmax < (unsigned long long)T && rmax < (unsigned long long)T)
+	{
+		for (int k = g.tid; k < 2 * T; k += g.nthr)
+			TX[k] = 0;
+		g.sync();
+		for (int k = g.tid; k < Ng; k += g.nthr)
+		{
+			const uint32_t cv = Cm[k], rv = Rm[k];
+			if (cv)
+				atom_add (g, TX + cv, 1u);
+			if (rv)
+				atom_add (g, TY + rv, 1u);
+		}
+		g.sync();
+		for (int base = 0; base < T; base += g.nthr)	// ascending count order: deterministic lists
+		{
+			const int cval = base + g.tid;
+			const uint32_t tx = cval < T ? TX[cval] : 0u, ty = cval < T ? TY[cval] : 0u;
+			const unsigned bx = g.ballot (tx != 0), by = g.ballot (ty != 0);
+			g.sync();	// every lane has read Rm / Cm (previous loop) before the lists overwrite them
+			if (tx)
+			{
+				const int pos = ndx + popc32 (bx & g.lanemask_lt());
+				cxl[pos] = (uint32_t)cval;
+				mxl[pos] = tx;
+			}
+			if (ty)
+			{
+				const int pos = ndy + popc32 (by & g.lanemask_lt());
+				cyl[pos] = (uint32_t)cval;
+				myl[pos] = ty;
+			}
+			ndx += popc32 (bx);
+			ndy += popc32 (by);
+		}
+		g.sync();
+		for (int i = g.tid; i < ndx; i += g.nthr)	// (the tables are dead: their region becomes the value lists)
+			pxc[i] = (double)cxl[i] / N;
+		g.sync();
+		for (int j = g.tid; j < ndy; j += g.nthr)
+			pyc[j] = (double)cyl[j] / N;
+	}
+	else
+	{
+		// large counts: one list entry per non-empty level, multiplicity 1
+		uint32_t* tmpx = cxl;	// counts first (the marginals are overwritten by the lists)
+		uint32_t* tmpy = cyl;
+		for (int base = 0; base < Ng; base += g.nthr)
+		{
+			const int k = base + g.tid;
+			const uint32_t cv = k < Ng ? Cm[k] : 0u, rv = k < Ng ? Rm[k] : 0u;
+			const unsigned bx = g.ballot (cv != 0), by = g.ballot (rv != 0);
+			g.sync();
+			if (cv)
+				tmpx[ndx + popc32 (bx & g.lanemask_lt())] = cv;
+			if (rv)
+				tmpy[ndy + popc32 (by & g.lanemask_lt())] = rv;
+			ndx += popc32 (bx);
+			ndy += popc32 (by);
+		}
+		g.sync();
+		for (int i = g.tid; i < ndx; i += g.nthr)
+		{
+			pxc[i] = (double)tmpx[i] / N;
+			mxl[i] = 1;
+		}
+		for (int j = g.tid; j < ndy; j += g.nthr)
+		{
+			pyc[j] = (double)tmpy[j] / N;
+			myl[j] = 1;
+		}
+	}
+	g.sync();	// px/py and the lists visible
 	cta_sum<M_N> (g, m);
 
 	// ---- pass 2: owner-computes terms of the joint cells
@@ -397,23 +482,22 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		if (sym)
 			J.clear (av * Ng + b);
 	}
-	for (int k = g.tid; k < 5 * Ng; k += g.nthr)
-		Rm[k] = 0;
 
-	// ---- HXY2 over the outer product of the non-empty marginals (glcm.cpp:905-911)
+	// ---- HXY2 over the outer product of the non-empty marginals (glcm.cpp:905-911), one term per pair of DISTINCT
+	// marginal values weighted by the number of level pairs that share it
 	double hxy2[1] = { 0 };
 	{
-		// flat index k = ii * ny + jj, advanced by nthr per step without a division
-		const int tot = nx * ny, nyy = ny > 0 ? ny : 1;
+		// flat index k = ii * ndy + jj, advanced by nthr per step without a division
+		const int tot = ndx * ndy, nyy = ndy > 0 ? ndy : 1;
 		int ii = g.tid / nyy, jj = g.tid - ii * nyy;
 		const int di = g.nthr / nyy, dj = g.nthr - di * nyy;
 		for (int k = g.tid; k < tot; k += g.nthr)
 		{
 			const double qv = dmul (pxc[ii], pyc[jj]);
-			hxy2[0] += dmul (qv, fast_log10 (dadd (qv, GLCM_EPSILON)));
+			hxy2[0] += (double)(mxl[ii] * myl[jj]) * dmul (qv, fast_log10 (dadd (qv, GLCM_EPSILON)));
 			ii += di;
 			jj += dj;
-			if (jj >= nyy)
+			while (jj >= nyy)
 			{
 				jj -= nyy;
 				ii++;
@@ -421,6 +505,9 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		}
 	}
 	cta_sum<1> (g, hxy2);
+	g.sync();	// the lists have been read: the marginal region goes back to all zero
+	for (int k = g.tid; k < 5 * Ng; k += g.nthr)
+		Rm[k] = 0;
 	g.sync();	// the region (incl. px/py/lists) may be reused by the next ROI
 
 	// ---- features of this angle
