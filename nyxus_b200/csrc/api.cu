@@ -284,6 +284,16 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out)
 			lnt[k] = k ? std::log ((double)k) : -INFINITY;
 		if ((e = cudaMemcpyToSymbol (g_ln_table, lnt, sizeof (lnt))) != cudaSuccess)
 			return fail (nullptr, NYXB200_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString (e));
+		static KWeights kwt[KW_TABLE_N];
+		for (uint32_t k = 0; k < KW_TABLE_N; k++)
+		{
+			const double kd = (double)k;
+			kwt[k].inv1pk2 = 1.0 / (1.0 + kd * kd);
+			kwt[k].inv1pk = 1.0 / (1.0 + kd);
+			kwt[k].invk2 = k ? 1.0 / (kd * kd) : 0.0;
+		}
+		if ((e = cudaMemcpyToSymbol (g_kw_table, kwt, sizeof (kwt))) != cudaSuccess)
+			return fail (nullptr, NYXB200_ECUDA, "cudaMemcpyToSymbol: %s", cudaGetErrorString (e));
 	}
 	nyxb200_ctx* ctx = new nyxb200_ctx();
 	ctx->st = *s;

@@ -101,12 +101,13 @@ NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned l
 		if (dv)
 		{
 			const double pm = (double)dv / N, kd = (double)k;
-			m[M_IDM] += pm / (1.0 + kd * kd);		// :685-687, HOM2 :1069
-			m[M_ID] += pm / (1.0 + kd);			// :1096-1097, HOM1 :942
-			m[M_IDN] += pm / (1.0 + kd / NgD);		// :1110-1111
-			m[M_IDMN] += pm / (1.0 + (kd * kd) / (NgD * NgD));	// :1082-1084
+			const KWeights kw = k_weights ((uint32_t)k);	// (reciprocal products instead of the reference's divisions: <= 2 ulp)
+			m[M_IDM] += pm * kw.inv1pk2;			// pm / (1 + k^2)		:685-687, HOM2 :1069
+			m[M_ID] += pm * kw.inv1pk;			// pm / (1 + k)			:1096-1097, HOM1 :942
+			m[M_IDN] += pm * (NgD / (NgD + kd));		// pm / (1 + k / Ng)		:1110-1111
+			m[M_IDMN] += pm * ((NgD * NgD) / (NgD * NgD + kd * kd));	// pm / (1 + k^2 / Ng^2)	:1082-1084
 			if (k >= 1)
-				m[M_IV] += pm / (kd * kd);		// :1123-1128
+				m[M_IV] += pm * kw.invk2;		// pm / k^2			:1123-1128
 			m[M_DENT] += dmul (pm, fast_log10 (dadd (pm, GLCM_EPSILON)));	// :778-781
 			const double dd = kd - diffavg;
 			m[M_DVAR] += dd * dd * pm;			// :753-765

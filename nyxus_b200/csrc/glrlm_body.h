@@ -72,13 +72,19 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 			const int pr = row - dy, pc = col - dx;
 			if (!(pr >= 0 && pc >= 0 && pc < w && (cell[pr * w + pc] & CELL_LEVEL) == lv))
 			{
+				// walk the run: at most `room` more cells before the tile border, linear index stride dy * w + dx
+				int room = dy ? h - 1 - row : w;
+				if (dx > 0)
+					room = room < w - 1 - col ? room : w - 1 - col;
+				else if (dx < 0)
+					room = room < col ? room : col;
+				const int stride = dy * w + dx;
+				int j = i + stride;
 				len = 1;
-				int y = row + dy, x = col + dx;
-				while (y < h && x >= 0 && x < w && (cell[y * w + x] & CELL_LEVEL) == lv)
+				while (len <= room && (cell[j] & CELL_LEVEL) == lv)
 				{
 					len++;
-					y += dy;
-					x += dx;
+					j += stride;
 				}
 				atom_add (g, P + (size_t)(lv - 1) * Nr + (len - 1), 1u);
 				atom_add (g, Ri + (lv - 1), 1u);

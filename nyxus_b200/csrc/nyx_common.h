@@ -148,6 +148,27 @@ NYX_D double ln_count (uint32_t k)
 }
 constexpr double INV_LN2 = 1.4426950408889634074;
 
+// weights that depend on a small integer k only: 1/(1+k^2), 1/(1+k), 1/k^2 (GLCM difference-marginal features), from a
+// table filled by the host at context creation instead of three FP64 divisions per marginal entry
+constexpr uint32_t KW_TABLE_N = 1024;
+struct KWeights { double inv1pk2, inv1pk, invk2; };
+#if NYX_DEVICE_BUILD
+__device__ KWeights g_kw_table[KW_TABLE_N];
+#endif
+NYX_D KWeights k_weights (uint32_t k)
+{
+#if NYX_DEVICE_BUILD
+	if (k < KW_TABLE_N)
+		return g_kw_table[k];
+#endif
+	const double kd = (double)k;
+	KWeights w;
+	w.inv1pk2 = 1.0 / (1.0 + kd * kd);
+	w.inv1pk = 1.0 / (1.0 + kd);
+	w.invk2 = k ? 1.0 / (kd * kd) : 0.0;
+	return w;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Grey-level binning (reference features/texture_feature.h:23-50,138-167; helpers/helpers.h:337-345)
 // ------------------------------------------------------------------------------------------------
