@@ -447,6 +447,36 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	// ---- 4-connected components of equal level: every cell starts hooked to the head of its horizontal same-level run,
 	// then one union per vertically adjacent pair of RUNS (a pair whose left neighbours already joined the same two
 	// runs is skipped), so the union-find only ever sees run heads
+#if NYX_DEVICE_BUILD
+	if (c.wmode)
+	{
+		// warp per ROI: the cells are walked in raster order 32 at a time, so the head of a cell's run is the nearest lane
+		// at or below it whose left neighbour differs (ballot + clz), or the head carried over from the previous 32 cells
+		uint32_t carry = 0;	// run head of the last cell of the previous chunk
+		for (int base = 0; base < ncell; base += 32)
+		{
+			const int i = base + c.tid;
+			bool head = true;
+			uint32_t lv = 0;
+			if (i < ncell)
+			{
+				lv = cell[i] & CELL_LEVEL;
+				const int x = i - (int)fw.div ((uint32_t)i) * w;
+				head = (ibsi && !lv) || x == 0 || (cell[i - 1] & CELL_LEVEL) != lv;
+			}
+			const unsigned heads = __ballot_sync (0xffffffffu, head);
+			const unsigned below = heads & (0xFFFFFFFFu >> (31 - c.tid));
+			const uint32_t hd = below ? (uint32_t)(base + 31 - __clz (below)) : carry;
+			if (i < ncell)
+			{
+				parent[i] = hd;
+				zmin[i] = 0x7FFFFFFFu;
+			}
+			carry = __shfl_sync (0xffffffffu, hd, 31);
+		}
+	}
+	else
+#endif
 	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
 		const uint32_t lv = cell[i] & CELL_LEVEL;
