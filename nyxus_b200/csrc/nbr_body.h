@@ -438,19 +438,37 @@ NYX_D void ngtdm_reduce (const Cta& c, const Params& prm, uint32_t* mem, int L1,
 		s[A_S] += Sl[k];			// :256-258
 	}
 	{
-		const int npair = nl * nl;
-		FastDiv fl;
-		fl.init ((uint32_t)(nl > 0 ? nl : 1));
-		for (int k = c.tid; k < npair; k += c.nthr)
+		// every term is symmetric in (a, b) and vanishes for a == b: sum over the pairs a < b only and double.  The
+		// triangular index walks forward by nthr positions per step (row a holds the nl - 1 - a pairs (a, a+1 .. nl-1)).
+		double t[4] = { 0, 0, 0, 0 };
+		int a = 0, b = 1 + c.tid;
+		while (a < nl - 1 && b >= nl)
 		{
-			const int a = (int)fl.div ((uint32_t)k), b = k - a * nl;
+			b -= nl;
+			a++;
+			b += a + 1;
+		}
+		while (a < nl - 1)
+		{
 			const double pi = Pl[a], pj = Pl[b];
 			const double iv = (double)lst[a], jv = (double)lst[b];
-			s[A_CON] += pi * pj * (iv - jv) * (iv - jv);						// :245-251
-			s[A_BUSY] += fabs (pi * iv - pj * jv);							// :283-287
-			s[A_CPLX] += fabs (iv - jv) * (pi * Sl[a] + pj * Sl[b]) / (pi + pj);			// :311-314
-			s[A_STR] += (pi + pj) * (iv - jv) * (iv - jv);						// :333-336
+			const double d = iv - jv, d2 = d * d;
+			t[0] += pi * pj * d2;								// :245-251
+			t[1] += fabs (pi * iv - pj * jv);						// :283-287
+			t[2] += fabs (d) * (pi * Sl[a] + pj * Sl[b]) / (pi + pj);			// :311-314
+			t[3] += (pi + pj) * d2;								// :333-336
+			b += c.nthr;
+			while (a < nl - 1 && b >= nl)
+			{
+				b -= nl;
+				a++;
+				b += a + 1;
+			}
 		}
+		s[A_CON] += 2.0 * t[0];
+		s[A_BUSY] += 2.0 * t[1];
+		s[A_CPLX] += 2.0 * t[2];
+		s[A_STR] += 2.0 * t[3];
 	}
 	cta_sum<A_N> (c, s);
 	c.sync();	// the lists may be rewritten by the next ROI
