@@ -96,7 +96,7 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 				q[Q_MUJ] += (unsigned long long)len;				// :640-646
 				q[Q_HGL] += (unsigned long long)i2;				// :744-751
 				if (lv < 65536u && (unsigned long long)i2 * (unsigned long long)j2 < 0x100000000ull)
-					emphasis6 (s, (double)i2, (double)(int)j2);			// :381-383,712-719,781,813,844,876 (no 32-bit wrap: i2j2 == i2 * j2)
+					emphasis6_int (s, lv, (uint32_t)len);			// :381-383,712-719,781,813,844,876 (no 32-bit wrap: i2j2 == i2 * j2)
 				else
 				{
 					s[A_SRE] += 1.0 / (double)(len * len);

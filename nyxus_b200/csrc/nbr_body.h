@@ -101,7 +101,7 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 		q[Q_MUJ] += (unsigned long long)j;				// :410
 		q[Q_MUI] += lv;							// :388-395
 		q[Q_HGL] += (unsigned long long)lv * (unsigned long long)lv;	// :470-484
-		emphasis6 (s, in * in, (double)(j * j));			// :301-302, 452-464, 498-550
+		emphasis6_int (s, lv, (uint32_t)j);			// :301-302, 452-464, 498-550
 	}
 	c.sync();
 	if (dbg && dbg->P)

@@ -115,22 +115,6 @@ NYX_HD double plogp (double p, double eps)
 	return ddiv (dmul (p, fast_log10 (dadd (p, eps))), LOG10_2);
 }
 
-// The six "emphasis" sums every run / zone / dependence family takes over its elements (level i, minor j):
-//   s[0] += 1/j^2   s[1] += 1/i^2   s[2] += 1/(i^2 j^2)   s[3] += i^2/j^2   s[4] += j^2/i^2   s[5] += i^2 j^2
-// (GLRLM glrlm.cpp:381-383,712-719,781,813,844,876; GLSZM glszm.cpp:372-375,424-427,559-563; GLDZM gldzm.cpp:402,421,
-// 440-443; GLDM gldm.cpp:301-302,452-550).  Two reciprocals instead of the reference's five-to-thirteen divisions per
-// element: each term differs from the reference's by at most 2 ulp (features are held to 1e-9, not bit-exact).
-NYX_HD void emphasis6 (double* s, double i2, double j2)
-{
-	const double ri = 1.0 / i2, rj = 1.0 / j2;
-	s[0] += rj;
-	s[1] += ri;
-	s[2] += ri * rj;
-	s[3] += i2 * rj;
-	s[4] += j2 * ri;
-	s[5] += i2 * j2;
-}
-
 // ln(k) of a small integer count.  Entropies over integer matrices, sum_cells P log(P/N), become
 // sum_elements ln(count) - n ln(N): the per-element log is a table load (the table is filled by the host when the
 // context is created).  |error| ~ 1e-16 relative to the reference's log(count/N + 2.2e-16).
@@ -168,6 +152,43 @@ NYX_D KWeights k_weights (uint32_t k)
 	w.invk2 = k ? 1.0 / (kd * kd) : 0.0;
 	return w;
 }
+
+// The six "emphasis" sums every run / zone / dependence family takes over its elements (level i, minor j):
+//   s[0] += 1/j^2   s[1] += 1/i^2   s[2] += 1/(i^2 j^2)   s[3] += i^2/j^2   s[4] += j^2/i^2   s[5] += i^2 j^2
+// (GLRLM glrlm.cpp:381-383,712-719,781,813,844,876; GLSZM glszm.cpp:372-375,424-427,559-563; GLDZM gldzm.cpp:402,421,
+// 440-443; GLDM gldm.cpp:301-302,452-550).  Two reciprocals instead of the reference's five-to-thirteen divisions per
+// element: each term differs from the reference's by at most 2 ulp (features are held to 1e-9, not bit-exact).
+NYX_HD void emphasis6 (double* s, double i2, double j2)
+{
+	const double ri = 1.0 / i2, rj = 1.0 / j2;
+	s[0] += rj;
+	s[1] += ri;
+	s[2] += ri * rj;
+	s[3] += i2 * rj;
+	s[4] += j2 * ri;
+	s[5] += i2 * j2;
+}
+
+// the same for small integer (i, j): 1/i^2 and 1/j^2 come from the table (no division at all)
+NYX_D void emphasis6_int (double* s, uint32_t i, uint32_t j)
+{
+#if NYX_DEVICE_BUILD
+	if (i - 1u < KW_TABLE_N - 1u && j - 1u < KW_TABLE_N - 1u)	// 1 <= i, j < KW_TABLE_N (0 keeps the division's inf)
+	{
+		const double ri = g_kw_table[i].invk2, rj = g_kw_table[j].invk2;
+		const double i2 = (double)(i * i), j2 = (double)(j * j);
+		s[0] += rj;
+		s[1] += ri;
+		s[2] += ri * rj;
+		s[3] += i2 * rj;
+		s[4] += j2 * ri;
+		s[5] += i2 * j2;
+		return;
+	}
+#endif
+	emphasis6 (s, (double)i * (double)i, (double)j * (double)j);
+}
+
 
 // ------------------------------------------------------------------------------------------------
 // Grey-level binning (reference features/texture_feature.h:23-50,138-167; helpers/helpers.h:337-345)

@@ -315,7 +315,7 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 		q[Q_MUJ] += sz;							// :380
 		q[Q_MUI] += lv;							// :381
 		q[Q_HGL] += (unsigned long long)lv * lv;			// :574-578
-		emphasis6 (s, (double)lv * (double)lv, (double)sz * (double)sz);	// :372-375, 424-427 (sz < 65536: int j*j exact), 559-563
+		emphasis6_int (s, lv, sz);	// :372-375, 424-427 (sz < 65536: int j*j exact), 559-563
 	}
 	c.sync();
 	cta_sum_u64<Q_N> (c, q);
@@ -542,7 +542,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		q[Q_ZDM] += dd;							// :445
 		q[Q_GLM] += lv;							// :444
 		q[Q_HGL] += (unsigned long long)lv * lv;			// :422
-		emphasis6 (s, (double)lv * (double)lv, (double)dd * (double)dd);	// :402, 421, 440-443
+		emphasis6_int (s, lv, dd);	// :402, 421, 440-443
 	}
 	c.sync();
 	cta_sum_u64<Q_N> (c, q);
