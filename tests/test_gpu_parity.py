@@ -124,9 +124,10 @@ def test_scan_run_segmentation_stress(H, W, kind):
         L = (1 + (np.arange(H)[:, None] // 50) * 40 + np.arange(W)[None, :] // 30).astype(np.uint32)
         L[rng.random((H, W)) < 0.05] = 0
     I = rng.integers(0, 60000, (H, W)).astype(np.uint16)
+    I32 = rng.integers(0, 2**25, (H, W)).astype(np.uint32)          # beyond 16 bits: the two-register (min, max) path (2^26 = range limit of the large-ROI first-order histogram)
     e = _engine(features=["MEAN"])
     try:
-        for inten in (I, I.astype(np.uint32)):
+        for inten in (I, I.astype(np.uint32), I32):
             e.featurize(inten, L)
             assert np.array_equal(e.debug_rois(), _phase1_expected(inten, L))
     finally:
