@@ -142,6 +142,58 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 	c.sync();
 	{
 		const double q[6] = { 0.01, 0.1, 0.25, 0.75, 0.9, 0.99 };
+#if NYX_DEVICE_BUILD
+		if (c.wmode)
+		{
+			// warp form of hist_percentile: 4 bins per lane, exclusive prefix of the bin counts by a shuffle scan, then per
+			// percentile the LAST bin whose [run, run + b] holds the target count evaluates the reference's formula
+			const int lane = c.tid;
+			uint32_t b4[4], run4[4], tot = 0;
+#pragma unroll
+			for (int k = 0; k < 4; k++)
+			{
+				b4[k] = lane * 4 + k < 100 ? b100[lane * 4 + k] : 0u;
+				run4[k] = tot;
+				tot += b4[k];
+			}
+			uint32_t inc = tot;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync (0xffffffffu, inc, o);
+				if (lane >= o)
+					inc += t;
+			}
+			const uint32_t excl = inc - tot;
+#pragma unroll
+			for (int qi = 0; qi < 6; qi++)
+			{
+				const double cnt = dmul (nd, q[qi]);
+				int last = 0;	// 1 + index of my last matching bin
+#pragma unroll
+				for (int k = 0; k < 4; k++)
+				{
+					const double r0 = (double)(excl + run4[k]), r1 = (double)((unsigned long long)excl + run4[k] + b4[k]);
+					if (lane * 4 + k < 100 && r0 <= cnt && cnt <= r1)
+						last = lane * 4 + k + 1;
+				}
+				const int glast = (int)__reduce_max_sync (0xffffffffu, (unsigned)last);
+				if (glast == 0)
+				{
+					if (lane == 0)
+						sh[qi] = 0.0;
+				}
+				else if (last == glast)
+				{
+					const int i = glast - 1, k = i & 3;
+					const uint32_t run = excl + (k == 0 ? run4[0] : k == 1 ? run4[1] : k == 2 ? run4[2] : run4[3]);
+					const uint32_t b = k == 0 ? b4[0] : k == 1 ? b4[1] : k == 2 ? b4[2] : b4[3];
+					sh[qi] = dadd (dadd (ddiv (dmul (cnt - (double)run, binW100), (double)b), (double)mn), dmul (binW100, (double)i));
+				}
+			}
+		}
+		else
+#endif
 		for (int k = c.tid; k < 6; k += c.nthr)
 			sh[k] = hist_percentile (b100, dmul (nd, q[k]), binW100, mn);
 	}
