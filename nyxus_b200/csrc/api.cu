@@ -1371,6 +1371,42 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	};
 
 	static const int fam_stage[FAM_COUNT] = { ST_INT, ST_GLCM, ST_GLRLM, ST_GLDZM, ST_GLSZM, ST_GLDM, ST_NGLDM, ST_NGTDM };
+
+	// ---- K2: CSR cloud + binned-tile store in one pass over the AABBs of ALL ROIs (the class lists of the batches are
+	// contiguous; main stream: every family depends on it)
+	ctx->cur_b = 0;
+	stage_begin (ctx, ST_PACK);
+	{
+		const uint32_t nsmall = ctx->giant_tbase - ctx->tbase[0];
+		if (nsmall && (want_cloud || tiles))
+		{
+			if (d3)
+				k_pack_cloud<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->tbase[0], nsmall, ctx->d_cloud.p);
+			else
+				k_pack_tiles<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->tbase[0], nsmall, prm,
+					want_cloud ? ctx->d_cloud.p : nullptr, (uint16_t*)imf.tileA, (uint16_t*)imf.tileB);
+			CU (cudaGetLastError());
+			ctx->counts[0]++;
+		}
+		const uint32_t nlarge = ctx->giant_tcount;
+		if (nlarge && want_cloud)
+		{
+			const int grid = (int)std::min<uint32_t> (nlarge, (uint32_t)ctx->sm_count * 4);
+			const size_t stride = (size_t)im.H * (size_t)im.D + 2;
+			CU (ctx->d_rowoff.reserve ((size_t)grid * stride));
+			k_pack_cloud_large<<<grid, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + ctx->giant_tbase, nlarge, ctx->d_cloud.p,
+				ctx->d_rowoff.p, stride);
+			CU (cudaGetLastError());
+			ctx->counts[0]++;
+		}
+	}
+	// ---- families: ONE fork onto the family streams (slot 0 = first-order, then one slot per texture family); the
+	// batches follow each other on every family stream without waiting for the main stream, which only joins them
+	// batch by batch to select and ship the finished rows
+	stage_begin (ctx, ST_FAMILIES);
+	ctx->open_stage = -1;
+	if (int rc = fork_families (ctx))
+		return rc;
 	for (int bb = 0; bb < nb; bb++)
 	{
 		ctx->cur_b = bb;
@@ -1382,39 +1418,6 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		const uint32_t* tb = ctx->tbase + bb * (NCLASS + 1);
 		const uint32_t* ab = ctx->abase + bb * (NACLASS + 1);
 
-		// ---- K2: CSR cloud + binned-tile store in one pass over the ROIs' AABBs (main stream: every family depends on it)
-		stage_begin (ctx, ST_PACK);
-		{
-			uint32_t nsmall = 0;
-			for (int c = 0; c < NCLASS; c++)
-				nsmall += ccount[c];
-			if (nsmall && (want_cloud || tiles))
-			{
-				if (d3)
-					k_pack_cloud<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[0], nsmall, ctx->d_cloud.p);
-				else
-					k_pack_tiles<<<(nsmall * 32 + 255) / 256, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[0], nsmall, prm,
-						want_cloud ? ctx->d_cloud.p : nullptr, (uint16_t*)imf.tileA, (uint16_t*)imf.tileB);
-				CU (cudaGetLastError());
-				ctx->counts[0]++;
-			}
-			const uint32_t nlarge = ccount[NCLASS];
-			if (nlarge && want_cloud)
-			{
-				const int grid = (int)std::min<uint32_t> (nlarge, (uint32_t)ctx->sm_count * 4);
-				const size_t stride = (size_t)im.H * (size_t)im.D + 2;
-				CU (ctx->d_rowoff.reserve ((size_t)grid * stride));
-				k_pack_cloud_large<<<grid, 256, 0, s>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[NCLASS], nlarge, ctx->d_cloud.p,
-					ctx->d_rowoff.p, stride);
-				CU (cudaGetLastError());
-				ctx->counts[0]++;
-			}
-		}
-
-		// ---- families: fork onto the family streams (slot 0 = first-order, then one slot per texture family)
-		stage_begin (ctx, ST_FAMILIES);
-		if (int rc = fork_families (ctx))
-			return rc;
 		use_family_stream (ctx, 0);
 		stage_begin (ctx, ST_INT, ctx->ls);
 		if (want_cloud)
@@ -1490,7 +1493,12 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		}
 		if (int rc = join_families (ctx))
 			return rc;
-		stage_end (ctx, ST_FAMILIES);
+		if (bb == nb - 1)
+		{
+			ctx->cur_b = 0;
+			stage_end (ctx, ST_FAMILIES);
+			ctx->cur_b = bb;
+		}
 		// ---- rows of this batch: select + D2H, overlapped with the next batch (deferred when giant ROIs are pending)
 		if (!any_giant)
 			if (int rc = select_and_copy (bb * bs, std::min<uint32_t> (nroi, (bb + 1) * bs), nb > 1))
