@@ -242,6 +242,7 @@ def main():
     # ---- per-stage times for the roofline lines: the same step with the families serialised on one stream (in the timed
     # region above they overlap on eight streams, so their own begin/end events include time shared with other kernels)
     eng.set_param("concurrent_families", 0)
+    eng.set_param("roi_batches", 1)      # one launch per kernel and size class: stage time == launch time
     serial_sum, n_serial = {}, 3
     step_resident()
     for _ in range(n_serial):
@@ -249,6 +250,7 @@ def main():
         for k, v in eng.timings().items():
             serial_sum[k] = serial_sum.get(k, 0.0) + v
     eng.set_param("concurrent_families", 1)
+    eng.set_param("roi_batches", 0)
     barrier()
 
     # ---- e2e (host pinned buffers through the C ABI): one pipelined K-slide job, and K separate calls
@@ -315,7 +317,7 @@ def main():
                        "features": FEATURES, "coarse_gray_depth": 64, "rois_per_gpu": nroi, "fg_pixels_per_gpu": nfg,
                        "mpix_per_s": npix * world * args.steps / ev_s / 1e6,
                        "l2": "inputs (%.0f MB per step) exceed the 126 MB L2; no explicit flush" % (npix * 6 / 1e6),
-                       "timing": "CUDA events on the library's launching stream (first to last event of every call), summed over the K steps, max over ranks; the families overlap on 8 streams in the timed region, the roofline lines use stage times of 3 extra serialised steps",
+                       "timing": "CUDA events on the library's launching stream (first to last event of every call), summed over the K steps, max over ranks; the families overlap on 8 streams and the ROI batches follow each other in the timed region; the roofline lines use stage times of 3 extra steps with the families serialised and one ROI batch (one launch per kernel and size class)",
                        "wall_ms_per_step": wall / args.steps * 1e3},
             "e2e": {"value": total_rois_e2e / wall_e2e, "unit": "ROIs/s", "h2d_bytes_per_step": npix * 6,
                     "d2h_bytes_per_step": nroi * (ncols + 2) * 8, "ms_per_step": wall_e2e / args.steps * 1e3,

@@ -1242,7 +1242,7 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 
 	// ---- ROI batches: rows of batch b travel to the host while batch b+1 computes (the reference also walks the ROIs in
 	// batches, phase2_2d.cpp:427-465 -- there to bound RAM, here to hide the table's D2H copy)
-	int nb = ctx->roi_batches > 0 ? ctx->roi_batches : (int)(nroi / 16384);
+	int nb = ctx->roi_batches > 0 ? ctx->roi_batches : (int)(nroi / 8192);
 	nb = std::max (1, std::min (nb, NB_MAX));
 	const uint32_t bs = (nroi + nb - 1) / nb;		// ROIs per batch (index ranges of the label-ordered ROI array)
 	nb = (int)((nroi + bs - 1) / bs);

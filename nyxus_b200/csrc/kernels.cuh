@@ -29,7 +29,7 @@ struct __align__(32) LabelStat
 // info block shared between device and host (one D2H copy per slide)
 constexpr int NCLASS = 5;		// tile classes by cell count
 constexpr int NACLASS = 5;		// cloud classes by area
-constexpr int NB_MAX = 8;		// ROI batches per slide (rows of batch b are copied to the host while batch b+1 computes)
+constexpr int NB_MAX = 16;		// ROI batches per slide (rows of batch b are copied to the host while batch b+1 computes)
 constexpr int NTK = NB_MAX * (NCLASS + 1), NAK = NB_MAX * (NACLASS + 1);	// (batch, class) keys
 struct SlideInfo
 {

@@ -279,7 +279,7 @@ def test_tile_store_and_direct_binning_give_identical_tables(ibsi):
         e.close()
 
 
-@pytest.mark.parametrize("nb", [2, 5, 8])
+@pytest.mark.parametrize("nb", [2, 5, 8, 16])
 def test_roi_batches_give_identical_tables(nb):
     """Rows are produced batch by batch (D2H of batch b overlaps batch b+1); the table must not depend on the split."""
     from nyxus_b200 import synth
