@@ -30,6 +30,7 @@
 #pragma once
 #include "nyx_common.h"
 #include "nyx_features.h"
+#include "glcm_body.h"		// Counters<> (16-bit packed counters)
 
 namespace nyx
 {
@@ -141,6 +142,33 @@ NYX_D void uf_unite (const Cta& c, uint32_t* parent, uint32_t a, uint32_t b)
 		a = old;
 	}
 }
+
+// 16-bit minimum into the halfword h16[i] of a packed array (CAS on the containing 32-bit word; a handful of calls per
+// cell, the halved footprint buys a whole extra CTA per SM)
+NYX_D void atom_min_u16 (const Cta& c, uint32_t* w32, uint32_t i, uint32_t v)
+{
+	uint32_t* p = w32 + (i >> 1);
+	const uint32_t sh = (i & 1u) * 16u;
+#if NYX_DEVICE_BUILD
+	uint32_t old = *(volatile uint32_t*)p;
+	for (;;)
+	{
+		if (((old >> sh) & 0xFFFFu) <= v)
+			return;
+		const uint32_t upd = (old & ~(0xFFFFu << sh)) | (v << sh);
+		const uint32_t seen = atomicCAS (p, old, upd);
+		if (seen == old)
+			return;
+		old = seen;
+	}
+#else
+	(void)c;
+	if (((*p >> sh) & 0xFFFFu) > v)
+		*p = (*p & ~(0xFFFFu << sh)) | (v << sh);
+#endif
+}
+
+typedef Counters<true> Counters16;
 
 struct ZoneDebug
 {
@@ -386,10 +414,15 @@ NYX_HD int gldzm_nd_bound (uint32_t maxcells, int maxwh)
 	if (s > maxwh) s = maxwh;
 	return (s + 1) / 2 + 2;
 }
-// region: P[Lmax+1][Nd] + Ri[Lmax+1] + Cd[Nd] (zero on entry/exit) + parent[ncell] + zmin[ncell]
+// region: P[Lmax+1][Nd] (16-bit packed: a count is at most the number of zones < 65536) + Ri[Lmax+1] + Cd[Nd] (zero on
+// entry/exit) + parent[ncell] + zmin[ncell] (16-bit packed)
+NYX_HD size_t gldzm_p_words (int Lmax, int Nd)
+{
+	return ((size_t)(Lmax + 1) * Nd + 1) / 2;
+}
 NYX_HD size_t gldzm_smem_words (int Lmax, int Nd, uint32_t maxcells)
 {
-	return (size_t)(Lmax + 1) * Nd + (Lmax + 1) + Nd + 2 * (size_t)maxcells;
+	return gldzm_p_words (Lmax, Nd) + (Lmax + 1) + Nd + (size_t)maxcells + ((size_t)maxcells + 1) / 2;
 }
 
 // distance of cell (x,y) to the ROI/tile border exactly as gldzm.cpp:306-351 (zeros = level-0 cells of the binned tile)
@@ -436,11 +469,12 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		return;
 	}
 	const bool ibsi = prm.ibsi != 0;
-	uint32_t* P = mem;					// [Lmax+1][Nd]  zones per (level, metric)
-	uint32_t* Ri = P + (size_t)(Lmax + 1) * Nd;		// [Lmax+1]      zones per level
+	const Counters16 P { mem };				// [Lmax+1][Nd]  zones per (level, metric), 16-bit packed
+	uint32_t* Ri = mem + gldzm_p_words (Lmax, Nd);		// [Lmax+1]      zones per level
 	uint32_t* Cd = Ri + (Lmax + 1);				// [Nd]          zones per metric
 	uint32_t* parent = Cd + Nd;				// [ncell]
-	uint32_t* zmin = parent + maxcells;			// [ncell] zone metric at the root
+	uint32_t* zminw = parent + maxcells;			// [ncell] zone metric at the root, 16-bit packed
+	const uint16_t* zmin = (const uint16_t*)zminw;
 	FastDiv fw;
 	fw.init ((uint32_t)w);
 
@@ -468,10 +502,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 			const unsigned below = heads & (0xFFFFFFFFu >> (31 - c.tid));
 			const uint32_t hd = below ? (uint32_t)(base + 31 - __clz (below)) : carry;
 			if (i < ncell)
-			{
 				parent[i] = hd;
-				zmin[i] = 0x7FFFFFFFu;
-			}
 			carry = __shfl_sync (0xffffffffu, hd, 31);
 		}
 	}
@@ -491,8 +522,9 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 			}
 		}
 		parent[i] = (uint32_t)hd;
-		zmin[i] = 0x7FFFFFFFu;
 	}
+	for (int i = c.tid; i < (ncell + 1) / 2; i += c.nthr)
+		zminw[i] = 0xFFFFFFFFu;
 	c.sync();
 	for (int i = c.tid + w; i < ncell; i += c.nthr)
 	{
@@ -513,7 +545,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 			continue;
 		int y = (int)fw.div ((uint32_t)i), x = i - y * w;
 		uint32_t root = uf_find (parent, (uint32_t)i);
-		atom_min (c, zmin + root, (uint32_t)gldzm_dist2border (cell, w, h, x, y, !ibsi));
+		atom_min_u16 (c, zminw, root, (uint32_t)gldzm_dist2border (cell, w, h, x, y, !ibsi));
 	}
 	c.sync();
 
@@ -532,7 +564,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
 			continue;
 		const uint32_t dd = zmin[i];
-		atom_add (c, P + (size_t)lv * Nd + dd, 1u);
+		P.inc (c, (int)(lv * (uint32_t)Nd + dd));
 		atom_add (c, Ri + lv, 1u);
 		atom_add (c, Cd + dd, 1u);
 		if (dbg && dbg->keys)
@@ -564,14 +596,14 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		const double di = (double)lv - glm, dj = (double)dd - zdm;
 		t[0] += di * di;						// :468-471
 		t[1] += dj * dj;						// :474-476
-		t[2] += ln_count (P[(size_t)lv * Nd + dd]);			// :446  log2(P/Ns + eps), summed as ln(P) and finished below
+		t[2] += ln_count (P.get ((int)(lv * (uint32_t)Nd + dd)));			// :446  log2(P/Ns + eps), summed as ln(P) and finished below
 	}
 	cta_sum_u64<2> (c, q2);
 	cta_sum<3> (c, t);
 	c.sync();
 	// ---- pass 3: restore the all-zero region
-	if ((size_t)(Lmax + 1) * (Nd + 1) + Nd <= (size_t)ncell * 2)	// small matrix: wipe P, Ri, Cd (contiguous) with 128-bit stores
-		wipe_words (c, P, (size_t)(Lmax + 1) * (Nd + 1) + Nd);
+	if (gldzm_p_words (Lmax, Nd) + (Lmax + 1) + Nd <= (size_t)ncell * 2)	// small matrix: wipe P, Ri, Cd (contiguous) with 128-bit stores
+		wipe_words (c, mem, gldzm_p_words (Lmax, Nd) + (Lmax + 1) + Nd);
 	else
 	{
 		for (int i = c.tid; i < ncell; i += c.nthr)
@@ -579,7 +611,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 			const uint32_t lv = cell[i] & CELL_LEVEL;
 			if ((ibsi && !lv) || parent[i] != (uint32_t)i)
 				continue;
-			P[(size_t)lv * Nd + zmin[i]] = 0;
+			P.clear ((int)(lv * (uint32_t)Nd + zmin[i]));
 		}
 		for (int k = c.tid; k < Lmax + 1 + Nd; k += c.nthr)
 			Ri[k] = 0;
