@@ -77,7 +77,7 @@ NYX_D void uf16_unite (const Cta& c, uint16_t* parent, uint32_t a, uint32_t b)
 	}
 }
 
-// region: hash keys[slots] + cnts[slots] (zero on entry/exit) + parent/label (u16 per cell) + zone sizes (u16 per cell)
+// region: hash keys[slots] + 16-bit cnts[slots] (zero on entry/exit) + parent/label (u16 per cell) + zone sizes (u16 per cell)
 NYX_HD size_t glszm3d_smem_words (uint32_t maxcells, uint32_t slots)
 {
 	return glszm_smem_words (maxcells, slots);
@@ -96,8 +96,8 @@ NYX_D void glszm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const
 	}
 	uint32_t* keys = mem;
 	uint32_t* cnts = keys + slots;
-	uint16_t* lab = (uint16_t*)(cnts + slots);
-	uint32_t* zsw = cnts + slots + ((size_t)maxcells + 1) / 2;
+	uint16_t* lab = (uint16_t*)(cnts + slots / 2);
+	uint32_t* zsw = cnts + slots / 2 + ((size_t)maxcells + 1) / 2;
 	const uint32_t mask = slots - 1;
 	const uint32_t skip = matlab ? 1u : 0u;
 	FastDiv fw, fh;

@@ -64,7 +64,7 @@ NYX_D uint32_t atom_cas (const Cta&, uint32_t* p, uint32_t cmp, uint32_t val)
 #endif
 }
 
-// ---- open-addressing table of integer counters: keys[slots] (0 = empty) + cnts[slots], slots = power of two
+// ---- open-addressing table of integer counters: keys[slots] (0 = empty) + 16-bit cnts[slots] (slots / 2 words), slots = power of two
 NYX_HD uint32_t htab_mix (uint32_t k)
 {
 	k *= 0x9E3779B1u;
@@ -82,14 +82,14 @@ NYX_D void htab_add (const Cta& c, uint32_t* keys, uint32_t* cnts, uint32_t mask
 			break;
 		slot = (slot + 1) & mask;
 	}
-	atom_add (c, cnts + slot, 1u);
+	atom_add (c, cnts + (slot >> 1), 1u << ((slot & 1u) * 16u));	// 16-bit packed counts (a count is at most the number of zones < 65536)
 }
 NYX_D uint32_t htab_get (const uint32_t* keys, const uint32_t* cnts, uint32_t mask, uint32_t key)
 {
 	uint32_t slot = htab_mix (key) & mask;
 	while (keys[slot] != key)
 		slot = (slot + 1) & mask;
-	return cnts[slot];
+	return ((const uint16_t*)cnts)[slot];
 }
 
 // upper bound of the distinct keys one GLSZM tile can produce: (level,size) keys -- sizes 1,2,3.. each usable by at
@@ -179,10 +179,10 @@ struct ZoneDebug
 // ------------------------------------------------------------------------------------------------
 // GLSZM
 // ------------------------------------------------------------------------------------------------
-// region: hash keys[slots] + cnts[slots] (zero on entry/exit) + lab (u16 per cell) + zone sizes (u16 per cell)
+// region: hash keys[slots] + 16-bit cnts[slots] (zero on entry/exit) + lab (u16 per cell) + zone sizes (u16 per cell)
 NYX_HD size_t glszm_smem_words (uint32_t maxcells, uint32_t slots)
 {
-	return (size_t)slots * 2 + 2 * (((size_t)maxcells + 1) / 2);
+	return (size_t)slots + slots / 2 + 2 * (((size_t)maxcells + 1) / 2);
 }
 
 NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, uint32_t* keys, uint32_t* cnts, uint32_t mask,
@@ -200,8 +200,8 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	}
 	uint32_t* keys = mem;						// [slots]
 	uint32_t* cnts = keys + slots;					// [slots]
-	uint16_t* lab = (uint16_t*)(cnts + slots);			// [ncell] zone label = raster index of the seed
-	uint32_t* zsw = cnts + slots + ((size_t)maxcells + 1) / 2;	// [ncell] zone size at the seed index, packed u16 pairs
+	uint16_t* lab = (uint16_t*)(cnts + slots / 2);			// [ncell] zone label = raster index of the seed
+	uint32_t* zsw = cnts + slots / 2 + ((size_t)maxcells + 1) / 2;	// [ncell] zone size at the seed index, packed u16 pairs
 	const uint16_t* zs = (const uint16_t*)zsw;
 	const uint32_t mask = slots - 1;
 
@@ -379,7 +379,7 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 	cta_sum_u64<2> (c, q2);
 	cta_sum<3> (c, t);
 	c.sync();
-	for (uint32_t i = c.tid; i < 2 * slots; i += c.nthr)	// restore the all-zero table
+	for (uint32_t i = c.tid; i < slots + slots / 2; i += c.nthr)	// restore the all-zero table (keys + packed counts)
 		keys[i] = 0;
 	c.sync();
 	if (c.tid == 0)
