@@ -18,14 +18,20 @@
 #pragma once
 #include "nyx_common.h"
 #include "nyx_features.h"
+#include "glcm_body.h"		// Counters<> (16-bit packed counters)
 
 namespace nyx
 {
 
-// words of ONE angle's region: P[Lmax][Nr] + Ri[Lmax] + Cj[Nr] (zero on entry/exit) + run length per cell (u16)
+// words of ONE angle's region: P[Lmax][Nr] (16-bit packed: a count is at most the number of runs <= cells of a tile, and the
+// shared-memory tile classes end at 40000 cells) + Ri[Lmax] + Cj[Nr] (zero on entry/exit) + run length per cell (u16)
+NYX_HD size_t glrlm_p_words (int Lmax, int Nr)
+{
+	return ((size_t)Lmax * Nr + 1) / 2;
+}
 NYX_HD size_t glrlm_angle_words (int Lmax, int Nr, int maxcells)
 {
-	return (size_t)Lmax * Nr + Lmax + Nr + ((size_t)maxcells + 1) / 2;
+	return glrlm_p_words (Lmax, Nr) + Lmax + Nr + ((size_t)maxcells + 1) / 2;
 }
 NYX_HD size_t glrlm_smem_words (int Lmax, int Nr, int maxcells)
 {
@@ -41,9 +47,9 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 	int Nr, double* out, const GlrlmDebug* dbg)
 {
 	const int w = r.w, h = r.h, ncell = w * h;
-	const size_t pw = (size_t)Lmax * Nr;
-	uint32_t* P = reg;			// [Lmax][Nr]
-	uint32_t* Ri = P + pw;			// [Lmax]  runs per level
+	const size_t pn = (size_t)Lmax * Nr, pw = glrlm_p_words (Lmax, Nr);
+	const Counters<true> P { reg };		// [Lmax][Nr], 16-bit packed
+	uint32_t* Ri = reg + pw;		// [Lmax]  runs per level
 	uint32_t* Cj = Ri + Lmax;		// [Nr]    runs per length
 	uint16_t* rl = (uint16_t*)(Cj + Nr);	// [ncell] length of the run starting at the cell (0: not a start)
 	const int dx = a == 2 ? 0 : (a == 3 ? -1 : 1), dy = a == 0 ? 0 : 1;	// E, SE, S, SW (glrlm.cpp:129-175)
@@ -86,7 +92,7 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 					len++;
 					j += stride;
 				}
-				atom_add (g, P + (size_t)(lv - 1) * Nr + (len - 1), 1u);
+				P.inc (g, (int)((lv - 1) * (uint32_t)Nr + (uint32_t)(len - 1)));
 				atom_add (g, Ri + (lv - 1), 1u);
 				atom_add (g, Cj + (len - 1), 1u);
 				const uint32_t i2 = lv * lv, j2 = (uint32_t)(len * len), i2j2 = lv * lv * (uint32_t)len * (uint32_t)len;	// 32-bit wrap
@@ -115,8 +121,8 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 	cta_sum<A_N> (g, s);
 
 	if (dbg && dbg->P)
-		for (size_t i = g.tid; i < pw; i += g.nthr)
-			dbg->P[(size_t)a * pw + i] = P[i];
+		for (size_t i = g.tid; i < pn; i += g.nthr)
+			dbg->P[(size_t)a * pn + i] = P.get ((int)i);
 
 	if (q[Q_SUM] == 0)	// :363-366 etc. (no run: the region is still all zero)
 	{
@@ -142,7 +148,7 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 		const double di = (double)lv - mui, dj = (double)len - muj;
 		t[0] += di * di;								// :608-616
 		t[1] += dj * dj;								// :649-656
-		const double p = (double)P[(size_t)(lv - 1) * Nr + (len - 1)] * inv_sum;
+		const double p = (double)P.get ((int)((lv - 1) * (uint32_t)Nr + (uint32_t)(len - 1))) * inv_sum;
 		t[2] += fast_log10 (dadd (p, EPS_ZONES));					// :684-685
 	}
 	cta_sum_u64<2> (g, q2);
@@ -151,14 +157,14 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 
 	// ---- pass 3: restore the all-zero region
 	if (pw + Lmax + Nr <= (size_t)ncell * 2)	// small matrix: wipe P, Ri, Cj (contiguous) with 128-bit stores
-		wipe_words (g, P, pw + Lmax + Nr);
+		wipe_words (g, reg, pw + Lmax + Nr);
 	else
 	{
 		for (int i = g.tid; i < ncell; i += g.nthr)
 		{
 			const int len = rl[i];
 			if (len)
-				P[(size_t)((cell[i] & CELL_LEVEL) - 1) * Nr + (len - 1)] = 0;
+				P.clear ((int)(((cell[i] & CELL_LEVEL) - 1) * (uint32_t)Nr + (uint32_t)(len - 1)));
 		}
 		for (int k = g.tid; k < Lmax + Nr; k += g.nthr)
 			Ri[k] = 0;
