@@ -169,6 +169,8 @@ struct nyxb200_ctx
 	size_t h_out_cap = 0, h_out_used = 0;
 
 	int glszm3_greydepth = 0, ngtdm3_greydepth = 0, ngtdm3_radius = 0;	// env_features.cpp:712-736: zero unless set
+	int glcm_greydepth = 0;		// GLCM_GREYDEPTH when set through "glcm/greydepth" / "3glcm/greydepth" (env_metaparams.cpp:83-91,112-120)
+	bool glcm_greydepth_set = false;	// else it follows coarse_gray_depth (env_features.cpp:730)
 
 	float stage_ms[NYXB200_NSTAGES] {};
 	int64_t counts[4] {};
@@ -431,11 +433,28 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 			return fail (ctx, NYXB200_EINVAL, "glcm/offset must be >= 0");
 		ctx->st.glcm_offset = iv;
 	}
-	else if (!strcmp (key, "glcm/greydepth") || !strcmp (key, "coarse_gray_depth"))
+	else if (!strcmp (key, "coarse_gray_depth"))
 	{
-		if (iv <= 0 || iv > 65535)
-			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 1..65535");
+		// NyxSetting::GREYDEPTH.  Negative = PyRadiomics bin count (texture_feature.h:23-50,106-118): not reachable from
+		// the reference's Python API (coarse_gray_depth is unsigned there, new_bindings_py.cpp:81,167) but it is what the
+		// reference's own gtests set on Fsettings, so the C ABI takes it.  Setting it re-derives GLCM_GREYDEPTH like
+		// Environment::compile_feature_settings does (env_features.cpp:720,730).
+		if (iv == 0 || iv > 65535 || iv < -65535)
+			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 1..65535 (or -65535..-1: PyRadiomics bin count)");
 		ctx->st.coarse_gray_depth = iv;
+		ctx->glcm_greydepth_set = false;
+	}
+	else if (!strcmp (key, "glcm/greydepth") || !strcmp (key, "3glcm/greydepth"))
+	{
+		// env_metaparams.cpp:83-91 / :112-120: writes ONLY GLCM_GREYDEPTH (any integer).  2D: feeds the blank-ROI test of
+		// GLCMFeature::calculate (glcm.cpp:22-28), the matrix keeps binning with GREYDEPTH (glcm.cpp:354).  3D: the
+		// binning of D3_GLCM_feature (3d_glcm.cpp:53-57); 0 = no binning, negative = PyRadiomics bin count.
+		if (!strcmp (key, "3glcm/greydepth") != (ctx->st.dim == 3))
+			return fail (ctx, NYXB200_EINVAL, "'%s' does not apply to a %dD context", key, ctx->st.dim);
+		if (iv > 65535 || iv < -65535)
+			return fail (ctx, NYXB200_EUNSUPPORTED, "grey depth must be in -65535..65535");
+		ctx->glcm_greydepth = iv;
+		ctx->glcm_greydepth_set = true;
 	}
 	else if (!strcmp (key, "ibsi"))
 		ctx->st.ibsi = iv != 0;
@@ -453,22 +472,16 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 	}
 	else if (!strcmp (key, "tile_store"))			// test knob: 0 = family kernels bin straight from the slide
 		ctx->use_tile_store = iv != 0;
-	else if (!strcmp (key, "3glcm/greydepth"))		// env_metaparams.cpp:109-120
+	else if (!strcmp (key, "3glszm/greydepth"))		// env_metaparams.cpp:222-233 (negative = PyRadiomics bin count)
 	{
-		if (iv <= 0 || iv > 65535)
-			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 1..65535");
-		ctx->st.coarse_gray_depth = iv;
-	}
-	else if (!strcmp (key, "3glszm/greydepth"))		// env_metaparams.cpp:222-233
-	{
-		if (iv < 0 || iv > 65535)
-			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 0..65535");
+		if (iv < -65535 || iv > 65535)
+			return fail (ctx, NYXB200_EUNSUPPORTED, "grey depth must be in -65535..65535");
 		ctx->glszm3_greydepth = iv;
 	}
 	else if (!strcmp (key, "3ngtdm/greydepth"))		// env_metaparams.cpp:175-186
 	{
-		if (iv < 0 || iv > 65535)
-			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 0..65535");
+		if (iv < -65535 || iv > 65535)
+			return fail (ctx, NYXB200_EUNSUPPORTED, "grey depth must be in -65535..65535");
 		ctx->ngtdm3_greydepth = iv;
 	}
 	else if (!strcmp (key, "3ngtdm/radius"))		// env_metaparams.cpp:187-197
@@ -500,11 +513,11 @@ template <class K> int set_smem (nyxb200_ctx* ctx, K kernel, size_t bytes)
 }
 
 // words of family matrices for a class
-size_t family_words (int fam, bool p16, int Lmax, uint32_t maxcells, int maxwh)
+size_t family_words (int fam, bool p16, int Lmax, uint32_t maxcells, int maxwh, bool rad)
 {
 	switch (fam)
 	{
-	case FAM_GLCM: return p16 ? glcm_smem_words<true> (Lmax, 4) : glcm_smem_words<false> (Lmax, 4);
+	case FAM_GLCM: return p16 ? glcm_smem_words<true> (Lmax, 4, rad) : glcm_smem_words<false> (Lmax, 4, rad);
 	case FAM_GLRLM: return glrlm_smem_words (Lmax, maxwh, (int)maxcells);
 	case FAM_GLDZM: return gldzm_smem_words (Lmax, gldzm_nd_bound (maxcells, maxwh), maxcells);
 	case FAM_GLSZM: return glszm_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));
@@ -524,7 +537,7 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 	if (!n)
 		return 0;
 	const size_t tilew = tile_words (maxcells);
-	const size_t famw = (family_words (FAM, P16, Lmax, maxcells, maxwh) + 1) & ~(size_t)1;
+	const size_t famw = (family_words (FAM, P16, Lmax, maxcells, maxwh, !prm.ibsi && prm.greydepth < 0) + 1) & ~(size_t)1;
 	// small tiles of the single-matrix families: one warp per ROI
 	if (FAM != FAM_GLCM && FAM != FAM_GLRLM && !dbg.u32 && maxcells <= 1024 && tilew + famw <= WARP_SLICE_LIMIT_WORDS)
 	{
@@ -628,7 +641,7 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 		return 0;
 	const size_t tilew = tile_words (maxcells);
 	size_t famw = 0;
-	if (FAM3 == FAM3_GLCM) famw = P16 ? glcm_smem_words<true> (Lmax, 4) : glcm_smem_words<false> (Lmax, 4);
+	if (FAM3 == FAM3_GLCM) famw = P16 ? glcm_smem_words<true> (Lmax, 4, greyinfo < 0) : glcm_smem_words<false> (Lmax, 4, greyinfo < 0);
 	if (FAM3 == FAM3_GLSZM) famw = glszm3d_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));
 	if (FAM3 == FAM3_NGTDM) famw = ngtdm3d_smem_words (Lmax);
 	famw = (famw + 1) & ~(size_t)1;
@@ -657,6 +670,7 @@ Params make_params (const nyxb200_ctx* ctx)
 {
 	Params p;
 	p.greydepth = ctx->st.coarse_gray_depth;
+	p.glcm_greydepth = ctx->glcm_greydepth_set ? ctx->glcm_greydepth : ctx->st.coarse_gray_depth;
 	p.ibsi = ctx->st.ibsi;
 	p.glcm_offset = ctx->st.glcm_offset;
 	p.glcm_symmetric = ctx->st.glcm_symmetric;
@@ -1239,6 +1253,15 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	}
 	if (ctx->st.ibsi && info.max_inten > CELL_LEVEL)
 		return fail (ctx, NYXB200_EUNSUPPORTED, "IBSI mode needs intensities < 2^24 (max %u)", info.max_inten);
+	if (!d3 && !ctx->st.ibsi && ctx->st.coarse_gray_depth < 0)
+	{
+		// PyRadiomics bin count as the general grey depth (C ABI only): GLCM, GLRLM, GLSZM, GLDM, NGTDM and first-order
+		// follow the reference.  GLDZM: the reference indexes I.end() for the level-0 zones and throws (gldzm.cpp:245-258);
+		// NGLDM: to_grayscale() takes the negative depth as a huge unsigned level count (ngldm.cpp:42) -- neither is a
+		// result worth reproducing
+		if (ctx->fam_mask & ((1 << FAM_GLDZM) | (1 << FAM_NGLDM)))
+			return fail (ctx, NYXB200_EUNSUPPORTED, "GLDZM and NGLDM are undefined for a negative (PyRadiomics) grey depth in the reference (gldzm.cpp:245-258 throws, ngldm.cpp:42)");
+	}
 
 	// ---- ROI batches: rows of batch b travel to the host while batch b+1 computes (the reference also walks the ROIs in
 	// batches, phase2_2d.cpp:427-465 -- there to bound RAM, here to hide the table's D2H copy)
@@ -1302,6 +1325,8 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	}
 	ctx->last_info = info;
 	const bool any_giant = !d3 && (ctx->giant_tcount || ctx->giant_acount);
+	if (any_giant && !ctx->st.ibsi && ctx->st.coarse_gray_depth < 0 && (ctx->fam_mask & ~(1 << FAM_INT)))
+		return fail (ctx, NYXB200_EUNSUPPORTED, "a negative (PyRadiomics) grey depth is not built for ROIs of the large-ROI path (bounding box > 40000 pixels)");
 
 	// ---- canonical table
 	CU (ctx->d_full.reserve ((size_t)nroi * ncol_all));
@@ -1309,14 +1334,14 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	if (d3)	// 3d_intensity.cpp:56-61: ROI range over the scanned range of the labelled voxels (slideprops.cpp:305-327)
 		prm.covered_den = (double)info.max_inten - (double)(~info.inv_min_inten);
 
-	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : ctx->st.coarse_gray_depth;
+	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : std::abs (ctx->st.coarse_gray_depth);
 	DebugOut nodbg { nullptr, nullptr, nullptr };
 	ImageView imf = im;		// the view the family kernels get (with the tile store when it is used)
 	const bool want_cloud = (ctx->fam_mask & (1 << FAM_INT)) != 0;
 	const bool want_tex = !d3 && (ctx->fam_mask & ~(1 << FAM_INT)) != 0;
 	// 16-bit tile codes hold 14-bit levels: MATLAB binning up to 16383 levels, IBSI (identity) up to that intensity
 	const bool tiles = want_tex && ctx->use_tile_store && info.n_tile_cells > 0 && (uint32_t)Lmax <= TILE16_LEVEL
-		&& (uint32_t)ctx->st.coarse_gray_depth <= TILE16_LEVEL;
+		&& (uint32_t)std::abs (ctx->st.coarse_gray_depth) <= TILE16_LEVEL;
 	const bool tiles_b = tiles && (ctx->fam_mask & (1 << FAM_NGLDM));
 	if (want_cloud)
 		CU (ctx->d_cloud.reserve ((size_t)info.n_fg + 4));
@@ -1442,10 +1467,10 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 				use_family_stream (ctx, fam);
 				stage_begin (ctx, st3[fam], ctx->ls);
 				// grey-binning info per family (3d_glcm.cpp:53-55, 3d_glszm.cpp:490-492, 3d_ngtdm.cpp:195-197); 0 = no binning
-				int g = fam == FAM3_GLCM ? ctx->st.coarse_gray_depth : fam == FAM3_GLSZM ? ctx->glszm3_greydepth : ctx->ngtdm3_greydepth;
+				int g = fam == FAM3_GLCM ? prm.glcm_greydepth : fam == FAM3_GLSZM ? ctx->glszm3_greydepth : ctx->ngtdm3_greydepth;
 				if (ctx->st.ibsi)
 					g = 0;
-				int Lm = g > 0 ? g : maxI;
+				int Lm = g != 0 ? std::abs (g) : maxI;	// > 0 MATLAB levels, < 0 PyRadiomics bins (texture_feature.h:52-77), 0 = intensities as they are
 				if (fam == FAM3_NGTDM && ctx->ngtdm3_radius == 0)
 					Lm = 1;		// nothing is accumulated (see ngtdm3d_body)
 				for (int c = 0; c < NCLASS; c++)
@@ -1900,7 +1925,7 @@ int nyxb200_debug_matrix (nyxb200_ctx* ctx, uint32_t label, int family, int64_t*
 		*n = cnt;
 		return NYXB200_OK;
 	}
-	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (r.imax, 1u) : ctx->st.coarse_gray_depth;
+	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (r.imax, 1u) : std::abs (ctx->st.coarse_gray_depth);
 	const int maxwh = std::max (r.w, r.h);
 	size_t words = 0;
 	switch (family)

@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(BG_T) k_big_glcm_reduce (const uint32_t* __res
 			}
 			if (k < 2 * Ng)
 				sv = SPP[k];
-			glcm_marginal_terms (k, Ng, cv, rv, dv, sv, N, mr, mc, diffavg, NgD, m, px, py);
+			glcm_marginal_terms (k, Ng, cv, rv, dv, sv, N, mr, mc, diffavg, NgD, m, px, py, (double)(k + 1), (double)k, true);
 			const unsigned bx = g.ballot (cv != 0), by = g.ballot (rv != 0);
 			if (cv)
 				lx[nx + popc32 (bx & g.lanemask_lt())] = (uint16_t)k;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(BG_T) k_big_glcm_reduce (const uint32_t* __res
 	double f[G_NANGLED];
 	glcm_finish (f, m, N, mr, diffavg, (double)q[Q_ASM], (double)q[Q_RC], (double)q[Q_D2], (double)q[Q_S], (double)jmax,
 		jd[0] / N * INV_LOG10_2, jd[1] / N * INV_LOG10_2, hxy2[0] * INV_LOG10_2, m[M_HX] * INV_LOG10_2, jd[2] / N,
-		nx == 1 || ny == 1, true, prm.softnan);
+		nx == 1 || ny == 1, true, prm.softnan, diffavg);
 	if (c.tid == 0)
 		for (int k = 0; k < G_NANGLED; k++)
 			out[k * 4 + a] = f[k];

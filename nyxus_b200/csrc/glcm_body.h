@@ -67,9 +67,57 @@ template <bool P16> NYX_HD size_t glcm_angle_words (int Ng)
 }
 
 // shared-memory words needed by glcm_body for `na` angles held at once
-template <bool P16> NYX_HD size_t glcm_smem_words (int Ng, int na)
+// (rad: + the level -> rank map [Ng + 1] and the rank -> level list [Ng] of PyRadiomics binning)
+template <bool P16> NYX_HD size_t glcm_smem_words (int Ng, int na, bool rad = false)
 {
-	return (size_t)na * glcm_angle_words<P16> (Ng);
+	return (size_t)na * glcm_angle_words<P16> (Ng) + (rad ? (size_t)2 * Ng + 2 : 0);
+}
+
+// PyRadiomics binning (glcm.cpp:388-398, 3d_glcm.cpp:286-296): I = the sorted distinct non-zero bins of the tile / cube;
+// the matrix is indexed by rank in I.  Rewrites every non-zero cell level to rank + 1, fills Ilev[rank] = level and
+// returns |I|.  n = |grey depth| (largest possible bin); map: n + 1 words of scratch.
+NYX_D int glcm_rank_levels (const Cta& c, uint32_t* cell, int ncell, int n, uint32_t* map, uint32_t* Ilev)
+{
+	for (int l = c.tid; l <= n; l += c.nthr)
+		map[l] = 0;
+	c.sync();
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (lv)
+			map[lv] = 1;
+	}
+	c.sync();
+	if (c.sub_id() == 0)
+	{
+		const Cta g = c.sub();
+		int base = 0;
+		for (int l0 = 1; l0 <= n; l0 += g.nthr)
+		{
+			const int l = l0 + g.tid;
+			const bool present = l <= n && map[l] != 0;
+			const unsigned b = g.ballot (present);
+			if (present)
+			{
+				const int rank = base + popc32 (b & g.lanemask_lt());
+				map[l] = (uint32_t)rank + 1u;
+				Ilev[rank] = (uint32_t)l;
+			}
+			base += popc32 (b);
+		}
+		if (g.tid == 0)
+			map[0] = (uint32_t)base;
+	}
+	c.sync();
+	const int cnt = (int)map[0];
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t cc = cell[i], lv = cc & CELL_LEVEL;
+		if (lv)
+			cell[i] = (cc & ~CELL_LEVEL) | map[lv];
+	}
+	c.sync();
+	return cnt;
 }
 
 struct GlcmDebug
@@ -82,20 +130,21 @@ constexpr double INV_LOG10_2 = 1.0 / LOG10_2;
 // sums over the marginals of one angle (shared by the per-pair ROI kernels and the dense large-ROI reducer)
 enum GlcmM { M_S2R, M_S2C, M_JVAR, M_HX, M_IDM, M_ID, M_IDN, M_IDMN, M_IV, M_DENT, M_DVAR, M_SENT, M_CP, M_CS, M_CT, M_N };
 
-// contribution of marginal index k (k < 2Ng): cv = C[k], rv = R[k], dv = SPM[k] (k < Ng), sv = SPP[k]
+// contribution of marginal index k (k < 2Ng): cv = C[k], rv = R[k], dv = SPM[k] (k < Ng), sv = SPP[k].
+// lv = grey level of index k (k + 1 unless the levels are the ROI's sorted unique bins: PyRadiomics binning), kdl =
+// kValuesDiff[k] (k likewise); clusters: CLUPROM / CLUSHADE / CLUTEND from the sum marginal (valid when level == index + 1)
 NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned long long rv, unsigned long long dv, unsigned long long sv,
-	double N, double mr, double mc, double diffavg, double NgD, double* m, double* px, double* py)
+	double N, double mr, double mc, double diffavg, double NgD, double* m, double* px, double* py, double lv, double kdl, bool clusters)
 {
 	if (k < Ng)
 	{
-		const double lv = (double)(k + 1);
 		const double pc = (double)cv / N, pr = (double)rv / N;
 		px[k] = pc;
 		py[k] = pr;
-		const double dr = lv - mr, dc = lv - mc;
+		const double dr = lv - mr, dc = lv - mc, dj = (double)(k + 1) - mr;
 		m[M_S2R] += pr * dr * dr;			// :612-618, f_var :667-675
 		m[M_S2C] += pc * dc * dc;			// :621-627
-		m[M_JVAR] += dr * dr * pc;			// :1194-1200 (column marginal, row-marginal mean)
+		m[M_JVAR] += dj * dj * pc;			// :1194-1200 (column marginal, row-marginal mean, INDEX + 1 not level)
 		if (cv)
 			m[M_HX] += dmul (pc, fast_log10 (dadd (pc, GLCM_EPSILON)));	// :873-876
 		if (dv)
@@ -107,7 +156,7 @@ NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned l
 			m[M_IDN] += pm * (NgD / (NgD + kd));		// pm / (1 + k / Ng)		:1110-1111
 			m[M_IDMN] += pm * ((NgD * NgD) / (NgD * NgD + kd * kd));	// pm / (1 + k^2 / Ng^2)	:1082-1084
 			if (k >= 1)
-				m[M_IV] += pm * kw.invk2;		// pm / k^2			:1123-1128
+				m[M_IV] += kdl == kd ? pm * kw.invk2 : pm / (kdl * kdl);	// pm / kValuesDiff[k]^2	:1123-1128
 			m[M_DENT] += dmul (pm, fast_log10 (dadd (pm, GLCM_EPSILON)));	// :778-781
 			const double dd = kd - diffavg;
 			m[M_DVAR] += dd * dd * pm;			// :753-765
@@ -117,10 +166,13 @@ NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned l
 	{
 		const double pp = (double)sv / N;
 		m[M_SENT] += dmul (pp, fast_log10 (dadd (pp, GLCM_EPSILON)));	// :712-716
-		const double mm = (double)(k + 2) - mc - mc;
-		m[M_CT] += mm * mm * pp;				// :1028-1036
-		m[M_CS] += mm * mm * mm * pp;				// :1001-1009
-		m[M_CP] += mm * mm * mm * mm * pp;			// :979-987
+		if (clusters)
+		{
+			const double mm = (double)(k + 2) - mc - mc;
+			m[M_CT] += mm * mm * pp;				// :1028-1036
+			m[M_CS] += mm * mm * mm * pp;				// :1001-1009
+			m[M_CP] += mm * mm * mm * mm * pp;			// :979-987
+		}
 	}
 }
 
@@ -128,7 +180,8 @@ NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned l
 // sum_s = sum (I_x+I_y) Pxpy*N (integers held in doubles are exact below 2^53);  HXY.. already scaled by 1/LOG10_2;
 // corr = sum (r-mr)(c-mc) p.  guard: the 2D softNaN guards (glcm.cpp:637-639,880-883; absent from 3d_glcm.cpp).
 NYX_D void glcm_finish (double* f, const double* m, double N, double mr, double diffavg, double sum_cnt2, double sum_rc, double sum_d2,
-	double sum_s, double jmax, double HXY, double HXY1, double HXY2, double HX, double corr, bool degenerate, bool guard, double softnan)
+	double sum_s, double jmax, double HXY, double HXY1, double HXY2, double HX, double corr, bool degenerate, bool guard, double softnan,
+	double dis)
 {
 	// A single non-empty row or column makes every p(i,j) EXACTLY px(i)*py(j): the reference then sums identical terms
 	// for HXY, HXY1 and HXY2 and gets HXY - HXY2 == 0 exactly (INFOMEAS2 = 0, not sqrt(1e-16)); keep that identity.
@@ -147,7 +200,7 @@ NYX_D void glcm_finish (double* f, const double* m, double N, double mr, double 
 	f[G_DIFAVE] = diffavg;
 	f[G_DIFENTRO] = -m[M_DENT] * INV_LOG10_2;
 	f[G_DIFVAR] = m[M_DVAR];
-	f[G_DIS] = diffavg;
+	f[G_DIS] = dis;						// :1050-1052 (index difference; == DIFAVE unless the levels are a sorted list)
 	f[G_ENTROPY] = -HXY;						// :722-739
 	f[G_JE] = -HXY;							// :1149-1165
 	f[G_HOM1] = m[M_ID];
@@ -176,12 +229,14 @@ template <bool D3> struct GlcmGeom
 {
 	int w, h, d, dx, dy, dz;
 	bool skipzero;
+	bool identity;	// the levels are the intensities themselves (grey info 0: IBSI flag, or a 3D GLCM grey depth of 0)
 	FastDiv fw, fh;
-	NYX_D void init (const RoiRec& r, int dx_, int dy_, int dz_, bool skipzero_)
+	NYX_D void init (const RoiRec& r, int dx_, int dy_, int dz_, bool skipzero_, bool identity_)
 	{
 		w = r.w; h = r.h; d = D3 ? r.d : 1;
 		dx = dx_; dy = dy_; dz = dz_;
 		skipzero = skipzero_;
+		identity = identity_;
 		fw.init ((uint32_t)w);
 		fh.init ((uint32_t)h);
 	}
@@ -224,9 +279,12 @@ template <bool D3> struct GlcmGeom
 // One angle, one warp-wide context g.  reg: this angle's region (all integer words zero on entry and on exit).
 // The angle's 30 values go to out[f * ostride + a].  guard: 2D softNaN guards of CORRELATION / INFOMEAS1
 // (glcm.cpp:637-639,880-883), absent from 3d_glcm.cpp.
-template <bool P16, bool D3>
+// RAD (PyRadiomics binning, grey depth < 0; glcm.cpp:388-398,455-466): the matrix is indexed by the RANK of a level in the
+// ROI's sorted list of distinct non-zero bins I[] (the caller has already rewritten the cell levels to rank + 1: see
+// glcm_rank_levels), NgRoi = |I|; formulas that use I[] take the level from Ilev[rank], the index-based ones do not change.
+template <bool P16, bool D3, bool RAD = false>
 NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec& r, const Params& prm, const uint32_t* cell,
-	uint32_t* reg, int Ng, double* out, int ostride, const GlcmDebug* dbg)
+	uint32_t* reg, int Ng, double* out, int ostride, const GlcmDebug* dbg, const uint32_t* Ilev = nullptr, int NgRoi = 0)
 {
 	const int ncell = G.ncell();
 	const double softnan = prm.softnan;
@@ -243,10 +301,11 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	double* pxc = py + Ng;			// [nx] px of the non-empty columns, ascending level
 	double* pyc = pxc + Ng;			// [ny] py of the non-empty rows
 
-	const bool sym = prm.glcm_symmetric || prm.ibsi;
+	const bool sym = prm.glcm_symmetric || G.identity || RAD;	// glcm.cpp:472-476, 3d_glcm.cpp:365-367
 
 	// ---- pass 1: build (glcm.cpp:431-478) + integer moments per pair
-	enum { Q_N, Q_R, Q_C, Q_D, Q_D2, Q_S, Q_RC, Q_CNT };
+	enum { Q_N, Q_R, Q_C, Q_D, Q_D2, Q_S, Q_RC, Q_DL2, Q_CNT_ALL };
+	constexpr int Q_CNT = RAD ? Q_CNT_ALL : Q_DL2;
 	unsigned long long q[Q_CNT];
 	for (int k = 0; k < Q_CNT; k++)
 		q[k] = 0;
@@ -256,7 +315,13 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		if (!G.pair (cell, i, b, av))
 			continue;
 		const int d = av > b ? av - b : b - av;
-		const unsigned long long lb = (unsigned long long)(b + 1), la = (unsigned long long)(av + 1), ld = (unsigned long long)d;
+		const unsigned long long lb = RAD ? Ilev[b] : (unsigned long long)(b + 1), la = RAD ? Ilev[av] : (unsigned long long)(av + 1);
+		const unsigned long long ld = (unsigned long long)d;
+		if constexpr (RAD)
+		{
+			const unsigned long long dl = la > lb ? la - lb : lb - la;	// CONTRAST uses the LEVEL difference (:566-584)
+			q[Q_DL2] += 2 * dl * dl;
+		}
 		J.inc (g, b * Ng + av);
 		atom_add (g, Rm + b, 1u);
 		atom_add (g, Cm + av, 1u);
@@ -306,8 +371,25 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	const double mc = (double)q[Q_C] / N;		// f_corr mc (:605-610), by_row_mean (:531-536)
 	const double diffavg = (double)q[Q_D] / N;	// f_difference_avg (:786-795), DIS (:1050-1052)
 	// Ng of THIS ROI: MATLAB = grey depth; IBSI = max level of the tile = aux_max (glcm.cpp:412-419).
-	// (the `Ng` argument may be a class-wide storage bound in IBSI mode)
-	const double NgD = prm.ibsi ? (double)r.imax : (double)Ng;
+	// (the `Ng` argument may be a class-wide storage bound in IBSI mode); PyRadiomics = number of distinct bins of the ROI
+	const double NgD = RAD ? (double)NgRoi : G.identity ? (double)r.imax : (double)Ng;
+	// kValuesDiff[k] / kValuesSum[k] (glcm.cpp:487-514): the LAST (x, y) of the x-outer / y-inner double loop with
+	// |x - y| == k resp. x + y == k wins, i.e. x = NgRoi - 1 resp. x = min (k, NgRoi - 1); with I[i] = i + 1 these are k and k + 2
+	double difavg_lv = diffavg, sumavg_lv = 0;
+	if (RAD)
+	{
+		double pre[2] = { 0, 0 };
+		for (int k = g.tid; k < 2 * NgRoi - 1; k += g.nthr)
+		{
+			if (k < NgRoi)
+				pre[0] += (double)(Ilev[NgRoi - 1] - Ilev[NgRoi - 1 - k]) * ((double)SPM[k] / N);	// f_difference_avg :786-795
+			const int x = k < NgRoi - 1 ? k : NgRoi - 1;
+			pre[1] += (double)(Ilev[x] + Ilev[k - x]) * ((double)SPP[k] / N);			// f_savg :693-704
+		}
+		cta_sum<2> (g, pre);
+		difavg_lv = pre[0];
+		sumavg_lv = pre[1];
+	}
 
 	// ---- marginal sweep: px/py, marginal-only features, lists of the non-empty levels
 	double m[M_N];
@@ -327,7 +409,11 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		}
 		if (k < 2 * Ng)
 			sv = SPP[k];
-		glcm_marginal_terms (k, Ng, cv, rv, dv, sv, N, mr, mc, diffavg, NgD, m, px, py);
+		if (RAD)
+			glcm_marginal_terms (k, Ng, cv, rv, dv, sv, N, mr, mc, difavg_lv, NgD, m, px, py, k < NgRoi ? (double)Ilev[k] : 0.0,
+				k < NgRoi ? (double)(Ilev[NgRoi - 1] - Ilev[NgRoi - 1 - k]) : 0.0, false);
+		else
+			glcm_marginal_terms (k, Ng, cv, rv, dv, sv, N, mr, mc, diffavg, NgD, m, px, py, (double)(k + 1), (double)k, true);
 		nx += popc32 (g.ballot (cv != 0));
 		ny += popc32 (g.ballot (rv != 0));
 		cmax = cv > cmax ? cv : cmax;
@@ -426,7 +512,8 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	// ---- pass 2: owner-computes terms of the joint cells
 	const double invN = 1.0 / N;
 	unsigned long long s_asm = 0, jmax = 0;
-	double jd[3] = { 0, 0, 0 };	// sum log(p_cell), sum log(px*py), sum (r-mr)(c-mc)
+	constexpr int NJD = RAD ? 6 : 3;
+	double jd[NJD] = {};	// sum log(p_cell), sum log(px*py), sum (r-mr)(c-mc) [, RAD: cluster sums m^2, m^3, m^4 per pair]
 	for (int i = g.tid; i < ncell; i += g.nthr)
 	{
 		int b, av;
@@ -436,14 +523,23 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		const double p = (double)cnt * invN;
 		const double l1 = fast_log10 (dadd (p, GLCM_EPSILON));					// HXY (glcm.cpp:868, 734-735, 1160-1161)
 		const double l2 = fast_log10 (dadd (dmul (px[av], py[b]), GLCM_EPSILON));		// HXY1 (:869)
-		double cr = ((double)(b + 1) - mr) * ((double)(av + 1) - mc);				// (:633)
+		const double vb = RAD ? (double)Ilev[b] : (double)(b + 1), va = RAD ? (double)Ilev[av] : (double)(av + 1);
+		double cr = (vb - mr) * (va - mc);								// (:633)
+		if constexpr (RAD)
+		{
+			// CLUTEND / CLUSHADE / CLUPROM over the joint cells (:979-1036): the level sum is not a function of x + y
+			const double mm = vb + va - mc - mc;
+			jd[3] += 2.0 * mm * mm;
+			jd[4] += 2.0 * mm * mm * mm;
+			jd[5] += 2.0 * mm * mm * mm * mm;
+		}
 		if (sym)
 		{
 			// the mirrored cell (av,b) holds the same count; px == py
 			s_asm += 2 * cnt;
 			jd[0] += l1 + l1;
 			jd[1] += l2 + fast_log10 (dadd (dmul (px[b], py[av]), GLCM_EPSILON));
-			cr += ((double)(av + 1) - mr) * ((double)(b + 1) - mc);
+			cr += (va - mr) * (vb - mc);
 		}
 		else
 		{
@@ -459,7 +555,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		cta_sum_u64<1> (g, t);	// (its shuffles/barrier also order pass 2's reads before pass 3's stores)
 		s_asm = t[0];
 	}
-	cta_sum<3> (g, jd);
+	cta_sum<NJD> (g, jd);
 	jmax = cta_max_u64 (g, jmax);
 	g.sync();
 
@@ -513,9 +609,18 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 
 	// ---- features of this angle
 	double f[G_NANGLED];
-	glcm_finish (f, m, N, mr, diffavg, (double)s_asm, (double)q[Q_RC], (double)q[Q_D2], (double)q[Q_S], (double)jmax,
+	double sum_d2 = (double)q[Q_D2];
+	if constexpr (RAD)
+	{
+		m[M_CT] = jd[3] / N;
+		m[M_CS] = jd[4] / N;
+		m[M_CP] = jd[5] / N;
+		sum_d2 = (double)q[Q_DL2];
+	}
+	glcm_finish (f, m, N, mr, difavg_lv, (double)s_asm, (double)q[Q_RC], sum_d2,
+		RAD ? sumavg_lv * N : (double)q[Q_S], (double)jmax,
 		jd[0] / N * INV_LOG10_2, jd[1] / N * INV_LOG10_2, hxy2[0] * INV_LOG10_2, m[M_HX] * INV_LOG10_2, jd[2] / N,
-		nx == 1 || ny == 1, !D3, softnan);
+		nx == 1 || ny == 1, !D3, softnan, diffavg);
 	if (g.tid == 0)
 		for (int k = 0; k < G_NANGLED; k++)
 			out[k * ostride + a] = f[k];
@@ -523,16 +628,16 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 
 // out: NCOL_GLCM doubles of this ROI (angled block then _AVE block).  mem: 4 angle regions, zero on entry and exit.
 template <bool P16>
-NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Ng,
+NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t* cell, uint32_t* mem, int Ng,
 	double* out, const GlcmDebug* dbg)
 {
 	constexpr int NA = 4;
 	const int ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
 
-	// ---- blank ROI (glcm.cpp:27-95)
+	// ---- blank ROI (glcm.cpp:22-28): the ONLY use of GLCM_GREYDEPTH ("glcm/greydepth"); the matrix bins with GREYDEPTH (:354)
 	{
 		Binner Bm;
-		Bm.init (prm.greydepth, r.imin, r.imax);
+		Bm.init (prm.glcm_greydepth, r.imin, r.imax);
 		if (Bm.bin (r.imin) == Bm.bin (r.imax))
 		{
 			for (int i = c.tid; i < NCOL_GLCM; i += c.nthr)
@@ -543,11 +648,17 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 	const size_t aw = glcm_angle_words<P16> (Ng);
 	const Cta g = c.sub();
 	const int o = prm.glcm_offset;
+	const bool rad = !prm.ibsi && prm.greydepth < 0;
+	uint32_t* Ilev = mem + NA * aw + Ng + 1;
+	const int ngroi = rad ? glcm_rank_levels (c, cell, r.w * r.h, Ng, mem + NA * aw, Ilev) : 0;
 	for (int a = c.sub_id(); a < NA; a += c.sub_count())
 	{
 		GlcmGeom<false> G;
-		G.init (r, a == 2 ? 0 : (a == 3 ? -o : o), a == 0 ? 0 : o, 0, false);	// glcm.cpp:234-251
-		glcm_angle<P16, false> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg);
+		G.init (r, a == 2 ? 0 : (a == 3 ? -o : o), a == 0 ? 0 : o, 0, false, prm.ibsi != 0);	// glcm.cpp:234-251
+		if (rad)
+			glcm_angle<P16, false, true> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg, Ilev, ngroi);
+		else
+			glcm_angle<P16, false> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg);
 	}
 	c.sync();
 
@@ -567,10 +678,13 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, const ui
 constexpr int G3_NDIR = 13;
 constexpr int NCOL_GLCM3 = G_NANGLED * G3_NDIR + G_NAVE;
 
+// greyinfo: what the cube was binned with (GLCM_GREYDEPTH, 0 under the IBSI flag): > 0 MATLAB levels, 0 none,
+// < 0 PyRadiomics bin count ("3glcm/greydepth=-N")
 template <bool P16>
-NYX_D void glcm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Ng,
-	double* out)
+NYX_D void glcm3d_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t* cell, uint32_t* mem, int Ng,
+	double* out, int greyinfo)
 {
+	const bool rad = greyinfo < 0;
 	const int ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
 	const int sx[G3_NDIR] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0 };
 	const int sy[G3_NDIR] = { 1, 1, 1, 0, 0, 0, -1, -1, -1, 1, 1, 1, 0 };
@@ -578,12 +692,17 @@ NYX_D void glcm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const 
 	const size_t aw = glcm_angle_words<P16> (Ng);
 	const Cta g = c.sub();
 	const int nsub = c.sub_count() < 4 ? c.sub_count() : 4;	// at most 4 regions
+	uint32_t* Ilev = mem + 4 * aw + Ng + 1;
+	const int ngroi = rad ? glcm_rank_levels (c, cell, r.w * r.h * r.d, Ng, mem + 4 * aw, Ilev) : 0;
 	if (c.sub_id() < nsub)
 		for (int a = c.sub_id(); a < G3_NDIR; a += nsub)
 		{
 			GlcmGeom<true> G;
-			G.init (r, sx[a], sy[a], sz[a], prm.ibsi != 0);
-			glcm_angle<P16, true> (g, a, G, r, prm, cell, mem + (size_t)c.sub_id() * aw, Ng, out, G3_NDIR, nullptr);
+			G.init (r, sx[a], sy[a], sz[a], greyinfo <= 0, greyinfo == 0);	// zero levels are skipped unless the binning is MATLAB's (3d_glcm.cpp:333-350)
+			if (rad)
+				glcm_angle<P16, true, true> (g, a, G, r, prm, cell, mem + (size_t)c.sub_id() * aw, Ng, out, G3_NDIR, nullptr, Ilev, ngroi);
+			else
+				glcm_angle<P16, true> (g, a, G, r, prm, cell, mem + (size_t)c.sub_id() * aw, Ng, out, G3_NDIR, nullptr);
 		}
 	c.sync();
 	for (int k = c.tid; k < G_NAVE; k += c.nthr)	// calc_ave (texture_feature.h:121-130)

@@ -23,6 +23,7 @@ namespace nyx
 // shared-memory words: sorted buffer (pow2 >= n) + 101 + (nb+1) bins + 8 doubles
 NYX_HD size_t intensity_smem_words (uint32_t npad, int nb)
 {
+	nb = nb < 0 ? -nb : nb;		// TrivialHistogram::initialize takes |n_cust_bins| (histogram.h:31)
 	return (size_t)npad + 101 + (size_t)nb + 1 + 1 /*align*/ + 16;
 }
 

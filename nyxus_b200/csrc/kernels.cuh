@@ -986,7 +986,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 		load_cube (c, im, r, B, cell);
 		c.sync();
 		if (FAM3 == FAM3_GLCM)
-			glcm3d_body<P16> (c, r, prm, cell, mem, Lmax, o + COL3_GLCM);
+			glcm3d_body<P16> (c, r, prm, cell, mem, Lmax, o + COL3_GLCM, greyinfo);
 		else if (FAM3 == FAM3_GLSZM)
 			glszm3d_body (c, r, prm, cell, mem, maxcells, glszm_hash_slots (Lmax, maxcells), greyinfo > 0, o + COL3_GLSZM);
 		else if (FAM3 == FAM3_NGTDM)

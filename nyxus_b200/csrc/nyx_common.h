@@ -195,20 +195,42 @@ NYX_D void emphasis6_int (double* s, uint32_t i, uint32_t j)
 // ------------------------------------------------------------------------------------------------
 struct Binner
 {
-	int greyinfo;		// >0 MATLAB levels, 0 IBSI identity (negative = PyRadiomics, not reachable from the Python API)
-	double slope;		// MATLAB: g / max
-	uint32_t n;
+	int greyinfo;		// >0 MATLAB levels, 0 IBSI identity, <0 PyRadiomics bin count
+	double slope;		// MATLAB: g / max;  PyRadiomics: the bin width (max - min) / |g|
+	uint32_t n;		// |g|
+	uint32_t mn;		// PyRadiomics: aux_min
 
-	NYX_HD void init (int greyinfo_, uint32_t /*imin*/, uint32_t imax)
+	NYX_HD void init (int greyinfo_, uint32_t imin, uint32_t imax)
 	{
 		greyinfo = greyinfo_;
-		n = (uint32_t)(greyinfo_ > 0 ? greyinfo_ : 0);
-		slope = greyinfo_ > 0 ? ddiv ((double)greyinfo_, (double)imax) : 0.0;
+		n = (uint32_t)(greyinfo_ > 0 ? greyinfo_ : -greyinfo_);
+		mn = imin;
+		if (greyinfo_ > 0)
+			slope = ddiv ((double)greyinfo_, (double)imax);
+		else if (greyinfo_ < 0)
+			slope = ddiv ((double)(uint32_t)(imax - imin), (double)(int)n);	// texture_feature.h:110
+		else
+			slope = 0.0;
 	}
 	NYX_HD uint32_t bin (uint32_t i) const
 	{
 		if (greyinfo == 0)
 			return i;
+		if (greyinfo < 0)
+		{
+			// to_grayscale_radiomix (texture_feature.h:106-118): 0 stays 0; 1-based bins, the last one a unit wider.
+			// (PixIntens)(double): x86-64 gcc converts through a 64-bit cvttsd2si and keeps the low 32 bits, so NaN
+			// (min == max: 0/0) and anything >= 2^63 give 0
+			if (i == 0)
+				return 0;
+			const double q = dadd (ddiv ((double)(uint32_t)(i - mn), slope), 1.0);
+			uint32_t y = 0;
+			if (q == q && q > -9223372036854775808.0 && q < 9223372036854775808.0)
+				y = (uint32_t)(unsigned long long)(long long)q;
+			if (y > n)
+				y = n;
+			return y;
+		}
 		if (i == 0)
 			return 1;
 		double r = floor (dadd (dmul (slope, (double)i), 1.0));
@@ -266,14 +288,15 @@ struct ImageView
 
 struct Params
 {
-	int32_t greydepth;	// coarse_gray_depth (>0)
+	int32_t greydepth;	// NyxSetting::GREYDEPTH = coarse_gray_depth (> 0 MATLAB levels; < 0 PyRadiomics bin count, C ABI only)
+	int32_t glcm_greydepth;	// NyxSetting::GLCM_GREYDEPTH: 2D = the GLCM blank-ROI test only (glcm.cpp:22-28); 3D = the GLCM binning (3d_glcm.cpp:53)
 	int32_t ibsi;
 	int32_t glcm_offset;
 	int32_t glcm_symmetric;
 	double softnan;
 	// 3D (Nyxus3D) settings: per-family grey depths (env_features.cpp:712-736: only GLCM gets a default, the rest are 0
 	// = no binning unless set through set_metaparam) and the NGTDM neighbourhood radius
-	int32_t glszm3_greydepth = 0, ngtdm3_greydepth = 0, ngtdm3_radius = 0, pad3 = 0;
+	int32_t glszm3_greydepth = 0, ngtdm3_greydepth = 0, ngtdm3_radius = 0;
 	double covered_den = 0;	// first-order COVERED_IMAGE_INTENSITY_RANGE denominator (slide max - min); 0 = in-memory sentinel
 };
 

@@ -50,13 +50,29 @@ def bin_pixel_matlab(i, mx, g):
     return max(1, min(v, g))
 
 
+def bin_pixel_radiomics(x, mn, mx, n):
+    """TextureFeature::to_grayscale_radiomix (texture_feature.h:106-118): 0 stays 0; 1-based bins of width (max-min)/n, the
+    last one a unit wider.  (PixIntens)(double) as x86-64 gcc does it: a 64-bit truncating conversion whose low 32 bits are
+    kept, NaN (min == max: 0/0) and out-of-range values giving 0."""
+    if x == 0:
+        return 0
+    d = float((x - mn) & 0xFFFFFFFF)
+    w = float((mx - mn) & 0xFFFFFFFF) / float(n)
+    if w == 0.0:
+        q = math.nan if d == 0.0 else math.inf
+    else:
+        q = d / w + 1.0
+    y = 0 if (q != q or abs(q) >= 9.223372036854775808e18) else int(q) & 0xFFFFFFFF
+    return min(y, n)
+
+
 def bin_tile(R, mn, mx, greyinfo):
-    """TextureFeature::bin_intensities (texture_feature.h:23-50): >0 MATLAB, 0 IBSI identity"""
+    """TextureFeature::bin_intensities (texture_feature.h:23-50): >0 MATLAB, 0 IBSI identity, <0 PyRadiomics bin count"""
     if greyinfo == 0:
         return R.astype(np.int64).copy()
     D = np.zeros(R.shape, np.int64)
     for idx, v in np.ndenumerate(R):
-        D[idx] = bin_pixel_matlab(int(v), int(mx), greyinfo)
+        D[idx] = bin_pixel_matlab(int(v), int(mx), greyinfo) if greyinfo > 0 else bin_pixel_radiomics(int(v), int(mn), int(mx), -greyinfo)
     return D
 
 

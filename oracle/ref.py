@@ -49,6 +49,11 @@ def lib():
     return _lib
 
 
+def set_glcm_greydepth(g=None):
+    """2D calls that follow behave as after set_metaparam("glcm/greydepth=g") (None: default = the grey depth)."""
+    lib().nyxref_set_glcm_greydepth(C.c_int(-2147483648 if g is None else int(g)))
+
+
 def columns():
     L = lib()
     n = L.nyxref_ncols()

@@ -151,6 +151,9 @@ namespace
 		}
 	}
 
+	// "glcm/greydepth" metaparameter (env_metaparams.cpp:83-91): overrides GLCM_GREYDEPTH only; INT_MIN = not set
+	int g_glcm_greydepth_override = INT_MIN;
+
 	// Same values Environment::compile_feature_settings() writes (src/nyx/env_features.cpp:712-736)
 	Fsettings make_settings (int greydepth, bool ibsi, int glcm_offset)
 	{
@@ -166,7 +169,7 @@ namespace
 		s[(int)NyxSetting::VERBOSLVL].ival = 0;
 		s[(int)NyxSetting::IBSI].bval = ibsi;
 		s[(int)NyxSetting::GLCM_OFFSET].ival = glcm_offset;
-		s[(int)NyxSetting::GLCM_GREYDEPTH].ival = greydepth;
+		s[(int)NyxSetting::GLCM_GREYDEPTH].ival = g_glcm_greydepth_override == INT_MIN ? greydepth : g_glcm_greydepth_override;
 		s[(int)NyxSetting::GLCM_NUMANG].ival = 4;
 		return s;
 	}
@@ -213,6 +216,9 @@ namespace
 
 extern "C"
 {
+
+// what set_metaparam("glcm/greydepth=N") does for the 2D calls that follow (INT_MIN: back to the default = greydepth)
+void nyxref_set_glcm_greydepth (int g) { g_glcm_greydepth_override = g; }
 
 int nyxref_ncols()
 {

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <climits>
 #include "../../nyxus_b200/csrc/nyx_common.h"
 #include "../../nyxus_b200/csrc/nyx_features.h"
 #include "../../nyxus_b200/csrc/glcm_body.h"
@@ -21,6 +22,21 @@ using namespace nyx;
 extern "C" int nyxemu_ncols() { return NCOL_ALL; }
 
 // tile: h*w intensities, mask: h*w membership.  fam_mask bits: 1 INT, 2 GLCM, 4 GLRLM, 8 GLDZM, 16 GLSZM, 32 GLDM, 64 NGLDM, 128 NGTDM
+static int g_glcm_greydepth = INT_MIN;	// "glcm/greydepth" (2D: blank test only); INT_MIN = follows the grey depth
+extern "C" void nyxemu_set_glcm_greydepth (int g) { g_glcm_greydepth = g; }
+
+static Params make_prm (int greydepth, int glcm_greydepth, int ibsi, int glcm_offset)
+{
+	Params prm;
+	prm.greydepth = greydepth;
+	prm.glcm_greydepth = glcm_greydepth;
+	prm.ibsi = ibsi;
+	prm.glcm_offset = glcm_offset;
+	prm.glcm_symmetric = 0;
+	prm.softnan = 0.0;
+	return prm;
+}
+
 extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, int w, int h,
 	int greydepth, int ibsi, int glcm_offset, unsigned fam_mask, double* out, int p16)
 {
@@ -51,7 +67,7 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 		return -1;
 	r.x0 = x0; r.y0 = y0; r.w = x1 - x0 + 1; r.h = y1 - y0 + 1;
 	ImageView im { tile, lab.data(), h, w, 0 };
-	Params prm { greydepth, ibsi, glcm_offset, 0, 0.0 };
+	Params prm = make_prm (greydepth, g_glcm_greydepth == INT_MIN ? greydepth : g_glcm_greydepth, ibsi, glcm_offset);
 	std::vector<double> red (RED_MAX * NW_MAX);
 	Cta c { 0, 1, red.data() };
 	const int ncell = r.w * r.h;
@@ -59,7 +75,8 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 	B.init (ibsi ? 0 : greydepth, r.imin, r.imax);
 	std::vector<uint32_t> cell (ncell);
 	load_tile (c, im, r, B, cell.data());
-	const int Lmax = ibsi ? (int)r.imax : greydepth;
+	const int Lmax = ibsi ? (int)r.imax : std::abs (greydepth);
+	const bool rad = !ibsi && greydepth < 0;
 	for (int i = 0; i < NCOL_ALL; i++)
 		out[i] = 0;
 	if (fam_mask & 1)
@@ -73,13 +90,15 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 		int Ng = Lmax;
 		if (p16)
 		{
-			std::vector<uint32_t> mem (glcm_smem_words<true> (Ng, 4));
-			glcm_body<true> (c, r, prm, cell.data(), mem.data(), Ng, out + COL_GLCM, nullptr);
+			std::vector<uint32_t> mem (glcm_smem_words<true> (Ng, 4, rad));
+			std::vector<uint32_t> cellg (cell);	// (PyRadiomics binning rewrites the levels to ranks)
+			glcm_body<true> (c, r, prm, cellg.data(), mem.data(), Ng, out + COL_GLCM, nullptr);
 		}
 		else
 		{
-			std::vector<uint32_t> mem (glcm_smem_words<false> (Ng, 4));
-			glcm_body<false> (c, r, prm, cell.data(), mem.data(), Ng, out + COL_GLCM, nullptr);
+			std::vector<uint32_t> mem (glcm_smem_words<false> (Ng, 4, rad));
+			std::vector<uint32_t> cellg (cell);
+			glcm_body<false> (c, r, prm, cellg.data(), mem.data(), Ng, out + COL_GLCM, nullptr);
 		}
 	}
 	if (fam_mask & 4)
@@ -124,6 +143,8 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 // ---- 3D: one labelled volume [D][H][W], label value `lab`; fam_mask bits: 1 INT, 2 GLCM, 4 NGTDM, 8 GLSZM.
 // out layout: 36 first-order | 30x13 + 29 GLCM | 5 NGTDM | 16 GLSZM   (the canonical 3D table of the library)
 extern "C" int nyxemu_ncols3d() { return NCOL_INT + NCOL_GLCM3 + NCOL_NGTDM + NCOL_GLSZM; }
+static int g_glcm3_greydepth = INT_MIN;	// "3glcm/greydepth"; INT_MIN = follows the grey depth
+extern "C" void nyxemu_set_glcm3_greydepth (int g) { g_glcm3_greydepth = g; }
 extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl, int D, int H, int W, uint32_t lab,
 	int greydepth, int glszm_g, int ngtdm_g, int ngtdm_radius, int ibsi, double covered_den, unsigned fam_mask, double* out)
 {
@@ -153,7 +174,8 @@ extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl,
 		return -1;
 	r.x0 = x0; r.y0 = y0; r.z0 = z0; r.w = x1 - x0 + 1; r.h = y1 - y0 + 1; r.d = z1 - z0 + 1;
 	ImageView im { vol, lbl, H, W, 0, D };
-	Params prm { greydepth, ibsi, 1, 0, 0.0 };
+	const int glcm_g = g_glcm3_greydepth == INT_MIN ? greydepth : g_glcm3_greydepth;
+	Params prm = make_prm (greydepth, glcm_g, ibsi, 1);
 	prm.glszm3_greydepth = glszm_g;
 	prm.ngtdm3_greydepth = ngtdm_g;
 	prm.ngtdm3_radius = ngtdm_radius;
@@ -177,17 +199,17 @@ extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl,
 		const unsigned bit = fam == 1 ? 2u : fam == 2 ? 8u : 4u;	// GLCM, GLSZM, NGTDM
 		if (!(fam_mask & bit))
 			continue;
-		int g = fam == 1 ? greydepth : fam == 2 ? glszm_g : ngtdm_g;
+		int g = fam == 1 ? glcm_g : fam == 2 ? glszm_g : ngtdm_g;
 		if (ibsi)
 			g = 0;
 		Binner B;
 		B.init (g, r.imin, r.imax);
 		load_cube (c, im, r, B, cell.data());
-		int Lm = g > 0 ? g : (int)std::max (r.imax, 1u);
+		int Lm = g != 0 ? std::abs (g) : (int)std::max (r.imax, 1u);
 		if (fam == 1)
 		{
-			std::vector<uint32_t> mem (glcm_smem_words<false> (Lm, 4));
-			glcm3d_body<false> (c, r, prm, cell.data(), mem.data(), Lm, out + O_GLCM);
+			std::vector<uint32_t> mem (glcm_smem_words<false> (Lm, 4, g < 0));
+			glcm3d_body<false> (c, r, prm, cell.data(), mem.data(), Lm, out + O_GLCM, g);
 		}
 		else if (fam == 2)
 		{
