@@ -115,6 +115,20 @@ int nyxb200_featurize_2d_list (nyxb200_ctx* ctx, const void* const* inten, int i
 int nyxb200_featurize_3d_list (nyxb200_ctx* ctx, const void* const* inten, int inten_is_u16, const uint32_t* const* label,
 	int on_device, int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t);
+/* Ownership hand-over of a result table (reference: the std::vector<double> moved into a capsule-owned numpy array,
+ * as_pyarray new_bindings_py.cpp:63-73,631-640): after a successful detach `t->data` belongs to the caller and stays
+ * valid across later featurize calls and nyxb200_destroy; give it back with nyxb200_host_release (the pinned buffer
+ * returns to a process-wide pool and is reused by the next call instead of being re-pinned). */
+int nyxb200_table_detach (nyxb200_ctx* ctx, nyxb200_table* t);
+void nyxb200_host_release (void* data);
+
+/* Device-free checks for the binding layer (the reference validates feature names in initialize_environment,
+ * env_features.cpp:496,507, and answers gpu_available_imp / get_gpu_props without touching a device context,
+ * new_bindings_py.cpp:887-922). */
+int nyxb200_validate_features (int dim, const char* const* names, int n, char* msg, size_t msgcap);
+int nyxb200_get_param (const nyxb200_ctx* ctx, const char* key, double* value);   /* same keys as nyxb200_set_param */
+int nyxb200_device_count (void);      /* one past the last CUDA ordinal of compute capability 10.x; 0 = none / no driver */
+int nyxb200_device_info (int device, char* name, size_t namecap, int64_t* total_mem, int* sm_count, int* cc_major, int* cc_minor);
 
 /* ---- measurement hooks ---- */
 #define NYXB200_NSTAGES 18

@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 #include "../../include/nyxus_b200.h"
@@ -89,6 +90,74 @@ template <class T> struct DevBuf
 };
 
 constexpr size_t SMEM_LIMIT_WORDS = (227 * 1024) / 4;
+
+// Process-wide pool of pinned (portable) host buffers for result tables.  A table whose ownership went to the caller
+// (nyxb200_table_detach: the pybind module wraps it in a numpy capsule, like the reference's as_pyarray hand-over,
+// new_bindings_py.cpp:63-73) comes back through nyxb200_host_release and is reused by the next call: pinning hundreds
+// of megabytes per call would cost more than the features.
+struct PinnedBuf { void* p; size_t bytes; bool in_use; };
+std::mutex g_pool_mtx;
+std::vector<PinnedBuf> g_pool;
+constexpr size_t POOL_MAX_FREE = 4;
+
+void* pool_acquire (size_t bytes, size_t* got)
+{
+	{
+		std::lock_guard<std::mutex> lk (g_pool_mtx);
+		int best = -1;
+		for (int i = 0; i < (int)g_pool.size(); i++)
+			if (!g_pool[i].in_use && g_pool[i].bytes >= bytes && (best < 0 || g_pool[i].bytes < g_pool[best].bytes))
+				best = i;
+		if (best >= 0)
+		{
+			g_pool[best].in_use = true;
+			*got = g_pool[best].bytes;
+			return g_pool[best].p;
+		}
+	}
+	void* p = nullptr;
+	if (cudaHostAlloc (&p, bytes, cudaHostAllocPortable) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	std::lock_guard<std::mutex> lk (g_pool_mtx);
+	g_pool.push_back ({ p, bytes, true });
+	*got = bytes;
+	return p;
+}
+
+void pool_release (void* p)
+{
+	if (!p)
+		return;
+	std::vector<void*> drop;
+	{
+		std::lock_guard<std::mutex> lk (g_pool_mtx);
+		for (auto& b : g_pool)
+			if (b.p == p)
+				b.in_use = false;
+		// keep the POOL_MAX_FREE largest free buffers
+		for (;;)
+		{
+			size_t nfree = 0;
+			int smallest = -1;
+			for (int i = 0; i < (int)g_pool.size(); i++)
+				if (!g_pool[i].in_use)
+				{
+					nfree++;
+					if (smallest < 0 || g_pool[i].bytes < g_pool[smallest].bytes)
+						smallest = i;
+				}
+			if (nfree <= POOL_MAX_FREE)
+				break;
+			drop.push_back (g_pool[smallest].p);
+			g_pool.erase (g_pool.begin() + smallest);
+		}
+	}
+	for (void* d : drop)
+		cudaFreeHost (d);
+}
 
 } // namespace
 
@@ -220,6 +289,72 @@ void rebuild_selection (nyxb200_ctx* ctx)
 	ctx->sel_dirty = true;
 }
 
+// the feature table of a 2D / 3D context
+std::vector<FeatureDef> feature_table (int dim)
+{
+	std::vector<FeatureDef> v;
+	if (dim == 3)
+		for (const auto& f : g_features3d_src)
+			v.push_back ({ f.name, f.code, f.family, f.col0, 1 });
+	else
+		for (const auto& f : g_features2d)
+			v.push_back (f);
+	return v;
+}
+
+// Group / feature names -> enabled flags, exactly as Environment::expand_featuregroups does (env_features.cpp:456-528);
+// needs no device (nyxb200_validate_features)
+int resolve_features (int dim, const std::vector<FeatureDef>& feats, const char* const* names, int n, bool* on, std::string& msg)
+{
+	const int nf = (int)feats.size();
+	const bool d3 = dim == 3;
+	for (int i = 0; i < NFEATURES_MAX; i++)
+		on[i] = false;	// env_features.cpp:459 "initially, no features are enabled"
+	for (int k = 0; k < n; k++)
+	{
+		const char* s = names[k];
+		if (!s)
+		{
+			msg = "null feature name";
+			return NYXB200_EINVAL;
+		}
+		bool found = false;
+		const GroupDef* groups = d3 ? g_groups3d : g_groups2d;
+		const int ngroups = d3 ? (int)(sizeof (g_groups3d) / sizeof (g_groups3d[0])) : (int)(sizeof (g_groups2d) / sizeof (g_groups2d[0]));
+		for (int gi = 0; gi < ngroups && !found; gi++)
+			if (!strcmp (groups[gi].name, s))
+			{
+				for (int i = 0; i < nf; i++)
+					if (groups[gi].fam_mask & (1 << feats[i].family))
+						on[i] = true;
+				found = true;
+			}
+		if (found)
+			continue;
+		if (d3)
+			for (const char* g : g_groups3d_unbuilt)
+				if (!strcmp (g, s))
+				{
+					msg = std::string ("feature group '") + s + "' contains 3D families outside this path "
+						"(built: *3D_ALL_INTENSITY*, *3D_GLCM*, *3D_GLSZM*, *3D_NGTDM*)";
+					return NYXB200_EUNSUPPORTED;
+				}
+		for (int i = 0; i < nf; i++)
+			if (!strcmp (feats[i].name, s))
+			{
+				on[i] = true;
+				found = true;
+				break;
+			}
+		if (!found)	// env_features.cpp:496,507
+		{
+			msg = std::string ("Error: '") + s + "' is not a valid " + (d3 ? "3D" : "2D") + " feature name ";
+			return NYXB200_EINVAL;
+		}
+	}
+	return NYXB200_OK;
+}
+
 } // namespace
 
 extern "C"
@@ -300,12 +435,7 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out)
 	nyxb200_ctx* ctx = new nyxb200_ctx();
 	ctx->st = *s;
 	ctx->sm_count = prop.multiProcessorCount;
-	if (s->dim == 3)
-		for (const auto& f : g_features3d_src)
-			ctx->feats.push_back ({ f.name, f.code, f.family, f.col0, 1 });
-	else
-		for (const auto& f : g_features2d)
-			ctx->feats.push_back (f);
+	ctx->feats = feature_table (s->dim);
 	for (int i = 0; i < NFEATURES_MAX; i++)
 		ctx->feat_on[i] = false;
 	if (cudaStreamCreateWithFlags (&ctx->stream, cudaStreamNonBlocking) != cudaSuccess)
@@ -347,8 +477,7 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	ctx->g_hcnts.release(); ctx->g_flags.release(); ctx->g_idx.release(); ctx->g_acc.release(); ctx->g_hkeys.release(); ctx->g_part.release();
 	ctx->g_recs.release();
 	ctx->d_rowoff.release(); ctx->d_dbg.release(); ctx->d_dbgf.release(); ctx->d_blkcells.release(); ctx->d_tiles.release();
-	if (ctx->h_out)
-		cudaFreeHost (ctx->h_out);
+	pool_release (ctx->h_out);
 	for (auto& ev : ctx->ev)
 		cudaEventDestroy (ev);
 	for (auto& ev : ctx->ev_end)
@@ -372,44 +501,33 @@ int nyxb200_select_features (nyxb200_ctx* ctx, const char* const* names, int n)
 	if (!ctx || (!names && n))
 		return fail (ctx, NYXB200_EINVAL, "null argument");
 	bool on[NFEATURES_MAX];
-	const int nf = (int)ctx->feats.size();
-	const bool d3 = ctx->st.dim == 3;
-	for (int i = 0; i < NFEATURES_MAX; i++)
-		on[i] = false;	// env_features.cpp:459 "initially, no features are enabled"
-	for (int k = 0; k < n; k++)
-	{
-		const char* s = names[k];
-		bool found = false;
-		const GroupDef* groups = d3 ? g_groups3d : g_groups2d;
-		const int ngroups = d3 ? (int)(sizeof (g_groups3d) / sizeof (g_groups3d[0])) : (int)(sizeof (g_groups2d) / sizeof (g_groups2d[0]));
-		for (int gi = 0; gi < ngroups && !found; gi++)
-			if (!strcmp (groups[gi].name, s))
-			{
-				for (int i = 0; i < nf; i++)
-					if (groups[gi].fam_mask & (1 << ctx->feats[i].family))
-						on[i] = true;
-				found = true;
-			}
-		if (found)
-			continue;
-		if (d3)
-			for (const char* g : g_groups3d_unbuilt)
-				if (!strcmp (g, s))
-					return fail (ctx, NYXB200_EUNSUPPORTED, "feature group '%s' contains 3D families outside this path "
-						"(built: *3D_ALL_INTENSITY*, *3D_GLCM*, *3D_GLSZM*, *3D_NGTDM*)", s);
-		for (int i = 0; i < nf; i++)
-			if (!strcmp (ctx->feats[i].name, s))
-			{
-				on[i] = true;
-				found = true;
-				break;
-			}
-		if (!found)	// env_features.cpp:496,507
-			return fail (ctx, NYXB200_EINVAL, "Error: '%s' is not a valid %s feature name ", s, d3 ? "3D" : "2D");
-	}
+	std::string msg;
+	if (int rc = resolve_features (ctx->st.dim, ctx->feats, names, n, on, msg))
+		return fail (ctx, rc, "%s", msg.c_str());
 	memcpy (ctx->feat_on, on, sizeof (on));
 	rebuild_selection (ctx);
 	return NYXB200_OK;
+}
+
+int nyxb200_validate_features (int dim, const char* const* names, int n, char* msg, size_t msgcap)
+{
+	if (msg && msgcap)
+		msg[0] = 0;
+	std::string m;
+	int rc = NYXB200_OK;
+	if ((dim != 2 && dim != 3) || (!names && n))
+	{
+		rc = NYXB200_EINVAL;
+		m = "bad argument";
+	}
+	else
+	{
+		bool on[NFEATURES_MAX];
+		rc = resolve_features (dim, feature_table (dim), names, n, on, m);
+	}
+	if (rc && msg && msgcap)
+		snprintf (msg, msgcap, "%s", m.c_str());
+	return rc;
 }
 
 int nyxb200_num_columns (const nyxb200_ctx* ctx) { return ctx ? (int)ctx->sel_cols.size() : 0; }
@@ -1127,21 +1245,23 @@ int join_families (nyxb200_ctx* ctx)
 	return 0;
 }
 
-// grow-only pinned host buffer for the result table (keeps its content when it grows)
+// grow-only pinned host buffer for the result table (keeps its content when it grows); buffers come from the pool
 int reserve_pinned_out (nyxb200_ctx* ctx, size_t n)
 {
 	if (n <= ctx->h_out_cap)
 		return 0;
-	size_t want = n + n / 2 + 1024;
-	double* p = nullptr;
-	CU (cudaMallocHost ((void**)&p, want * sizeof (double)));
+	const size_t want = ctx->h_out ? n + n / 2 + 1024 : n + 1024;
+	size_t got = 0;
+	double* p = (double*)pool_acquire (want * sizeof (double), &got);
+	if (!p)
+		return fail (ctx, NYXB200_ENOMEM, "cannot allocate %zu bytes of pinned host memory for the result table", want * sizeof (double));
 	if (ctx->h_out)
 	{
 		memcpy (p, ctx->h_out, ctx->h_out_used * sizeof (double));
-		cudaFreeHost (ctx->h_out);
+		pool_release (ctx->h_out);
 	}
 	ctx->h_out = p;
-	ctx->h_out_cap = want;
+	ctx->h_out_cap = got / sizeof (double);
 	return 0;
 }
 
@@ -1170,7 +1290,32 @@ int launch_scan (nyxb200_ctx* ctx, const ImageView& im, uint32_t nrows, uint32_t
 }
 
 // One slide already resident on the device.  Appends its rows to the context's pinned table buffer.
+int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t* nrows_out);
+
+// Failure funnel: an error return in the middle of a slide (unsupported configuration found after the fork, a CUDA
+// failure) must not leave kernels in flight on the family / copy streams or the launch-stream selection pointing at
+// a family stream -- the caller's buffers may be released as soon as the call returns.
 int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t* nrows_out)
+{
+	const int rc = process_slide_body (ctx, im, img_index, nrows_out);
+	if (rc)
+	{
+		const std::string msg = ctx->err;
+		for (auto& fs : ctx->fstream)
+			cudaStreamSynchronize (fs);
+		cudaStreamSynchronize (ctx->copy_stream);
+		cudaStreamSynchronize (ctx->stream);
+		cudaGetLastError();
+		ctx->ls = ctx->stream;
+		ctx->lsi = 0;
+		ctx->open_stage = -1;
+		ctx->cur_b = 0;
+		ctx->err = msg;
+	}
+	return rc;
+}
+
+int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t* nrows_out)
 {
 	const unsigned long long npix = (unsigned long long)im.D * (unsigned long long)im.H * (unsigned long long)im.W;
 	const bool d3 = ctx->st.dim == 3;
@@ -1756,6 +1901,83 @@ void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t)
 		t->data = nullptr;
 		t->nrows = 0;
 	}
+}
+
+int nyxb200_table_detach (nyxb200_ctx* ctx, nyxb200_table* t)
+{
+	if (!ctx || !t)
+		return fail (ctx, NYXB200_EINVAL, "null argument");
+	if (!t->data)
+		return NYXB200_OK;	// empty table: nothing to hand over
+	if (t->data != ctx->h_out)
+		return fail (ctx, NYXB200_EINVAL, "the table is not the context's current result");
+	// the caller owns the buffer from here on (nyxb200_host_release); the next featurize call takes another one
+	ctx->h_out = nullptr;
+	ctx->h_out_cap = 0;
+	ctx->h_out_used = 0;
+	return NYXB200_OK;
+}
+
+void nyxb200_host_release (void* p)
+{
+	pool_release (p);
+}
+
+int nyxb200_get_param (const nyxb200_ctx* ctx, const char* key, double* value)
+{
+	if (!ctx || !key || !value)
+		return NYXB200_EINVAL;
+	if (!strcmp (key, "glcm/offset")) *value = ctx->st.glcm_offset;
+	else if (!strcmp (key, "coarse_gray_depth")) *value = ctx->st.coarse_gray_depth;
+	else if (!strcmp (key, "glcm/greydepth") || !strcmp (key, "3glcm/greydepth"))
+		*value = ctx->glcm_greydepth_set ? ctx->glcm_greydepth : ctx->st.coarse_gray_depth;
+	else if (!strcmp (key, "ibsi")) *value = ctx->st.ibsi;
+	else if (!strcmp (key, "glcm/symmetric")) *value = ctx->st.glcm_symmetric;
+	else if (!strcmp (key, "soft_nan")) *value = ctx->st.soft_nan;
+	else if (!strcmp (key, "concurrent_families")) *value = ctx->concurrent;
+	else if (!strcmp (key, "roi_batches")) *value = ctx->roi_batches;
+	else if (!strcmp (key, "tile_store")) *value = ctx->use_tile_store;
+	else if (!strcmp (key, "3glszm/greydepth")) *value = ctx->glszm3_greydepth;
+	else if (!strcmp (key, "3ngtdm/greydepth")) *value = ctx->ngtdm3_greydepth;
+	else if (!strcmp (key, "3ngtdm/radius")) *value = ctx->ngtdm3_radius;
+	else
+		return NYXB200_EINVAL;
+	return NYXB200_OK;
+}
+
+int nyxb200_device_count (void)
+{
+	int ndev = 0;
+	if (cudaGetDeviceCount (&ndev) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return 0;
+	}
+	int n = 0;
+	for (int d = 0; d < ndev; d++)
+	{
+		int major = 0;
+		if (cudaDeviceGetAttribute (&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10)
+			n = d + 1;	// ordinals are CUDA's: the count is "one past the last usable device"
+	}
+	return n;
+}
+
+int nyxb200_device_info (int device, char* name, size_t namecap, int64_t* total_mem, int* sm_count, int* cc_major, int* cc_minor)
+{
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties (&prop, device) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return NYXB200_ECUDA;
+	}
+	if (name && namecap)
+		snprintf (name, namecap, "%s", prop.name);
+	if (total_mem) *total_mem = (int64_t)prop.totalGlobalMem;
+	if (sm_count) *sm_count = prop.multiProcessorCount;
+	if (cc_major) *cc_major = prop.major;
+	if (cc_minor) *cc_minor = prop.minor;
+	return NYXB200_OK;
 }
 
 int nyxb200_last_timings (const nyxb200_ctx* ctx, float* ms, int n)

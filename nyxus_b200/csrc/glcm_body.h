@@ -358,7 +358,17 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 
 	if (dbg && dbg->joint)
 		for (int i = g.tid; i < Ng * Ng; i += g.nthr)
-			dbg->joint[(size_t)a * Ng * Ng + i] = J.get (i);
+		{
+			if constexpr (RAD)
+			{
+				// the dump is by grey LEVEL (the oracle reports I[row], I[col]); the matrix is by rank
+				const int row = i / Ng, col = i % Ng;
+				if (row < NgRoi && col < NgRoi)
+					dbg->joint[(size_t)a * Ng * Ng + (size_t)(Ilev[row] - 1) * Ng + (Ilev[col] - 1)] = J.get (i);
+			}
+			else
+				dbg->joint[(size_t)a * Ng * Ng + i] = J.get (i);
+		}
 
 	if (!q[Q_N])	// glcm.cpp:260-295 (nothing was counted: the region is still all zero)
 	{

@@ -41,3 +41,18 @@ NGLDM_NONIBSI_MATRIX = np.array([[1, 2, 3, 0, 0, 0], [1, 2, 3, 2, 0, 0], [0, 1, 
 GLDZM_IBSI_IMAGE = np.array([[1, 2, 2, 3], [1, 2, 3, 3], [4, 2, 4, 1], [4, 1, 2, 3]])
 # rows = grey level 1..4, columns = zone distance 1..2 (test_data.h:258-265)
 GLDZM_IBSI_MATRIX = np.array([[3, 0], [2, 0], [2, 0], [1, 1]])
+
+# tests/python/test_data.py:3-46 -- `intens` / `seg` of the reference's Python test-suite (the IBSI phantom as the Python
+# tests hold it: slice 3 carries a 6 where test_data.h has a 9)
+PY_INTENS = np.array([
+    [[1, 4, 4, 1, 1], [1, 4, 6, 1, 1], [4, 1, 6, 4, 1], [4, 4, 6, 4, 1]],
+    [[1, 4, 4, 1, 1], [1, 1, 6, 1, 1], [1, 1, 3, 1, 1], [4, 4, 6, 1, 1]],
+    [[1, 4, 4, 1, 1], [1, 1, 1, 1, 1], [1, 1, 6, 1, 1], [1, 1, 6, 1, 1]],
+    [[1, 4, 4, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 6, 1, 1]],
+])
+PY_SEG = np.array([
+    [[1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1]],
+    [[1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [0, 1, 1, 1, 1], [1, 1, 1, 1, 1]],
+    [[1, 1, 1, 0, 0], [1, 1, 1, 1, 1], [1, 1, 0, 1, 1], [1, 1, 1, 1, 1]],
+    [[1, 1, 1, 0, 0], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1], [1, 1, 1, 1, 1]],
+])

@@ -1,0 +1,121 @@
+"""GPU tests (-m gpu) of the drop-in boundary as a COMPILED module: the reference's own, unmodified Python layer
+(src/nyx/python/nyxus/nyxus.py, staged under oracle/_ref/pyb200 by oracle/Makefile.backend) drives
+nyxus_b200/backend*.so, and its DataFrames are compared with the same Python layer over the reference's own compiled
+backend (oracle/_ref/pyref, SURVEY 8c option B).  Also reproduces tests/python/test_nyxus.py:400-446 of the reference."""
+import os
+
+import numpy as np
+import pytest
+
+import nyx_testutil as tu
+from oracle import pyref
+from reference_fixtures import PY_INTENS, PY_SEG
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not pyref.staged_available(), reason="reference Python layer not staged (oracle/Makefile.backend)")]
+
+TEX = ["*ALL_GLCM*", "*ALL_GLRLM*", "*ALL_GLDZM*", "*ALL_GLSZM*", "*ALL_GLDM*", "*ALL_NGLDM*", "*ALL_NGTDM*"]
+
+
+def _frames_match(ref_df, got_df):
+    assert list(ref_df.columns) == list(got_df.columns)
+    assert ref_df.shape == got_df.shape
+    for c in ("intensity_image", "mask_image"):
+        assert list(ref_df[c]) == list(got_df[c]), c
+    assert np.array_equal(ref_df.ROI_label.to_numpy(), got_df.ROI_label.to_numpy())
+    cols = list(ref_df.columns[2:])
+    bad = tu.mismatches(ref_df[cols].to_numpy(np.float64), got_df[cols].to_numpy(np.float64), cols)
+    assert not bad, bad[:8]
+
+
+def test_reference_pytest_in_memory_2d():
+    """tests/python/test_nyxus.py:400-409"""
+    nyxus = pyref.reference_on_b200()
+    nyx = nyxus.Nyxus(["*ALL_GLCM*"], ibsi=True)
+    names = ["test_name_1"]
+    df = nyx.featurize(PY_INTENS[0], PY_SEG[0], names, names)
+    assert nyx.error_message == ''
+    assert df.shape[0] == 1 and list(df.intensity_image) == names and list(df.mask_image) == names
+
+
+def test_reference_pytest_in_memory_3d():
+    """tests/python/test_nyxus.py:411-446 (IBSI consensus values of the phantom, 1 % / 10 %)"""
+    nyxus = pyref.reference_on_b200()
+    nyx = nyxus.Nyxus([
+        "GLCM_ASM", "GLCM_CONTRAST", "GLCM_CORRELATION", "GLCM_DIFAVE",
+        "GLCM_DIFENTRO", "GLCM_DIFVAR", "GLCM_ENERGY", "GLCM_ENTROPY",
+        "GLCM_HOM1", "GLCM_INFOMEAS1", "GLCM_INFOMEAS2", "GLCM_IDM",
+        "GLCM_SUMAVERAGE", "GLCM_SUMENTROPY", "GLCM_SUMVARIANCE", "GLCM_VARIANCE"], ibsi=True)
+    names = ["test_name_1", "test_name_2", "test_name_3", "test_name_4"]
+    nyx.set_metaparam("glcm/greydepth=100")
+    nyx.set_metaparam("glcm/offset=1")
+    df = nyx.featurize(PY_INTENS, PY_SEG, names, names)
+    assert nyx.error_message == ''
+    mean_values = df.mean(numeric_only=True).tolist()
+    mean_values.pop(0)
+    mean_values.pop(0)
+    averaged = [sum(mean_values[i:i + 4]) / 4 for i in range(0, len(mean_values), 4)]
+    assert pytest.approx(averaged[0], 0.01) == 0.368
+    assert pytest.approx(averaged[1], 0.01) == 5.28
+    assert pytest.approx(averaged[2], 0.01) == -0.0121
+    assert pytest.approx(averaged[4], 0.01) == 1.40
+    assert pytest.approx(averaged[5], 0.1) == 2.90
+
+
+@pytest.mark.skipif(not pyref.reference_available(), reason="oracle/_ref/pyref (the reference's compiled backend) not built")
+@pytest.mark.parametrize("ibsi", [False, True])
+def test_reference_python_layer_same_table_over_both_backends(ibsi):
+    from nyxus_b200 import synth
+    ref_nyxus, our_nyxus = pyref.reference(), pyref.reference_on_b200()
+    inten, label = synth.blob_slide(192, 256, 32, 7, 12, seed=21, jitter=2)
+    inten2, label2 = synth.blob_slide(192, 256, 32, 8, 13, seed=22, jitter=1)
+    I = np.stack([inten, inten2]).astype(np.uint16)
+    L = np.stack([label, label2])
+    if ibsi:
+        I = (I >> 6).astype(np.uint16)      # IBSI mode indexes matrices by raw intensity: keep the levels small
+    feats = TEX + ["*ALL_INTENSITY*"]
+    kw = dict(ibsi=ibsi, coarse_gray_depth=48, n_feature_calc_threads=4)
+    ref_df = ref_nyxus.Nyxus(feats, **kw).featurize(I.copy(), L.copy(), ["a.tif", "b.tif"], ["ma.tif", "mb.tif"])
+    our = our_nyxus.Nyxus(feats, **kw)
+    got_df = our.featurize(I.copy(), L.copy(), ["a.tif", "b.tif"], ["ma.tif", "mb.tif"])
+    assert our.error_message == ''
+    _frames_match(ref_df, got_df)
+    # metaparameters through the reference's set_metaparam: glcm/offset changes the GLCM block, glcm/greydepth only the blank test
+    r2, o2 = ref_nyxus.Nyxus(["*ALL_GLCM*"], **kw), our_nyxus.Nyxus(["*ALL_GLCM*"], **kw)
+    for n in (r2, o2):
+        n.set_metaparam("glcm/offset=2")
+        n.set_metaparam("glcm/greydepth=3")
+    _frames_match(r2.featurize(I[0].copy(), L[0].copy()), o2.featurize(I[0].copy(), L[0].copy()))
+    # negative intensities are shifted by the Python layer (nyxus.py:482-484) before they reach the backend
+    J = I[0].astype(np.int32) - 500
+    _frames_match(ref_nyxus.Nyxus(["*ALL_GLRLM*"], **kw).featurize(J.copy(), L[0].copy()),
+                  our_nyxus.Nyxus(["*ALL_GLRLM*"], **kw).featurize(J.copy(), L[0].copy()))
+
+
+@pytest.mark.skipif(not pyref.reference_available(), reason="oracle/_ref/pyref (the reference's compiled backend) not built")
+def test_reference_nyxus3d_featurize_files_over_both_backends(tmp_path):
+    """Nyxus3D.featurize_files on NIfTI volumes (new_bindings_py.cpp:753-856): file names, row order and values"""
+    from nyxus_b200 import nifti
+    ref_nyxus, our_nyxus = pyref.reference(), pyref.reference_on_b200()
+    rng = np.random.default_rng(5)
+    files = []
+    for k in range(2):
+        D, H, W = 20, 24, 28
+        vol = rng.integers(1, 900, (D, H, W)).astype(np.uint16)
+        lab = np.zeros((D, H, W), np.uint16)
+        lab[2:11, 3:14, 2:12] = 1
+        lab[9:19, 10:22, 14:26] = 2 + k
+        lab[4:8, 16:22, 3:9] = 7
+        lab[rng.random((D, H, W)) < 0.08] = 0
+        fi, fm = str(tmp_path / ("v%d.nii" % k)), str(tmp_path / ("m%d.nii" % k))
+        nifti.write(fi, vol)
+        nifti.write(fm, lab)
+        files.append((fi, fm))
+    feats = ["*3D_GLCM*", "*3D_GLSZM*", "*3D_NGTDM*", "*3D_ALL_INTENSITY*"]
+
+    def run(mod):
+        n = mod.Nyxus3D(feats, coarse_gray_depth=32)
+        for mp in ("3glcm/greydepth=24", "3glszm/greydepth=16", "3ngtdm/greydepth=16", "3ngtdm/radius=1"):
+            n.set_metaparam(mp)
+        return n.featurize_files([f[0] for f in files], [f[1] for f in files], False)
+    _frames_match(run(ref_nyxus), run(our_nyxus))
