@@ -137,6 +137,130 @@ def reference_arm(args, rank, world):
     print(json.dumps(line))
 
 
+def c5_job(args, rank, local_rank, world):
+    """BASELINE configs[4]: ONE job of 64 distinct configs[1]-shaped slides (seeds 100..163), *ALL_TEXTURE* + *ALL_INTENSITY*,
+    sharded by pixel count over N GPUs of one box through nyxb200_featurize_2d_list_multi: one process, one host thread
+    and one context per device, no inter-GPU exchange, every row copied from its device straight into ONE pinned host
+    table.  Strong scaling: the job is the same at every N.  Under torchrun the ranks only provide the barrier (NCCL):
+    rank 0 drives all N devices, which is how a caller of the library would use a multi-GPU box."""
+    import torch
+    import torch.distributed as dist
+    from nyxus_b200 import Engine, synth
+    from nyxus_b200.engine import featurize_list_multi, shard_slides
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback")
+    N = args.gpus
+    if torch.cuda.device_count() < N:
+        raise SystemExit("bench.py: --gpus %d but only %d devices are visible" % (N, torch.cuda.device_count()))
+    if world > 1:
+        torch.cuda.set_device(local_rank)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
+        if rank != 0:
+            dist.barrier()      # rank 0 works; the others wait for it
+            dist.destroy_process_group()
+            return
+    S = args.slides
+    size = args.size
+    owner = shard_slides(N, S)          # equal pixel counts: slide k -> device k % N
+    # ---- the slides: generated on the device that will process them (resident leg) + pinned host copies (e2e leg)
+    d_int, d_lab = [], []
+    for k in range(S):
+        i, l = synth.config2_device(100 + k, "cuda:%d" % owner[k], size=size)
+        d_int.append(i)
+        d_lab.append(l)
+    for d in range(N):
+        torch.cuda.synchronize(d)
+    import psutil
+    per_slide = size * size * 6
+    nh = args.host_slides if args.host_slides > 0 else (S if psutil.virtual_memory().available > 3 * S * per_slide + (64 << 30) else min(S, 16))
+    h_int = [torch.empty((size, size), dtype=torch.uint16).pin_memory() for _ in range(nh)]
+    h_lab = [torch.empty((size, size), dtype=torch.int32).pin_memory() for _ in range(nh)]
+    for k in range(nh):
+        h_int[k].copy_(d_int[k])
+        h_lab[k].copy_(d_lab[k])
+    engines = [Engine(FEATURES, device=d, coarse_gray_depth=64) for d in range(N)]
+    ncols = len(engines[0].columns)
+
+    def sync_all():
+        for d in range(N):
+            torch.cuda.synchronize(d)
+
+    def job(resident):
+        if resident:
+            ips, lps = [t.data_ptr() for t in d_int], [t.data_ptr() for t in d_lab]
+        else:
+            ips, lps = [h_int[k % nh].data_ptr() for k in range(S)], [h_lab[k % nh].data_ptr() for k in range(S)]
+        tab, rimg = featurize_list_multi(engines, ips, True, lps, size, size, on_device=resident, copy=False)
+        dev_ms = max(e.timings()["total"] for e in engines)
+        launches = sum(e.counts()["launches"] for e in engines)
+        return tab.shape[0], dev_ms, launches, tab, rimg
+
+    res = {}
+    samplers = [ClockSampler(d) for d in range(N)]
+    for resident in (True, False):
+        for _ in range(max(1, min(args.warmup, 2))):      # the first job also pins the 18 GB result table
+            job(resident)
+        sync_all()
+        if resident:
+            for sm in samplers:
+                sm.start()
+        t0 = time.perf_counter()
+        dev_ms = 0.0
+        rois = 0
+        launches = 0
+        for _ in range(args.steps):
+            n, ms, ln, tab, rimg = job(resident)
+            rois += n
+            dev_ms += ms
+            launches += ln
+        sync_all()
+        wall = time.perf_counter() - t0
+        if resident:
+            clocks = [sm.stop() for sm in samplers]
+        # the one table: rows of slide k are contiguous, slides in order, labels ascending inside a slide
+        assert tab.shape[1] == ncols + 2 and np.all(np.diff(rimg) >= 0) and int(rimg[-1]) == S - 1
+        res[resident] = dict(rois=rois, dev_ms=dev_ms, wall=wall, launches=launches, rows=tab.shape[0])
+    r, e = res[True], res[False]
+    nroi = r["rows"]
+    npix = size * size * S
+    clk = {"sm_mhz": min(c["sm_mhz"] or 0 for c in clocks), "sm_max_mhz": max(c["sm_max_mhz"] or 0 for c in clocks),
+           "reasons": sorted(set(x for c in clocks for x in c["reasons"])), "per_gpu_sm_mhz": [c["sm_mhz"] for c in clocks]}
+    line = {
+        "metric": METRIC, "value": r["rois"] / r["wall"], "unit": "ROIs/s", "n_gpus": N, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": r["wall"] / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "configs[4]: ONE job of %d distinct %dx%d uint16 slides + uint32 masks (%d ROIs, seeds 100..%d, generated on the device: synth.config2_device), *ALL_TEXTURE*+*ALL_INTENSITY* (%d columns), sharded by pixel count over %d GPU(s) by nyxb200_featurize_2d_list_multi, rows gathered in ONE pinned host table inside the timed region" % (S, size, size, nroi, 100 + S - 1, ncols, N),
+                   "features": FEATURES, "coarse_gray_depth": 64, "rois_per_job": nroi, "slides": S,
+                   "mpix_per_s": npix * args.steps / r["wall"] / 1e6,
+                   "l2": "every slide (600 MB) exceeds the 126 MB L2; no explicit flush",
+                   "timing": "host clock around the K jobs, all devices synchronised on both sides (one call spans N devices, so there is no single stream to put events on); device_ms_per_step = max over devices of the summed per-slide CUDA-event times",
+                   "device_ms_per_step": r["dev_ms"] / args.steps,
+                   "process_model": "one process, one host thread + one context per GPU (torchrun ranks > 0 only join the barrier)"},
+        "e2e": {"value": e["rois"] / e["wall"], "unit": "ROIs/s", "h2d_bytes_per_step": npix * 6, "d2h_bytes_per_step": nroi * (ncols + 2) * 8,
+                "ms_per_step": e["wall"] / args.steps * 1e3, "mpix_per_s": npix * args.steps / e["wall"] / 1e6,
+                "how": "the same call with %d distinct PINNED host slides%s; every slide's H2D and every row's D2H inside the timed region" % (nh, "" if nh == S else " cycled over the %d slides of the job" % S)},
+        "gpu_launches": r["launches"],
+        "clocks": clk,
+    }
+    print(json.dumps(line))
+    for en in engines:
+        en.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -147,6 +271,11 @@ def main():
     ap.add_argument("--ref-crop", type=int, default=0, help="side of the crop the CPU reference is timed on (0 = sized from a probe: "
                     "~4 s per step for --impl reference, ~15 s for the cpu_baseline of the default arm)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"], help="c2 = configs[1], one slide per GPU (default, weak scaling); "
+                    "c5 = configs[4], ONE job of --slides distinct slides sharded by pixel count over the --gpus devices (strong scaling)")
+    ap.add_argument("--slides", type=int, default=64, help="slides of the c5 job (configs[4] = 64)")
+    ap.add_argument("--host-slides", type=int, default=0, help="c5: distinct slides held in pinned host memory for the e2e leg "
+                    "(0 = all of them when the host has the memory, else 16 cycled)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
 
@@ -156,6 +285,9 @@ def main():
 
     if args.impl == "reference":
         reference_arm(args, rank, world)
+        return
+    if args.workload == "c5":
+        c5_job(args, rank, local_rank, world)
         return
 
     import torch
@@ -273,15 +405,32 @@ def main():
     barrier()
     wall_e2e_single = time.perf_counter() - t1
 
+    # ---- the drop-in call itself: Nyxus.featurize(numpy uint16, numpy uint32) on PAGEABLE arrays, DataFrame included
+    from nyxus_b200 import Nyxus
+    nyx = Nyxus(FEATURES, use_gpu_device=local_rank)
+    api_rows = 0
+    for _ in range(2):
+        nyx.featurize(inten, label)
+    barrier()
+    n_api = min(args.steps, 5)
+    t1 = time.perf_counter()
+    for i in range(n_api):
+        df = nyx.featurize(inten if i % 2 == 0 else inten2, label if i % 2 == 0 else label2)
+        api_rows += df.shape[0]
+        del df
+    barrier()
+    wall_api = time.perf_counter() - t1
+    del nyx
+
     # ---- max over ranks
     ev_s = ev_ms / 1e3
-    tt = torch.tensor([ev_s, wall, wall_e2e, wall_e2e_single], dtype=torch.float64, device="cuda")
-    nn = torch.tensor([float(nroi), float(rois_e2e)], dtype=torch.float64, device="cuda")
+    tt = torch.tensor([ev_s, wall, wall_e2e, wall_e2e_single, wall_api], dtype=torch.float64, device="cuda")
+    nn = torch.tensor([float(nroi), float(rois_e2e), float(api_rows)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(nn, op=dist.ReduceOp.SUM)
-    ev_s, wall, wall_e2e, wall_e2e_single = [float(x) for x in tt.tolist()]
-    total_rois, total_rois_e2e = [float(x) for x in nn.tolist()]
+    ev_s, wall, wall_e2e, wall_e2e_single, wall_api = [float(x) for x in tt.tolist()]
+    total_rois, total_rois_e2e, total_rois_api = [float(x) for x in nn.tolist()]
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -301,8 +450,9 @@ def main():
         # DRAM bytes per step of every stage from the committed `ncu --set full` capture (dram__bytes_read.sum +
         # dram__bytes_write.sum, summed over the stage's launches of one step; tools/ncu_traffic.py)
         traffic = {}
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tp) and args.size == 10000:
+        tps = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+        tp = os.path.join(ROOT, "profiles", tps[-1]) if tps else ""
+        if tp and args.size == 10000:
             try:
                 traffic = json.load(open(tp))["bytes_per_step"]
             except Exception:
@@ -330,6 +480,8 @@ def main():
             "e2e_single": {"value": total_rois * args.steps / wall_e2e_single, "unit": "ROIs/s",
                            "ms_per_step": wall_e2e_single / args.steps * 1e3,
                            "how": "%d separate nyxb200_featurize_2d_u16 calls, one slide each (no overlap across calls)" % args.steps},
+            "e2e_api": {"value": total_rois_api / wall_api, "unit": "ROIs/s", "ms_per_step": wall_api / n_api * 1e3,
+                        "how": "%d calls of nyxus_b200.Nyxus.featurize(numpy uint16 [H,W], numpy uint32 [H,W]) on PAGEABLE arrays (two slides alternating), pandas DataFrame included; host clock" % n_api},
             "gpu_launches": launches,
             "clocks": clocks,
             "stage_ms": {k: round(v, 4) for k, v in per_conc.items()},

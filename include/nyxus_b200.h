@@ -114,6 +114,21 @@ int nyxb200_featurize_2d_list (nyxb200_ctx* ctx, const void* const* inten, int i
 	int on_device, int n_img, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
 int nyxb200_featurize_3d_list (nyxb200_ctx* ctx, const void* const* inten, int inten_is_u16, const uint32_t* const* label,
 	int on_device, int n_vol, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image);
+/* SEVERAL DEVICES, one call (BASELINE configs[4]: a list of slides sharded by pixel count over the GPUs of one box;
+ * reference: the slide loop of processDataset_2D_segmented / processMontage, one slide after the other on the host
+ * cores).  `ctxs`: one 2D context per device with the same feature selection.  Slide k goes to the device
+ * nyxb200_shard_slides() names: longest-processing-time-first on `weight[k]` (pixel count or any cost estimate; NULL =
+ * equal, slide k -> device k % n_ctx), every device walking its slides in ascending order with the pipeline of
+ * nyxb200_featurize_2d_list (upload of its next slide || compute || D2H of finished ROI batches), one host thread per
+ * device.  No inter-GPU exchange: ROIs never span slides.  Rows land in ONE pinned host table, slide-major in slide
+ * order and by ascending label inside a slide -- the order a single-device call gives -- without a gather pass: a
+ * slide claims its row range as soon as its ROI count is known and its rows are copied from the device straight to
+ * their final place.  With on_device != 0, inten[k] / label[k] must live on the device of ctxs[owner[k]].
+ * The table belongs to ctxs[0] (valid until its next call; nyxb200_table_detach works on it). */
+int nyxb200_shard_slides (int n_dev, int n_img, const int64_t* weight, int32_t* owner);
+int nyxb200_featurize_2d_list_multi (nyxb200_ctx* const* ctxs, int n_ctx, const void* const* inten, int inten_is_u16,
+	const uint32_t* const* label, int on_device, int n_img, int64_t H, int64_t W, const int64_t* weight,
+	nyxb200_table* out, const int32_t** row_image);
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t);
 /* Ownership hand-over of a result table (reference: the std::vector<double> moved into a capsule-owned numpy array,
  * as_pyarray new_bindings_py.cpp:63-73,631-640): after a successful detach `t->data` belongs to the caller and stays

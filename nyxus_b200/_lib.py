@@ -53,6 +53,16 @@ def lib():
     L.nyxb200_featurize_2d_list.argtypes = [vp, C.POINTER(vp), i32, C.POINTER(vp), i32, i32, i64, i64, C.POINTER(Table), C.POINTER(C.POINTER(C.c_int32))]
     L.nyxb200_featurize_3d_list.argtypes = [vp, C.POINTER(vp), i32, C.POINTER(vp), i32, i32, i64, i64, i64, C.POINTER(Table), C.POINTER(C.POINTER(C.c_int32))]
     L.nyxb200_table_free.argtypes = [vp, C.POINTER(Table)]
+    L.nyxb200_table_detach.argtypes = [vp, C.POINTER(Table)]
+    L.nyxb200_host_release.argtypes = [vp]
+    L.nyxb200_host_release.restype = None
+    L.nyxb200_validate_features.argtypes = [i32, C.POINTER(C.c_char_p), i32, C.c_char_p, C.c_size_t]
+    L.nyxb200_get_param.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double)]
+    L.nyxb200_device_count.argtypes = []
+    L.nyxb200_device_info.argtypes = [i32, C.c_char_p, C.c_size_t, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    L.nyxb200_shard_slides.argtypes = [i32, i32, C.POINTER(i64), C.POINTER(C.c_int32)]
+    L.nyxb200_featurize_2d_list_multi.argtypes = [C.POINTER(vp), i32, C.POINTER(vp), i32, C.POINTER(vp), i32, i32, i64, i64,
+                                                  C.POINTER(i64), C.POINTER(Table), C.POINTER(C.POINTER(C.c_int32))]
     L.nyxb200_last_timings.argtypes = [vp, C.POINTER(C.c_float), i32]
     L.nyxb200_last_counts.argtypes = [vp, C.POINTER(C.c_int64), i32]
     L.nyxb200_stage_name.restype = C.c_char_p
@@ -71,4 +81,6 @@ EXPORTS = ["nyxb200_default_settings", "nyxb200_create", "nyxb200_destroy", "nyx
            "nyxb200_featurize_2d_u16", "nyxb200_featurize_2d_device", "nyxb200_featurize_3d_u32", "nyxb200_featurize_3d_u16",
            "nyxb200_featurize_3d_device", "nyxb200_featurize_2d_list", "nyxb200_featurize_3d_list", "nyxb200_table_free", "nyxb200_last_timings",
            "nyxb200_last_counts", "nyxb200_stage_name", "nyxb200_debug_rois", "nyxb200_debug_cloud", "nyxb200_debug_matrix",
-           "nyxb200_family_id", "nyxb200_version"]
+           "nyxb200_family_id", "nyxb200_version", "nyxb200_table_detach", "nyxb200_host_release", "nyxb200_validate_features",
+           "nyxb200_get_param", "nyxb200_device_count", "nyxb200_device_info", "nyxb200_shard_slides",
+           "nyxb200_featurize_2d_list_multi"]

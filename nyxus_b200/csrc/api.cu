@@ -7,8 +7,10 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <condition_variable>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 #include "../../include/nyxus_b200.h"
@@ -161,9 +163,37 @@ void pool_release (void* p)
 
 } // namespace
 
+// One result table shared by several contexts (nyxb200_featurize_2d_list_multi): slide k claims its row range as soon as
+// its ROI count is known, in slide order, and its rows are copied device -> host straight to their final place.
+struct SharedOut
+{
+	std::mutex m;
+	std::condition_variable cv;
+	double* base = nullptr;
+	size_t cap_rows = 0, rowlen = 0;
+	int n_img = 0;
+	int next_slide = 0;		// the slide whose claim is due (claims are made in slide order: a deterministic table)
+	int64_t cursor = 0;		// rows claimed so far
+	std::vector<int64_t> row0, nrows;	// per slide
+	std::vector<char> deferred;		// slides that did not fit the first estimate (second pass)
+	bool failed = false;
+};
+
 struct nyxb200_ctx
 {
 	nyxb200_settings st;
+	SharedOut* share = nullptr;	// set while the context works for a multi-device call
+	// pageable host slides: worker threads copy chunks into pinned slots and send them on their own streams
+	// (the driver's own pageable path stages through one thread); 0 = leave it to cudaMemcpyAsync
+	int staging_threads = 4;
+	int multi_row_pad = 65536;	// slack rows of the shared table's first estimate (test knob: 0 forces the second pass)
+	static constexpr int STG_MAX = 16;
+	static constexpr size_t STG_CHUNK = (size_t)8 << 20;
+	uint8_t* stg_slot[STG_MAX * 2] {};
+	cudaStream_t stg_stream[STG_MAX] {};
+	cudaEvent_t stg_ev[STG_MAX * 2] {};
+	std::vector<std::thread> stg_workers;
+	int stg_rc = 0;
 	std::string err;
 	int sm_count = 148;
 	cudaStream_t stream = nullptr;
@@ -478,6 +508,18 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	ctx->g_recs.release();
 	ctx->d_rowoff.release(); ctx->d_dbg.release(); ctx->d_dbgf.release(); ctx->d_blkcells.release(); ctx->d_tiles.release();
 	pool_release (ctx->h_out);
+	for (auto& t : ctx->stg_workers)
+		if (t.joinable())
+			t.join();
+	for (auto& p : ctx->stg_slot)
+		if (p)
+			cudaFreeHost (p);
+	for (auto& st : ctx->stg_stream)
+		if (st)
+			cudaStreamDestroy (st);
+	for (auto& ev : ctx->stg_ev)
+		if (ev)
+			cudaEventDestroy (ev);
 	for (auto& ev : ctx->ev)
 		cudaEventDestroy (ev);
 	for (auto& ev : ctx->ev_end)
@@ -569,7 +611,7 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 		// binning of D3_GLCM_feature (3d_glcm.cpp:53-57); 0 = no binning, negative = PyRadiomics bin count.
 		if (!strcmp (key, "3glcm/greydepth") != (ctx->st.dim == 3))
 			return fail (ctx, NYXB200_EINVAL, "'%s' does not apply to a %dD context", key, ctx->st.dim);
-		if (iv > 65535 || iv < -65535)
+		if (ctx->st.dim == 3 && (iv > 65535 || iv < -65535))	// 2D: any integer (it only feeds the blank-ROI comparison)
 			return fail (ctx, NYXB200_EUNSUPPORTED, "grey depth must be in -65535..65535");
 		ctx->glcm_greydepth = iv;
 		ctx->glcm_greydepth_set = true;
@@ -590,6 +632,14 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 	}
 	else if (!strcmp (key, "tile_store"))			// test knob: 0 = family kernels bin straight from the slide
 		ctx->use_tile_store = iv != 0;
+	else if (!strcmp (key, "multi_row_pad"))
+		ctx->multi_row_pad = iv < 0 ? 0 : iv;
+	else if (!strcmp (key, "staging_threads"))		// pageable host slides: copy threads (0 = the driver's pageable path)
+	{
+		if (iv < 0 || iv > nyxb200_ctx::STG_MAX)
+			return fail (ctx, NYXB200_EINVAL, "staging_threads must be in 0..%d", nyxb200_ctx::STG_MAX);
+		ctx->staging_threads = iv;
+	}
 	else if (!strcmp (key, "3glszm/greydepth"))		// env_metaparams.cpp:222-233 (negative = PyRadiomics bin count)
 	{
 		if (iv < -65535 || iv > 65535)
@@ -1311,6 +1361,12 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 		ctx->open_stage = -1;
 		ctx->cur_b = 0;
 		ctx->err = msg;
+		if (SharedOut* sh = ctx->share)
+		{
+			std::lock_guard<std::mutex> lk (sh->m);
+			sh->failed = true;
+			sh->cv.notify_all();
+		}
 	}
 	return rc;
 }
@@ -1384,6 +1440,46 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	}
 	const uint32_t nroi = info.n_roi;
 	*nrows_out = nroi;
+	double* shared_dst = nullptr;
+	if (SharedOut* sh = ctx->share)
+	{
+		// claim rows [row0, row0 + nroi) of the shared table, in slide order
+		std::unique_lock<std::mutex> lk (sh->m);
+		sh->cv.wait (lk, [&] { return sh->failed || sh->next_slide == img_index; });
+		if (sh->failed)
+			return fail (ctx, NYXB200_ECUDA, "another device of the multi-device call failed");
+		if (!sh->base)
+		{
+			// capacity from the first slide's ROI count (slides of one job are alike); a slide that does not fit is
+			// deferred to a second pass with the exact size
+			sh->cap_rows = (size_t)nroi * sh->n_img + (size_t)nroi * sh->n_img / 4 + (size_t)ctx->multi_row_pad;
+			size_t got = 0;
+			sh->base = (double*)pool_acquire (sh->cap_rows * sh->rowlen * sizeof (double), &got);
+			if (!sh->base)
+			{
+				sh->failed = true;
+				sh->cv.notify_all();
+				return fail (ctx, NYXB200_ENOMEM, "cannot allocate the pinned result table of the multi-device call");
+			}
+			sh->cap_rows = got / (sh->rowlen * sizeof (double));
+		}
+		sh->row0[img_index] = sh->cursor;
+		sh->nrows[img_index] = nroi;
+		const bool fits = (size_t)(sh->cursor + nroi) <= sh->cap_rows;
+		sh->deferred[img_index] = fits ? 0 : 1;
+		if (fits)
+			shared_dst = sh->base + (size_t)sh->cursor * sh->rowlen;
+		sh->cursor += nroi;
+		sh->next_slide++;
+		lk.unlock();
+		sh->cv.notify_all();
+		if (!fits)
+		{
+			stage_begin (ctx, ST_TOTAL);
+			ctx->open_stage = -1;
+			return 0;
+		}
+	}
 	ctx->counts[1] += nroi;
 	ctx->counts[2] += (int64_t)info.n_fg;
 	ctx->counts[3] += (int64_t)npix;
@@ -1513,10 +1609,14 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	}
 	const size_t rowlen = (size_t)nsel + 2, outn = (size_t)nroi * rowlen;
 	CU (ctx->d_sel_out.reserve (outn));
-	if (int rc = reserve_pinned_out (ctx, ctx->h_out_used + outn))
-		return rc;
-	double* const h_dst = ctx->h_out + ctx->h_out_used;
-	ctx->h_out_used += outn;
+	double* h_dst = shared_dst;
+	if (!h_dst)
+	{
+		if (int rc = reserve_pinned_out (ctx, ctx->h_out_used + outn))
+			return rc;
+		h_dst = ctx->h_out + ctx->h_out_used;
+		ctx->h_out_used += outn;
+	}
 	auto select_and_copy = [&](uint32_t r0, uint32_t r1, bool overlap) -> int
 	{
 		// rows [r0, r1): gather the enabled columns on the main stream, copy them on the copy stream (overlap) or in line
@@ -1714,13 +1814,91 @@ void collect_timings (nyxb200_ctx* ctx)
 		ctx->stage_ms[ST_TOTAL] += ms;
 }
 
+bool host_pageable (const void* p)
+{
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes (&a, p) != cudaSuccess)
+	{
+		cudaGetLastError();
+		return true;
+	}
+	return a.type == cudaMemoryTypeUnregistered;
+}
+
+// pageable slide -> device: `staging_threads` workers, each with two pinned 8 MiB slots and its own stream; worker t takes
+// the chunks c == t (mod T) of both buffers.  Returns at once; staged_upload_wait joins the workers (data is then on
+// the device).
+int staged_upload_start (nyxb200_ctx* ctx, uint8_t* d_int, const uint8_t* h_int, size_t ibytes, uint8_t* d_lab, const uint8_t* h_lab, size_t lbytes)
+{
+	const int T = ctx->staging_threads;
+	for (int t = 0; t < T; t++)
+	{
+		if (!ctx->stg_stream[t])
+			CU (cudaStreamCreateWithFlags (&ctx->stg_stream[t], cudaStreamNonBlocking));
+		for (int q = 0; q < 2; q++)
+		{
+			if (!ctx->stg_slot[t * 2 + q])
+				CU (cudaHostAlloc ((void**)&ctx->stg_slot[t * 2 + q], nyxb200_ctx::STG_CHUNK, cudaHostAllocDefault));
+			if (!ctx->stg_ev[t * 2 + q])
+				CU (cudaEventCreateWithFlags (&ctx->stg_ev[t * 2 + q], cudaEventDisableTiming));
+		}
+	}
+	ctx->stg_rc = 0;
+	const size_t CH = nyxb200_ctx::STG_CHUNK;
+	const size_t nci = (ibytes + CH - 1) / CH, ncl = (lbytes + CH - 1) / CH;
+	const int dev = ctx->st.device;
+	for (int t = 0; t < T; t++)
+		ctx->stg_workers.emplace_back ([=]()
+		{
+			if (cudaSetDevice (dev) != cudaSuccess)
+			{
+				ctx->stg_rc = 1;
+				return;
+			}
+			int q = 0;
+			bool used[2] = { false, false };
+			for (size_t c = t; c < nci + ncl; c += T)
+			{
+				const bool isl = c >= nci;
+				const size_t off = (isl ? c - nci : c) * CH, tot = isl ? lbytes : ibytes, n = std::min (CH, tot - off);
+				const uint8_t* src = (isl ? h_lab : h_int) + off;
+				uint8_t* dst = (isl ? d_lab : d_int) + off;
+				uint8_t* slot = ctx->stg_slot[t * 2 + q];
+				if (used[q] && cudaEventSynchronize (ctx->stg_ev[t * 2 + q]) != cudaSuccess)
+					ctx->stg_rc = 1;
+				memcpy (slot, src, n);
+				if (cudaMemcpyAsync (dst, slot, n, cudaMemcpyHostToDevice, ctx->stg_stream[t]) != cudaSuccess
+					|| cudaEventRecord (ctx->stg_ev[t * 2 + q], ctx->stg_stream[t]) != cudaSuccess)
+					ctx->stg_rc = 1;
+				used[q] = true;
+				q ^= 1;
+			}
+			if (cudaStreamSynchronize (ctx->stg_stream[t]) != cudaSuccess)
+				ctx->stg_rc = 1;
+		});
+	return 0;
+}
+
+int staged_upload_wait (nyxb200_ctx* ctx)
+{
+	for (auto& t : ctx->stg_workers)
+		if (t.joinable())
+			t.join();
+	ctx->stg_workers.clear();
+	if (ctx->stg_rc)
+		return fail (ctx, NYXB200_ECUDA, "staged upload of a pageable host slide failed");
+	return 0;
+}
+
 // `inten[k]` / `label[k]`: slide k (host or device memory).  Host slides are uploaded on the upload stream into two
 // alternating device buffers, slide k+1 while slide k computes; the main stream's "h2d" stage is the part of the
 // upload it had to wait for.
 int featurize_slides (nyxb200_ctx* ctx, const void* const* inten, int inten_u16, const uint32_t* const* label, bool on_device,
-	int n_img, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image)
+	int n_img, int64_t D, int64_t H, int64_t W, nyxb200_table* out, const int32_t** row_image,
+	const int* order = nullptr, int n_order = 0)
 {
-	if (!ctx || !inten || !label || !out)
+	// `order` (multi-device calls): the slides of the list this context processes, ascending; else all of them
+	if (!ctx || !inten || !label || (!out && !ctx->share))
 		return fail (ctx, NYXB200_EINVAL, "null argument");
 	if (n_img <= 0 || H <= 0 || W <= 0 || D <= 0)
 		return fail (ctx, NYXB200_EINVAL, "bad image dimensions");
@@ -1728,13 +1906,18 @@ int featurize_slides (nyxb200_ctx* ctx, const void* const* inten, int inten_u16,
 		return fail (ctx, NYXB200_EUNSUPPORTED, "volume has more than 2^31-1 rows");
 	if (H > 0x7FFFFFFF || W > 0x7FFFFFFF)
 		return fail (ctx, NYXB200_EUNSUPPORTED, "image side exceeds 2^31-1");
-	for (int k = 0; k < n_img; k++)
-		if (!inten[k] || !label[k])
-			return fail (ctx, NYXB200_EINVAL, "null slide pointer (image %d)", k);
-	out->data = nullptr;
-	out->nrows = 0;
-	out->ncols = (int)ctx->sel_cols.size() + 2;
-	out->reserved = 0;
+	const int nmine = order ? n_order : n_img;
+	auto slide_of = [&](int j) { return order ? order[j] : j; };
+	for (int j = 0; j < nmine; j++)
+		if (!inten[slide_of (j)] || !label[slide_of (j)])
+			return fail (ctx, NYXB200_EINVAL, "null slide pointer (image %d)", slide_of (j));
+	if (out)
+	{
+		out->data = nullptr;
+		out->nrows = 0;
+		out->ncols = (int)ctx->sel_cols.size() + 2;
+		out->reserved = 0;
+	}
 	CU (cudaSetDevice (ctx->st.device));
 	for (auto& m : ctx->stage_ms) m = 0;
 	for (auto& v : ctx->counts) v = 0;
@@ -1743,25 +1926,30 @@ int featurize_slides (nyxb200_ctx* ctx, const void* const* inten, int inten_u16,
 	const size_t npix = (size_t)D * (size_t)H * (size_t)W;
 	const size_t ibytes = npix * (inten_u16 ? 2 : 4), lbytes = npix * 4;
 	ctx->h_out_used = 0;
-	const int nbuf = on_device ? 0 : (n_img > 1 ? 2 : 1);
+	const int nbuf = on_device ? 0 : (nmine > 1 ? 2 : 1);
 	for (int b = 0; b < nbuf; b++)
 	{
 		CU (ctx->d_inten[b].reserve (ibytes));
 		CU (ctx->d_label[b].reserve (npix));
 	}
-	auto upload = [&](int k) -> int
+	bool staged[2] = { false, false };
+	auto upload = [&](int j) -> int
 	{
-		const int b = k & 1;
+		const int b = j & 1, k = slide_of (j);
+		staged[b] = ctx->staging_threads > 0 && ibytes + lbytes >= ((size_t)32 << 20) && host_pageable (inten[k]) && host_pageable (label[k]);
+		if (staged[b])
+			return staged_upload_start (ctx, ctx->d_inten[b].p, (const uint8_t*)inten[k], ibytes, (uint8_t*)ctx->d_label[b].p, (const uint8_t*)label[k], lbytes);
 		CU (cudaMemcpyAsync (ctx->d_inten[b].p, inten[k], ibytes, cudaMemcpyHostToDevice, ctx->up_stream));
 		CU (cudaMemcpyAsync (ctx->d_label[b].p, label[k], lbytes, cudaMemcpyHostToDevice, ctx->up_stream));
 		CU (cudaEventRecord (ctx->ev_up[b], ctx->up_stream));
 		return 0;
 	};
-	if (!on_device)
+	if (!on_device && nmine > 0)
 		if (int rc = upload (0))
 			return rc;
-	for (int k = 0; k < n_img; k++)
+	for (int j = 0; j < nmine; j++)
 	{
+		const int k = slide_of (j);
 		for (auto& u : ctx->ev_used) u = false;
 		for (auto& u : ctx->ev_end_used) u = false;
 		ctx->open_stage = -1;
@@ -1778,31 +1966,66 @@ int featurize_slides (nyxb200_ctx* ctx, const void* const* inten, int inten_u16,
 		}
 		else
 		{
-			// buffer (k+1)&1 held slide k-1, which has been fully processed (process_slide ends synchronised)
-			if (k + 1 < n_img)
-				if (int rc = upload (k + 1))
+			// buffer (j+1)&1 held the slide before this one, which has been fully processed (process_slide ends synchronised)
+			if (staged[j & 1])
+			{
+				if (int rc = staged_upload_wait (ctx))	// slide j is on the device from here on
 					return rc;
-			CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_up[k & 1], 0));
-			im.inten = ctx->d_inten[k & 1].p;
-			im.label = ctx->d_label[k & 1].p;
+			}
+			else
+				CU (cudaStreamWaitEvent (ctx->stream, ctx->ev_up[j & 1], 0));
+			if (j + 1 < nmine)
+				if (int rc = upload (j + 1))
+					return rc;
+			im.inten = ctx->d_inten[j & 1].p;
+			im.label = ctx->d_label[j & 1].p;
 		}
 		int64_t nr = 0;
 		int rc = process_slide (ctx, im, k, &nr);
 		if (rc)
 		{
+			const std::string msg = ctx->err;
+			staged_upload_wait (ctx);
 			cudaStreamSynchronize (ctx->up_stream);	// nothing may still be reading the caller's buffers
+			ctx->err = msg;
 			return rc;
 		}
 		collect_timings (ctx);
-		for (int64_t i = 0; i < nr; i++)
-			ctx->row_image.push_back (k);
+		if (!ctx->share)
+			for (int64_t i = 0; i < nr; i++)
+				ctx->row_image.push_back (k);
 	}
-	out->nrows = (int64_t)ctx->row_image.size();
-	if (out->nrows)
-		out->data = ctx->h_out;
+	if (out)
+	{
+		out->nrows = (int64_t)ctx->row_image.size();
+		if (out->nrows)
+			out->data = ctx->h_out;
+	}
 	if (row_image)
 		*row_image = ctx->row_image.data();
 	return NYXB200_OK;
+}
+
+// Longest-processing-time-first assignment of slides to devices by weight (pixel count); every device's list ascending.
+// Equal weights give slide k to device k % n_dev.
+void shard_slides (int n_dev, int n_img, const int64_t* weight, std::vector<int>& owner)
+{
+	owner.assign (n_img, 0);
+	std::vector<int> idx (n_img);
+	for (int i = 0; i < n_img; i++)
+		idx[i] = i;
+	if (weight)
+		std::stable_sort (idx.begin(), idx.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+	std::vector<long long> load (n_dev, 0);
+	for (int i : idx)
+	{
+		int best = 0;
+		for (int d = 1; d < n_dev; d++)
+			if (load[d] < load[best])
+				best = d;
+		owner[i] = best;
+		load[best] += weight ? (long long)std::max<int64_t> (weight[i], 1) : 1;
+	}
 }
 
 // contiguous stack of n_img slides
@@ -1893,6 +2116,149 @@ int nyxb200_featurize_3d_list (nyxb200_ctx* ctx, const void* const* inten, int i
 	return featurize_slides (ctx, inten, inten_is_u16 ? 1 : 0, label, on_device != 0, n_vol, D, H, W, out, row_image);
 }
 
+int nyxb200_shard_slides (int n_dev, int n_img, const int64_t* weight, int32_t* owner)
+{
+	if (n_dev <= 0 || n_img < 0 || (!owner && n_img))
+		return NYXB200_EINVAL;
+	std::vector<int> o;
+	shard_slides (n_dev, n_img, weight, o);
+	for (int i = 0; i < n_img; i++)
+		owner[i] = o[i];
+	return NYXB200_OK;
+}
+
+int nyxb200_featurize_2d_list_multi (nyxb200_ctx* const* ctxs, int n_ctx, const void* const* inten, int inten_is_u16,
+	const uint32_t* const* label, int on_device, int n_img, int64_t H, int64_t W, const int64_t* weight,
+	nyxb200_table* out, const int32_t** row_image)
+{
+	if (!ctxs || n_ctx <= 0 || !ctxs[0])
+		return NYXB200_EINVAL;
+	nyxb200_ctx* c0 = ctxs[0];
+	if (!inten || !label || !out)
+		return fail (c0, NYXB200_EINVAL, "null argument");
+	if (n_img <= 0 || H <= 0 || W <= 0)
+		return fail (c0, NYXB200_EINVAL, "bad image dimensions");
+	for (int d = 0; d < n_ctx; d++)
+	{
+		if (!ctxs[d] || ctxs[d]->st.dim != 2)
+			return fail (c0, NYXB200_EINVAL, "context %d is null or not a 2D context", d);
+		if (ctxs[d]->sel_cols != c0->sel_cols)
+			return fail (c0, NYXB200_EINVAL, "context %d selects other features than context 0", d);
+		for (int e = 0; e < d; e++)
+			if (ctxs[e] == ctxs[d])
+				return fail (c0, NYXB200_EINVAL, "context %d is given twice", d);
+	}
+	out->data = nullptr;
+	out->nrows = 0;
+	out->ncols = (int)c0->sel_cols.size() + 2;
+	out->reserved = 0;
+	std::vector<int> owner;
+	shard_slides (n_ctx, n_img, weight, owner);
+	std::vector<std::vector<int>> mine (n_ctx);
+	for (int k = 0; k < n_img; k++)
+		mine[owner[k]].push_back (k);
+	// the previous result of context 0 goes back to the pool (the shared table takes its place)
+	pool_release (c0->h_out);
+	c0->h_out = nullptr;
+	c0->h_out_cap = c0->h_out_used = 0;
+	SharedOut sh;
+	sh.rowlen = (size_t)out->ncols;
+	sh.n_img = n_img;
+	sh.row0.assign (n_img, 0);
+	sh.nrows.assign (n_img, 0);
+	sh.deferred.assign (n_img, 0);
+	std::vector<int> rcs (n_ctx, 0);
+	auto work = [&](int d)
+	{
+		nyxb200_ctx* c = ctxs[d];
+		c->share = &sh;
+		rcs[d] = mine[d].empty() ? 0 : featurize_slides (c, inten, inten_is_u16 ? 1 : 0, label, on_device != 0, n_img, 1, H, W, nullptr, nullptr,
+			mine[d].data(), (int)mine[d].size());
+		c->share = nullptr;
+		if (rcs[d])
+		{
+			std::lock_guard<std::mutex> lk (sh.m);
+			sh.failed = true;
+			sh.cv.notify_all();
+		}
+	};
+	{
+		// one host thread per device (context 0 on the calling thread)
+		std::vector<std::thread> th;
+		for (int d = 1; d < n_ctx; d++)
+			th.emplace_back (work, d);
+		work (0);
+		for (auto& t : th)
+			t.join();
+	}
+	for (int d = 0; d < n_ctx; d++)
+		if (rcs[d])
+		{
+			if (d)
+				c0->err = "device " + std::to_string (ctxs[d]->st.device) + ": " + ctxs[d]->err;
+			pool_release (sh.base);
+			return rcs[d];
+		}
+	cudaSetDevice (c0->st.device);
+	// slides that did not fit the estimate: grow to the exact size, then a second pass on context 0 (their row ranges are known)
+	const size_t total = (size_t)sh.cursor;
+	bool any_deferred = false;
+	for (int k = 0; k < n_img; k++)
+		any_deferred = any_deferred || sh.deferred[k];
+	if (any_deferred)
+	{
+		size_t got = 0;
+		double* nb = (double*)pool_acquire ((total + 1) * sh.rowlen * sizeof (double), &got);
+		if (!nb)
+		{
+			pool_release (sh.base);
+			return fail (c0, NYXB200_ENOMEM, "cannot grow the pinned result table");
+		}
+		for (int k = 0; k < n_img; k++)
+			if (!sh.deferred[k])
+				memcpy (nb + (size_t)sh.row0[k] * sh.rowlen, sh.base + (size_t)sh.row0[k] * sh.rowlen, (size_t)sh.nrows[k] * sh.rowlen * sizeof (double));
+		pool_release (sh.base);
+		sh.base = nb;
+		sh.cap_rows = got / (sh.rowlen * sizeof (double));
+		for (int k = 0; k < n_img; k++)
+		{
+			if (!sh.deferred[k])
+				continue;
+			// replay the claim for exactly this slide
+			const int64_t r0 = sh.row0[k];
+			SharedOut one;
+			one.rowlen = sh.rowlen;
+			one.n_img = 1;
+			one.base = sh.base + (size_t)r0 * sh.rowlen;
+			one.cap_rows = (size_t)sh.nrows[k];
+			one.row0.assign (n_img, 0);
+			one.nrows.assign (n_img, 0);
+			one.deferred.assign (n_img, 0);
+			one.next_slide = k;
+			c0->share = &one;
+			const int rc = featurize_slides (c0, inten, inten_is_u16 ? 1 : 0, label, on_device != 0, n_img, 1, H, W, nullptr, nullptr, &k, 1);
+			c0->share = nullptr;
+			if (rc || one.deferred[k])
+			{
+				pool_release (sh.base);
+				return rc ? rc : fail (c0, NYXB200_ECUDA, "second pass of slide %d saw another ROI count", k);
+			}
+		}
+	}
+	c0->row_image.resize (total);
+	for (int k = 0; k < n_img; k++)
+		std::fill (c0->row_image.begin() + sh.row0[k], c0->row_image.begin() + sh.row0[k] + sh.nrows[k], k);
+	// the table becomes context 0's current result (nyxb200_table_detach / the next call handle it like any other)
+	c0->h_out = sh.base;
+	c0->h_out_cap = sh.cap_rows * sh.rowlen;
+	c0->h_out_used = total * sh.rowlen;
+	out->nrows = (int64_t)total;
+	out->data = total ? sh.base : nullptr;
+	if (row_image)
+		*row_image = c0->row_image.data();
+	return NYXB200_OK;
+}
+
 void nyxb200_table_free (nyxb200_ctx* ctx, nyxb200_table* t)
 {
 	(void)ctx;	// the rows live in the context's grow-only pinned buffer, reused by the next featurize call
@@ -1937,6 +2303,7 @@ int nyxb200_get_param (const nyxb200_ctx* ctx, const char* key, double* value)
 	else if (!strcmp (key, "concurrent_families")) *value = ctx->concurrent;
 	else if (!strcmp (key, "roi_batches")) *value = ctx->roi_batches;
 	else if (!strcmp (key, "tile_store")) *value = ctx->use_tile_store;
+	else if (!strcmp (key, "staging_threads")) *value = ctx->staging_threads;
 	else if (!strcmp (key, "3glszm/greydepth")) *value = ctx->glszm3_greydepth;
 	else if (!strcmp (key, "3ngtdm/greydepth")) *value = ctx->ngtdm3_greydepth;
 	else if (!strcmp (key, "3ngtdm/radius")) *value = ctx->ngtdm3_radius;

@@ -1,5 +1,7 @@
 """Thin object wrapper over the C ABI: one Engine == one nyxb200_ctx (one CUDA device)."""
 import ctypes as C
+import weakref
+
 import numpy as np
 from . import _lib
 
@@ -71,13 +73,22 @@ class Engine:
         return [self._L.nyxb200_column_code(self._ctx, i) for i in range(n)]
 
     def _collect(self, tab, rimg, copy=True):
+        """copy=True: private copies; copy=False: views of the library's pinned buffer (valid until the next call on this
+        context); copy="detach": the pinned table changes owner (nyxb200_table_detach) -- the returned array keeps it
+        alive and hands it back to the library's pool when it is garbage-collected, like the reference's zero-copy
+        capsule (new_bindings_py.cpp:63-73)"""
         n, nc = tab.nrows, tab.ncols
         if n:
-            # the table lives in the context's pinned host buffer (include/nyxus_b200.h: valid until the next featurize
-            # call on this context); copy=False hands out a view of it, like the reference's zero-copy capsule
-            # (new_bindings_py.cpp:63-73)
-            data = np.ctypeslib.as_array(tab.data, shape=(n, nc))
             img = np.ctypeslib.as_array(rimg, shape=(n,))
+            if copy == "detach":
+                img = img.copy()
+                self._check(self._L.nyxb200_table_detach(self._ctx, C.byref(tab)))
+                addr = C.cast(tab.data, C.c_void_p).value
+                buf = (C.c_double * (n * nc)).from_address(addr)
+                weakref.finalize(buf, self._L.nyxb200_host_release, addr)
+                data = np.frombuffer(buf, dtype=np.float64).reshape(n, nc)
+                return data, img
+            data = np.ctypeslib.as_array(tab.data, shape=(n, nc))
             if copy:
                 data, img = data.copy(), img.copy()
         else:
@@ -86,7 +97,7 @@ class Engine:
         self._L.nyxb200_table_free(self._ctx, C.byref(tab))
         return data, img
 
-    def featurize(self, inten, label):
+    def featurize(self, inten, label, copy=True):
         """inten: uint16 or uint32 [N,H,W] (or [H,W]); label: uint32 same shape.  Returns (table[nrows, 2+F], image index per row)."""
         inten = np.asarray(inten)
         label = np.asarray(label)
@@ -103,7 +114,7 @@ class Engine:
         rimg = C.POINTER(C.c_int32)()
         fn = self._L.nyxb200_featurize_2d_u16 if inten.dtype == np.uint16 else self._L.nyxb200_featurize_2d_u32
         self._check(fn(self._ctx, inten.ctypes.data, label.ctypes.data, N, H, W, C.byref(tab), C.byref(rimg)))
-        return self._collect(tab, rimg)
+        return self._collect(tab, rimg, copy)
 
     def featurize_volume(self, inten, label):
         """3D (dim=3 engines).  inten: uint16 or uint32 [D,H,W] or [N,D,H,W]; label: uint32 same shape.
@@ -159,6 +170,12 @@ class Engine:
         self._check(rc)
         return self._collect(tab, rimg, copy)
 
+    def get_param(self, key):
+        v = C.c_double()
+        if self._L.nyxb200_get_param(self._ctx, key.encode(), C.byref(v)) != 0:
+            raise ValueError("unknown parameter '%s'" % key)
+        return v.value
+
     def timings(self):
         ms = (C.c_float * _lib.NSTAGES)()
         self._L.nyxb200_last_timings(self._ctx, ms, _lib.NSTAGES)
@@ -195,3 +212,36 @@ class Engine:
         self._check(self._L.nyxb200_debug_matrix(self._ctx, int(label), fid, trip.ctypes.data, n.value, C.byref(n), sv.ctypes.data))
         t = [tuple(int(x) for x in row) for row in trip[:n.value]]
         return t, sv[:n.value].tolist()
+
+
+def shard_slides(n_dev, n_img, weight=None):
+    """device that nyxb200_featurize_2d_list_multi gives every slide (LPT on `weight`; equal weights: k % n_dev)"""
+    L = _lib.lib()
+    owner = (C.c_int32 * max(n_img, 1))()
+    w = None
+    if weight is not None:
+        w = (C.c_int64 * n_img)(*[int(x) for x in weight])
+    if L.nyxb200_shard_slides(int(n_dev), int(n_img), w, owner) != 0:
+        raise ValueError("bad shard arguments")
+    return [int(owner[i]) for i in range(n_img)]
+
+
+def featurize_list_multi(engines, inten_ptrs, inten_is_u16, label_ptrs, H, W, on_device=False, weight=None, copy=True):
+    """One job over several devices (one Engine each, same features): the slides are sharded by `weight` (pixel count),
+    the rows of all slides land in ONE host table in slide order.  Returns (table, slide index per row)."""
+    n = len(inten_ptrs)
+    if n != len(label_ptrs) or n == 0 or not engines:
+        raise ValueError("Intensity and label lists must have the same, non-zero length")
+    L = engines[0]._L
+    cs = (C.c_void_p * len(engines))(*[e._ctx.value for e in engines])
+    ip = (C.c_void_p * n)(*[int(p) for p in inten_ptrs])
+    lp = (C.c_void_p * n)(*[int(p) for p in label_ptrs])
+    w = None
+    if weight is not None:
+        w = (C.c_int64 * n)(*[int(x) for x in weight])
+    tab = _lib.Table()
+    rimg = C.POINTER(C.c_int32)()
+    rc = L.nyxb200_featurize_2d_list_multi(cs, len(engines), ip, int(inten_is_u16), lp, int(on_device), n, H, W, w,
+                                           C.byref(tab), C.byref(rimg))
+    engines[0]._check(rc)
+    return engines[0]._collect(tab, rimg, copy)

@@ -106,11 +106,13 @@ class Nyxus:
         if intensity_images.ndim == 2:
             if label_images.ndim != 2:
                 raise ValueError("Both intensity and label arrays must be the same dimension")
-            intensity_images = np.array([intensity_images])
-            label_images = np.array([label_images])
+            single = True
+            intensity_images = intensity_images[None]      # a view: the reference's np.array([...]) copies the slide (nyxus.py:447-448)
+            label_images = label_images[None]
         elif intensity_images.ndim == 3:
             if label_images.ndim != 3:
                 raise ValueError("Both intensity and label arrays must be the same dimension")
+            single = False
         else:
             raise ValueError("Intensity and label arrays must be 2D or 3D")
         if intensity_images.shape != label_images.shape:
@@ -124,28 +126,29 @@ class Nyxus:
         if label_images.shape[0] != len(label_names):
             raise ValueError("Number of segmentation names must be the same as the number of images.")
 
-        # Hounsfield-type scale: shift into the unsigned range IN PLACE like the reference (nyxus.py:481-484)
+        # Hounsfield-type scale: shift into the unsigned range like the reference (nyxus.py:481-484: IN PLACE on a stack the
+        # caller passed, on its own copy for a single 2D slide).  Unsigned types cannot be negative: no pass over them.
         I = intensity_images
-        min_raw_I = np.min(intensity_images)
-        if min_raw_I < 0:
-            I -= min_raw_I
+        if not np.issubdtype(I.dtype, np.unsignedinteger):
+            min_raw_I = np.min(I)
+            if min_raw_I < 0:
+                if single:
+                    I = I - min_raw_I
+                else:
+                    I -= min_raw_I
         if I.dtype != np.uint16 and I.dtype != np.uint32:     # uint16 goes to the device as is (no widening copy)
             I = I.astype(np.uint32)
-        M = label_images.astype(np.uint32)
+        M = label_images.astype(np.uint32, copy=False)        # no copy when the mask already is uint32
         if self._mergerois:                                   # phase1.cpp:392-393, phase2_2d.cpp:665-666
             M = (M != 0).astype(np.uint32)
 
-        numeric, row_img = self._engine.featurize(I, M)
+        # the numeric table is the library's pinned buffer, handed over without a copy (released when the frame dies)
+        numeric, row_img = self._engine.featurize(I, M, copy="detach")
         self.error_message = ''
         header = ["intensity_image", "mask_image", "ROI_label", "t_index"] + self._engine.columns
-        string_data = np.array([[intensity_names[k], label_names[k]] for k in row_img], dtype=object).reshape(-1, 2)
-        df = pd.concat(
-            [
-                pd.DataFrame(string_data, columns=header[:2]),
-                pd.DataFrame(numeric, columns=header[2:]),
-            ],
-            axis=1,
-        )
+        df = pd.DataFrame(numeric, columns=header[2:], copy=False)
+        df.insert(0, "mask_image", np.asarray(label_names, dtype=object)[row_img])
+        df.insert(0, "intensity_image", np.asarray(intensity_names, dtype=object)[row_img])
         if "ROI_label" in df.columns:
             df.ROI_label = df.ROI_label.astype(np.uint32)
         return df

@@ -130,3 +130,41 @@ def ellipsoid_volume(D, H, W, pitch, amin, amax, seed, dtype=np.uint16, zero_fra
 def config4(seed=4, size=512):
     """C4: size^3 uint16 volume, ellipsoid ROIs (semi-axes 6..14) on a pitch-39 lattice: 13^3 = 2197 ROIs at 512^3"""
     return ellipsoid_volume(size, size, size, 39, 6, 14, seed)
+
+
+def config2_device(seed, device, size=10000, pitch=31, rmin=7, rmax=12):
+    """configs[4] needs 64 distinct configs[1]-shaped slides; blob_slide (numpy PCG64) takes ~25 s per slide on the host, so
+    the 64-slide job generates them ON THE DEVICE: same geometry model (pitch-31 grid of 5-lobe blobs, radius U{7..12},
+    label = 1 + row-major grid index) and intensity model (2000 + 1500 * smoothed noise + 800 * N(0,1), clipped to
+    [1, 65535], 1 % of the in-ROI pixels forced to 0), torch's Philox generator seeded with `seed` instead of PCG64.
+    Returns (uint16 [size, size], int32 [size, size]) torch tensors on `device` (the int32 bits are the uint32 labels)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed(int(seed))
+    H = W = int(size)
+    ny, nx = H // pitch, W // pitch
+    r = torch.randint(rmin, rmax + 1, (ny, nx), generator=g, device=dev).float()
+    ph = torch.rand((ny, nx), generator=g, device=dev) * (2 * 3.141592653589793)
+    ys = torch.arange(H, device=dev)
+    xs = torch.arange(W, device=dev)
+    cj = torch.clamp(ys // pitch, max=ny - 1)
+    ci = torch.clamp(xs // pitch, max=nx - 1)
+    Y = (ys % pitch - pitch // 2).float()[:, None]
+    X = (xs % pitch - pitch // 2).float()[None, :]
+    inside = ((ys < ny * pitch)[:, None]) & ((xs < nx * pitch)[None, :])
+    rr = r[cj][:, ci] + 3.0 * torch.sin(5.0 * torch.atan2(Y, X).expand(H, W) + ph[cj][:, ci])
+    ids = (1 + cj[:, None] * nx + ci[None, :]).int()
+    label = torch.where((torch.hypot(Y, X).expand(H, W) <= rr) & inside, ids, torch.zeros((), dtype=torch.int32, device=dev))
+    del rr, ids, inside
+    a = torch.randn((1, 1, H, W), generator=g, device=dev)
+    for _ in range(3):
+        a = torch.nn.functional.avg_pool2d(a, 13, stride=1, padding=6, count_include_pad=True)
+    a = a[0, 0]
+    a = a / (a.std() + 1e-12)
+    inten = 2000.0 + 1500.0 * a + 800.0 * torch.randn((H, W), generator=g, device=dev)
+    del a
+    inten = inten.clamp_(1, 65535)
+    z = (torch.rand((H, W), generator=g, device=dev) < 0.01) & (label != 0)
+    inten[z] = 0
+    return inten.to(torch.uint16), label

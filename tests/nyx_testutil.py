@@ -37,10 +37,35 @@ def finite0(a):
 
 
 def mismatches(ref, got, cols=None, rtol=RTOL, atol=ATOL):
-    """list of (index / column, ref, got) entries outside |a-b| <= atol + rtol*max(|a|,|b|)"""
+    """list of (index / column, ref, got) entries outside |a-b| <= atol + rtol*max(|a|,|b|).
+
+    One documented exception: GLCM_CLUSHADE* = sum (i+j-mx-my)^3 p is a signed sum that cancels to (near) zero on symmetric
+    matrices -- the reference then returns round-off residue of its own summation order (seen: 3e-11 where the exact
+    value is 0).  Its terms are bounded by CLUPROM^(3/4) (power-mean inequality), so for those columns the relative
+    tolerance is taken against max(|a|, |b|, CLUPROM^(3/4)) of the same angle: 1e-9 of the magnitude being summed.
+    Likewise GLCM_INFOMEAS2* = sqrt(1 - exp(-2 x)), x = HXY2 - HXY (glcm.cpp:888-913): x is the difference of two
+    entropies of magnitude H, each a float32-log sum good to 1e-9 relative at best, and df = dx * exp(-2x) / f, so a 1e-9
+    relative agreement of the entropies allows |df| <= 1e-9 * 2H / f (ill-conditioned when the matrix is nearly
+    independent, f -> 0); the tolerance scale of those columns is max(|a|, |b|, min(2 H / f, 1e4))."""
     a, b = finite0(ref), finite0(got)
     diff = np.abs(a - b)
-    bad = diff > atol + rtol * np.maximum(np.abs(a), np.abs(b))
+    scale = np.maximum(np.abs(a), np.abs(b))
+    if cols is not None and a.ndim >= 1 and a.shape[-1] == len(cols):
+        names = list(cols)
+        for j, c in enumerate(names):
+            if c.startswith("GLCM_CLUSHADE"):
+                prom = c.replace("CLUSHADE", "CLUPROM")
+                if prom in names:
+                    k = names.index(prom)
+                    scale[..., j] = np.maximum(scale[..., j], np.maximum(np.abs(a[..., k]), np.abs(b[..., k])) ** 0.75)
+            if c.startswith("GLCM_INFOMEAS2"):
+                ent = c.replace("INFOMEAS2", "ENTROPY")
+                if ent in names:
+                    k = names.index(ent)
+                    H = np.maximum(np.abs(a[..., k]), np.abs(b[..., k]))
+                    f = np.maximum(np.maximum(np.abs(a[..., j]), np.abs(b[..., j])), 1e-30)
+                    scale[..., j] = np.maximum(scale[..., j], np.minimum(2.0 * H / f, 1e4))
+    bad = diff > atol + rtol * scale
     out = []
     for idx in zip(*np.nonzero(bad)):
         name = cols[idx[-1]] if cols is not None else idx

@@ -475,3 +475,49 @@ def test_giant_whole_slide_properties():
         assert t1[0, c["GLSZM_SAE"]] == 0.0     # >= 65536 cells: the reference's int j*j wrap turns SAE into NaN -> noval
     finally:
         e.close()
+
+
+# ------------------------------------------------------------------------------------------------ several devices, one call
+def _multi_slides(counts, seed=31):
+    from nyxus_b200 import synth
+    out = []
+    for k, n in enumerate(counts):
+        I, L = synth.blob_slide(160, 192, 32, 7, 12, seed=seed + k, jitter=1)
+        L = np.where(L <= n, L, 0).astype(np.uint32)        # slide k keeps its first n ROIs
+        out.append((np.ascontiguousarray(I), L))
+    return out
+
+
+@pytest.mark.parametrize("nctx,pad", [(1, 65536), (3, 65536), (2, 0)])
+def test_multi_device_list_call_gives_the_single_device_table(nctx, pad):
+    """nyxb200_featurize_2d_list_multi: slides sharded over several contexts (here on ONE device: each context has its own
+    host thread, streams and buffers, which is all the call relies on), rows claimed in slide order into one table.  pad = 0
+    makes the first estimate too small for the later slides, which exercises the second pass."""
+    import torch
+    from nyxus_b200 import Engine
+    from nyxus_b200.engine import featurize_list_multi
+    slides = _multi_slides([3, 30, 12, 0, 25, 7, 30])
+    single = _engine()
+    engines = [_engine() for _ in range(nctx)]
+    try:
+        want = [single.featurize(I, L) for I, L in slides]
+        want_tab = np.concatenate([w[0] for w in want])
+        want_idx = np.concatenate([np.full(len(w[0]), k, np.int32) for k, w in enumerate(want)])
+        engines[0].set_param("multi_row_pad", pad)
+        for e in engines[1:]:
+            e.set_param("multi_row_pad", pad)
+        for on_device in (False, True):
+            if on_device:
+                keep = [(torch.from_numpy(I).cuda(), torch.from_numpy(L.view(np.int32)).cuda()) for I, L in slides]
+                ips, lps = [t[0].data_ptr() for t in keep], [t[1].data_ptr() for t in keep]
+            else:
+                ips, lps = [I.ctypes.data for I, _ in slides], [L.ctypes.data for _, L in slides]
+            for rep in range(2):        # the second call reuses the pooled table
+                tab, idx = featurize_list_multi(engines, ips, True, lps, 160, 192, on_device=on_device,
+                                                weight=[int(np.count_nonzero(L)) + 1 for _, L in slides] if rep else None)
+                assert np.array_equal(idx, want_idx)
+                assert np.array_equal(tab, want_tab)
+    finally:
+        single.close()
+        for e in engines:
+            e.close()

@@ -131,3 +131,37 @@ def test_sharded_featurize_world_size_2_gloo(tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29517", str(script)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "SHARD_OK" in r.stdout, r.stdout + r.stderr
+
+
+def test_cabi_shard_slides_is_lpt_and_ascending():
+    """nyxb200_shard_slides (the device-free half of nyxb200_featurize_2d_list_multi): equal weights -> slide k on device k % n;
+    weights -> longest-processing-time-first within Graham's bound; deterministic"""
+    from nyxus_b200.engine import shard_slides
+    assert shard_slides(4, 10) == [k % 4 for k in range(10)]
+    assert shard_slides(1, 5) == [0] * 5
+    w = [100, 90, 80, 10, 10, 10, 5, 5, 70, 1]
+    own = shard_slides(3, len(w), w)
+    assert own == shard_slides(3, len(w), w) and set(own) == {0, 1, 2}
+    loads = [sum(w[i] for i in range(len(w)) if own[i] == d) for d in range(3)]
+    assert max(loads) <= (4.0 / 3.0) * (sum(w) / 3.0) + max(w) / 3.0
+    with pytest.raises(ValueError):
+        shard_slides(0, 3)
+
+
+def test_cabi_device_free_validation_and_device_count():
+    L, _ = _lib()
+    msg = C.create_string_buffer(512)
+
+    def val(dim, names):
+        arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
+        return L.nyxb200_validate_features(dim, arr, len(names), msg, 512), msg.value.decode()
+    assert val(2, ["*ALL_TEXTURE*", "*ALL_INTENSITY*", "GLCM_ASM", "MEAN"])[0] == 0
+    rc, m = val(2, ["GLCM_NOPE"])
+    assert rc == -1 and "not a valid 2D feature name" in m
+    rc, m = val(3, ["*3D_ALL_TEXTURE*"])
+    assert rc == -3 and "outside this path" in m
+    assert val(3, ["*3D_GLCM*", "3MEAN"])[0] == 0
+    assert val(4, ["MEAN"])[0] == -1
+    import torch
+    if not torch.cuda.is_available():
+        assert L.nyxb200_device_count() == 0
