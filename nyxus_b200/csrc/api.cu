@@ -44,6 +44,7 @@ const GroupDef g_groups2d[] = {
 	{ "*ALL_GLDM*", 1 << FAM_GLDM },
 	{ "*ALL_NGLDM*", 1 << FAM_NGLDM },
 	{ "*ALL_NGTDM*", 1 << FAM_NGTDM },
+	{ "*BASIC_MORPHOLOGY*", 1 << FAM_MORPH },		// featureset.cpp:654
 	{ "*ALL_TEXTURE*", (1 << FAM_GLCM) | (1 << FAM_GLRLM) | (1 << FAM_GLDZM) | (1 << FAM_GLSZM) | (1 << FAM_GLDM) | (1 << FAM_NGLDM) | (1 << FAM_NGTDM) },
 };
 // reference featureset.cpp:940-953 (3D group names) for the 3D families on this path
@@ -223,7 +224,8 @@ struct nyxb200_ctx
 	// selection
 	std::vector<FeatureDef> feats;	// the context's feature table (2D or 3D codes)
 	bool feat_on[NFEATURES_MAX];
-	int fam_mask = 0;
+	int fam_mask = 0;		// first-order + texture families (bits of Family)
+	bool want_morph = false;	// *BASIC_MORPHOLOGY* columns selected
 	std::vector<int> sel_cols;		// canonical column of every output column
 	std::vector<std::string> sel_names;
 	std::vector<int> sel_codes;
@@ -301,6 +303,7 @@ void rebuild_selection (nyxb200_ctx* ctx)
 	ctx->sel_names.clear();
 	ctx->sel_codes.clear();
 	ctx->fam_mask = 0;
+	ctx->want_morph = false;
 	static const int angles[4] = { 0, 45, 90, 135 };
 	// enabled features in ascending code order (reference featureset.cpp getEnabledFeatures; the table is already sorted)
 	for (int i = 0; i < (int)ctx->feats.size(); i++)
@@ -308,7 +311,10 @@ void rebuild_selection (nyxb200_ctx* ctx)
 		if (!ctx->feat_on[i])
 			continue;
 		const FeatureDef& f = ctx->feats[i];
-		ctx->fam_mask |= 1 << f.family;
+		if (f.family == FAM_MORPH)
+			ctx->want_morph = true;
+		else
+			ctx->fam_mask |= 1 << f.family;
 		for (int k = 0; k < f.ncols; k++)
 		{
 			ctx->sel_cols.push_back (f.col0 + k);
@@ -656,8 +662,8 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 	{
 		if (iv < 0)
 			return fail (ctx, NYXB200_EINVAL, "3ngtdm/radius: expecting a positive integer");
-		if (iv > 1)
-			return fail (ctx, NYXB200_EUNSUPPORTED, "3ngtdm/radius > 1 is not built (26-neighbourhood only)");
+		if (iv > NGTDM3_RMAX)
+			return fail (ctx, NYXB200_EUNSUPPORTED, "3ngtdm/radius > %d is not supported", NGTDM3_RMAX);
 		ctx->ngtdm3_radius = iv;
 	}
 	else
@@ -811,7 +817,7 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 	size_t famw = 0;
 	if (FAM3 == FAM3_GLCM) famw = P16 ? glcm_smem_words<true> (Lmax, 4, greyinfo < 0) : glcm_smem_words<false> (Lmax, 4, greyinfo < 0);
 	if (FAM3 == FAM3_GLSZM) famw = glszm3d_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));
-	if (FAM3 == FAM3_NGTDM) famw = ngtdm3d_smem_words (Lmax);
+	if (FAM3 == FAM3_NGTDM) famw = ngtdm3d_smem_words (Lmax, prm.ngtdm3_radius);
 	famw = (famw + 1) & ~(size_t)1;
 	size_t smem_words = RED_WORDS + tilew + famw;
 	uint32_t* gs = nullptr;
@@ -829,6 +835,44 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 		return NYXB200_ECUDA;
 	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,
 		NCOL3_ALL, gs, famw);
+	CU (cudaGetLastError());
+	ctx->counts[0]++;
+	return 0;
+}
+
+// 3D cubes beyond the shared-memory classes: cube + work arrays in per-CTA slots of global memory (k_roi_family3_big)
+template <int FAM3>
+int launch_family3_big (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list, uint32_t n, const Params& prm, int greyinfo,
+	int Lmax, unsigned long long maxcells, double* out)
+{
+	if (!n)
+		return 0;
+	if (maxcells > 0x40000000ull)
+		return fail (ctx, NYXB200_EUNSUPPORTED, "a 3D ROI whose bounding cube exceeds 2^30 voxels is not supported");
+	const size_t tilew = ((size_t)maxcells + 7) & ~(size_t)7;
+	uint32_t slots = 0;
+	size_t famw = 0;
+	if (FAM3 == FAM3_GLCM) famw = glcm_smem_words<false> (Lmax, 4, greyinfo < 0);
+	if (FAM3 == FAM3_GLSZM)
+	{
+		slots = glszm3d_big_slots (Lmax, maxcells);
+		famw = glszm3d_big_words (maxcells, slots);
+	}
+	if (FAM3 == FAM3_NGTDM) famw = ngtdm3d_smem_words (Lmax, prm.ngtdm3_radius);
+	famw = (famw + 3) & ~(size_t)3;
+	const size_t slotw = tilew + famw;
+	size_t freeb = 0, totalb = 0;
+	CU (cudaMemGetInfo (&freeb, &totalb));
+	const size_t budget = std::min<size_t> ((size_t)4 << 30, freeb / 2 + ctx->d_scratch[ctx->lsi].cap * 4);
+	if (slotw * 4 > budget)
+		return fail (ctx, NYXB200_ENOMEM, "a 3D ROI of %llu voxels needs %zu MB of work space", maxcells, slotw * 4 >> 20);
+	const int grid = (int)std::max<size_t> (1, std::min<size_t> (std::min<size_t> (n, (size_t)ctx->sm_count), budget / (slotw * 4)));
+	CU (ctx->d_scratch[ctx->lsi].reserve ((size_t)grid * slotw));
+	uint32_t* gs = ctx->d_scratch[ctx->lsi].p;
+	CU (cudaMemsetAsync (gs, 0, (size_t)grid * slotw * 4, ctx->ls));
+	auto kern = k_roi_family3_big<FAM3>;
+	kern<<<grid, ROI_THREADS, RED_WORDS * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out, NCOL3_ALL,
+		gs, slotw, tilew, slots);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
 	return 0;
@@ -1593,10 +1637,6 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 		imf.tileB = tiles_b ? ctx->d_tiles.p + info.n_tile_cells : nullptr;
 	}
 	ctx->last_im = imf;
-	if (d3 && (ctx->fam_mask & ~(1 << FAM3_INT)))
-		for (int bb = 0; bb < nb; bb++)
-			if (info.class_count[bb * (NCLASS + 1) + NCLASS])
-				return fail (ctx, NYXB200_EUNSUPPORTED, "a 3D ROI whose bounding cube exceeds 40000 voxels needs the large-ROI texture path (not in this build)");
 
 	// ---- output buffers
 	const int nsel = (int)ctx->sel_cols.size();
@@ -1700,6 +1740,27 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 				if (int rc = launch_intensity (ctx, ctx->d_alist.p + ab[NACLASS], acount[NACLASS], prm, amaxarea[NACLASS], ctx->d_full.p, ncol_all))
 					return rc;
 		}
+		if (ctx->want_morph && !d3)
+		{
+			// basic morphology rides on the first-order stream: warp per ROI for the shared-memory size classes of this batch
+			// (their lists are contiguous), CTA per ROI for the oversize class
+			uint32_t nsmall = 0;
+			for (int c = 0; c < NCLASS; c++)
+				nsmall += ccount[c];
+			if (nsmall)
+			{
+				k_roi_morph_w<<<(nsmall * 32 + 255) / 256, 256, 0, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[0], nsmall, prm, ctx->d_full.p, ncol_all);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+			if (ccount[NCLASS])
+			{
+				const int grid = (int)std::min<uint32_t> (ccount[NCLASS], (uint32_t)ctx->sm_count * 4);
+				k_roi_morph<<<grid, ROI_THREADS, RED_WORDS * 4, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[NCLASS], ccount[NCLASS], prm, ctx->d_full.p, ncol_all);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+		}
 		stage_end (ctx, ST_INT, ctx->ls);
 		if (d3)
 		{
@@ -1718,29 +1779,35 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 				int Lm = g != 0 ? std::abs (g) : maxI;	// > 0 MATLAB levels, < 0 PyRadiomics bins (texture_feature.h:52-77), 0 = intensities as they are
 				if (fam == FAM3_NGTDM && ctx->ngtdm3_radius == 0)
 					Lm = 1;		// nothing is accumulated (see ngtdm3d_body)
-				for (int c = 0; c < NCLASS; c++)
+				for (int c = 0; c <= NCLASS; c++)
 				{
 					const uint32_t n = ccount[c], mc = cmaxcells[c];
+					if (!n)
+						continue;
+					const bool big = c == NCLASS;	// cube beyond the shared-memory classes: global-memory path
 					const uint32_t* lst = ctx->d_tlist.p + tb[c];
 					int rc = 0;
 					if (fam == FAM3_GLCM)
 					{
 						if (g == 0 && Lm > 4096)
 							return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLCM without grey binning needs intensities <= 4096 (max %d)", Lm);
-						rc = mc < 32768 ? launch_family3_t<FAM3_GLCM, true> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
+						rc = big ? launch_family3_big<FAM3_GLCM> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
+							: mc < 32768 ? launch_family3_t<FAM3_GLCM, true> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
 							: launch_family3_t<FAM3_GLCM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
 					}
 					else if (fam == FAM3_GLSZM)
 					{
 						if (Lm > 65535)
 							return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLSZM needs grey levels < 65536 (max %d)", Lm);
-						rc = launch_family3_t<FAM3_GLSZM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+						rc = big ? launch_family3_big<FAM3_GLSZM> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
+							: launch_family3_t<FAM3_GLSZM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
 					}
 					else
 					{
-						if ((unsigned long long)(Lm + 2) * NGTDM3_NDMAX * (unsigned long long)mc >= 0xFFFFFFFFull || Lm + 2 > 65535)
-							return fail (ctx, NYXB200_EUNSUPPORTED, "3D NGTDM: level range %d too large for the exact integer accumulators; set 3ngtdm/greydepth", Lm);
-						rc = launch_family3_t<FAM3_NGTDM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+						if ((unsigned long long)(Lm + 2) * (unsigned long long)ngtdm3_ndmax (ctx->ngtdm3_radius) * (unsigned long long)mc >= 0xFFFFFFFFull || Lm + 2 > 65535)
+							return fail (ctx, NYXB200_EUNSUPPORTED, "3D NGTDM: %d grey levels x %d neighbours x %u voxels overflow the exact 32-bit accumulators; lower 3ngtdm/greydepth or 3ngtdm/radius", Lm, ngtdm3_ndmax (ctx->ngtdm3_radius), mc);
+						rc = big ? launch_family3_big<FAM3_NGTDM> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
+							: launch_family3_t<FAM3_NGTDM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
 					}
 					if (rc)
 						return rc;

@@ -82,6 +82,8 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 
 	// ---- pass 2: central sums + histograms (intensity.cpp:101-110,169-182; histogram.h:50-77)
 	const double binW100 = ddiv ((double)range, 100.0);
+	const double inv_binW100 = range ? 1.0 / binW100 : 0.0, inv_range = range ? 1.0 / (double)range : 0.0;
+	const bool fast_gs = range != 0 && nb < 65536;
 	enum { C_MAD, C_M2, C_M3, C_M4, C_P5, C_P6, C_N };
 	double cs[C_N] = { 0, 0, 0, 0, 0, 0 };
 	const bool blank = (mn == 0 && mx == 0);
@@ -95,10 +97,11 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 		cs[C_M4] += d2 * d2;
 		cs[C_P5] += d2 * d2 * d;
 		cs[C_P6] += d2 * d2 * d2;
-		double ri = ddiv ((double)(uint32_t)(v - mn), binW100);
-		int idx = (ri == ri) ? (int)ri : 0;
+		// bin of the 100-bin histogram: (int)((v - min) / binW), NaN (range 0: 0 / 0) -> 0 (histogram.h:55-66)
+		const int idx = range ? trunc_div_exact ((double)(uint32_t)(v - mn), binW100, inv_binW100) : 0;
 		atom_add (c, b100 + idx, 1u);
-		atom_add (c, bc + to_grayscale (v, mn, range, (uint32_t)nb, false), 1u);
+		// custom-bin histogram (histogram.h:68-77): to_grayscale, NaN (range 0) -> 0
+		atom_add (c, bc + (fast_gs ? to_grayscale_fast (v - mn, range, (uint32_t)nb, inv_range) : to_grayscale (v, mn, range, (uint32_t)nb, false)), 1u);
 	}
 	c.sync();
 	cta_sum<C_N> (c, cs);
@@ -201,6 +204,25 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 
 	// ---- entropy / uniformity over the custom bins (histogram.h:145-151)
 	double eu[2] = { 0, 0 };
+#if NYX_DEVICE_BUILD
+	if (c.wmode && n < LN_TABLE_N)
+	{
+		// log2 (cnt / n + 2.2e-16) = (ln cnt - ln n) / ln 2 up to 2.2e-16 * n / cnt <= 3e-13 (n < 1024): table loads
+		// instead of a double-precision logarithm per bin; empty bins contribute 0 * log2 (2.2e-16) = 0
+		const double ln_n = g_ln_table[n], inv_n = 1.0 / nd;
+		for (int k = c.tid; k <= nb; k += c.nthr)
+		{
+			const uint32_t cnt = bc[k];
+			if (cnt)
+			{
+				const double p = (double)cnt * inv_n;
+				eu[0] += p * ((g_ln_table[cnt] - ln_n) * INV_LN2);
+				eu[1] += p * p;
+			}
+		}
+	}
+	else
+#endif
 	for (int k = c.tid; k <= nb; k += c.nthr)
 	{
 		double p = (double)bc[k] / nd;
@@ -219,6 +241,33 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 	else
 		median = (double)(uint32_t)(srt[n / 2] + srt[n / 2 - 1]) / 2.0;
 	unsigned long long best = 0;	// (run length << 32) | ~value : longest run wins, ties -> smallest value
+#if NYX_DEVICE_BUILD
+	if (c.wmode)
+	{
+		// chunks of 32 consecutive sorted keys, last chunk first: a run head's length is the distance to the next head,
+		// found in the chunk's head mask or, when the run leaves the chunk, in the carried index of the next head
+		const int lane = c.tid;
+		uint32_t next_head = n;		// index of the first run head after the current chunk
+		for (int base = (int)((n - 1) & ~31u); base >= 0; base -= 32)
+		{
+			const uint32_t i = (uint32_t)base + lane;
+			const bool in = i < n;
+			const uint32_t v = in ? srt[i] : 0u;
+			const bool head = in && (i == 0 || srt[i - 1] != v);
+			const unsigned heads = __ballot_sync (0xffffffffu, head);
+			if (head)
+			{
+				const unsigned later = lane < 31 ? heads >> (lane + 1) : 0u;
+				const uint32_t nxt = later ? i + (uint32_t)__ffs (later) : next_head;
+				const unsigned long long key = ((unsigned long long)(nxt - i) << 32) | (unsigned long long)(~v);
+				best = key > best ? key : best;
+			}
+			if (heads)
+				next_head = (uint32_t)base + (uint32_t)__ffs (heads) - 1u;
+		}
+	}
+	else
+#endif
 	for (uint32_t i = c.tid; i < n; i += c.nthr)
 	{
 		uint32_t v = srt[i];
@@ -285,14 +334,15 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 		double skew = 0, kurt = 0, ekurt = 0;
 		if (M2 != 0.0)
 		{
-			skew = n > 3 ? (sqrt (nd) * M3) / pow (M2, 1.5) : 0.0;
+			skew = n > 3 ? (sqrt (nd) * M3) / (M2 * sqrt (M2)) : 0.0;	// pow (M2, 1.5) within 2 ulp, without the generic pow()
 			kurt = n > 4 ? (nd * M4) / (M2 * M2) : 0.0;
 			ekurt = n > 4 ? (nd * M4) / (M2 * M2) - 3.0 : 0.0;
 		}
 		out[I_SKEWNESS] = skew;
 		out[I_KURTOSIS] = kurt;
 		out[I_EXCESS_KURTOSIS] = ekurt;
-		double den5 = nd * pow (sd, 5.0), den6 = nd * pow (sd, 6.0);	// intensity.cpp:185-191
+		const double sd2 = sd * sd;
+		double den5 = nd * (sd2 * sd2 * sd), den6 = nd * (sd2 * sd2 * sd2);	// nd * pow (sd, 5 | 6) (intensity.cpp:185-191) within 3 ulp
 		out[I_HYPERSKEWNESS] = den5 == 0.0 ? 0.0 : cs[C_P5] / den5;
 		out[I_HYPERFLATNESS] = den6 == 0.0 ? 0.0 : cs[C_P6] / den6;
 	}

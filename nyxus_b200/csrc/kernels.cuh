@@ -9,6 +9,7 @@
 #include "nbr_body.h"
 #include "intensity_body.h"
 #include "vol_body.h"
+#include "morph_body.h"
 
 namespace nyx
 {
@@ -731,6 +732,8 @@ __global__ void __launch_bounds__(256) k_pack_tiles (ImageView im, const RoiRec*
 	uint16_t* tb = tileB ? tileB + r.tile_off : nullptr;
 	const size_t origin = (size_t)r.y0 * im.W + (size_t)r.x0;
 	uint32_t run = 0;
+	const bool gs_fast = !prm.ibsi && r.imax != 0 && prm.greydepth > 0 && prm.greydepth < 65536;
+	const double inv_imax = gs_fast ? 1.0 / (double)r.imax : 0.0;
 	constexpr int UN = 4;	// 32-cell chunks whose (independent) label and intensity loads are issued together
 	for (uint32_t base0 = 0; base0 < npad; base0 += 32 * UN)
 	{
@@ -767,7 +770,12 @@ __global__ void __launch_bounds__(256) k_pack_tiles (ImageView im, const RoiRec*
 					ta[i] = (uint16_t)code;
 				}
 				if (tb)
-					tb[i] = in ? (uint16_t)((to_grayscale (v, 0, r.imax, (uint32_t)prm.greydepth, prm.ibsi != 0) & TILE16_LEVEL) | 0x4000u) : (uint16_t)0;
+				{
+					// NGLDM's grey scale: to_grayscale over [0, aux_max] (exact, the division only where it could matter)
+					const uint32_t lvb = gs_fast ? to_grayscale_fast (v, r.imax, (uint32_t)prm.greydepth, inv_imax)
+						: to_grayscale (v, 0, r.imax, (uint32_t)prm.greydepth, prm.ibsi != 0);
+					tb[i] = in ? (uint16_t)((lvb & TILE16_LEVEL) | 0x4000u) : (uint16_t)0;
+				}
 			}
 			if (dst)
 			{
@@ -995,6 +1003,38 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 	}
 }
 
+// 3D cubes beyond the shared-memory size classes (organ-sized masks, whole-volume ROIs): one CTA per ROI, the cube AND the
+// family's work arrays in a per-CTA slot of global memory (`slotwords` words: the cube first, `tilewords` words, then the
+// family region, zero on entry and exit).  Throughput is that of one CTA per ROI walking L2 / HBM -- the job of this
+// path is to give such ROIs their reference values at all (the reference walks them on one host thread).
+template <int FAM3>
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_family3_big (ImageView im, const RoiRec* __restrict__ rois,
+	const uint32_t* __restrict__ list, uint32_t n, Params prm, int greyinfo, int Lmax, unsigned long long maxcells,
+	double* out, int out_stride, uint32_t* gscratch, size_t slotwords, size_t tilewords, uint32_t slots)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
+	uint32_t* cell = gscratch + (size_t)blockIdx.x * slotwords;
+	uint32_t* mem = cell + tilewords;
+	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		const RoiRec r = rois[ri];
+		double* o = out + (size_t)ri * out_stride;
+		Binner B;
+		B.init (greyinfo, r.imin, r.imax);
+		load_cube (c, im, r, B, cell);
+		c.sync();
+		if (FAM3 == FAM3_GLCM)
+			glcm3d_body<false> (c, r, prm, cell, mem, Lmax, o + COL3_GLCM, greyinfo);
+		else if (FAM3 == FAM3_GLSZM)
+			glszm3d_body_big (c, r, prm, cell, mem, maxcells, slots, greyinfo > 0, o + COL3_GLSZM);
+		else if (FAM3 == FAM3_NGTDM)
+			ngtdm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_NGTDM);
+		c.sync();
+	}
+}
+
 // first-order: reads the ROI's CSR slice
 template <bool GSCR>
 __global__ void __launch_bounds__(ROI_THREADS) k_roi_intensity (const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
@@ -1026,6 +1066,30 @@ __global__ void __launch_bounds__(ROI_THREADS, 6) k_roi_intensity_w (const RoiRe
 		const uint32_t ri = list ? list[k] : k;
 		const RoiRec r = rois[ri];
 		intensity_body (c, r, prm, cloud + r.cloud_off, r.area, max (next_pow2 (r.area), 64u), mem, out + (size_t)ri * out_stride + COL_INT);
+		c.sync();
+	}
+}
+
+// *BASIC_MORPHOLOGY*: warp per ROI (AABBs of the shared-memory size classes) / CTA per ROI (larger ones); reads the slide
+__global__ void __launch_bounds__(256) k_roi_morph_w (ImageView im, const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+	uint32_t n, Params prm, double* out, int out_stride)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (warp >= n)
+		return;
+	const uint32_t ri = list ? list[warp] : warp;
+	Cta c { (int)(threadIdx.x & 31), 32, nullptr, 1 };
+	morph_body (c, im, rois[ri], prm, out + (size_t)ri * out_stride + COL_MORPH);
+}
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_morph (ImageView im, const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+	uint32_t n, Params prm, double* out, int out_stride)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
+	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		morph_body (c, im, rois[ri], prm, out + (size_t)ri * out_stride + COL_MORPH);
 		c.sync();
 	}
 }

@@ -254,6 +254,32 @@ NYX_HD uint32_t to_grayscale (uint32_t i, uint32_t mn, uint32_t range, uint32_t 
 	return (uint32_t)pi;
 }
 
+// (int)(x / w) for x >= 0, w > 0 exactly as the reference's double division would give it, mostly without dividing:
+// q = x * (1/w) is within a few ulp of x / w, so both truncate alike unless q sits next to an integer; only then the
+// correctly rounded division decides.  inv_w = 1 / w (rounded).
+NYX_HD int trunc_div_exact (double x, double w, double inv_w)
+{
+	const double q = x * inv_w;
+	const int k = (int)q;
+	const double fr = q - (double)k;
+	if (fr > 1e-7 && fr < 1.0 - 1e-7)
+		return k;
+	return (int)ddiv (x, w);
+}
+
+// Nyxus::to_grayscale (helpers.h:337-345) = (uint)(double(x) / double(range) * double(n)) with x = i - min <= range:
+// the two roundings move the product by < 2^-35 (n < 2^16), so it truncates like the exact x * n / range unless that is
+// (next to) an integer -- only then the reference's own operation sequence is evaluated.  inv_range = 1 / range.
+NYX_HD uint32_t to_grayscale_fast (uint32_t x, uint32_t range, uint32_t n, double inv_range)
+{
+	const double q = (double)x * (double)n * inv_range;
+	const uint32_t k = (uint32_t)q;
+	const double fr = q - (double)k;
+	if (fr > 1e-7 && fr < 1.0 - 1e-7)
+		return k;
+	return to_grayscale (x, 0u, range, n, false);
+}
+
 NYX_HD double finite_or (double v, double sub)
 {
 	return (isnan (v) || isinf (v)) ? sub : v;

@@ -31,7 +31,13 @@ constexpr int COL_GLSZM = COL_GLDZM + NCOL_GLDZM;
 constexpr int COL_GLDM = COL_GLSZM + NCOL_GLSZM;
 constexpr int COL_NGLDM = COL_GLDM + NCOL_GLDM;
 constexpr int COL_NGTDM = COL_NGLDM + NCOL_NGLDM;
-constexpr int NCOL_ALL = COL_NGTDM + NCOL_NGTDM;	// 337
+constexpr int NCOL_TEXINT = COL_NGTDM + NCOL_NGTDM;	// 337: first-order + the seven texture families
+// *BASIC_MORPHOLOGY*  is appended to the canonical table; the OUTPUT order is by Feature2D code (the feature
+// table), so its columns still come out between the first-order and the GLCM columns like the reference's
+constexpr int FAM_MORPH = FAM_COUNT;			// not a texture family: no size classes, no tile
+constexpr int NCOL_MORPH = 15;
+constexpr int COL_MORPH = NCOL_TEXINT;
+constexpr int NCOL_ALL = COL_MORPH + NCOL_MORPH;	// 352
 
 // ---- first-order (Feature2D::COV .. UNIFORMITY_PIU, featureset.h:13-48)
 enum IntCol : int
@@ -41,6 +47,14 @@ enum IntCol : int
 	I_MEDIAN_ABSOLUTE_DEVIATION, I_MIN, I_MODE, I_P01, I_P10, I_P25, I_P75, I_P90, I_P99, I_QCOD, I_RANGE, I_ROBUST_MEAN,
 	I_ROBUST_MEAN_ABSOLUTE_DEVIATION, I_ROOT_MEAN_SQUARED, I_SKEWNESS, I_STANDARD_DEVIATION, I_STANDARD_DEVIATION_BIASED,
 	I_STANDARD_ERROR, I_VARIANCE, I_VARIANCE_BIASED, I_UNIFORMITY, I_UNIFORMITY_PIU
+};
+
+// ---- basic morphology (Feature2D::AREA_PIXELS_COUNT .. ASPECT_RATIO, featureset.h:46-60)
+enum MorphCol : int
+{
+	MO_AREA_PIXELS_COUNT = 0, MO_AREA_UM2, MO_CENTROID_X, MO_CENTROID_Y, MO_WEIGHTED_CENTROID_Y, MO_WEIGHTED_CENTROID_X,
+	MO_MASS_DISPLACEMENT, MO_COMPACTNESS, MO_BBOX_YMIN, MO_BBOX_XMIN, MO_BBOX_HEIGHT, MO_BBOX_WIDTH, MO_DIAMETER_EQUAL_AREA,
+	MO_EXTENT, MO_ASPECT_RATIO
 };
 
 // ---- GLCM angled features in enum order (featureset.h:174-203); column = COL_GLCM + 4*f + angle

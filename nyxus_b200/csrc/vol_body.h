@@ -168,12 +168,18 @@ NYX_D void glszm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// 3D NGTDM, Chebyshev radius <= 1 (26 neighbours).  L1 = level slots = (largest binned level) + 2 (room for the +1 shift)
+// 3D NGTDM, Chebyshev radius R (3d_ngtdm.cpp:69-94: the (2R+1)^3 - 1 in-cube neighbours, background included).
+// L1 = level slots = (largest binned level) + 2 (room for the +1 shift)
 // ------------------------------------------------------------------------------------------------
-constexpr int NGTDM3_NDMAX = 26;
-NYX_HD size_t ngtdm3d_smem_words (int Lmax)
+constexpr int NGTDM3_RMAX = 4;
+NYX_HD int ngtdm3_ndmax (int R)
 {
-	return ngtdm_words (Lmax + 2, NGTDM3_NDMAX) + 2;
+	const int s = 2 * (R < 1 ? 1 : R) + 1;
+	return s * s * s - 1;
+}
+NYX_HD size_t ngtdm3d_smem_words (int Lmax, int R)
+{
+	return ngtdm_words (Lmax + 2, ngtdm3_ndmax (R)) + 2;
 }
 
 // cell: cube binned with the NGTDM grey depth; matlab: the binning was MATLAB (zeroI = 1); maxlevel: largest level in the cube
@@ -191,10 +197,11 @@ NYX_D void ngtdm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const
 			out[i] = nan ("");
 		return;
 	}
+	const int NDMAX = ngtdm3_ndmax (R);
 	uint32_t* Nn = mem;
 	uint32_t* SI = Nn + L1;
-	uint32_t* PR = SI + (size_t)L1 * NGTDM3_NDMAX;
-	uint32_t* flags = mem + ngtdm_words (L1, NGTDM3_NDMAX);	// [0] some cell has level 0, [1] largest level
+	uint32_t* PR = SI + (size_t)L1 * NDMAX;
+	uint32_t* flags = mem + ngtdm_words (L1, NDMAX);	// [0] some cell has level 0, [1] largest level
 	FastDiv fw, fh;
 	fw.init ((uint32_t)w);
 	fh.init ((uint32_t)h);
@@ -260,7 +267,7 @@ NYX_D void ngtdm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const
 		{
 			long long df = (long long)lv * nd - (long long)sum;
 			atom_add (c, Nn + lv, 1u);
-			atom_add (c, SI + (size_t)lv * NGTDM3_NDMAX + (nd - 1), (uint32_t)(df < 0 ? -df : df));
+			atom_add (c, SI + (size_t)lv * NDMAX + (nd - 1), (uint32_t)(df < 0 ? -df : df));
 			q[0]++;
 		}
 	}
@@ -268,7 +275,241 @@ NYX_D void ngtdm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const
 	cta_sum_u64<1> (c, q);
 	// |I|: IBSI flag -> 0..max (max + 1 levels); else the number of distinct values = Ngp, found by the sweep (-1)
 	const int isize = ibsi ? (int)maxlv + 1 : -1;
-	ngtdm_reduce (c, prm, mem, L1, NGTDM3_NDMAX, 0, (double)q[0], isize, false, out, nullptr);
+	ngtdm_reduce (c, prm, mem, L1, NDMAX, 0, (double)q[0], isize, false, out, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3D GLSZM of a LARGE cube (beyond the shared-memory size classes: organ-sized masks, whole-volume ROIs).  Same
+// semantics as glszm3d_body; everything lives in global memory: 32-bit union-find parents and zone sizes, and the
+// sparse (level, size) matrix + marginals in one open-addressing table of 64-bit keys with 32-bit counts.
+// SAE / LAE take `j * j` in int like the reference (3d_glszm.cpp:calc_SAE / calc_LAE: wraps for zones of >= 46341 voxels);
+// the other emphasis sums use double j^2 (calc_sums_of_P).
+// ------------------------------------------------------------------------------------------------
+NYX_HD uint32_t glszm3d_big_slots (int Lmax, unsigned long long maxcells)
+{
+	// distinct sizes d: 1 + 2 + .. + d <= cells; distinct (level, size) keys <= min (cells, Lmax * d)
+	unsigned long long d = 2;
+	while (d * (d + 1) / 2 <= maxcells) d++;
+	unsigned long long K = (unsigned long long)Lmax * d;
+	if (K > maxcells) K = maxcells;
+	K += (unsigned long long)Lmax + d + 2;
+	K += K / 2;
+	if (K > 0x40000000ull) K = 0x40000000ull;
+	return next_pow2 ((uint32_t)K);
+}
+// words: parent[cells] + size[cells] + keys[slots] (64-bit) + cnts[slots]
+NYX_HD size_t glszm3d_big_words (unsigned long long maxcells, uint32_t slots)
+{
+	return (size_t)(2 * maxcells + (maxcells & 1) * 0 + 3ull * slots + 2);
+}
+
+NYX_D void htab64_add (const Cta& c, unsigned long long* keys, uint32_t* cnts, uint32_t mask, unsigned long long key)
+{
+	uint32_t slot = htab_mix ((uint32_t)key ^ (uint32_t)(key >> 29)) & mask;
+	for (;;)
+	{
+		unsigned long long k = ((volatile unsigned long long*)keys)[slot];
+		if (k == 0)
+		{
+#if NYX_DEVICE_BUILD
+			k = atomicCAS (keys + slot, 0ull, key);
+#else
+			keys[slot] = key;
+#endif
+		}
+		if (k == 0 || k == key)
+			break;
+		slot = (slot + 1) & mask;
+	}
+	atom_add (c, cnts + slot, 1u);
+}
+NYX_D uint32_t htab64_get (const unsigned long long* keys, const uint32_t* cnts, uint32_t mask, unsigned long long key)
+{
+	uint32_t slot = htab_mix ((uint32_t)key ^ (uint32_t)(key >> 29)) & mask;
+	while (keys[slot] != key)
+		slot = (slot + 1) & mask;
+	return cnts[slot];
+}
+
+// mem: glszm3d_big_words (maxcells, slots) words of global memory, keys / cnts all zero on entry and exit
+NYX_D void glszm3d_body_big (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem,
+	unsigned long long maxcells, uint32_t slots, bool matlab, double* out)
+{
+	const int w = r.w, h = r.h, d = r.d, ncell = w * h * d;
+	if (r.imin == r.imax)
+	{
+		for (int i = c.tid; i < NCOL_GLSZM; i += c.nthr)
+			out[i] = prm.softnan;
+		return;
+	}
+	uint32_t* lab = mem;
+	uint32_t* zs = lab + maxcells;
+	unsigned long long* keys = (unsigned long long*)(zs + maxcells + (maxcells & 1));
+	uint32_t* cnts = (uint32_t*)(keys + slots);
+	const uint32_t mask = slots - 1;
+	const uint32_t skip = matlab ? 1u : 0u;
+	FastDiv fw, fh;
+	fw.init ((uint32_t)w);
+	fh.init ((uint32_t)h);
+	const unsigned long long K_PAIR = 1ull << 63, K_LEVEL = 1ull << 62, K_SIZE = 1ull << 61;
+
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		zs[i] = 0;
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		int hd = i;
+		if (lv != skip)
+		{
+			int x = i - (int)fw.div ((uint32_t)i) * w;
+			while (x > 0 && (cell[hd - 1] & CELL_LEVEL) == lv)
+			{
+				hd--;
+				x--;
+			}
+		}
+		lab[i] = (uint32_t)hd;
+	}
+	c.sync();
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (lv == skip)
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+		const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+		for (int dz = -1; dz <= 0; dz++)
+		{
+			const int zz = z + dz;
+			if (zz < 0)
+				continue;
+			for (int dy = -1; dy <= (dz < 0 ? 1 : -1); dy++)
+			{
+				const int yy = y + dy;
+				if (yy < 0 || yy >= h)
+					continue;
+				for (int dx = -1; dx <= 1; dx++)
+				{
+					const int xx = x + dx;
+					if (xx < 0 || xx >= w)
+						continue;
+					const int j = (zz * h + yy) * w + xx;
+					if ((cell[j] & CELL_LEVEL) == lv)
+						uf_unite (c, lab, (uint32_t)i, (uint32_t)j);
+				}
+			}
+		}
+	}
+	c.sync();
+	unsigned long long np[1] = { 0 };
+	for (int i = c.tid; i < ncell; i += c.nthr)
+		if ((cell[i] & CELL_LEVEL) != skip)
+		{
+			const uint32_t root = uf_find (lab, (uint32_t)i);
+			if (root != (uint32_t)i)
+				lab[i] = root;
+			atom_add (c, zs + root, 1u);
+			np[0]++;
+		}
+	c.sync();
+
+	// ---- pass 1 over the zones (= root cells)
+	enum { Q_NZ, Q_MUJ, Q_MUI, Q_HGL, Q_N };
+	unsigned long long q[Q_N];
+	for (int k = 0; k < Q_N; k++)
+		q[k] = 0;
+	long long lae[1] = { 0 };
+	enum { A_SAE, A_LGL, A_SAL, A_SAH, A_LAL, A_LAH, A_N };
+	double s[A_N];
+	for (int k = 0; k < A_N; k++)
+		s[k] = 0;
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (lv == skip || lab[i] != (uint32_t)i)
+			continue;
+		const uint32_t sz = zs[i];
+		htab64_add (c, keys, cnts, mask, K_PAIR | ((unsigned long long)lv << 36) | sz);
+		htab64_add (c, keys, cnts, mask, K_LEVEL | lv);
+		htab64_add (c, keys, cnts, mask, K_SIZE | sz);
+		q[Q_NZ] += 1;
+		q[Q_MUJ] += sz;
+		q[Q_MUI] += lv;
+		q[Q_HGL] += (unsigned long long)lv * lv;
+		const int jj = (int)(sz * sz);		// `j * j` in int
+		lae[0] += (long long)jj;
+		const double i2 = (double)lv * (double)lv, j2 = (double)sz * (double)sz;
+		s[A_SAE] += 1.0 / (double)jj;
+		s[A_LGL] += 1.0 / i2;
+		s[A_SAL] += 1.0 / (i2 * j2);
+		s[A_SAH] += i2 / j2;
+		s[A_LAL] += j2 / i2;
+		s[A_LAH] += i2 * j2;
+	}
+	c.sync();
+	cta_sum_u64<Q_N> (c, q);
+	{
+		unsigned long long t[2] = { (unsigned long long)(lae[0] < 0 ? -lae[0] : 0), (unsigned long long)(lae[0] > 0 ? lae[0] : 0) };
+		cta_sum_u64<2> (c, t);
+		lae[0] = (long long)t[1] - (long long)t[0];
+	}
+	cta_sum<A_N> (c, s);
+	const uint32_t nz = (uint32_t)q[Q_NZ];
+	if (nz == 0)
+	{
+		for (int i = c.tid; i < NCOL_GLSZM; i += c.nthr)
+			out[i] = prm.softnan;
+		return;
+	}
+	const double sum = (double)nz;
+	const double mui = (double)q[Q_MUI] / sum, muj = (double)q[Q_MUJ] / sum;
+	const double inv_sum = 1.0 / sum;
+
+	// ---- pass 2: terms that need the counts (owner computes)
+	unsigned long long q2[2] = { 0, 0 };
+	double t[3] = { 0, 0, 0 };
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (lv == skip || lab[i] != (uint32_t)i)
+			continue;
+		const uint32_t sz = zs[i];
+		q2[0] += htab64_get (keys, cnts, mask, K_LEVEL | lv);
+		q2[1] += htab64_get (keys, cnts, mask, K_SIZE | sz);
+		const double di = (double)lv - mui, dj = (double)sz - muj;
+		t[0] += di * di;
+		t[1] += dj * dj;
+		const double pn = (double)htab64_get (keys, cnts, mask, K_PAIR | ((unsigned long long)lv << 36) | sz) * inv_sum;
+		t[2] += fast_log10 (dadd (pn, EPS_ZONES));
+	}
+	cta_sum_u64<2> (c, q2);
+	cta_sum<3> (c, t);
+	c.sync();
+	for (size_t i = c.tid; i < (size_t)slots; i += c.nthr)	// restore the all-zero table
+	{
+		keys[i] = 0;
+		cnts[i] = 0;
+	}
+	c.sync();
+	if (c.tid == 0)
+	{
+		out[S_SAE] = s[A_SAE] / sum;
+		out[S_LAE] = (double)lae[0] / sum;
+		out[S_GLN] = (double)q2[0] / sum;
+		out[S_GLNN] = (double)q2[0] / (sum * sum);
+		out[S_SZN] = (double)q2[1] / sum;
+		out[S_SZNN] = (double)q2[1] / (sum * sum);
+		out[S_ZP] = sum / (double)r.area;
+		out[S_GLV] = t[0] / sum;
+		out[S_ZV] = t[1] / sum;
+		out[S_ZE] = -(t[2] / sum) * (1.0 / LOG10_2);
+		out[S_LGLZE] = s[A_LGL] / sum;
+		out[S_HGLZE] = (double)q[Q_HGL] / sum;
+		out[S_SALGLE] = s[A_SAL] / sum;
+		out[S_SAHGLE] = s[A_SAH] / sum;
+		out[S_LALGLE] = s[A_LAL] / sum;
+		out[S_LAHGLE] = s[A_LAH] / sum;
+	}
+	(void)np;
 }
 
 } // namespace nyx

@@ -147,8 +147,11 @@ class Nyxus:
         self.error_message = ''
         header = ["intensity_image", "mask_image", "ROI_label", "t_index"] + self._engine.columns
         df = pd.DataFrame(numeric, columns=header[2:], copy=False)
-        df.insert(0, "mask_image", np.asarray(label_names, dtype=object)[row_img])
-        df.insert(0, "intensity_image", np.asarray(intensity_names, dtype=object)[row_img])
+        # string columns by a take on the (few) names in pandas' own string type: what DataFrame(string_data) infers, without
+        # converting 2 x nrows Python objects
+        sdt = pd.Series(np.array(["x"], dtype=object)).infer_objects().dtype
+        df.insert(0, "mask_image", pd.array([str(v) for v in label_names], dtype=sdt).take(row_img))
+        df.insert(0, "intensity_image", pd.array([str(v) for v in intensity_names], dtype=sdt).take(row_img))
         if "ROI_label" in df.columns:
             df.ROI_label = df.ROI_label.astype(np.uint32)
         return df

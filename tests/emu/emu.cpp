@@ -16,6 +16,7 @@
 #include "../../nyxus_b200/csrc/nbr_body.h"
 #include "../../nyxus_b200/csrc/intensity_body.h"
 #include "../../nyxus_b200/csrc/vol_body.h"
+#include "../../nyxus_b200/csrc/morph_body.h"
 
 using namespace nyx;
 
@@ -143,6 +144,7 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 // ---- 3D: one labelled volume [D][H][W], label value `lab`; fam_mask bits: 1 INT, 2 GLCM, 4 NGTDM, 8 GLSZM.
 // out layout: 36 first-order | 30x13 + 29 GLCM | 5 NGTDM | 16 GLSZM   (the canonical 3D table of the library)
 extern "C" int nyxemu_ncols3d() { return NCOL_INT + NCOL_GLCM3 + NCOL_NGTDM + NCOL_GLSZM; }
+static bool g_big3d = false;	// 3D GLSZM through the large-cube body
 static int g_glcm3_greydepth = INT_MIN;	// "3glcm/greydepth"; INT_MIN = follows the grey depth
 extern "C" void nyxemu_set_glcm3_greydepth (int g) { g_glcm3_greydepth = g; }
 extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl, int D, int H, int W, uint32_t lab,
@@ -213,21 +215,62 @@ extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl,
 		}
 		else if (fam == 2)
 		{
-			const uint32_t slots = glszm_hash_slots (Lm, (uint32_t)ncell);
-			std::vector<uint32_t> mem (glszm3d_smem_words ((uint32_t)ncell, slots));
-			glszm3d_body (c, r, prm, cell.data(), mem.data(), (uint32_t)ncell, slots, g > 0, out + O_GLSZM);
+			if (g_big3d)	// the large-cube body (32-bit labels, 64-bit hash keys)
+			{
+				const uint32_t slots = glszm3d_big_slots (Lm, (unsigned long long)ncell);
+				std::vector<uint32_t> mem (glszm3d_big_words ((unsigned long long)ncell, slots) + 2);
+				uint32_t* m8 = mem.data() + (((uintptr_t)mem.data() & 7) ? 1 : 0);	// 8-byte aligned keys
+				glszm3d_body_big (c, r, prm, cell.data(), m8, (unsigned long long)ncell, slots, g > 0, out + O_GLSZM);
+			}
+			else
+			{
+				const uint32_t slots = glszm_hash_slots (Lm, (uint32_t)ncell);
+				std::vector<uint32_t> mem (glszm3d_smem_words ((uint32_t)ncell, slots));
+				glszm3d_body (c, r, prm, cell.data(), mem.data(), (uint32_t)ncell, slots, g > 0, out + O_GLSZM);
+			}
 		}
 		else
 		{
 			if (ngtdm_radius == 0)
 				Lm = 1;
-			std::vector<uint32_t> mem (ngtdm3d_smem_words (Lm));
+			std::vector<uint32_t> mem (ngtdm3d_smem_words (Lm, ngtdm_radius));
 			ngtdm3d_body (c, r, prm, cell.data(), mem.data(), Lm, g > 0, out + O_NGTDM);
 		}
 	}
 	return 0;
 }
 
+extern "C" void nyxemu_set_big3d (int on) { g_big3d = on != 0; }
 extern "C" double nyxemu_fast_log10 (double x) { return fast_log10 (x); }
 extern "C" unsigned nyxemu_bin (unsigned x, unsigned mn, unsigned mx, int g) { Binner B; B.init (g, mn, mx); return B.bin (x); }
 extern "C" unsigned nyxemu_to_grayscale (unsigned i, unsigned mn, unsigned range, unsigned n) { return to_grayscale (i, mn, range, n, false); }
+
+// *BASIC_MORPHOLOGY* of the ROI `lab` of a labelled uint32 slide: the 15 columns of morph_body in Feature2D code order
+extern "C" int nyxemu_morph (const uint32_t* inten, const uint32_t* lbl, int H, int W, unsigned lab, double* out)
+{
+	RoiRec r;
+	memset (&r, 0, sizeof (r));
+	r.label = lab;
+	r.imin = 0xFFFFFFFFu;
+	int x0 = W, x1 = -1, y0 = H, y1 = -1;
+	for (int y = 0; y < H; y++)
+		for (int x = 0; x < W; x++)
+			if (lbl[(size_t)y * W + x] == lab)
+			{
+				const uint32_t v = inten[(size_t)y * W + x];
+				r.area++;
+				r.imin = std::min (r.imin, v);
+				r.imax = std::max (r.imax, v);
+				x0 = std::min (x0, x); x1 = std::max (x1, x);
+				y0 = std::min (y0, y); y1 = std::max (y1, y);
+			}
+	if (!r.area)
+		return -1;
+	r.x0 = x0; r.y0 = y0; r.w = x1 - x0 + 1; r.h = y1 - y0 + 1; r.d = 1;
+	ImageView im { inten, lbl, H, W, 0 };
+	Params prm = make_prm (64, 64, false, 1);
+	std::vector<double> red (RED_MAX * NW_MAX);
+	Cta c { 0, 1, red.data() };
+	morph_body (c, im, r, prm, out);
+	return 0;
+}

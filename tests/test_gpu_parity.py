@@ -4,6 +4,8 @@
   (3) the numpy oracle,
 with every matrix entry exact and every derived feature within 1e-9 relative (north_star), plus size-independent
 properties at the full configs[1] size."""
+import os
+
 import numpy as np
 import pytest
 
@@ -521,3 +523,67 @@ def test_multi_device_list_call_gives_the_single_device_table(nctx, pad):
         single.close()
         for e in engines:
             e.close()
+
+
+# ------------------------------------------------------------------------------------------------ 3D: large cubes, NGTDM radius > 1
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so did not travel")
+@pytest.mark.parametrize("radius,g", [(1, 64), (2, 32)])
+def test_large_3d_rois_and_ngtdm_radius_against_compiled_reference(radius, g):
+    """ROIs whose bounding cube exceeds the shared-memory classes (> 40000 voxels: organ-sized masks) run through the
+    global-memory path (k_roi_family3_big: 32-bit union-find, 64-bit hash keys); small ROIs of the same volume keep the
+    shared-memory kernels.  3ngtdm/radius = 2 is the 124-neighbour Chebyshev cube (3d_ngtdm.cpp:69-94)."""
+    rng = np.random.default_rng(40 + radius)
+    D, H, W = 50, 72, 80
+    zz, yy, xx = np.mgrid[0:D, 0:H, 0:W]
+    L = np.zeros((D, H, W), np.uint32)
+    big = (((zz - 24) / 22.0) ** 2 + ((yy - 35) / 30.0) ** 2 + ((xx - 38) / 33.0) ** 2) < 1        # cube ~ 45 x 60 x 66 = 178k voxels
+    big &= ~((((zz - 20) / 8.0) ** 2 + ((yy - 30) / 9.0) ** 2 + ((xx - 40) / 10.0) ** 2) < 1)      # a hole
+    L[big] = 5
+    L[2:9, 60:70, 68:79] = 9                                # small ROIs next to it
+    L[40:49, 2:10, 2:12] = 2
+    field = (np.sin(zz / 5.0) + np.cos(yy / 7.0) * np.sin(xx / 6.0) + 2.2) * 300.0
+    I = (field + rng.normal(0, 60, (D, H, W))).clip(1, 4000).astype(np.uint16)
+    I[rng.random((D, H, W)) < 0.005] = 0
+    e = _engine3([g, g, g, radius, 0])
+    try:
+        tab, _ = e.featurize_volume(I, L)
+        rl, rt, _ = ref.featurize_3d(I.astype(np.uint32), L, greydepth=g, glszm_greydepth=g, ngtdm_greydepth=g, ngtdm_radius=radius, nthreads=8)
+        assert np.array_equal(tab[:, 0].astype(np.int64), rl.astype(np.int64)) and list(rl) == [2, 5, 9]
+        recs = e.debug_rois()
+        assert max(int(r[6]) * int(r[7]) for r in recs) * 45 > 40000
+        bad = tu.mismatches(rt, tab[:, 2:], GV["columns"])
+        assert not bad, bad[:8]
+    finally:
+        e.close()
+
+
+# ------------------------------------------------------------------------------------------------ *BASIC_MORPHOLOGY* (SURVEY 8f-3)
+def test_basic_morphology_against_reference_golden():
+    """golden_morph.npz = the reference's own pybind module on a slide of blobs + degenerate shapes (1 and 2 pixels, 2x2
+    square, line, ring, all-zero intensities, sparse ROI with a huge bounding box).  Alone, and together with every other
+    family: the 15 columns come out between the first-order and the GLCM columns, like the reference's."""
+    Zm = np.load(os.path.join(tu.GOLDEN, "golden_morph.npz"))
+    I, L = Zm["inten"], Zm["label"]
+    e = _engine(["*BASIC_MORPHOLOGY*"])
+    try:
+        tab, _ = e.featurize(I, L)
+        assert e.columns == [str(c) for c in Zm["columns"]]
+        assert np.array_equal(tab[:, 0].astype(np.int64), Zm["labels"])
+        bad = tu.mismatches(Zm["table"], tab[:, 2:], e.columns)
+        assert not bad, bad[:8]
+    finally:
+        e.close()
+    e = _engine(["*ALL_INTENSITY*", "*BASIC_MORPHOLOGY*", "*ALL_TEXTURE*"])
+    try:
+        tab, _ = e.featurize(I.astype(np.uint16), L)
+        assert e.columns == [str(c) for c in Zm["all_columns"]]
+        bad = tu.mismatches(Zm["all_table"], tab[:, 2:], e.columns)
+        assert not bad, bad[:8]
+        e.set_param("roi_batches", 3)
+        tab3, _ = e.featurize(I.astype(np.uint16), L)
+        assert np.array_equal(tab3, tab)
+    finally:
+        e.close()
+    from nyxus_b200 import Nyxus
+    df = Nyxus(["*BASIC_MORPHOLOGY*", "MEAN"]).featurize(I, L)
+    assert list(df.columns[4:6]) == ["MEAN", "AREA_PIXELS_COUNT"] and df.shape[1] == 4 + 16

@@ -73,12 +73,13 @@ def test_nyxus_argument_validation_matches_reference():
 
 def test_feature_table_layout():
     from nyxus_b200 import feature_table as ft
-    assert len(ft.CANONICAL_COLUMNS) == 337 and len(ft.FEATURES) == 199
+    assert len(ft.CANONICAL_COLUMNS) == 337 + 15 and len(ft.FEATURES) == 199 + 15      # + *BASIC_MORPHOLOGY* (appended)
     assert ft.CANONICAL_COLUMNS[0] == "COV" and ft.CANONICAL_COLUMNS[35] == "UNIFORMITY_PIU"
     assert ft.CANONICAL_COLUMNS[36:40] == ["GLCM_ASM_0", "GLCM_ASM_45", "GLCM_ASM_90", "GLCM_ASM_135"]
-    assert ft.CANONICAL_COLUMNS[-5:] == ["NGTDM_COARSENESS", "NGTDM_CONTRAST", "NGTDM_BUSYNESS", "NGTDM_COMPLEXITY", "NGTDM_STRENGTH"]
+    assert ft.CANONICAL_COLUMNS[332:337] == ["NGTDM_COARSENESS", "NGTDM_CONTRAST", "NGTDM_BUSYNESS", "NGTDM_COMPLEXITY", "NGTDM_STRENGTH"]
+    assert ft.CANONICAL_COLUMNS[337] == "AREA_PIXELS_COUNT" and ft.CANONICAL_COLUMNS[-1] == "ASPECT_RATIO"
     codes = [f[1] for f in ft.FEATURES]
-    assert codes == sorted(codes) and codes[0] == 0 and codes[36] == 144   # Feature2D::COV, GLCM_ASM
+    assert codes == sorted(codes) and codes[0] == 0 and codes[36] == 36 and codes[51] == 144   # COV, AREA_PIXELS_COUNT, GLCM_ASM
 
 
 def test_lpt_partition_balances_and_is_deterministic():

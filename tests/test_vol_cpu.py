@@ -78,3 +78,28 @@ def test_3d_column_contract_of_the_library():
     inc = os.path.join(tu.ROOT, "nyxus_b200", "csrc", "nyx_feature_table3d.inc")
     names = [ln.split('"')[1] for ln in open(inc) if ln.startswith("{")]
     assert names == GV["columns"] and len(names) == 116
+
+
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so not built")
+def test_3d_ngtdm_radius_above_one_and_large_cube_glszm_against_compiled_reference():
+    """3ngtdm/radius = 2, 3 (3d_ngtdm.cpp:69-94: the (2R+1)^3 - 1 Chebyshev neighbourhood) and the large-cube GLSZM body
+    (32-bit union-find, 64-bit hash keys) give the reference's values"""
+    L = tu.build_emu()
+    rng = np.random.default_rng(91)
+    cols = GV["columns"]
+    try:
+        for it in range(12):
+            D, H, W = [int(rng.integers(3, 10)) for _ in range(3)]
+            V = rng.integers(1, 3000, (D, H, W)) if it % 2 == 0 else rng.integers(1, 7, (D, H, W))
+            M = (rng.random((D, H, W)) < rng.choice([0.7, 1.0])).astype(np.uint32) * 7
+            M[0, 0, 0] = 7
+            rad = int(rng.choice([2, 3]))
+            gz, gn = int(rng.choice([0, 16, 64])), int(rng.choice([16, 64]))
+            if gz == 0 and it % 2 == 0:
+                gz = 32
+            labs, tab, _ = ref.featurize_3d(V.astype(np.uint32), M, greydepth=64, glszm_greydepth=gz, ngtdm_greydepth=gn, ngtdm_radius=rad)
+            L.nyxemu_set_big3d(it % 3 != 0)
+            got = tu.emu_roi_features_3d(L, V, M, 7, 64, gz, gn, rad, False, cols)
+            assert not tu.mismatches(tab[0], got, cols), (it, rad, gz, gn)
+    finally:
+        L.nyxemu_set_big3d(0)
