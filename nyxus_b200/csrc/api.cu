@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <condition_variable>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <thread>
 #include <string>
@@ -679,10 +680,22 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 namespace
 {
 
+// The dynamic shared-memory limit of a kernel is per-device state shared by every context (and host thread) that uses
+// the device: it is only ever RAISED, under a lock -- two contexts on one device (or two threads of a multi-device call
+// given contexts of the same device) must not lower each other's limit between a set and the launch that relies on it.
+std::mutex g_attr_mtx;
+std::map<std::pair<const void*, int>, size_t> g_attr_bytes;
 template <class K> int set_smem (nyxb200_ctx* ctx, K kernel, size_t bytes)
 {
-	if (bytes > 48 * 1024)
+	if (bytes <= 48 * 1024)
+		return 0;
+	std::lock_guard<std::mutex> lk (g_attr_mtx);
+	size_t& cur = g_attr_bytes[{ reinterpret_cast<const void*> (kernel), ctx->st.device }];
+	if (bytes > cur)
+	{
 		CU (cudaFuncSetAttribute (kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+		cur = bytes;
+	}
 	return 0;
 }
 
@@ -2258,14 +2271,20 @@ int nyxb200_featurize_2d_list_multi (nyxb200_ctx* const* ctxs, int n_ctx, const 
 		for (auto& t : th)
 			t.join();
 	}
-	for (int d = 0; d < n_ctx; d++)
-		if (rcs[d])
+	{
+		// report the failure that started it, not the "another device failed" of the contexts that gave up after it
+		int bad = -1;
+		for (int d = 0; d < n_ctx; d++)
+			if (rcs[d] && (bad < 0 || ctxs[bad]->err.find ("another device") != std::string::npos))
+				bad = d;
+		if (bad >= 0)
 		{
-			if (d)
-				c0->err = "device " + std::to_string (ctxs[d]->st.device) + ": " + ctxs[d]->err;
+			if (bad)
+				c0->err = "context " + std::to_string (bad) + " (device " + std::to_string (ctxs[bad]->st.device) + "): " + ctxs[bad]->err;
 			pool_release (sh.base);
-			return rcs[d];
+			return rcs[bad];
 		}
+	}
 	cudaSetDevice (c0->st.device);
 	// slides that did not fit the estimate: grow to the exact size, then a second pass on context 0 (their row ranges are known)
 	const size_t total = (size_t)sh.cursor;

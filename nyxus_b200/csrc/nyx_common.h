@@ -259,6 +259,8 @@ NYX_HD uint32_t to_grayscale (uint32_t i, uint32_t mn, uint32_t range, uint32_t 
 // correctly rounded division decides.  inv_w = 1 / w (rounded).
 NYX_HD int trunc_div_exact (double x, double w, double inv_w)
 {
+	if (x == 0.0)
+		return 0;
 	const double q = x * inv_w;
 	const int k = (int)q;
 	const double fr = q - (double)k;
@@ -272,6 +274,8 @@ NYX_HD int trunc_div_exact (double x, double w, double inv_w)
 // (next to) an integer -- only then the reference's own operation sequence is evaluated.  inv_range = 1 / range.
 NYX_HD uint32_t to_grayscale_fast (uint32_t x, uint32_t range, uint32_t n, double inv_range)
 {
+	if (x == 0)	// 0 / range * n == 0 exactly (every cell outside the ROI takes this exit)
+		return 0;
 	const double q = (double)x * (double)n * inv_range;
 	const uint32_t k = (uint32_t)q;
 	const double fr = q - (double)k;

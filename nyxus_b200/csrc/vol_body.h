@@ -300,7 +300,7 @@ NYX_HD uint32_t glszm3d_big_slots (int Lmax, unsigned long long maxcells)
 // words: parent[cells] + size[cells] + keys[slots] (64-bit) + cnts[slots]
 NYX_HD size_t glszm3d_big_words (unsigned long long maxcells, uint32_t slots)
 {
-	return (size_t)(2 * maxcells + (maxcells & 1) * 0 + 3ull * slots + 2);
+	return (size_t)(2 * maxcells + 3ull * slots + 2);
 }
 
 NYX_D void htab64_add (const Cta& c, unsigned long long* keys, uint32_t* cnts, uint32_t mask, unsigned long long key)
@@ -344,7 +344,7 @@ NYX_D void glszm3d_body_big (const Cta& c, const RoiRec& r, const Params& prm, c
 	}
 	uint32_t* lab = mem;
 	uint32_t* zs = lab + maxcells;
-	unsigned long long* keys = (unsigned long long*)(zs + maxcells + (maxcells & 1));
+	unsigned long long* keys = (unsigned long long*)(zs + maxcells);	// 2 * maxcells words past the (8-byte aligned) region start
 	uint32_t* cnts = (uint32_t*)(keys + slots);
 	const uint32_t mask = slots - 1;
 	const uint32_t skip = matlab ? 1u : 0u;

@@ -4,7 +4,10 @@
   C4  512^3 volume, 2197 ROIs, 3D GLCM / GLSZM / NGTDM + first-order     (resident)
   C5  a job of N configs[1] slides from pinned host memory, *ALL_TEXTURE* + *ALL_INTENSITY* (pipelined list call) --
       what ONE GPU of the 64-slide job does
-usage: run_configs.py [c1,c2ibsi,c3,c4,c5] [n_slides_c5]    -> prints one JSON line per config (profiles/r1_configs_*.json)"""
+usage: run_configs.py [c1,c2ibsi,c3,c4,c5] [n_slides_c5] [cpu]   -> prints one JSON line per config (profiles/rN_configs_*.jsonl)
+`cpu`: also time the reference's own CPU code (oracle/_ref, all host cores) for C1, C3 and C4 -- BASELINE.md section 2: C1 and
+C4 at full size, C3 GLCM + GLRLM on an 8192^2 crop (one ROI = one host thread; x4 pixels to the full slide, flagged) and C3
+GLSZM at 2048^2 (the reference materialises w*h*Ng ints, glszm.cpp:211-217: 4.3 GB there, 275 GB at 16k^2 -- it cannot run)."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,6 +16,18 @@ from nyxus_b200 import Engine, synth
 
 which = (sys.argv[1] if len(sys.argv) > 1 else "c1,c2ibsi,c3,c4,c5").split(",")
 n5 = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+do_cpu = len(sys.argv) > 3 and sys.argv[3] == "cpu"
+NT = os.cpu_count() or 1
+
+
+def cpu_line(name, fn, sample):
+    from oracle import ref
+    if not ref.available():
+        return
+    t0 = time.perf_counter()
+    n = fn(ref)
+    dt = time.perf_counter() - t0
+    print(json.dumps({"config": name, "impl": "reference (oracle/_ref, -O2)", "cores": NT, "s": dt, "rois": int(n), "sample": sample}), flush=True)
 
 
 def timed(fn, reps=3):
@@ -34,6 +49,9 @@ if "c1" in which:
                       "rois": int(tab.shape[0]), "rois_per_s": tab.shape[0] / dt, "mpix_per_s": I.size / dt / 1e6,
                       "stage_ms": {k: round(v, 3) for k, v in eng.timings().items() if v > 0.001}}), flush=True)
     eng.close()
+    if do_cpu:
+        cpu_line("C1 CPU", lambda ref: len(ref.featurize_2d(I.astype(np.uint32), L, greydepth=64, fam_mask=ref.FAM["INT"] | ref.FAM["GLCM"], nthreads=NT)[0]),
+                 "the full C1 slide, GLCM + first-order")
 
 if "c2ibsi" in which:
     # second sweep with ibsi=True on configs[1] after re-quantising the intensities to <= 256 levels
@@ -62,6 +80,15 @@ if "c3" in which:
                       "stage_ms": {k: round(v, 3) for k, v in eng.timings().items() if v > 0.001}}), flush=True)
     eng.close()
     del d_i, d_l
+    if do_cpu:
+        Ic = np.ascontiguousarray(I[:8192, :8192]).astype(np.uint32)
+        Lc = np.ascontiguousarray(L[:8192, :8192])
+        cpu_line("C3 CPU GLCM+GLRLM", lambda ref: len(ref.featurize_2d(Ic, Lc, greydepth=256, fam_mask=ref.FAM["GLCM"] | ref.FAM["GLRLM"], nthreads=NT)[0]),
+                 "8192^2 crop of the C3 slide = 1/4 of its pixels (a single ROI runs on ONE host thread); linear extrapolation to 16384^2: x4")
+        Is = np.ascontiguousarray(I[:2048, :2048]).astype(np.uint32)
+        Ls = np.ascontiguousarray(L[:2048, :2048])
+        cpu_line("C3 CPU GLSZM", lambda ref: len(ref.featurize_2d(Is, Ls, greydepth=256, fam_mask=ref.FAM["GLSZM"], nthreads=NT)[0]),
+                 "2048^2 crop (1/64 of the pixels); the reference's GLSZM allocates w*h*Ng ints: it cannot run at 16384^2")
 
 if "c4" in which:
     I, L = synth.config4()
@@ -79,6 +106,9 @@ if "c4" in which:
                       "stage_ms": {k: round(v, 3) for k, v in eng.timings().items() if v > 0.001}}), flush=True)
     eng.close()
     del d_i, d_l
+    if do_cpu:
+        cpu_line("C4 CPU", lambda ref: len(ref.featurize_3d(I.astype(np.uint32), L, greydepth=64, glszm_greydepth=64, ngtdm_greydepth=64, ngtdm_radius=1, nthreads=NT)[0]),
+                 "the full 512^3 volume, 3D GLCM / GLSZM / NGTDM + first-order, ROIs spread over the host threads")
 
 if "c5" in which:
     slides = [synth.config2(seed=100 + k) for k in range(2)]

@@ -22,4 +22,25 @@ for k, v in (("3glszm/greydepth", 64), ("3ngtdm/greydepth", 64), ("3ngtdm/radius
     e3.set_param(k, v)
 t5, _ = e3.featurize_volume(V, LV)
 e3.close()
+# round 2: PyRadiomics binning, basic morphology, the multi-device list call (two contexts on this device), a 3D cube beyond
+# the shared-memory classes (global-memory path) with the 124-neighbour NGTDM
+er = Engine(["*ALL_GLCM*", "*ALL_GLRLM*", "*ALL_GLSZM*", "*ALL_GLDM*", "*ALL_NGTDM*", "*ALL_INTENSITY*", "*BASIC_MORPHOLOGY*"])
+er.set_param("coarse_gray_depth", -24)
+t6, _ = er.featurize(I, L)
+er.close()
+from nyxus_b200.engine import featurize_list_multi
+ea, eb = Engine(["*ALL_TEXTURE*", "*ALL_INTENSITY*"]), Engine(["*ALL_TEXTURE*", "*ALL_INTENSITY*"])
+sl = [(np.ascontiguousarray(I), L), (np.ascontiguousarray(I[::-1]), np.ascontiguousarray(L[::-1])), (np.ascontiguousarray(I[:, ::-1]), np.ascontiguousarray(L[:, ::-1]))]
+t7, _ = featurize_list_multi([ea, eb], [a.ctypes.data for a, _ in sl], True, [b.ctypes.data for _, b in sl], I.shape[0], I.shape[1])
+ea.close(); eb.close()
+zz, yy, xx = np.mgrid[0:40, 0:52, 0:60]
+LB = ((((zz - 19) / 18.0) ** 2 + ((yy - 25) / 24.0) ** 2 + ((xx - 29) / 27.0) ** 2) < 1).astype(np.uint32) * 4     # cube ~ 37 x 49 x 55 > 40000 voxels
+LB[0:5, 0:6, 0:7] = 9
+VB = np.random.default_rng(8).integers(1, 2000, LB.shape).astype(np.uint16)
+e4 = Engine(["*3D_ALL_INTENSITY*", "*3D_GLCM*", "*3D_GLSZM*", "*3D_NGTDM*"], dim=3)
+for k, v in (("3glszm/greydepth", 32), ("3ngtdm/greydepth", 32), ("3ngtdm/radius", 2)):
+    e4.set_param(k, v)
+t8, _ = e4.featurize_volume(VB, LB)
+e4.close()
+print("round-2 rows", t6.shape, t7.shape, t8.shape, "finite", all(np.isfinite(t).all() for t in (t6, t7, t8)))
 print("rows", t1.shape, t2.shape, t3.shape, t4.shape, t5.shape, "finite", all(np.isfinite(t).all() for t in (t1, t2, t3, t4, t5)))
