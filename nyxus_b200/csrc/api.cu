@@ -46,6 +46,7 @@ const GroupDef g_groups2d[] = {
 	{ "*ALL_NGLDM*", 1 << FAM_NGLDM },
 	{ "*ALL_NGTDM*", 1 << FAM_NGTDM },
 	{ "*BASIC_MORPHOLOGY*", 1 << FAM_MORPH },		// featureset.cpp:654
+	{ "*ALL_IH*", 1 << FAM_IH },				// featureset.cpp:665: IBSI mode only
 	{ "*ALL_TEXTURE*", (1 << FAM_GLCM) | (1 << FAM_GLRLM) | (1 << FAM_GLDZM) | (1 << FAM_GLSZM) | (1 << FAM_GLDM) | (1 << FAM_NGLDM) | (1 << FAM_NGTDM) },
 };
 // reference featureset.cpp:940-953 (3D group names) for the 3D families on this path
@@ -227,6 +228,7 @@ struct nyxb200_ctx
 	bool feat_on[NFEATURES_MAX];
 	int fam_mask = 0;		// first-order + texture families (bits of Family)
 	bool want_morph = false;	// *BASIC_MORPHOLOGY* columns selected
+	bool want_ih = false;		// IH_* columns selected (and IBSI mode on)
 	std::vector<int> sel_cols;		// canonical column of every output column
 	std::vector<std::string> sel_names;
 	std::vector<int> sel_codes;
@@ -305,6 +307,7 @@ void rebuild_selection (nyxb200_ctx* ctx)
 	ctx->sel_codes.clear();
 	ctx->fam_mask = 0;
 	ctx->want_morph = false;
+	ctx->want_ih = false;
 	static const int angles[4] = { 0, 45, 90, 135 };
 	// enabled features in ascending code order (reference featureset.cpp getEnabledFeatures; the table is already sorted)
 	for (int i = 0; i < (int)ctx->feats.size(); i++)
@@ -312,7 +315,14 @@ void rebuild_selection (nyxb200_ctx* ctx)
 		if (!ctx->feat_on[i])
 			continue;
 		const FeatureDef& f = ctx->feats[i];
-		if (f.family == FAM_MORPH)
+		if (f.family == FAM_IH)
+		{
+			// the reference strips the IH family when IBSI compliance is off (env_features.cpp:513-527): no columns at all
+			if (!ctx->st.ibsi)
+				continue;
+			ctx->want_ih = true;
+		}
+		else if (f.family == FAM_MORPH)
 			ctx->want_morph = true;
 		else
 			ctx->fam_mask |= 1 << f.family;
@@ -624,7 +634,10 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 		ctx->glcm_greydepth_set = true;
 	}
 	else if (!strcmp (key, "ibsi"))
+	{
 		ctx->st.ibsi = iv != 0;
+		rebuild_selection (ctx);	// the IH_* columns exist in IBSI mode only
+	}
 	else if (!strcmp (key, "glcm/symmetric"))
 		ctx->st.glcm_symmetric = iv != 0;
 	else if (!strcmp (key, "soft_nan"))
@@ -1635,7 +1648,7 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : std::abs (ctx->st.coarse_gray_depth);
 	DebugOut nodbg { nullptr, nullptr, nullptr };
 	ImageView imf = im;		// the view the family kernels get (with the tile store when it is used)
-	const bool want_cloud = (ctx->fam_mask & (1 << FAM_INT)) != 0;
+	const bool want_cloud = (ctx->fam_mask & (1 << FAM_INT)) != 0 || (ctx->want_ih && !d3);
 	const bool want_tex = !d3 && (ctx->fam_mask & ~(1 << FAM_INT)) != 0;
 	// 16-bit tile codes hold 14-bit levels: MATLAB binning up to 16383 levels, IBSI (identity) up to that intensity
 	const bool tiles = want_tex && ctx->use_tile_store && info.n_tile_cells > 0 && (uint32_t)Lmax <= TILE16_LEVEL
@@ -1770,6 +1783,35 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 			{
 				const int grid = (int)std::min<uint32_t> (ccount[NCLASS], (uint32_t)ctx->sm_count * 4);
 				k_roi_morph<<<grid, ROI_THREADS, RED_WORDS * 4, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[NCLASS], ccount[NCLASS], prm, ctx->d_full.p, ncol_all);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+		}
+		if (ctx->want_ih && !d3)
+		{
+			// the IBSI intensity-histogram family reads the same CSR slices: warp per ROI for the area classes of this batch
+			// (contiguous lists), CTA per ROI for clouds above 32768 pixels
+			uint32_t nsmall = 0;
+			for (int c = 0; c < NACLASS; c++)
+				nsmall += acount[c];
+			const size_t memw = (ih_smem_words (prm.greydepth) + 3) & ~(size_t)3;
+			if (nsmall)
+			{
+				const size_t bytes = memw * 4 * ROI_WARPS;
+				if (set_smem (ctx, k_roi_ih_w, bytes))
+					return NYXB200_ECUDA;
+				const int grid = (int)std::min<uint32_t> ((nsmall + ROI_WARPS - 1) / ROI_WARPS, (uint32_t)ctx->sm_count * 8);
+				k_roi_ih_w<<<grid, ROI_THREADS, bytes, ctx->ls>>> (ctx->d_rois.p, ctx->d_alist.p + ab[0], nsmall, prm, ctx->d_cloud.p, ctx->d_full.p, ncol_all, memw);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+			if (acount[NACLASS])
+			{
+				const size_t bytes = (RED_WORDS + memw) * 4;
+				if (set_smem (ctx, k_roi_ih, bytes))
+					return NYXB200_ECUDA;
+				const int grid = (int)std::min<uint32_t> (acount[NACLASS], (uint32_t)ctx->sm_count * 4);
+				k_roi_ih<<<grid, ROI_THREADS, bytes, ctx->ls>>> (ctx->d_rois.p, ctx->d_alist.p + ab[NACLASS], acount[NACLASS], prm, ctx->d_cloud.p, ctx->d_full.p, ncol_all);
 				CU (cudaGetLastError());
 				ctx->counts[0]++;
 			}

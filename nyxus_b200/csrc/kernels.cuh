@@ -10,6 +10,7 @@
 #include "intensity_body.h"
 #include "vol_body.h"
 #include "morph_body.h"
+#include "ih_body.h"
 
 namespace nyx
 {
@@ -1066,6 +1067,37 @@ __global__ void __launch_bounds__(ROI_THREADS, 6) k_roi_intensity_w (const RoiRe
 		const uint32_t ri = list ? list[k] : k;
 		const RoiRec r = rois[ri];
 		intensity_body (c, r, prm, cloud + r.cloud_off, r.area, max (next_pow2 (r.area), 64u), mem, out + (size_t)ri * out_stride + COL_INT);
+		c.sync();
+	}
+}
+
+// *ALL_IH*: warp per ROI (CSR slices of the shared-memory area classes) / CTA per ROI (larger clouds); reads the CSR cloud
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_ih_w (const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list, uint32_t n,
+	Params prm, const uint32_t* __restrict__ cloud, double* out, int out_stride, size_t memw)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	uint32_t* mem = smem + (size_t)warp * memw;
+	Cta c { lane, 32, nullptr, 1 };
+	for (uint32_t k = blockIdx.x * ROI_WARPS + warp; k < n; k += gridDim.x * ROI_WARPS)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		const RoiRec r = rois[ri];
+		ih_body (c, r, prm, cloud + r.cloud_off, r.area, mem, out + (size_t)ri * out_stride + COL_IH);
+		c.sync();
+	}
+}
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_ih (const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list, uint32_t n,
+	Params prm, const uint32_t* __restrict__ cloud, double* out, int out_stride)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
+	uint32_t* mem = smem + RED_WORDS;
+	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		const RoiRec r = rois[ri];
+		ih_body (c, r, prm, cloud + r.cloud_off, r.area, mem, out + (size_t)ri * out_stride + COL_IH);
 		c.sync();
 	}
 }

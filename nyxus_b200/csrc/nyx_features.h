@@ -37,7 +37,11 @@ constexpr int NCOL_TEXINT = COL_NGTDM + NCOL_NGTDM;	// 337: first-order + the se
 constexpr int FAM_MORPH = FAM_COUNT;			// not a texture family: no size classes, no tile
 constexpr int NCOL_MORPH = 15;
 constexpr int COL_MORPH = NCOL_TEXINT;
-constexpr int NCOL_ALL = COL_MORPH + NCOL_MORPH;	// 352
+// *ALL_IH* (SURVEY 8f-2): the IBSI intensity-histogram family, 46 columns, IBSI mode only
+constexpr int FAM_IH = FAM_COUNT + 1;
+constexpr int NCOL_IH = 46;
+constexpr int COL_IH = COL_MORPH + NCOL_MORPH;
+constexpr int NCOL_ALL = COL_IH + NCOL_IH;		// 398
 
 // ---- first-order (Feature2D::COV .. UNIFORMITY_PIU, featureset.h:13-48)
 enum IntCol : int
@@ -55,6 +59,20 @@ enum MorphCol : int
 	MO_AREA_PIXELS_COUNT = 0, MO_AREA_UM2, MO_CENTROID_X, MO_CENTROID_Y, MO_WEIGHTED_CENTROID_Y, MO_WEIGHTED_CENTROID_X,
 	MO_MASS_DISPLACEMENT, MO_COMPACTNESS, MO_BBOX_YMIN, MO_BBOX_XMIN, MO_BBOX_HEIGHT, MO_BBOX_WIDTH, MO_DIAMETER_EQUAL_AREA,
 	MO_EXTENT, MO_ASPECT_RATIO
+};
+
+// ---- IBSI intensity histogram (Feature2D::IH_MEAN_VAL .. IH_BIN_SIZE, featureset.h:590-637)
+enum IhCol : int
+{
+	IH_MEAN_VAL = 0, IH_VARIANCE_VAL, IH_SKEWNESS_VAL, IH_EXCESS_KURTOSIS_VAL, IH_MEDIAN_VAL, IH_MINIMUM_VAL, IH_P10_VAL, IH_P90_VAL,
+	IH_MAXIMUM_VAL, IH_MODE_VAL, IH_INTERQUANTILE_RANGE_VAL, IH_RANGE_VAL, IH_MEAN_ABSOLUTE_DEVIATION_VAL,
+	IH_ROBUST_MEAN_ABSOLUTE_DEVIATION_VAL, IH_MEDIAN_ABSOLUTE_DEVIATION_VAL, IH_COEFFICIENT_OF_VARIATION_VAL,
+	IH_QUANTILE_COEFFICIENT_OF_DISPERSION_VAL, IH_ENTROPY_VAL, IH_UNIFORMITY_VAL, IH_ROBUST_MEAN_VAL, IH_MEAN_IDX, IH_VARIANCE_IDX,
+	IH_SKEWNESS_IDX, IH_EXCESS_KURTOSIS_IDX, IH_MEDIAN_IDX, IH_MINIMUM_IDX, IH_P10_IDX, IH_P90_IDX, IH_MAXIMUM_IDX, IH_MODE_IDX,
+	IH_INTERQUANTILE_RANGE_IDX, IH_RANGE_IDX, IH_MEAN_ABSOLUTE_DEVIATION_IDX, IH_ROBUST_MEAN_ABSOLUTE_DEVIATION_IDX,
+	IH_MEDIAN_ABSOLUTE_DEVIATION_IDX, IH_COEFFICIENT_OF_VARIATION_IDX, IH_QUANTILE_COEFFICIENT_OF_DISPERSION_IDX, IH_ENTROPY_IDX,
+	IH_UNIFORMITY_IDX, IH_MAX_GRADIENT, IH_MAX_GRADIENT_IDX, IH_MIN_GRADIENT, IH_MIN_GRADIENT_IDX, IH_ROBUST_MEAN_IDX, IH_NUM_BINS,
+	IH_BIN_SIZE
 };
 
 // ---- GLCM angled features in enum order (featureset.h:174-203); column = COL_GLCM + 4*f + angle

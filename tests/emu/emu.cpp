@@ -17,6 +17,7 @@
 #include "../../nyxus_b200/csrc/intensity_body.h"
 #include "../../nyxus_b200/csrc/vol_body.h"
 #include "../../nyxus_b200/csrc/morph_body.h"
+#include "../../nyxus_b200/csrc/ih_body.h"
 
 using namespace nyx;
 
@@ -272,5 +273,27 @@ extern "C" int nyxemu_morph (const uint32_t* inten, const uint32_t* lbl, int H, 
 	std::vector<double> red (RED_MAX * NW_MAX);
 	Cta c { 0, 1, red.data() };
 	morph_body (c, im, r, prm, out);
+	return 0;
+}
+
+// *ALL_IH* of a pixel cloud (IBSI mode): the 46 columns of ih_body in Feature2D code order
+extern "C" int nyxemu_ih (const uint32_t* vals, unsigned n, int greydepth, int ibsi, double* out)
+{
+	if (!n)
+		return -1;
+	RoiRec r;
+	memset (&r, 0, sizeof (r));
+	r.area = n;
+	r.imin = 0xFFFFFFFFu;
+	for (unsigned i = 0; i < n; i++)
+	{
+		r.imin = std::min (r.imin, vals[i]);
+		r.imax = std::max (r.imax, vals[i]);
+	}
+	Params prm = make_prm (greydepth, greydepth, ibsi != 0, 1);
+	std::vector<double> red (RED_MAX * NW_MAX);
+	Cta c { 0, 1, red.data() };
+	std::vector<uint32_t> mem (ih_smem_words (greydepth));
+	ih_body (c, r, prm, vals, n, mem.data(), out);
 	return 0;
 }

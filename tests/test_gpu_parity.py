@@ -587,3 +587,36 @@ def test_basic_morphology_against_reference_golden():
     from nyxus_b200 import Nyxus
     df = Nyxus(["*BASIC_MORPHOLOGY*", "MEAN"]).featurize(I, L)
     assert list(df.columns[4:6]) == ["MEAN", "AREA_PIXELS_COUNT"] and df.shape[1] == 4 + 16
+
+
+# ------------------------------------------------------------------------------------------------ *ALL_IH* 
+@pytest.mark.parametrize("g", [64, 20, 7])
+def test_intensity_histogram_family_against_reference_golden(g):
+    """golden_ih.npz = the reference's own pybind module (ibsi=True) on blobs + a constant ROI, a ROI with fewer distinct
+    values than bins and a three-spike ROI, at three grey depths"""
+    Zi = np.load(os.path.join(tu.GOLDEN, "golden_ih.npz"))
+    e = _engine(["*ALL_IH*"], ibsi=True, coarse_gray_depth=g)
+    try:
+        tab, _ = e.featurize(Zi["inten"], Zi["label"])
+        assert e.columns == [str(c) for c in Zi["columns"]]
+        assert np.array_equal(tab[:, 0].astype(np.int64), Zi["labels"])
+        bad = tu.mismatches(Zi["table_%d" % g], tab[:, 2:], e.columns)
+        assert not bad, bad[:8]
+    finally:
+        e.close()
+
+
+def test_intensity_histogram_family_needs_ibsi_and_orders_by_code():
+    Zi = np.load(os.path.join(tu.GOLDEN, "golden_ih.npz"))
+    e = _engine(["*ALL_IH*", "MEAN"], ibsi=False)           # stripped like env_features.cpp:513-527 does
+    try:
+        assert e.columns == [str(c) for c in Zi["columns_ibsi_off"]]
+        e.set_param("ibsi", 1)
+        assert len(e.columns) == 47 and e.columns[0] == "MEAN" and e.columns[1] == "IH_MEAN_VAL"
+    finally:
+        e.close()
+    e = _engine(["*ALL_IH*", "*ALL_INTENSITY*", "*BASIC_MORPHOLOGY*", "GLCM_ASM", "NGTDM_STRENGTH"], ibsi=True)
+    try:
+        assert e.columns == [str(c) for c in Zi["mixed_columns"]]
+    finally:
+        e.close()
