@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(BG_T) k_big_glrlm_build (const uint32_t* __res
 		sm[k] = 0;
 	__syncthreads();
 	unsigned long long np[1] = { 0 };
+	uint32_t maxlen[4] = { 0, 0, 0, 0 };	// longest run per angle: the reducer sweeps only the populated run lengths
 	CellIter it;
 	for (it.init (ncell, w); it.valid(); it.next (w))
 	{
@@ -396,7 +397,15 @@ __global__ void __launch_bounds__(BG_T) k_big_glrlm_build (const uint32_t* __res
 				atomicAdd (&sm[((size_t)a * Lmax + (lv - 1)) * SL + (len - 1)], 1u);
 			else
 				atomicAdd (&P[((size_t)a * Lmax + (lv - 1)) * Nr + (len - 1)], 1u);
+			maxlen[a] = (uint32_t)len > maxlen[a] ? (uint32_t)len : maxlen[a];
 		}
+	}
+#pragma unroll
+	for (int a = 0; a < 4; a++)
+	{
+		const uint32_t m = __reduce_max_sync (0xffffffffu, maxlen[a]);
+		if ((threadIdx.x & 31) == 0 && m)
+			atomicMax (&acc[BG_NACC + a], (unsigned long long)m);
 	}
 	__syncthreads();
 	for (size_t k = threadIdx.x; k < nsm; k += blockDim.x)
@@ -423,6 +432,9 @@ __global__ void __launch_bounds__(BG_T) k_big_glrlm_reduce (const uint32_t* __re
 	for (int k = c.tid; k < Lmax + Nr; k += c.nthr)
 		sm[k] = 0;
 	__syncthreads();
+	// columns beyond the longest run of this angle are empty (k_big_glrlm_build records it): a 16k x 16k slide has
+	// Nr = 16384 columns and runs of a few dozen pixels
+	const int Nre = (int)min ((unsigned long long)Nr, acc[BG_NACC + a]);
 	enum { Q_SUM, Q_LRE, Q_MUI, Q_MUJ, Q_HGL, Q_N };
 	unsigned long long q[Q_N];
 	for (int k = 0; k < Q_N; k++)
@@ -432,7 +444,7 @@ __global__ void __launch_bounds__(BG_T) k_big_glrlm_reduce (const uint32_t* __re
 	for (int k = 0; k < A_N; k++)
 		s[k] = 0;
 	for (int l = 0; l < Lmax; l++)
-		for (int j = c.tid; j < Nr; j += c.nthr)
+		for (int j = c.tid; j < Nre; j += c.nthr)
 		{
 			const unsigned long long cnt = P[(size_t)l * Nr + j];
 			if (!cnt)
@@ -469,11 +481,11 @@ __global__ void __launch_bounds__(BG_T) k_big_glrlm_reduce (const uint32_t* __re
 	unsigned long long q2[2] = { 0, 0 };
 	for (int k = c.tid; k < Lmax; k += c.nthr)
 		q2[0] += (unsigned long long)Ri[k] * Ri[k];			// :441-448
-	for (int k = c.tid; k < Nr; k += c.nthr)
+	for (int k = c.tid; k < Nre; k += c.nthr)
 		q2[1] += (unsigned long long)Cj[k] * Cj[k];			// :509-517
 	double t[3] = { 0, 0, 0 };
 	for (int l = 0; l < Lmax; l++)
-		for (int j = c.tid; j < Nr; j += c.nthr)
+		for (int j = c.tid; j < Nre; j += c.nthr)
 		{
 			const unsigned long long cnt = P[(size_t)l * Nr + j];
 			if (!cnt)

@@ -154,16 +154,24 @@ NYX_D void glszm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const
 		}
 	}
 	c.sync();
-	// flatten: lab[i] = root.  A root keeps pointing to itself, and a non-root is only ever read through find(), so the
-	// in-place rewrite is safe without a second buffer.
-	for (int i = c.tid; i < ncell; i += c.nthr)
-		if ((cell[i] & CELL_LEVEL) != skip)
-		{
-			const uint32_t root = uf16_find (lab, (uint32_t)i);
-			if (root != (uint32_t)i)
-				lab[i] = (uint16_t)root;
-		}
-	c.sync();
+	// flatten: lab[i] = root, staged through the (still all-zero) zone-size array so that no thread rewrites a parent
+	// another thread may be chasing: reads of this phase see only the final forest (round 1's in-place rewrite was
+	// correct -- a root keeps pointing to itself and parents only ever move towards it -- but it was a read/write
+	// hazard in compute-sanitizer's racecheck).  Every thread stages and copies back its own cells.
+	{
+		uint16_t* stage = (uint16_t*)zsw;
+		for (int i = c.tid; i < ncell; i += c.nthr)
+			if ((cell[i] & CELL_LEVEL) != skip)
+				stage[i] = (uint16_t)uf16_find (lab, (uint32_t)i);
+		c.sync();
+		for (int i = c.tid; i < ncell; i += c.nthr)
+			if ((cell[i] & CELL_LEVEL) != skip)
+			{
+				lab[i] = stage[i];
+				stage[i] = 0;
+			}
+		c.sync();
+	}
 	glszm_reduce (c, prm, cell, keys, cnts, mask, lab, zsw, ncell, skip, (double)r.area, out, nullptr);
 }
 
