@@ -31,7 +31,7 @@ struct FeatureDef3 { const char* name; int code; int family; int col0; };
 const FeatureDef3 g_features3d_src[] = {
 #include "nyx_feature_table3d.inc"
 };
-constexpr int NFEATURES_MAX = 256;
+constexpr int NFEATURES_MAX = 512;
 
 struct GroupDef { const char* name; int fam_mask; };
 // reference featureset.cpp:650-668 (2D group names); *ALL_TEXTURE* is defined HERE as the union of the seven 2D
@@ -717,7 +717,7 @@ size_t family_words (int fam, bool p16, int Lmax, uint32_t maxcells, int maxwh, 
 {
 	switch (fam)
 	{
-	case FAM_GLCM: return p16 ? glcm_smem_words<true> (Lmax, 4, rad) : glcm_smem_words<false> (Lmax, 4, rad);
+	case FAM_GLCM: return p16 ? glcm_smem_words<true> (Lmax, 4, rad, maxcells) : glcm_smem_words<false> (Lmax, 4, rad, maxcells);
 	case FAM_GLRLM: return glrlm_smem_words (Lmax, maxwh, (int)maxcells);
 	case FAM_GLDZM: return gldzm_smem_words (Lmax, gldzm_nd_bound (maxcells, maxwh), maxcells);
 	case FAM_GLSZM: return glszm_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));

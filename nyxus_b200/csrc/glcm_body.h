@@ -68,9 +68,10 @@ template <bool P16> NYX_HD size_t glcm_angle_words (int Ng)
 
 // shared-memory words needed by glcm_body for `na` angles held at once
 // (rad: + the level -> rank map [Ng + 1] and the rank -> level list [Ng] of PyRadiomics binning)
-template <bool P16> NYX_HD size_t glcm_smem_words (int Ng, int na, bool rad = false)
+// (listcells > 0, 2D: + the 16-bit list of the tile's non-zero cells, the only cells that can be the centre of a pair)
+template <bool P16> NYX_HD size_t glcm_smem_words (int Ng, int na, bool rad = false, uint32_t listcells = 0)
 {
-	return (size_t)na * glcm_angle_words<P16> (Ng) + (rad ? (size_t)2 * Ng + 2 : 0);
+	return (size_t)na * glcm_angle_words<P16> (Ng) + (rad ? (size_t)2 * Ng + 2 : 0) + ((size_t)listcells + 1) / 2;
 }
 
 // PyRadiomics binning (glcm.cpp:388-398, 3d_glcm.cpp:286-296): I = the sorted distinct non-zero bins of the tile / cube;
@@ -284,9 +285,12 @@ template <bool D3> struct GlcmGeom
 // glcm_rank_levels), NgRoi = |I|; formulas that use I[] take the level from Ilev[rank], the index-based ones do not change.
 template <bool P16, bool D3, bool RAD = false>
 NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec& r, const Params& prm, const uint32_t* cell,
-	uint32_t* reg, int Ng, double* out, int ostride, const GlcmDebug* dbg, const uint32_t* Ilev = nullptr, int NgRoi = 0)
+	uint32_t* reg, int Ng, double* out, int ostride, const GlcmDebug* dbg, const uint32_t* Ilev = nullptr, int NgRoi = 0,
+	const uint16_t* act = nullptr, int nact = 0)
 {
-	const int ncell = G.ncell();
+	// act / nact (2D): the tile's non-zero cells in raster order -- a pair needs a non-zero centre, so the three
+	// pair loops walk this list (every lane busy) instead of the whole bounding box (~25 % of it lies outside the ROI)
+	const int ncell = act ? nact : G.ncell();
 	const double softnan = prm.softnan;
 	const size_t jw = Counters<P16>::words ((size_t)Ng * Ng);
 	Counters<P16> J { reg };
@@ -309,8 +313,9 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	unsigned long long q[Q_CNT];
 	for (int k = 0; k < Q_CNT; k++)
 		q[k] = 0;
-	for (int i = g.tid; i < ncell; i += g.nthr)
+	for (int k = g.tid; k < ncell; k += g.nthr)
 	{
+		const int i = act ? (int)act[k] : k;
 		int b, av;
 		if (!G.pair (cell, i, b, av))
 			continue;
@@ -524,8 +529,9 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	unsigned long long s_asm = 0, jmax = 0;
 	constexpr int NJD = RAD ? 6 : 3;
 	double jd[NJD] = {};	// sum log(p_cell), sum log(px*py), sum (r-mr)(c-mc) [, RAD: cluster sums m^2, m^3, m^4 per pair]
-	for (int i = g.tid; i < ncell; i += g.nthr)
+	for (int k = g.tid; k < ncell; k += g.nthr)
 	{
+		const int i = act ? (int)act[k] : k;
 		int b, av;
 		if (!G.pair (cell, i, b, av))
 			continue;
@@ -580,8 +586,9 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	}
 	else
 #endif
-	for (int i = g.tid; i < ncell; i += g.nthr)
+	for (int k = g.tid; k < ncell; k += g.nthr)
 	{
+		const int i = act ? (int)act[k] : k;
 		int b, av;
 		if (!G.pair (cell, i, b, av))
 			continue;
@@ -639,7 +646,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 // out: NCOL_GLCM doubles of this ROI (angled block then _AVE block).  mem: 4 angle regions, zero on entry and exit.
 template <bool P16>
 NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t* cell, uint32_t* mem, int Ng,
-	double* out, const GlcmDebug* dbg)
+	double* out, const GlcmDebug* dbg, uint32_t listcells = 0)
 {
 	constexpr int NA = 4;
 	const int ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
@@ -661,14 +668,46 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 	const bool rad = !prm.ibsi && prm.greydepth < 0;
 	uint32_t* Ilev = mem + NA * aw + Ng + 1;
 	const int ngroi = rad ? glcm_rank_levels (c, cell, r.w * r.h, Ng, mem + NA * aw, Ilev) : 0;
+	// ---- the non-zero cells of the tile, raster order (one warp, ballot compaction: a deterministic list)
+	uint16_t* act = nullptr;
+	int nact = 0;
+	const int ncell = r.w * r.h;
+	if (listcells && ncell < 65536 && c.red)
+	{
+		act = (uint16_t*)(mem + NA * aw + (rad ? (size_t)2 * Ng + 2 : 0));
+#if NYX_DEVICE_BUILD
+		if (c.sub_id() == 0)
+		{
+			int run = 0;
+			for (int base = 0; base < ncell; base += g.nthr)
+			{
+				const int i = base + g.tid;
+				const bool nz = i < ncell && (cell[i] & CELL_NZ) != 0;
+				const unsigned b = g.ballot (nz);
+				if (nz)
+					act[run + popc32 (b & g.lanemask_lt())] = (uint16_t)i;
+				run += popc32 (b);
+			}
+			if (g.tid == 0)
+				c.red[0] = (double)run;
+		}
+		c.sync();
+		nact = (int)c.red[0];
+		c.sync();
+#else
+		for (int i = 0; i < ncell; i++)
+			if (cell[i] & CELL_NZ)
+				act[nact++] = (uint16_t)i;
+#endif
+	}
 	for (int a = c.sub_id(); a < NA; a += c.sub_count())
 	{
 		GlcmGeom<false> G;
 		G.init (r, a == 2 ? 0 : (a == 3 ? -o : o), a == 0 ? 0 : o, 0, false, prm.ibsi != 0);	// glcm.cpp:234-251
 		if (rad)
-			glcm_angle<P16, false, true> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg, Ilev, ngroi);
+			glcm_angle<P16, false, true> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg, Ilev, ngroi, act, nact);
 		else
-			glcm_angle<P16, false> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg);
+			glcm_angle<P16, false> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg, nullptr, 0, act, nact);
 	}
 	c.sync();
 

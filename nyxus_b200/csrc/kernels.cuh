@@ -878,7 +878,7 @@ __device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, c
 	if (FAM == FAM_GLCM)
 	{
 		GlcmDebug d { dbg.u32 };
-		glcm_body<P16> (c, r, prm, cell, mem, Lmax, o + COL_GLCM, dbg.u32 ? &d : nullptr);
+		glcm_body<P16> (c, r, prm, cell, mem, Lmax, o + COL_GLCM, dbg.u32 ? &d : nullptr, maxcells);
 	}
 	else if (FAM == FAM_GLRLM)
 	{

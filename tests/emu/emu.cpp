@@ -21,7 +21,7 @@
 
 using namespace nyx;
 
-extern "C" int nyxemu_ncols() { return NCOL_ALL; }
+extern "C" int nyxemu_ncols() { return NCOL_TEXINT; }
 
 // tile: h*w intensities, mask: h*w membership.  fam_mask bits: 1 INT, 2 GLCM, 4 GLRLM, 8 GLDZM, 16 GLSZM, 32 GLDM, 64 NGLDM, 128 NGTDM
 static int g_glcm_greydepth = INT_MIN;	// "glcm/greydepth" (2D: blank test only); INT_MIN = follows the grey depth
@@ -79,7 +79,7 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 	load_tile (c, im, r, B, cell.data());
 	const int Lmax = ibsi ? (int)r.imax : std::abs (greydepth);
 	const bool rad = !ibsi && greydepth < 0;
-	for (int i = 0; i < NCOL_ALL; i++)
+	for (int i = 0; i < NCOL_TEXINT; i++)
 		out[i] = 0;
 	if (fam_mask & 1)
 	{
@@ -92,15 +92,15 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 		int Ng = Lmax;
 		if (p16)
 		{
-			std::vector<uint32_t> mem (glcm_smem_words<true> (Ng, 4, rad));
+			std::vector<uint32_t> mem (glcm_smem_words<true> (Ng, 4, rad, (uint32_t)(r.w * r.h)));
 			std::vector<uint32_t> cellg (cell);	// (PyRadiomics binning rewrites the levels to ranks)
-			glcm_body<true> (c, r, prm, cellg.data(), mem.data(), Ng, out + COL_GLCM, nullptr);
+			glcm_body<true> (c, r, prm, cellg.data(), mem.data(), Ng, out + COL_GLCM, nullptr, (uint32_t)(r.w * r.h));
 		}
 		else
 		{
-			std::vector<uint32_t> mem (glcm_smem_words<false> (Ng, 4, rad));
+			std::vector<uint32_t> mem (glcm_smem_words<false> (Ng, 4, rad, (uint32_t)(r.w * r.h)));
 			std::vector<uint32_t> cellg (cell);
-			glcm_body<false> (c, r, prm, cellg.data(), mem.data(), Ng, out + COL_GLCM, nullptr);
+			glcm_body<false> (c, r, prm, cellg.data(), mem.data(), Ng, out + COL_GLCM, nullptr, (uint32_t)(r.w * r.h));
 		}
 	}
 	if (fam_mask & 4)
