@@ -166,8 +166,13 @@ def c5_job(args, rank, local_rank, world):
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+        store = dist.distributed_c10d._get_default_store()
         if rank != 0:
-            dist.barrier()      # rank 0 works; the others wait for it
+            # rank 0 works; the others wait for it on the rendezvous store (host side: an NCCL barrier would keep a
+            # spinning kernel on every GPU and a spinning thread on every rank's core while rank 0 uses them)
+            from datetime import timedelta
+            store.wait(["nyx_c5_done"], timedelta(minutes=30))
+            dist.barrier()
             dist.destroy_process_group()
             return
     S = args.slides
@@ -257,6 +262,7 @@ def c5_job(args, rank, local_rank, world):
     for en in engines:
         en.close()
     if world > 1:
+        store.set("nyx_c5_done", "1")
         dist.barrier()
         dist.destroy_process_group()
 

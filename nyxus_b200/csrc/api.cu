@@ -189,6 +189,7 @@ struct nyxb200_ctx
 	// pageable host slides: worker threads copy chunks into pinned slots and send them on their own streams
 	// (the driver's own pageable path stages through one thread); 0 = leave it to cudaMemcpyAsync
 	int staging_threads = 4;
+	int covered_from_scan = 0;	// 2D: COVERED_IMAGE_INTENSITY_RANGE against the scanned slide range (file-based workflows)
 	int multi_row_pad = 65536;	// slack rows of the shared table's first estimate (test knob: 0 forces the second pass)
 	static constexpr int STG_MAX = 16;
 	static constexpr size_t STG_CHUNK = (size_t)8 << 20;
@@ -652,6 +653,8 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 	}
 	else if (!strcmp (key, "tile_store"))			// test knob: 0 = family kernels bin straight from the slide
 		ctx->use_tile_store = iv != 0;
+	else if (!strcmp (key, "covered_range_from_scan"))	// 1: the slide came from a file (featurize_directory / featurize_files)
+		ctx->covered_from_scan = iv != 0;
 	else if (!strcmp (key, "multi_row_pad"))
 		ctx->multi_row_pad = iv < 0 ? 0 : iv;
 	else if (!strcmp (key, "staging_threads"))		// pageable host slides: copy threads (0 = the driver's pageable path)
@@ -1642,7 +1645,10 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	// ---- canonical table
 	CU (ctx->d_full.reserve ((size_t)nroi * ncol_all));
 	CU (cudaMemsetAsync (ctx->d_full.p, 0, (size_t)nroi * ncol_all * sizeof (double), s));
-	if (d3)	// 3d_intensity.cpp:56-61: ROI range over the scanned range of the labelled voxels (slideprops.cpp:305-327)
+	// COVERED_IMAGE_INTENSITY_RANGE: ROI range over the slide's range.  File-based workflows prescan the slide over its
+	// labelled pixels / voxels (slideprops.cpp:83-200, 305-327; 3d_intensity.cpp:56-61) -- the phase-1 scan has exactly
+	// those extrema; the in-memory montage path leaves the sentinels (-> -0.0, see intensity_body.h)
+	if (d3 || ctx->covered_from_scan)
 		prm.covered_den = (double)info.max_inten - (double)(~info.inv_min_inten);
 
 	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : std::abs (ctx->st.coarse_gray_depth);
@@ -2432,6 +2438,7 @@ int nyxb200_get_param (const nyxb200_ctx* ctx, const char* key, double* value)
 	else if (!strcmp (key, "roi_batches")) *value = ctx->roi_batches;
 	else if (!strcmp (key, "tile_store")) *value = ctx->use_tile_store;
 	else if (!strcmp (key, "staging_threads")) *value = ctx->staging_threads;
+	else if (!strcmp (key, "covered_range_from_scan")) *value = ctx->covered_from_scan;
 	else if (!strcmp (key, "3glszm/greydepth")) *value = ctx->glszm3_greydepth;
 	else if (!strcmp (key, "3ngtdm/greydepth")) *value = ctx->ngtdm3_greydepth;
 	else if (!strcmp (key, "3ngtdm/radius")) *value = ctx->ngtdm3_radius;
