@@ -395,14 +395,185 @@ void set_environment_params_imp (
 	(void)using_gpu;
 }
 
-py::tuple featurize_directory_imp (uint64_t, const std::string&, const std::string&, const std::string&, const std::string&, const std::string& = "")
+// ---- 2D image files.  Decoding is host IO outside the hot path: the reference links libtiff / z5 / dcmtk, this module
+// asks the interpreter's OpenCV (cv2.imread, IMREAD_UNCHANGED: tiled / stripped / compressed TIFF incl. OME-TIFF pages,
+// PNG, ...) and falls back to Pillow.  Integer grey images only (the floating-point dynamic-range remap of the
+// reference's loaders, image_loader.cpp, is outside this path).
+py::array_t<uint32_t> decode_image (const std::string& path, const char* what)
 {
-	outside_path ("featurize_directory (TIFF / OME-Zarr / DICOM ingest)");
+	py::object arr = py::none();
+	try
+	{
+		py::module_ cv2 = py::module_::import ("cv2");
+		arr = cv2.attr ("imread") (path, -1);
+	}
+	catch (py::error_already_set&) {}
+	if (arr.is_none())
+	{
+		try
+		{
+			py::module_ np = py::module_::import ("numpy");
+			arr = np.attr ("asarray") (py::module_::import ("PIL.Image").attr ("open") (path));
+		}
+		catch (py::error_already_set&)
+		{
+			throw std::runtime_error (std::string ("Error: cannot decode ") + what + " image " + path + " (needs OpenCV or Pillow in the interpreter)");
+		}
+	}
+	py::array a = py::array::ensure (arr);
+	if (!a || a.ndim() != 2)
+		throw std::runtime_error (std::string ("Error: ") + what + " image " + path + " is not a single-channel 2D image");
+	const char kind = a.dtype().kind();
+	if (kind == 'f')
+		throw std::runtime_error (std::string ("Error: ") + what + " image " + path + " holds floating-point pixels: the dynamic-range remap of the reference's loaders is outside the nyxus_b200 path");
+	py::module_ np = py::module_::import ("numpy");
+	if (kind == 'i' && np.attr ("min") (a).cast<long long>() < 0)
+		throw std::runtime_error (std::string ("Error: ") + what + " image " + path + " holds negative pixels (Hounsfield-type scale): outside the nyxus_b200 path");
+	return py::array_t<uint32_t, py::array::c_style | py::array::forcecast>::ensure (a);
 }
 
-py::tuple featurize_fname_lists_imp (uint64_t, const py::list&, const py::list&, bool, const std::string&, const std::string&)
+// image files of a list -> one table (reference: processDataset_2D_segmented / _wholeslide, workflow_2d_*.cpp): slides of one
+// shape go through ONE pipelined list call; COVERED_IMAGE_INTENSITY_RANGE is taken against the scanned slide range like
+// the file-based workflows do (slideprops.cpp:83-200), not against the sentinels of the in-memory montage path
+py::tuple featurize_images (Env& e, const std::vector<std::string>& ifiles, const std::vector<std::string>& mfiles, bool single_roi)
 {
-	outside_path ("featurize_files on 2D image files (TIFF / OME-Zarr / DICOM ingest)");
+	nyxb200_ctx* c = ctx_for (e);
+	const size_t n = ifiles.size();
+	std::vector<py::array_t<uint32_t>> I (n), M (n);
+	bool same_shape = true;
+	for (size_t k = 0; k < n; k++)
+	{
+		I[k] = decode_image (ifiles[k], "intensity");
+		if (single_roi)
+		{
+			M[k] = py::array_t<uint32_t> ({ I[k].shape (0), I[k].shape (1) });
+			std::fill (M[k].mutable_data(), M[k].mutable_data() + M[k].size(), 1u);		// whole slide = ROI 1
+		}
+		else
+		{
+			M[k] = decode_image (mfiles[k], "mask");
+			if (M[k].shape (0) != I[k].shape (0) || M[k].shape (1) != I[k].shape (1))
+				throw std::runtime_error ("Error: intensity / mask image size mismatch: " + ifiles[k] + " vs " + mfiles[k]);
+		}
+		same_shape = same_shape && I[k].shape (0) == I[0].shape (0) && I[k].shape (1) == I[0].shape (1);
+	}
+	struct Restore
+	{
+		nyxb200_ctx* c;
+		~Restore() { nyxb200_set_param (c, "covered_range_from_scan", 0); }
+	} restore { c };
+	nyxb200_set_param (c, "covered_range_from_scan", 1);
+	py::module_ np = py::module_::import ("numpy");
+	py::array header = header_array (c);
+	const std::vector<std::string> mnames = single_roi ? std::vector<std::string> (n, "") : mfiles;
+	if (same_shape)
+	{
+		std::vector<const void*> ip (n);
+		std::vector<const uint32_t*> lp (n);
+		for (size_t k = 0; k < n; k++)
+		{
+			ip[k] = I[k].data();
+			lp[k] = M[k].data();
+		}
+		nyxb200_table t {};
+		const int32_t* row_image = nullptr;
+		int rc;
+		{
+			py::gil_scoped_release nogil;
+			rc = nyxb200_featurize_2d_list (c, ip.data(), 0, lp.data(), 0, (int)n, I[0].shape (0), I[0].shape (1), &t, &row_image);
+		}
+		if (rc != NYXB200_OK)
+			throw std::runtime_error (std::string ("Error occurred during dataset processing: ") + nyxb200_last_error (c));
+		const int64_t nrows = t.nrows;
+		py::array strs = string_columns (ifiles, mnames, row_image, nrows);
+		return py::make_tuple (header, strs, table_to_numpy (c, t));
+	}
+	py::list str_parts, num_parts;
+	for (size_t k = 0; k < n; k++)
+	{
+		nyxb200_table t {};
+		const int32_t* row_image = nullptr;
+		int rc;
+		{
+			py::gil_scoped_release nogil;
+			rc = nyxb200_featurize_2d_u32 (c, I[k].data(), M[k].data(), 1, I[k].shape (0), I[k].shape (1), &t, &row_image);
+		}
+		if (rc != NYXB200_OK)
+			throw std::runtime_error (std::string ("Error occurred during dataset processing: ") + nyxb200_last_error (c));
+		const int64_t nrows = t.nrows;
+		str_parts.append (string_columns ({ ifiles[k] }, { mnames[k] }, row_image, nrows));
+		num_parts.append (table_to_numpy (c, t));
+	}
+	return py::make_tuple (header, np.attr ("concatenate") (str_parts, py::arg ("axis") = 0), np.attr ("concatenate") (num_parts, py::arg ("axis") = 0));
+}
+
+py::tuple featurize_fname_lists_imp (uint64_t instid, const py::list& int_fnames, const py::list& seg_fnames, bool single_roi,
+	const std::string& output_type, const std::string& output_path)
+{
+	Env& e = findenv (instid);
+	if (e.dim != 2)
+		throw std::runtime_error ("featurize_fname_lists_imp needs a 2D instance");
+	e.single_roi = single_roi;
+	check_output_type (output_type);
+	(void)output_path;
+	std::vector<std::string> ifiles, mfiles;
+	for (auto it : int_fnames) ifiles.push_back (it.cast<std::string>());
+	// reference :664-676, :709-723
+	if (ifiles.size() == 0)
+		throw std::runtime_error ("Intensity file list is blank");
+	for (auto& f : ifiles)
+		if (!fs::exists (f))
+			throw std::runtime_error ("File does not exist: " + f);
+	if (!single_roi)
+	{
+		for (auto it : seg_fnames) mfiles.push_back (it.cast<std::string>());
+		if (ifiles.size() != mfiles.size())
+			throw std::runtime_error ("Imbalanced intensity (" + std::to_string (ifiles.size()) + " items) and segmentation mask (" + std::to_string (mfiles.size()) + " items) file lists");
+		for (auto& f : mfiles)
+			if (!fs::exists (f))
+				throw std::runtime_error ("File does not exist: " + f);
+	}
+	return featurize_images (e, ifiles, mfiles, single_roi);
+}
+
+py::tuple featurize_directory_imp (uint64_t instid, const std::string& intensity_dir, const std::string& labels_dir,
+	const std::string& file_pattern, const std::string& output_type, const std::string& output_path = "")
+{
+	Env& e = findenv (instid);
+	if (e.dim != 2)
+		throw std::runtime_error ("featurize_directory_imp needs a 2D instance");
+	check_output_type (output_type);
+	(void)output_path;
+	std::regex rx;
+	try
+	{
+		rx = std::regex (file_pattern);
+	}
+	catch (const std::regex_error&)
+	{
+		throw std::invalid_argument ("Invalid filepattern " + file_pattern);		// reference :236-237
+	}
+	const bool single = intensity_dir == labels_dir;	// whole-slide flag (reference :244-248)
+	e.single_roi = single;
+	std::vector<std::string> names;
+	for (auto& ent : fs::directory_iterator (intensity_dir))
+		if (ent.is_regular_file() && std::regex_match (ent.path().filename().string(), rx))
+			names.push_back (ent.path().filename().string());
+	std::sort (names.begin(), names.end());
+	if (names.empty())
+		throw std::runtime_error ("Error reading the dataset: no files in " + intensity_dir + " match " + file_pattern);
+	std::vector<std::string> ifiles, mfiles;
+	for (auto& nm : names)
+	{
+		ifiles.push_back ((fs::path (intensity_dir) / nm).string());
+		if (!single)
+		{
+			mfiles.push_back ((fs::path (labels_dir) / nm).string());
+			if (!fs::exists (mfiles.back()))
+				throw std::runtime_error ("Error reading the dataset: missing mask file " + mfiles.back());
+		}
+	}
+	return featurize_images (e, ifiles, mfiles, single);
 }
 
 py::tuple featurize_montage_imp (

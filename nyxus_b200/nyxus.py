@@ -157,6 +157,82 @@ class Nyxus:
         return df
 
 
+    # ---- file-based entry points (reference nyxus.py:303-384, 524-600; new_bindings_py.cpp:224-384, 647-752)
+    def featurize_files(self, intensity_files: list, mask_files: list, single_roi: bool, output_type: Optional[str] = "pandas",
+                        output_path: Optional[str] = ""):
+        """Features of intensity / mask image file pairs (single_roi: every intensity image is one whole-slide ROI)."""
+        import os
+        from . import imageio
+        if intensity_files is None:
+            raise IOError("The list of intensity file paths is empty")
+        if mask_files is None:
+            raise IOError("The list of segment file paths is empty")
+        if output_type not in self._valid_output_types:
+            raise ValueError(f'Invalid output type {output_type}. Valid output types are {self._valid_output_types}.')
+        if output_type != 'pandas':
+            raise ValueError("arrowipc / parquet writers are outside the texture/intensity path implemented by nyxus_b200")
+        if len(intensity_files) == 0:
+            raise RuntimeError("Intensity file list is blank")
+        if not single_roi and len(intensity_files) != len(mask_files):
+            raise RuntimeError(f"Imbalanced intensity ({len(intensity_files)} items) and segmentation mask ({len(mask_files)} items) file lists")
+        for f in list(intensity_files) + ([] if single_roi else list(mask_files)):
+            if not os.path.exists(f):
+                raise RuntimeError(f"File does not exist: {f}")
+        eng = self._engine
+        frames = []
+        eng.set_param("covered_range_from_scan", 1)      # file-based: the slide's range is the scanned one (slideprops.cpp:83-200)
+        try:
+            for k, ifile in enumerate(intensity_files):
+                I = imageio.read_image(ifile, "intensity")
+                if single_roi:
+                    M = np.ones(I.shape, np.uint32)       # whole slide = ROI 1
+                    mname = ""
+                else:
+                    M = imageio.read_image(mask_files[k], "mask").astype(np.uint32, copy=False)
+                    mname = os.path.basename(mask_files[k])
+                    if M.shape != I.shape:
+                        raise ValueError(f"intensity / mask image size mismatch: {ifile} {I.shape} vs {mask_files[k]} {M.shape}")
+                if self._mergerois:
+                    M = (M != 0).astype(np.uint32)
+                numeric, row_img = eng.featurize(I, M, copy="detach")
+                header = ["intensity_image", "mask_image", "ROI_label", "t_index"] + eng.columns
+                df = pd.DataFrame(numeric, columns=header[2:], copy=False)
+                df.insert(0, "mask_image", [mname] * len(df))
+                df.insert(0, "intensity_image", [os.path.basename(ifile)] * len(df))
+                frames.append(df)
+        finally:
+            eng.set_param("covered_range_from_scan", 0)
+        df = pd.concat(frames, axis=0, ignore_index=True)
+        if "ROI_label" in df.columns:
+            df.ROI_label = df.ROI_label.astype(np.uint32)
+        self.error_message = ''
+        return df
+
+    def featurize_directory(self, intensity_dir: str, label_dir: Optional[str] = None, file_pattern: Optional[str] = ".*",
+                            output_type: Optional[str] = "pandas", output_path: Optional[str] = ""):
+        """Features of the images of `intensity_dir` whose names match `file_pattern`, masks of the same names in `label_dir`
+        (None or the same directory: every image is one whole-slide ROI)."""
+        import os
+        import re
+        if not os.path.exists(intensity_dir):
+            raise IOError(f"Provided intensity image directory '{intensity_dir}' does not exist.")
+        if label_dir is not None and not os.path.exists(label_dir):
+            raise IOError(f"Provided label image directory '{label_dir}' does not exist.")
+        if label_dir is None:
+            label_dir = intensity_dir
+        single = os.path.abspath(label_dir) == os.path.abspath(intensity_dir)
+        try:
+            rx = re.compile(file_pattern)
+        except re.error:
+            raise ValueError("Invalid filepattern " + file_pattern)
+        names = sorted(f for f in os.listdir(intensity_dir) if rx.fullmatch(f) and os.path.isfile(os.path.join(intensity_dir, f)))
+        if not names:
+            raise RuntimeError(f"Error reading the dataset: no files in {intensity_dir} match {file_pattern}")
+        ifiles = [os.path.join(intensity_dir, f) for f in names]
+        mfiles = [] if single else [os.path.join(label_dir, f) for f in names]
+        return self.featurize_files(ifiles, mfiles, single, output_type, output_path)
+
+
 _VALID_KEYS_3D = {
     'neighbor_distance', 'pixels_per_micron', 'coarse_gray_depth',
     'n_feature_calc_threads', 'use_gpu_device', 'ibsi', 'channel_signature',

@@ -119,3 +119,60 @@ def test_reference_nyxus3d_featurize_files_over_both_backends(tmp_path):
             n.set_metaparam(mp)
         return n.featurize_files([f[0] for f in files], [f[1] for f in files], False)
     _frames_match(run(ref_nyxus), run(our_nyxus))
+
+
+def _write_tiffs(tmp_path, n=3, same_shape=True):
+    import cv2
+    from nyxus_b200 import synth
+    idir, sdir = tmp_path / "int", tmp_path / "seg"
+    idir.mkdir()
+    sdir.mkdir()
+    slides = []
+    for k in range(n):
+        H, W = (160, 192) if same_shape or k % 2 == 0 else (128, 224)
+        I, L = synth.blob_slide(H, W, 32, 7, 12, seed=60 + k, jitter=1)
+        name = "p0_y1_r%d_c0.ome.tif" % k
+        assert cv2.imwrite(str(idir / name), I.astype(np.uint16))
+        assert cv2.imwrite(str(sdir / name), L.astype(np.uint16))
+        slides.append((name, I.astype(np.uint32), L.astype(np.uint32)))
+    (idir / "notes.txt").write_text("not an image")
+    return str(idir), str(sdir), slides
+
+
+@pytest.mark.skipif(not pyref.reference_available(), reason="oracle/_ref/pyref (the reference's compiled backend) not built")
+@pytest.mark.parametrize("same_shape", [True, False])
+def test_file_based_entry_points_2d(tmp_path, same_shape):
+    """featurize_directory / featurize_files on TIFF files (new_bindings_py.cpp:224-384, 647-752): the reference's nyxus.py over
+    the product's backend module AND the product's own Python mirror against the reference's in-memory featurize() of the
+    decoded arrays (the oracle build has no libtiff).  COVERED_IMAGE_INTENSITY_RANGE is the one column that differs by
+    design between the in-memory and the file-based workflow: file-based, the denominator is the slide's scanned range
+    over its labelled pixels (slideprops.cpp:83-200)."""
+    pytest.importorskip("cv2")
+    idir, sdir, slides = _write_tiffs(tmp_path, 3, same_shape)
+    feats = ["*ALL_GLCM*", "*ALL_GLSZM*", "*ALL_NGTDM*", "*ALL_INTENSITY*", "*BASIC_MORPHOLOGY*"]
+    ref_nyxus, our_nyxus = pyref.reference(), pyref.reference_on_b200()
+    refn = ref_nyxus.Nyxus(feats)
+    want = []
+    for name, I, L in slides:
+        df = refn.featurize(I.copy(), L.copy(), [name], [name])
+        fg = I[L > 0].astype(np.float64)
+        df["COVERED_IMAGE_INTENSITY_RANGE"] = (df["MAX"] - df["MIN"]) / (fg.max() - fg.min())
+        want.append(df)
+    import pandas as pd
+    want = pd.concat(want, axis=0, ignore_index=True)
+    on_b200 = our_nyxus.Nyxus(feats)
+    got_dir = on_b200.featurize_directory(idir, sdir, r".*\.ome\.tif")
+    _frames_match(want, got_dir)
+    got_files = on_b200.featurize_files([os.path.join(idir, s[0]) for s in slides], [os.path.join(sdir, s[0]) for s in slides], False)
+    _frames_match(want, got_files)
+    # the in-memory path still reports the sentinel ratio (-0.0 -> 0) afterwards
+    mem = on_b200.featurize(slides[0][1].copy(), slides[0][2].copy())
+    assert (mem["COVERED_IMAGE_INTENSITY_RANGE"] == 0).all()
+    from nyxus_b200 import Nyxus
+    mirror = Nyxus(feats)
+    _frames_match(want, mirror.featurize_directory(idir, sdir, r".*\.ome\.tif"))
+    # whole-slide mode: one ROI per image, label 1
+    ws = on_b200.featurize_files([os.path.join(idir, slides[0][0])], [], True)
+    assert ws.shape[0] == 1 and int(ws.ROI_label[0]) == 1 and ws.AREA_PIXELS_COUNT[0] == slides[0][1].size
+    with pytest.raises(RuntimeError, match="File does not exist"):
+        on_b200.featurize_files([os.path.join(idir, "nope.tif")], [os.path.join(sdir, "nope.tif")], False)
