@@ -3,7 +3,7 @@
 // Same module name, same 23 functions, same positional signatures and the same return shapes as the reference's
 // src/nyx/python/new_bindings_py.cpp:1090-1116, so the reference's own Python layer (src/nyx/python/nyxus/nyxus.py,
 // `from .backend import ...`) drives the B200 path unmodified.  What is on the texture + intensity path is computed by
-// libnyxus_b200.so; what is outside it (TIFF / OME-Zarr / DICOM ingest, nested ROIs, Arrow writers, ROI blacklists)
+// libnyxus_b200.so; what is outside it (OME-Zarr / DICOM ingest, nested ROIs, Arrow writers, ROI blacklists)
 // raises the way the reference raises for a build without that component.  There is no CPU fallback: everything that
 // computes needs an sm_100 device, and `use_gpu_device = -1` (the reference's "CPU") means "device 0" here.
 //
