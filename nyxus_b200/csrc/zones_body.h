@@ -186,7 +186,7 @@ NYX_HD size_t glszm_smem_words (uint32_t maxcells, uint32_t slots)
 }
 
 NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, uint32_t* keys, uint32_t* cnts, uint32_t mask,
-	const uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg);
+	uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg);
 
 NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, uint32_t maxcells,
 	uint32_t slots, double* out, const ZoneDebug* dbg)
@@ -302,7 +302,7 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 // Common tail of 2D and 3D GLSZM.  lab[i] = zone id (cell index of the zone's representative) of every cell whose level is
 // not `skip`; zsw: zeroed packed u16 size counters.  np_fixed >= 0 overrides Np (3D: the voxel-cloud size, 3d_glszm.cpp:534).
 NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, uint32_t* keys, uint32_t* cnts, uint32_t mask,
-	const uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg)
+	uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg)
 {
 	const uint16_t* zs = (const uint16_t*)zsw;
 	const uint32_t slots = mask + 1;
@@ -317,6 +317,30 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 		}
 	c.sync();
 
+	// ---- warp per ROI: compact the seeds (cells that are their own label) into a list, IN PLACE over the label array --
+	// the labels are dead once the sizes are counted, a list slot is never above the cell it came from, and a warp walks
+	// the cells 32 at a time (every lane has read its label before the ballot).  The two passes over the zones then run
+	// with every lane busy instead of skipping the ~45 % of the cells that are not seeds.
+	int nseed = -1;
+#if NYX_DEVICE_BUILD
+	if (c.wmode)
+	{
+		int run = 0;
+		for (int base = 0; base < ncell; base += 32)
+		{
+			const int i = base + c.tid;
+			const bool seed = i < ncell && (cell[i] & CELL_LEVEL) != skip && lab[i] == (uint32_t)i;
+			const unsigned b = __ballot_sync (0xffffffffu, seed);
+			if (seed)
+				lab[run + __popc (b & ((1u << c.tid) - 1u))] = (uint16_t)i;
+			run += __popc (b);
+			__syncwarp();
+		}
+		nseed = run;
+	}
+#endif
+	const int nloop = nseed >= 0 ? nseed : ncell;
+
 	// ---- pass 1 over the zones (= seed cells): matrix cell (level,size) and both marginals into the hash; direct sums
 	enum { Q_NZ, Q_LAE, Q_MUJ, Q_MUI, Q_HGL, Q_NP, Q_N };
 	unsigned long long q[Q_N];
@@ -327,10 +351,11 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 	double s[A_N];
 	for (int k = 0; k < A_N; k++)
 		s[k] = 0;
-	for (int i = c.tid; i < ncell; i += c.nthr)
+	for (int k = c.tid; k < nloop; k += c.nthr)
 	{
+		const int i = nseed >= 0 ? (int)lab[k] : k;
 		const uint32_t lv = cell[i] & CELL_LEVEL;
-		if (lv == skip || lab[i] != (uint32_t)i)
+		if (nseed < 0 && (lv == skip || lab[i] != (uint32_t)i))
 			continue;
 		const uint32_t sz = zs[i];
 		htab_add (c, keys, cnts, mask, (lv << 16) | sz);
@@ -362,10 +387,11 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 	// ---- pass 2: terms that need the counts (owner computes)
 	unsigned long long q2[2] = { 0, 0 };	// sum n_level^2 (:450-454), sum n_size^2 (:481-485)
 	double t[3] = { 0, 0, 0 };		// GLV, ZV, ZE
-	for (int i = c.tid; i < ncell; i += c.nthr)
+	for (int k = c.tid; k < nloop; k += c.nthr)
 	{
+		const int i = nseed >= 0 ? (int)lab[k] : k;
 		const uint32_t lv = cell[i] & CELL_LEVEL;
-		if (lv == skip || lab[i] != (uint32_t)i)
+		if (nseed < 0 && (lv == skip || lab[i] != (uint32_t)i))
 			continue;
 		const uint32_t sz = zs[i];
 		q2[0] += htab_get (keys, cnts, mask, lv << 16);
@@ -549,6 +575,27 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	}
 	c.sync();
 
+	// ---- warp per ROI: the roots compacted into a list, in place over the parent array (dead from here on; see glszm_reduce)
+	int nroot = -1;
+#if NYX_DEVICE_BUILD
+	if (c.wmode)
+	{
+		int run = 0;
+		for (int base = 0; base < ncell; base += 32)
+		{
+			const int i = base + c.tid;
+			const bool root = i < ncell && !(ibsi && !(cell[i] & CELL_LEVEL)) && parent[i] == (uint32_t)i;
+			const unsigned b = __ballot_sync (0xffffffffu, root);
+			if (root)
+				parent[run + __popc (b & ((1u << c.tid) - 1u))] = (uint32_t)i;
+			run += __popc (b);
+			__syncwarp();
+		}
+		nroot = run;
+	}
+#endif
+	const int nloop = nroot >= 0 ? nroot : ncell;
+
 	// ---- pass 1 over the zones (= roots)
 	enum { Q_NS, Q_LDE, Q_ZDM, Q_GLM, Q_HGL, Q_N };
 	unsigned long long q[Q_N];
@@ -558,10 +605,11 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	double s[A_N];
 	for (int k = 0; k < A_N; k++)
 		s[k] = 0;
-	for (int i = c.tid; i < ncell; i += c.nthr)
+	for (int k = c.tid; k < nloop; k += c.nthr)
 	{
+		const int i = nroot >= 0 ? (int)parent[k] : k;
 		const uint32_t lv = cell[i] & CELL_LEVEL;
-		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
+		if (nroot < 0 && ((ibsi && !lv) || parent[i] != (uint32_t)i))
 			continue;
 		const uint32_t dd = zmin[i];
 		P.inc (c, (int)(lv * (uint32_t)Nd + dd));
@@ -585,10 +633,11 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	// ---- pass 2: terms that need the counts (owner computes)
 	unsigned long long q2[2] = { 0, 0 };	// sum n_level^2 (:423), sum n_metric^2 (:404)
 	double t[3] = { 0, 0, 0 };		// GLV, ZDV, ZDE
-	for (int i = c.tid; i < ncell; i += c.nthr)
+	for (int k = c.tid; k < nloop; k += c.nthr)
 	{
+		const int i = nroot >= 0 ? (int)parent[k] : k;
 		const uint32_t lv = cell[i] & CELL_LEVEL;
-		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
+		if (nroot < 0 && ((ibsi && !lv) || parent[i] != (uint32_t)i))
 			continue;
 		const uint32_t dd = zmin[i];
 		q2[0] += Ri[lv];
@@ -606,10 +655,11 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		wipe_words (c, mem, gldzm_p_words (Lmax, Nd) + (Lmax + 1) + Nd);
 	else
 	{
-		for (int i = c.tid; i < ncell; i += c.nthr)
+		for (int k = c.tid; k < nloop; k += c.nthr)
 		{
+			const int i = nroot >= 0 ? (int)parent[k] : k;
 			const uint32_t lv = cell[i] & CELL_LEVEL;
-			if ((ibsi && !lv) || parent[i] != (uint32_t)i)
+			if (nroot < 0 && ((ibsi && !lv) || parent[i] != (uint32_t)i))
 				continue;
 			P.clear ((int)(lv * (uint32_t)Nd + zmin[i]));
 		}
