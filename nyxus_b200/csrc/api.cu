@@ -230,6 +230,7 @@ struct nyxb200_ctx
 	int fam_mask = 0;		// first-order + texture families (bits of Family)
 	bool want_morph = false;	// *BASIC_MORPHOLOGY* columns selected
 	bool want_ih = false;		// IH_* columns selected (and IBSI mode on)
+	int geom_variants = 0;		// geometric moments selected: bit 0 shape (SPAT_ / CENTRAL_ / NORM_ / HU_M), bit 1 intensity (IMOM_)
 	std::vector<int> sel_cols;		// canonical column of every output column
 	std::vector<std::string> sel_names;
 	std::vector<int> sel_codes;
@@ -309,6 +310,7 @@ void rebuild_selection (nyxb200_ctx* ctx)
 	ctx->fam_mask = 0;
 	ctx->want_morph = false;
 	ctx->want_ih = false;
+	ctx->geom_variants = 0;
 	static const int angles[4] = { 0, 45, 90, 135 };
 	// enabled features in ascending code order (reference featureset.cpp getEnabledFeatures; the table is already sorted)
 	for (int i = 0; i < (int)ctx->feats.size(); i++)
@@ -325,6 +327,8 @@ void rebuild_selection (nyxb200_ctx* ctx)
 		}
 		else if (f.family == FAM_MORPH)
 			ctx->want_morph = true;
+		else if (f.family == FAM_GEOM)
+			ctx->geom_variants |= f.col0 < COL_GEOM + GM_NCOL ? 1 : 2;
 		else
 			ctx->fam_mask |= 1 << f.family;
 		for (int k = 0; k < f.ncols; k++)
@@ -379,6 +383,15 @@ int resolve_features (int dim, const std::vector<FeatureDef>& feats, const char*
 			}
 		if (found)
 			continue;
+		if (!d3)
+			for (const char* g : { "*GEOMOMS*", "*IGEOMOMS*", "*SGEOMOMS*" })
+				if (!strcmp (g, s))
+				{
+					msg = std::string ("feature group '") + s + "' contains the distance-to-contour WEIGHTED moments, which are not built; "
+						"select the unweighted moments by name (SPAT_MOMENT_pq, CENTRAL_MOMENT_pq, NORM_SPAT_MOMENT_pq, NORM_CENTRAL_MOMENT_pq, HU_Mk, "
+						"IMOM_RM_pq, IMOM_CM_pq, IMOM_NRM_pq, IMOM_NCM_pq, IMOM_HUk)";
+					return NYXB200_EUNSUPPORTED;
+				}
 		if (d3)
 			for (const char* g : g_groups3d_unbuilt)
 				if (!strcmp (g, s))
@@ -1789,6 +1802,25 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 			{
 				const int grid = (int)std::min<uint32_t> (ccount[NCLASS], (uint32_t)ctx->sm_count * 4);
 				k_roi_morph<<<grid, ROI_THREADS, RED_WORDS * 4, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[NCLASS], ccount[NCLASS], prm, ctx->d_full.p, ncol_all);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+		}
+		if (ctx->geom_variants && !d3)
+		{
+			uint32_t nsmall = 0;
+			for (int c = 0; c < NCLASS; c++)
+				nsmall += ccount[c];
+			if (nsmall)
+			{
+				k_roi_geom_w<<<(nsmall * 32 + 255) / 256, 256, 0, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[0], nsmall, ctx->geom_variants, ctx->d_full.p, ncol_all);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+			if (ccount[NCLASS])
+			{
+				const int grid = (int)std::min<uint32_t> (ccount[NCLASS], (uint32_t)ctx->sm_count * 4);
+				k_roi_geom<<<grid, ROI_THREADS, RED_WORDS * 4, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[NCLASS], ccount[NCLASS], ctx->geom_variants, ctx->d_full.p, ncol_all);
 				CU (cudaGetLastError());
 				ctx->counts[0]++;
 			}

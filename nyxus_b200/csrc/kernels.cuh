@@ -11,6 +11,7 @@
 #include "vol_body.h"
 #include "morph_body.h"
 #include "ih_body.h"
+#include "geomom_body.h"
 
 namespace nyx
 {
@@ -1067,6 +1068,30 @@ __global__ void __launch_bounds__(ROI_THREADS, 6) k_roi_intensity_w (const RoiRe
 		const uint32_t ri = list ? list[k] : k;
 		const RoiRec r = rois[ri];
 		intensity_body (c, r, prm, cloud + r.cloud_off, r.area, max (next_pow2 (r.area), 64u), mem, out + (size_t)ri * out_stride + COL_INT);
+		c.sync();
+	}
+}
+
+// unweighted geometric moments: warp per ROI (shared-memory size classes) / CTA per ROI (larger); reads the slide
+__global__ void __launch_bounds__(256) k_roi_geom_w (ImageView im, const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+	uint32_t n, int variants, double* out, int out_stride)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	if (warp >= n)
+		return;
+	const uint32_t ri = list ? list[warp] : warp;
+	Cta c { (int)(threadIdx.x & 31), 32, nullptr, 1 };
+	geomom_body (c, im, rois[ri], variants, out + (size_t)ri * out_stride + COL_GEOM);
+}
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_geom (ImageView im, const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+	uint32_t n, int variants, double* out, int out_stride)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
+	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		geomom_body (c, im, rois[ri], variants, out + (size_t)ri * out_stride + COL_GEOM);
 		c.sync();
 	}
 }

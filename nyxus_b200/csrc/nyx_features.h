@@ -41,7 +41,13 @@ constexpr int COL_MORPH = NCOL_TEXINT;
 constexpr int FAM_IH = FAM_COUNT + 1;
 constexpr int NCOL_IH = 46;
 constexpr int COL_IH = COL_MORPH + NCOL_MORPH;
-constexpr int NCOL_ALL = COL_IH + NCOL_IH;		// 398
+// unweighted geometric moments: shape variant (SPAT_MOMENT_* ... HU_M*) then intensity variant (IMOM_*),
+// each RM[13] | CM[16] | NRM[16] | NCM[7] | HU[7]
+constexpr int FAM_GEOM = FAM_COUNT + 2;
+constexpr int GM_NCOL = 13 + 16 + 16 + 7 + 7;		// 59
+constexpr int NCOL_GEOMOM = 2 * GM_NCOL;
+constexpr int COL_GEOM = COL_IH + NCOL_IH;
+constexpr int NCOL_ALL = COL_GEOM + NCOL_GEOMOM;	// 516
 
 // ---- first-order (Feature2D::COV .. UNIFORMITY_PIU, featureset.h:13-48)
 enum IntCol : int

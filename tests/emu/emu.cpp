@@ -18,6 +18,7 @@
 #include "../../nyxus_b200/csrc/vol_body.h"
 #include "../../nyxus_b200/csrc/morph_body.h"
 #include "../../nyxus_b200/csrc/ih_body.h"
+#include "../../nyxus_b200/csrc/geomom_body.h"
 
 using namespace nyx;
 
@@ -295,5 +296,34 @@ extern "C" int nyxemu_ih (const uint32_t* vals, unsigned n, int greydepth, int i
 	Cta c { 0, 1, red.data() };
 	std::vector<uint32_t> mem (ih_smem_words (greydepth));
 	ih_body (c, r, prm, vals, n, mem.data(), out);
+	return 0;
+}
+
+// unweighted geometric moments of the ROI `lab` of a labelled uint32 slide: 118 columns (shape variant, intensity variant)
+extern "C" int nyxemu_geomom (const uint32_t* inten, const uint32_t* lbl, int H, int W, unsigned lab, double* out)
+{
+	RoiRec r;
+	memset (&r, 0, sizeof (r));
+	r.label = lab;
+	r.imin = 0xFFFFFFFFu;
+	int x0 = W, x1 = -1, y0 = H, y1 = -1;
+	for (int y = 0; y < H; y++)
+		for (int x = 0; x < W; x++)
+			if (lbl[(size_t)y * W + x] == lab)
+			{
+				const uint32_t v = inten[(size_t)y * W + x];
+				r.area++;
+				r.imin = std::min (r.imin, v);
+				r.imax = std::max (r.imax, v);
+				x0 = std::min (x0, x); x1 = std::max (x1, x);
+				y0 = std::min (y0, y); y1 = std::max (y1, y);
+			}
+	if (!r.area)
+		return -1;
+	r.x0 = x0; r.y0 = y0; r.w = x1 - x0 + 1; r.h = y1 - y0 + 1; r.d = 1;
+	ImageView im { inten, lbl, H, W, 0 };
+	std::vector<double> red (RED_MAX * NW_MAX);
+	Cta c { 0, 1, red.data() };
+	geomom_body (c, im, r, 3, out);
 	return 0;
 }

@@ -65,6 +65,15 @@ def mismatches(ref, got, cols=None, rtol=RTOL, atol=ATOL):
                     H = np.maximum(np.abs(a[..., k]), np.abs(b[..., k]))
                     f = np.maximum(np.maximum(np.abs(a[..., j]), np.abs(b[..., j])), 1e-30)
                     scale[..., j] = np.maximum(scale[..., j], np.minimum(2.0 * H / f, 1e4))
+            # first-order CENTRAL moments (CENTRAL_MOMENT_01 / _10, IMOM_CM_01 / _10) are identically zero: sum I (x - ox) with
+            # ox = m10 / m00; what either side returns is the round-off residue of sums whose terms have the magnitude
+            # sqrt (mu20 * mu00) resp. sqrt (mu02 * mu00) (Cauchy-Schwarz) -- the tolerance is relative to that
+            for first, second in (("_01", "_02"), ("_10", "_20")):
+                if (c.startswith("CENTRAL_MOMENT") or c.startswith("IMOM_CM")) and c.endswith(first):
+                    c2, c0 = c[:-3] + second, c[:-3] + "_00"
+                    if c2 in names and c0 in names:
+                        k2, k0 = names.index(c2), names.index(c0)
+                        scale[..., j] = np.maximum(scale[..., j], np.sqrt(np.abs(a[..., k2] * a[..., k0])))
     bad = diff > atol + rtol * scale
     out = []
     for idx in zip(*np.nonzero(bad)):

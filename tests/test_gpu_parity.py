@@ -620,3 +620,28 @@ def test_intensity_histogram_family_needs_ibsi_and_orders_by_code():
         assert e.columns == [str(c) for c in Zi["mixed_columns"]]
     finally:
         e.close()
+
+
+# ------------------------------------------------------------------------------------------------ geometric moments
+def test_unweighted_geometric_moments_against_reference_golden():
+    """golden_geomom.npz = the reference's own pybind module: the 118 unweighted shape / intensity moments (raw, central,
+    normalised raw, normalised central, Hu).  The contour-weighted moments are refused by name and by group."""
+    Zg = np.load(os.path.join(tu.GOLDEN, "golden_geomom.npz"))
+    cols = [str(c) for c in Zg["columns"]]
+    e = _engine(cols)
+    try:
+        tab, _ = e.featurize(Zg["inten"], Zg["label"])
+        assert e.columns == cols and np.array_equal(tab[:, 0].astype(np.int64), Zg["labels"])
+        bad = tu.mismatches(Zg["table"], tab[:, 2:], cols)
+        assert not bad, bad[:8]
+        e.select(["IMOM_HU1", "IMOM_RM_11"])            # intensity variant alone
+        t2, _ = e.featurize(Zg["inten"].astype(np.uint16), Zg["label"])
+        assert e.columns == ["IMOM_RM_11", "IMOM_HU1"]
+        assert not tu.mismatches(Zg["table"][:, [cols.index(c) for c in e.columns]], t2[:, 2:], e.columns)
+        for bad_name in ("*IGEOMOMS*", "*SGEOMOMS*", "*GEOMOMS*"):
+            with pytest.raises(Exception, match="WEIGHTED"):
+                e.select([bad_name])
+        with pytest.raises(ValueError):
+            e.select(["IMOM_WRM_00"])
+    finally:
+        e.close()

@@ -28,6 +28,6 @@ def test_ih_body_matches_reference_golden(g):
 
 def test_ih_columns_follow_the_texture_columns_and_need_ibsi():
     from nyxus_b200 import feature_table as ft
-    names = [f[0] for f in ft.FEATURES]
-    assert names[-46:] == COLS and names[-47] == "NGTDM_STRENGTH"
+    names = [f[0] for f in ft.FEATURES if f[2] == "IH"]
+    assert names == COLS and min(f[1] for f in ft.FEATURES if f[2] == "IH") > max(f[1] for f in ft.FEATURES if f[2] == "NGTDM")
     assert [str(c) for c in Z["columns_ibsi_off"]] == ["MEAN"]       # IBSI off: the reference strips the family
