@@ -230,6 +230,7 @@ struct nyxb200_ctx
 	int fam_mask = 0;		// first-order + texture families (bits of Family)
 	bool want_morph = false;	// *BASIC_MORPHOLOGY* columns selected
 	bool want_ih = false;		// IH_* columns selected (and IBSI mode on)
+	int row_stride = NCOL_TEXINT;	// doubles per ROI of the canonical table: the appended families only when one of them is selected
 	int geom_variants = 0;		// geometric moments selected: bit 0 shape (SPAT_ / CENTRAL_ / NORM_ / HU_M), bit 1 intensity (IMOM_)
 	std::vector<int> sel_cols;		// canonical column of every output column
 	std::vector<std::string> sel_names;
@@ -763,7 +764,7 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 			return NYXB200_ECUDA;
 		const int per_sm = (int)std::max<size_t> (1, std::min<size_t> (16, (size_t)(227 * 1024) / (bytes + 1024)));
 		const int grid = (int)std::min<uint32_t> ((n + ROI_WARPS - 1) / ROI_WARPS, (uint32_t)(ctx->sm_count * per_sm));
-		kw<<<grid, ROI_THREADS, bytes, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out, NCOL_ALL, famw);
+		kw<<<grid, ROI_THREADS, bytes, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out, ctx->row_stride, famw);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		return 0;
@@ -784,7 +785,7 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
 	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out,
-		NCOL_ALL, gs, famw, dbg);
+		ctx->row_stride, gs, famw, dbg);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
 	return 0;
@@ -1461,7 +1462,11 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 {
 	const unsigned long long npix = (unsigned long long)im.D * (unsigned long long)im.H * (unsigned long long)im.W;
 	const bool d3 = ctx->st.dim == 3;
-	const int ncol_all = d3 ? NCOL3_ALL : NCOL_ALL;
+	// 2D: the canonical row ends after the last selected family (the texture + first-order block is always there; the
+	// appended morphology / IH / moment blocks cost their 1.4 KB per ROI of memset and row stride only when selected)
+	if (!d3)
+		ctx->row_stride = ctx->geom_variants ? NCOL_ALL : ctx->want_ih ? COL_IH + NCOL_IH : ctx->want_morph ? COL_MORPH + NCOL_MORPH : NCOL_TEXINT;
+	const int ncol_all = d3 ? NCOL3_ALL : ctx->row_stride;
 	Params prm = make_params (ctx);
 	cudaStream_t s = ctx->stream;
 	ctx->cur_b = 0;
