@@ -936,7 +936,7 @@ const MetaDef g_meta[] = {
 	{ "3glcm", "offset", nullptr, false, false },		// D3_GLCM_feature uses a static offset of 1 (3d_glcm.cpp:16-31): stored, never read
 	{ "3glcm", "numang", nullptr, false, false },
 	{ "3glcm", "sparseintensities", nullptr, true, false },
-	{ "3gldm", "greydepth", nullptr, false, false },
+	{ "3gldm", "greydepth", "3gldm/greydepth", false, false },
 	{ "3ngtdm", "greydepth", "3ngtdm/greydepth", false, false },
 	{ "3ngtdm", "radius", "3ngtdm/radius", false, true },
 	{ "3glrlm", "greydepth", nullptr, false, false },

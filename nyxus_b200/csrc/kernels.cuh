@@ -969,10 +969,11 @@ __global__ void __launch_bounds__(ROI_THREADS, (FAM == FAM_GLDM || FAM == FAM_NG
 // 3D (Nyxus3D) families: CTA per ROI, the ROI's AABB cube in shared memory, family region in shared memory or in a
 // per-CTA global slot.  FAM3: 1 GLCM, 2 GLSZM, 3 NGTDM.
 // ------------------------------------------------------------------------------------------------
-enum Family3 : int { FAM3_INT = 0, FAM3_GLCM, FAM3_GLSZM, FAM3_NGTDM, FAM3_COUNT };
-constexpr int NCOL3_INT = NCOL_INT, NCOL3_GLCM = NCOL_GLCM3, NCOL3_NGTDM = NCOL_NGTDM, NCOL3_GLSZM = NCOL_GLSZM;
+enum Family3 : int { FAM3_INT = 0, FAM3_GLCM, FAM3_GLSZM, FAM3_NGTDM, FAM3_GLDM, FAM3_COUNT };
+constexpr int NCOL3_INT = NCOL_INT, NCOL3_GLCM = NCOL_GLCM3, NCOL3_NGTDM = NCOL_NGTDM, NCOL3_GLSZM = NCOL_GLSZM, NCOL3_GLDM = NCOL_GLDM;
 constexpr int COL3_INT = 0, COL3_GLCM = COL3_INT + NCOL3_INT, COL3_NGTDM = COL3_GLCM + NCOL3_GLCM, COL3_GLSZM = COL3_NGTDM + NCOL3_NGTDM;
-constexpr int NCOL3_ALL = COL3_GLSZM + NCOL3_GLSZM;
+constexpr int COL3_GLDM = COL3_GLSZM + NCOL3_GLSZM;
+constexpr int NCOL3_ALL = COL3_GLDM + NCOL3_GLDM;
 
 template <int FAM3, bool P16, bool GSCR>
 __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, const RoiRec* __restrict__ rois,
@@ -1001,6 +1002,8 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 			glszm3d_body (c, r, prm, cell, mem, maxcells, glszm_hash_slots (Lmax, maxcells), greyinfo > 0, o + COL3_GLSZM);
 		else if (FAM3 == FAM3_NGTDM)
 			ngtdm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_NGTDM);
+		else if (FAM3 == FAM3_GLDM)
+			gldm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_GLDM);
 		c.sync();
 	}
 }
@@ -1033,6 +1036,8 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3_big (ImageView im, 
 			glszm3d_body_big (c, r, prm, cell, mem, maxcells, slots, greyinfo > 0, o + COL3_GLSZM);
 		else if (FAM3 == FAM3_NGTDM)
 			ngtdm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_NGTDM);
+		else if (FAM3 == FAM3_GLDM)
+			gldm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_GLDM);
 		c.sync();
 	}
 }

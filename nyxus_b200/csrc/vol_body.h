@@ -287,6 +287,145 @@ NYX_D void ngtdm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3D GLDM (reference features/3d_gldm.cpp): blank :61-78; binning with GLDM_GREYDEPTH ("3gldm/greydepth", 0 unless set = no
+// binning; IBSI forces 0) :93-97; background level zeroI = 1 under MATLAB binning, else 0 :117; every voxel whose level is
+// not zeroI is a centre, its dependence = 1 + the number of its 26 in-cube neighbours of the same level :120-152;
+// matrix[level][dependence 1..27]; features :271-530 -- the 2D formulas over level VALUES (gldm_body) with Nd = 27.
+// region: P[(Lmax+1)][28] + Si[Lmax+1] + Sj[28] (zero on entry and exit) + one byte per cell (its dependence)
+// ------------------------------------------------------------------------------------------------
+constexpr int GLDM3_ND = 28;
+NYX_HD size_t gldm3d_smem_words (int Lmax, uint32_t maxcells)
+{
+	return (size_t)(Lmax + 1) * (GLDM3_ND + 1) + GLDM3_ND + ((size_t)maxcells + 3) / 4;
+}
+
+NYX_D void gldm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax,
+	bool matlab, double* out)
+{
+	const int w = r.w, h = r.h, d = r.d, ncell = w * h * d;
+	if (r.imin == r.imax)
+	{
+		for (int i = c.tid; i < NCOL_GLDM; i += c.nthr)
+			out[i] = prm.softnan;
+		return;
+	}
+	uint32_t* P = mem;					// [level][nd], nd in 1..27
+	uint32_t* Si = P + (size_t)(Lmax + 1) * GLDM3_ND;	// [level]
+	uint32_t* Sj = Si + (Lmax + 1);				// [nd]
+	uint8_t* aux = (uint8_t*)(Sj + GLDM3_ND);		// [ncell]
+	const uint32_t zeroI = matlab ? 1u : 0u;
+	FastDiv fw, fh;
+	fw.init ((uint32_t)w);
+	fh.init ((uint32_t)h);
+
+	enum { Q_NZ, Q_LDE, Q_MUI, Q_MUJ, Q_HGL, Q_N };
+	unsigned long long q[Q_N];
+	for (int k = 0; k < Q_N; k++)
+		q[k] = 0;
+	enum { A_SDE, A_LGL, A_SDL, A_SDH, A_LDL, A_LDH, A_N };
+	double s[A_N];
+	for (int k = 0; k < A_N; k++)
+		s[k] = 0;
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (lv == zeroI)
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+		const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+		int j = 1;
+		for (int dz = -1; dz <= 1; dz++)
+		{
+			const int zz = z + dz;
+			if (zz < 0 || zz >= d)
+				continue;
+			for (int dy = -1; dy <= 1; dy++)
+			{
+				const int yy = y + dy;
+				if (yy < 0 || yy >= h)
+					continue;
+				for (int dx = -1; dx <= 1; dx++)
+				{
+					const int xx = x + dx;
+					if ((!dx && !dy && !dz) || xx < 0 || xx >= w)
+						continue;
+					j += (cell[(zz * h + yy) * w + xx] & CELL_LEVEL) == lv ? 1 : 0;
+				}
+			}
+		}
+		aux[i] = (uint8_t)j;
+		atom_add (c, P + (size_t)lv * GLDM3_ND + j, 1u);
+		atom_add (c, Si + lv, 1u);
+		atom_add (c, Sj + j, 1u);
+		q[Q_NZ] += 1;
+		q[Q_LDE] += (unsigned long long)(j * j);
+		q[Q_MUJ] += (unsigned long long)j;
+		q[Q_MUI] += lv;
+		q[Q_HGL] += (unsigned long long)lv * (unsigned long long)lv;
+		emphasis6_int (s, lv, (uint32_t)j);
+	}
+	c.sync();
+	cta_sum_u64<Q_N> (c, q);
+	cta_sum<A_N> (c, s);
+	if (q[Q_NZ] == 0)	// 3d_gldm.cpp:196-213
+	{
+		for (int i = c.tid; i < NCOL_GLDM; i += c.nthr)
+			out[i] = prm.softnan;
+		return;
+	}
+	const double Nz = (double)q[Q_NZ];
+	const double mui = (double)q[Q_MUI] / Nz, muj = (double)q[Q_MUJ] / Nz;
+	const double inv_nz = 1.0 / Nz;
+	unsigned long long q2[2] = { 0, 0 };
+	double t[3] = { 0, 0, 0 };
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (lv == zeroI)
+			continue;
+		const uint32_t j = aux[i];
+		q2[0] += Si[lv];
+		q2[1] += Sj[j];
+		const double di = (double)lv - mui, dj = (double)j - muj;
+		t[0] += di * di;
+		t[1] += dj * dj;
+		const double p = (double)P[(size_t)lv * GLDM3_ND + j] * inv_nz;
+		t[2] += fast_log10 (dadd (p, EPS_ZONES));
+	}
+	cta_sum_u64<2> (c, q2);
+	cta_sum<3> (c, t);
+	c.sync();
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (lv == zeroI)
+			continue;
+		P[(size_t)lv * GLDM3_ND + aux[i]] = 0;
+		Si[lv] = 0;
+	}
+	for (int k = c.tid; k < GLDM3_ND; k += c.nthr)
+		Sj[k] = 0;
+	c.sync();
+	if (c.tid == 0)
+	{
+		out[D_SDE] = s[A_SDE] / Nz;
+		out[D_LDE] = (double)q[Q_LDE] / Nz;
+		out[D_GLN] = (double)q2[0] / Nz;
+		out[D_DN] = (double)q2[1] / Nz;
+		out[D_DNN] = (double)q2[1] / (Nz * Nz);
+		out[D_GLV] = t[0] / Nz;
+		out[D_DV] = t[1] / Nz;
+		out[D_DE] = -(t[2] / Nz) * (1.0 / LOG10_2);
+		out[D_LGLE] = s[A_LGL] / Nz;
+		out[D_HGLE] = (double)q[Q_HGL] / Nz;
+		out[D_SDLGLE] = s[A_SDL] / Nz;
+		out[D_SDHGLE] = s[A_SDH] / Nz;
+		out[D_LDLGLE] = s[A_LDL] / Nz;
+		out[D_LDHGLE] = s[A_LDH] / Nz;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3D GLSZM of a LARGE cube (beyond the shared-memory size classes: organ-sized masks, whole-volume ROIs).  Same
 // semantics as glszm3d_body; everything lives in global memory: 32-bit union-find parents and zone sizes, and the
 // sparse (level, size) matrix + marginals in one open-addressing table of 64-bit keys with 32-bit counts.

@@ -145,7 +145,9 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 
 // ---- 3D: one labelled volume [D][H][W], label value `lab`; fam_mask bits: 1 INT, 2 GLCM, 4 NGTDM, 8 GLSZM.
 // out layout: 36 first-order | 30x13 + 29 GLCM | 5 NGTDM | 16 GLSZM   (the canonical 3D table of the library)
-extern "C" int nyxemu_ncols3d() { return NCOL_INT + NCOL_GLCM3 + NCOL_NGTDM + NCOL_GLSZM; }
+extern "C" int nyxemu_ncols3d() { return NCOL_INT + NCOL_GLCM3 + NCOL_NGTDM + NCOL_GLSZM + NCOL_GLDM; }
+static int g_gldm3_greydepth = 0;	// "3gldm/greydepth" (0 = no binning)
+extern "C" void nyxemu_set_gldm3_greydepth (int g) { g_gldm3_greydepth = g; }
 static bool g_big3d = false;	// 3D GLSZM through the large-cube body
 static int g_glcm3_greydepth = INT_MIN;	// "3glcm/greydepth"; INT_MIN = follows the grey depth
 extern "C" void nyxemu_set_glcm3_greydepth (int g) { g_glcm3_greydepth = g; }
@@ -190,7 +192,7 @@ extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl,
 	const int n3 = nyxemu_ncols3d();
 	for (int i = 0; i < n3; i++)
 		out[i] = 0;
-	const int O_GLCM = NCOL_INT, O_NGTDM = O_GLCM + NCOL_GLCM3, O_GLSZM = O_NGTDM + NCOL_NGTDM;
+	const int O_GLCM = NCOL_INT, O_NGTDM = O_GLCM + NCOL_GLCM3, O_GLSZM = O_NGTDM + NCOL_NGTDM, O_GLDM = O_GLSZM + NCOL_GLSZM;
 	std::vector<uint32_t> cell (ncell);
 	if (fam_mask & 1)
 	{
@@ -198,12 +200,12 @@ extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl,
 		std::vector<uint32_t> mem (intensity_smem_words (npad, greydepth));
 		intensity_body (c, r, prm, cloud.data(), r.area, npad, mem.data(), out);
 	}
-	for (int fam = 1; fam <= 3; fam++)
+	for (int fam = 1; fam <= 4; fam++)
 	{
-		const unsigned bit = fam == 1 ? 2u : fam == 2 ? 8u : 4u;	// GLCM, GLSZM, NGTDM
+		const unsigned bit = fam == 1 ? 2u : fam == 2 ? 8u : fam == 3 ? 4u : 16u;	// GLCM, GLSZM, NGTDM, GLDM
 		if (!(fam_mask & bit))
 			continue;
-		int g = fam == 1 ? glcm_g : fam == 2 ? glszm_g : ngtdm_g;
+		int g = fam == 1 ? glcm_g : fam == 2 ? glszm_g : fam == 3 ? ngtdm_g : g_gldm3_greydepth;
 		if (ibsi)
 			g = 0;
 		Binner B;
@@ -230,6 +232,11 @@ extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl,
 				std::vector<uint32_t> mem (glszm3d_smem_words ((uint32_t)ncell, slots));
 				glszm3d_body (c, r, prm, cell.data(), mem.data(), (uint32_t)ncell, slots, g > 0, out + O_GLSZM);
 			}
+		}
+		else if (fam == 4)
+		{
+			std::vector<uint32_t> mem (gldm3d_smem_words (Lm, (uint32_t)ncell));
+			gldm3d_body (c, r, prm, cell.data(), mem.data(), Lm, g > 0, out + O_GLDM);
 		}
 		else
 		{

@@ -139,8 +139,8 @@ def load_golden_vol():
 
 
 def canonical3d_index(cols):
-    """position of every reference 3D column in the library's canonical 3D table (36 | 30x13+29 | 5 | 16)"""
-    idx, nave, pi, pn, pz = [], 0, 0, 0, 0
+    """position of every reference 3D column in the library's canonical 3D table (36 | 30x13+29 | 5 | 16 | 14)"""
+    idx, nave, pi, pn, pz, pd = [], 0, 0, 0, 0, 0
     for c in cols:
         if c.startswith("3GLCM_"):
             s = c[6:]
@@ -155,22 +155,25 @@ def canonical3d_index(cols):
         elif c.startswith("3GLSZM_"):
             idx.append(36 + 419 + 5 + pz)
             pz += 1
+        elif c.startswith("3GLDM_"):
+            idx.append(36 + 419 + 5 + 16 + pd)
+            pd += 1
         else:
             idx.append(pi)
             pi += 1
     return np.array(idx)
 
 
-def emu_roi_features_3d(L, vol, lbl, lab, g, gz, gn, rad, ibsi, cols):
+def emu_roi_features_3d(L, vol, lbl, lab, g, gz, gn, rad, ibsi, cols, fam_mask=15):
     """host-emulated 3D bodies for the ROI `lab` of a labelled volume, in the reference's column order"""
     V = np.ascontiguousarray(vol, np.uint32)
     M = np.ascontiguousarray(lbl, np.uint32)
     fg = V[M > 0]
     den = float(fg.max()) - float(fg.min())
-    out = np.zeros(36 + 419 + 5 + 16)
+    out = np.zeros(36 + 419 + 5 + 16 + 14)
     D, H, W = V.shape
     rc = L.nyxemu_roi_features_3d(V.ctypes.data, M.ctypes.data, D, H, W, int(lab), int(g), int(gz), int(gn), int(rad), int(bool(ibsi)),
-                                  den, 15, out.ctypes.data)
+                                  den, fam_mask, out.ctypes.data)
     assert rc == 0
     return finite0(out[canonical3d_index(cols)])
 

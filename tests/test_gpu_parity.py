@@ -645,3 +645,20 @@ def test_unweighted_geometric_moments_against_reference_golden():
             e.select(["IMOM_WRM_00"])
     finally:
         e.close()
+
+
+# ------------------------------------------------------------------------------------------------ more 3D families
+@pytest.mark.parametrize("g", [0, 16, -12])
+def test_3d_gldm_against_reference_golden(g):
+    from nyxus_b200 import Engine
+    Zv = np.load(os.path.join(tu.GOLDEN, "golden_vol_more.npz"))
+    e = Engine(["*3D_GLDM*"], dim=3)
+    try:
+        e.set_param("3gldm/greydepth", g)
+        tab, _ = e.featurize_volume(Zv["vol"], Zv["label"])
+        assert e.columns == [str(c) for c in Zv["GLDM/columns"]]
+        assert np.array_equal(tab[:, 0].astype(np.int64), Zv["GLDM/labels"])
+        bad = tu.mismatches(Zv["GLDM/table_%d" % g], tab[:, 2:], e.columns)
+        assert not bad, bad[:8]
+    finally:
+        e.close()

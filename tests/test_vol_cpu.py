@@ -76,8 +76,12 @@ def test_nifti_round_trip(tmp_path):
 def test_3d_column_contract_of_the_library():
     """the generated 3D table (nyx_feature_table3d.inc) lists the reference's 116 columns in Feature3D code order"""
     inc = os.path.join(tu.ROOT, "nyxus_b200", "csrc", "nyx_feature_table3d.inc")
-    names = [ln.split('"')[1] for ln in open(inc) if ln.startswith("{")]
-    assert names == GV["columns"] and len(names) == 116
+    rows = [ln for ln in open(inc) if ln.startswith("{")]
+    names = [ln.split('"')[1] for ln in rows]
+    codes = [int(ln.split(",")[1]) for ln in rows]
+    assert codes == sorted(codes)
+    extra = [n for n in names if n.startswith("3GLDM_")]                # appended 3D families (SURVEY 8f-5)
+    assert [n for n in names if n not in extra] == GV["columns"] and len(names) == 116 + len(extra) and len(extra) == 14
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so not built")
@@ -103,3 +107,21 @@ def test_3d_ngtdm_radius_above_one_and_large_cube_glszm_against_compiled_referen
             assert not tu.mismatches(tab[0], got, cols), (it, rad, gz, gn)
     finally:
         L.nyxemu_set_big3d(0)
+
+
+ZM = np.load(os.path.join(tu.GOLDEN, "golden_vol_more.npz"))
+
+
+@pytest.mark.parametrize("g", [0, 16, -12])
+def test_3d_gldm_body_matches_reference_golden(g):
+    """3D GLDM: golden_vol_more.npz = the reference's own pybind module on a NIfTI volume (make_golden3d_more.py)"""
+    L = tu.build_emu()
+    cols = [str(c) for c in ZM["GLDM/columns"]]
+    try:
+        L.nyxemu_set_gldm3_greydepth(g)
+        for k, lab in enumerate(ZM["GLDM/labels"]):
+            got = tu.emu_roi_features_3d(L, ZM["vol"], ZM["label"], int(lab), 64, 0, 0, 0, False, cols, fam_mask=16)
+            bad = tu.mismatches(ZM["GLDM/table_%d" % g][k], got, cols)
+            assert not bad, (g, int(lab), bad[:4])
+    finally:
+        L.nyxemu_set_gldm3_greydepth(0)
