@@ -56,10 +56,14 @@ const GroupDef g_groups3d[] = {
 	{ "*3D_GLSZM*", 1 << FAM3_GLSZM },
 	{ "*3D_NGTDM*", 1 << FAM3_NGTDM },
 	{ "*3D_GLDM*", 1 << FAM3_GLDM },
+	{ "*3D_GLRLM*", 1 << FAM3_GLRLM },
+	{ "*3D_GLDZM*", 1 << FAM3_GLDZM },
+	{ "*3D_NGLDM*", 1 << FAM3_NGLDM },
+	// featureset.h: the texture group = the seven 3D texture families, the neighbour group = GLDM, NGLDM, NGTDM
+	{ "*3D_ALL_TEXTURE*", (1 << FAM3_GLCM) | (1 << FAM3_GLSZM) | (1 << FAM3_NGTDM) | (1 << FAM3_GLDM) | (1 << FAM3_GLRLM) | (1 << FAM3_GLDZM) | (1 << FAM3_NGLDM) },
 };
-// 3D groups of the reference that contain families outside this path (3D GLRLM / GLDM / GLDZM / NGLDM, morphology, moments)
-const char* g_groups3d_unbuilt[] = { "*3D_ALL*", "*3D_ALL_TEXTURE*", "*3D_ALL_MORPHOLOGY*", "*3D_GLDZM*", "*3D_GLRLM*",
-	"*3D_NGLDM*", "*3D_ALL_NEIGHBOR*", "*3D_MOMENTS*" };
+// 3D groups of the reference that contain families outside this path (surface morphology, moments)
+const char* g_groups3d_unbuilt[] = { "*3D_ALL*", "*3D_ALL_MORPHOLOGY*", "*3D_ALL_NEIGHBOR*", "*3D_MOMENTS*" };
 
 const char* g_stage_names[NYXB200_NSTAGES] = { "h2d", "init", "scan", "compact", "pack", "intensity", "glcm", "glrlm", "gldzm",
 	"glszm", "gldm", "ngldm", "ngtdm", "select", "d2h", "total", "families", "giant" };
@@ -278,6 +282,7 @@ struct nyxb200_ctx
 
 	int glszm3_greydepth = 0, ngtdm3_greydepth = 0, ngtdm3_radius = 0;	// env_features.cpp:712-736: zero unless set
 	int gldm3_greydepth = 0;	// "3gldm/greydepth" (env_metaparams.cpp:158-173)
+	int glrlm3_greydepth = 0;	// "3glrlm/greydepth" (env_metaparams.cpp:204-220)
 	int glcm_greydepth = 0;		// GLCM_GREYDEPTH when set through "glcm/greydepth" / "3glcm/greydepth" (env_metaparams.cpp:83-91,112-120)
 	bool glcm_greydepth_set = false;	// else it follows coarse_gray_depth (env_features.cpp:730)
 
@@ -400,7 +405,7 @@ int resolve_features (int dim, const std::vector<FeatureDef>& feats, const char*
 				if (!strcmp (g, s))
 				{
 					msg = std::string ("feature group '") + s + "' contains 3D families outside this path "
-						"(built: *3D_ALL_INTENSITY*, *3D_GLCM*, *3D_GLSZM*, *3D_NGTDM*, *3D_GLDM*)";
+						"(built: *3D_ALL_INTENSITY*, *3D_ALL_TEXTURE* = *3D_GLCM*, *3D_GLSZM*, *3D_NGTDM*, *3D_GLDM*, *3D_GLRLM*, *3D_GLDZM*, *3D_NGLDM*)";
 					return NYXB200_EUNSUPPORTED;
 				}
 		for (int i = 0; i < nf; i++)
@@ -691,6 +696,12 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 			return fail (ctx, NYXB200_EUNSUPPORTED, "grey depth must be in -65535..65535");
 		ctx->gldm3_greydepth = iv;
 	}
+	else if (!strcmp (key, "3glrlm/greydepth"))		// env_metaparams.cpp:204-220 (negative = PyRadiomics bin count)
+	{
+		if (iv < -65535 || iv > 65535)
+			return fail (ctx, NYXB200_EUNSUPPORTED, "grey depth must be in -65535..65535");
+		ctx->glrlm3_greydepth = iv;
+	}
 	else if (!strcmp (key, "3ngtdm/greydepth"))		// env_metaparams.cpp:175-186
 	{
 		if (iv < -65535 || iv > 65535)
@@ -870,6 +881,9 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 	if (FAM3 == FAM3_GLSZM) famw = glszm3d_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));
 	if (FAM3 == FAM3_NGTDM) famw = ngtdm3d_smem_words (Lmax, prm.ngtdm3_radius);
 	if (FAM3 == FAM3_GLDM) famw = gldm3d_smem_words (Lmax, maxcells);
+	if (FAM3 == FAM3_GLRLM) famw = glrlm3d_smem_words (Lmax, prm.cube_maxdim, maxcells);
+	if (FAM3 == FAM3_GLDZM) famw = gldzm3d_smem_words (Lmax, gldzm_nd_bound (maxcells, prm.cube_maxdim), maxcells);
+	if (FAM3 == FAM3_NGLDM) famw = ngldm3d_smem_words (Lmax);
 	famw = (famw + 1) & ~(size_t)1;
 	size_t smem_words = RED_WORDS + tilew + famw;
 	uint32_t* gs = nullptr;
@@ -912,6 +926,9 @@ int launch_family3_big (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* l
 	}
 	if (FAM3 == FAM3_NGTDM) famw = ngtdm3d_smem_words (Lmax, prm.ngtdm3_radius);
 	if (FAM3 == FAM3_GLDM) famw = gldm3d_smem_words (Lmax, (uint32_t)maxcells);
+	if (FAM3 == FAM3_GLRLM) famw = glrlm3d_smem_words (Lmax, prm.cube_maxdim, maxcells);
+	if (FAM3 == FAM3_GLDZM) famw = gldzm3d_smem_words (Lmax, gldzm_nd_bound ((uint32_t)maxcells, prm.cube_maxdim), maxcells);
+	if (FAM3 == FAM3_NGLDM) famw = ngldm3d_smem_words (Lmax);
 	famw = (famw + 3) & ~(size_t)3;
 	const size_t slotw = tilew + famw;
 	size_t freeb = 0, totalb = 0;
@@ -1875,16 +1892,29 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 			const int maxI = (int)std::max<uint32_t> (info.max_inten, 1u);
 			for (int fam = FAM3_GLCM; fam < FAM3_COUNT; fam++)
 			{
-				static const int st3[FAM3_COUNT] = { ST_INT, ST_GLCM, ST_GLSZM, ST_NGTDM, ST_GLDM };
+				static const int st3[FAM3_COUNT] = { ST_INT, ST_GLCM, ST_GLSZM, ST_NGTDM, ST_GLDM, ST_GLRLM, ST_GLDZM, ST_NGLDM };
 				if (!(ctx->fam_mask & (1 << fam)))
 					continue;
 				use_family_stream (ctx, fam);
 				stage_begin (ctx, st3[fam], ctx->ls);
-				// grey-binning info per family (3d_glcm.cpp:53-55, 3d_glszm.cpp:490-492, 3d_ngtdm.cpp:195-197); 0 = no binning
-				int g = fam == FAM3_GLCM ? prm.glcm_greydepth : fam == FAM3_GLSZM ? ctx->glszm3_greydepth : fam == FAM3_GLDM ? ctx->gldm3_greydepth : ctx->ngtdm3_greydepth;
+				// grey-binning info per family (3d_glcm.cpp:53-55, 3d_glszm.cpp:490-492, 3d_ngtdm.cpp:195-197, 3d_gldm.cpp:93-97,
+				// 3d_glrlm.cpp:148-152: per-family depths, 0 = no binning; 3d_gldzm.cpp:65-72 and 3d_ngldm.cpp:204: the coarse depth)
+				int g = fam == FAM3_GLCM ? prm.glcm_greydepth : fam == FAM3_GLSZM ? ctx->glszm3_greydepth : fam == FAM3_GLDM ? ctx->gldm3_greydepth
+					: fam == FAM3_GLRLM ? ctx->glrlm3_greydepth : fam == FAM3_NGTDM ? ctx->ngtdm3_greydepth : prm.greydepth;
 				if (ctx->st.ibsi)
 					g = 0;
 				int Lm = g != 0 ? std::abs (g) : maxI;	// > 0 MATLAB levels, < 0 PyRadiomics bins (texture_feature.h:52-77), 0 = intensities as they are
+				if (fam == FAM3_NGLDM)
+				{
+					// to_grayscale over [0, aux_max]: levels 0..depth (IBSI: the intensities themselves)
+					g = ctx->st.ibsi ? 0 : prm.greydepth;
+					if (g < 0)
+						return fail (ctx, NYXB200_EUNSUPPORTED, "3D NGLDM needs a positive grey depth");
+					Lm = ctx->st.ibsi ? maxI : g;
+				}
+				if (fam == FAM3_GLDZM && g < 0)
+					return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLDZM with a negative (PyRadiomics) grey depth is undefined in the reference "
+						"(level-0 zones index its matrix out of range, 3d_gldzm.cpp:294-297)");
 				if (fam == FAM3_NGTDM && ctx->ngtdm3_radius == 0)
 					Lm = 1;		// nothing is accumulated (see ngtdm3d_body)
 				for (int c = 0; c <= NCLASS; c++)
@@ -1909,6 +1939,22 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 							return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLSZM needs grey levels < 65536 (max %d)", Lm);
 						rc = big ? launch_family3_big<FAM3_GLSZM> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p)
 							: launch_family3_t<FAM3_GLSZM, false> (ctx, im, lst, n, prm, g, Lm, mc, ctx->d_full.p);
+					}
+					else if (fam == FAM3_GLRLM || fam == FAM3_GLDZM || fam == FAM3_NGLDM)
+					{
+						if (Lm > 65535)
+							return fail (ctx, NYXB200_EUNSUPPORTED, "3D GLRLM / GLDZM / NGLDM need grey levels < 65536 (max %d)", Lm);
+						Params p3 = prm;
+						p3.cube_maxdim = (int)cmaxwh[c];
+						if (fam == FAM3_GLRLM)
+							rc = big ? launch_family3_big<FAM3_GLRLM> (ctx, im, lst, n, p3, g, Lm, mc, ctx->d_full.p)
+								: launch_family3_t<FAM3_GLRLM, false> (ctx, im, lst, n, p3, g, Lm, mc, ctx->d_full.p);
+						else if (fam == FAM3_GLDZM)
+							rc = big ? launch_family3_big<FAM3_GLDZM> (ctx, im, lst, n, p3, g, Lm, mc, ctx->d_full.p)
+								: launch_family3_t<FAM3_GLDZM, false> (ctx, im, lst, n, p3, g, Lm, mc, ctx->d_full.p);
+						else
+							rc = big ? launch_family3_big<FAM3_NGLDM> (ctx, im, lst, n, p3, g, Lm, mc, ctx->d_full.p)
+								: launch_family3_t<FAM3_NGLDM, false> (ctx, im, lst, n, p3, g, Lm, mc, ctx->d_full.p);
 					}
 					else if (fam == FAM3_GLDM)
 					{
@@ -2495,6 +2541,7 @@ int nyxb200_get_param (const nyxb200_ctx* ctx, const char* key, double* value)
 	else if (!strcmp (key, "covered_range_from_scan")) *value = ctx->covered_from_scan;
 	else if (!strcmp (key, "3glszm/greydepth")) *value = ctx->glszm3_greydepth;
 	else if (!strcmp (key, "3gldm/greydepth")) *value = ctx->gldm3_greydepth;
+	else if (!strcmp (key, "3glrlm/greydepth")) *value = ctx->glrlm3_greydepth;
 	else if (!strcmp (key, "3ngtdm/greydepth")) *value = ctx->ngtdm3_greydepth;
 	else if (!strcmp (key, "3ngtdm/radius")) *value = ctx->ngtdm3_radius;
 	else

@@ -939,7 +939,7 @@ const MetaDef g_meta[] = {
 	{ "3gldm", "greydepth", "3gldm/greydepth", false, false },
 	{ "3ngtdm", "greydepth", "3ngtdm/greydepth", false, false },
 	{ "3ngtdm", "radius", "3ngtdm/radius", false, true },
-	{ "3glrlm", "greydepth", nullptr, false, false },
+	{ "3glrlm", "greydepth", "3glrlm/greydepth", false, false },
 	{ "3glszm", "greydepth", "3glszm/greydepth", false, false },
 };
 

@@ -969,11 +969,39 @@ __global__ void __launch_bounds__(ROI_THREADS, (FAM == FAM_GLDM || FAM == FAM_NG
 // 3D (Nyxus3D) families: CTA per ROI, the ROI's AABB cube in shared memory, family region in shared memory or in a
 // per-CTA global slot.  FAM3: 1 GLCM, 2 GLSZM, 3 NGTDM.
 // ------------------------------------------------------------------------------------------------
-enum Family3 : int { FAM3_INT = 0, FAM3_GLCM, FAM3_GLSZM, FAM3_NGTDM, FAM3_GLDM, FAM3_COUNT };
+enum Family3 : int { FAM3_INT = 0, FAM3_GLCM, FAM3_GLSZM, FAM3_NGTDM, FAM3_GLDM, FAM3_GLRLM, FAM3_GLDZM, FAM3_NGLDM, FAM3_COUNT };
 constexpr int NCOL3_INT = NCOL_INT, NCOL3_GLCM = NCOL_GLCM3, NCOL3_NGTDM = NCOL_NGTDM, NCOL3_GLSZM = NCOL_GLSZM, NCOL3_GLDM = NCOL_GLDM;
+constexpr int NCOL3_GLRLM = NCOL_GLRLM3, NCOL3_GLDZM = NCOL_GLDZM, NCOL3_NGLDM = NCOL_NGLDM;
 constexpr int COL3_INT = 0, COL3_GLCM = COL3_INT + NCOL3_INT, COL3_NGTDM = COL3_GLCM + NCOL3_GLCM, COL3_GLSZM = COL3_NGTDM + NCOL3_NGTDM;
-constexpr int COL3_GLDM = COL3_GLSZM + NCOL3_GLSZM;
-constexpr int NCOL3_ALL = COL3_GLDM + NCOL3_GLDM;
+constexpr int COL3_GLDM = COL3_GLSZM + NCOL3_GLSZM, COL3_GLRLM = COL3_GLDM + NCOL3_GLDM, COL3_GLDZM = COL3_GLRLM + NCOL3_GLRLM;
+constexpr int COL3_NGLDM = COL3_GLDZM + NCOL3_GLDZM;
+constexpr int NCOL3_ALL = COL3_NGLDM + NCOL3_NGLDM;
+
+// per-family work of one cube (after load_cube); Nd / Nr bounds of the launch's ROI class come from prm.cube_maxdim
+template <int FAM3, bool P16, bool BIG>
+__device__ __forceinline__ void family3_dispatch (const Cta& c, const RoiRec& r, const Params& prm, uint32_t* cell, uint32_t* mem,
+	int greyinfo, int Lmax, unsigned long long maxcells, uint32_t slots, double* o)
+{
+	if (FAM3 == FAM3_GLCM)
+		glcm3d_body<P16> (c, r, prm, cell, mem, Lmax, o + COL3_GLCM, greyinfo);
+	else if (FAM3 == FAM3_GLSZM)
+	{
+		if (BIG)
+			glszm3d_body_big (c, r, prm, cell, mem, maxcells, slots, greyinfo > 0, o + COL3_GLSZM);
+		else
+			glszm3d_body (c, r, prm, cell, mem, (uint32_t)maxcells, slots, greyinfo > 0, o + COL3_GLSZM);
+	}
+	else if (FAM3 == FAM3_NGTDM)
+		ngtdm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_NGTDM);
+	else if (FAM3 == FAM3_GLDM)
+		gldm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_GLDM);
+	else if (FAM3 == FAM3_GLRLM)
+		glrlm3d_body (c, r, prm, cell, mem, Lmax, prm.cube_maxdim, o + COL3_GLRLM);
+	else if (FAM3 == FAM3_GLDZM)
+		gldzm3d_body (c, r, prm, cell, mem, Lmax, gldzm_nd_bound ((uint32_t)maxcells, prm.cube_maxdim), maxcells, o + COL3_GLDZM);
+	else if (FAM3 == FAM3_NGLDM)
+		ngldm3d_body (c, r, prm, cell, mem, Lmax, o + COL3_NGLDM);
+}
 
 template <int FAM3, bool P16, bool GSCR>
 __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, const RoiRec* __restrict__ rois,
@@ -993,17 +1021,13 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 		const RoiRec r = rois[ri];
 		double* o = out + (size_t)ri * out_stride;
 		Binner B;
-		B.init (greyinfo, r.imin, r.imax);
+		if (FAM3 == FAM3_NGLDM)
+			B.init_tg (greyinfo, r.imax, prm.ibsi != 0);
+		else
+			B.init (greyinfo, r.imin, r.imax);
 		load_cube (c, im, r, B, cell);
 		c.sync();
-		if (FAM3 == FAM3_GLCM)
-			glcm3d_body<P16> (c, r, prm, cell, mem, Lmax, o + COL3_GLCM, greyinfo);
-		else if (FAM3 == FAM3_GLSZM)
-			glszm3d_body (c, r, prm, cell, mem, maxcells, glszm_hash_slots (Lmax, maxcells), greyinfo > 0, o + COL3_GLSZM);
-		else if (FAM3 == FAM3_NGTDM)
-			ngtdm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_NGTDM);
-		else if (FAM3 == FAM3_GLDM)
-			gldm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_GLDM);
+		family3_dispatch<FAM3, P16, false> (c, r, prm, cell, mem, greyinfo, Lmax, maxcells, FAM3 == FAM3_GLSZM ? glszm_hash_slots (Lmax, maxcells) : 0u, o);
 		c.sync();
 	}
 }
@@ -1027,17 +1051,13 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3_big (ImageView im, 
 		const RoiRec r = rois[ri];
 		double* o = out + (size_t)ri * out_stride;
 		Binner B;
-		B.init (greyinfo, r.imin, r.imax);
+		if (FAM3 == FAM3_NGLDM)
+			B.init_tg (greyinfo, r.imax, prm.ibsi != 0);
+		else
+			B.init (greyinfo, r.imin, r.imax);
 		load_cube (c, im, r, B, cell);
 		c.sync();
-		if (FAM3 == FAM3_GLCM)
-			glcm3d_body<false> (c, r, prm, cell, mem, Lmax, o + COL3_GLCM, greyinfo);
-		else if (FAM3 == FAM3_GLSZM)
-			glszm3d_body_big (c, r, prm, cell, mem, maxcells, slots, greyinfo > 0, o + COL3_GLSZM);
-		else if (FAM3 == FAM3_NGTDM)
-			ngtdm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_NGTDM);
-		else if (FAM3 == FAM3_GLDM)
-			gldm3d_body (c, r, prm, cell, mem, Lmax, greyinfo > 0, o + COL3_GLDM);
+		family3_dispatch<FAM3, false, true> (c, r, prm, cell, mem, greyinfo, Lmax, maxcells, slots, o);
 		c.sync();
 	}
 }

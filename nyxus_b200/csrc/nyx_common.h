@@ -193,15 +193,27 @@ NYX_D void emphasis6_int (double* s, uint32_t i, uint32_t j)
 // ------------------------------------------------------------------------------------------------
 // Grey-level binning (reference features/texture_feature.h:23-50,138-167; helpers/helpers.h:337-345)
 // ------------------------------------------------------------------------------------------------
+NYX_HD uint32_t to_grayscale (uint32_t i, uint32_t mn, uint32_t range, uint32_t n, bool disable);
 struct Binner
 {
 	int greyinfo;		// >0 MATLAB levels, 0 IBSI identity, <0 PyRadiomics bin count
 	double slope;		// MATLAB: g / max;  PyRadiomics: the bin width (max - min) / |g|
 	uint32_t n;		// |g|
 	uint32_t mn;		// PyRadiomics: aux_min
+	uint32_t tg;		// 0, or 1 + disable: Nyxus::to_grayscale (v, 0, range = mn, n, disable) instead (3D NGLDM)
 
+	// the NGLDM grey scale (3d_ngldm.cpp:88-103): to_grayscale over [0, aux_max]
+	NYX_HD void init_tg (int ngreys, uint32_t imax, bool disable)
+	{
+		greyinfo = 0;
+		slope = 0.0;
+		n = (uint32_t)ngreys;
+		mn = imax;
+		tg = disable ? 2u : 1u;
+	}
 	NYX_HD void init (int greyinfo_, uint32_t imin, uint32_t imax)
 	{
+		tg = 0;
 		greyinfo = greyinfo_;
 		n = (uint32_t)(greyinfo_ > 0 ? greyinfo_ : -greyinfo_);
 		mn = imin;
@@ -214,6 +226,8 @@ struct Binner
 	}
 	NYX_HD uint32_t bin (uint32_t i) const
 	{
+		if (tg)
+			return to_grayscale (i, 0u, mn, n, tg == 2u);
 		if (greyinfo == 0)
 			return i;
 		if (greyinfo < 0)
@@ -327,6 +341,7 @@ struct Params
 	// 3D (Nyxus3D) settings: per-family grey depths (env_features.cpp:712-736: only GLCM gets a default, the rest are 0
 	// = no binning unless set through set_metaparam) and the NGTDM neighbourhood radius
 	int32_t glszm3_greydepth = 0, ngtdm3_greydepth = 0, ngtdm3_radius = 0;
+	int32_t cube_maxdim = 0;	// 3D launches: the longest cube edge of the launch's ROI class (run-length / distance bounds)
 	double covered_den = 0;	// first-order COVERED_IMAGE_INTENSITY_RANGE denominator (slide max - min); 0 = in-memory sentinel
 };
 

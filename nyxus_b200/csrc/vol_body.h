@@ -426,6 +426,489 @@ NYX_D void gldm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// 3D NGLDM (reference features/3d_ngldm.cpp): blank :173-198; levels = Nyxus::to_grayscale (v, 0, aux_max, GREYDEPTH, ibsi) of
+// EVERY cube voxel, background included (:88-103, 219-223) -- the cube passed here carries those levels (Binner::init_tg); the
+// sorted unique levels are the matrix rows.  Centres: the voxels with all 26 cube neighbours in range (margins skipped, off-ROI
+// centres NOT skipped :128-147); dependence = number of the 24 neighbours listed at :12-41 ((0,0,+-1) are not among them)
+// with the centre's level; Nr = max dependence + 1 :167.  Features :262-355: Ns sums ALL columns, every other sum skips the
+// zero-dependence column; GLV takes the 1-based ROW INDEX against a mean of level VALUES (:331), reproduced.
+// region: M[(Lmax+1)][25] + rank[Lmax+1] + Sr[25] + 256 words of scan scratch (zero on entry and exit)
+// ------------------------------------------------------------------------------------------------
+constexpr int NGLDM3_NC = 25;
+NYX_HD size_t ngldm3d_smem_words (int Lmax)
+{
+	return (size_t)(Lmax + 1) * (NGLDM3_NC + 1) + NGLDM3_NC + 256;
+}
+
+NYX_D void ngldm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax, double* out)
+{
+	const int w = r.w, h = r.h, d = r.d, ncell = w * h * d;
+	if (r.imin == r.imax)
+	{
+		for (int i = c.tid; i < NCOL_NGLDM; i += c.nthr)
+			out[i] = prm.softnan;
+		return;
+	}
+	const int L1 = Lmax + 1;
+	uint32_t* M = mem;					// [level][dependence 0..24]
+	uint32_t* rank = M + (size_t)L1 * NGLDM3_NC;		// [level]: voxel count, then the 1-based row of the level (0 = absent)
+	uint32_t* Sr = rank + L1;				// [dependence]: centres per dependence
+	uint32_t* part = Sr + NGLDM3_NC;			// [nthr <= 256]
+	FastDiv fw, fh;
+	fw.init ((uint32_t)w);
+	fh.init ((uint32_t)h);
+	for (int i = c.tid; i < ncell; i += c.nthr)
+		atom_add (c, rank + (cell[i] & CELL_LEVEL), 1u);
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+		const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+		if (x < 1 || x >= w - 1 || y < 1 || y >= h - 1 || z < 1 || z >= d - 1)
+			continue;
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		int n = 0;
+		for (int dz = -1; dz <= 1; dz++)
+			for (int dy = -1; dy <= 1; dy++)
+				for (int dx = -1; dx <= 1; dx++)
+					if (dx || dy)
+						n += (cell[((z + dz) * h + (y + dy)) * w + (x + dx)] & CELL_LEVEL) == lv ? 1 : 0;
+		atom_add (c, M + (size_t)lv * NGLDM3_NC + n, 1u);
+		atom_add (c, Sr + n, 1u);
+	}
+	c.sync();
+	// rows: 1-based rank of every level that occurs in the cube
+	const int chunk = (L1 + c.nthr - 1) / c.nthr, lo = c.tid * chunk, hi = lo + chunk < L1 ? lo + chunk : L1;
+	uint32_t np = 0;
+	for (int lv = lo; lv < hi; lv++)
+		np += rank[lv] ? 1u : 0u;
+	part[c.tid] = np;
+	c.sync();
+	uint32_t base = 0;
+	for (int t = 0; t < c.tid; t++)
+		base += part[t];
+	for (int lv = lo; lv < hi; lv++)
+		rank[lv] = rank[lv] ? ++base : 0u;
+	int Nr = 1;
+	unsigned long long ns_all = 0, dcnu = 0;
+	for (int j = 0; j < NGLDM3_NC; j++)
+	{
+		const unsigned long long sj = Sr[j];
+		ns_all += sj;
+		if (sj)
+			Nr = j + 1;
+		if (j)
+			dcnu += sj * sj;		// :317-328 (columns above the largest dependence are empty)
+	}
+	c.sync();
+	const double Ns = (double)ns_all;
+	enum { Q_HDE, Q_HGL, Q_GLM, Q_DCM, Q_ENE, Q_GLNU, Q_N };
+	unsigned long long q[Q_N];
+	for (int k = 0; k < Q_N; k++)
+		q[k] = 0;
+	enum { A_LDE, A_LGL, A_LDL, A_LDH, A_HDL, A_HDH, A_ENT, A_N };
+	double s[A_N];
+	for (int k = 0; k < A_N; k++)
+		s[k] = 0;
+	for (int lv = c.tid; lv < L1; lv += c.nthr)
+	{
+		if (!rank[lv])
+			continue;
+		const double g = (double)lv, g2 = g * g;
+		unsigned long long srow = 0;
+		for (int j = 1; j < Nr; j++)
+		{
+			const unsigned long long sij = M[(size_t)lv * NGLDM3_NC + j];
+			if (!sij)
+				continue;
+			const double sd = (double)sij, jd = (double)j, kd = (double)(j + 1), pij = sd / Ns;
+			srow += sij;
+			q[Q_HDE] += sij * (unsigned long long)(j * j);
+			q[Q_HGL] += sij * (unsigned long long)lv * (unsigned long long)lv;
+			q[Q_GLM] += sij * (unsigned long long)lv;
+			q[Q_DCM] += sij * (unsigned long long)(j + 1);
+			q[Q_ENE] += sij * sij;
+			s[A_LDE] += sd / jd / jd;
+			if (lv)
+			{
+				s[A_LGL] += sd / g / g;
+				s[A_LDL] += sd / jd / jd / g / g;
+				s[A_HDL] += sd * kd * kd / g2;
+			}
+			s[A_LDH] += sd * g2 / kd / kd;
+			s[A_HDH] += sd * kd * kd * g2;
+			s[A_ENT] += pij * log (pij);
+		}
+		q[Q_GLNU] += srow * srow;
+	}
+	cta_sum_u64<Q_N> (c, q);
+	cta_sum<A_N> (c, s);
+	const double glm = (double)q[Q_GLM] / Ns, dcm = (double)q[Q_DCM] / Ns;
+	double t[2] = { 0, 0 };
+	for (int lv = c.tid; lv < L1; lv += c.nthr)
+	{
+		const uint32_t rk = rank[lv];
+		if (!rk)
+			continue;
+		for (int j = 1; j < Nr; j++)
+		{
+			const uint32_t sij = M[(size_t)lv * NGLDM3_NC + j];
+			if (!sij)
+				continue;
+			const double pij = (double)sij / Ns, di = (double)rk - glm, dj = (double)(j + 1) - dcm;
+			t[0] += di * di * pij;
+			t[1] += dj * dj * pij;
+		}
+	}
+	cta_sum<2> (c, t);
+	c.sync();
+	wipe_words (c, mem, (size_t)L1 * (NGLDM3_NC + 1) + NGLDM3_NC);
+	c.sync();
+	if (c.tid == 0)
+	{
+		out[N_LDE] = s[A_LDE] / Ns;
+		out[N_HDE] = (double)q[Q_HDE] / Ns;
+		out[N_LGLCE] = s[A_LGL] / Ns;
+		out[N_HGLCE] = (double)q[Q_HGL] / Ns;
+		out[N_LDLGLE] = s[A_LDL] / Ns;
+		out[N_LDHGLE] = s[A_LDH] / Ns;
+		out[N_HDLGLE] = s[A_HDL] / Ns;
+		out[N_HDHGLE] = s[A_HDH] / Ns;
+		out[N_GLNU] = (double)q[Q_GLNU] / Ns;
+		out[N_GLNUN] = (double)q[Q_GLNU] / (Ns * Ns);
+		out[N_DCNU] = (double)dcnu / Ns;
+		out[N_DCNUN] = (double)dcnu / (Ns * Ns);
+		out[N_DCP] = 1.0;
+		out[N_GLM] = ns_all ? glm : 0.0;
+		out[N_GLV] = t[0];
+		out[N_DCM] = ns_all ? dcm : 0.0;
+		out[N_DCV] = t[1];
+		out[N_DCENT] = -s[A_ENT] * INV_LN2;
+		out[N_DCENE] = ns_all ? (double)q[Q_ENE] / (Ns * Ns) : 0.0;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3D GLDZM (reference features/3d_gldzm.cpp): blank :523-546; binned with the coarse grey depth (IBSI: none) :65-72; zones =
+// 6-connected components of equal level (E,S,W,N,up,down with back-tracking :94-283), level 0 skipped in IBSI mode only; the
+// distance of a voxel is taken IN ITS SLICE (dist2border looks along x and y only :330-375); zone metric = minimum over the
+// members; features :412-519 as in 2D.  A negative (PyRadiomics) depth makes the reference index its matrix out of range
+// (level-0 zones have no row :294-297) -- refused by the host.
+// region: P[Lmax+1][Nd] + Ri[Lmax+1] + Cd[Nd] (zero on entry and exit) + parent[ncell] + zmin[ncell]
+// ------------------------------------------------------------------------------------------------
+NYX_HD size_t gldzm3d_smem_words (int Lmax, int Nd, unsigned long long maxcells)
+{
+	return (size_t)(Lmax + 1) * Nd + (Lmax + 1) + Nd + 2 * (size_t)maxcells;
+}
+
+NYX_D void gldzm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax, int Nd,
+	unsigned long long maxcells, double* out)
+{
+	const int w = r.w, h = r.h, d = r.d, wh = w * h, ncell = wh * d;
+	if (r.imin == r.imax)
+	{
+		for (int i = c.tid; i < NCOL_GLDZM; i += c.nthr)
+			out[i] = prm.softnan;
+		return;
+	}
+	const bool ibsi = prm.ibsi != 0;
+	uint32_t* P = mem;					// [Lmax+1][Nd]
+	uint32_t* Ri = P + (size_t)(Lmax + 1) * Nd;		// [Lmax+1]
+	uint32_t* Cd = Ri + (Lmax + 1);				// [Nd]
+	uint32_t* parent = Cd + Nd;				// [ncell]
+	uint32_t* zmin = parent + maxcells;			// [ncell]
+	FastDiv fw, fh;
+	fw.init ((uint32_t)w);
+	fh.init ((uint32_t)h);
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		parent[i] = (uint32_t)i;
+		zmin[i] = 0xFFFFFFFFu;
+	}
+	c.sync();
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (ibsi && !lv)
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+		const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+		if (x > 0 && (cell[i - 1] & CELL_LEVEL) == lv)
+			uf_unite (c, parent, (uint32_t)i, (uint32_t)(i - 1));
+		if (y > 0 && (cell[i - w] & CELL_LEVEL) == lv)
+			uf_unite (c, parent, (uint32_t)i, (uint32_t)(i - w));
+		if (z > 0 && (cell[i - wh] & CELL_LEVEL) == lv)
+			uf_unite (c, parent, (uint32_t)i, (uint32_t)(i - wh));
+	}
+	c.sync();
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if (ibsi && !lv)
+			continue;
+		const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+		const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+		const uint32_t root = uf_find (parent, (uint32_t)i);
+		atom_min_ret (c, zmin + root, (uint32_t)gldzm_dist2border (cell + (size_t)z * wh, w, h, x, y, !ibsi));
+	}
+	c.sync();
+	enum { Q_NS, Q_LDE, Q_ZDM, Q_GLM, Q_HGL, Q_N };
+	unsigned long long q[Q_N];
+	for (int k = 0; k < Q_N; k++)
+		q[k] = 0;
+	enum { A_SDE, A_LGL, A_SDL, A_SDH, A_LDL, A_LDH, A_N };
+	double s[A_N];
+	for (int k = 0; k < A_N; k++)
+		s[k] = 0;
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
+			continue;
+		const uint32_t dd = zmin[i];
+		atom_add (c, P + (size_t)lv * Nd + dd, 1u);
+		atom_add (c, Ri + lv, 1u);
+		atom_add (c, Cd + dd, 1u);
+		q[Q_NS] += 1;
+		q[Q_LDE] += (unsigned long long)dd * dd;
+		q[Q_ZDM] += dd;
+		q[Q_GLM] += lv;
+		q[Q_HGL] += (unsigned long long)lv * lv;
+		emphasis6_int (s, lv, dd);
+	}
+	c.sync();
+	cta_sum_u64<Q_N> (c, q);
+	cta_sum<A_N> (c, s);
+	const double Ns = (double)q[Q_NS], Nv = (double)r.area;
+	const double glm = (double)q[Q_GLM] / Ns, zdm = (double)q[Q_ZDM] / Ns;
+	unsigned long long q2[2] = { 0, 0 };
+	double t[3] = { 0, 0, 0 };
+	for (int i = c.tid; i < ncell; i += c.nthr)
+	{
+		const uint32_t lv = cell[i] & CELL_LEVEL;
+		if ((ibsi && !lv) || parent[i] != (uint32_t)i)
+			continue;
+		const uint32_t dd = zmin[i];
+		q2[0] += Ri[lv];
+		q2[1] += Cd[dd];
+		const double di = (double)lv - glm, dj = (double)dd - zdm;
+		t[0] += di * di;
+		t[1] += dj * dj;
+		t[2] += ln_count (P[(size_t)lv * Nd + dd]);
+	}
+	cta_sum_u64<2> (c, q2);
+	cta_sum<3> (c, t);
+	c.sync();
+	const size_t mw = (size_t)(Lmax + 1) * Nd + (Lmax + 1) + Nd;
+	if (mw <= (size_t)ncell * 4)		// small matrix: wipe P, Ri, Cd (contiguous)
+		wipe_words (c, mem, mw);
+	else
+	{
+		for (int i = c.tid; i < ncell; i += c.nthr)
+		{
+			const uint32_t lv = cell[i] & CELL_LEVEL;
+			if ((ibsi && !lv) || parent[i] != (uint32_t)i)
+				continue;
+			P[(size_t)lv * Nd + zmin[i]] = 0;
+			Ri[lv] = 0;
+		}
+		for (int k = c.tid; k < Nd; k += c.nthr)
+			Cd[k] = 0;
+	}
+	c.sync();
+	if (c.tid == 0)
+	{
+		const double zdnu = (double)q2[1] / Ns, glnu = (double)q2[0] / Ns;
+		out[Z_SDE] = s[A_SDE] / Ns;
+		out[Z_LDE] = (double)q[Q_LDE] / Ns;
+		out[Z_LGLZE] = s[A_LGL] / Ns;
+		out[Z_HGLZE] = (double)q[Q_HGL] / Ns;
+		out[Z_SDLGLE] = s[A_SDL] / Ns;
+		out[Z_SDHGLE] = s[A_SDH] / Ns;
+		out[Z_LDLGLE] = s[A_LDL] / Ns;
+		out[Z_LDHGLE] = s[A_LDH] / Ns;
+		out[Z_GLNU] = glnu;
+		out[Z_GLNUN] = glnu / Ns;
+		out[Z_ZDNU] = zdnu;
+		out[Z_ZDNUN] = zdnu / Ns;
+		out[Z_ZP] = Ns / Nv;
+		out[Z_GLM] = glm;
+		out[Z_GLV] = t[0] / Ns;
+		out[Z_ZDM] = zdm;
+		out[Z_ZDV] = t[1] / Ns;
+		out[Z_ZDE] = -((t[2] - Ns * log (Ns)) * INV_LN2 / Ns);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3D GLRLM (reference features/3d_glrlm.cpp): blank :113-136 (softNaN in every angle, so in the _AVE too); binned with
+// GLRLM_GREYDEPTH ("3glrlm/greydepth", 0 unless set = no binning; IBSI forces 0) :148-152; 13 directions :17-32 (dz, dy, dx), all
+// raster-forward, so the flood of :34-106 finds the maximal same-level segments of every line; level 0 neither starts nor joins
+// a run; Np = the voxel-cloud size :196; 16 features per direction :211-226 with the 32-bit products of the 2D family
+// (:556, 603, 627, 651, 675); the table keeps direction 0 only (save_value :266-281 stores vectors, the output takes [0])
+// plus the 13-direction averages :284-299.
+// region: P[Lmax][Nr] + Ri[Lmax] + Cj[Nr] (zero on entry and exit) + run length per cell
+// ------------------------------------------------------------------------------------------------
+constexpr int GLRLM3_NA = 13;
+constexpr int NCOL_GLRLM3 = 2 * R_NANGLED;
+NYX_HD size_t glrlm3d_smem_words (int Lmax, int Nr, unsigned long long maxcells)
+{
+	return (size_t)Lmax * Nr + Lmax + Nr + (size_t)maxcells;
+}
+
+NYX_D void glrlm3d_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, int Lmax, int Nr,
+	double* out)
+{
+	const int w = r.w, h = r.h, d = r.d, wh = w * h, ncell = wh * d;
+	if (r.imin == r.imax)
+	{
+		for (int i = c.tid; i < NCOL_GLRLM3; i += c.nthr)
+			out[i] = prm.softnan;
+		return;
+	}
+	uint32_t* P = mem;				// [Lmax][Nr]
+	uint32_t* Ri = P + (size_t)Lmax * Nr;		// [Lmax]
+	uint32_t* Cj = Ri + Lmax;			// [Nr]
+	uint32_t* rl = Cj + Nr;				// [ncell] length of the run starting at the cell (0: not a start)
+	FastDiv fw, fh;
+	fw.init ((uint32_t)w);
+	fh.init ((uint32_t)h);
+	double ave[R_NANGLED];
+	for (int k = 0; k < R_NANGLED; k++)
+		ave[k] = 0;
+	for (int a = 0; a < GLRLM3_NA; a++)
+	{
+		// :17-32: dz = 1 for a < 9, dy = 1, 0, -1 by threes; then dz = 0: (dy, dx) = (1,1), (1,0), (1,-1), (0,1)
+		const int dz = a < 9 ? 1 : 0;
+		const int dy = a < 9 ? 1 - a / 3 : (a < 12 ? 1 : 0);
+		const int dx = a < 9 ? 1 - a % 3 : (a < 12 ? 10 - a : 1);
+		enum { Q_SUM, Q_LRE, Q_MUI, Q_MUJ, Q_HGL, Q_N };
+		unsigned long long q[Q_N];
+		for (int k = 0; k < Q_N; k++)
+			q[k] = 0;
+		enum { A_SRE, A_LGL, A_SRL, A_SRH, A_LRL, A_LRH, A_N };
+		double s[A_N];
+		for (int k = 0; k < A_N; k++)
+			s[k] = 0;
+		const int stride = dz * wh + dy * w + dx;
+		for (int i = c.tid; i < ncell; i += c.nthr)
+		{
+			const uint32_t lv = cell[i] & CELL_LEVEL;
+			int len = 0;
+			if (lv)
+			{
+				const int row = (int)fw.div ((uint32_t)i), x = i - row * w;
+				const int z = (int)fh.div ((uint32_t)row), y = row - z * h;
+				const int px = x - dx, py = y - dy, pz = z - dz;
+				if (!(px >= 0 && px < w && py >= 0 && py < h && pz >= 0 && (cell[i - stride] & CELL_LEVEL) == lv))
+				{
+					int xx = x + dx, yy = y + dy, zz = z + dz, j = i + stride;
+					len = 1;
+					while (xx >= 0 && xx < w && yy >= 0 && yy < h && zz < d && (cell[j] & CELL_LEVEL) == lv)
+					{
+						len++;
+						xx += dx;
+						yy += dy;
+						zz += dz;
+						j += stride;
+					}
+					atom_add (c, P + (size_t)(lv - 1) * Nr + (len - 1), 1u);
+					atom_add (c, Ri + (lv - 1), 1u);
+					atom_add (c, Cj + (len - 1), 1u);
+					const uint32_t i2 = lv * lv, j2 = (uint32_t)(len * len), i2j2 = lv * lv * (uint32_t)len * (uint32_t)len;	// 32-bit wrap
+					q[Q_SUM] += 1;
+					q[Q_LRE] += (unsigned long long)len * (unsigned long long)len;
+					q[Q_MUI] += lv;
+					q[Q_MUJ] += (unsigned long long)len;
+					q[Q_HGL] += (unsigned long long)lv * (unsigned long long)lv;	// :603 double(inten) * double(inten): no wrap
+					if (lv < 65536u && (unsigned long long)i2 * (unsigned long long)j2 < 0x100000000ull)
+						emphasis6_int (s, lv, (uint32_t)len);
+					else
+					{
+						s[A_SRE] += 1.0 / (double)(len * len);
+						s[A_LGL] += 1.0 / (double)i2;
+						s[A_SRL] += 1.0 / (double)i2j2;
+						s[A_SRH] += (double)i2 / (double)(int)j2;
+						s[A_LRL] += (double)(int)j2 / (double)i2;
+						s[A_LRH] += (double)i2j2;
+					}
+				}
+			}
+			rl[i] = (uint32_t)len;
+		}
+		c.sync();
+		cta_sum_u64<Q_N> (c, q);
+		cta_sum<A_N> (c, s);
+		double f[R_NANGLED];
+		for (int k = 0; k < R_NANGLED; k++)
+			f[k] = 0.0;
+		if (q[Q_SUM])		// no run: every feature 0 (:331-333 ...), RP = 0 / Np
+		{
+			const double sum = (double)q[Q_SUM], Np = (double)r.area;
+			const double mui = (double)q[Q_MUI] / sum, muj = (double)q[Q_MUJ] / sum;
+			const double inv_sum = 1.0 / sum;
+			unsigned long long q2[2] = { 0, 0 };
+			double t[3] = { 0, 0, 0 };
+			for (int i = c.tid; i < ncell; i += c.nthr)
+			{
+				const int len = (int)rl[i];
+				if (!len)
+					continue;
+				const uint32_t lv = cell[i] & CELL_LEVEL;
+				q2[0] += Ri[lv - 1];
+				q2[1] += Cj[len - 1];
+				const double di = (double)lv - mui, dj = (double)len - muj;
+				t[0] += di * di;
+				t[1] += dj * dj;
+				const double p = (double)P[(size_t)(lv - 1) * Nr + (len - 1)] * inv_sum;
+				t[2] += fast_log10 (dadd (p, EPS_ZONES));
+			}
+			cta_sum_u64<2> (c, q2);
+			cta_sum<3> (c, t);
+			c.sync();
+			const size_t mw = (size_t)Lmax * Nr + Lmax + Nr;
+			if (mw <= (size_t)ncell * 4)		// small matrix: wipe P, Ri, Cj (contiguous)
+				wipe_words (c, mem, mw);
+			else
+				for (int i = c.tid; i < ncell; i += c.nthr)
+				{
+					const int len = (int)rl[i];
+					if (!len)
+						continue;
+					const uint32_t lv = cell[i] & CELL_LEVEL;
+					P[(size_t)(lv - 1) * Nr + (len - 1)] = 0;
+					Ri[lv - 1] = 0;
+					Cj[len - 1] = 0;
+				}
+			f[R_SRE] = s[A_SRE] / sum;
+			f[R_LRE] = (double)q[Q_LRE] / sum;
+			f[R_GLN] = (double)q2[0] / sum;
+			f[R_GLNN] = (double)q2[0] / (sum * sum);
+			f[R_RLN] = (double)q2[1] / sum;
+			f[R_RLNN] = (double)q2[1] / (sum * sum);
+			f[R_RP] = sum / Np;
+			f[R_GLV] = t[0] / sum;
+			f[R_RV] = t[1] / sum;
+			f[R_RE] = -(t[2] / sum) * (1.0 / LOG10_2);
+			f[R_LGLRE] = s[A_LGL] / sum;
+			f[R_HGLRE] = (double)q[Q_HGL] / sum;
+			f[R_SRLGLE] = s[A_SRL] / sum;
+			f[R_SRHGLE] = s[A_SRH] / sum;
+			f[R_LRLGLE] = s[A_LRL] / sum;
+			f[R_LRHGLE] = s[A_LRH] / sum;
+		}
+		c.sync();
+		for (int k = 0; k < R_NANGLED; k++)
+			ave[k] += f[k];
+		if (a == 0 && c.tid == 0)
+			for (int k = 0; k < R_NANGLED; k++)
+				out[k] = f[k];
+	}
+	if (c.tid == 0)
+		for (int k = 0; k < R_NANGLED; k++)
+			out[R_NANGLED + k] = ave[k] / (double)GLRLM3_NA;
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3D GLSZM of a LARGE cube (beyond the shared-memory size classes: organ-sized masks, whole-volume ROIs).  Same
 // semantics as glszm3d_body; everything lives in global memory: 32-bit union-find parents and zone sizes, and the
 // sparse (level, size) matrix + marginals in one open-addressing table of 64-bit keys with 32-bit counts.

@@ -244,12 +244,13 @@ _VALID_KEYS_3D = {
 
 class Nyxus3D:
     """3D feature extraction (reference nyxus.py:923-1489) for the 3D families on this path: first-order
-    (*3D_ALL_INTENSITY*), *3D_GLCM*, *3D_GLSZM*, *3D_NGTDM* on a B200.
+    (*3D_ALL_INTENSITY*) and *3D_ALL_TEXTURE* (= *3D_GLCM*, *3D_GLSZM*, *3D_NGTDM*, *3D_GLDM*, *3D_GLRLM*, *3D_GLDZM*, *3D_NGLDM*)
+    on a B200.
 
     Like the reference, the class has no in-memory entry point of its own: `featurize_files` /
     `featurize_directory` read NIfTI volumes.  `featurize(volume, labels)` is an addition for callers that already hold
     the voxels.  Metaparameters follow the reference: only 3glcm/greydepth has a default (coarse_gray_depth);
-    3glszm/greydepth, 3ngtdm/greydepth and 3ngtdm/radius are 0 until set with `set_metaparam` (env_features.cpp:712-736)."""
+    3glszm/greydepth, 3gldm/greydepth, 3glrlm/greydepth, 3ngtdm/greydepth and 3ngtdm/radius are 0 until set with `set_metaparam` (env_features.cpp:712-736)."""
 
     def __init__(self, features: List[str], **kwargs):
         invalid_keys = set(kwargs.keys()) - _VALID_KEYS_3D

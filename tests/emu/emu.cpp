@@ -143,9 +143,13 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 }
 
 
-// ---- 3D: one labelled volume [D][H][W], label value `lab`; fam_mask bits: 1 INT, 2 GLCM, 4 NGTDM, 8 GLSZM.
-// out layout: 36 first-order | 30x13 + 29 GLCM | 5 NGTDM | 16 GLSZM   (the canonical 3D table of the library)
-extern "C" int nyxemu_ncols3d() { return NCOL_INT + NCOL_GLCM3 + NCOL_NGTDM + NCOL_GLSZM + NCOL_GLDM; }
+// ---- 3D: one labelled volume [D][H][W], label value `lab`; fam_mask bits: 1 INT, 2 GLCM, 4 NGTDM, 8 GLSZM, 16 GLDM, 32 GLRLM,
+// 64 GLDZM, 128 NGLDM.
+// out layout: 36 first-order | 30x13 + 29 GLCM | 5 NGTDM | 16 GLSZM | 14 GLDM | 32 GLRLM | 18 GLDZM | 19 NGLDM   (the canonical
+// 3D table of the library)
+extern "C" int nyxemu_ncols3d() { return NCOL_INT + NCOL_GLCM3 + NCOL_NGTDM + NCOL_GLSZM + NCOL_GLDM + NCOL_GLRLM3 + NCOL_GLDZM + NCOL_NGLDM; }
+static int g_glrlm3_greydepth = 0;	// "3glrlm/greydepth" (0 = no binning)
+extern "C" void nyxemu_set_glrlm3_greydepth (int g) { g_glrlm3_greydepth = g; }
 static int g_gldm3_greydepth = 0;	// "3gldm/greydepth" (0 = no binning)
 extern "C" void nyxemu_set_gldm3_greydepth (int g) { g_gldm3_greydepth = g; }
 static bool g_big3d = false;	// 3D GLSZM through the large-cube body
@@ -193,6 +197,8 @@ extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl,
 	for (int i = 0; i < n3; i++)
 		out[i] = 0;
 	const int O_GLCM = NCOL_INT, O_NGTDM = O_GLCM + NCOL_GLCM3, O_GLSZM = O_NGTDM + NCOL_NGTDM, O_GLDM = O_GLSZM + NCOL_GLSZM;
+	const int O_GLRLM = O_GLDM + NCOL_GLDM, O_GLDZM = O_GLRLM + NCOL_GLRLM3, O_NGLDM = O_GLDZM + NCOL_GLDZM;
+	const int maxdim = std::max (r.w, std::max (r.h, r.d));
 	std::vector<uint32_t> cell (ncell);
 	if (fam_mask & 1)
 	{
@@ -200,18 +206,40 @@ extern "C" int nyxemu_roi_features_3d (const uint32_t* vol, const uint32_t* lbl,
 		std::vector<uint32_t> mem (intensity_smem_words (npad, greydepth));
 		intensity_body (c, r, prm, cloud.data(), r.area, npad, mem.data(), out);
 	}
-	for (int fam = 1; fam <= 4; fam++)
+	for (int fam = 1; fam <= 7; fam++)
 	{
-		const unsigned bit = fam == 1 ? 2u : fam == 2 ? 8u : fam == 3 ? 4u : 16u;	// GLCM, GLSZM, NGTDM, GLDM
-		if (!(fam_mask & bit))
+		static const unsigned bits[8] = { 1u, 2u, 8u, 4u, 16u, 32u, 64u, 128u };	// INT, GLCM, GLSZM, NGTDM, GLDM, GLRLM, GLDZM, NGLDM
+		if (!(fam_mask & bits[fam]))
 			continue;
-		int g = fam == 1 ? glcm_g : fam == 2 ? glszm_g : fam == 3 ? ngtdm_g : g_gldm3_greydepth;
+		int g = fam == 1 ? glcm_g : fam == 2 ? glszm_g : fam == 3 ? ngtdm_g : fam == 4 ? g_gldm3_greydepth : fam == 5 ? g_glrlm3_greydepth : greydepth;
 		if (ibsi)
 			g = 0;
 		Binner B;
-		B.init (g, r.imin, r.imax);
+		if (fam == 7)
+			B.init_tg (g, r.imax, ibsi != 0);
+		else
+			B.init (g, r.imin, r.imax);
 		load_cube (c, im, r, B, cell.data());
 		int Lm = g != 0 ? std::abs (g) : (int)std::max (r.imax, 1u);
+		if (fam == 5)
+		{
+			std::vector<uint32_t> mem (glrlm3d_smem_words (Lm, maxdim, (unsigned long long)ncell));
+			glrlm3d_body (c, r, prm, cell.data(), mem.data(), Lm, maxdim, out + O_GLRLM);
+			continue;
+		}
+		if (fam == 6)
+		{
+			const int Nd = gldzm_nd_bound ((uint32_t)ncell, maxdim);
+			std::vector<uint32_t> mem (gldzm3d_smem_words (Lm, Nd, (unsigned long long)ncell));
+			gldzm3d_body (c, r, prm, cell.data(), mem.data(), Lm, Nd, (unsigned long long)ncell, out + O_GLDZM);
+			continue;
+		}
+		if (fam == 7)
+		{
+			std::vector<uint32_t> mem (ngldm3d_smem_words (Lm));
+			ngldm3d_body (c, r, prm, cell.data(), mem.data(), Lm, out + O_NGLDM);
+			continue;
+		}
 		if (fam == 1)
 		{
 			std::vector<uint32_t> mem (glcm_smem_words<false> (Lm, 4, g < 0));

@@ -139,9 +139,13 @@ def load_golden_vol():
 
 
 def canonical3d_index(cols):
-    """position of every reference 3D column in the library's canonical 3D table (36 | 30x13+29 | 5 | 16 | 14)"""
-    idx, nave, pi, pn, pz, pd = [], 0, 0, 0, 0, 0
+    """position of every reference 3D column in the library's canonical 3D table (36 | 30x13+29 | 5 | 16 | 14 | 32 | 18 | 19)"""
+    idx, nave, pi = [], 0, 0
+    base = {"3NGTDM_": 36 + 419, "3GLSZM_": 36 + 419 + 5, "3GLDM_": 36 + 419 + 5 + 16, "3GLRLM_": 36 + 419 + 5 + 16 + 14,
+            "3GLDZM_": 36 + 419 + 5 + 16 + 14 + 32, "3NGLDM_": 36 + 419 + 5 + 16 + 14 + 32 + 18}
+    pos = dict.fromkeys(base, 0)
     for c in cols:
+        fam = next((f for f in base if c.startswith(f)), None)
         if c.startswith("3GLCM_"):
             s = c[6:]
             if s.endswith("_AVE"):
@@ -149,15 +153,13 @@ def canonical3d_index(cols):
                 nave += 1
             else:
                 idx.append(36 + G3.index(s) * 13)
-        elif c.startswith("3NGTDM_"):
-            idx.append(36 + 419 + pn)
-            pn += 1
-        elif c.startswith("3GLSZM_"):
-            idx.append(36 + 419 + 5 + pz)
-            pz += 1
-        elif c.startswith("3GLDM_"):
-            idx.append(36 + 419 + 5 + 16 + pd)
-            pd += 1
+        elif fam == "3GLRLM_":                                       # 16 direction-0 values, then the 16 averages
+            ave = c.endswith("_AVE")
+            names = [x for x in cols if x.startswith("3GLRLM_") and x.endswith("_AVE") == ave]
+            idx.append(base[fam] + (16 if ave else 0) + names.index(c))
+        elif fam:
+            idx.append(base[fam] + pos[fam])
+            pos[fam] += 1
         else:
             idx.append(pi)
             pi += 1
@@ -170,7 +172,7 @@ def emu_roi_features_3d(L, vol, lbl, lab, g, gz, gn, rad, ibsi, cols, fam_mask=1
     M = np.ascontiguousarray(lbl, np.uint32)
     fg = V[M > 0]
     den = float(fg.max()) - float(fg.min())
-    out = np.zeros(36 + 419 + 5 + 16 + 14)
+    out = np.zeros(36 + 419 + 5 + 16 + 14 + 32 + 18 + 19)
     D, H, W = V.shape
     rc = L.nyxemu_roi_features_3d(V.ctypes.data, M.ctypes.data, D, H, W, int(lab), int(g), int(gz), int(gn), int(rad), int(bool(ibsi)),
                                   den, fam_mask, out.ctypes.data)

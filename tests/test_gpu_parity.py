@@ -407,7 +407,7 @@ def test_nyxus3d_featurize_files_nifti(tmp_path):
     for c in df.columns[4:]:
         assert not tu.mismatches(ref_tab[:, cols.index(c)], df[c].to_numpy()), c
     with pytest.raises(NyxusError_or_ValueError()):
-        Nyxus3D(["*3D_ALL_TEXTURE*"])                    # holds 3D families outside this path
+        Nyxus3D(["*3D_ALL*"])                            # holds 3D families outside this path (surface morphology)
     with pytest.raises(ValueError, match="not a valid 3D feature name"):
         Nyxus3D(["GLCM_ASM"])
 
@@ -660,5 +660,58 @@ def test_3d_gldm_against_reference_golden(g):
         assert np.array_equal(tab[:, 0].astype(np.int64), Zv["GLDM/labels"])
         bad = tu.mismatches(Zv["GLDM/table_%d" % g], tab[:, 2:], e.columns)
         assert not bad, bad[:8]
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("g", [0, 16, -12])
+def test_3d_glrlm_against_reference_golden(g):
+    from nyxus_b200 import Engine
+    Zv = np.load(os.path.join(tu.GOLDEN, "golden_vol_more.npz"))
+    e = Engine(["*3D_GLRLM*"], dim=3)
+    try:
+        e.set_param("3glrlm/greydepth", g)
+        tab, _ = e.featurize_volume(Zv["vol"], Zv["label"])
+        assert e.columns == [str(c) for c in Zv["GLRLM/columns"]]
+        bad = tu.mismatches(Zv["GLRLM/table_%d" % g], tab[:, 2:], e.columns)
+        assert not bad, bad[:8]
+    finally:
+        e.close()
+
+
+@pytest.mark.parametrize("fam", ["GLDZM", "NGLDM"])
+@pytest.mark.parametrize("tag", ["64", "20", "ibsi"])
+def test_3d_gldzm_ngldm_against_reference_golden(fam, tag):
+    from nyxus_b200 import Engine
+    Zv = np.load(os.path.join(tu.GOLDEN, "golden_vol_more.npz"))
+    kw = {"ibsi": True} if tag == "ibsi" else {"coarse_gray_depth": int(tag)}
+    e = Engine(["*3D_%s*" % fam], dim=3, **kw)
+    try:
+        tab, _ = e.featurize_volume(Zv["vol"], Zv["label"])
+        assert e.columns == [str(c) for c in Zv[fam + "/columns"]]
+        assert np.array_equal(tab[:, 0].astype(np.int64), Zv[fam + "/labels"])
+        bad = tu.mismatches(Zv["%s/table_%s" % (fam, tag)], tab[:, 2:], e.columns)
+        assert not bad, bad[:8]
+    finally:
+        e.close()
+
+
+def test_3d_all_texture_group_and_edge_case_rois():
+    """*3D_ALL_TEXTURE* = the seven 3D texture families in one call; the edge-case volume (slab, plate, blank ROI, single voxel,
+    zeros) of golden_vol_more.npz against the reference's values for the four later families"""
+    from nyxus_b200 import Engine
+    Zv = np.load(os.path.join(tu.GOLDEN, "golden_vol_more.npz"))
+    e = Engine(["*3D_ALL_TEXTURE*"], dim=3, coarse_gray_depth=5)
+    try:
+        e.set_param("3gldm/greydepth", 5)
+        e.set_param("3glrlm/greydepth", -4)
+        tab, _ = e.featurize_volume(Zv["e/vol"], Zv["e/label"])
+        cols = e.columns
+        assert np.array_equal(tab[:, 0].astype(np.int64), Zv["e/GLDM/labels"])
+        for fam, tag in (("GLDM", "5"), ("GLRLM", "-4"), ("GLDZM", "5"), ("NGLDM", "5")):
+            fc = [str(c) for c in Zv[fam + "/columns"]]
+            sel = [cols.index(c) for c in fc]
+            bad = tu.mismatches(tu.finite0(Zv["e/%s/table_%s" % (fam, tag)]), tu.finite0(tab[:, 2:][:, sel]), fc)
+            assert not bad, (fam, bad[:8])
     finally:
         e.close()

@@ -161,9 +161,10 @@ def test_cabi_device_free_validation_and_device_count():
     assert val(2, ["*ALL_TEXTURE*", "*ALL_INTENSITY*", "GLCM_ASM", "MEAN"])[0] == 0
     rc, m = val(2, ["GLCM_NOPE"])
     assert rc == -1 and "not a valid 2D feature name" in m
-    rc, m = val(3, ["*3D_ALL_TEXTURE*"])
+    rc, m = val(3, ["*3D_ALL_MORPHOLOGY*"])
     assert rc == -3 and "outside this path" in m
     assert val(3, ["*3D_GLCM*", "3MEAN"])[0] == 0
+    assert val(3, ["*3D_ALL_TEXTURE*", "3GLRLM_SRE_AVE", "3GLDZM_ZDE", "3NGLDM_DCP"])[0] == 0
     assert val(4, ["MEAN"])[0] == -1
     import torch
     if not torch.cuda.is_available():

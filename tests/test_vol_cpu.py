@@ -55,6 +55,7 @@ def test_3d_feature_bodies_randomised_against_compiled_reference():
         labs, tab, _ = ref.featurize_3d(V.astype(np.uint32), M, greydepth=g, glszm_greydepth=gz, ngtdm_greydepth=gn, ngtdm_radius=rad, ibsi=ibsi)
         got = tu.emu_roi_features_3d(L, V, M, 7, g, gz, gn, rad, ibsi, cols)
         assert not tu.mismatches(tab[0], got, cols), (it, kind, ibsi)
+ZM = np.load(os.path.join(tu.GOLDEN, "golden_vol_more.npz"))
 
 
 def test_nifti_round_trip(tmp_path):
@@ -80,8 +81,11 @@ def test_3d_column_contract_of_the_library():
     names = [ln.split('"')[1] for ln in rows]
     codes = [int(ln.split(",")[1]) for ln in rows]
     assert codes == sorted(codes)
-    extra = [n for n in names if n.startswith("3GLDM_")]                # appended 3D families
-    assert [n for n in names if n not in extra] == GV["columns"] and len(names) == 116 + len(extra) and len(extra) == 14
+    extra = [n for n in names if n.startswith(("3GLDM_", "3GLRLM_", "3GLDZM_", "3NGLDM_"))]          # the later 3D families
+    assert [n for n in names if n not in extra] == GV["columns"] and len(names) == 116 + len(extra) and len(extra) == 14 + 32 + 18 + 19
+    # the reference's own column order of every family, as its pybind module returned it (golden_vol_more.npz)
+    for fam in ("GLDM", "GLRLM", "GLDZM", "NGLDM"):
+        assert [n for n in names if n.startswith("3%s_" % fam)] == [str(c) for c in ZM[fam + "/columns"]]
 
 
 @pytest.mark.skipif(not ref.available(), reason="oracle/_ref/libnyxus_ref.so not built")
@@ -109,9 +113,6 @@ def test_3d_ngtdm_radius_above_one_and_large_cube_glszm_against_compiled_referen
         L.nyxemu_set_big3d(0)
 
 
-ZM = np.load(os.path.join(tu.GOLDEN, "golden_vol_more.npz"))
-
-
 @pytest.mark.parametrize("g", [0, 16, -12])
 def test_3d_gldm_body_matches_reference_golden(g):
     """3D GLDM: golden_vol_more.npz = the reference's own pybind module on a NIfTI volume (make_golden3d_more.py)"""
@@ -125,3 +126,62 @@ def test_3d_gldm_body_matches_reference_golden(g):
             assert not bad, (g, int(lab), bad[:4])
     finally:
         L.nyxemu_set_gldm3_greydepth(0)
+
+
+@pytest.mark.parametrize("g", [0, 16, -12])
+def test_3d_glrlm_body_matches_reference_golden(g):
+    """3D GLRLM: direction 0 of 13 + the 13-direction averages (3d_glrlm.cpp:266-299)"""
+    L = tu.build_emu()
+    cols = [str(c) for c in ZM["GLRLM/columns"]]
+    try:
+        L.nyxemu_set_glrlm3_greydepth(g)
+        for k, lab in enumerate(ZM["GLRLM/labels"]):
+            got = tu.emu_roi_features_3d(L, ZM["vol"], ZM["label"], int(lab), 64, 0, 0, 0, False, cols, fam_mask=32)
+            bad = tu.mismatches(ZM["GLRLM/table_%d" % g][k], got, cols)
+            assert not bad, (g, int(lab), bad[:4])
+    finally:
+        L.nyxemu_set_glrlm3_greydepth(0)
+
+
+@pytest.mark.parametrize("fam,bit", [("GLDZM", 64), ("NGLDM", 128)])
+@pytest.mark.parametrize("tag", ["64", "20", "ibsi"])
+def test_3d_gldzm_ngldm_bodies_match_reference_golden(fam, bit, tag):
+    """3D GLDZM (6-connected zones, in-slice distances) and 3D NGLDM (24-neighbour dependence of interior voxels): both are
+    binned by the coarse grey depth of the constructor; 'ibsi' = IBSI mode (no binning)"""
+    L = tu.build_emu()
+    cols = [str(c) for c in ZM[fam + "/columns"]]
+    depth, ibsi = (64, True) if tag == "ibsi" else (int(tag), False)
+    for k, lab in enumerate(ZM[fam + "/labels"]):
+        got = tu.emu_roi_features_3d(L, ZM["vol"], ZM["label"], int(lab), depth, 0, 0, 0, ibsi, cols, fam_mask=bit)
+        bad = tu.mismatches(ZM["%s/table_%s" % (fam, tag)][k], got, cols)
+        assert not bad, (fam, tag, int(lab), bad[:4])
+
+
+def _edge_rows(L, fam, tag, bit, depth, ibsi):
+    cols = [str(c) for c in ZM[fam + "/columns"]]
+    for k, lab in enumerate(ZM["e/%s/labels" % fam]):
+        got = tu.emu_roi_features_3d(L, ZM["e/vol"], ZM["e/label"], int(lab), depth, 0, 0, 0, ibsi, cols, fam_mask=bit)
+        bad = tu.mismatches(tu.finite0(ZM["e/%s/table_%s" % (fam, tag)][k]), got, cols)
+        assert not bad, (fam, tag, int(lab), bad[:4])
+
+
+@pytest.mark.parametrize("g", [0, 5, -4])
+def test_3d_gldm_glrlm_edge_cases_against_reference_golden(g):
+    """one-slice slab, two-slice plate, constant (blank) ROI, single voxel, intensity-0 voxels, long runs"""
+    L = tu.build_emu()
+    try:
+        L.nyxemu_set_gldm3_greydepth(g)
+        L.nyxemu_set_glrlm3_greydepth(g)
+        _edge_rows(L, "GLDM", str(g), 16, 64, False)
+        _edge_rows(L, "GLRLM", str(g), 32, 64, False)
+    finally:
+        L.nyxemu_set_gldm3_greydepth(0)
+        L.nyxemu_set_glrlm3_greydepth(0)
+
+
+@pytest.mark.parametrize("tag", ["64", "5", "ibsi"])
+def test_3d_gldzm_ngldm_edge_cases_against_reference_golden(tag):
+    L = tu.build_emu()
+    depth, ibsi = (64, True) if tag == "ibsi" else (int(tag), False)
+    _edge_rows(L, "GLDZM", tag, 64, depth, ibsi)
+    _edge_rows(L, "NGLDM", tag, 128, depth, ibsi)
