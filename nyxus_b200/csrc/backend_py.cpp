@@ -63,6 +63,7 @@ struct Env
 	std::string gabor[7];
 	nyxb200_ctx* ctx = nullptr;
 	bool ctx_stale = true;		// metaparameters changed since they were pushed to ctx
+	std::string arrow_path;		// file written by the last arrowipc / parquet call (ArrowOutputStream::get_arrow_path)
 
 	~Env()
 	{
@@ -166,10 +167,104 @@ py::array string_columns (const std::vector<std::string>& inames, const std::vec
 	throw std::runtime_error (std::string (what) + " is outside the texture + intensity path of the nyxus_b200 backend");
 }
 
+// ---- Arrow IPC / Parquet output (reference: arrow_output_stream.cpp, output_writers.cpp, arrow_helpers.cpp).  The reference links
+// libarrow; this module drives the interpreter's pyarrow (like its image decoding drives the interpreter's OpenCV / Pillow) and fails
+// with the reference's own message where pyarrow is absent.
+bool have_pyarrow()
+{
+	try
+	{
+		py::module_::import ("pyarrow");
+		return true;
+	}
+	catch (py::error_already_set&)
+	{
+		return false;
+	}
+}
+
+bool is_arrow_type (const std::string& output_type)
+{
+	return output_type == "arrowipc" || output_type == "parquet";
+}
+
 void check_output_type (const std::string& output_type)
 {
-	if (output_type == "arrowipc" || output_type == "parquet")
+	if (is_arrow_type (output_type) && !have_pyarrow())
 		throw std::runtime_error ("Arrow functionality is not available. Rebuild Nyxus with Arrow enabled.");	// reference :1038,1052
+}
+
+bool ends_with (const std::string& s, const char* t)
+{
+	const size_t n = strlen (t);
+	return s.size() >= n && s.compare (s.size() - n, n, t) == 0;
+}
+
+// arrow_helpers.cpp:9-62: directory (existing, or spelled with a trailing separator, or without extension under a missing parent)
+// -> default file name inside it; the extension always follows the output type
+std::string arrow_filename (const std::string& output_path, bool parquet)
+{
+	const char* ext = parquet ? ".parquet" : ".arrow";
+	if (output_path.empty())
+		return std::string ("NyxusFeatures") + ext;
+	fs::path p (output_path);
+	if (fs::is_directory (p) || ends_with (output_path, "/") || ends_with (output_path, "\\"))
+		p = p / "NyxusFeatures";
+	else if (!p.has_extension() && !fs::is_directory (p.parent_path()))
+		p = p / "NyxusFeatures";
+	p.replace_extension (ext);
+	return p.string();
+}
+
+// header[0..1] utf8, header[2] (ROI_label) int32, the rest float64 (output_writers.cpp:21-30, 228-237); one record batch
+void write_arrow (Env& e, const py::object& header, const py::object& strs, const py::object& num, const std::string& output_type,
+	const std::string& output_path)
+{
+	const bool parquet = output_type == "parquet";
+	const std::string path = arrow_filename (output_path, parquet);
+	e.arrow_path = path;
+	const fs::path parent = fs::path (path).parent_path();
+	if (!parent.empty() && !fs::is_directory (parent))
+		fs::create_directory (parent);		// arrow_output_stream.cpp:19-27 (one level, like the reference)
+	py::module_ pa = py::module_::import ("pyarrow"), np = py::module_::import ("numpy");
+	py::list names, arrays;
+	const py::ssize_t ncol = py::len (header);
+	const py::object all = py::slice (py::none(), py::none(), py::none());
+	for (py::ssize_t k = 0; k < ncol; k++)
+	{
+		names.append (py::str (header.attr ("__getitem__") (k)));
+		if (k < 2)
+			arrays.append (pa.attr ("array") (strs.attr ("__getitem__") (py::make_tuple (all, k)).attr ("tolist") (), py::arg ("type") = pa.attr ("utf8") ()));
+		else
+		{
+			py::object col = np.attr ("ascontiguousarray") (num.attr ("__getitem__") (py::make_tuple (all, k - 2)));
+			if (k == 2)
+				col = col.attr ("astype") (np.attr ("int32"));
+			arrays.append (pa.attr ("array") (col));
+		}
+	}
+	py::object table = pa.attr ("Table").attr ("from_arrays") (arrays, py::arg ("names") = names);
+	if (parquet)
+		py::module_::import ("pyarrow.parquet").attr ("write_table") (table, path);	// the Arrow schema is stored with the file (output_writers.cpp:40-43)
+	else
+	{
+		py::object sink = pa.attr ("OSFile") (path, "wb");
+		py::object writer = pa.attr ("ipc").attr ("new_file") (sink, table.attr ("schema"));
+		writer.attr ("write_table") (table);
+		writer.attr ("close") ();
+		sink.attr ("close") ();
+	}
+}
+
+// the tail of every featurize_*_imp: the buffers as they are, or an Arrow file and the reference's empty / one-element tuple
+py::tuple finish_output (Env& e, const py::tuple& res, const std::string& output_type, const std::string& output_path, bool montage)
+{
+	if (!is_arrow_type (output_type))
+		return res;
+	write_arrow (e, res[0], res[1], res[2], output_type, output_path);
+	if (montage)
+		return py::make_tuple (std::string (""));	// new_bindings_py.cpp:643
+	return py::tuple (0);				// new_bindings_py.cpp:559
 }
 
 // ---- minimal NIfTI-1 reader (single-file .nii / .nii.gz) for the Nyxus3D entry points.  The reference decodes with its
@@ -515,7 +610,6 @@ py::tuple featurize_fname_lists_imp (uint64_t instid, const py::list& int_fnames
 		throw std::runtime_error ("featurize_fname_lists_imp needs a 2D instance");
 	e.single_roi = single_roi;
 	check_output_type (output_type);
-	(void)output_path;
 	std::vector<std::string> ifiles, mfiles;
 	for (auto it : int_fnames) ifiles.push_back (it.cast<std::string>());
 	// reference :664-676, :709-723
@@ -533,7 +627,7 @@ py::tuple featurize_fname_lists_imp (uint64_t instid, const py::list& int_fnames
 			if (!fs::exists (f))
 				throw std::runtime_error ("File does not exist: " + f);
 	}
-	return featurize_images (e, ifiles, mfiles, single_roi);
+	return finish_output (e, featurize_images (e, ifiles, mfiles, single_roi), output_type, output_path, false);
 }
 
 py::tuple featurize_directory_imp (uint64_t instid, const std::string& intensity_dir, const std::string& labels_dir,
@@ -543,7 +637,6 @@ py::tuple featurize_directory_imp (uint64_t instid, const std::string& intensity
 	if (e.dim != 2)
 		throw std::runtime_error ("featurize_directory_imp needs a 2D instance");
 	check_output_type (output_type);
-	(void)output_path;
 	std::regex rx;
 	try
 	{
@@ -573,7 +666,7 @@ py::tuple featurize_directory_imp (uint64_t instid, const std::string& intensity
 				throw std::runtime_error ("Error reading the dataset: missing mask file " + mfiles.back());
 		}
 	}
-	return featurize_images (e, ifiles, mfiles, single);
+	return finish_output (e, featurize_images (e, ifiles, mfiles, single), output_type, output_path, false);
 }
 
 py::tuple featurize_montage_imp (
@@ -590,7 +683,6 @@ py::tuple featurize_montage_imp (
 		throw std::runtime_error ("featurize_montage_imp needs a 2D instance");
 	e.single_roi = false;
 	check_output_type (output_type);
-	(void)output_path;
 	auto ib = intensity_images.request(), lb = label_images.request();
 	if (ib.ndim != 3 || lb.ndim != 3)
 		throw std::invalid_argument ("Intensity and label arrays must be 3-dimensional [n, rows, cols]");
@@ -617,7 +709,7 @@ py::tuple featurize_montage_imp (
 	py::array header = header_array (c);
 	py::array strs = string_columns (intensity_names, label_names, row_image, nrows);
 	py::array num = table_to_numpy (c, t);
-	return py::make_tuple (header, strs, num, std::string (""));
+	return finish_output (e, py::make_tuple (header, strs, num, std::string ("")), output_type, output_path, true);
 }
 
 // volumes of a file list -> one table (reference: processDataset_3D_segmented, workflow_3d_segmented.cpp:35-260)
@@ -701,7 +793,6 @@ py::tuple featurize_fname_lists_3D_imp (
 		throw std::runtime_error ("featurize_fname_lists_3D_imp needs a 3D instance");
 	e.single_roi = single_roi;
 	check_output_type (output_type);
-	(void)output_path;
 	std::vector<std::string> ifiles, mfiles;
 	for (auto it : pyside_int_fnames) ifiles.push_back (it.cast<std::string>());
 	for (auto it : pyside_seg_fnames) mfiles.push_back (it.cast<std::string>());
@@ -722,7 +813,7 @@ py::tuple featurize_fname_lists_3D_imp (
 		if (!single_roi && !fs::exists (mfiles[i]))
 			throw std::runtime_error ("File does not exist: " + mfiles[i]);
 	}
-	return featurize_volumes (e, ifiles, mfiles, single_roi);
+	return finish_output (e, featurize_volumes (e, ifiles, mfiles, single_roi), output_type, output_path, false);
 }
 
 py::tuple featurize_directory_3D_imp (
@@ -737,7 +828,6 @@ py::tuple featurize_directory_3D_imp (
 	if (e.dim != 3)
 		throw std::runtime_error ("featurize_directory_3D_imp needs a 3D instance");
 	check_output_type (output_type);
-	(void)output_path;
 	std::regex rx;
 	try
 	{
@@ -767,7 +857,7 @@ py::tuple featurize_directory_3D_imp (
 				throw std::runtime_error ("Error reading the dataset: missing mask file " + mfiles.back());
 		}
 	}
-	return featurize_volumes (e, ifiles, mfiles, single);
+	return finish_output (e, featurize_volumes (e, ifiles, mfiles, single), output_type, output_path, false);
 }
 
 py::tuple findrelations_imp (uint64_t, std::string&, std::string&, std::string&)
@@ -881,19 +971,21 @@ std::map<std::string, ParameterTypes> get_params_imp (uint64_t instid, const std
 	return subset;
 }
 
-std::string get_arrow_file_imp (uint64_t)
+std::string get_arrow_file_imp (uint64_t instid)
 {
-	throw std::runtime_error ("Arrow functionality is not available. Rebuild Nyxus with Arrow enabled.");
+	if (!have_pyarrow())
+		throw std::runtime_error ("Arrow functionality is not available. Rebuild Nyxus with Arrow enabled.");
+	return findenv (instid).arrow_path;
 }
 
-std::string get_parquet_file_imp (uint64_t)
+std::string get_parquet_file_imp (uint64_t instid)
 {
-	throw std::runtime_error ("Arrow functionality is not available. Rebuild Nyxus with Arrow enabled.");
+	return get_arrow_file_imp (instid);
 }
 
 bool arrow_is_enabled_imp (uint64_t)
 {
-	return false;
+	return have_pyarrow();
 }
 
 // ---- metaparameters (env_metaparams.cpp:63-247): "<feature>/<param>=<value>"

@@ -5,6 +5,7 @@ checks, error messages, DataFrame layout and column names (reference src/nyx/pyt
 but the work is done by the B200 library through the C ABI (include/nyxus_b200.h).  Feature names outside the
 texture/intensity path raise ValueError exactly like an unknown feature name does in the reference
 (env_features.cpp:496)."""
+import os
 from typing import List, Optional
 
 import numpy as np
@@ -21,6 +22,53 @@ _VALID_KEYS = {
     'max_intensity', 'ram_limit', 'verbose',
     'anisotropy_x', 'anisotropy_y', 'mergerois', 'preserve_hu'
 }
+
+
+
+# ---- Arrow IPC / Parquet output (reference arrow_helpers.cpp:9-62, output_writers.cpp:21-30,228-237): written with pyarrow
+def _need_pyarrow():
+    try:
+        import pyarrow  # noqa: F401
+    except ImportError:
+        raise RuntimeError("Arrow functionality is not available. Rebuild Nyxus with Arrow enabled.")
+
+
+def arrow_filename(output_path: str, parquet: bool) -> str:
+    """the reference's get_arrow_filename: a directory (existing, spelled with a trailing separator, or extension-less under a
+    missing parent) receives NyxusFeatures.<ext>; the extension always follows the output type"""
+    ext = ".parquet" if parquet else ".arrow"
+    if not output_path:
+        return "NyxusFeatures" + ext
+    p = output_path
+    if os.path.isdir(p) or p.endswith("/") or p.endswith("\\"):
+        p = os.path.join(p, "NyxusFeatures")
+    elif not os.path.splitext(os.path.basename(p))[1] and not os.path.isdir(os.path.dirname(p)):
+        p = os.path.join(p, "NyxusFeatures")
+    return os.path.splitext(p)[0] + ext if os.path.splitext(os.path.basename(p))[1] else p + ext
+
+
+def _emit(obj, df, output_type, output_path):
+    """the DataFrame, or the path of the Arrow IPC / Parquet file it was written to (utf8, utf8, int32, float64...)"""
+    if output_type == 'pandas':
+        return df
+    import pyarrow as pa
+    path = arrow_filename(output_path, output_type == 'parquet')
+    parent = os.path.dirname(path)
+    if parent and not os.path.isdir(parent):
+        os.mkdir(parent)
+    cols = [pa.array(df[c].astype(str).tolist(), type=pa.utf8()) for c in df.columns[:2]]
+    cols.append(pa.array(df[df.columns[2]].to_numpy().astype(np.int32)))
+    cols += [pa.array(np.ascontiguousarray(df[c].to_numpy(np.float64))) for c in df.columns[3:]]
+    table = pa.Table.from_arrays(cols, names=[str(c) for c in df.columns])
+    if output_type == 'parquet':
+        import pyarrow.parquet as pq
+        pq.write_table(table, path)
+    else:
+        with pa.OSFile(path, "wb") as sink:
+            with pa.ipc.new_file(sink, table.schema) as w:
+                w.write_table(table)
+    obj._arrow_path = path
+    return path
 
 
 class Nyxus:
@@ -90,6 +138,20 @@ class Nyxus:
     def feature_columns(self):
         return self._engine.columns
 
+    # reference nyxus.py:870-920
+    def get_arrow_ipc_file(self):
+        return getattr(self, "_arrow_path", "")
+
+    def get_parquet_file(self):
+        return getattr(self, "_arrow_path", "")
+
+    def arrow_is_enabled(self):
+        try:
+            import pyarrow  # noqa: F401
+            return True
+        except ImportError:
+            return False
+
     def featurize(self, intensity_images: np.ndarray, label_images: np.ndarray, intensity_names: list = [],
                   label_names: list = [], output_type: Optional[str] = "pandas", output_path: Optional[str] = ""):
         if (output_type != "" and output_type not in self._valid_output_types):
@@ -101,7 +163,7 @@ class Nyxus:
         if (output_type not in self._valid_output_types):
             raise ValueError(f'Invalid output type {output_type}. Valid output types are {self._valid_output_types}.')
         if output_type != 'pandas':
-            raise ValueError("arrowipc / parquet writers are outside the texture/intensity path implemented by nyxus_b200")
+            _need_pyarrow()
 
         if intensity_images.ndim == 2:
             if label_images.ndim != 2:
@@ -154,7 +216,7 @@ class Nyxus:
         df.insert(0, "intensity_image", pd.array([str(v) for v in intensity_names], dtype=sdt).take(row_img))
         if "ROI_label" in df.columns:
             df.ROI_label = df.ROI_label.astype(np.uint32)
-        return df
+        return _emit(self, df, output_type, output_path)
 
 
     # ---- file-based entry points (reference nyxus.py:303-384, 524-600; new_bindings_py.cpp:224-384, 647-752)
@@ -170,7 +232,7 @@ class Nyxus:
         if output_type not in self._valid_output_types:
             raise ValueError(f'Invalid output type {output_type}. Valid output types are {self._valid_output_types}.')
         if output_type != 'pandas':
-            raise ValueError("arrowipc / parquet writers are outside the texture/intensity path implemented by nyxus_b200")
+            _need_pyarrow()
         if len(intensity_files) == 0:
             raise RuntimeError("Intensity file list is blank")
         if not single_roi and len(intensity_files) != len(mask_files):
@@ -206,7 +268,7 @@ class Nyxus:
         if "ROI_label" in df.columns:
             df.ROI_label = df.ROI_label.astype(np.uint32)
         self.error_message = ''
-        return df
+        return _emit(self, df, output_type, output_path)
 
     def featurize_directory(self, intensity_dir: str, label_dir: Optional[str] = None, file_pattern: Optional[str] = ".*",
                             output_type: Optional[str] = "pandas", output_path: Optional[str] = ""):
@@ -296,6 +358,20 @@ class Nyxus3D:
     def feature_columns(self):
         return self._engine.columns
 
+    # reference nyxus.py:870-920
+    def get_arrow_ipc_file(self):
+        return getattr(self, "_arrow_path", "")
+
+    def get_parquet_file(self):
+        return getattr(self, "_arrow_path", "")
+
+    def arrow_is_enabled(self):
+        try:
+            import pyarrow  # noqa: F401
+            return True
+        except ImportError:
+            return False
+
     def _frame(self, numeric, row_vol, int_names, seg_names):
         header = ["intensity_image", "mask_image", "ROI_label", "t_index"] + self._engine.columns
         string_data = np.array([[int_names[k], seg_names[k]] for k in row_vol], dtype=object).reshape(-1, 2)
@@ -330,7 +406,7 @@ class Nyxus3D:
         if output_type not in self._valid_output_types:
             raise ValueError(f'Invalid output type {output_type}. Valid output types are {self._valid_output_types}')
         if output_type != 'pandas':
-            raise ValueError("arrowipc / parquet writers are outside the texture/intensity path implemented by nyxus_b200")
+            _need_pyarrow()
         if not single_roi and len(intensity_files) != len(mask_files):
             raise ValueError("Number of intensity files must match the number of mask files")
         frames = []
@@ -352,7 +428,7 @@ class Nyxus3D:
             frames.append(self._frame(numeric, row_vol, [os.path.basename(ifile)], [mname]))
         if not frames:
             return self._frame(np.zeros((0, 2 + len(self._engine.columns))), [], [], [])
-        return pd.concat(frames, axis=0, ignore_index=True)
+        return _emit(self, pd.concat(frames, axis=0, ignore_index=True), output_type, output_path)
 
     def featurize_directory(self, intensity_dir: str, label_dir: str, file_pattern: str, output_type: Optional[str] = "pandas",
                             output_path: Optional[str] = ""):

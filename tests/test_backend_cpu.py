@@ -65,9 +65,8 @@ def test_environment_protocol_without_a_device():
     ok, msg = be.set_metaparam_imp(iid, "3ngtdm/radius=0")
     assert ok is False and "positive integer" in msg
     assert be.set_metaparam_imp(iid, "3glcm/sparseintensities=true") == (True, "success")
-    assert be.arrow_is_enabled_imp(iid) is False
-    with pytest.raises(RuntimeError, match="Arrow"):
-        be.get_arrow_file_imp(iid)
+    assert be.arrow_is_enabled_imp(iid) is True         # Arrow IPC / Parquet through the interpreter's pyarrow
+    assert be.get_arrow_file_imp(iid) == "" and be.get_parquet_file_imp(iid) == ""      # nothing written yet
     be.release_environment_imp(iid)
     # an invalid feature name is an invalid_argument -> ValueError (env_features.cpp:496,507)
     with pytest.raises(ValueError, match="not a valid 2D feature name"):

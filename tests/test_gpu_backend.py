@@ -207,3 +207,32 @@ def test_reference_own_pytest_suite_runs_unmodified_on_the_dropin_deployment():
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
     import re
     assert int(re.search(r"(\d+) passed", r.stdout).group(1)) >= 10, tail
+
+
+@pytest.mark.parametrize("otype,ext", [("arrowipc", ".arrow"), ("parquet", ".parquet")])
+def test_arrow_and_parquet_output_through_the_reference_python_layer(tmp_path, otype, ext):
+    """output_type='arrowipc' / 'parquet' (nyxus.py:486-518, arrow_helpers.cpp:9-62, output_writers.cpp:21-30): the file the
+    reference's Python layer returns holds the table of the pandas call, typed utf8 / utf8 / int32 / float64..."""
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    from nyxus_b200 import synth
+    nyxus = pyref.reference_on_b200()
+    inten, label = synth.blob_slide(128, 160, 32, 7, 12, seed=5, jitter=1)
+    nyx = nyxus.Nyxus(["*ALL_GLCM*", "*ALL_INTENSITY*"])
+    assert nyx.arrow_is_enabled()
+    df = nyx.featurize(inten.astype(np.uint16), label, ["i.tif"], ["m.tif"])
+    path = nyx.featurize(inten.astype(np.uint16), label, ["i.tif"], ["m.tif"], output_type=otype, output_path=str(tmp_path / "out") + "/")
+    assert path == str(tmp_path / "out" / ("NyxusFeatures" + ext)) and os.path.exists(path)
+    assert (nyx.get_arrow_ipc_file() if otype == "arrowipc" else nyx.get_parquet_file()) == path
+    t = pa.ipc.open_file(path).read_all() if otype == "arrowipc" else pq.read_table(path)
+    assert t.column_names == list(df.columns)
+    assert [str(f.type) for f in t.schema][:4] == ["string", "string", "int32", "double"]
+    got = t.to_pandas()
+    assert list(got.intensity_image) == list(df.intensity_image) and np.array_equal(got.ROI_label.to_numpy(), df.ROI_label.to_numpy())
+    assert np.array_equal(got.iloc[:, 3:].to_numpy(np.float64), df.iloc[:, 3:].to_numpy(np.float64))
+    # the host-side mirror writes the same file
+    from nyxus_b200 import Nyxus
+    mine = Nyxus(["*ALL_GLCM*", "*ALL_INTENSITY*"])
+    p2 = mine.featurize(inten.astype(np.uint16), label, ["i.tif"], ["m.tif"], output_type=otype, output_path=str(tmp_path / ("x" + ext)))
+    t2 = pa.ipc.open_file(p2).read_all() if otype == "arrowipc" else pq.read_table(p2)
+    assert t2.schema.equals(t.schema) and t2.equals(t)

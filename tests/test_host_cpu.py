@@ -169,3 +169,27 @@ def test_cabi_device_free_validation_and_device_count():
     import torch
     if not torch.cuda.is_available():
         assert L.nyxb200_device_count() == 0
+
+
+def test_arrow_file_name_rules_and_writer(tmp_path):
+    """the reference's get_arrow_filename cases 1-6 (arrow_helpers.cpp:11-31) and the typed table (output_writers.cpp:21-30)"""
+    import pandas as pd
+    import pyarrow as pa
+    from nyxus_b200 import nyxus as N
+    d = str(tmp_path)
+    assert N.arrow_filename("", False) == "NyxusFeatures.arrow"                                     # case 6
+    assert N.arrow_filename(d, True) == os.path.join(d, "NyxusFeatures.parquet")                    # case 1
+    assert N.arrow_filename(d + "/new/", False) == os.path.join(d, "new", "NyxusFeatures.arrow")    # case 1 (trailing separator)
+    assert N.arrow_filename(d + "/bar", False) == d + "/bar.arrow"                                  # case 2
+    assert N.arrow_filename(d + "/foo/bar", False) == d + "/foo/bar/NyxusFeatures.arrow"            # case 3
+    assert N.arrow_filename(d + "/bar.csv", True) == d + "/bar.parquet"                             # case 5
+
+    class Holder:
+        pass
+    df = pd.DataFrame({"intensity_image": ["a", "b"], "mask_image": ["m", "n"], "ROI_label": np.array([1, 2], np.uint32),
+                       "t_index": [0., 0.], "MEAN": [1.5, 2.5]})
+    h = Holder()
+    p = N._emit(h, df, "arrowipc", d + "/sub/f.arrow")
+    t = pa.ipc.open_file(p).read_all()
+    assert [str(f.type) for f in t.schema] == ["string", "string", "int32", "double", "double"] and h._arrow_path == p
+    assert t.to_pandas().MEAN.tolist() == [1.5, 2.5]
