@@ -42,5 +42,17 @@ for k, v in (("3glszm/greydepth", 32), ("3ngtdm/greydepth", 32), ("3ngtdm/radius
     e4.set_param(k, v)
 t8, _ = e4.featurize_volume(VB, LB)
 e4.close()
+# round 2, later: the 3D families that complete *3D_ALL_TEXTURE* (GLDM, GLRLM, GLDZM, NGLDM) on the shared-memory classes and on
+# the large-cube path, the IBSI intensity-histogram family and the unweighted geometric moments
+e5 = Engine(["*3D_ALL_TEXTURE*"], dim=3, coarse_gray_depth=24)
+for k, v in (("3glszm/greydepth", 24), ("3ngtdm/greydepth", 24), ("3ngtdm/radius", 1), ("3gldm/greydepth", 24), ("3glrlm/greydepth", -20)):
+    e5.set_param(k, v)
+t9, _ = e5.featurize_volume(V, LV)
+t10, _ = e5.featurize_volume(VB, LB)
+e5.close()
+e6 = Engine(["*ALL_IH*", "SPAT_MOMENT_11", "HU_M3", "IMOM_RM_12", "IMOM_HU5"], ibsi=True)
+t11, _ = e6.featurize((I >> 8).astype(np.uint16), L)
+e6.close()
+print("round-2b rows", t9.shape, t10.shape, t11.shape, "finite", all(np.isfinite(t).all() for t in (t9, t10, t11)))
 print("round-2 rows", t6.shape, t7.shape, t8.shape, "finite", all(np.isfinite(t).all() for t in (t6, t7, t8)))
 print("rows", t1.shape, t2.shape, t3.shape, t4.shape, t5.shape, "finite", all(np.isfinite(t).all() for t in (t1, t2, t3, t4, t5)))
