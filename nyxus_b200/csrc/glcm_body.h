@@ -137,9 +137,10 @@ enum GlcmM { M_S2R, M_S2C, M_JVAR, M_HX, M_IDM, M_ID, M_IDN, M_IDMN, M_IV, M_DEN
 NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned long long rv, unsigned long long dv, unsigned long long sv,
 	double N, double mr, double mc, double diffavg, double NgD, double* m, double* px, double* py, double lv, double kdl, bool clusters)
 {
+	const double invN = 1.0 / N;	// one reciprocal per marginal index instead of four divisions (features are held to 1e-9, not bit-exact)
 	if (k < Ng)
 	{
-		const double pc = (double)cv / N, pr = (double)rv / N;
+		const double pc = (double)cv * invN, pr = (double)rv * invN;
 		px[k] = pc;
 		py[k] = pr;
 		const double dr = lv - mr, dc = lv - mc, dj = (double)(k + 1) - mr;
@@ -150,7 +151,7 @@ NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned l
 			m[M_HX] += dmul (pc, fast_log10 (dadd (pc, GLCM_EPSILON)));	// :873-876
 		if (dv)
 		{
-			const double pm = (double)dv / N, kd = (double)k;
+			const double pm = (double)dv * invN, kd = (double)k;
 			const KWeights kw = k_weights ((uint32_t)k);	// (reciprocal products instead of the reference's divisions: <= 2 ulp)
 			m[M_IDM] += pm * kw.inv1pk2;			// pm / (1 + k^2)		:685-687, HOM2 :1069
 			m[M_ID] += pm * kw.inv1pk;			// pm / (1 + k)			:1096-1097, HOM1 :942
@@ -165,7 +166,7 @@ NYX_D void glcm_marginal_terms (int k, int Ng, unsigned long long cv, unsigned l
 	}
 	if (k < 2 * Ng && sv)
 	{
-		const double pp = (double)sv / N;
+		const double pp = (double)sv * invN;
 		m[M_SENT] += dmul (pp, fast_log10 (dadd (pp, GLCM_EPSILON)));	// :712-716
 		if (clusters)
 		{
@@ -382,6 +383,7 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		return;
 	}
 	const double N = (double)q[Q_N];
+	const double invN = 1.0 / N;			// every probability of this angle is count * invN (marginals, their lists, joint cells)
 	const double mr = (double)q[Q_R] / N;		// f_corr mr (:598-603), f_var mean (:657-665), JAVE (:1140-1146)
 	const double mc = (double)q[Q_C] / N;		// f_corr mc (:605-610), by_row_mean (:531-536)
 	const double diffavg = (double)q[Q_D] / N;	// f_difference_avg (:786-795), DIS (:1050-1052)
@@ -486,10 +488,10 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		}
 		g.sync();
 		for (int i = g.tid; i < ndx; i += g.nthr)	// (the tables are dead: their region becomes the value lists)
-			pxc[i] = (double)cxl[i] / N;
+			pxc[i] = (double)cxl[i] * invN;
 		g.sync();
 		for (int j = g.tid; j < ndy; j += g.nthr)
-			pyc[j] = (double)cyl[j] / N;
+			pyc[j] = (double)cyl[j] * invN;
 	}
 	else
 	{
@@ -512,12 +514,12 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 		g.sync();
 		for (int i = g.tid; i < ndx; i += g.nthr)
 		{
-			pxc[i] = (double)tmpx[i] / N;
+			pxc[i] = (double)tmpx[i] * invN;
 			mxl[i] = 1;
 		}
 		for (int j = g.tid; j < ndy; j += g.nthr)
 		{
-			pyc[j] = (double)tmpy[j] / N;
+			pyc[j] = (double)tmpy[j] * invN;
 			myl[j] = 1;
 		}
 	}
@@ -525,7 +527,6 @@ NYX_D void glcm_angle (const Cta& g, int a, const GlcmGeom<D3>& G, const RoiRec&
 	cta_sum<M_N> (g, m);
 
 	// ---- pass 2: owner-computes terms of the joint cells
-	const double invN = 1.0 / N;
 	unsigned long long s_asm = 0, jmax = 0;
 	constexpr int NJD = RAD ? 6 : 3;
 	double jd[NJD] = {};	// sum log(p_cell), sum log(px*py), sum (r-mr)(c-mc) [, RAD: cluster sums m^2, m^3, m^4 per pair]

@@ -174,22 +174,22 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 	if (g.tid == 0)
 	{
 		double f[R_NANGLED];
-		f[R_SRE] = s[A_SRE] / sum;
-		f[R_LRE] = (double)q[Q_LRE] / sum;
-		f[R_GLN] = (double)q2[0] / sum;
-		f[R_GLNN] = (double)q2[0] / (sum * sum);
-		f[R_RLN] = (double)q2[1] / sum;
-		f[R_RLNN] = (double)q2[1] / (sum * sum);
+		f[R_SRE] = s[A_SRE] * inv_sum;
+		f[R_LRE] = (double)q[Q_LRE] * inv_sum;
+		f[R_GLN] = (double)q2[0] * inv_sum;
+		f[R_GLNN] = (double)q2[0] * (inv_sum * inv_sum);
+		f[R_RLN] = (double)q2[1] * inv_sum;
+		f[R_RLNN] = (double)q2[1] * (inv_sum * inv_sum);
 		f[R_RP] = sum / Np;					// :573
-		f[R_GLV] = t[0] / sum;
-		f[R_RV] = t[1] / sum;
-		f[R_RE] = -(t[2] / sum) * (1.0 / LOG10_2);
-		f[R_LGLRE] = s[A_LGL] / sum;
-		f[R_HGLRE] = (double)q[Q_HGL] / sum;
-		f[R_SRLGLE] = s[A_SRL] / sum;
-		f[R_SRHGLE] = s[A_SRH] / sum;
-		f[R_LRLGLE] = s[A_LRL] / sum;
-		f[R_LRHGLE] = s[A_LRH] / sum;
+		f[R_GLV] = t[0] * inv_sum;
+		f[R_RV] = t[1] * inv_sum;
+		f[R_RE] = -(t[2] * inv_sum) * (1.0 / LOG10_2);
+		f[R_LGLRE] = s[A_LGL] * inv_sum;
+		f[R_HGLRE] = (double)q[Q_HGL] * inv_sum;
+		f[R_SRLGLE] = s[A_SRL] * inv_sum;
+		f[R_SRHGLE] = s[A_SRH] * inv_sum;
+		f[R_LRLGLE] = s[A_LRL] * inv_sum;
+		f[R_LRHGLE] = s[A_LRH] * inv_sum;
 		for (int k = 0; k < R_NANGLED; k++)
 			out[k * 4 + a] = f[k];
 	}

@@ -27,25 +27,25 @@ struct DenseDebug
 };
 
 
-// number of 8-neighbours q of cell (x,y) with (cell[q] & flag) and the same level
+// number of 8-neighbours q of cell (x,y) with (cell[q] & flag) and the same level (flag: ONE flag bit).  Branch-free: a
+// neighbour outside the tile is redirected to the centre cell and masked out, so all lanes of a warp run the same eight
+// load / compare / add groups whatever their position in the tile
 NYX_D int nbr_same_level (const uint32_t* cell, int w, int h, int x, int y, uint32_t lv, uint32_t flag)
 {
+	const int i = y * w + x;
+	const bool xl = x > 0, xr = x < w - 1, yu = y > 0, yd = y < h - 1;
+	const uint32_t msk = flag | CELL_LEVEL, want = flag | lv;
 	int n = 0;
-	for (int dy = -1; dy <= 1; dy++)
-	{
-		const int yy = y + dy;
-		if (yy < 0 || yy >= h)
-			continue;
-		for (int dx = -1; dx <= 1; dx++)
-		{
-			const int xx = x + dx;
-			if ((!dx && !dy) || xx < 0 || xx >= w)
-				continue;
-			const uint32_t q = cell[yy * w + xx];
-			if ((q & flag) && (q & CELL_LEVEL) == lv)
-				n++;
-		}
-	}
+#define NYX_NB(ok, off) { const bool k_ = (ok); const uint32_t q_ = cell[k_ ? i + (off) : i]; n += (k_ && (q_ & msk) == want) ? 1 : 0; }
+	NYX_NB (yu && xl, -w - 1)
+	NYX_NB (yu, -w)
+	NYX_NB (yu && xr, -w + 1)
+	NYX_NB (xl, -1)
+	NYX_NB (xr, 1)
+	NYX_NB (yd && xl, w - 1)
+	NYX_NB (yd, w)
+	NYX_NB (yd && xr, w + 1)
+#undef NYX_NB
 	return n;
 }
 
@@ -154,20 +154,20 @@ NYX_D void gldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 	c.sync();
 	if (c.tid == 0)
 	{
-		out[D_SDE] = s[A_SDE] / Nz;
-		out[D_LDE] = (double)q[Q_LDE] / Nz;
-		out[D_GLN] = (double)q2[0] / Nz;
-		out[D_DN] = (double)q2[1] / Nz;
-		out[D_DNN] = (double)q2[1] / (Nz * Nz);
-		out[D_GLV] = t[0] / Nz;
-		out[D_DV] = t[1] / Nz;
-		out[D_DE] = -(t[2] / Nz) * (1.0 / LOG10_2);
-		out[D_LGLE] = s[A_LGL] / Nz;
-		out[D_HGLE] = (double)q[Q_HGL] / Nz;
-		out[D_SDLGLE] = s[A_SDL] / Nz;
-		out[D_SDHGLE] = s[A_SDH] / Nz;
-		out[D_LDLGLE] = s[A_LDL] / Nz;
-		out[D_LDHGLE] = s[A_LDH] / Nz;
+		out[D_SDE] = s[A_SDE] * inv_nz;
+		out[D_LDE] = (double)q[Q_LDE] * inv_nz;
+		out[D_GLN] = (double)q2[0] * inv_nz;
+		out[D_DN] = (double)q2[1] * inv_nz;
+		out[D_DNN] = (double)q2[1] * (inv_nz * inv_nz);
+		out[D_GLV] = t[0] * inv_nz;
+		out[D_DV] = t[1] * inv_nz;
+		out[D_DE] = -(t[2] * inv_nz) * (1.0 / LOG10_2);
+		out[D_LGLE] = s[A_LGL] * inv_nz;
+		out[D_HGLE] = (double)q[Q_HGL] * inv_nz;
+		out[D_SDLGLE] = s[A_SDL] * inv_nz;
+		out[D_SDHGLE] = s[A_SDH] * inv_nz;
+		out[D_LDLGLE] = s[A_LDL] * inv_nz;
+		out[D_LDHGLE] = s[A_LDH] * inv_nz;
 	}
 }
 
@@ -239,12 +239,12 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 		q[Q_NS] += 1;
 		q[Q_G] += lv;
 		q[Q_DC] += (unsigned long long)(nm + 1);
-		const double d2 = dc * dc, g2 = g * g, rd = 1.0 / d2;	// reciprocals instead of the reference's chained divisions (<= 2 ulp)
+		const double d2 = dc * dc, g2 = g * g, rd = inv_sq_int ((uint32_t)(nm + 1));	// reciprocals (from the table) instead of the reference's chained divisions (<= 2 ulp)
 		s[A_LDE] += rd;
 		s[A_HDE] += d2;
 		if (g != 0.0)
 		{
-			const double rg = 1.0 / g2;
+			const double rg = inv_sq_int (lv);
 			s[A_LGLCE] += rg;
 			s[A_LDLGLE] += rd * rg;
 			s[A_HDLGLE] += d2 * rg;
@@ -298,25 +298,26 @@ NYX_D void ngldm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_
 	c.sync();
 	if (c.tid == 0)
 	{
-		out[N_LDE] = s[A_LDE] / Ns;
-		out[N_HDE] = s[A_HDE] / Ns;
-		out[N_LGLCE] = s[A_LGLCE] / Ns;
-		out[N_HGLCE] = s[A_HGLCE] / Ns;
-		out[N_LDLGLE] = s[A_LDLGLE] / Ns;
-		out[N_LDHGLE] = s[A_LDHGLE] / Ns;
-		out[N_HDLGLE] = s[A_HDLGLE] / Ns;
-		out[N_HDHGLE] = s[A_HDHGLE] / Ns;
-		out[N_GLNU] = (double)q2[0] / Ns;
-		out[N_GLNUN] = (double)q2[0] / (Ns * Ns);
-		out[N_DCNU] = (double)q2[1] / Ns;
-		out[N_DCNUN] = (double)q2[1] / (Ns * Ns);
+		const double inv_ns = 1.0 / Ns;		// one reciprocal instead of 16 divisions (features are held to 1e-9, not bit-exact)
+		out[N_LDE] = s[A_LDE] * inv_ns;
+		out[N_HDE] = s[A_HDE] * inv_ns;
+		out[N_LGLCE] = s[A_LGLCE] * inv_ns;
+		out[N_HGLCE] = s[A_HGLCE] * inv_ns;
+		out[N_LDLGLE] = s[A_LDLGLE] * inv_ns;
+		out[N_LDHGLE] = s[A_LDHGLE] * inv_ns;
+		out[N_HDLGLE] = s[A_HDLGLE] * inv_ns;
+		out[N_HDHGLE] = s[A_HDHGLE] * inv_ns;
+		out[N_GLNU] = (double)q2[0] * inv_ns;
+		out[N_GLNUN] = (double)q2[0] * (inv_ns * inv_ns);
+		out[N_DCNU] = (double)q2[1] * inv_ns;
+		out[N_DCNUN] = (double)q2[1] * (inv_ns * inv_ns);
 		out[N_DCP] = 1.0;						// :354
 		out[N_GLM] = glm;
-		out[N_GLV] = t[0] / Ns;
+		out[N_GLV] = t[0] * inv_ns;
 		out[N_DCM] = dcm;
-		out[N_DCV] = t[1] / Ns;
-		out[N_DCENT] = -((t[2] - Ns * log (Ns)) / Ns) * INV_LN2;
-		out[N_DCENE] = (double)q2[2] / (Ns * Ns);
+		out[N_DCV] = t[1] * inv_ns;
+		out[N_DCENT] = -((t[2] - Ns * log (Ns)) * inv_ns) * INV_LN2;
+		out[N_DCENE] = (double)q2[2] * (inv_ns * inv_ns);
 	}
 }
 
@@ -377,7 +378,7 @@ NYX_D void ngtdm_reduce (const Cta& c, const Params& prm, uint32_t* mem, int L1,
 				{
 					const uint32_t si = SI[(size_t)lv * ndmax + k];
 					if (si)
-						sv += (double)si / (double)(k + 1);
+						sv += ndmax <= 8 ? (double)si * k_weights ((uint32_t)k).inv1pk : (double)si / (double)(k + 1);	// 2D: 1 / (k + 1) from the table (<= 1 ulp)
 					SI[(size_t)lv * ndmax + k] = 0;
 				}
 				Nn[lv] = 0;
@@ -504,23 +505,19 @@ NYX_D void ngtdm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		const int y = (int)fw.div ((uint32_t)i), x = i - y * w;
 		int nd = 0;
 		uint32_t sum = 0;
-		for (int dy = -1; dy <= 1; dy++)
 		{
-			const int yy = y + dy;
-			if (yy < 0 || yy >= h)
-				continue;
-			for (int dx = -1; dx <= 1; dx++)
-			{
-				const int xx = x + dx;
-				if ((!dx && !dy) || xx < 0 || xx >= w)
-					continue;
-				const uint32_t qv = cell[yy * w + xx] & CELL_LEVEL;
-				if (qv)
-				{
-					sum += qv;
-					nd++;
-				}
-			}
+			// branch-free 8-neighbourhood (see nbr_same_level): a neighbour outside the tile reads the centre and counts as level 0
+			const bool xl = x > 0, xr = x < w - 1, yu = y > 0, yd = y < h - 1;
+#define NYX_NB(ok, off) { const bool k_ = (ok); const uint32_t q_ = k_ ? cell[i + (off)] & CELL_LEVEL : 0u; sum += q_; nd += q_ ? 1 : 0; }
+			NYX_NB (yu && xl, -w - 1)
+			NYX_NB (yu, -w)
+			NYX_NB (yu && xr, -w + 1)
+			NYX_NB (xl, -1)
+			NYX_NB (xr, 1)
+			NYX_NB (yd && xl, w - 1)
+			NYX_NB (yd, w)
+			NYX_NB (yd && xr, w + 1)
+#undef NYX_NB
 		}
 		if (nd > 0)	// ngtdm.cpp:83-146
 		{

@@ -153,6 +153,16 @@ NYX_D KWeights k_weights (uint32_t k)
 	return w;
 }
 
+// 1 / k^2 of a positive integer (table for small k: no division)
+NYX_D double inv_sq_int (uint32_t k)
+{
+#if NYX_DEVICE_BUILD
+	if (k - 1u < KW_TABLE_N - 1u)
+		return g_kw_table[k].invk2;
+#endif
+	return 1.0 / ((double)k * (double)k);
+}
+
 // The six "emphasis" sums every run / zone / dependence family takes over its elements (level i, minor j):
 //   s[0] += 1/j^2   s[1] += 1/i^2   s[2] += 1/(i^2 j^2)   s[3] += i^2/j^2   s[4] += j^2/i^2   s[5] += i^2 j^2
 // (GLRLM glrlm.cpp:381-383,712-719,781,813,844,876; GLSZM glszm.cpp:372-375,424-427,559-563; GLDZM gldzm.cpp:402,421,

@@ -331,6 +331,7 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 			const int i = base + c.tid;
 			const bool seed = i < ncell && (cell[i] & CELL_LEVEL) != skip && lab[i] == (uint32_t)i;
 			const unsigned b = __ballot_sync (0xffffffffu, seed);
+			__syncwarp();	// every lane has read its label: the list may overwrite the labels of this chunk (a vote orders no memory)
 			if (seed)
 				lab[run + __popc (b & ((1u << c.tid) - 1u))] = (uint16_t)i;
 			run += __popc (b);
@@ -410,22 +411,22 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 	c.sync();
 	if (c.tid == 0)
 	{
-		out[S_SAE] = s[A_SAE] / sum;
-		out[S_LAE] = (double)q[Q_LAE] / sum;
-		out[S_GLN] = (double)q2[0] / sum;
-		out[S_GLNN] = (double)q2[0] / (sum * sum);
-		out[S_SZN] = (double)q2[1] / sum;
-		out[S_SZNN] = (double)q2[1] / (sum * sum);
+		out[S_SAE] = s[A_SAE] * inv_sum;
+		out[S_LAE] = (double)q[Q_LAE] * inv_sum;
+		out[S_GLN] = (double)q2[0] * inv_sum;
+		out[S_GLNN] = (double)q2[0] * (inv_sum * inv_sum);
+		out[S_SZN] = (double)q2[1] * inv_sum;
+		out[S_SZNN] = (double)q2[1] * (inv_sum * inv_sum);
 		out[S_ZP] = sum / (np_fixed >= 0 ? np_fixed : (double)q[Q_NP]);	// :507-511
-		out[S_GLV] = t[0] / sum;
-		out[S_ZV] = t[1] / sum;
-		out[S_ZE] = -(t[2] / sum) * (1.0 / LOG10_2);
-		out[S_LGLZE] = s[A_LGL] / sum;
-		out[S_HGLZE] = (double)q[Q_HGL] / sum;
-		out[S_SALGLE] = s[A_SAL] / sum;
-		out[S_SAHGLE] = s[A_SAH] / sum;
-		out[S_LALGLE] = s[A_LAL] / sum;
-		out[S_LAHGLE] = s[A_LAH] / sum;
+		out[S_GLV] = t[0] * inv_sum;
+		out[S_ZV] = t[1] * inv_sum;
+		out[S_ZE] = -(t[2] * inv_sum) * (1.0 / LOG10_2);
+		out[S_LGLZE] = s[A_LGL] * inv_sum;
+		out[S_HGLZE] = (double)q[Q_HGL] * inv_sum;
+		out[S_SALGLE] = s[A_SAL] * inv_sum;
+		out[S_SAHGLE] = s[A_SAH] * inv_sum;
+		out[S_LALGLE] = s[A_LAL] * inv_sum;
+		out[S_LAHGLE] = s[A_LAH] * inv_sum;
 	}
 }
 
@@ -586,6 +587,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 			const int i = base + c.tid;
 			const bool root = i < ncell && !(ibsi && !(cell[i] & CELL_LEVEL)) && parent[i] == (uint32_t)i;
 			const unsigned b = __ballot_sync (0xffffffffu, root);
+			__syncwarp();	// every lane has read its parent: the list may overwrite the parents of this chunk (a vote orders no memory)
 			if (root)
 				parent[run + __popc (b & ((1u << c.tid) - 1u))] = (uint32_t)i;
 			run += __popc (b);
@@ -669,25 +671,26 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	c.sync();
 	if (c.tid == 0)
 	{
-		const double zdnu = (double)q2[1] / Ns, glnu = (double)q2[0] / Ns;
-		out[Z_SDE] = s[A_SDE] / Ns;
-		out[Z_LDE] = (double)q[Q_LDE] / Ns;
-		out[Z_LGLZE] = s[A_LGL] / Ns;
-		out[Z_HGLZE] = (double)q[Q_HGL] / Ns;
-		out[Z_SDLGLE] = s[A_SDL] / Ns;
-		out[Z_SDHGLE] = s[A_SDH] / Ns;
-		out[Z_LDLGLE] = s[A_LDL] / Ns;
-		out[Z_LDHGLE] = s[A_LDH] / Ns;
+		const double inv_ns = 1.0 / Ns;		// one reciprocal instead of 17 divisions (features are held to 1e-9, not bit-exact)
+		const double zdnu = (double)q2[1] * inv_ns, glnu = (double)q2[0] * inv_ns;
+		out[Z_SDE] = s[A_SDE] * inv_ns;
+		out[Z_LDE] = (double)q[Q_LDE] * inv_ns;
+		out[Z_LGLZE] = s[A_LGL] * inv_ns;
+		out[Z_HGLZE] = (double)q[Q_HGL] * inv_ns;
+		out[Z_SDLGLE] = s[A_SDL] * inv_ns;
+		out[Z_SDHGLE] = s[A_SDH] * inv_ns;
+		out[Z_LDLGLE] = s[A_LDL] * inv_ns;
+		out[Z_LDHGLE] = s[A_LDH] * inv_ns;
 		out[Z_GLNU] = glnu;
-		out[Z_GLNUN] = glnu / Ns;					// :428
+		out[Z_GLNUN] = glnu * inv_ns;					// :428
 		out[Z_ZDNU] = zdnu;
-		out[Z_ZDNUN] = zdnu / Ns;					// :411
+		out[Z_ZDNUN] = zdnu * inv_ns;					// :411
 		out[Z_ZP] = Ns / Nv;						// :455
 		out[Z_GLM] = glm;
-		out[Z_GLV] = t[0] / Ns;
+		out[Z_GLV] = t[0] * inv_ns;
 		out[Z_ZDM] = zdm;
-		out[Z_ZDV] = t[1] / Ns;
-		out[Z_ZDE] = -((t[2] - Ns * log (Ns)) * INV_LN2 / Ns);
+		out[Z_ZDV] = t[1] * inv_ns;
+		out[Z_ZDE] = -((t[2] - Ns * log (Ns)) * INV_LN2 * inv_ns);
 	}
 }
 
