@@ -334,9 +334,9 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 			__syncwarp();	// every lane has read its label: the list may overwrite the labels of this chunk (a vote orders no memory)
 			if (seed)
 				lab[run + __popc (b & ((1u << c.tid) - 1u))] = (uint16_t)i;
-			run += __popc (b);
-			__syncwarp();
+			run += __popc (b);	// (list positions never exceed the chunk's own cells: later chunks are still intact)
 		}
+		__syncwarp();
 		nseed = run;
 	}
 #endif
@@ -590,9 +590,9 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 			__syncwarp();	// every lane has read its parent: the list may overwrite the parents of this chunk (a vote orders no memory)
 			if (root)
 				parent[run + __popc (b & ((1u << c.tid) - 1u))] = (uint32_t)i;
-			run += __popc (b);
-			__syncwarp();
+			run += __popc (b);	// (list positions never exceed the chunk's own cells: later chunks are still intact)
 		}
+		__syncwarp();
 		nroot = run;
 	}
 #endif

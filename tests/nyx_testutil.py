@@ -235,3 +235,20 @@ def giant_cases():
     I[:, 210:] = 40000 + rng.integers(0, 40, (250, 210)) ** 2 // 40   # skewed, narrow range on a high mean
     out.append(("blank_and_lowcontrast", I, L, dict(g=64)))
     return out
+
+
+def big_volume_3d():
+    """the seeded volume of tests/golden/golden_vol_big.npz: 44 x 56 x 64 uint16 (intensities <= 1500), one ROI whose bounding
+    cube holds ~ 110 000 voxels (beyond the 40 000-voxel shared-memory classes), a medium one and two small ones"""
+    rng = np.random.default_rng(4242)
+    D, H, W = 44, 56, 64
+    zz, yy, xx = np.mgrid[0:D, 0:H, 0:W]
+    vol = ((np.sin(zz / 5.0) * np.cos(yy / 6.0) + np.sin(xx / 4.5) + 2.3) * 280.0 + rng.normal(0, 60, (D, H, W))).clip(1, 1500).astype(np.uint16)
+    vol[rng.random((D, H, W)) < 0.004] = 0
+    lab = np.zeros((D, H, W), np.uint16)
+    lab[(((zz - 21) / 20.5) ** 2 + ((yy - 27) / 25.5) ** 2 + ((xx - 30) / 27.5) ** 2) < 1] = 2     # cube ~ 41 x 51 x 55
+    lab[(((zz - 30) / 9.0) ** 2 + ((yy - 40) / 11.0) ** 2 + ((xx - 48) / 10.0) ** 2) < 1] = 5      # medium, carved out of the big one
+    lab[0:4, 0:9, 52:64] = 7
+    lab[40:44, 50:56, 0:5] = 11
+    lab[rng.random((D, H, W)) < 0.02] = 0
+    return vol, lab

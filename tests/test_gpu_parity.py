@@ -715,3 +715,29 @@ def test_3d_all_texture_group_and_edge_case_rois():
             assert not bad, (fam, bad[:8])
     finally:
         e.close()
+
+
+def test_3d_later_families_large_cube_path_against_reference_golden():
+    """the four later 3D families through k_roi_family3_big (a ROI whose cube exceeds the 40 000-voxel shared-memory classes)
+    and the shared-memory classes in one volume, against the reference's own pybind module (golden_vol_big.npz)"""
+    from nyxus_b200 import Engine
+    Zb = np.load(os.path.join(tu.GOLDEN, "golden_vol_big.npz"))
+    Zm = np.load(os.path.join(tu.GOLDEN, "golden_vol_more.npz"))
+    vol, lab = tu.big_volume_3d()
+    for ibsi, tag_dr, tag_cz in ((False, ("0", "32", "-20"), "64"), (True, (), "ibsi")):
+        e = Engine(["*3D_GLDM*", "*3D_GLRLM*", "*3D_GLDZM*", "*3D_NGLDM*"], dim=3, ibsi=ibsi)
+        try:
+            for t in (tag_dr or ("0",)):
+                e.set_param("3gldm/greydepth", int(t))
+                e.set_param("3glrlm/greydepth", int(t))
+                tab, _ = e.featurize_volume(vol, lab)
+                cols = e.columns
+                assert np.array_equal(tab[:, 0].astype(np.int64), Zb["GLDZM/labels"])
+                fams = [("GLDZM", tag_cz), ("NGLDM", tag_cz)] + ([("GLDM", t), ("GLRLM", t)] if tag_dr else [])
+                for fam, tag in fams:
+                    fc = [str(c) for c in Zm[fam + "/columns"]]
+                    sel = [cols.index(c) for c in fc]
+                    bad = tu.mismatches(tu.finite0(Zb["%s/table_%s" % (fam, tag)]), tu.finite0(tab[:, 2:][:, sel]), fc)
+                    assert not bad, (fam, tag, bad[:8])
+        finally:
+            e.close()

@@ -185,3 +185,29 @@ def test_3d_gldzm_ngldm_edge_cases_against_reference_golden(tag):
     depth, ibsi = (64, True) if tag == "ibsi" else (int(tag), False)
     _edge_rows(L, "GLDZM", tag, 64, depth, ibsi)
     _edge_rows(L, "NGLDM", tag, 128, depth, ibsi)
+
+
+ZB = np.load(os.path.join(tu.GOLDEN, "golden_vol_big.npz"))
+
+
+def test_3d_later_families_on_large_cubes_match_reference_golden():
+    """golden_vol_big.npz: an organ-sized ROI (cube ~ 110 000 voxels), a medium and two small ones; the bodies of the four later
+    3D families against the reference's own values (host emulation; the GPU test runs the same rows through the large-cube
+    kernel)"""
+    L = tu.build_emu()
+    vol, lab = tu.big_volume_3d()
+    try:
+        for fam, bit, tags in (("GLDM", 16, ("0", "32", "-20")), ("GLRLM", 32, ("0", "32", "-20")), ("GLDZM", 64, ("64", "ibsi")), ("NGLDM", 128, ("64", "ibsi"))):
+            cols = [str(c) for c in ZM[fam + "/columns"]]
+            for tag in tags:
+                if fam in ("GLDM", "GLRLM"):
+                    L.nyxemu_set_gldm3_greydepth(int(tag))
+                    L.nyxemu_set_glrlm3_greydepth(int(tag))
+                ibsi = tag == "ibsi"
+                for k, lb in enumerate(ZB[fam + "/labels"]):
+                    got = tu.emu_roi_features_3d(L, vol, lab, int(lb), 64, 0, 0, 0, ibsi, cols, fam_mask=bit)
+                    bad = tu.mismatches(tu.finite0(ZB["%s/table_%s" % (fam, tag)][k]), got, cols)
+                    assert not bad, (fam, tag, int(lb), bad[:4])
+    finally:
+        L.nyxemu_set_gldm3_greydepth(0)
+        L.nyxemu_set_glrlm3_greydepth(0)
