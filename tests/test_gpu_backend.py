@@ -188,7 +188,8 @@ def test_reference_own_pytest_suite_runs_unmodified_on_the_dropin_deployment():
     in place of the reference's binary (oracle/_ref/pyb200_site), and the reference's OWN, UNMODIFIED tests/python/test_nyxus.py
     run against it with pytest -- the tests whose features lie on the texture + intensity path:
       test_in_memory_2d / _3d             IBSI phantom, IBSI consensus GLCM values
-      test_3d_glcm / ngtdm / glszm_compatibility   NIfTI MRI + liver mask against PyRadiomics ground truth (PyRadiomics binning)
+      test_3d_glcm / ngtdm / glszm / gldm / glrlm_compatibility   NIfTI MRI + liver mask against PyRadiomics ground truth
+                                          (PyRadiomics binning through set_metaparam)
       TestSingleRoi (5 tests)             featurize_files / featurize_directory on the suite's OME-TIFFs, whole-slide mode
     (the rest of that file needs *ALL* = every family of the reference, Arrow writers or image quality)."""
     import shutil
@@ -199,14 +200,15 @@ def test_reference_own_pytest_suite_runs_unmodified_on_the_dropin_deployment():
     for f in ("backend" + sysconfig.get_config_var("EXT_SUFFIX"), "libnyxus_b200.so"):      # the binaries under test = the built ones
         shutil.copy2(os.path.join(tu.ROOT, "nyxus_b200", f), os.path.join(pkg, f))
     env = dict(os.environ, PYTHONPATH=DROPIN_SITE)
-    sel = "in_memory_2d or in_memory_3d or 3d_glcm_compatibility or 3d_ngtdm_compatibility or 3d_glszm_compatibility or TestSingleRoi"
+    sel = ("in_memory_2d or in_memory_3d or 3d_glcm_compatibility or 3d_ngtdm_compatibility or 3d_glszm_compatibility "
+           "or 3d_gldm_compatibility or 3d_glrlm_compatibility or TestSingleRoi")
     r = subprocess.run([sys.executable, "-m", "pytest", "test_nyxus.py", "-q", "-p", "no:cacheprovider", "-k", sel],
                        cwd=REF_PYTESTS, env=env, capture_output=True, text=True, timeout=900)
     tail = (r.stdout + r.stderr)[-3000:]
     assert r.returncode == 0, tail
     assert " passed" in r.stdout and "failed" not in r.stdout, tail
     import re
-    assert int(re.search(r"(\d+) passed", r.stdout).group(1)) >= 10, tail
+    assert int(re.search(r"(\d+) passed", r.stdout).group(1)) >= 12, tail
 
 
 @pytest.mark.parametrize("otype,ext", [("arrowipc", ".arrow"), ("parquet", ".parquet")])
