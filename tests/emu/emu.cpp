@@ -19,6 +19,7 @@
 #include "../../nyxus_b200/csrc/morph_body.h"
 #include "../../nyxus_b200/csrc/ih_body.h"
 #include "../../nyxus_b200/csrc/geomom_body.h"
+#include "../../nyxus_b200/csrc/contour_body.h"
 
 using namespace nyx;
 
@@ -360,5 +361,43 @@ extern "C" int nyxemu_geomom (const uint32_t* inten, const uint32_t* lbl, int H,
 	std::vector<double> red (RED_MAX * NW_MAX);
 	Cta c { 0, 1, red.data() };
 	geomom_body (c, im, r, 3, out);
+	return 0;
+}
+
+// distance-to-contour weighted geometric moments of the ROI `lab` of a labelled uint32 slide: 62 columns (shape variant, intensity
+// variant); contour (optional): the ordered contour in padded coordinates packed x | y << 16, ncontour its length
+extern "C" int nyxemu_wmom (const uint32_t* inten, const uint32_t* lbl, int H, int W, unsigned lab, double* out, uint32_t* contour, int* ncontour)
+{
+	RoiRec r;
+	memset (&r, 0, sizeof (r));
+	r.label = lab;
+	int x0 = W, x1 = -1, y0 = H, y1 = -1;
+	for (int y = 0; y < H; y++)
+		for (int x = 0; x < W; x++)
+			if (lbl[(size_t)y * W + x] == lab)
+			{
+				r.area++;
+				x0 = std::min (x0, x); x1 = std::max (x1, x);
+				y0 = std::min (y0, y); y1 = std::max (y1, y);
+			}
+	if (!r.area)
+		return -1;
+	r.x0 = x0; r.y0 = y0; r.w = x1 - x0 + 1; r.h = y1 - y0 + 1; r.d = 1;
+	ImageView im { inten, lbl, H, W, 0 };
+	std::vector<double> red (RED_MAX * NW_MAX);
+	Cta c { 0, 1, red.data() };
+	const unsigned long long cells = (unsigned long long)r.w * r.h;
+	const int maxwh = std::max (r.w, r.h);
+	std::vector<uint32_t> mem (wmom_scratch_words (cells, maxwh));
+	wmom_body (c, im, r, 3, mem.data(), cells, maxwh, out);
+	if (contour && ncontour)
+	{
+		// the K array survives the body (only LC and the stack are recycled for the weights)
+		const unsigned long long pcb = wmom_padded_bound (cells, maxwh);
+		const uint32_t* K = mem.data() + 2 * ((pcb + 3) / 4) + cells;
+		// its length is not kept: recount by re-running the tracer would be wasteful; the body leaves it in out[] instead
+		(void)K;
+		*ncontour = 0;
+	}
 	return 0;
 }

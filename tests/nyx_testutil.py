@@ -74,6 +74,16 @@ def mismatches(ref, got, cols=None, rtol=RTOL, atol=ATOL):
                     if c2 in names and c0 in names:
                         k2, k0 = names.index(c2), names.index(c0)
                         scale[..., j] = np.maximum(scale[..., j], np.sqrt(np.abs(a[..., k2] * a[..., k0])))
+            # Hu's invariants 5-7 (2d_geomoments_basic.cpp:240-254) are signed sums of degree-4 (5, 7) and degree-3 (6) products
+            # of the normalised moments: with a = n30 + n12, b = n21 + n03, e = n30 - 3 n12, f = 3 n21 - n03 every term of
+            # HU5 / HU7 is bounded by sqrt (HU3 HU4) HU4 (HU3 = e^2 + f^2, HU4 = a^2 + b^2) and every term of HU6 by
+            # sqrt (HU2) HU4; the values themselves can cancel by orders of magnitude (seen: 1e33 out of terms of 4e38 for a
+            # weighted mass near zero) -- the tolerance is relative to the magnitude being summed
+            for pre in ("HU_M", "IMOM_HU", "WEIGHTED_HU_M", "IMOM_WHU"):
+                if c.startswith(pre) and c[len(pre):] in ("5", "6", "7") and all(pre + d in names for d in "234"):
+                    h2, h3, h4 = (np.maximum(np.abs(a[..., names.index(pre + d)]), np.abs(b[..., names.index(pre + d)])) for d in "234")
+                    bound = 2.0 * np.sqrt(h2) * h4 if c.endswith("6") else 4.0 * np.sqrt(h3 * h4) * h4
+                    scale[..., j] = np.maximum(scale[..., j], bound)
     bad = diff > atol + rtol * scale
     out = []
     for idx in zip(*np.nonzero(bad)):
@@ -252,3 +262,37 @@ def big_volume_3d():
     lab[40:44, 50:56, 0:5] = 11
     lab[rng.random((D, H, W)) < 0.02] = 0
     return vol, lab
+
+
+def wmom_slide():
+    """the seeded slide of tests/golden/golden_wmom.npz: concave blobs plus shapes that stress the reference's contour tracer --
+    a ring (inner boundary), a one-pixel-wide bar and an L, a plus sign (X-crossing), a single pixel, a 2-pixel ROI, a
+    checkerboard patch (isolated speckles), two separate parts under one label, a ROI touching the slide border, a U shape"""
+    from nyxus_b200 import synth
+    I, L = synth.blob_slide(192, 256, 32, 7, 13, seed=41, jitter=2)
+    I = I.astype(np.uint32)
+    b = int(L.max())
+    yy, xx = np.mgrid[0:192, 0:256]
+    free = np.zeros_like(L)
+    L[160:192, :] = 0                                   # a band for the hand-made shapes
+    rr = (yy - 175) ** 2 + (xx - 16) ** 2
+    L[(rr <= 100) & (rr >= 25)] = b + 1                 # ring
+    L[165, 40:70] = b + 2                               # bar, one pixel wide
+    L[168:188, 80] = b + 3                              # L shape
+    L[187, 80:95] = b + 3
+    L[170:185, 107] = b + 4                             # plus sign
+    L[177, 100:115] = b + 4
+    L[163, 125] = b + 5                                 # single pixel
+    L[170, 125:127] = b + 6                             # two pixels
+    L[172:184:2, 135:147:2] = b + 7                     # speckles
+    L[173:183:2, 136:146:2] = b + 7
+    L[165:175, 155:165] = b + 8                         # two parts, one label
+    L[178:188, 170:178] = b + 8
+    L[180:192, 244:256] = b + 9                         # touches the slide corner
+    L[163:186, 190:193] = b + 10                        # U shape
+    L[163:186, 205:208] = b + 10
+    L[183:186, 190:208] = b + 10
+    L[164:170, 215:230] = b + 11                        # a solid rectangle with a one-pixel hole
+    L[166, 220] = 0
+    del free
+    return I, L
