@@ -67,7 +67,8 @@ int nyxb200_create (const nyxb200_settings* s, nyxb200_ctx** out);
 void nyxb200_destroy (nyxb200_ctx* ctx);
 const char* nyxb200_last_error (const nyxb200_ctx* ctx);   /* ctx may be NULL: error of the last failed create */
 
-/* Feature selection: group names ("*ALL_INTENSITY*", "*ALL_GLCM*", ... plus "*ALL_TEXTURE*") and individual
+/* Feature selection: group names ("*ALL_INTENSITY*", "*ALL_GLCM*", ..., "*BASIC_MORPHOLOGY*", "*ALL_IH*", "*GEOMOMS*", "*SGEOMOMS*",
+ * "*IGEOMOMS*", plus "*ALL_TEXTURE*"; dim == 3: "*3D_ALL_INTENSITY*", "*3D_ALL_TEXTURE*", "*3D_GLCM*" ...) and individual
  * feature names, exactly as Environment::expand_featuregroups does (env_features.cpp:456-528).  Unknown name -> EINVAL. */
 int nyxb200_select_features (nyxb200_ctx* ctx, const char* const* names, int n);
 int nyxb200_num_columns (const nyxb200_ctx* ctx);               /* feature columns (without ROI_label, t_index) */
@@ -75,7 +76,8 @@ const char* nyxb200_column_name (const nyxb200_ctx* ctx, int i); /* e.g. "GLCM_A
 int nyxb200_column_code (const nyxb200_ctx* ctx, int i);         /* Feature2D code of column i */
 /* replaces set_metaparam_imp("glcm/offset=..") etc. for the keys this path reads (env_metaparams.cpp:63-247):
  * "glcm/offset", "glcm/greydepth", "coarse_gray_depth", "ibsi", "glcm/symmetric", "soft_nan", and for dim == 3
- * "3glcm/greydepth", "3glszm/greydepth", "3ngtdm/greydepth", "3ngtdm/radius" */
+ * "3glcm/greydepth", "3glszm/greydepth", "3gldm/greydepth", "3glrlm/greydepth", "3ngtdm/greydepth", "3ngtdm/radius";
+ * per-call flags of the file-based workflows: "covered_range_from_scan", "single_roi" (the reference's whole-slide mode) */
 int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value);
 
 /* THE hot path.  Host buffers (pageable or pinned), `n_img` images of H x W, row-major, C-contiguous:

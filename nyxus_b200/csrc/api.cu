@@ -195,6 +195,7 @@ struct nyxb200_ctx
 	// (the driver's own pageable path stages through one thread); 0 = leave it to cudaMemcpyAsync
 	int staging_threads = 4;
 	int covered_from_scan = 0;	// 2D: COVERED_IMAGE_INTENSITY_RANGE against the scanned slide range (file-based workflows)
+	int single_roi = 0;		// the caller runs the reference's whole-slide (single ROI) mode on this call
 	int multi_row_pad = 65536;	// slack rows of the shared table's first estimate (test knob: 0 forces the second pass)
 	static constexpr int STG_MAX = 16;
 	static constexpr size_t STG_CHUNK = (size_t)8 << 20;
@@ -237,6 +238,8 @@ struct nyxb200_ctx
 	bool want_ih = false;		// IH_* columns selected (and IBSI mode on)
 	int row_stride = NCOL_TEXINT;	// doubles per ROI of the canonical table: the appended families only when one of them is selected
 	int geom_variants = 0;		// geometric moments selected: bit 0 shape (SPAT_ / CENTRAL_ / NORM_ / HU_M), bit 1 intensity (IMOM_)
+	int wmom_variants = 0;		// distance-to-contour weighted moments selected: bit 0 shape (WEIGHTED_ / WT_NORM_CTR_MOM_), bit 1 intensity (IMOM_W)
+	DevBuf<uint32_t> d_wmom;	// their per-warp / per-CTA scratch slots
 	std::vector<int> sel_cols;		// canonical column of every output column
 	std::vector<std::string> sel_names;
 	std::vector<int> sel_codes;
@@ -319,6 +322,7 @@ void rebuild_selection (nyxb200_ctx* ctx)
 	ctx->want_morph = false;
 	ctx->want_ih = false;
 	ctx->geom_variants = 0;
+	ctx->wmom_variants = 0;
 	static const int angles[4] = { 0, 45, 90, 135 };
 	// enabled features in ascending code order (reference featureset.cpp getEnabledFeatures; the table is already sorted)
 	for (int i = 0; i < (int)ctx->feats.size(); i++)
@@ -337,6 +341,8 @@ void rebuild_selection (nyxb200_ctx* ctx)
 			ctx->want_morph = true;
 		else if (f.family == FAM_GEOM)
 			ctx->geom_variants |= f.col0 < COL_GEOM + GM_NCOL ? 1 : 2;
+		else if (f.family == FAM_WMOM)
+			ctx->wmom_variants |= f.col0 < COL_WMOM + WMOM_NCOL ? 1 : 2;
 		else
 			ctx->fam_mask |= 1 << f.family;
 		for (int k = 0; k < f.ncols; k++)
@@ -392,14 +398,25 @@ int resolve_features (int dim, const std::vector<FeatureDef>& feats, const char*
 		if (found)
 			continue;
 		if (!d3)
-			for (const char* g : { "*GEOMOMS*", "*IGEOMOMS*", "*SGEOMOMS*" })
-				if (!strcmp (g, s))
+		{
+			// env_features.cpp:316-333: the shape moments (Smoms2D, 90 features), the intensity moments (Imoms2D, 90), or both --
+			// each the unweighted block and the distance-to-contour weighted block of its variant
+			const int gm = !strcmp (s, "*GEOMOMS*") ? 3 : !strcmp (s, "*SGEOMOMS*") ? 1 : !strcmp (s, "*IGEOMOMS*") ? 2 : 0;
+			if (gm)
+			{
+				for (int i = 0; i < nf; i++)
 				{
-					msg = std::string ("feature group '") + s + "' contains the distance-to-contour WEIGHTED moments, which are not built; "
-						"select the unweighted moments by name (SPAT_MOMENT_pq, CENTRAL_MOMENT_pq, NORM_SPAT_MOMENT_pq, NORM_CENTRAL_MOMENT_pq, HU_Mk, "
-						"IMOM_RM_pq, IMOM_CM_pq, IMOM_NRM_pq, IMOM_NCM_pq, IMOM_HUk)";
-					return NYXB200_EUNSUPPORTED;
+					int v = 0;
+					if (feats[i].family == FAM_GEOM)
+						v = feats[i].col0 < COL_GEOM + GM_NCOL ? 1 : 2;
+					else if (feats[i].family == FAM_WMOM)
+						v = feats[i].col0 < COL_WMOM + WMOM_NCOL ? 1 : 2;
+					if (v & gm)
+						on[i] = true;
 				}
+				continue;
+			}
+		}
 		if (d3)
 			for (const char* g : g_groups3d_unbuilt)
 				if (!strcmp (g, s))
@@ -542,6 +559,7 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	ctx->d_blkcnt.release(); ctx->d_blkarea.release(); ctx->d_rois.release(); ctx->d_classslot.release(); ctx->d_tlist.release();
 	ctx->d_alist.release(); ctx->d_bases.release(); ctx->d_cloud.release(); ctx->d_full.release(); ctx->d_sel_out.release();
 	for (auto& b : ctx->d_scratch) b.release();
+	ctx->d_wmom.release();
 	ctx->g_cell.release(); ctx->g_cell2.release(); ctx->g_auxA.release(); ctx->g_auxB.release(); ctx->g_auxC.release(); ctx->g_mat.release();
 	ctx->g_hcnts.release(); ctx->g_flags.release(); ctx->g_idx.release(); ctx->g_acc.release(); ctx->g_hkeys.release(); ctx->g_part.release();
 	ctx->g_recs.release();
@@ -674,6 +692,8 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 	}
 	else if (!strcmp (key, "tile_store"))			// test knob: 0 = family kernels bin straight from the slide
 		ctx->use_tile_store = iv != 0;
+	else if (!strcmp (key, "single_roi"))	// 1: whole-slide mode (SINGLEROI): features whose reference code branches on it can tell
+		ctx->single_roi = iv != 0;
 	else if (!strcmp (key, "covered_range_from_scan"))	// 1: the slide came from a file (featurize_directory / featurize_files)
 		ctx->covered_from_scan = iv != 0;
 	else if (!strcmp (key, "multi_row_pad"))
@@ -1492,7 +1512,7 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	// 2D: the canonical row ends after the last selected family (the texture + first-order block is always there; the
 	// appended morphology / IH / moment blocks cost their 1.4 KB per ROI of memset and row stride only when selected)
 	if (!d3)
-		ctx->row_stride = ctx->geom_variants ? NCOL_ALL : ctx->want_ih ? COL_IH + NCOL_IH : ctx->want_morph ? COL_MORPH + NCOL_MORPH : NCOL_TEXINT;
+		ctx->row_stride = ctx->wmom_variants ? NCOL_ALL : ctx->geom_variants ? COL_GEOM + NCOL_GEOMOM : ctx->want_ih ? COL_IH + NCOL_IH : ctx->want_morph ? COL_MORPH + NCOL_MORPH : NCOL_TEXINT;
 	const int ncol_all = d3 ? NCOL3_ALL : ctx->row_stride;
 	Params prm = make_params (ctx);
 	cudaStream_t s = ctx->stream;
@@ -1853,6 +1873,43 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 			{
 				const int grid = (int)std::min<uint32_t> (ccount[NCLASS], (uint32_t)ctx->sm_count * 4);
 				k_roi_geom<<<grid, ROI_THREADS, RED_WORDS * 4, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[NCLASS], ccount[NCLASS], ctx->geom_variants, ctx->d_full.p, ncol_all);
+				CU (cudaGetLastError());
+				ctx->counts[0]++;
+			}
+		}
+		if (ctx->wmom_variants && !d3)
+		{
+			// whole-slide mode weighs by the distance to the four slide edges instead of a traced contour (2d_geomoments_basic.cpp:
+			// 59-96, contour.cpp:914-931); that variant is reachable through TIFF input only and has no golden here: refused
+			if (ctx->single_roi)
+				return fail (ctx, NYXB200_EUNSUPPORTED, "the distance-to-contour weighted moments are not built for whole-slide (single ROI) mode");
+			// distance-to-contour weighted moments: warp per ROI, one launch per size class (the scratch slot of a warp is sized
+			// for the class); CTA per ROI for the oversize class
+			for (int c = 0; c <= NCLASS; c++)
+			{
+				const uint32_t n = ccount[c];
+				if (!n)
+					continue;
+				const unsigned long long mc = cmaxcells[c];
+				const int mwh = (int)cmaxwh[c];
+				if (mwh > 65532)
+					return fail (ctx, NYXB200_EUNSUPPORTED, "weighted geometric moments: a ROI edge of %d pixels exceeds 65532", mwh);
+				const size_t slotw = (wmom_scratch_words (mc, mwh) + 3) & ~(size_t)3;
+				const bool big = c == NCLASS;
+				size_t freeb = 0, totalb = 0;
+				CU (cudaMemGetInfo (&freeb, &totalb));
+				const size_t budget = freeb / 2 + ctx->d_wmom.cap * 4;
+				if (slotw * 4 > budget)
+					return fail (ctx, NYXB200_ENOMEM, "weighted geometric moments: a ROI of %llu cells needs %zu MB of work space", mc, slotw * 4 >> 20);
+				size_t slots = big ? std::min<size_t> (n, (size_t)ctx->sm_count) : std::min<size_t> (((size_t)n + ROI_WARPS - 1) / ROI_WARPS * ROI_WARPS, (size_t)ctx->sm_count * 16);
+				slots = std::max<size_t> (big ? 1 : ROI_WARPS, std::min<size_t> (slots, budget / (slotw * 4)));
+				if (!big)
+					slots = std::max<size_t> (ROI_WARPS, slots / ROI_WARPS * ROI_WARPS);
+				CU (ctx->d_wmom.reserve (slots * slotw));
+				if (big)
+					k_roi_wmom<<<(int)slots, ROI_THREADS, RED_WORDS * 4, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[c], n, ctx->wmom_variants, ctx->d_wmom.p, slotw, mc, mwh, ctx->d_full.p, ncol_all);
+				else
+					k_roi_wmom_w<<<(int)(slots / ROI_WARPS), ROI_THREADS, 0, ctx->ls>>> (im, ctx->d_rois.p, ctx->d_tlist.p + tb[c], n, ctx->wmom_variants, ctx->d_wmom.p, slotw, (uint32_t)mc, mwh, ctx->d_full.p, ncol_all);
 				CU (cudaGetLastError());
 				ctx->counts[0]++;
 			}
@@ -2539,6 +2596,7 @@ int nyxb200_get_param (const nyxb200_ctx* ctx, const char* key, double* value)
 	else if (!strcmp (key, "tile_store")) *value = ctx->use_tile_store;
 	else if (!strcmp (key, "staging_threads")) *value = ctx->staging_threads;
 	else if (!strcmp (key, "covered_range_from_scan")) *value = ctx->covered_from_scan;
+	else if (!strcmp (key, "single_roi")) *value = ctx->single_roi;
 	else if (!strcmp (key, "3glszm/greydepth")) *value = ctx->glszm3_greydepth;
 	else if (!strcmp (key, "3gldm/greydepth")) *value = ctx->gldm3_greydepth;
 	else if (!strcmp (key, "3glrlm/greydepth")) *value = ctx->glrlm3_greydepth;

@@ -555,9 +555,10 @@ py::tuple featurize_images (Env& e, const std::vector<std::string>& ifiles, cons
 	struct Restore
 	{
 		nyxb200_ctx* c;
-		~Restore() { nyxb200_set_param (c, "covered_range_from_scan", 0); }
+		~Restore() { nyxb200_set_param (c, "covered_range_from_scan", 0); nyxb200_set_param (c, "single_roi", 0); }
 	} restore { c };
 	nyxb200_set_param (c, "covered_range_from_scan", 1);
+	nyxb200_set_param (c, "single_roi", single_roi ? 1 : 0);
 	py::module_ np = py::module_::import ("numpy");
 	py::array header = header_array (c);
 	const std::vector<std::string> mnames = single_roi ? std::vector<std::string> (n, "") : mfiles;

@@ -12,6 +12,7 @@
 #include "morph_body.h"
 #include "ih_body.h"
 #include "geomom_body.h"
+#include "contour_body.h"
 
 namespace nyx
 {
@@ -1117,6 +1118,35 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_geom (ImageView im, const R
 	{
 		const uint32_t ri = list ? list[k] : k;
 		geomom_body (c, im, rois[ri], variants, out + (size_t)ri * out_stride + COL_GEOM);
+		c.sync();
+	}
+}
+
+// distance-to-contour weighted geometric moments (contour_body.h): warp per ROI (one launch per size class, every warp owns a
+// scratch slot of `slotw` words sized for the class) / CTA per ROI (oversize ROIs); reads the slide
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_wmom_w (ImageView im, const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+	uint32_t n, int variants, uint32_t* scratch, size_t slotw, uint32_t maxcells, int maxwh, double* out, int out_stride)
+{
+	const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+	Cta c { (int)(threadIdx.x & 31), 32, nullptr, 1 };
+	uint32_t* mem = scratch + (size_t)warp * slotw;
+	for (uint32_t k = warp; k < n; k += nwarps)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		wmom_body (c, im, rois[ri], variants, mem, maxcells, maxwh, out + (size_t)ri * out_stride + COL_WMOM);
+		c.sync();
+	}
+}
+__global__ void __launch_bounds__(ROI_THREADS) k_roi_wmom (ImageView im, const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+	uint32_t n, int variants, uint32_t* scratch, size_t slotw, unsigned long long maxcells, int maxwh, double* out, int out_stride)
+{
+	extern __shared__ __align__(16) uint32_t smem[];
+	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
+	uint32_t* mem = scratch + (size_t)blockIdx.x * slotw;
+	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
+	{
+		const uint32_t ri = list ? list[k] : k;
+		wmom_body (c, im, rois[ri], variants, mem, maxcells, maxwh, out + (size_t)ri * out_stride + COL_WMOM);
 		c.sync();
 	}
 }

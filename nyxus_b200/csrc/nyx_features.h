@@ -47,7 +47,12 @@ constexpr int FAM_GEOM = FAM_COUNT + 2;
 constexpr int GM_NCOL = 13 + 16 + 16 + 7 + 7;		// 59
 constexpr int NCOL_GEOMOM = 2 * GM_NCOL;
 constexpr int COL_GEOM = COL_IH + NCOL_IH;
-constexpr int NCOL_ALL = COL_GEOM + NCOL_GEOMOM;	// 516
+// the distance-to-contour weighted moments (contour_body.h): shape variant [WRM 10 | WCM 7 | WNCM 7 | WHU 7], then intensity
+constexpr int FAM_WMOM = FAM_COUNT + 3;
+constexpr int WMOM_NCOL = 10 + 7 + 7 + 7;		// 31
+constexpr int NCOL_WMOM = 2 * WMOM_NCOL;
+constexpr int COL_WMOM = COL_GEOM + NCOL_GEOMOM;
+constexpr int NCOL_ALL = COL_WMOM + NCOL_WMOM;	// 578
 
 // ---- first-order (Feature2D::COV .. UNIFORMITY_PIU, featureset.h:13-48)
 enum IntCol : int

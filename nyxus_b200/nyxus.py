@@ -243,6 +243,7 @@ class Nyxus:
         eng = self._engine
         frames = []
         eng.set_param("covered_range_from_scan", 1)      # file-based: the slide's range is the scanned one (slideprops.cpp:83-200)
+        eng.set_param("single_roi", 1 if single_roi else 0)
         try:
             for k, ifile in enumerate(intensity_files):
                 I = imageio.read_image(ifile, "intensity")
@@ -264,6 +265,7 @@ class Nyxus:
                 frames.append(df)
         finally:
             eng.set_param("covered_range_from_scan", 0)
+            eng.set_param("single_roi", 0)
         df = pd.concat(frames, axis=0, ignore_index=True)
         if "ROI_label" in df.columns:
             df.ROI_label = df.ROI_label.astype(np.uint32)

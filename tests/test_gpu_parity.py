@@ -625,7 +625,7 @@ def test_intensity_histogram_family_needs_ibsi_and_orders_by_code():
 # ------------------------------------------------------------------------------------------------ geometric moments
 def test_unweighted_geometric_moments_against_reference_golden():
     """golden_geomom.npz = the reference's own pybind module: the 118 unweighted shape / intensity moments (raw, central,
-    normalised raw, normalised central, Hu).  The contour-weighted moments are refused by name and by group."""
+    normalised raw, normalised central, Hu)"""
     Zg = np.load(os.path.join(tu.GOLDEN, "golden_geomom.npz"))
     cols = [str(c) for c in Zg["columns"]]
     e = _engine(cols)
@@ -638,11 +638,37 @@ def test_unweighted_geometric_moments_against_reference_golden():
         t2, _ = e.featurize(Zg["inten"].astype(np.uint16), Zg["label"])
         assert e.columns == ["IMOM_RM_11", "IMOM_HU1"]
         assert not tu.mismatches(Zg["table"][:, [cols.index(c) for c in e.columns]], t2[:, 2:], e.columns)
-        for bad_name in ("*IGEOMOMS*", "*SGEOMOMS*", "*GEOMOMS*"):
-            with pytest.raises(Exception, match="WEIGHTED"):
-                e.select([bad_name])
-        with pytest.raises(ValueError):
-            e.select(["IMOM_WRM_00"])
+    finally:
+        e.close()
+
+
+def test_weighted_geometric_moments_against_reference_golden():
+    """golden_wmom.npz = the reference's own pybind module on 51 ROIs (concave blobs, a ring, one-pixel-wide bars, a plus sign,
+    speckles, two-part ROIs, a ROI at the slide corner): the 62 distance-to-contour weighted moments -- contour tracer, the
+    reference's approximate ordered-contour distance, float weights -- and the three moment groups of the reference"""
+    Zw = np.load(os.path.join(tu.GOLDEN, "golden_wmom.npz"))
+    cols = [str(c) for c in Zw["columns"]]
+    wcols = [c for c in cols if c.startswith(("WEIGHTED_", "WT_NORM_CTR_MOM_", "IMOM_W"))]
+    assert len(wcols) == 62
+    I, L = tu.wmom_slide()
+    e = _engine(wcols)
+    try:
+        tab, _ = e.featurize(I, L)
+        assert e.columns == wcols and np.array_equal(tab[:, 0].astype(np.int64), Zw["labels"])
+        ref = tu.finite0(Zw["table"][:, [cols.index(c) for c in wcols]])
+        bad = tu.mismatches(ref, tab[:, 2:], wcols)
+        assert not bad, bad[:8]
+        t16, _ = e.featurize(I.astype(np.uint16), L)          # uint16 intensities: the same table
+        assert np.array_equal(t16, tab)
+        e.select(["*SGEOMOMS*"])                               # env_features.cpp:329-333: 59 unweighted + 31 weighted shape moments
+        assert len(e.columns) == 90 and "WEIGHTED_HU_M7" in e.columns and "SPAT_MOMENT_00" in e.columns and not any(c.startswith("IMOM") for c in e.columns)
+        ts, _ = e.featurize(I, L)
+        sw = [c for c in e.columns if c in wcols]
+        assert not tu.mismatches(ref[:, [wcols.index(c) for c in sw]], ts[:, 2:][:, [e.columns.index(c) for c in sw]], sw)
+        e.select(["*IGEOMOMS*"])
+        assert len(e.columns) == 90 and all(c.startswith("IMOM") for c in e.columns)
+        e.select(["*GEOMOMS*"])
+        assert len(e.columns) == 180
     finally:
         e.close()
 

@@ -73,13 +73,15 @@ def test_nyxus_argument_validation_matches_reference():
 
 def test_feature_table_layout():
     from nyxus_b200 import feature_table as ft
-    assert len(ft.CANONICAL_COLUMNS) == 337 + 15 + 46 + 118 and len(ft.FEATURES) == 199 + 15 + 46 + 118     # + *BASIC_MORPHOLOGY*, *ALL_IH*, unweighted geometric moments (appended)
+    # + *BASIC_MORPHOLOGY*, *ALL_IH*, the unweighted and the distance-to-contour weighted geometric moments (appended)
+    assert len(ft.CANONICAL_COLUMNS) == 337 + 15 + 46 + 118 + 62 and len(ft.FEATURES) == 199 + 15 + 46 + 118 + 62
     assert ft.CANONICAL_COLUMNS[0] == "COV" and ft.CANONICAL_COLUMNS[35] == "UNIFORMITY_PIU"
     assert ft.CANONICAL_COLUMNS[36:40] == ["GLCM_ASM_0", "GLCM_ASM_45", "GLCM_ASM_90", "GLCM_ASM_135"]
     assert ft.CANONICAL_COLUMNS[332:337] == ["NGTDM_COARSENESS", "NGTDM_CONTRAST", "NGTDM_BUSYNESS", "NGTDM_COMPLEXITY", "NGTDM_STRENGTH"]
     assert ft.CANONICAL_COLUMNS[337] == "AREA_PIXELS_COUNT" and ft.CANONICAL_COLUMNS[351] == "ASPECT_RATIO"
     assert ft.CANONICAL_COLUMNS[352] == "IH_MEAN_VAL" and ft.CANONICAL_COLUMNS[397] == "IH_BIN_SIZE"
-    assert ft.CANONICAL_COLUMNS[398] == "SPAT_MOMENT_00" and ft.CANONICAL_COLUMNS[-1] == "IMOM_HU7"
+    assert ft.CANONICAL_COLUMNS[398] == "SPAT_MOMENT_00" and ft.CANONICAL_COLUMNS[515] == "IMOM_HU7"
+    assert ft.CANONICAL_COLUMNS[516] == "WEIGHTED_SPAT_MOMENT_00" and ft.CANONICAL_COLUMNS[-1] == "IMOM_WHU7"
     codes = [f[1] for f in ft.FEATURES]
     assert codes == sorted(codes) and codes[0] == 0 and codes[36] == 36 and codes[51] == 144   # COV, AREA_PIXELS_COUNT, GLCM_ASM
 

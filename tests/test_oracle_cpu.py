@@ -88,7 +88,7 @@ def test_compiled_reference_reproduces_golden(case):
 def test_reference_column_layout_is_the_generated_table():
     from nyxus_b200 import feature_table as ft
     assert ft.CANONICAL_COLUMNS[:337] == ref.columns()        # (the appended *BASIC_MORPHOLOGY* columns: tests/test_morph_cpu.py)
-    assert len(ft.CANONICAL_COLUMNS) == 337 + 15 + 46 + 118
+    assert len(ft.CANONICAL_COLUMNS) == 337 + 15 + 46 + 118 + 62
 
 
 def test_golden_slide_matches_oracle():
