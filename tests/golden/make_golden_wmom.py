@@ -27,3 +27,12 @@ df = keep.featurize(I.copy(), L.copy())
 np.savez_compressed(os.path.join(HERE, "golden_wmom.npz"), labels=df.ROI_label.to_numpy(np.int64),
                     columns=np.array(list(df.columns[4:])), table=df.iloc[:, 4:].to_numpy(np.float64))
 print(df.shape, list(df.columns[4:8]))
+
+# ---- one ROI beyond the 40 000-cell shared-memory classes (the CTA-per-ROI launch) with holes and a ragged outline, and a
+# thin diagonal band: tests/golden/golden_wmom_big.npz (the slide is regenerated from the seed: tu.wmom_slide_big)
+Ib, Lb = tu.wmom_slide_big()
+keepb = nyxus.Nyxus(names + diag)
+dfb = keepb.featurize(Ib.copy(), Lb.copy())
+np.savez_compressed(os.path.join(HERE, "golden_wmom_big.npz"), labels=dfb.ROI_label.to_numpy(np.int64),
+                    columns=np.array(list(dfb.columns[4:])), table=dfb.iloc[:, 4:].to_numpy(np.float64))
+print(dfb.shape)

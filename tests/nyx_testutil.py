@@ -296,3 +296,24 @@ def wmom_slide():
     L[166, 220] = 0
     del free
     return I, L
+
+
+def wmom_slide_big():
+    """the seeded slide of tests/golden/golden_wmom_big.npz: 260 x 300, one ragged ROI with holes whose bounding box exceeds
+    40 000 cells, a thin diagonal band and a small blob"""
+    rng = np.random.default_rng(77)
+    H, W = 260, 300
+    yy, xx = np.mgrid[0:H, 0:W]
+    I = (1500 + 900 * np.sin(xx / 17.0) * np.cos(yy / 23.0) + rng.normal(0, 200, (H, W))).clip(1, 60000).astype(np.uint32)
+    ang = np.arctan2(yy - 125, xx - 140)
+    rad = np.hypot((yy - 125) / 115.0, (xx - 140) / 130.0)
+    L = np.zeros((H, W), np.uint32)
+    L[rad < 0.93 + 0.06 * np.sin(7 * ang)] = 3
+    L[(yy - 90) ** 2 + (xx - 100) ** 2 < 300] = 0          # holes
+    L[(yy - 160) ** 2 + (xx - 190) ** 2 < 120] = 0
+    L[120:124, 60:220] = 0                                   # a slit
+    L[rng.random((H, W)) < 0.002] = 0                        # pinholes
+    band = np.abs((yy - 240) - 0.06 * (xx - 10)) < 1.2
+    L[band & (xx > 10) & (xx < 280) & (L == 0)] = 9
+    L[(yy - 250) ** 2 + (xx - 285) ** 2 < 40] = 12
+    return I, L

@@ -660,6 +660,14 @@ def test_weighted_geometric_moments_against_reference_golden():
         assert not bad, bad[:8]
         t16, _ = e.featurize(I.astype(np.uint16), L)          # uint16 intensities: the same table
         assert np.array_equal(t16, tab)
+        # a ROI beyond the 40 000-cell classes (CTA per ROI) with holes, a slit and pinholes; a thin diagonal band
+        Zb = np.load(os.path.join(tu.GOLDEN, "golden_wmom_big.npz"))
+        Ib, Lb = tu.wmom_slide_big()
+        tb, _ = e.featurize(Ib, Lb)
+        assert np.array_equal(tb[:, 0].astype(np.int64), Zb["labels"])
+        bcols = [str(c) for c in Zb["columns"]]
+        badb = tu.mismatches(tu.finite0(Zb["table"][:, [bcols.index(c) for c in wcols]]), tb[:, 2:], wcols)
+        assert not badb, badb[:8]
         e.select(["*SGEOMOMS*"])                               # env_features.cpp:329-333: 59 unweighted + 31 weighted shape moments
         assert len(e.columns) == 90 and "WEIGHTED_HU_M7" in e.columns and "SPAT_MOMENT_00" in e.columns and not any(c.startswith("IMOM") for c in e.columns)
         ts, _ = e.featurize(I, L)

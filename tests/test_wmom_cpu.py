@@ -33,3 +33,21 @@ def test_wmom_body_matches_reference_golden():
         if bad:
             worst.append((int(lab), bad[:3]))
     assert not worst, worst[:6]
+
+
+def test_wmom_body_on_a_large_ragged_roi_matches_reference_golden():
+    """golden_wmom_big.npz: a ROI of ~ 60 000 bounding-box cells with holes, a slit and pinholes (many inner contours, failed
+    loops, long ordered contour for the hill descent), a thin diagonal band, a small blob"""
+    Zb = np.load(os.path.join(tu.GOLDEN, "golden_wmom_big.npz"))
+    cols = [str(c) for c in Zb["columns"]]
+    E = tu.build_emu()
+    E.nyxemu_wmom.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p]
+    I, L = tu.wmom_slide_big()
+    I, L = np.ascontiguousarray(I, np.uint32), np.ascontiguousarray(L, np.uint32)
+    H, W = I.shape
+    sel = [cols.index(c) for c in CANON]
+    for k, lab in enumerate(Zb["labels"]):
+        out = np.zeros(62)
+        assert E.nyxemu_wmom(I.ctypes.data, L.ctypes.data, H, W, int(lab), out.ctypes.data, None, None) == 0
+        bad = tu.mismatches(tu.finite0(Zb["table"][k][sel]), tu.finite0(out), CANON)
+        assert not bad, (int(lab), bad[:4])
