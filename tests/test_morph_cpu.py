@@ -32,5 +32,5 @@ def test_morphology_columns_sit_between_first_order_and_glcm():
     for name, code, fam, col0, ncols in ft.FEATURES:
         names += [name] if ncols == 1 else ["%s_%d" % (name, a) for a in (0, 45, 90, 135)]
     from nyxus_b200 import feature_table as ft2
-    other = {f[0] for f in ft2.FEATURES if f[2] in ("IH", "GEOM")}
+    other = {f[0] for f in ft2.FEATURES if f[2] in ("IH", "GEOM", "WMOM")}
     assert [n for n in names if n not in other] == [str(c) for c in Z["all_columns"]]
