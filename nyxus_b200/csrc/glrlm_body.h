@@ -51,7 +51,7 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 	const Counters<true> P { reg };		// [Lmax][Nr], 16-bit packed
 	uint32_t* Ri = reg + pw;		// [Lmax]  runs per level
 	uint32_t* Cj = Ri + Lmax;		// [Nr]    runs per length
-	uint16_t* rl = (uint16_t*)(Cj + Nr);	// [ncell] length of the run starting at the cell (0: not a start)
+	uint16_t* rl = (uint16_t*)(Cj + Nr);	// [ncell] length of the run recorded at ONE of its cells (device: the last, host: the first; 0: none)
 	const int dx = a == 2 ? 0 : (a == 3 ? -1 : 1), dy = a == 0 ? 0 : 1;	// E, SE, S, SW (glrlm.cpp:129-175)
 	FastDiv fw;
 	fw.init ((uint32_t)w);
@@ -65,6 +65,93 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 	double s[A_N];
 	for (int k = 0; k < A_N; k++)
 		s[k] = 0;
+#if NYX_DEVICE_BUILD
+	// Runs without walking them.  The cells are visited LINE BY LINE along the warp's direction -- rows (E), columns (S), or
+	// the tile's diagonals wrapped around its left / right edge (SE: column (c0 + row) mod w, SW: (c0 - row) mod w), so that
+	// every direction is one sequence of ncell cells in which a run is a maximal stretch of equal levels between BREAKS
+	// (first cell of a line, the cell after a wrap, a level change).  32 consecutive cells per step: a ballot of the breaks
+	// gives every break the position of the break before it, and the lane of a break closes the run that ended on the cell
+	// before it (level and tile index of that cell come over from the lane below, or from the previous step for lane 0).
+	// A virtual break at position ncell closes the last run.  rl[] is written at the run's LAST cell (same level as its head).
+	{
+		uint32_t* rlw = (uint32_t*)rl;
+		for (int k = g.tid; k < (ncell + 1) / 2; k += g.nthr)
+			rlw[k] = 0;
+		g.sync();
+		const int lane = g.tid, L = a == 0 ? w : h;
+		FastDiv fl;
+		fl.init ((uint32_t)L);
+		uint32_t carry_lv = 0;
+		int carry_idx = 0, carry_head = 0;
+		for (int base = 0; base <= ncell; base += 32)
+		{
+			const int sq = base + lane;
+			int idx = 0;
+			uint32_t lv0 = 0;
+			bool border = true;
+			if (sq < ncell)
+			{
+				const int line = (int)fl.div ((uint32_t)sq), pos = sq - line * L;
+				int row = pos, col = line;
+				if (a == 0)
+				{
+					row = line;
+					col = pos;
+				}
+				else if (a != 2)
+				{
+					const uint32_t t = (uint32_t)line + (uint32_t)pos * (a == 1 ? 1u : (uint32_t)(w - 1));
+					col = (int)(t - fw.div (t) * (uint32_t)w);
+				}
+				border = pos == 0 || (a == 1 && col == 0) || (a == 3 && col == w - 1);
+				idx = row * w + col;
+				const uint32_t cc = cell[idx];
+				if (cc & CELL_NZ)
+					q[Q_NP]++;
+				lv0 = cc & CELL_LEVEL;
+			}
+			uint32_t lv = __shfl_up_sync (0xffffffffu, lv0, 1);
+			int pidx = __shfl_up_sync (0xffffffffu, idx, 1);
+			if (lane == 0)
+			{
+				lv = carry_lv;
+				pidx = carry_idx;
+			}
+			const bool brk = sq <= ncell && (border || lv != lv0);
+			const unsigned bm = __ballot_sync (0xffffffffu, brk);
+			if (brk && lv)
+			{
+				const unsigned below = bm & ((1u << lane) - 1u);
+				const int len = sq - (below ? base + 31 - __clz (below) : carry_head);
+				rl[pidx] = (uint16_t)len;
+				P.inc (g, (int)((lv - 1) * (uint32_t)Nr + (uint32_t)(len - 1)));
+				atom_add (g, Ri + (lv - 1), 1u);
+				atom_add (g, Cj + (len - 1), 1u);
+				const uint32_t i2 = lv * lv, j2 = (uint32_t)(len * len), i2j2 = lv * lv * (uint32_t)len * (uint32_t)len;	// 32-bit wrap
+				q[Q_SUM] += 1;
+				q[Q_LRE] += (unsigned long long)len * (unsigned long long)len;	// :409-415
+				q[Q_MUI] += lv;							// :598-605
+				q[Q_MUJ] += (unsigned long long)len;				// :640-646
+				q[Q_HGL] += (unsigned long long)i2;				// :744-751
+				if (lv < 65536u && (unsigned long long)i2 * (unsigned long long)j2 < 0x100000000ull)
+					emphasis6_int (s, lv, (uint32_t)len);			// :381-383,712-719,781,813,844,876 (no 32-bit wrap: i2j2 == i2 * j2)
+				else
+				{
+					s[A_SRE] += 1.0 / (double)(len * len);
+					s[A_LGL] += 1.0 / (double)i2;
+					s[A_SRL] += 1.0 / (double)i2j2;
+					s[A_SRH] += (double)i2 / (double)(int)j2;
+					s[A_LRL] += (double)(int)j2 / (double)i2;
+					s[A_LRH] += (double)i2j2;
+				}
+			}
+			carry_lv = __shfl_sync (0xffffffffu, lv0, 31);
+			carry_idx = __shfl_sync (0xffffffffu, idx, 31);
+			if (bm)
+				carry_head = base + 31 - __clz (bm);
+		}
+	}
+#else
 	for (int i = g.tid; i < ncell; i += g.nthr)
 	{
 		const uint32_t cc = cell[i];
@@ -116,6 +203,7 @@ NYX_D void glrlm_angle (const Cta& g, int a, const RoiRec& r, const Params& prm,
 		}
 		rl[i] = (uint16_t)len;
 	}
+#endif
 	g.sync();
 	cta_sum_u64<Q_N> (g, q);
 	cta_sum<A_N> (g, s);
