@@ -808,13 +808,14 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 		ctx->counts[0]++;
 		return 0;
 	}
-	size_t smem_words = RED_WORDS + tilew + famw;
+	const size_t ringw = FAM == FAM_GLCM || FAM == FAM_GLRLM ? PF_RING_WORDS : 0;	// in-flight list entries / records of the pipelined loop
+	size_t smem_words = RED_WORDS + tilew + famw + ringw;
 	uint32_t* gs = nullptr;
 	int grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 16);
 	if (smem_words > SMEM_LIMIT_WORDS)
 	{
 		// matrices go to a per-CTA slot in global memory (L2 resident), the tile stays in shared memory
-		smem_words = RED_WORDS + tilew;
+		smem_words = RED_WORDS + tilew + ringw;
 		grid = (int)std::min<uint32_t> (n, (uint32_t)ctx->sm_count * 2);
 		CU (ctx->d_scratch[ctx->lsi].reserve ((size_t)grid * famw));
 		gs = ctx->d_scratch[ctx->lsi].p;

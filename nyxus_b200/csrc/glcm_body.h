@@ -701,21 +701,27 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 				act[nact++] = (uint16_t)i;
 #endif
 	}
+	// the 4 x 30 angled values are staged in the reduction scratch (the angle warps never use it) instead of being written
+	// to the table and read back for the averages (a global-memory round trip at the end of every ROI)
+	double* st = c.red ? c.red : out;
 	for (int a = c.sub_id(); a < NA; a += c.sub_count())
 	{
 		GlcmGeom<false> G;
 		G.init (r, a == 2 ? 0 : (a == 3 ? -o : o), a == 0 ? 0 : o, 0, false, prm.ibsi != 0);	// glcm.cpp:234-251
 		if (rad)
-			glcm_angle<P16, false, true> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg, Ilev, ngroi, act, nact);
+			glcm_angle<P16, false, true> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, st, 4, dbg, Ilev, ngroi, act, nact);
 		else
-			glcm_angle<P16, false> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, out, 4, dbg, nullptr, 0, act, nact);
+			glcm_angle<P16, false> (g, a, G, r, prm, cell, mem + (size_t)a * aw, Ng, st, 4, dbg, nullptr, 0, act, nact);
 	}
 	c.sync();
 
-	// ---- _AVE = ((v0+v1)+v2)+v3)/4 (glcm.cpp:1205-1214)
+	// ---- the angled block leaves as one coalesced store; _AVE = ((v0+v1)+v2)+v3)/4 (glcm.cpp:1205-1214) from the staged values
+	if (st != out)
+		for (int k = c.tid; k < G_NANGLED * 4; k += c.nthr)
+			out[k] = st[k];
 	for (int k = c.tid; k < G_NAVE; k += c.nthr)
 	{
-		const double* v = out + ave_order[k] * 4;
+		const double* v = st + ave_order[k] * 4;
 		out[G_NANGLED * 4 + k] = (((v[0] + v[1]) + v[2]) + v[3]) / 4.0;
 	}
 }

@@ -297,12 +297,16 @@ NYX_D void glrlm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	}
 	const size_t aw = glrlm_angle_words (Lmax, Nr, maxcells);
 	const Cta g = c.sub();
+	double* st = c.red ? c.red : out;	// angled values staged in the reduction scratch (unused by the angle warps), see glcm_body
 	for (int a = c.sub_id(); a < NA; a += c.sub_count())
-		glrlm_angle (g, a, r, prm, cell, mem + (size_t)a * aw, Lmax, Nr, out, dbg);
+		glrlm_angle (g, a, r, prm, cell, mem + (size_t)a * aw, Lmax, Nr, st, dbg);
 	c.sync();
+	if (st != out)
+		for (int k = c.tid; k < R_NANGLED * 4; k += c.nthr)
+			out[k] = st[k];
 	for (int k = c.tid; k < R_NANGLED; k += c.nthr)		// glrlm.cpp:336-351, 902-909
 	{
-		const double* v = out + k * 4;
+		const double* v = st + k * 4;
 		out[R_NANGLED * 4 + k] = (((v[0] + v[1]) + v[2]) + v[3]) / 4.0;
 	}
 }

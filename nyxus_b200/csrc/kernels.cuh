@@ -156,6 +156,16 @@ __device__ __forceinline__ void cp_async16 (void* smem, const void* gmem)
 	const unsigned sa = (unsigned)__cvta_generic_to_shared (smem);
 	asm volatile ("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(sa), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async8 (void* smem, const void* gmem)
+{
+	const uint32_t sa = (uint32_t)__cvta_generic_to_shared (smem);
+	asm volatile ("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4 (void* smem, const void* gmem)
+{
+	const uint32_t sa = (uint32_t)__cvta_generic_to_shared (smem);
+	asm volatile ("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(sa), "l"(gmem) : "memory");
+}
 
 // the (unit, row) sequence of one warp: units warp, warp + nwarps, ...; inside a unit the rows top-down
 struct ScanCursor
@@ -864,9 +874,11 @@ constexpr int ROI_WARPS = ROI_THREADS / 32;
 // tile load + one family body for one ROI, run by the context c (a CTA or a single warp)
 template <int FAM, bool P16>
 __device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, const RoiRec& r, const Params& prm, uint32_t* cell,
-	uint32_t* mem, int Lmax, uint32_t maxcells, int maxwh, double* o, const DebugOut& dbg)
+	uint32_t* mem, int Lmax, uint32_t maxcells, int maxwh, double* o, const DebugOut& dbg, bool preloaded = false)
 {
-	if (FAM == FAM_NGLDM ? im.tileB != nullptr : im.tileA != nullptr)
+	if (preloaded)
+		;	// the caller has already put the tile into cell[] (the pipelined CTA-per-ROI loop)
+	else if (FAM == FAM_NGLDM ? im.tileB != nullptr : im.tileA != nullptr)
 		load_tile_store (c, (FAM == FAM_NGLDM ? im.tileB : im.tileA) + r.tile_off, r.w * r.h, cell);
 	else if (FAM == FAM_NGLDM)
 		load_tile_ngldm (c, im, r, prm, cell);
@@ -933,6 +945,71 @@ __global__ void __launch_bounds__(ROI_THREADS, FAM == FAM_GLCM ? 4 : FAM == FAM_
 	if (!GSCR)
 		for (size_t i = threadIdx.x; i < gwords; i += blockDim.x)
 			mem[i] = 0;
+	// ---- GLCM / GLRLM on the binned-tile store, tiles of at most 1024 cells: a software pipeline over the CTA's ROIs.  The
+	// loop is a chain of three dependent global loads per ROI (list entry -> ROI record -> tile) in front of ~20 us of
+	// shared-memory work, and a CTA has nothing else to do while it waits (4 - 6 CTAs per SM): ~10 % of the GLCM kernel's
+	// stall samples sat on these loads.  Here every stage of the chain is a cp.async issued one ROI earlier than its consumer
+	// needs it: while ROI i is computed, the 16-bit codes of tile i+1 land in the upper part of the reduction scratch (which
+	// the angle warps of these two families never use), the record of ROI i+2 in a two-slot ring, the list entry of ROI i+3
+	// in a four-slot ring.  One wait + barrier per ROI; no registers are held across the body.
+	if ((FAM == FAM_GLCM || FAM == FAM_GLRLM) && im.tileA != nullptr && maxcells <= 1024)
+	{
+		static_assert (sizeof (RoiRec) == 56 && 4 + 2 * sizeof (RoiRec) / 4 <= PF_RING_WORDS, "ring sized for two 56-byte records");
+		uint16_t* stage = (uint16_t*)(smem + PF_STAGE_OFF);				// [<= 1024] codes of the next tile
+		uint32_t* ring = cell + tile_words (maxcells) + (GSCR ? 0 : gwords);		// PF_RING_WORDS after the family region
+		uint32_t* idxr = ring;								// [4] ROI index of iteration it .. it + 3
+		RoiRec* recr = (RoiRec*)(ring + 4);						// [2] record of iteration it, it + 1
+		const uint32_t k0 = blockIdx.x, g = gridDim.x, tid = threadIdx.x;
+		auto issue_tile = [&] (const RoiRec& rr) {
+			const uint32_t chunks = (uint32_t)((rr.w * rr.h + 7) >> 3);		// 8 codes = 16 bytes (slots are padded to 8 cells)
+			const uint16_t* src = im.tileA + rr.tile_off;
+			for (uint32_t q = tid; q < chunks; q += blockDim.x)
+				cp_async16 (stage + q * 8, src + q * 8);
+		};
+		// prologue (once per CTA, latencies exposed): list entries of the first three ROIs, records of the first two, tile of the first
+		if (tid < 3 && k0 + tid * g < n)
+			idxr[tid] = list ? list[k0 + tid * g] : k0 + tid * g;
+		__syncthreads();
+		if (tid < 2 && k0 + tid * g < n)
+			recr[tid] = rois[idxr[tid]];
+		__syncthreads();
+		if (k0 < n)
+			issue_tile (recr[0]);
+		asm volatile ("cp.async.commit_group;" ::: "memory");
+		uint32_t it = 0;
+		for (uint32_t k = k0; k < n; k += g, it++)
+		{
+			asm volatile ("cp.async.wait_all;" ::: "memory");
+			__syncthreads();	// tile it, record it + 1, list entry it + 2 have landed (and the previous body is done with cell[])
+			const RoiRec r = recr[it & 1];
+			const uint32_t ri = idxr[it & 3];
+			{
+				const uint32_t* s2 = (const uint32_t*)stage;
+				const int n2 = (r.w * r.h + 1) >> 1;
+				for (int q = tid; q < n2; q += blockDim.x)
+				{
+					const uint32_t u = s2[q];
+					cell[2 * q] = tile16_decode (u & 0xFFFFu);
+					cell[2 * q + 1] = tile16_decode (u >> 16);
+				}
+			}
+			__syncthreads();	// cell[] complete; stage, recr[it & 1] and idxr[it & 3] are free again
+			if (k + g < n)
+				issue_tile (recr[(it + 1) & 1]);
+			if (k + 2 * g < n && tid < sizeof (RoiRec) / 8)
+				cp_async8 ((char*)&recr[it & 1] + tid * 8, (const char*)&rois[idxr[(it + 2) & 3]] + tid * 8);
+			if (k + 3 * g < n && tid == 32)
+			{
+				if (list)
+					cp_async4 (&idxr[(it + 3) & 3], list + k + 3 * g);
+				else
+					idxr[(it + 3) & 3] = k + 3 * g;
+			}
+			asm volatile ("cp.async.commit_group;" ::: "memory");
+			run_family<FAM, P16> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, dbg, true);
+		}
+		return;
+	}
 	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
 	{
 		const uint32_t ri = list ? list[k] : k;

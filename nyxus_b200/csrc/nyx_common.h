@@ -429,6 +429,11 @@ struct FastDiv
 constexpr int RED_MAX = 48;
 constexpr int NW_MAX = 8;	// CTAs have at most 256 threads
 constexpr int RED_WORDS = RED_MAX * NW_MAX * 2;	// 32-bit words of reduction scratch
+// the pipelined GLCM / GLRLM loop (k_roi_family): words [0, PF_STAGE_OFF) of the scratch hold the staged angle values
+// (4 x 30 doubles), words [PF_STAGE_OFF, PF_STAGE_OFF + 512) the 16-bit codes of the next tile (<= 1024 cells);
+// PF_RING_WORDS after the family region: 4 list entries + 2 ROI records in flight
+constexpr int PF_STAGE_OFF = 240, PF_RING_WORDS = 32;
+static_assert (PF_STAGE_OFF + 512 <= RED_WORDS, "tile stage does not fit the reduction scratch");
 
 NYX_D void atom_add (const Cta&, uint32_t* p, uint32_t v)
 {
