@@ -238,6 +238,7 @@ struct nyxb200_ctx
 	bool want_ih = false;		// IH_* columns selected (and IBSI mode on)
 	int row_stride = NCOL_TEXINT;	// doubles per ROI of the canonical table: the appended families only when one of them is selected
 	int geom_variants = 0;		// geometric moments selected: bit 0 shape (SPAT_ / CENTRAL_ / NORM_ / HU_M), bit 1 intensity (IMOM_)
+	bool want_hist = false;	// the opt-in HISTOGRAM feature (one column per grey-depth bin) is selected
 	int wmom_variants = 0;		// distance-to-contour weighted moments selected: bit 0 shape (WEIGHTED_ / WT_NORM_CTR_MOM_), bit 1 intensity (IMOM_W)
 	DevBuf<uint32_t> d_wmom;	// their per-warp / per-CTA scratch slots
 	std::vector<int> sel_cols;		// canonical column of every output column
@@ -323,6 +324,7 @@ void rebuild_selection (nyxb200_ctx* ctx)
 	ctx->want_ih = false;
 	ctx->geom_variants = 0;
 	ctx->wmom_variants = 0;
+	ctx->want_hist = false;
 	static const int angles[4] = { 0, 45, 90, 135 };
 	// enabled features in ascending code order (reference featureset.cpp getEnabledFeatures; the table is already sorted)
 	for (int i = 0; i < (int)ctx->feats.size(); i++)
@@ -336,6 +338,19 @@ void rebuild_selection (nyxb200_ctx* ctx)
 			if (!ctx->st.ibsi)
 				continue;
 			ctx->want_ih = true;
+		}
+		else if (f.family == FAM_HIST)
+		{
+			// HISTOGRAM_BIN_0 .. _N-1, N = coarse grey depth (output_2_buffer.cpp:158-168; a negative depth gives no column)
+			const int nbins = ctx->st.dim == 3 ? 0 : ctx->st.coarse_gray_depth;
+			ctx->want_hist = nbins > 0;
+			for (int k = 0; k < nbins; k++)
+			{
+				ctx->sel_cols.push_back (COL_HIST + k);
+				ctx->sel_codes.push_back (f.code);
+				ctx->sel_names.push_back (std::string (f.name) + "_BIN_" + std::to_string (k));
+			}
+			continue;
 		}
 		else if (f.family == FAM_MORPH)
 			ctx->want_morph = true;
@@ -660,6 +675,7 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 			return fail (ctx, NYXB200_EINVAL, "grey depth must be in 1..65535 (or -65535..-1: PyRadiomics bin count)");
 		ctx->st.coarse_gray_depth = iv;
 		ctx->glcm_greydepth_set = false;
+		rebuild_selection (ctx);	// the HISTOGRAM block has one column per bin
 	}
 	else if (!strcmp (key, "glcm/greydepth") || !strcmp (key, "3glcm/greydepth"))
 	{
@@ -981,6 +997,7 @@ Params make_params (const nyxb200_ctx* ctx)
 	p.glszm3_greydepth = ctx->glszm3_greydepth;
 	p.ngtdm3_greydepth = ctx->ngtdm3_greydepth;
 	p.ngtdm3_radius = ctx->ngtdm3_radius;
+	p.hist_col = ctx->want_hist && ctx->st.dim != 3 ? COL_HIST : 0;
 	return p;
 }
 
@@ -1369,7 +1386,7 @@ int process_giant_rois (nyxb200_ctx* ctx, const ImageView& im, const SlideInfo& 
 				return rc;
 		ctx->giant_rois += (int64_t)recs.size();
 	}
-	if ((ctx->fam_mask & (1 << FAM_INT)) && ctx->giant_acount)
+	if (((ctx->fam_mask & (1 << FAM_INT)) || ctx->want_hist) && ctx->giant_acount)
 	{
 		if (int rc = fetch_class_rois (ctx, ctx->d_alist.p + ctx->giant_abase, ctx->giant_acount, recs, idx))
 			return rc;
@@ -1513,7 +1530,7 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	// 2D: the canonical row ends after the last selected family (the texture + first-order block is always there; the
 	// appended morphology / IH / moment blocks cost their 1.4 KB per ROI of memset and row stride only when selected)
 	if (!d3)
-		ctx->row_stride = ctx->wmom_variants ? NCOL_ALL : ctx->geom_variants ? COL_GEOM + NCOL_GEOMOM : ctx->want_ih ? COL_IH + NCOL_IH : ctx->want_morph ? COL_MORPH + NCOL_MORPH : NCOL_TEXINT;
+		ctx->row_stride = ctx->want_hist ? COL_HIST + ctx->st.coarse_gray_depth : ctx->wmom_variants ? NCOL_ALL : ctx->geom_variants ? COL_GEOM + NCOL_GEOMOM : ctx->want_ih ? COL_IH + NCOL_IH : ctx->want_morph ? COL_MORPH + NCOL_MORPH : NCOL_TEXINT;
 	const int ncol_all = d3 ? NCOL3_ALL : ctx->row_stride;
 	Params prm = make_params (ctx);
 	cudaStream_t s = ctx->stream;
@@ -1720,7 +1737,7 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	const int Lmax = ctx->st.ibsi ? (int)std::max<uint32_t> (info.max_inten, 1u) : std::abs (ctx->st.coarse_gray_depth);
 	DebugOut nodbg { nullptr, nullptr, nullptr };
 	ImageView imf = im;		// the view the family kernels get (with the tile store when it is used)
-	const bool want_cloud = (ctx->fam_mask & (1 << FAM_INT)) != 0 || (ctx->want_ih && !d3);
+	const bool want_cloud = (ctx->fam_mask & (1 << FAM_INT)) != 0 || ((ctx->want_ih || ctx->want_hist) && !d3);
 	const bool want_tex = !d3 && (ctx->fam_mask & ~(1 << FAM_INT)) != 0;
 	// 16-bit tile codes hold 14-bit levels: MATLAB binning up to 16383 levels, IBSI (identity) up to that intensity
 	const bool tiles = want_tex && ctx->use_tile_store && info.n_tile_cells > 0 && (uint32_t)Lmax <= TILE16_LEVEL

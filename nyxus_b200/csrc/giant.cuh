@@ -1733,8 +1733,14 @@ __global__ void __launch_bounds__(BG_T) k_big_int_reduce (const uint32_t* __rest
 		out[I_COV] = sd / mean;
 		out[I_STANDARD_ERROR] = sd / sqrt (nd);
 	}
+	double* hist_out = prm.hist_col ? out + (prm.hist_col - COL_INT) : nullptr;	// HISTOGRAM_BIN_* (see intensity_body.h)
 	if (blank)	// intensity.cpp:121-122
+	{
+		if (hist_out)
+			for (int k = c.tid; k < nb; k += c.nthr)
+				hist_out[k] = 0.0;
 		return;
+	}
 	if (c.tid == 0)
 	{
 		b100[99] += b100[100];
@@ -1743,6 +1749,9 @@ __global__ void __launch_bounds__(BG_T) k_big_int_reduce (const uint32_t* __rest
 		bc[nb] = 0;
 	}
 	__syncthreads();
+	if (hist_out)
+		for (int k = c.tid; k < nb; k += c.nthr)
+			hist_out[k] = (double)bc[k];
 	{
 		const double qq[6] = { 0.01, 0.1, 0.25, 0.75, 0.9, 0.99 };
 		if (c.tid < 6)

@@ -132,8 +132,16 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 		out[I_COV] = sd / mean;
 		out[I_STANDARD_ERROR] = sd / sqrt (nd);
 	}
+	// HISTOGRAM (intensity.cpp:129, histogram.h:190-198; blank ROIs: padded with zeros, output_2_buffer.cpp:283-293): `out` is the
+	// ROI's first-order block, the per-bin block starts hist_col - COL_INT columns further
+	double* hist = prm.hist_col ? out + (prm.hist_col - COL_INT) : nullptr;
 	if (blank)	// intensity.cpp:121-122
+	{
+		if (hist)
+			for (int k = c.tid; k < nb; k += c.nthr)
+				hist[k] = 0.0;
 		return;
+	}
 
 	// ---- fold the special last bins, percentiles (one thread per percentile)
 	if (c.tid == 0)
@@ -232,6 +240,9 @@ NYX_D void intensity_body (const Cta& c, const RoiRec& r, const Params& prm, con
 	c.sync();
 	cta_sum<2> (c, eu);
 	const double p01 = sh[0], p10 = sh[1], p25 = sh[2], p75 = sh[3], p90 = sh[4], p99 = sh[5];
+	if (hist)	// the folded grey-depth histogram itself: raw counts of bins 0 .. nb-1
+		for (int k = c.tid; k < nb; k += c.nthr)
+			hist[k] = (double)bc[k];
 
 	// ---- sort -> median (histogram.h:268-287), mode (:289-309)
 	sort_keys (c, srt, npad);

@@ -353,6 +353,7 @@ struct Params
 	int32_t glszm3_greydepth = 0, ngtdm3_greydepth = 0, ngtdm3_radius = 0;
 	int32_t cube_maxdim = 0;	// 3D launches: the longest cube edge of the launch's ROI class (run-length / distance bounds)
 	double covered_den = 0;	// first-order COVERED_IMAGE_INTENSITY_RANGE denominator (slide max - min); 0 = in-memory sentinel
+	int32_t hist_col = 0;	// canonical column of HISTOGRAM_BIN_0 when the opt-in HISTOGRAM feature is selected (grey depth > 0), else 0
 };
 
 NYX_HD uint32_t load_inten (const ImageView& im, size_t idx)

@@ -53,6 +53,11 @@ constexpr int WMOM_NCOL = 10 + 7 + 7 + 7;		// 31
 constexpr int NCOL_WMOM = 2 * WMOM_NCOL;
 constexpr int COL_WMOM = COL_GEOM + NCOL_GEOMOM;
 constexpr int NCOL_ALL = COL_WMOM + NCOL_WMOM;	// 578
+// HISTOGRAM (featureset.h: opt-in, multi-valued): one column per bin of the first-order family's grey-depth histogram,
+// HISTOGRAM_BIN_0 .. _N-1 with N = coarse grey depth (output_2_buffer.cpp:158-168,283-293) -- the only block of the canonical
+// row whose width is a run-time value; it sits after every fixed block
+constexpr int FAM_HIST = FAM_COUNT + 4;
+constexpr int COL_HIST = NCOL_ALL;
 
 // ---- first-order (Feature2D::COV .. UNIFORMITY_PIU, featureset.h:13-48)
 enum IntCol : int

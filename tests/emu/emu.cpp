@@ -335,6 +335,31 @@ extern "C" int nyxemu_ih (const uint32_t* vals, unsigned n, int greydepth, int i
 	return 0;
 }
 
+// first-order block + the opt-in HISTOGRAM block of a plain list of intensities: out[0 .. 36) = *ALL_INTENSITY*,
+// out[36 .. 36 + greydepth) = HISTOGRAM_BIN_0 .. (intensity.cpp:129, histogram.h:190-198)
+extern "C" int nyxemu_histogram (const uint32_t* vals, unsigned n, int greydepth, double* out)
+{
+	if (!n || greydepth <= 0)
+		return -1;
+	RoiRec r;
+	memset (&r, 0, sizeof (r));
+	r.area = n;
+	r.imin = 0xFFFFFFFFu;
+	for (unsigned i = 0; i < n; i++)
+	{
+		r.imin = std::min (r.imin, vals[i]);
+		r.imax = std::max (r.imax, vals[i]);
+	}
+	Params prm = make_prm (greydepth, greydepth, 0, 1);
+	prm.hist_col = NCOL_INT;
+	std::vector<double> red (RED_MAX * NW_MAX);
+	Cta c { 0, 1, red.data() };
+	const uint32_t npad = std::max (next_pow2 (n), 64u);
+	std::vector<uint32_t> mem (intensity_smem_words (npad, greydepth));
+	intensity_body (c, r, prm, vals, n, npad, mem.data(), out);
+	return 0;
+}
+
 // unweighted geometric moments of the ROI `lab` of a labelled uint32 slide: 118 columns (shape variant, intensity variant)
 extern "C" int nyxemu_geomom (const uint32_t* inten, const uint32_t* lbl, int H, int W, unsigned lab, double* out)
 {

@@ -86,6 +86,9 @@ def test_reference_python_layer_same_table_over_both_backends(ibsi):
         n.set_metaparam("glcm/offset=2")
         n.set_metaparam("glcm/greydepth=3")
     _frames_match(r2.featurize(I[0].copy(), L[0].copy()), o2.featurize(I[0].copy(), L[0].copy()))
+    # the opt-in multi-valued HISTOGRAM feature: one column per bin of the grey depth, through both backends
+    _frames_match(ref_nyxus.Nyxus(["HISTOGRAM", "MEDIAN"], **kw).featurize(I[0].copy(), L[0].copy()),
+                  our_nyxus.Nyxus(["HISTOGRAM", "MEDIAN"], **kw).featurize(I[0].copy(), L[0].copy()))
     # negative intensities are shifted by the Python layer (nyxus.py:482-484) before they reach the backend
     J = I[0].astype(np.int32) - 500
     _frames_match(ref_nyxus.Nyxus(["*ALL_GLRLM*"], **kw).featurize(J.copy(), L[0].copy()),

@@ -622,6 +622,48 @@ def test_intensity_histogram_family_needs_ibsi_and_orders_by_code():
         e.close()
 
 
+# ------------------------------------------------------------------------------------------------ HISTOGRAM (opt-in, multi-valued)
+@pytest.mark.parametrize("g,ibsi", [(64, False), (20, False), (7, False), (20, True)])
+def test_histogram_feature_against_reference_golden(g, ibsi):
+    """golden_hist.npz = the reference's own pybind module: HISTOGRAM_BIN_0 .. _N-1 (raw counts of the first-order family's
+    grey-depth histogram, N = coarse grey depth) next to MEAN / ENTROPY; the slide holds a blank ROI (bins padded with zeros)"""
+    Zh = np.load(os.path.join(tu.GOLDEN, "golden_hist.npz"))
+    Zi = np.load(os.path.join(tu.GOLDEN, "golden_ih.npz"))
+    I = Zi["inten"].copy()
+    I[2:6, 2:8] = 0
+    tag = "%d%s" % (g, "_ibsi" if ibsi else "")
+    e = _engine(["HISTOGRAM", "MEAN", "ENTROPY"], ibsi=ibsi, coarse_gray_depth=g)
+    try:
+        tab, _ = e.featurize(I, Zi["label"])
+        assert e.columns == [str(c) for c in Zh["columns_" + tag]]
+        assert np.array_equal(tab[:, 0].astype(np.int64), Zh["labels"])
+        assert np.array_equal(tab[:, 4:], Zh["table_" + tag][:, 2:])                     # the bins: exact
+        bad = tu.mismatches(Zh["table_" + tag][:, :2], tab[:, 2:4], e.columns[:2])
+        assert not bad, bad[:8]
+        t16, _ = e.featurize(I.astype(np.uint16), Zi["label"])
+        assert np.array_equal(t16, tab)
+        e.set_param("coarse_gray_depth", 5)                                             # the block follows the grey depth
+        assert e.columns == ["ENTROPY", "MEAN"] + ["HISTOGRAM_BIN_%d" % k for k in range(5)]
+        t5, _ = e.featurize(I, Zi["label"])
+        assert t5.shape[1] == 2 + 7 and np.array_equal(t5[:, 4:].sum(axis=1)[1:], tab[:, 4:].sum(axis=1)[1:])
+    finally:
+        e.close()
+
+
+def test_histogram_feature_column_order_and_selection():
+    Zh = np.load(os.path.join(tu.GOLDEN, "golden_hist.npz"))
+    e = _engine(["IH_MEAN_VAL", "HISTOGRAM", "IMOM_WHU7", "GLCM_ASM", "MEAN"], ibsi=True, coarse_gray_depth=5)
+    try:
+        assert e.columns == [str(c) for c in Zh["mixed_columns"]]
+    finally:
+        e.close()
+    e = _engine(["*ALL_INTENSITY*"])                           # opt-in: not part of the first-order group (intensity.cpp:50-54)
+    try:
+        assert len(e.columns) == 36 and not any(c.startswith("HISTOGRAM") for c in e.columns)
+    finally:
+        e.close()
+
+
 # ------------------------------------------------------------------------------------------------ geometric moments (SURVEY 8f-1)
 def test_unweighted_geometric_moments_against_reference_golden():
     """golden_geomom.npz = the reference's own pybind module: the 118 unweighted shape / intensity moments (raw, central,
