@@ -73,8 +73,10 @@ def test_nyxus_argument_validation_matches_reference():
 
 def test_feature_table_layout():
     from nyxus_b200 import feature_table as ft
-    # + *BASIC_MORPHOLOGY*, *ALL_IH*, the unweighted and the distance-to-contour weighted geometric moments (appended)
-    assert len(ft.CANONICAL_COLUMNS) == 337 + 15 + 46 + 118 + 62 and len(ft.FEATURES) == 199 + 15 + 46 + 118 + 62
+    # + *BASIC_MORPHOLOGY*, *ALL_IH*, the unweighted and the distance-to-contour weighted geometric moments (appended);
+    # + the multi-valued HISTOGRAM feature (no fixed columns: one per grey-depth bin, after the fixed blocks)
+    assert len(ft.CANONICAL_COLUMNS) == 337 + 15 + 46 + 118 + 62 and len(ft.FEATURES) == 199 + 15 + 46 + 118 + 62 + 1
+    assert [f for f in ft.FEATURES if f[4] == 0] == [("HISTOGRAM", 492, "HIST", 578, 0)]
     assert ft.CANONICAL_COLUMNS[0] == "COV" and ft.CANONICAL_COLUMNS[35] == "UNIFORMITY_PIU"
     assert ft.CANONICAL_COLUMNS[36:40] == ["GLCM_ASM_0", "GLCM_ASM_45", "GLCM_ASM_90", "GLCM_ASM_135"]
     assert ft.CANONICAL_COLUMNS[332:337] == ["NGTDM_COARSENESS", "NGTDM_CONTRAST", "NGTDM_BUSYNESS", "NGTDM_COMPLEXITY", "NGTDM_STRENGTH"]
