@@ -871,10 +871,18 @@ struct DebugOut
 constexpr int ROI_THREADS = 128;
 constexpr int ROI_WARPS = ROI_THREADS / 32;
 
+// per-LAUNCH constant of a family that is a function of the class bounds only (GLSZM: hash slots -- a loop with 64-bit
+// divisions; GLDZM: distance bound): computed once per thread at kernel start, not once per ROI (it was 7 % of the
+// instructions of the GLSZM kernel)
+template <int FAM> __device__ __forceinline__ uint32_t family_aux (int Lmax, uint32_t maxcells, int maxwh)
+{
+	return FAM == FAM_GLSZM ? glszm_hash_slots (Lmax, maxcells) : FAM == FAM_GLDZM ? (uint32_t)gldzm_nd_bound (maxcells, maxwh) : 0u;
+}
+
 // tile load + one family body for one ROI, run by the context c (a CTA or a single warp)
 template <int FAM, bool P16>
 __device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, const RoiRec& r, const Params& prm, uint32_t* cell,
-	uint32_t* mem, int Lmax, uint32_t maxcells, int maxwh, double* o, const DebugOut& dbg, bool preloaded = false)
+	uint32_t* mem, int Lmax, uint32_t maxcells, int maxwh, double* o, const DebugOut& dbg, uint32_t aux, bool preloaded = false)
 {
 	if (preloaded)
 		;	// the caller has already put the tile into cell[] (the pipelined CTA-per-ROI loop)
@@ -902,12 +910,12 @@ __device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, c
 	else if (FAM == FAM_GLDZM)
 	{
 		ZoneDebug d { dbg.u32, dbg.nkeys };
-		gldzm_body (c, r, prm, cell, mem, Lmax, gldzm_nd_bound (maxcells, maxwh), maxcells, o + COL_GLDZM, dbg.u32 ? &d : nullptr);
+		gldzm_body (c, r, prm, cell, mem, Lmax, (int)aux, maxcells, o + COL_GLDZM, dbg.u32 ? &d : nullptr);
 	}
 	else if (FAM == FAM_GLSZM)
 	{
 		ZoneDebug d { dbg.u32, dbg.nkeys };
-		glszm_body (c, r, prm, cell, mem, maxcells, glszm_hash_slots (Lmax, maxcells), o + COL_GLSZM, dbg.u32 ? &d : nullptr);
+		glszm_body (c, r, prm, cell, mem, maxcells, aux, o + COL_GLSZM, dbg.u32 ? &d : nullptr);
 	}
 	else if (FAM == FAM_GLDM)
 	{
@@ -938,6 +946,7 @@ __global__ void __launch_bounds__(ROI_THREADS, FAM == FAM_GLCM ? 4 : FAM == FAM_
 {
 	extern __shared__ __align__(16) uint32_t smem[];
 	Cta c { (int)threadIdx.x, (int)blockDim.x, (double*)smem };
+	const uint32_t aux = family_aux<FAM> (Lmax, maxcells, maxwh);
 	uint32_t* cell = smem + RED_WORDS;
 	uint32_t* mem = GSCR ? gscratch + (size_t)blockIdx.x * gwords : cell + tile_words (maxcells);
 	// the family region is all zero on entry of every body and every body leaves it all zero again (owner-zeroing):
@@ -1006,7 +1015,7 @@ __global__ void __launch_bounds__(ROI_THREADS, FAM == FAM_GLCM ? 4 : FAM == FAM_
 					idxr[(it + 3) & 3] = k + 3 * g;
 			}
 			asm volatile ("cp.async.commit_group;" ::: "memory");
-			run_family<FAM, P16> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, dbg, true);
+			run_family<FAM, P16> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, dbg, aux, true);
 		}
 		return;
 	}
@@ -1014,14 +1023,14 @@ __global__ void __launch_bounds__(ROI_THREADS, FAM == FAM_GLCM ? 4 : FAM == FAM_
 	{
 		const uint32_t ri = list ? list[k] : k;
 		const RoiRec r = rois[ri];
-		run_family<FAM, P16> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, dbg);
+		run_family<FAM, P16> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, dbg, aux);
 	}
 }
 
 // WARP per ROI (single-matrix families on small tiles): every warp of the CTA owns a private shared-memory slice
 // (tile + family region) and walks its own ROIs -- no block-wide barrier anywhere, reductions are shuffle trees.
 template <int FAM>
-__global__ void __launch_bounds__(ROI_THREADS, (FAM == FAM_GLDM || FAM == FAM_NGLDM) ? 8 : FAM == FAM_NGTDM ? 7 : 1) k_roi_family_w (ImageView im, const RoiRec* __restrict__ rois,
+__global__ void __launch_bounds__(ROI_THREADS, (FAM == FAM_GLDM || FAM == FAM_NGLDM) ? 8 : FAM == FAM_NGTDM ? 7 : (FAM == FAM_GLDZM || FAM == FAM_GLSZM) ? 5 : 1) k_roi_family_w (ImageView im, const RoiRec* __restrict__ rois,
 	const uint32_t* __restrict__ list, uint32_t n, Params prm, int Lmax, uint32_t maxcells, int maxwh,
 	double* out, int out_stride, size_t famw)
 {
@@ -1031,6 +1040,7 @@ __global__ void __launch_bounds__(ROI_THREADS, (FAM == FAM_GLDM || FAM == FAM_NG
 	uint32_t* cell = smem + (size_t)warp * (tilew + famw);
 	uint32_t* mem = cell + tilew;
 	Cta c { lane, 32, nullptr, 1 };
+	const uint32_t aux = family_aux<FAM> (Lmax, maxcells, maxwh);
 	for (size_t i = lane; i < famw; i += 32)
 		mem[i] = 0;
 	__syncwarp();
@@ -1039,7 +1049,7 @@ __global__ void __launch_bounds__(ROI_THREADS, (FAM == FAM_GLDM || FAM == FAM_NG
 	{
 		const uint32_t ri = list ? list[k] : k;
 		const RoiRec r = rois[ri];
-		run_family<FAM, false> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, nodbg);
+		run_family<FAM, false> (c, im, r, prm, cell, mem, Lmax, maxcells, maxwh, out + (size_t)ri * out_stride, nodbg, aux);
 	}
 }
 
@@ -1093,6 +1103,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 	if (!GSCR)
 		for (size_t i = threadIdx.x; i < gwords; i += blockDim.x)
 			mem[i] = 0;
+	const uint32_t slots3 = FAM3 == FAM3_GLSZM ? glszm_hash_slots (Lmax, maxcells) : 0u;	// per launch, not per ROI
 	for (uint32_t k = blockIdx.x; k < n; k += gridDim.x)
 	{
 		const uint32_t ri = list ? list[k] : k;
@@ -1105,7 +1116,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, cons
 			B.init (greyinfo, r.imin, r.imax);
 		load_cube (c, im, r, B, cell);
 		c.sync();
-		family3_dispatch<FAM3, P16, false> (c, r, prm, cell, mem, greyinfo, Lmax, maxcells, FAM3 == FAM3_GLSZM ? glszm_hash_slots (Lmax, maxcells) : 0u, o);
+		family3_dispatch<FAM3, P16, false> (c, r, prm, cell, mem, greyinfo, Lmax, maxcells, slots3, o);
 		c.sync();
 	}
 }
