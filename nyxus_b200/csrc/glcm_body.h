@@ -121,6 +121,13 @@ NYX_D int glcm_rank_levels (const Cta& c, uint32_t* cell, int ncell, int n, uint
 	return cnt;
 }
 
+// angled feature behind every _AVE column, in output order
+#if NYX_DEVICE_BUILD
+__constant__ int g_glcm_ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
+#else
+static const int g_glcm_ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
+#endif
+
 struct GlcmDebug
 {
 	uint32_t* joint;	// [4][Ng*Ng] dense dump (row = centre level-1, col = neighbour level-1), may be null
@@ -650,7 +657,7 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 	double* out, const GlcmDebug* dbg, uint32_t listcells = 0)
 {
 	constexpr int NA = 4;
-	const int ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
+	const int* ave_order = g_glcm_ave_order;	// (a table in constant memory: a local array was re-initialised on the stack for every ROI)
 
 	// ---- blank ROI (glcm.cpp:22-28): the ONLY use of GLCM_GREYDEPTH ("glcm/greydepth"); the matrix bins with GREYDEPTH (:354)
 	{
@@ -677,6 +684,45 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 	{
 		act = (uint16_t*)(mem + NA * aw + (rad ? (size_t)2 * Ng + 2 : 0));
 #if NYX_DEVICE_BUILD
+		const int nchunk = (ncell + 31) >> 5;
+		if (nchunk <= 32)
+		{
+			// up to 1024 cells: ALL warps build the list (one warp alone kept the other three at the barrier).  Chunk ch = 32
+			// consecutive cells belongs to warp ch mod nw: count, barrier, every warp scans the <= 32 counts itself, then
+			// writes its chunks at their offsets -- raster order, deterministic
+			uint32_t* cnt = (uint32_t*)c.red;
+			const int nw = c.sub_count(), wi = c.sub_id(), lane = g.tid;
+			for (int ch = wi; ch < nchunk; ch += nw)
+			{
+				const int i = ch * 32 + lane;
+				const unsigned b = g.ballot (i < ncell && (cell[i] & CELL_NZ) != 0);
+				if (lane == 0)
+					cnt[ch] = (uint32_t)popc32 (b);
+			}
+			c.sync();
+			const uint32_t mine = lane < nchunk ? cnt[lane] : 0u;
+			uint32_t inc = mine;
+#pragma unroll
+			for (int o2 = 1; o2 < 32; o2 <<= 1)
+			{
+				const uint32_t t = __shfl_up_sync (0xffffffffu, inc, o2);
+				if (lane >= o2)
+					inc += t;
+			}
+			nact = (int)__shfl_sync (0xffffffffu, inc, 31);
+			for (int ch = wi; ch < nchunk; ch += nw)
+			{
+				const int i = ch * 32 + lane;
+				const bool nz = i < ncell && (cell[i] & CELL_NZ) != 0;
+				const unsigned b = g.ballot (nz);
+				const uint32_t off = __shfl_sync (0xffffffffu, inc - mine, ch);
+				if (nz)
+					act[off + popc32 (b & g.lanemask_lt())] = (uint16_t)i;
+			}
+			c.sync();
+		}
+		else
+		{
 		if (c.sub_id() == 0)
 		{
 			int run = 0;
@@ -695,6 +741,7 @@ NYX_D void glcm_body (const Cta& c, const RoiRec& r, const Params& prm, uint32_t
 		c.sync();
 		nact = (int)c.red[0];
 		c.sync();
+		}
 #else
 		for (int i = 0; i < ncell; i++)
 			if (cell[i] & CELL_NZ)
@@ -741,7 +788,7 @@ NYX_D void glcm3d_body (const Cta& c, const RoiRec& r, const Params& prm, uint32
 	double* out, int greyinfo)
 {
 	const bool rad = greyinfo < 0;
-	const int ave_order[G_NAVE] = NYX_GLCM_AVE_ORDER;
+	const int* ave_order = g_glcm_ave_order;	// (a table in constant memory: a local array was re-initialised on the stack for every ROI)
 	const int sx[G3_NDIR] = { 1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0 };
 	const int sy[G3_NDIR] = { 1, 1, 1, 0, 0, 0, -1, -1, -1, 1, 1, 1, 0 };
 	const int sz[G3_NDIR] = { 1, 0, -1, 1, 0, -1, 1, 0, -1, 1, 0, -1, 1 };
