@@ -1666,6 +1666,24 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	nb = std::max (1, std::min (nb, NB_MAX));
 	const uint32_t bs = (nroi + nb - 1) / nb;		// ROIs per batch (index ranges of the label-ordered ROI array)
 	nb = (int)((nroi + bs - 1) / bs);
+	// The copy of the LAST batch's rows is the one transfer nothing hides.  Automatic batching tapers the end of the slide:
+	// the last uniform batch [tail_start, nroi) is cut into 2q | q | rest, so the exposed copy carries a quarter of a batch
+	uint32_t tail_start = 0xFFFFFFFFu, tail_q = 1;
+	if (ctx->roi_batches <= 0 && nb >= 4 && nb + 2 <= NB_MAX && nroi - (uint32_t)(nb - 1) * bs >= 256)
+	{
+		tail_start = (uint32_t)(nb - 1) * bs;
+		tail_q = (nroi - tail_start + 3) / 4;
+		nb += 2;
+	}
+	// first ROI index of batch b (b == nb: the end)
+	auto batch_lo = [&] (int b) -> uint32_t {
+		if (tail_start == 0xFFFFFFFFu)
+			return std::min<uint32_t> (nroi, (uint32_t)b * bs);
+		const int nbm = nb - 3;		// uniform batches in front of the tapered tail
+		if (b <= nbm)
+			return (uint32_t)b * bs;
+		return b == nbm + 1 ? std::min (nroi, tail_start + 2 * tail_q) : b == nbm + 2 ? std::min (nroi, tail_start + 3 * tail_q) : nroi;
+	};
 
 	// ---- ROI records + class lists per (batch, class)
 	CU (ctx->d_rois.reserve (nroi));
@@ -1676,7 +1694,7 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 	{
 		const uint32_t nblk = (ctx->stats_cap + CB - 1) / CB;
 		k_compact_write<<<nblk, CB, 0, s>>> (ctx->d_stats.p, ctx->stats_cap, ctx->d_info.p, ctx->d_blkcnt.p, ctx->d_blkarea.p,
-			ctx->d_blkcells.p, ctx->d_rois.p, ctx->d_classslot.p, bs, d3 ? ctx->d_ztab.p : nullptr);
+			ctx->d_blkcells.p, ctx->d_rois.p, ctx->d_classslot.p, bs, d3 ? ctx->d_ztab.p : nullptr, tail_start, tail_q);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		CU (cudaMemcpyAsync (&info, ctx->d_info.p, sizeof (info), cudaMemcpyDeviceToHost, s));
@@ -2074,7 +2092,7 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 		}
 		// ---- rows of this batch: select + D2H, overlapped with the next batch (deferred when giant ROIs are pending)
 		if (!any_giant)
-			if (int rc = select_and_copy (bb * bs, std::min<uint32_t> (nroi, (bb + 1) * bs), nb > 1))
+			if (int rc = select_and_copy (batch_lo (bb), batch_lo (bb + 1), nb > 1))
 				return rc;
 	}
 	// ---- ROIs too large for the shared-memory classes: one at a time, whole-GPU kernels (giant.cuh)

@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(CB) k_compact_scan (uint32_t* blk_cnt, unsigne
 
 __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uint32_t cap, SlideInfo* info,
 	const uint32_t* blk_cnt, const unsigned long long* blk_area, const unsigned long long* blk_cells, RoiRec* rois,
-	uint32_t* class_slot, uint32_t batch_rois, const uint2* ztab = nullptr)
+	uint32_t* class_slot, uint32_t batch_rois, const uint2* ztab = nullptr, uint32_t tail_start = 0xFFFFFFFFu, uint32_t tail_q = 1)
 {
 	__shared__ uint32_t sa[33];
 	__shared__ unsigned long long sb[33], sc[33];
@@ -639,7 +639,14 @@ __global__ void __launch_bounds__(CB) k_compact_write (const LabelStat* tab, uin
 		rois[idx] = r;
 		const unsigned long long ncell64 = (unsigned long long)r.w * (unsigned long long)r.h * (unsigned long long)r.d;
 		const uint32_t ncell = ncell64 > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)ncell64;
-		const int batch = (int)(idx / batch_rois);
+		// uniform batches of batch_rois ROIs; from tail_start on, the last batch is cut into 2q | q | rest (the table copy of the
+		// very last batch is the only one no later batch hides: see process_slide_body)
+		int batch = (int)(idx / batch_rois);
+		if (idx >= tail_start)
+		{
+			const uint32_t off = idx - tail_start;
+			batch = (int)(tail_start / batch_rois) + (off < 2 * tail_q ? 0 : off < 3 * tail_q ? 1 : 2);
+		}
 		tc_ = batch * (NCLASS + 1) + tile_class (ncell);
 		ac = batch * (NACLASS + 1) + area_class (r.area);
 		tslot = atomicAdd (&s_cnt[tc_], 1u);
