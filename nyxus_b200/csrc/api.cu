@@ -241,6 +241,9 @@ struct nyxb200_ctx
 	bool want_hist = false;	// the opt-in HISTOGRAM feature (one column per grey-depth bin) is selected
 	int wmom_variants = 0;		// distance-to-contour weighted moments selected: bit 0 shape (WEIGHTED_ / WT_NORM_CTR_MOM_), bit 1 intensity (IMOM_W)
 	DevBuf<uint32_t> d_wmom;	// their per-warp / per-CTA scratch slots
+	// masks with large / sparse label values: presence bitmap, per-word ranks, block sums, rank -> label, the re-labelled mask
+	DevBuf<uint32_t> d_rl_bitmap, d_rl_wprefix, d_rl_blocks, d_rl_labmap, d_rl_mask;
+	bool relabelled = false;	// the current slide runs on d_rl_mask (labels 1 .. K); the label column is mapped back through d_rl_labmap
 	std::vector<int> sel_cols;		// canonical column of every output column
 	std::vector<std::string> sel_names;
 	std::vector<int> sel_codes;
@@ -575,6 +578,7 @@ void nyxb200_destroy (nyxb200_ctx* ctx)
 	ctx->d_alist.release(); ctx->d_bases.release(); ctx->d_cloud.release(); ctx->d_full.release(); ctx->d_sel_out.release();
 	for (auto& b : ctx->d_scratch) b.release();
 	ctx->d_wmom.release();
+	ctx->d_rl_bitmap.release(); ctx->d_rl_wprefix.release(); ctx->d_rl_blocks.release(); ctx->d_rl_labmap.release(); ctx->d_rl_mask.release();
 	ctx->g_cell.release(); ctx->g_cell2.release(); ctx->g_auxA.release(); ctx->g_auxB.release(); ctx->g_auxC.release(); ctx->g_mat.release();
 	ctx->g_hcnts.release(); ctx->g_flags.release(); ctx->g_idx.release(); ctx->g_acc.release(); ctx->g_hkeys.release(); ctx->g_part.release();
 	ctx->g_recs.release();
@@ -1523,8 +1527,10 @@ int process_slide (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t
 	return rc;
 }
 
-int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, int64_t* nrows_out)
+int process_slide_body (nyxb200_ctx* ctx, const ImageView& im_in, int img_index, int64_t* nrows_out)
 {
+	ImageView im = im_in;	// (the mask pointer is replaced when the labels have to be made dense)
+	ctx->relabelled = false;
 	const unsigned long long npix = (unsigned long long)im.D * (unsigned long long)im.H * (unsigned long long)im.W;
 	const bool d3 = ctx->st.dim == 3;
 	// 2D: the canonical row ends after the last selected family (the texture + first-order block is always there; the
@@ -1587,8 +1593,35 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 		{
 			if (attempt > 0)
 				return fail (ctx, NYXB200_ECUDA, "label table overflow persisted");
-			if (info.max_label >= (1u << 27))
-				return fail (ctx, NYXB200_EUNSUPPORTED, "label value %u exceeds the dense label table limit (2^27); relabel the mask", info.max_label);
+			if (info.max_label >= RELABEL_MIN)
+			{
+				// large / sparse label values: ranks 1 .. K instead (ascending label order, so the rows come out in the same order)
+				const size_t nwords = ((size_t)info.max_label >> 5) + 1, nblocks = (nwords + RL_BLOCK_WORDS - 1) / RL_BLOCK_WORDS;
+				CU (ctx->d_rl_bitmap.reserve (nwords));
+				CU (ctx->d_rl_wprefix.reserve (nwords));
+				CU (ctx->d_rl_blocks.reserve (nblocks + 1));
+				CU (ctx->d_rl_mask.reserve ((size_t)npix));
+				CU (cudaMemsetAsync (ctx->d_rl_bitmap.p, 0, nwords * 4, s));
+				const int g = ctx->sm_count * 16;
+				k_rl_mark<<<g, 256, 0, s>>> (im.label, (size_t)npix, ctx->d_rl_bitmap.p);
+				k_rl_block_popc<<<(unsigned)nblocks, 256, 0, s>>> (ctx->d_rl_bitmap.p, nwords, ctx->d_rl_blocks.p);
+				k_rl_scan_blocks<<<1, 1024, 0, s>>> (ctx->d_rl_blocks.p, (uint32_t)nblocks, ctx->d_rl_blocks.p + nblocks);
+				k_rl_word_prefix<<<(unsigned)nblocks, 32, 0, s>>> (ctx->d_rl_bitmap.p, nwords, ctx->d_rl_blocks.p, ctx->d_rl_wprefix.p);
+				uint32_t K = 0;
+				CU (cudaMemcpyAsync (&K, ctx->d_rl_blocks.p + nblocks, 4, cudaMemcpyDeviceToHost, s));
+				CU (cudaStreamSynchronize (s));
+				CU (ctx->d_rl_labmap.reserve (std::max<uint32_t> (K, 1)));
+				k_rl_list<<<g, 256, 0, s>>> (ctx->d_rl_bitmap.p, nwords, ctx->d_rl_wprefix.p, ctx->d_rl_labmap.p);
+				k_rl_apply<<<g, 256, 0, s>>> (im.label, (size_t)npix, ctx->d_rl_bitmap.p, ctx->d_rl_wprefix.p, ctx->d_rl_mask.p);
+				CU (cudaGetLastError());
+				ctx->counts[0] += 6;
+				if (K >= (1u << 27))
+					return fail (ctx, NYXB200_EUNSUPPORTED, "%u distinct labels exceed the label table limit (2^27)", K);
+				im.label = ctx->d_rl_mask.p;
+				ctx->relabelled = true;
+				ctx->stats_cap = std::max<uint32_t> (ctx->stats_cap, K + 1);
+				continue;
+			}
 			ctx->stats_cap = info.max_label + 1;
 			continue;
 		}
@@ -1797,7 +1830,7 @@ int process_slide_body (nyxb200_ctx* ctx, const ImageView& im, int img_index, in
 		stage_begin (ctx, ST_SELECT);
 		const int grid = (int)std::min<size_t> ((n + 255) / 256, (size_t)ctx->sm_count * 16);
 		k_select_columns<<<grid, 256, 0, s>>> (ctx->d_full.p + (size_t)r0 * ncol_all, ncol_all, ctx->d_rois.p + r0, r1 - r0, ctx->d_sel.p, nsel,
-			ctx->st.soft_nan, 0.0, ctx->d_sel_out.p + (size_t)r0 * rowlen);
+			ctx->st.soft_nan, 0.0, ctx->d_sel_out.p + (size_t)r0 * rowlen, ctx->relabelled ? ctx->d_rl_labmap.p : nullptr);
 		CU (cudaGetLastError());
 		ctx->counts[0]++;
 		stage_end (ctx, ST_SELECT);

@@ -1301,10 +1301,125 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_morph (ImageView im, const 
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Large / sparse label values (the reference keys its ROIs by a hash of the int label, pixel_feed.cpp:28 -- any value goes;
+// the label table here is dense): masks whose largest label is beyond RELABEL_MIN are re-labelled on the device to
+// 1 .. K in ascending label order before the scan, and the table's label column is mapped back at the end.
+// A presence bitmap over [0, max_label] (one atomicOr per label RUN of a row), popcounts per 1024-word block, one
+// single-CTA scan of the block sums, exclusive prefix per word: rank (label) = prefix[word] + popc (bits below) + 1.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t RELABEL_MIN = 1u << 24;	// below: the dense table simply grows (512 MB at the limit)
+constexpr int RL_BLOCK_WORDS = 1024;
+
+__global__ void k_rl_mark (const uint32_t* __restrict__ label, size_t npix, uint32_t* bitmap)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const uint32_t l = label[i];
+		if (l && (i == 0 || label[i - 1] != l))
+			atomicOr (bitmap + (l >> 5), 1u << (l & 31u));
+	}
+}
+// per block of RL_BLOCK_WORDS words: its popcount
+__global__ void __launch_bounds__(256) k_rl_block_popc (const uint32_t* __restrict__ bitmap, size_t nwords, uint32_t* blocksum)
+{
+	__shared__ uint32_t red[8];
+	const size_t w0 = (size_t)blockIdx.x * RL_BLOCK_WORDS;
+	uint32_t c = 0;
+	for (int k = threadIdx.x; k < RL_BLOCK_WORDS; k += 256)
+		if (w0 + k < nwords)
+			c += (uint32_t)__popc (bitmap[w0 + k]);
+	c = __reduce_add_sync (0xffffffffu, c);
+	if ((threadIdx.x & 31) == 0)
+		red[threadIdx.x >> 5] = c;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t t = 0;
+		for (int k = 0; k < 8; k++)
+			t += red[k];
+		blocksum[blockIdx.x] = t;
+	}
+}
+// exclusive scan of the block sums in place (one CTA; nblocks <= 2^17), total -> *total
+__global__ void __launch_bounds__(1024) k_rl_scan_blocks (uint32_t* blocksum, uint32_t nblocks, uint32_t* total)
+{
+	__shared__ uint32_t part[1024];
+	const uint32_t per = (nblocks + 1023) / 1024, b0 = threadIdx.x * per;
+	uint32_t c = 0;
+	for (uint32_t k = b0; k < b0 + per && k < nblocks; k++)
+		c += blocksum[k];
+	part[threadIdx.x] = c;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		uint32_t run = 0;
+		for (int k = 0; k < 1024; k++)
+		{
+			const uint32_t t = part[k];
+			part[k] = run;
+			run += t;
+		}
+		*total = run;
+	}
+	__syncthreads();
+	uint32_t run = part[threadIdx.x];
+	for (uint32_t k = b0; k < b0 + per && k < nblocks; k++)
+	{
+		const uint32_t t = blocksum[k];
+		blocksum[k] = run;
+		run += t;
+	}
+}
+// exclusive prefix of the popcounts per word (one thread walks 32 consecutive words: 32 threads per block of 1024 words)
+__global__ void k_rl_word_prefix (const uint32_t* __restrict__ bitmap, size_t nwords, const uint32_t* __restrict__ blockbase, uint32_t* wprefix)
+{
+	__shared__ uint32_t seg[32];
+	const size_t w0 = (size_t)blockIdx.x * RL_BLOCK_WORDS + (size_t)threadIdx.x * 32;
+	uint32_t c = 0;
+	for (int k = 0; k < 32; k++)
+		if (w0 + k < nwords)
+			c += (uint32_t)__popc (bitmap[w0 + k]);
+	seg[threadIdx.x] = c;
+	__syncwarp();
+	uint32_t run = blockbase[blockIdx.x];
+	for (int k = 0; k < (int)threadIdx.x; k++)
+		run += seg[k];
+	for (int k = 0; k < 32; k++)
+		if (w0 + k < nwords)
+		{
+			wprefix[w0 + k] = run;
+			run += (uint32_t)__popc (bitmap[w0 + k]);
+		}
+}
+// the K original labels in ascending order: labmap[rank - 1]
+__global__ void k_rl_list (const uint32_t* __restrict__ bitmap, size_t nwords, const uint32_t* __restrict__ wprefix, uint32_t* labmap)
+{
+	for (size_t w = (size_t)blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += (size_t)gridDim.x * blockDim.x)
+	{
+		uint32_t bits = bitmap[w], pos = wprefix[w];
+		while (bits)
+		{
+			const int b = __ffs (bits) - 1;
+			labmap[pos++] = (uint32_t)(w << 5) + (uint32_t)b;
+			bits &= bits - 1;
+		}
+	}
+}
+__global__ void k_rl_apply (const uint32_t* __restrict__ label, size_t npix, const uint32_t* __restrict__ bitmap,
+	const uint32_t* __restrict__ wprefix, uint32_t* dense)
+{
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x)
+	{
+		const uint32_t l = label[i];
+		dense[i] = l ? wprefix[l >> 5] + (uint32_t)__popc (bitmap[l >> 5] & ((1u << (l & 31u)) - 1u)) + 1u : 0u;
+	}
+}
+
 // final gather: canonical table -> [label, t_index, selected columns], values through force_finite_number(v, noval)
 // (reference output_2_buffer.cpp:490,577)
 __global__ void k_select_columns (const double* __restrict__ full, int full_stride, const RoiRec* __restrict__ rois, uint32_t n,
-	const int* __restrict__ sel, int nsel, double noval, double t_index, double* __restrict__ dst)
+	const int* __restrict__ sel, int nsel, double noval, double t_index, double* __restrict__ dst, const uint32_t* __restrict__ labmap = nullptr)
 {
 	const size_t total = (size_t)n * (nsel + 2);
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -1313,7 +1428,7 @@ __global__ void k_select_columns (const double* __restrict__ full, int full_stri
 		const int cidx = (int)(i - (size_t)r * (nsel + 2));
 		double v;
 		if (cidx == 0)
-			v = (double)(int32_t)rois[r].label;	// the reference keeps labels as int (pixel_feed.cpp:28)
+			v = (double)(int32_t)(labmap ? labmap[rois[r].label - 1u] : rois[r].label);	// the reference keeps labels as int (pixel_feed.cpp:28); labmap: the mask was re-labelled (k_rl_*)
 		else if (cidx == 1)
 			v = t_index;
 		else

@@ -255,10 +255,40 @@ def test_label_table_growth_and_limit(eng64):
     L[8:12, 8:12] = 17
     tab, _ = eng64.featurize(I, L)
     assert list(tab[:, 0]) == [17, 3_000_000]
-    from nyxus_b200 import NyxusB200Error
-    L[2:6, 2:6] = (1 << 27) + 5
-    with pytest.raises(NyxusB200Error, match="label"):
-        eng64.featurize(I, L)
+    L[2:6, 2:6] = (1 << 27) + 5       # beyond the dense table: the mask is re-labelled on the device, the label comes back
+    tab, _ = eng64.featurize(I, L)
+    assert list(tab[:, 0]) == [17, (1 << 27) + 5]
+
+
+def test_large_and_sparse_label_values_are_relabelled_on_the_device():
+    """the reference keys ROIs by the int label itself (pixel_feed.cpp:28): any value is fine.  Labels beyond 2^24 go through
+    the device re-labelling (ranks in ascending label order): same rows, same order, the original labels in column 0 --
+    checked against the same slide with small labels and against the compiled reference"""
+    from nyxus_b200 import synth
+    inten, label = synth.blob_slide(160, 192, 32, 7, 12, seed=31, jitter=2)
+    small = np.unique(label[label != 0])
+    rng = np.random.default_rng(5)
+    big = np.sort(rng.choice(np.arange(1 << 24, (1 << 31) - 1, dtype=np.int64), size=len(small), replace=False)).astype(np.uint32)
+    big[0], big[-1] = 50_000_000, 2_147_000_001
+    big.sort()
+    lut = np.zeros(int(small.max()) + 1, np.uint32)
+    lut[small] = big                                        # ascending -> ascending: the row order does not change
+    Lbig = lut[label]
+    e = _engine()
+    try:
+        t_small, _ = e.featurize(inten, label)
+        t_big, _ = e.featurize(inten, Lbig)
+        assert np.array_equal(t_big[:, 0].astype(np.int64), big.astype(np.int64))
+        assert np.array_equal(t_big[:, 1:], t_small[:, 1:])
+        t_again, _ = e.featurize(inten, label)              # and a small-label slide afterwards is untouched
+        assert np.array_equal(t_again, t_small)
+    finally:
+        e.close()
+    if ref.available():
+        rl, rt, _ = ref.featurize_2d(inten.astype(np.uint32), Lbig)
+        assert np.array_equal(rl.astype(np.int64), big.astype(np.int64))
+        bad = tu.mismatches(rt, t_big[:, 2:], COLS)
+        assert not bad, bad[:6]
 
 
 @pytest.mark.parametrize("ibsi", [False, True])
