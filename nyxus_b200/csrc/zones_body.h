@@ -505,36 +505,77 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	FastDiv fw;
 	fw.init ((uint32_t)w);
 
-	// ---- 4-connected components of equal level: every cell starts hooked to the head of its horizontal same-level run,
-	// then one union per vertically adjacent pair of RUNS (a pair whose left neighbours already joined the same two
-	// runs is skipped), so the union-find only ever sees run heads
+	// ---- 4-connected components of equal level + zone metric (= minimum member distance).
 #if NYX_DEVICE_BUILD
 	if (c.wmode)
 	{
-		// warp per ROI: the cells are walked in raster order 32 at a time, so the head of a cell's run is the nearest lane
-		// at or below it whose left neighbour differs (ballot + clz), or the head carried over from the previous 32 cells
-		uint32_t carry = 0;	// run head of the last cell of the previous chunk
+		// Warp per ROI, ONE pass over the cells in raster order, 32 at a time:
+		//  * the head of a cell's horizontal same-level run is the nearest lane at or below it whose left neighbour differs
+		//    (ballot + clz), or the head carried over from the previous 32 cells: parent[i] = head;
+		//  * the cell's distance goes straight to its run head's metric (the head is in a register: no find);
+		//  * one union per vertically adjacent pair of RUNS (a pair whose left neighbours already joined the same two runs is
+		//    skipped) -- both cells have their parents by then (the upper one lies at least one row back).
+		// Afterwards only the run heads that are not roots (runs hooked under an earlier run: few) look for their root and
+		// hand their metric over.  A metric other than 0xFFFF marks a run head.
+		for (int i = c.tid; i < (ncell + 1) / 2; i += c.nthr)
+			zminw[i] = 0xFFFFFFFFu;
+		__syncwarp();
+		const int lane = c.tid;
+		uint32_t carry = 0, carry_lv = 0xFFFFFFFFu;	// run head / level of the last cell of the previous chunk
 		for (int base = 0; base < ncell; base += 32)
 		{
-			const int i = base + c.tid;
-			bool head = true;
+			const int i = base + lane;
+			const bool in = i < ncell;
 			uint32_t lv = 0;
-			if (i < ncell)
+			int x = 0, y = 0;
+			if (in)
 			{
 				lv = cell[i] & CELL_LEVEL;
-				const int x = i - (int)fw.div ((uint32_t)i) * w;
-				head = (ibsi && !lv) || x == 0 || (cell[i - 1] & CELL_LEVEL) != lv;
+				y = (int)fw.div ((uint32_t)i);
+				x = i - y * w;
 			}
-			const unsigned heads = __ballot_sync (0xffffffffu, head);
-			const unsigned below = heads & (0xFFFFFFFFu >> (31 - c.tid));
+			const bool skip = !in || (ibsi && !lv);
+			uint32_t left_lv = __shfl_up_sync (0xffffffffu, lv, 1);
+			if (lane == 0)
+				left_lv = carry_lv;
+			const bool left_same = !skip && x > 0 && left_lv == lv;
+			const unsigned heads = __ballot_sync (0xffffffffu, !left_same);
+			const unsigned below = heads & (0xFFFFFFFFu >> (31 - lane));
 			const uint32_t hd = below ? (uint32_t)(base + 31 - __clz (below)) : carry;
-			if (i < ncell)
+			bool link = false;
+			if (in)
+			{
 				parent[i] = hd;
+				if (!skip)
+				{
+					atom_min_u16 (c, zminw, hd, (uint32_t)gldzm_dist2border (cell, w, h, x, y, !ibsi));
+					if (y > 0 && (cell[i - w] & CELL_LEVEL) == lv)
+						link = !(left_same && (cell[i - w - 1] & CELL_LEVEL) == lv);
+				}
+			}
+			__syncwarp();	// the parents of this chunk are in place
+			if (link)
+				uf_unite (c, parent, (uint32_t)i, (uint32_t)(i - w));
 			carry = __shfl_sync (0xffffffffu, hd, 31);
+			carry_lv = __shfl_sync (0xffffffffu, in ? lv : 0xFFFFFFFFu, 31);
 		}
+		for (int base = 0; base < ncell; base += 32)
+		{
+			__syncwarp();	// (a metric is read plainly here and updated by CAS on its 32-bit word below: keep the two apart)
+			const int i = base + lane;
+			const uint32_t m = i < ncell ? zmin[i] : 0xFFFFu;
+			const bool moves = m != 0xFFFFu && parent[i] != (uint32_t)i;
+			__syncwarp();
+			if (moves)
+				atom_min_u16 (c, zminw, uf_find (parent, (uint32_t)i), m);
+		}
+		__syncwarp();
 	}
 	else
 #endif
+	{
+	// (CTA per ROI / host emulation) every cell starts hooked to the head of its horizontal same-level run, then one union per
+	// vertically adjacent pair of RUNS, then every cell's distance goes to its root
 	for (int i = c.tid; i < ncell; i += c.nthr)
 	{
 		const uint32_t lv = cell[i] & CELL_LEVEL;
@@ -576,6 +617,7 @@ NYX_D void gldzm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	}
 	c.sync();
 
+	}
 	// ---- warp per ROI: the roots compacted into a list, in place over the parent array (dead from here on; see glszm_reduce)
 	int nroot = -1;
 #if NYX_DEVICE_BUILD
