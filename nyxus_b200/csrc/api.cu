@@ -796,7 +796,7 @@ size_t family_words (int fam, bool p16, int Lmax, uint32_t maxcells, int maxwh, 
 	case FAM_GLCM: return p16 ? glcm_smem_words<true> (Lmax, 4, rad, maxcells) : glcm_smem_words<false> (Lmax, 4, rad, maxcells);
 	case FAM_GLRLM: return glrlm_smem_words (Lmax, maxwh, (int)maxcells);
 	case FAM_GLDZM: return gldzm_smem_words (Lmax, gldzm_nd_bound (maxcells, maxwh), maxcells);
-	case FAM_GLSZM: return glszm_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells));
+	case FAM_GLSZM: return glszm_smem_words (maxcells, glszm_hash_slots (Lmax, maxcells), Lmax <= GLSZM_LMARG_MAX ? Lmax : 0);
 	case FAM_GLDM: return gldm_smem_words (Lmax, maxcells);
 	case FAM_NGLDM: return ngldm_smem_words (Lmax, maxcells);
 	case FAM_NGTDM: return ngtdm_smem_words (Lmax);

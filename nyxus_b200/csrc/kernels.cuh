@@ -922,7 +922,7 @@ __device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, c
 	else if (FAM == FAM_GLSZM)
 	{
 		ZoneDebug d { dbg.u32, dbg.nkeys };
-		glszm_body (c, r, prm, cell, mem, maxcells, aux, o + COL_GLSZM, dbg.u32 ? &d : nullptr);
+		glszm_body (c, r, prm, cell, mem, maxcells, aux, o + COL_GLSZM, dbg.u32 ? &d : nullptr, Lmax <= GLSZM_LMARG_MAX ? Lmax : 0);
 	}
 	else if (FAM == FAM_GLDM)
 	{

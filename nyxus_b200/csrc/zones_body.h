@@ -180,16 +180,24 @@ struct ZoneDebug
 // GLSZM
 // ------------------------------------------------------------------------------------------------
 // region: hash keys[slots] + 16-bit cnts[slots] (zero on entry/exit) + lab (u16 per cell) + zone sizes (u16 per cell)
-NYX_HD size_t glszm_smem_words (uint32_t maxcells, uint32_t slots)
+// Lmarg > 0 (2D, at most GLSZM_LMARG_MAX levels): + DIRECT 16-bit arrays for the two marginals -- zones per level [Lmarg + 1]
+// and zones per size for sizes below GLSZM_DIRECT_SIZES -- right behind the table (zero on entry / exit like it).  Four of
+// the six table operations per zone were marginal keys; larger sizes (few zones) still go through the table.
+constexpr int GLSZM_LMARG_MAX = 255, GLSZM_DIRECT_SIZES = 64;
+NYX_HD size_t glszm_marg_words (int Lmarg)
 {
-	return (size_t)slots + slots / 2 + 2 * (((size_t)maxcells + 1) / 2);
+	return Lmarg > 0 ? ((size_t)(Lmarg + 1) + GLSZM_DIRECT_SIZES + 1) / 2 : 0;
+}
+NYX_HD size_t glszm_smem_words (uint32_t maxcells, uint32_t slots, int Lmarg = 0)
+{
+	return (size_t)slots + slots / 2 + glszm_marg_words (Lmarg) + 2 * (((size_t)maxcells + 1) / 2);
 }
 
 NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, uint32_t* keys, uint32_t* cnts, uint32_t mask,
-	uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg);
+	uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg, int Lmarg = 0);
 
 NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const uint32_t* cell, uint32_t* mem, uint32_t maxcells,
-	uint32_t slots, double* out, const ZoneDebug* dbg)
+	uint32_t slots, double* out, const ZoneDebug* dbg, int Lmarg = 0)
 {
 	const int w = r.w, h = r.h, ncell = w * h;
 	if (r.imin == r.imax)
@@ -200,8 +208,9 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 	}
 	uint32_t* keys = mem;						// [slots]
 	uint32_t* cnts = keys + slots;					// [slots]
-	uint16_t* lab = (uint16_t*)(cnts + slots / 2);			// [ncell] zone label = raster index of the seed
-	uint32_t* zsw = cnts + slots / 2 + ((size_t)maxcells + 1) / 2;	// [ncell] zone size at the seed index, packed u16 pairs
+	const size_t mw = glszm_marg_words (Lmarg);			// direct marginal arrays behind the table (see glszm_smem_words)
+	uint16_t* lab = (uint16_t*)(cnts + slots / 2 + mw);		// [ncell] zone label = raster index of the seed
+	uint32_t* zsw = cnts + slots / 2 + mw + ((size_t)maxcells + 1) / 2;	// [ncell] zone size at the seed index, packed u16 pairs
 	const uint16_t* zs = (const uint16_t*)zsw;
 	const uint32_t mask = slots - 1;
 
@@ -296,16 +305,18 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 		}
 	}
 	c.sync();
-	glszm_reduce (c, prm, cell, keys, cnts, mask, lab, zsw, ncell, 0u, -1.0, out, dbg);
+	glszm_reduce (c, prm, cell, keys, cnts, mask, lab, zsw, ncell, 0u, -1.0, out, dbg, Lmarg);
 }
 
 // Common tail of 2D and 3D GLSZM.  lab[i] = zone id (cell index of the zone's representative) of every cell whose level is
 // not `skip`; zsw: zeroed packed u16 size counters.  np_fixed >= 0 overrides Np (3D: the voxel-cloud size, 3d_glszm.cpp:534).
 NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, uint32_t* keys, uint32_t* cnts, uint32_t mask,
-	uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg)
+	uint16_t* lab, uint32_t* zsw, int ncell, uint32_t skip, double np_fixed, double* out, const ZoneDebug* dbg, int Lmarg)
 {
 	const uint16_t* zs = (const uint16_t*)zsw;
 	const uint32_t slots = mask + 1;
+	uint32_t* margw = Lmarg > 0 ? cnts + slots / 2 : nullptr;	// zones per level [Lmarg + 1], then zones per size < GLSZM_DIRECT_SIZES (u16 each)
+	const uint32_t sz0 = (uint32_t)Lmarg + 1;			// index of size 0 in the packed array
 	// ---- zone sizes (packed 16-bit counters: a size is at most the cell count < 65536), Np
 	unsigned long long np[1] = { 0 };
 	for (int i = c.tid; i < ncell; i += c.nthr)
@@ -360,8 +371,19 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 			continue;
 		const uint32_t sz = zs[i];
 		htab_add (c, keys, cnts, mask, (lv << 16) | sz);
-		htab_add (c, keys, cnts, mask, lv << 16);
-		htab_add (c, keys, cnts, mask, sz);
+		if (margw)
+		{
+			atom_add (c, margw + (lv >> 1), 1u << ((lv & 1u) * 16u));
+			if (sz < (uint32_t)GLSZM_DIRECT_SIZES)
+				atom_add (c, margw + ((sz0 + sz) >> 1), 1u << (((sz0 + sz) & 1u) * 16u));
+			else
+				htab_add (c, keys, cnts, mask, sz);
+		}
+		else
+		{
+			htab_add (c, keys, cnts, mask, lv << 16);
+			htab_add (c, keys, cnts, mask, sz);
+		}
 		if (dbg && dbg->keys)
 			dbg->keys[atom_inc_ret (c, dbg->nkeys)] = (lv << 16) | sz;
 		q[Q_NZ] += 1;
@@ -395,8 +417,17 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 		if (nseed < 0 && (lv == skip || lab[i] != (uint32_t)i))
 			continue;
 		const uint32_t sz = zs[i];
-		q2[0] += htab_get (keys, cnts, mask, lv << 16);
-		q2[1] += htab_get (keys, cnts, mask, sz);
+		if (margw)
+		{
+			const uint16_t* m16 = (const uint16_t*)margw;
+			q2[0] += m16[lv];
+			q2[1] += sz < (uint32_t)GLSZM_DIRECT_SIZES ? (uint32_t)m16[sz0 + sz] : htab_get (keys, cnts, mask, sz);
+		}
+		else
+		{
+			q2[0] += htab_get (keys, cnts, mask, lv << 16);
+			q2[1] += htab_get (keys, cnts, mask, sz);
+		}
 		const double di = (double)lv - mui, dj = (double)sz - muj;
 		t[0] += di * di;									// :518-526
 		t[1] += dj * dj;									// :535-542
@@ -406,7 +437,7 @@ NYX_D void glszm_reduce (const Cta& c, const Params& prm, const uint32_t* cell, 
 	cta_sum_u64<2> (c, q2);
 	cta_sum<3> (c, t);
 	c.sync();
-	for (uint32_t i = c.tid; i < slots + slots / 2; i += c.nthr)	// restore the all-zero table (keys + packed counts)
+	for (uint32_t i = c.tid; i < slots + slots / 2 + (uint32_t)glszm_marg_words (Lmarg); i += c.nthr)	// restore the all-zero table (keys + packed counts + direct marginals)
 		keys[i] = 0;
 	c.sync();
 	if (c.tid == 0)

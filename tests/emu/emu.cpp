@@ -120,8 +120,9 @@ extern "C" int nyxemu_roi_features (const uint32_t* tile, const uint8_t* mask, i
 	if (fam_mask & 16)
 	{
 		const uint32_t slots = glszm_hash_slots (Lmax, (uint32_t)ncell);
-		std::vector<uint32_t> mem (glszm_smem_words ((uint32_t)ncell, slots));
-		glszm_body (c, r, prm, cell.data(), mem.data(), (uint32_t)ncell, slots, out + COL_GLSZM, nullptr);
+		const int Lmarg = Lmax <= GLSZM_LMARG_MAX ? Lmax : 0;	// direct marginal arrays like the kernels
+		std::vector<uint32_t> mem (glszm_smem_words ((uint32_t)ncell, slots, Lmarg));
+		glszm_body (c, r, prm, cell.data(), mem.data(), (uint32_t)ncell, slots, out + COL_GLSZM, nullptr, Lmarg);
 	}
 	if (fam_mask & 32)
 	{
