@@ -2346,8 +2346,7 @@ int featurize_slides (nyxb200_ctx* ctx, const void* const* inten, int inten_u16,
 		}
 		collect_timings (ctx);
 		if (!ctx->share)
-			for (int64_t i = 0; i < nr; i++)
-				ctx->row_image.push_back (k);
+			ctx->row_image.insert (ctx->row_image.end(), (size_t)nr, k);	// (one fill: the device is idle between two slides of a job)
 	}
 	if (out)
 	{
