@@ -219,7 +219,54 @@ NYX_D void glszm_body (const Cta& c, const RoiRec& r, const Params& prm, const u
 
 	// ---- forward-reachability labels, row by row
 #if NYX_DEVICE_BUILD
-	if (c.wmode)
+	if (c.wmode && w <= 32)
+	{
+		// tiles at most 32 cells wide (nearly all of them): a lane owns a COLUMN.  The levels / labels of the previous row stay
+		// in registers, so the {NW, N, NE} candidates are shuffles, not dependent shared-memory loads; the segmented min-scan
+		// along the row's same-level runs stops as soon as no run is longer than the distance already covered
+		const int lane = c.tid;
+		const bool inx = lane < w;
+		uint32_t plv = 0, plab = 0;
+		for (int y = 0; y < h; y++)
+		{
+			const int i = y * w + lane;
+			uint32_t lv = 0, m = 0xFFFFu;
+			if (inx)
+			{
+				lv = cell[i] & CELL_LEVEL;
+				m = (uint32_t)i;
+			}
+			const uint32_t nw_lv = __shfl_up_sync (0xffffffffu, plv, 1), nw_lab = __shfl_up_sync (0xffffffffu, plab, 1);
+			const uint32_t ne_lv = __shfl_down_sync (0xffffffffu, plv, 1), ne_lab = __shfl_down_sync (0xffffffffu, plab, 1);
+			if (lv && y > 0)
+			{
+				if (lane > 0 && nw_lv == lv) m = min (m, nw_lab);
+				if (plv == lv) m = min (m, plab);
+				if (lane + 1 < w && ne_lv == lv) m = min (m, ne_lab);
+			}
+			const uint32_t left_lv = __shfl_up_sync (0xffffffffu, lv, 1);
+			const bool head = !lv || lane == 0 || left_lv != lv;
+			const unsigned heads = __ballot_sync (0xffffffffu, head);
+			const int start = 31 - __clz (heads & (0xFFFFFFFFu >> (31 - lane)));	// lane of the head of my run (bit 0 is always set)
+			unsigned pos = ~heads;		// lanes at distance >= o from their run head (o = 1 here)
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1)
+			{
+				if (!pos)
+					break;
+				const uint32_t t = __shfl_up_sync (0xffffffffu, m, o);
+				if (lane - o >= start)
+					m = min (m, t);
+				pos &= pos << o;
+			}
+			if (inx)
+				lab[i] = (uint16_t)m;
+			plv = lv;
+			plab = m;
+		}
+		__syncwarp();
+	}
+	else if (c.wmode)
 	{
 		const int lane = c.tid;
 		for (int y = 0; y < h; y++)
