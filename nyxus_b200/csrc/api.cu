@@ -902,7 +902,7 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 	auto kern = gs ? k_roi_intensity<true> : k_roi_intensity<false>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
-	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
+	kern<<<grid, smem_words * 4 > ROI_BIG_SMEM_BYTES || gs ? ROI_THREADS_BIG : ROI_THREADS, smem_words * 4, ctx->ls>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
 		ostride, gs, memw);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
@@ -940,7 +940,7 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 	auto kern = gs ? k_roi_family3<FAM3, P16, true> : k_roi_family3<FAM3, P16, false>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
-	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,
+	kern<<<grid, smem_words * 4 > ROI_BIG_SMEM_BYTES ? ROI_THREADS_BIG : ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,
 		NCOL3_ALL, gs, famw);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;

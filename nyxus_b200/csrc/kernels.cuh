@@ -877,6 +877,10 @@ struct DebugOut
 
 constexpr int ROI_THREADS = 128;
 constexpr int ROI_WARPS = ROI_THREADS / 32;
+// CTA-per-ROI kernels whose shared-memory footprint leaves room for at most three CTAs on an SM (3D cubes, large first-order
+// clouds) run with twice the threads: the same shared memory then feeds 8 instead of 4 warps (NW_MAX)
+constexpr int ROI_THREADS_BIG = 256;
+constexpr size_t ROI_BIG_SMEM_BYTES = 56 * 1024;
 
 // per-LAUNCH constant of a family that is a function of the class bounds only (GLSZM: hash slots -- a loop with 64-bit
 // divisions; GLDZM: distance bound): computed once per thread at kernel start, not once per ROI (it was 7 % of the
@@ -1099,7 +1103,7 @@ __device__ __forceinline__ void family3_dispatch (const Cta& c, const RoiRec& r,
 }
 
 template <int FAM3, bool P16, bool GSCR>
-__global__ void __launch_bounds__(ROI_THREADS) k_roi_family3 (ImageView im, const RoiRec* __restrict__ rois,
+__global__ void __launch_bounds__(ROI_THREADS_BIG) k_roi_family3 (ImageView im, const RoiRec* __restrict__ rois,
 	const uint32_t* __restrict__ list, uint32_t n, Params prm, int greyinfo, int Lmax, uint32_t maxcells,
 	double* out, int out_stride, uint32_t* gscratch, size_t gwords)
 {
@@ -1160,7 +1164,7 @@ __global__ void __launch_bounds__(ROI_THREADS) k_roi_family3_big (ImageView im, 
 
 // first-order: reads the ROI's CSR slice
 template <bool GSCR>
-__global__ void __launch_bounds__(ROI_THREADS) k_roi_intensity (const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
+__global__ void __launch_bounds__(ROI_THREADS_BIG) k_roi_intensity (const RoiRec* __restrict__ rois, const uint32_t* __restrict__ list,
 	uint32_t n, Params prm, const uint32_t* __restrict__ cloud, uint32_t npad_max, double* out, int out_stride,
 	uint32_t* gscratch, size_t gwords)
 {
