@@ -447,6 +447,40 @@ def NyxusError_or_ValueError():
     return (NyxusB200Error, ValueError)
 
 
+# ------------------------------------------------------------------------------------------------ the mid-size tile classes
+@pytest.mark.skipif(not ref.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("ibsi", [False, True])
+def test_mid_size_rois_against_compiled_reference(ibsi):
+    """ROIs of 1 600 ... 39 800 bounding-box cells: the CTA-per-ROI forms of every family (tiles wider than a warp: GLRLM's
+    wrapped diagonals over many 32-cell steps, GLSZM rows in several chunks, GLDZM / neighbourhood kernels with block-wide
+    reductions, matrices in global scratch where they exceed shared memory), next to small ROIs of the warp-per-ROI forms"""
+    rng = np.random.default_rng(2024)
+    H, W = 460, 520
+    yy, xx = np.mgrid[0:H, 0:W]
+    I = (3000 + 2000 * np.sin(xx / 23.0) * np.cos(yy / 31.0) + rng.normal(0, 500, (H, W))).clip(1, 60000).astype(np.uint32)
+    L = np.zeros((H, W), np.uint32)
+    boxes = [(5, 5, 40, 40), (5, 60, 64, 70), (5, 150, 120, 130), (140, 5, 199, 200), (140, 220, 33, 290), (200, 220, 250, 35),
+             (5, 300, 20, 21), (30, 300, 9, 31)]
+    for k, (y0, x0, h, w) in enumerate(boxes):
+        cy, cx = y0 + h / 2.0, x0 + w / 2.0
+        m = ((yy - cy) / (h / 2.0)) ** 2 + ((xx - cx) / (w / 2.0)) ** 2 <= 1.0 if k % 2 == 0 else \
+            (yy >= y0) & (yy < y0 + h) & (xx >= x0) & (xx < x0 + w)
+        L[m & (L == 0)] = 7 + 5 * k
+    L[200:215, 60:90] = 0                     # a hole in the largest ROI
+    I[rng.random((H, W)) < 0.01] = 0
+    if ibsi:
+        I = (I >> 8).astype(np.uint32)        # IBSI mode indexes the matrices by raw intensity
+    e = _engine(ibsi=ibsi)
+    try:
+        tab, _ = e.featurize(I, L)
+    finally:
+        e.close()
+    rl, rt, _ = ref.featurize_2d(I, L, ibsi=ibsi, nthreads=8)
+    assert np.array_equal(tab[:, 0].astype(np.int64), rl.astype(np.int64))
+    bad = tu.mismatches(rt, tab[:, 2:], COLS)
+    assert not bad, bad[:8]
+
+
 # ------------------------------------------------------------------------------------------------ large ROIs (giant.cuh)
 _GIANT = tu.giant_cases()
 
