@@ -215,6 +215,7 @@ struct nyxb200_ctx
 	bool ev_end_used[NB_MAX * NEV];
 	int cur_b = 0;			// batch whose event set stage_begin / stage_end record into
 	int roi_batches = 0;		// 0 = automatic
+	int big_cta_threads = 1;	// measurement knob: 0 = the CTA-per-ROI kernels always run 128 threads
 	cudaStream_t copy_stream = nullptr;	// D2H of a finished batch's rows
 	cudaEvent_t ev_sel;
 	// host slides travel on their own stream into two alternating device buffers: slide k+1 is uploaded while slide k computes
@@ -704,6 +705,8 @@ int nyxb200_set_param (nyxb200_ctx* ctx, const char* key, double value)
 		ctx->st.soft_nan = value;
 	else if (!strcmp (key, "concurrent_families"))	// measurement knob: 0 = one family after the other (clean per-stage times)
 		ctx->concurrent = iv != 0;
+	else if (!strcmp (key, "big_cta_threads"))
+		ctx->big_cta_threads = iv != 0;
 	else if (!strcmp (key, "roi_batches"))			// 0 = automatic, else 1..NB_MAX
 	{
 		if (iv < 0 || iv > NB_MAX)
@@ -844,7 +847,9 @@ int launch_family_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* list
 	auto kern = gs ? k_roi_family<FAM, P16, true> : k_roi_family<FAM, P16, false>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
-	kern<<<grid, ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out,
+	// single-matrix families on tiles that leave room for at most three CTAs per SM: twice the threads on the same shared memory
+	const int threads = ctx->big_cta_threads && FAM != FAM_GLCM && FAM != FAM_GLRLM && smem_words * 4 > ROI_BIG_SMEM_BYTES ? ROI_THREADS_BIG : ROI_THREADS;
+	kern<<<grid, threads, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, Lmax, maxcells, maxwh, out,
 		ctx->row_stride, gs, famw, dbg);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
@@ -902,7 +907,7 @@ int launch_intensity (nyxb200_ctx* ctx, const uint32_t* list, uint32_t n, const 
 	auto kern = gs ? k_roi_intensity<true> : k_roi_intensity<false>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
-	kern<<<grid, smem_words * 4 > ROI_BIG_SMEM_BYTES || gs ? ROI_THREADS_BIG : ROI_THREADS, smem_words * 4, ctx->ls>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
+	kern<<<grid, ctx->big_cta_threads && (smem_words * 4 > ROI_BIG_SMEM_BYTES || gs) ? ROI_THREADS_BIG : ROI_THREADS, smem_words * 4, ctx->ls>>> (ctx->d_rois.p, list, n, prm, ctx->d_cloud.p, npad, out,
 		ostride, gs, memw);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;
@@ -940,7 +945,7 @@ int launch_family3_t (nyxb200_ctx* ctx, const ImageView& im, const uint32_t* lis
 	auto kern = gs ? k_roi_family3<FAM3, P16, true> : k_roi_family3<FAM3, P16, false>;
 	if (set_smem (ctx, kern, smem_words * 4))
 		return NYXB200_ECUDA;
-	kern<<<grid, smem_words * 4 > ROI_BIG_SMEM_BYTES ? ROI_THREADS_BIG : ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,
+	kern<<<grid, ctx->big_cta_threads && smem_words * 4 > ROI_BIG_SMEM_BYTES ? ROI_THREADS_BIG : ROI_THREADS, smem_words * 4, ctx->ls>>> (im, ctx->d_rois.p, list, n, prm, greyinfo, Lmax, maxcells, out,
 		NCOL3_ALL, gs, famw);
 	CU (cudaGetLastError());
 	ctx->counts[0]++;

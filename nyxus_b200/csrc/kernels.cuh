@@ -951,7 +951,7 @@ __device__ __forceinline__ void run_family (const Cta& c, const ImageView& im, c
 // template parameter, not a run-time select, so that in the common case the compiler sees a pure shared-memory pointer
 // and emits LDS / STS / ATOMS with 32-bit addressing instead of generic LD / ATOM with 64-bit address arithmetic.
 template <int FAM, bool P16, bool GSCR>
-__global__ void __launch_bounds__(ROI_THREADS, FAM == FAM_GLCM ? 4 : FAM == FAM_GLRLM ? 6 : 1) k_roi_family (ImageView im, const RoiRec* __restrict__ rois,
+__global__ void __launch_bounds__((FAM == FAM_GLCM || FAM == FAM_GLRLM) ? ROI_THREADS : ROI_THREADS_BIG, FAM == FAM_GLCM ? 4 : FAM == FAM_GLRLM ? 6 : 1) k_roi_family (ImageView im, const RoiRec* __restrict__ rois,
 	const uint32_t* __restrict__ list, uint32_t n, Params prm, int Lmax, uint32_t maxcells, int maxwh,
 	double* out, int out_stride, uint32_t* gscratch, size_t gwords, DebugOut dbg)
 {
